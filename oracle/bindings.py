@@ -1,0 +1,98 @@
+"""
+oracle/bindings.py -- TEST INFRASTRUCTURE ONLY (ctypes access to oracle/_ref/*.so).
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs import this.
+  * liboracle.so        : C restatements (hevc_oracle.c, color_oracle.c) + FFmpeg wrapper (ffhevc.c)
+  * libheif_ref.so      : the UNMODIFIED reference libheif core, compiled from /root/reference by oracle/Makefile
+  * liboracle_plugin.so : CPU decoder plugin (FFmpeg or restatement) registered into libheif_ref.so
+"""
+import ctypes as C
+import glob
+import os
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+REF = os.path.join(HERE, "_ref")
+
+
+def avcodec_dir():
+    """Directory of the FFmpeg libraries bundled in the opencv-python-headless wheel (no import of cv2 needed)."""
+    import importlib.util
+    spec = importlib.util.find_spec("cv2")
+    if spec is None:
+        return None
+    site = os.path.dirname(os.path.dirname(spec.origin))
+    d = os.path.join(site, "opencv_python_headless.libs")
+    return d if glob.glob(os.path.join(d, "libavcodec-*")) else None
+
+
+class _FFPic(C.Structure):
+    _fields_ = [("width", C.c_int), ("height", C.c_int), ("cw", C.c_int), ("ch", C.c_int), ("bit_depth", C.c_int),
+                ("chroma", C.c_int), ("full_range_name", C.c_int), ("plane", C.POINTER(C.c_uint16) * 3)]
+
+
+class _HOPic(C.Structure):
+    _fields_ = [("width", C.c_int), ("height", C.c_int), ("cw", C.c_int), ("ch", C.c_int), ("bit_depth", C.c_int),
+                ("chroma_format", C.c_int), ("vui_colour_present", C.c_int), ("colour_primaries", C.c_int),
+                ("transfer_characteristics", C.c_int), ("matrix_coeffs", C.c_int), ("full_range", C.c_int),
+                ("video_signal_present", C.c_int), ("plane", C.POINTER(C.c_uint16) * 3)]
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        path = os.path.join(REF, "liboracle.so")
+        if not os.path.exists(path):
+            raise RuntimeError("oracle/_ref/liboracle.so missing: run `make -C oracle` (or __graft_entry__.build())")
+        _lib = C.CDLL(path, mode=C.RTLD_GLOBAL)
+        _lib.ffhevc_init.argtypes = [C.c_char_p]
+        _lib.ffhevc_decode.argtypes = [C.c_char_p, C.c_size_t, C.c_int, C.POINTER(_FFPic)]
+        _lib.hevc_oracle_decode.argtypes = [C.c_char_p, C.c_size_t, C.c_int, C.POINTER(_HOPic)]
+    return _lib
+
+
+def _planes(pic, chroma):
+    out = []
+    for c in range(3 if chroma else 1):
+        w, h = (pic.cw, pic.ch) if c else (pic.width, pic.height)
+        a = np.ctypeslib.as_array(pic.plane[c], shape=(h, w)).copy()
+        out.append(a)
+    return out
+
+
+_ff_ready = False
+
+
+def ffmpeg_decode(au: bytes, threads: int = 1):
+    """Decode one length-prefixed HEVC access unit with FFmpeg. Returns (planes[list of uint16 HxW], bit_depth, chroma)."""
+    global _ff_ready
+    l = lib()
+    if not _ff_ready:
+        d = avcodec_dir()
+        if d is None or l.ffhevc_init(d.encode()) != 0:
+            raise RuntimeError("FFmpeg (cv2 wheel) not available")
+        _ff_ready = True
+    pic = _FFPic()
+    rc = l.ffhevc_decode(au, len(au), threads, C.byref(pic))
+    if rc != 0:
+        raise RuntimeError(f"ffhevc_decode rc={rc}")
+    pl = _planes(pic, pic.chroma)
+    l.ffhevc_free_picture(C.byref(pic))
+    return pl, pic.bit_depth, pic.chroma
+
+
+def restatement_decode(au: bytes, stage: int = 0):
+    """Decode with the C restatement. stage 0 final, 1 before deblocking, 2 after deblocking before SAO."""
+    l = lib()
+    pic = _HOPic()
+    rc = l.hevc_oracle_decode(au, len(au), stage, C.byref(pic))
+    if rc != 0:
+        raise RuntimeError(f"hevc_oracle_decode rc={rc}")
+    pl = _planes(pic, pic.chroma_format)
+    info = dict(bit_depth=pic.bit_depth, chroma=pic.chroma_format, cp=pic.colour_primaries,
+                tc=pic.transfer_characteristics, mc=pic.matrix_coeffs, full_range=pic.full_range)
+    l.hevc_oracle_free_picture(C.byref(pic))
+    return pl, info

@@ -1,0 +1,118 @@
+/*
+ * oracle/ref_plugin.cc -- TEST INFRASTRUCTURE ONLY. Never linked, imported or executed by the product.
+ *
+ * CPU reference decoder plugin for the reference libheif built by oracle/Makefile
+ * (oracle/_ref/libheif_ref.so): the libde265 role (libheif/plugins/decoder_libde265.cc) filled by
+ * FFmpeg (oracle/ffhevc.c) -- or, selectable, by the C restatement (oracle/hevc_oracle.c) -- so that
+ * heif_decode_image() of the UNMODIFIED reference runs end to end on this machine.  Member order of the
+ * plugin table follows decoder_libde265.cc:497-517; plane hand-over follows :97-171; nclx from VUI :426-448.
+ *
+ * Env: B200_ORACLE_BACKEND=ffmpeg|restatement (default ffmpeg), B200_ORACLE_DUMP_DIR=<dir> dumps every
+ * pushed access unit (used once to harvest the HEVC streams of the reference's fixtures).
+ */
+#include <libheif/heif.h>
+#include <libheif/heif_plugin.h>
+#include <atomic>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+extern "C" {
+typedef struct { int width, height, cw, ch, bit_depth, chroma, full_range_name; uint16_t* plane[3]; } ffhevc_picture;
+int ffhevc_init(const char* dir);
+int ffhevc_decode(const uint8_t* data, size_t size, int threads, ffhevc_picture* out);
+void ffhevc_free_picture(ffhevc_picture* p);
+typedef struct { int width, height, cw, ch, bit_depth, chroma_format, vui_colour_present, colour_primaries,
+  transfer_characteristics, matrix_coeffs, full_range, video_signal_present; uint16_t* plane[3]; } hevc_oracle_picture;
+int hevc_oracle_decode(const uint8_t* data, size_t size, int stage, hevc_oracle_picture* out);
+void hevc_oracle_free_picture(hevc_oracle_picture* p);
+int hevc_oracle_parse_vui(const uint8_t* data, size_t size, int out[4]);
+}
+
+namespace {
+struct Dec { std::vector<uint8_t> data; int strict = 0; int threads = 1; };
+std::atomic<int> g_dump_counter{0};
+const char kOk[] = "Success";
+
+heif_error ok() { return heif_error{heif_error_Ok, heif_suberror_Unspecified, kOk}; }
+heif_error fail(const char* m) { return heif_error{heif_error_Decoder_plugin_error, heif_suberror_Unspecified, m}; }
+
+const char* name() { return "b200 test oracle (FFmpeg libavcodec / C restatement)"; }
+void init() {} void deinit() {}
+int supports(heif_compression_format f) { return f == heif_compression_HEVC ? 500 : 0; }
+int supports2(const heif_decoder_plugin_compressed_format_description* d) { return supports(d->format); }
+heif_error new_dec2(void** out, const heif_decoder_plugin_options* o) {
+  Dec* d = new Dec; d->strict = o->strict_decoding; d->threads = o->num_threads > 0 ? o->num_threads : 1; *out = d; return ok();
+}
+heif_error new_dec(void** out) { heif_decoder_plugin_options o{}; o.format = heif_compression_HEVC; return new_dec2(out, &o); }
+void free_dec(void* p) { delete (Dec*)p; }
+heif_error push2(void* p, const void* data, size_t n, uintptr_t) { Dec* d = (Dec*)p; d->data.insert(d->data.end(), (const uint8_t*)data, (const uint8_t*)data + n); return ok(); }
+heif_error push(void* p, const void* data, size_t n) { return push2(p, data, n, 0); }
+heif_error flush(void*) { return ok(); }
+void set_strict(void* p, int f) { ((Dec*)p)->strict = f; }
+
+heif_error decode2(void* p, heif_image** out, uintptr_t* ud, const heif_security_limits* limits) {
+  Dec* d = (Dec*)p;
+  *out = nullptr;
+  if (ud) *ud = 0;
+  if (d->data.empty()) return ok();
+  if (const char* dir = getenv("B200_ORACLE_DUMP_DIR")) {
+    char path[4096]; snprintf(path, sizeof path, "%s/au_%04d.bin", dir, g_dump_counter++);
+    if (FILE* f = fopen(path, "wb")) { fwrite(d->data.data(), 1, d->data.size(), f); fclose(f); }
+  }
+  const char* be = getenv("B200_ORACLE_BACKEND");
+  int w, h, cw, ch, bd, chroma; uint16_t* planes[3];
+  ffhevc_picture fp{}; hevc_oracle_picture op{};
+  bool restate = be && strcmp(be, "restatement") == 0;
+  if (restate) {
+    if (hevc_oracle_decode(d->data.data(), d->data.size(), 0, &op) != 0) { d->data.clear(); return fail("hevc_oracle_decode failed"); }
+    w = op.width; h = op.height; cw = op.cw; ch = op.ch; bd = op.bit_depth; chroma = op.chroma_format;
+    for (int i = 0; i < 3; i++) planes[i] = op.plane[i];
+  } else {
+    if (ffhevc_decode(d->data.data(), d->data.size(), d->threads, &fp) != 0) { d->data.clear(); return fail("ffhevc_decode failed"); }
+    w = fp.width; h = fp.height; cw = fp.cw; ch = fp.ch; bd = fp.bit_depth; chroma = fp.chroma;
+    for (int i = 0; i < 3; i++) planes[i] = fp.plane[i];
+  }
+  int vui[4]; hevc_oracle_parse_vui(d->data.data(), d->data.size(), vui);
+  d->data.clear();
+  heif_image* img = nullptr;
+  heif_error err = heif_image_create(w, h, chroma == 0 ? heif_colorspace_monochrome : heif_colorspace_YCbCr, (heif_chroma)chroma, &img);
+  if (err.code) return err;
+  const heif_channel chans[3] = {heif_channel_Y, heif_channel_Cb, heif_channel_Cr};
+  for (int c = 0; c < (chroma ? 3 : 1) && !err.code; c++) {
+    int pw = c ? cw : w, ph = c ? ch : h;
+    err = heif_image_add_plane_safe(img, chans[c], pw, ph, bd, limits);
+    if (err.code) break;
+    size_t stride; uint8_t* dst = heif_image_get_plane2(img, chans[c], &stride);
+    for (int y = 0; y < ph; y++) {
+      const uint16_t* src = planes[c] + (size_t)y * pw;
+      if (bd == 8) for (int x = 0; x < pw; x++) dst[y * stride + x] = (uint8_t)src[x];
+      else memcpy(dst + y * stride, src, (size_t)pw * 2);
+    }
+  }
+  if (restate) hevc_oracle_free_picture(&op); else ffhevc_free_picture(&fp);
+  if (err.code) { heif_image_release(img); return err; }
+  heif_color_profile_nclx* nclx = heif_nclx_color_profile_alloc();
+  heif_nclx_color_profile_set_color_primaries(nclx, (uint16_t)vui[0]);
+  heif_nclx_color_profile_set_transfer_characteristics(nclx, (uint16_t)vui[1]);
+  heif_nclx_color_profile_set_matrix_coefficients(nclx, (uint16_t)vui[2]);
+  nclx->full_range_flag = (uint8_t)vui[3];
+  heif_image_set_nclx_color_profile(img, nclx);
+  heif_nclx_color_profile_free(nclx);
+  *out = img;
+  return ok();
+}
+heif_error decode_next(void* p, heif_image** out, const heif_security_limits* l) { return decode2(p, out, nullptr, l); }
+heif_error decode_img(void* p, heif_image** out) { return decode2(p, out, nullptr, nullptr); }
+
+const heif_decoder_plugin g_plugin = {5, name, init, deinit, supports, new_dec, free_dec, push, decode_img, set_strict,
+                                      "b200-oracle", decode_next, LIBHEIF_MAKE_VERSION(1, 21, 0), supports2, new_dec2, push2, flush, decode2};
+}  // namespace
+
+extern "C" int b200_oracle_register(const char* avcodec_dir) {
+  if (avcodec_dir && ffhevc_init(avcodec_dir) != 0) return -1;
+  heif_error e = heif_register_decoder_plugin(&g_plugin);
+  return e.code;
+}
