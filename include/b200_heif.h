@@ -1,0 +1,103 @@
+/*
+ * b200_heif.h -- C ABI of libb200heif.so: the B200-native replacement for libheif's per-tile decode
+ * pixel pipeline (HEVC-intra decoder in the libde265 role + colour-conversion / rotate / mirror / crop /
+ * overlay post-stage).  Plain pointers and sizes only; no C++ or torch types.
+ *
+ * Every entry point cites the reference interface it replaces (paths relative to the libheif tree).
+ * Device pointers are ordinary CUDA device pointers of the current device; `stream` is a cudaStream_t
+ * passed as void* (NULL = default stream).  All functions return 0 on success or a negative B200_E_* code;
+ * b200_last_error() gives a thread-local message.  Nothing here falls back to a CPU path: without a
+ * CUDA device the device functions fail with B200_E_CUDA.
+ */
+#ifndef B200_HEIF_H
+#define B200_HEIF_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B200_OK 0
+#define B200_E_INVALID (-1)      /* bad argument */
+#define B200_E_UNSUPPORTED (-2)  /* valid input outside the supported tool set (maps to heif_error_Unsupported_feature) */
+#define B200_E_BITSTREAM (-3)    /* corrupt HEVC stream (maps to heif_error_Decoder_plugin_error) */
+#define B200_E_CUDA (-4)         /* CUDA runtime error / no device */
+#define B200_E_LIMIT (-5)        /* security limit exceeded (heif_security_limits.max_image_size_pixels) */
+
+const char* b200_last_error(void);
+int b200_version(void);
+
+/* ------------------------------------------------------------------------------------------------
+ * Colour post-stage (K6): chroma upsample + YCbCr->RGB + bit depth / interleave / endianness, fused with
+ * the geometric transforms, one pass over HBM.
+ * Replaces: convert_colorspace()                     libheif/color-conversion/colorconversion.cc:490-623
+ *           Op_YCbCr_to_RGB<T>                       libheif/color-conversion/yuv2rgb.cc:92-292
+ *           Op_YCbCr420_to_RGB24 / _RGB32            yuv2rgb.cc:345-426 / :481-562
+ *           Op_YCbCr420_to_RRGGBBaa                  yuv2rgb.cc:622-734
+ *           Op_RGB_to_RGB24_32, Op_to_sdr_planes     rgb2rgb.cc:71-150, hdr_sdr.cc:147-200
+ *           HeifPixelImage::rotate_ccw / mirror_inplace / crop   libheif/image/pixelimage.cc:1175-1546
+ * ------------------------------------------------------------------------------------------------ */
+
+/* heif_chroma values of the reference (api/libheif/heif_image.h) used for input and output layouts */
+enum b200_chroma {
+  B200_CHROMA_MONO = 0, B200_CHROMA_420 = 1, B200_CHROMA_422 = 2, B200_CHROMA_444 = 3,
+  B200_CHROMA_INTERLEAVED_RGB = 10, B200_CHROMA_INTERLEAVED_RGBA = 11,
+  B200_CHROMA_INTERLEAVED_RRGGBB_BE = 12, B200_CHROMA_INTERLEAVED_RRGGBBAA_BE = 13,
+  B200_CHROMA_INTERLEAVED_RRGGBB_LE = 14, B200_CHROMA_INTERLEAVED_RRGGBBAA_LE = 15
+};
+
+/* One YCbCr (or monochrome) picture in device or host memory.  Samples are uint8 when bit_depth == 8,
+   otherwise native-endian uint16 (reference plane layout, pixelimage.cc:389-501).  Strides in bytes. */
+typedef struct b200_planes {
+  const void* y; const void* cb; const void* cr; const void* alpha;   /* alpha may be NULL */
+  size_t y_stride, c_stride, alpha_stride;
+  int width, height;       /* luma size */
+  int chroma;              /* B200_CHROMA_MONO/420/422/444 */
+  int bit_depth;           /* 8..16 (alpha must have the same depth) */
+  /* CICP as carried by the image's nclx (nclx.h:121-173); 2 = unspecified */
+  int colour_primaries, transfer_characteristics, matrix_coefficients, full_range;
+} b200_planes;
+
+/* Geometry applied BEFORE colour conversion (image-items/image_item.cc:947-1020 applies irot / imir / clap
+   in ipma property order).  Any chain of those transforms is an affine map with coefficients in {-1,0,1}
+   from an output pixel (u,v) back to the decoded picture; the host composes the chain by calling the
+   b200_geometry_* functions in the same order libheif applies the properties. */
+typedef struct b200_geometry {
+  int m[6];          /* src_x = m[0]*u + m[1]*v + m[2] ;  src_y = m[3]*u + m[4]*v + m[5] */
+  int out_w, out_h;  /* size of the transformed picture */
+} b200_geometry;
+
+void b200_geometry_identity(int width, int height, b200_geometry* g);
+int b200_geometry_rotate_ccw(b200_geometry* g, int degrees /*0,90,180,270*/);   /* HeifPixelImage::rotate_ccw, pixelimage.cc:1175-1333 */
+int b200_geometry_mirror(b200_geometry* g, int direction /*heif_transform_mirror_direction: 0 = vertical (top<->bottom), 1 = horizontal (left<->right)*/); /* pixelimage.cc:1336-1424 */
+int b200_geometry_crop(b200_geometry* g, int left, int right, int top, int bottom); /* HeifPixelImage::crop, inclusive right/bottom, pixelimage.cc:1433-1546 */
+
+typedef struct b200_color_options {
+  int out_chroma;                 /* B200_CHROMA_INTERLEAVED_* or B200_CHROMA_444 (planar RGB) */
+  int out_bit_depth;              /* 0 = reference default (8 for RGB/RGBA, input depth for RRGGBB*, colorconversion.cc:591-605) */
+  int chroma_upsampling;          /* 0 = reference default planner choice (nearest neighbour), 1 = bilinear forced
+                                     (heif_color_conversion_options.only_use_preferred_chroma_algorithm) */
+} b200_color_options;
+
+/* Device -> device.  `out` points to out_h rows of out_stride bytes (planar RGB: out, out_g, out_b).
+   Reports which reference op chain was mirrored in *pipeline (bit mask B200_PIPE_*), may be NULL. */
+#define B200_PIPE_INT420 1       /* Op_YCbCr420_to_RGB24 / RGB32 integer arithmetic */
+#define B200_PIPE_FLOAT 2        /* Op_YCbCr_to_RGB<T> / Op_YCbCr420_to_RRGGBBaa float arithmetic */
+#define B200_PIPE_BILINEAR 4     /* Op_YCbCr420_bilinear_to_YCbCr444 first */
+#define B200_PIPE_SDR_SHIFT 8    /* Op_to_sdr_planes (>> (bpp-8)) */
+int b200_color_convert_device(const b200_planes* in, const b200_geometry* geom, const b200_color_options* opt,
+                              void* out, void* out_g, void* out_b, size_t out_stride, void* stream, int* pipeline);
+
+/* Host -> host convenience with H2D/D2H inside (what a libheif ColorConversionOperation would call). */
+int b200_color_convert_host(const b200_planes* in, const b200_geometry* geom, const b200_color_options* opt,
+                            void* out, void* out_g, void* out_b, size_t out_stride, int* pipeline);
+
+/* nclx helper: the 4 float coefficients exactly as nclx.cc:84-173 derives them */
+void b200_ycbcr_to_rgb_coefficients(int matrix_coefficients, int colour_primaries, float out_coeffs[4] /* r_cr,g_cb,g_cr,b_cb */);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,115 @@
+// b200_api.cu -- extern "C" surface of libb200heif.so (see include/b200_heif.h for the reference citations)
+#include "b200_internal.h"
+
+namespace b200 {
+static thread_local char g_err[512] = "";
+int set_error(int code, const char* fmt, ...) {
+  va_list ap; va_start(ap, fmt); vsnprintf(g_err, sizeof g_err, fmt, ap); va_end(ap);
+  return code;
+}
+}  // namespace b200
+
+using namespace b200;
+
+extern "C" {
+
+const char* b200_last_error(void) { return g_err; }
+int b200_version(void) { return 100; }
+
+void b200_ycbcr_to_rgb_coefficients(int mc, int cp, float out[4]) { ycbcr_to_rgb_coefficients(mc, cp, out); }
+
+void b200_geometry_identity(int w, int h, b200_geometry* g) {
+  g->m[0] = 1; g->m[1] = 0; g->m[2] = 0; g->m[3] = 0; g->m[4] = 1; g->m[5] = 0; g->out_w = w; g->out_h = h;
+}
+
+// new(u,v) -> old(u',v') = T(u,v), then old mapping applied: m' = m o T
+static void compose(b200_geometry* g, const int t[6], int nw, int nh) {
+  int n[6];
+  n[0] = g->m[0] * t[0] + g->m[1] * t[3]; n[1] = g->m[0] * t[1] + g->m[1] * t[4]; n[2] = g->m[0] * t[2] + g->m[1] * t[5] + g->m[2];
+  n[3] = g->m[3] * t[0] + g->m[4] * t[3]; n[4] = g->m[3] * t[1] + g->m[4] * t[4]; n[5] = g->m[3] * t[2] + g->m[4] * t[5] + g->m[5];
+  for (int i = 0; i < 6; i++) g->m[i] = n[i];
+  g->out_w = nw; g->out_h = nh;
+}
+
+int b200_geometry_rotate_ccw(b200_geometry* g, int degrees) {
+  const int w = g->out_w, h = g->out_h;
+  if (degrees == 0) return B200_OK;
+  if (degrees == 90) { const int t[6] = {0, -1, w - 1, 1, 0, 0}; compose(g, t, h, w); return B200_OK; }        // out[y][x] = in[x][w-1-y]
+  if (degrees == 180) { const int t[6] = {-1, 0, w - 1, 0, -1, h - 1}; compose(g, t, w, h); return B200_OK; }
+  if (degrees == 270) { const int t[6] = {0, 1, 0, -1, 0, h - 1}; compose(g, t, h, w); return B200_OK; }       // out[y][x] = in[h-1-x][y]
+  return set_error(B200_E_INVALID, "rotation %d", degrees);
+}
+
+int b200_geometry_mirror(b200_geometry* g, int direction) {
+  const int w = g->out_w, h = g->out_h;
+  if (direction == 1) { const int t[6] = {-1, 0, w - 1, 0, 1, 0}; compose(g, t, w, h); return B200_OK; }
+  if (direction == 0) { const int t[6] = {1, 0, 0, 0, -1, h - 1}; compose(g, t, w, h); return B200_OK; }
+  return set_error(B200_E_INVALID, "mirror direction %d", direction);
+}
+
+int b200_geometry_crop(b200_geometry* g, int left, int right, int top, int bottom) {
+  if (left < 0 || top < 0 || right >= g->out_w || bottom >= g->out_h || right < left || bottom < top)
+    return set_error(B200_E_INVALID, "crop window outside image");
+  const int t[6] = {1, 0, left, 0, 1, top};
+  compose(g, t, right - left + 1, bottom - top + 1);
+  return B200_OK;
+}
+
+int b200_color_convert_device(const b200_planes* in, const b200_geometry* geom, const b200_color_options* opt, void* out,
+                              void* out_g, void* out_b, size_t out_stride, void* stream, int* pipeline) {
+  return launch_color(in, geom, opt, out, out_g, out_b, out_stride, (cudaStream_t)stream, pipeline);
+}
+
+static size_t out_row_bytes(int fmt, int w, int bit_depth_in) {
+  switch (fmt) {
+    case B200_CHROMA_INTERLEAVED_RGB: return (size_t)w * 3;
+    case B200_CHROMA_INTERLEAVED_RGBA: return (size_t)w * 4;
+    case B200_CHROMA_INTERLEAVED_RRGGBB_BE: case B200_CHROMA_INTERLEAVED_RRGGBB_LE: return (size_t)w * 6;
+    case B200_CHROMA_INTERLEAVED_RRGGBBAA_BE: case B200_CHROMA_INTERLEAVED_RRGGBBAA_LE: return (size_t)w * 8;
+    default: return (size_t)w * (bit_depth_in > 8 ? 2 : 1);
+  }
+}
+
+int b200_color_convert_host(const b200_planes* in, const b200_geometry* geom, const b200_color_options* opt, void* out,
+                            void* out_g, void* out_b, size_t out_stride, int* pipeline) {
+  if (!in || !geom || !opt || !out) return set_error(B200_E_INVALID, "null argument");
+  const int bps = in->bit_depth > 8 ? 2 : 1;
+  const int sh = (in->chroma == B200_CHROMA_420 || in->chroma == B200_CHROMA_422) ? 1 : 0;
+  const int sv = in->chroma == B200_CHROMA_420 ? 1 : 0;
+  const int cw = in->chroma == B200_CHROMA_MONO ? 0 : (in->width + sh) >> sh, ch = in->chroma == B200_CHROMA_MONO ? 0 : (in->height + sv) >> sv;
+  const size_t ypitch = (((size_t)in->width * bps) + 255) & ~(size_t)255, cpitch = (((size_t)cw * bps) + 255) & ~(size_t)255;
+  const size_t rowb = out_row_bytes(opt->out_chroma, geom->out_w, in->bit_depth);
+  const size_t opitch = (rowb + 255) & ~(size_t)255;
+  const int nout = opt->out_chroma == B200_CHROMA_444 ? 3 : 1;
+  char *dy = nullptr, *dcb = nullptr, *dcr = nullptr, *da = nullptr, *dout = nullptr;
+  cudaStream_t s; B200_CUDA_CHECK(cudaStreamCreate(&s));
+  int rc = B200_OK;
+  auto fail = [&](cudaError_t e, const char* what) { if (e != cudaSuccess && rc == B200_OK) rc = set_error(B200_E_CUDA, "%s: %s", what, cudaGetErrorString(e)); };
+  fail(cudaMalloc(&dy, ypitch * in->height), "cudaMalloc");
+  if (cw) { fail(cudaMalloc(&dcb, cpitch * ch), "cudaMalloc"); fail(cudaMalloc(&dcr, cpitch * ch), "cudaMalloc"); }
+  if (in->alpha) fail(cudaMalloc(&da, ypitch * in->height), "cudaMalloc");
+  fail(cudaMalloc(&dout, opitch * geom->out_h * nout), "cudaMalloc");
+  if (rc == B200_OK) {
+    fail(cudaMemcpy2DAsync(dy, ypitch, in->y, in->y_stride, (size_t)in->width * bps, in->height, cudaMemcpyHostToDevice, s), "H2D");
+    if (cw) {
+      fail(cudaMemcpy2DAsync(dcb, cpitch, in->cb, in->c_stride, (size_t)cw * bps, ch, cudaMemcpyHostToDevice, s), "H2D");
+      fail(cudaMemcpy2DAsync(dcr, cpitch, in->cr, in->c_stride, (size_t)cw * bps, ch, cudaMemcpyHostToDevice, s), "H2D");
+    }
+    if (in->alpha) fail(cudaMemcpy2DAsync(da, ypitch, in->alpha, in->alpha_stride, (size_t)in->width * bps, in->height, cudaMemcpyHostToDevice, s), "H2D");
+  }
+  if (rc == B200_OK) {
+    b200_planes d = *in;
+    d.y = dy; d.cb = dcb; d.cr = dcr; d.alpha = da; d.y_stride = ypitch; d.c_stride = cpitch; d.alpha_stride = ypitch;
+    rc = launch_color(&d, geom, opt, dout, dout + opitch * geom->out_h, dout + 2 * opitch * geom->out_h, opitch, s, pipeline);
+  }
+  if (rc == B200_OK) {
+    void* outs[3] = {out, out_g, out_b};
+    for (int c = 0; c < nout; c++)
+      fail(cudaMemcpy2DAsync(outs[c], out_stride, dout + c * opitch * geom->out_h, opitch, rowb, geom->out_h, cudaMemcpyDeviceToHost, s), "D2H");
+    fail(cudaStreamSynchronize(s), "sync");
+  }
+  cudaFree(dy); cudaFree(dcb); cudaFree(dcr); cudaFree(da); cudaFree(dout); cudaStreamDestroy(s);
+  return rc;
+}
+
+}  // extern "C"

@@ -1,0 +1,316 @@
+// b200_color.cu -- K6: fused colour post-stage for sm_100a.
+//
+// One pass over HBM does what the reference does in 2-4 passes with calloc'ed intermediates
+// (libheif/color-conversion/colorconversion.cc:450-487 runs each op into a fresh image):
+//   geometric transform (rotate_ccw / mirror / crop, libheif/image/pixelimage.cc:1175-1546) by addressing,
+//   nearest-neighbour chroma upsampling (cx = x >> shiftH, cy = y >> shiftV, yuv2rgb.cc:226-229),
+//   YCbCr -> RGB in the reference's integer arithmetic (yuv2rgb.cc:386-424) or float arithmetic
+//   (yuv2rgb.cc:270-282, :696-709), optional ">> (bpp-8)" (hdr_sdr.cc:147-200), and the interleave /
+//   endianness step (rgb2rgb.cc:71-150, yuv2rgb.cc:715-729).
+//
+// Layout: every CTA owns a 64x64 output tile.  The corresponding source window (also 64x64 because all
+// transforms are axis permutations) is staged in shared memory with 16-byte loads, then each thread turns a
+// 16-pixel strip into RGB and writes it with 128-bit stores (48 B of RGB24 = 3 x uint4).
+// HBM-bound byte work: algorithmic traffic 4.5 B/px (8-bit -> RGB24), 9 B/px (16-bit -> RRGGBB).
+//
+// Bit-exactness: float expressions use __fmul_rn/__fadd_rn explicitly (no FMA contraction; the x86-64
+// reference build has no FMA), evaluation order is the reference's, rounding is (int32)(fx + 0.5f).
+#include "b200_internal.h"
+
+namespace b200 {
+
+constexpr int TILE = 64;
+constexpr int SROWS = TILE + 2;     // an odd source origin needs one extra chroma row/column
+constexpr int SPAD = 4;             // padding elements per shared row
+
+struct K6Args {
+  const void *y, *cb, *cr, *a;
+  long long ys, cs, as;             // strides in bytes
+  void* out[3];
+  long long os;                     // output stride in bytes
+  int src_w, src_h;
+  int out_w, out_h;
+  int m[6];
+  int sh, sv;                       // chroma subsampling shifts; -1 = monochrome
+  int bpp;
+  int full_range;
+  int int_mode;                     // 1: Op_YCbCr420_to_RGB24/32 integer arithmetic
+  float cf[4];                      // r_cr, g_cb, g_cr, b_cb
+  int ci[4];                        // lround(256*cf)
+  int out_fmt;                      // b200_chroma value
+  int sdr_shift;                    // Op_to_sdr_planes applied to the RGB result
+  int pre_shift;                    // Op_to_sdr_planes applied to the YCbCr planes first (then integer op)
+  int alpha_fill;                   // alpha value when the target wants alpha and the input has none
+  int out_bytes;                    // bytes per output sample (1 or 2)
+};
+
+__device__ __forceinline__ int clip_f(float fx, int maxv) {      // common_utils.h:108-114 clip_f_u16
+  int x = __float2int_rz(__fadd_rn(fx, 0.5f));
+  return x < 0 ? 0 : (x > maxv ? maxv : x);
+}
+__device__ __forceinline__ int clip_u8(int x) { return x < 0 ? 0 : (x > 255 ? 255 : x); }
+
+template <typename T>
+__device__ __forceinline__ void convert_px(const K6Args& p, int Y, int Cb, int Cr, int& r, int& g, int& b) {
+  if (p.sh < 0) { r = g = b = Y; return; }
+  if (p.int_mode) {                                               // yuv2rgb.cc:401-417
+    int cb = Cb - 128, cr = Cr - 128;
+    r = clip_u8(Y + ((p.ci[0] * cr + 128) >> 8));
+    g = clip_u8(Y + ((p.ci[1] * cb + p.ci[2] * cr + 128) >> 8));
+    b = clip_u8(Y + ((p.ci[3] * cb + 128) >> 8));
+    return;
+  }
+  const int half = 1 << (p.bpp - 1), maxv = (1 << p.bpp) - 1;     // yuv2rgb.cc:270-282
+  float yv = (float)Y, cb = (float)(Cb - half), cr = (float)(Cr - half);
+  if (!p.full_range) {
+    yv = __fmul_rn(__fsub_rn(yv, (float)(16 << (p.bpp - 8))), 1.1689f);
+    cb = __fmul_rn(cb, 1.1429f);
+    cr = __fmul_rn(cr, 1.1429f);
+  }
+  r = clip_f(__fadd_rn(yv, __fmul_rn(p.cf[0], cr)), maxv);
+  g = clip_f(__fadd_rn(__fadd_rn(yv, __fmul_rn(p.cf[1], cb)), __fmul_rn(p.cf[2], cr)), maxv);
+  b = clip_f(__fadd_rn(yv, __fmul_rn(p.cf[3], cb)), maxv);
+  if (p.sdr_shift) { r >>= p.sdr_shift; g >>= p.sdr_shift; b >>= p.sdr_shift; }
+}
+
+// stage a w x h window (origin x0,y0, clipped to pw x ph) of a plane into shared memory
+template <typename T>
+__device__ __forceinline__ void stage_plane(T (*dst)[TILE + SPAD], const void* base, long long stride, int x0, int y0,
+                                            int w, int h, int pw, int ph) {
+  const int tid = threadIdx.x;
+  constexpr int VEC = 16 / sizeof(T);
+  const bool vec_ok = (x0 % VEC == 0) && (w % VEC == 0) && (x0 + w <= pw) && (stride % 16 == 0) &&
+                      ((reinterpret_cast<uintptr_t>(base) & 15) == 0);
+  if (vec_ok) {
+    const int per_row = w / VEC;
+    for (int i = tid; i < per_row * h; i += blockDim.x) {
+      int r = i / per_row, c = i - r * per_row;
+      int sy = y0 + r;
+      if (sy >= ph) continue;
+      const uint4 v = __ldg(reinterpret_cast<const uint4*>(static_cast<const char*>(base) + (long long)sy * stride) + (x0 / VEC + c));
+      T tmp[VEC];
+      *reinterpret_cast<uint4*>(tmp) = v;
+#pragma unroll
+      for (int k = 0; k < VEC; k++) dst[r][c * VEC + k] = tmp[k];
+    }
+  } else {
+    for (int i = tid; i < w * h; i += blockDim.x) {
+      int r = i / w, c = i - r * w;
+      int sy = y0 + r, sx = x0 + c;
+      if (sy < ph && sx < pw) dst[r][c] = reinterpret_cast<const T*>(static_cast<const char*>(base) + (long long)sy * stride)[sx];
+    }
+  }
+}
+
+template <typename T, bool HAS_ALPHA>
+__global__ void __launch_bounds__(256) k6_color_kernel(const K6Args p) {
+  __shared__ __align__(16) T sY[TILE][TILE + SPAD];
+  __shared__ __align__(16) T sCb[SROWS][TILE + SPAD];
+  __shared__ __align__(16) T sCr[SROWS][TILE + SPAD];
+  __shared__ __align__(16) T sA[HAS_ALPHA ? TILE : 1][TILE + SPAD];
+
+  const int ox = blockIdx.x * TILE, oy = blockIdx.y * TILE;
+  const int tw = min(TILE, p.out_w - ox), th = min(TILE, p.out_h - oy);
+  // source window = image of the output tile's corners
+  const int ax = p.m[0] * ox + p.m[1] * oy + p.m[2], ay = p.m[3] * ox + p.m[4] * oy + p.m[5];
+  const int bx = p.m[0] * (ox + tw - 1) + p.m[1] * (oy + th - 1) + p.m[2];
+  const int by = p.m[3] * (ox + tw - 1) + p.m[4] * (oy + th - 1) + p.m[5];
+  const int s0x = min(ax, bx), s0y = min(ay, by);
+  const int sw = abs(ax - bx) + 1, sh_ = abs(ay - by) + 1;
+
+  // round the window out to 16-sample columns where the picture allows so the vector path is taken
+  int lx0 = s0x & ~15, lw = ((s0x + sw + 15) & ~15) - lx0;
+  if (lw > TILE || lx0 + lw > p.src_w) { lx0 = s0x; lw = sw; }
+  stage_plane<T>(sY, p.y, p.ys, lx0, s0y, lw, sh_, p.src_w, p.src_h);
+  if (HAS_ALPHA) stage_plane<T>(sA, p.a, p.as, lx0, s0y, lw, sh_, p.src_w, p.src_h);
+  int c0x = 0, c0y = 0;
+  if (p.sh >= 0) {
+    const int cw_pl = (p.src_w + (1 << p.sh) - 1) >> p.sh, ch_pl = (p.src_h + (1 << p.sv) - 1) >> p.sv;
+    c0x = lx0 >> p.sh; c0y = s0y >> p.sv;
+    int cw = ((lx0 + lw - 1) >> p.sh) - c0x + 1, chh = ((s0y + sh_ - 1) >> p.sv) - c0y + 1;
+    int cl0 = c0x & ~15, clw = ((c0x + cw + 15) & ~15) - cl0;
+    if (clw > TILE || cl0 + clw > cw_pl) { cl0 = c0x; clw = cw; }
+    stage_plane<T>(sCb, p.cb, p.cs, cl0, c0y, clw, chh, cw_pl, ch_pl);
+    stage_plane<T>(sCr, p.cr, p.cs, cl0, c0y, clw, chh, cw_pl, ch_pl);
+    c0x = cl0;
+  }
+  __syncthreads();
+
+  const int row = threadIdx.x >> 2, strip = threadIdx.x & 3;
+  const int y = oy + row, x_begin = ox + strip * 16;
+  if (row >= th || x_begin >= p.out_w) return;
+  const int npx = min(16, p.out_w - x_begin);
+
+  int R[16], G[16], B[16], A[16];
+#pragma unroll
+  for (int i = 0; i < 16; i++) {
+    const int x = x_begin + (i < npx ? i : 0);
+    const int sx = p.m[0] * x + p.m[1] * y + p.m[2], sy = p.m[3] * x + p.m[4] * y + p.m[5];
+    const int Y = sY[sy - s0y][sx - lx0] >> p.pre_shift;
+    int Cb = 0, Cr = 0;
+    if (p.sh >= 0) { Cb = sCb[(sy >> p.sv) - c0y][(sx >> p.sh) - c0x] >> p.pre_shift; Cr = sCr[(sy >> p.sv) - c0y][(sx >> p.sh) - c0x] >> p.pre_shift; }
+    convert_px<T>(p, Y, Cb, Cr, R[i], G[i], B[i]);
+    if (HAS_ALPHA) A[i] = sA[sy - s0y][sx - lx0] >> (p.sdr_shift + p.pre_shift); else A[i] = p.alpha_fill;
+  }
+
+  char* orow = static_cast<char*>(p.out[0]) + (long long)y * p.os;
+  const int fmt = p.out_fmt;
+  if (fmt == B200_CHROMA_444) {                      // planar RGB (yuv2rgb.cc Op_YCbCr_to_RGB output)
+    for (int c = 0; c < 3; c++) {
+      const int* v = c == 0 ? R : (c == 1 ? G : B);
+      char* prow = static_cast<char*>(p.out[c]) + (long long)y * p.os;
+      if (p.out_bytes == 1) for (int i = 0; i < npx; i++) reinterpret_cast<uint8_t*>(prow)[x_begin + i] = (uint8_t)v[i];
+      else for (int i = 0; i < npx; i++) reinterpret_cast<uint16_t*>(prow)[x_begin + i] = (uint16_t)v[i];
+    }
+    return;
+  }
+  // interleaved formats: build the 16-pixel strip in registers, then 128-bit stores
+  const int nch = (fmt == B200_CHROMA_INTERLEAVED_RGB || fmt == B200_CHROMA_INTERLEAVED_RRGGBB_BE || fmt == B200_CHROMA_INTERLEAVED_RRGGBB_LE) ? 3 : 4;
+  const int bps = (fmt == B200_CHROMA_INTERLEAVED_RGB || fmt == B200_CHROMA_INTERLEAVED_RGBA) ? 1 : 2;
+  const int le = (fmt == B200_CHROMA_INTERLEAVED_RRGGBB_LE || fmt == B200_CHROMA_INTERLEAVED_RRGGBBAA_LE);
+  __align__(16) uint8_t buf[16 * 8];
+  if (bps == 1) {
+#pragma unroll
+    for (int i = 0; i < 16; i++) {
+      if (nch == 3) { buf[3 * i] = (uint8_t)R[i]; buf[3 * i + 1] = (uint8_t)G[i]; buf[3 * i + 2] = (uint8_t)B[i]; }
+      else { buf[4 * i] = (uint8_t)R[i]; buf[4 * i + 1] = (uint8_t)G[i]; buf[4 * i + 2] = (uint8_t)B[i]; buf[4 * i + 3] = (uint8_t)A[i]; }
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < 16; i++) {
+      const int v[4] = {R[i], G[i], B[i], A[i]};
+#pragma unroll
+      for (int c = 0; c < 4; c++) {
+        if (c < nch) {
+          buf[(nch * i + c) * 2 + (le ? 1 : 0)] = (uint8_t)(v[c] >> 8);     // yuv2rgb.cc:715-729
+          buf[(nch * i + c) * 2 + (le ? 0 : 1)] = (uint8_t)(v[c] & 0xff);
+        }
+      }
+    }
+  }
+  const int bpp_out = nch * bps;
+  char* dst = orow + (long long)x_begin * bpp_out;
+  const int nbytes = npx * bpp_out;
+  if (npx == 16 && (reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
+    const uint4* src = reinterpret_cast<const uint4*>(buf);
+    const int nvec = bpp_out;                      // 16 px * bpp_out bytes / 16
+    for (int k = 0; k < nvec; k++) __stcs(reinterpret_cast<uint4*>(dst) + k, src[k]);
+  } else {
+    for (int k = 0; k < nbytes; k++) dst[k] = buf[k];
+  }
+}
+
+// ---------------------------------------------------------------------------------------------- host
+// nclx.cc:84-173, evaluated in float exactly as the reference does
+static void primaries_of(int idx, float p[8], bool& defined) {
+  defined = true;   // order: gx, gy, bx, by, rx, ry, wx, wy (nclx.cc:31-42 constructor argument order)
+  switch (idx) {
+    case 1: { const float v[8] = {0.300f, 0.600f, 0.150f, 0.060f, 0.640f, 0.330f, 0.3127f, 0.3290f}; memcpy(p, v, sizeof v); break; }
+    case 4: { const float v[8] = {0.21f, 0.71f, 0.14f, 0.08f, 0.67f, 0.33f, 0.310f, 0.316f}; memcpy(p, v, sizeof v); break; }
+    case 5: { const float v[8] = {0.29f, 0.60f, 0.15f, 0.06f, 0.64f, 0.33f, 0.3127f, 0.3290f}; memcpy(p, v, sizeof v); break; }
+    case 6: case 7: { const float v[8] = {0.310f, 0.595f, 0.155f, 0.070f, 0.630f, 0.340f, 0.3127f, 0.3290f}; memcpy(p, v, sizeof v); break; }
+    case 8: { const float v[8] = {0.243f, 0.692f, 0.145f, 0.049f, 0.681f, 0.319f, 0.310f, 0.316f}; memcpy(p, v, sizeof v); break; }
+    case 9: { const float v[8] = {0.170f, 0.797f, 0.131f, 0.046f, 0.708f, 0.292f, 0.3127f, 0.3290f}; memcpy(p, v, sizeof v); break; }
+    case 10: { const float v[8] = {0.0f, 1.0f, 0.0f, 0.0f, 1.0f, 0.0f, 0.333333f, 0.33333f}; memcpy(p, v, sizeof v); break; }
+    case 11: { const float v[8] = {0.265f, 0.690f, 0.150f, 0.060f, 0.680f, 0.320f, 0.314f, 0.351f}; memcpy(p, v, sizeof v); break; }
+    case 12: { const float v[8] = {0.265f, 0.690f, 0.150f, 0.060f, 0.680f, 0.320f, 0.3127f, 0.3290f}; memcpy(p, v, sizeof v); break; }
+    case 22: { const float v[8] = {0.295f, 0.605f, 0.155f, 0.077f, 0.630f, 0.340f, 0.3127f, 0.3290f}; memcpy(p, v, sizeof v); break; }
+    default: defined = false; for (int i = 0; i < 8; i++) p[i] = 0.0f;
+  }
+}
+
+void ycbcr_to_rgb_coefficients(int matrix, int primaries, float out[4]) {
+  volatile float Kr = 0.0f, Kb = 0.0f;              // volatile: keep every intermediate rounded to float
+  if (matrix == 12 || matrix == 13) {
+    float p[8]; bool def;
+    primaries_of(primaries, p, def);
+    const float gx = p[0], gy = p[1], bx = p[2], by = p[3], rx = p[4], ry = p[5], wx = p[6], wy = p[7];
+    float zr = 1 - (rx + ry), zg = 1 - (gx + gy), zb = 1 - (bx + by), zw = 1 - (wx + wy);
+    float denom = wy * (rx * (gy * zb - by * zg) + gx * (by * zr - ry * zb) + bx * (ry * zg - gy * zr));
+    if (denom != 0.0f) {
+      Kr = (ry * (wx * (gy * zb - by * zg) + wy * (bx * zg - gx * zb) + zw * (gx * by - bx * gy))) / denom;
+      Kb = (by * (wx * (ry * zg - gy * zr) + wy * (gx * zr - rx * zg) + zw * (rx * gy - gx * ry))) / denom;
+    }
+  } else {
+    switch (matrix) {
+      case 1: Kr = 0.2126f; Kb = 0.0722f; break;
+      case 4: Kr = 0.30f; Kb = 0.11f; break;
+      case 5: case 6: Kr = 0.299f; Kb = 0.114f; break;
+      case 7: Kr = 0.212f; Kb = 0.087f; break;
+      case 9: case 10: Kr = 0.2627f; Kb = 0.0593f; break;
+      default: break;
+    }
+  }
+  const float kr = Kr, kb = Kb;
+  if (kb != 0 || kr != 0) {
+    out[0] = 2 * (-kr + 1);
+    out[1] = 2 * kb * (-kb + 1) / (kb + kr - 1);
+    out[2] = 2 * kr * (-kr + 1) / (kb + kr - 1);
+    out[3] = 2 * (-kb + 1);
+  } else { out[0] = 1.402f; out[1] = -0.344136f; out[2] = -0.714136f; out[3] = 1.772f; }
+}
+
+// Mirror of the reference planner's choice for the supported states (colorconversion.cc:279-435; the
+// measured pipelines are tabulated in SURVEY.md Appendix A and re-checked by tests/test_color_parity.py).
+int launch_color(const b200_planes* in, const b200_geometry* g, const b200_color_options* opt, void* out, void* out_g,
+                 void* out_b, size_t out_stride, cudaStream_t stream, int* pipeline) {
+  if (!in || !g || !opt || !out) return set_error(B200_E_INVALID, "null argument");
+  if (in->bit_depth < 8 || in->bit_depth > 16) return set_error(B200_E_UNSUPPORTED, "bit depth %d", in->bit_depth);
+  const int fmt = opt->out_chroma;
+  const bool interleaved8 = fmt == B200_CHROMA_INTERLEAVED_RGB || fmt == B200_CHROMA_INTERLEAVED_RGBA;
+  const bool interleaved16 = fmt >= B200_CHROMA_INTERLEAVED_RRGGBB_BE && fmt <= B200_CHROMA_INTERLEAVED_RRGGBBAA_LE;
+  if (!interleaved8 && !interleaved16 && fmt != B200_CHROMA_444) return set_error(B200_E_UNSUPPORTED, "output chroma %d", fmt);
+  const int mc = in->matrix_coefficients;
+  if (in->chroma != B200_CHROMA_MONO && (mc == 0 || mc == 8 || mc == 11 || mc == 14 || mc == 16))
+    return set_error(B200_E_UNSUPPORTED, "matrix_coefficients %d has no linear YCbCr->RGB path here", mc);
+  if (interleaved16 && in->bit_depth == 8) return set_error(B200_E_UNSUPPORTED, "8-bit input to RRGGBB output");
+  K6Args a{};
+  a.y = in->y; a.cb = in->cb; a.cr = in->cr; a.a = in->alpha;
+  a.ys = (long long)in->y_stride; a.cs = (long long)in->c_stride; a.as = (long long)in->alpha_stride;
+  a.out[0] = out; a.out[1] = out_g; a.out[2] = out_b; a.os = (long long)out_stride;
+  a.src_w = in->width; a.src_h = in->height; a.out_w = g->out_w; a.out_h = g->out_h;
+  for (int i = 0; i < 6; i++) a.m[i] = g->m[i];
+  switch (in->chroma) {
+    case B200_CHROMA_MONO: a.sh = a.sv = -1; break;
+    case B200_CHROMA_420: a.sh = 1; a.sv = 1; break;
+    case B200_CHROMA_422: a.sh = 1; a.sv = 0; break;
+    case B200_CHROMA_444: a.sh = 0; a.sv = 0; break;
+    default: return set_error(B200_E_INVALID, "input chroma %d", in->chroma);
+  }
+  a.bpp = in->bit_depth; a.full_range = in->full_range ? 1 : 0;
+  ycbcr_to_rgb_coefficients(mc, in->colour_primaries, a.cf);
+  for (int i = 0; i < 4; i++) a.ci[i] = (int)lroundf(256 * a.cf[i]);      // yuv2rgb.cc:377-380
+  a.out_fmt = fmt;
+  const bool want_alpha = fmt == B200_CHROMA_INTERLEAVED_RGBA || fmt == B200_CHROMA_INTERLEAVED_RRGGBBAA_BE || fmt == B200_CHROMA_INTERLEAVED_RRGGBBAA_LE;
+  const bool has_alpha = in->alpha != nullptr && want_alpha;
+  int pipe = 0;
+  // integer fast path: 4:2:0, 8 bit, full range, interleaved 8-bit target (yuv2rgb.cc:300-340, :440-478)
+  a.int_mode = (in->chroma == B200_CHROMA_420 && in->bit_depth == 8 && in->full_range && interleaved8) ? 1 : 0;
+  pipe |= a.int_mode ? B200_PIPE_INT420 : B200_PIPE_FLOAT;
+  a.sdr_shift = 0; a.pre_shift = 0;
+  a.out_bytes = in->bit_depth > 8 ? 2 : 1;
+  if (in->bit_depth > 8 && interleaved8) {
+    a.out_bytes = 1; pipe |= B200_PIPE_SDR_SHIFT;
+    if (in->chroma == B200_CHROMA_420 && in->full_range) {
+      // the reference planner shifts the YCbCr planes to 8 bit first and then takes the integer op
+      a.pre_shift = in->bit_depth - 8; a.int_mode = 1; a.bpp = 8; pipe = B200_PIPE_SDR_SHIFT | B200_PIPE_INT420;
+    } else a.sdr_shift = in->bit_depth - 8;
+  }
+  a.alpha_fill = a.out_bytes == 1 ? 0xFF : (1 << in->bit_depth) - 1;
+  if (fmt == B200_CHROMA_444 && (!out_g || !out_b)) return set_error(B200_E_INVALID, "planar output needs three planes");
+  if (pipeline) *pipeline = pipe;
+  if (g->out_w <= 0 || g->out_h <= 0) return B200_OK;
+  dim3 grid((g->out_w + TILE - 1) / TILE, (g->out_h + TILE - 1) / TILE);
+  if (in->bit_depth == 8) {
+    if (has_alpha) k6_color_kernel<uint8_t, true><<<grid, 256, 0, stream>>>(a);
+    else k6_color_kernel<uint8_t, false><<<grid, 256, 0, stream>>>(a);
+  } else {
+    if (has_alpha) k6_color_kernel<uint16_t, true><<<grid, 256, 0, stream>>>(a);
+    else k6_color_kernel<uint16_t, false><<<grid, 256, 0, stream>>>(a);
+  }
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return set_error(B200_E_CUDA, "k6 launch: %s", cudaGetErrorString(e));
+  return B200_OK;
+}
+
+}  // namespace b200

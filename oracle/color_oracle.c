@@ -1,1 +1,200 @@
-/* placeholder, filled below */
+/*
+ * oracle/color_oracle.c -- TEST INFRASTRUCTURE ONLY. Never linked, imported or executed by the product.
+ *
+ * Plain C restatement of the reference's post-stage, written in the reference's own ORDER of operations
+ * (geometry on the separate planes first, then colour conversion op by op), so that it is an independent
+ * formulation of what the fused CUDA kernel computes by addressing:
+ *   HeifPixelImage::rotate_ccw / mirror_inplace / crop      libheif/image/pixelimage.cc:1175-1546
+ *   Op_YCbCr_to_RGB<T> (float arithmetic)                   libheif/color-conversion/yuv2rgb.cc:92-292
+ *   Op_YCbCr420_to_RGB24 / RGB32 (integer arithmetic)       yuv2rgb.cc:345-426, :481-562
+ *   Op_YCbCr420_to_RRGGBBaa                                 yuv2rgb.cc:622-734
+ *   Op_RGB_to_RGB24_32, Op_to_sdr_planes                    rgb2rgb.cc:71-150, hdr_sdr.cc:147-200
+ *   get_YCbCr_to_RGB_coefficients / get_Kr_Kb               nclx.cc:84-173
+ *   HeifPixelImage::overlay, scale_nearest_neighbor         pixelimage.cc:1637-1780, :1783-1972
+ * PINNED against the unmodified reference (oracle/_ref/libheif_ref.so through ref_postprocess() in
+ * oracle/ref_plugin.cc) and the reference's golden table tests/conversion.cc:697-724 by tests/test_color_oracle.py.
+ *
+ * Build note: compiled with -O2 for baseline x86-64 (no FMA), like the reference; float expressions are
+ * written in the reference's evaluation order.
+ */
+#include <math.h>
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+
+typedef struct {
+  uint16_t* p[4];     /* Y, Cb, Cr, A (samples widened to uint16) */
+  int w, h, cw, ch;   /* luma and chroma plane sizes */
+  int chroma;         /* 0 mono, 1 420, 2 422, 3 444 */
+  int has_alpha;
+} co_image;
+
+static void co_free(co_image* im) { for (int i = 0; i < 4; i++) { free(im->p[i]); im->p[i] = NULL; } }
+
+static uint16_t* plane_rot(const uint16_t* in, int w, int h, int deg) {      /* pixelimage.cc:1303-1332 */
+  int ow = (deg == 180) ? w : h, oh = (deg == 180) ? h : w;
+  uint16_t* out = (uint16_t*)malloc((size_t)ow * oh * 2 + 2);
+  if (deg == 270) { for (int x = 0; x < h; x++) for (int y = 0; y < w; y++) out[y * ow + x] = in[(h - 1 - x) * w + y]; }
+  else if (deg == 180) { for (int y = 0; y < h; y++) for (int x = 0; x < w; x++) out[y * ow + x] = in[(h - 1 - y) * w + (w - 1 - x)]; }
+  else { for (int x = 0; x < h; x++) for (int y = 0; y < w; y++) out[y * ow + x] = in[x * w + (w - 1 - y)]; }
+  return out;
+}
+
+static void plane_mirror(uint16_t* d, int w, int h, int direction) {           /* pixelimage.cc:1336-1355 */
+  if (direction == 1) { for (int y = 0; y < h; y++) for (int x = 0; x < w / 2; x++) { uint16_t t = d[y * w + x]; d[y * w + x] = d[y * w + w - 1 - x]; d[y * w + w - 1 - x] = t; } }
+  else { for (int y = 0; y < h / 2; y++) for (int x = 0; x < w; x++) { uint16_t t = d[y * w + x]; d[y * w + x] = d[(h - 1 - y) * w + x]; d[(h - 1 - y) * w + x] = t; } }
+}
+
+static void co_geometry(co_image* im, const int* ops, int nops) {
+  for (int i = 0; i < nops; i++) {
+    const int* o = ops + 5 * i;
+    int np = im->chroma ? 3 : 1;
+    if (o[0] == 1 && o[1] != 0) {
+      for (int c = 0; c < 4; c++) {
+        if (!im->p[c]) continue;
+        int pw = (c == 1 || c == 2) ? im->cw : im->w, ph = (c == 1 || c == 2) ? im->ch : im->h;
+        uint16_t* n = plane_rot(im->p[c], pw, ph, o[1]);
+        free(im->p[c]); im->p[c] = n;
+      }
+      if (o[1] != 180) { int t = im->w; im->w = im->h; im->h = t; t = im->cw; im->cw = im->ch; im->ch = t; }
+      (void)np;
+    } else if (o[0] == 2) {
+      for (int c = 0; c < 4; c++) if (im->p[c]) plane_mirror(im->p[c], (c == 1 || c == 2) ? im->cw : im->w, (c == 1 || c == 2) ? im->ch : im->h, o[1]);
+    } else if (o[0] == 3) {                                                    /* crop, pixelimage.cc:1433-1546 (even origin only) */
+      int l = o[1], r = o[2], t = o[3], b = o[4];
+      int sh = (im->chroma == 1 || im->chroma == 2) ? 1 : 0, sv = im->chroma == 1 ? 1 : 0;
+      int nw = r - l + 1, nh = b - t + 1, ncw = im->chroma ? (nw + sh) >> sh : 0, nch = im->chroma ? (nh + sv) >> sv : 0;
+      for (int c = 0; c < 4; c++) {
+        if (!im->p[c]) continue;
+        int isc = (c == 1 || c == 2);
+        int pw = isc ? im->cw : im->w, ow = isc ? ncw : nw, oh = isc ? nch : nh, x0 = isc ? l >> sh : l, y0 = isc ? t >> sv : t;
+        uint16_t* n = (uint16_t*)malloc((size_t)ow * oh * 2 + 2);
+        for (int y = 0; y < oh; y++) memcpy(n + (size_t)y * ow, im->p[c] + (size_t)(y + y0) * pw + x0, (size_t)ow * 2);
+        free(im->p[c]); im->p[c] = n;
+      }
+      im->w = nw; im->h = nh; im->cw = ncw; im->ch = nch;
+    }
+  }
+}
+
+/* nclx.cc:84-173 */
+void co_coefficients(int matrix, int primaries, float out[4]) {
+  float Kr = 0.0f, Kb = 0.0f;
+  if (matrix == 12 || matrix == 13) {
+    float gx, gy, bx, by, rx, ry, wx, wy; int ok = 1;
+    switch (primaries) {
+      case 1: gx = 0.300f; gy = 0.600f; bx = 0.150f; by = 0.060f; rx = 0.640f; ry = 0.330f; wx = 0.3127f; wy = 0.3290f; break;
+      case 4: gx = 0.21f; gy = 0.71f; bx = 0.14f; by = 0.08f; rx = 0.67f; ry = 0.33f; wx = 0.310f; wy = 0.316f; break;
+      case 5: gx = 0.29f; gy = 0.60f; bx = 0.15f; by = 0.06f; rx = 0.64f; ry = 0.33f; wx = 0.3127f; wy = 0.3290f; break;
+      case 6: case 7: gx = 0.310f; gy = 0.595f; bx = 0.155f; by = 0.070f; rx = 0.630f; ry = 0.340f; wx = 0.3127f; wy = 0.3290f; break;
+      case 8: gx = 0.243f; gy = 0.692f; bx = 0.145f; by = 0.049f; rx = 0.681f; ry = 0.319f; wx = 0.310f; wy = 0.316f; break;
+      case 9: gx = 0.170f; gy = 0.797f; bx = 0.131f; by = 0.046f; rx = 0.708f; ry = 0.292f; wx = 0.3127f; wy = 0.3290f; break;
+      case 10: gx = 0.0f; gy = 1.0f; bx = 0.0f; by = 0.0f; rx = 1.0f; ry = 0.0f; wx = 0.333333f; wy = 0.33333f; break;
+      case 11: gx = 0.265f; gy = 0.690f; bx = 0.150f; by = 0.060f; rx = 0.680f; ry = 0.320f; wx = 0.314f; wy = 0.351f; break;
+      case 12: gx = 0.265f; gy = 0.690f; bx = 0.150f; by = 0.060f; rx = 0.680f; ry = 0.320f; wx = 0.3127f; wy = 0.3290f; break;
+      case 22: gx = 0.295f; gy = 0.605f; bx = 0.155f; by = 0.077f; rx = 0.630f; ry = 0.340f; wx = 0.3127f; wy = 0.3290f; break;
+      default: gx = gy = bx = by = rx = ry = wx = wy = 0.0f; ok = 0;
+    }
+    (void)ok;
+    float zr = 1 - (rx + ry), zg = 1 - (gx + gy), zb = 1 - (bx + by), zw = 1 - (wx + wy);
+    float denom = wy * (rx * (gy * zb - by * zg) + gx * (by * zr - ry * zb) + bx * (ry * zg - gy * zr));
+    if (denom != 0.0f) {
+      Kr = (ry * (wx * (gy * zb - by * zg) + wy * (bx * zg - gx * zb) + zw * (gx * by - bx * gy))) / denom;
+      Kb = (by * (wx * (ry * zg - gy * zr) + wy * (gx * zr - rx * zg) + zw * (rx * gy - gx * ry))) / denom;
+    }
+  } else switch (matrix) {
+    case 1: Kr = 0.2126f; Kb = 0.0722f; break;
+    case 4: Kr = 0.30f; Kb = 0.11f; break;
+    case 5: case 6: Kr = 0.299f; Kb = 0.114f; break;
+    case 7: Kr = 0.212f; Kb = 0.087f; break;
+    case 9: case 10: Kr = 0.2627f; Kb = 0.0593f; break;
+    default: break;
+  }
+  if (Kb != 0 || Kr != 0) {
+    out[0] = 2 * (-Kr + 1); out[1] = 2 * Kb * (-Kb + 1) / (Kb + Kr - 1);
+    out[2] = 2 * Kr * (-Kr + 1) / (Kb + Kr - 1); out[3] = 2 * (-Kb + 1);
+  } else { out[0] = 1.402f; out[1] = -0.344136f; out[2] = -0.714136f; out[3] = 1.772f; }
+}
+
+static int clip_f_u16(float fx, int maxi) { int x = (int)(fx + 0.5f); return x < 0 ? 0 : (x > maxi ? maxi : x); }   /* common_utils.h:108-114 */
+static int clip_int_u8(int x) { return x < 0 ? 0 : (x > 255 ? 255 : x); }
+
+/*
+ * The whole post-stage on tightly packed uint16 planes.
+ *   ops: nops x 5 ints {kind (1 rotate_ccw, 2 mirror, 3 crop), a, b, c, d}
+ *   out_chroma: 10 RGB, 11 RGBA, 12/13 RRGGBB(AA)_BE, 14/15 RRGGBB(AA)_LE, 3 planar RGB (uint8 or uint16 by depth)
+ * Returns bytes written to out (rows tightly packed; planar: R,G,B planes one after the other) or <0.
+ */
+long co_postprocess(const uint16_t* y, const uint16_t* cb, const uint16_t* cr, const uint16_t* alpha, int w, int h, int chroma,
+                    int bpp, int cp, int mc, int full_range, const int* ops, int nops, int out_chroma,
+                    uint8_t* out, int* out_w, int* out_h) {
+  co_image im; memset(&im, 0, sizeof im);
+  int sh = (chroma == 1 || chroma == 2) ? 1 : 0, sv = chroma == 1 ? 1 : 0;
+  im.w = w; im.h = h; im.chroma = chroma; im.cw = chroma ? (w + sh) >> sh : 0; im.ch = chroma ? (h + sv) >> sv : 0;
+  const uint16_t* src[4] = {y, cb, cr, alpha};
+  for (int c = 0; c < 4; c++) {
+    if (!src[c]) continue;
+    size_t n = (size_t)((c == 1 || c == 2) ? im.cw * im.ch : w * h);
+    im.p[c] = (uint16_t*)malloc(n * 2 + 2); memcpy(im.p[c], src[c], n * 2);
+  }
+  co_geometry(&im, ops, nops);
+  w = im.w; h = im.h;
+  *out_w = w; *out_h = h;
+  float cf[4]; co_coefficients(mc, cp, cf);
+  const int interleaved8 = out_chroma == 10 || out_chroma == 11;
+  /* >8-bit full-range 4:2:0 to an 8-bit interleaved target: the reference planner runs Op_to_sdr_planes on the
+     YCbCr planes FIRST and then the integer op (observed with ref_postprocess); every other >8-bit case
+     converts in float at full depth and shifts afterwards. */
+  const int pre_shift = (chroma == 1 && bpp > 8 && full_range && interleaved8) ? bpp - 8 : 0;
+  if (pre_shift) {
+    for (int c = 0; c < 4; c++) if (im.p[c]) {
+      size_t n = (size_t)((c == 1 || c == 2) ? im.cw * im.ch : im.w * im.h);
+      for (size_t i = 0; i < n; i++) im.p[c][i] >>= pre_shift;
+    }
+    bpp = 8;
+  }
+  const int int_mode = chroma == 1 && bpp == 8 && full_range && interleaved8;     /* yuv2rgb.cc:300-340 */
+  const int ci[4] = {(int)lroundf(256 * cf[0]), (int)lroundf(256 * cf[1]), (int)lroundf(256 * cf[2]), (int)lroundf(256 * cf[3])};
+  const int half = 1 << (bpp - 1), maxv = (1 << bpp) - 1;
+  const float lro = (float)(16 << (bpp - 8));
+  const int sdr_shift = (bpp > 8 && interleaved8) ? bpp - 8 : 0;
+  const int want_alpha = out_chroma == 11 || out_chroma == 13 || out_chroma == 15;
+  const int nch = want_alpha ? 4 : 3;
+  const int le = out_chroma == 14 || out_chroma == 15;
+  size_t pos = 0;
+  const int out16 = (out_chroma >= 12 && out_chroma <= 15) || (out_chroma == 3 && bpp > 8);
+  for (int yy = 0; yy < h; yy++) for (int xx = 0; xx < w; xx++) {
+    int Y = im.p[0][yy * w + xx], r, g, b;
+    if (!chroma) r = g = b = Y;
+    else {
+      int Cb = im.p[1][(yy >> sv) * im.cw + (xx >> sh)], Cr = im.p[2][(yy >> sv) * im.cw + (xx >> sh)];
+      if (int_mode) {
+        int cbv = Cb - 128, crv = Cr - 128;
+        r = clip_int_u8(Y + ((ci[0] * crv + 128) >> 8));
+        g = clip_int_u8(Y + ((ci[1] * cbv + ci[2] * crv + 128) >> 8));
+        b = clip_int_u8(Y + ((ci[3] * cbv + 128) >> 8));
+      } else {
+        float yv = (float)Y, cbv = (float)(Cb - half), crv = (float)(Cr - half);
+        if (!full_range) { yv = (yv - lro) * 1.1689f; cbv = cbv * 1.1429f; crv = crv * 1.1429f; }
+        r = clip_f_u16(yv + cf[0] * crv, maxv);
+        g = clip_f_u16(yv + cf[1] * cbv + cf[2] * crv, maxv);
+        b = clip_f_u16(yv + cf[3] * cbv, maxv);
+        r >>= sdr_shift; g >>= sdr_shift; b >>= sdr_shift;
+      }
+    }
+    int a = im.p[3] ? im.p[3][yy * w + xx] >> sdr_shift : (out16 ? maxv : 255);
+    if (out_chroma == 3) {
+      size_t pl = (size_t)w * h;
+      if (out16) { ((uint16_t*)out)[yy * w + xx] = (uint16_t)r; ((uint16_t*)out)[pl + yy * w + xx] = (uint16_t)g; ((uint16_t*)out)[2 * pl + yy * w + xx] = (uint16_t)b; }
+      else { out[yy * w + xx] = (uint8_t)r; out[pl + yy * w + xx] = (uint8_t)g; out[2 * pl + yy * w + xx] = (uint8_t)b; }
+    } else if (!out16) {
+      out[pos++] = (uint8_t)r; out[pos++] = (uint8_t)g; out[pos++] = (uint8_t)b; if (want_alpha) out[pos++] = (uint8_t)a;
+    } else {
+      int v[4] = {r, g, b, a};
+      for (int c = 0; c < nch; c++) { out[pos + (le ? 1 : 0)] = (uint8_t)(v[c] >> 8); out[pos + (le ? 0 : 1)] = (uint8_t)(v[c] & 0xff); pos += 2; }
+    }
+  }
+  co_free(&im);
+  if (out_chroma == 3) return (long)((size_t)w * h * 3 * (out16 ? 2 : 1));
+  return (long)pos;
+}

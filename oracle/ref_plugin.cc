@@ -116,3 +116,77 @@ extern "C" int b200_oracle_register(const char* avcodec_dir) {
   heif_error e = heif_register_decoder_plugin(&g_plugin);
   return e.code;
 }
+
+// ------------------------------------------------------------------------------------------------
+// Direct access to the UNMODIFIED reference post-stage (internal C++ API of libheif_ref.so) so that the
+// C restatement (color_oracle.c) and the CUDA path can be pinned on arbitrary synthetic planes:
+// HeifPixelImage::rotate_ccw / mirror_inplace / crop (libheif/image/pixelimage.cc:1175-1546) followed by
+// convert_colorspace (libheif/color-conversion/colorconversion.cc:490-623) with the options
+// heif_decode_image uses (api/libheif/heif_decoding.cc:78-81; target nclx = sRGB defaults, context.cc:1545-1558).
+#include "image/pixelimage.h"
+#include "color-conversion/colorconversion.h"
+#include "security_limits.h"
+
+extern "C" int ref_postprocess(const void* y, const void* cb, const void* cr, const void* alpha, int w, int h, int chroma, int bpp,
+                               int has_nclx, int cp, int tc, int mc, int full_range, const int* ops, int nops,
+                               int out_colorspace, int out_chroma, int only_preferred, int upsampling, int hdr_to_8bit,
+                               uint8_t* out, size_t out_capacity, int* out_w, int* out_h, int* out_rowbytes, int* out_planes) {
+  const heif_security_limits* limits = heif_get_global_security_limits();
+  auto img = std::make_shared<HeifPixelImage>();
+  img->create(w, h, chroma == 0 ? heif_colorspace_monochrome : heif_colorspace_YCbCr, (heif_chroma)chroma);
+  const int sh = (chroma == 1 || chroma == 2) ? 1 : 0, sv = chroma == 1 ? 1 : 0;
+  const int cw = (w + sh) >> sh, ch = (h + sv) >> sv, bps = bpp > 8 ? 2 : 1;
+  struct { heif_channel c; const void* p; int w, h; } pl[4] = {{heif_channel_Y, y, w, h}, {heif_channel_Cb, cb, cw, ch}, {heif_channel_Cr, cr, cw, ch}, {heif_channel_Alpha, alpha, w, h}};
+  for (auto& q : pl) {
+    if (!q.p) continue;
+    if (img->add_channel(q.c, q.w, q.h, bpp, limits)) return -1;
+    size_t stride; uint8_t* dst = img->get_channel_memory(q.c, &stride);
+    for (int r = 0; r < q.h; r++) memcpy(dst + r * stride, (const uint8_t*)q.p + (size_t)r * q.w * bps, (size_t)q.w * bps);
+  }
+  if (has_nclx) {
+    nclx_profile p;
+    p.set_colour_primaries((uint16_t)cp); p.set_transfer_characteristics((uint16_t)tc);
+    p.set_matrix_coefficients((uint16_t)mc); p.set_full_range_flag(full_range != 0);
+    img->set_color_profile_nclx(p);
+  }
+  for (int i = 0; i < nops; i++) {
+    const int* o = ops + 5 * i;
+    Result<std::shared_ptr<HeifPixelImage>> r = Error::Ok;
+    if (o[0] == 1) r = img->rotate_ccw(o[1], limits);
+    else if (o[0] == 2) r = img->mirror_inplace((heif_transform_mirror_direction)o[1], limits);
+    else if (o[0] == 3) r = img->crop(o[1], o[2], o[3], o[4], limits);
+    else return -2;
+    if (!r) return -3;
+    img = *r;
+  }
+  heif_color_conversion_options copt{};
+  copt.version = 1;
+  copt.preferred_chroma_downsampling_algorithm = heif_chroma_downsampling_average;
+  copt.preferred_chroma_upsampling_algorithm = (heif_chroma_upsampling_algorithm)upsampling;
+  copt.only_use_preferred_chroma_algorithm = (uint8_t)only_preferred;
+  nclx_profile target; target.set_sRGB_defaults();
+  auto res = convert_colorspace(img, (heif_colorspace)out_colorspace, (heif_chroma)out_chroma, target, hdr_to_8bit ? 8 : 0, copt, nullptr, limits);
+  if (!res) return -4;
+  auto o = *res;
+  *out_w = o->get_width(); *out_h = o->get_height();
+  size_t pos = 0;
+  std::vector<heif_channel> chans;
+  if (o->has_channel(heif_channel_interleaved)) chans = {heif_channel_interleaved};
+  else { chans = {heif_channel_R, heif_channel_G, heif_channel_B}; if (o->has_channel(heif_channel_Alpha)) chans.push_back(heif_channel_Alpha); }
+  *out_planes = (int)chans.size();
+  for (heif_channel c : chans) {
+    size_t stride; const uint8_t* src = o->get_channel_memory(c, &stride);
+    int obpp = o->get_bits_per_pixel(c);
+    size_t rowb;
+    if (c == heif_channel_interleaved) {
+      heif_chroma oc = o->get_chroma_format();
+      int bytes = oc == heif_chroma_interleaved_RGB ? 3 : oc == heif_chroma_interleaved_RGBA ? 4 :
+                  (oc == heif_chroma_interleaved_RRGGBB_BE || oc == heif_chroma_interleaved_RRGGBB_LE) ? 6 : 8;
+      rowb = (size_t)*out_w * bytes;
+    } else rowb = (size_t)*out_w * (obpp > 8 ? 2 : 1);
+    *out_rowbytes = (int)rowb;
+    if (pos + rowb * *out_h > out_capacity) return -5;
+    for (int r = 0; r < *out_h; r++) { memcpy(out + pos, src + r * stride, rowb); pos += rowb; }
+  }
+  return 0;
+}

@@ -1,0 +1,60 @@
+"""CPU: pin the colour restatement (oracle/color_oracle.c) against the UNMODIFIED reference
+(oracle/_ref/libheif_ref.so: HeifPixelImage transforms + convert_colorspace) on LCG-random planes.
+Mirrors the differential strategy of the reference's tests/conversion.cc (every state pair, small images)."""
+import numpy as np
+import pytest
+
+from util import oracle_postprocess, random_ycbcr, ref_plugin, ref_postprocess
+
+needs_ref = pytest.mark.skipif(ref_plugin() is None, reason="oracle/_ref reference build not present")
+
+SIZES = [(2, 2), (6, 4), (34, 18), (64, 64), (130, 70)]
+CASES = [
+    # chroma, bpp, nclx (cp,tc,mc,full), out_chroma
+    (1, 8, (1, 13, 6, 1), 10), (1, 8, (1, 13, 6, 0), 10), (1, 8, (2, 2, 2, 0), 10), (1, 8, (1, 13, 1, 0), 10),
+    (1, 8, (9, 16, 9, 0), 10), (1, 8, (1, 13, 5, 1), 11), (1, 8, (1, 13, 6, 0), 11), (1, 8, None, 10),
+    (3, 8, (1, 13, 6, 1), 10), (3, 8, (1, 13, 6, 0), 10), (2, 8, (1, 13, 6, 1), 10), (2, 8, (1, 13, 1, 0), 11),
+    (1, 10, (9, 16, 9, 0), 14), (1, 10, (9, 16, 9, 1), 14), (1, 12, (9, 16, 9, 0), 14), (1, 10, (9, 16, 9, 0), 12),
+    (1, 10, (1, 13, 1, 0), 10), (1, 12, (1, 13, 6, 1), 10), (1, 8, (1, 13, 6, 0), 3), (1, 10, (9, 16, 9, 0), 3),
+    (1, 8, (1, 13, 12, 1), 10), (1, 8, (9, 13, 13, 0), 10), (1, 8, (1, 13, 4, 0), 10), (1, 8, (1, 13, 7, 1), 10),
+]
+
+
+@needs_ref
+@pytest.mark.parametrize("case", CASES)
+@pytest.mark.parametrize("size", SIZES)
+def test_restatement_matches_reference(case, size):
+    chroma, bpp, nclx, outc = case
+    w, h = size
+    y, cb, cr, _ = random_ycbcr(0xB200 + w * 131 + h, w, h, chroma, bpp)
+    hdr8 = 1 if (bpp > 8 and outc in (10, 11)) else 0
+    ref, rw, rh, _ = ref_postprocess(y, cb, cr, None, chroma, bpp, nclx, [], outc, hdr_to_8bit=hdr8)
+    got, ow, oh = oracle_postprocess(y, cb, cr, None, chroma, bpp, nclx, [], outc)
+    assert (ow, oh) == (rw, rh)
+    assert np.array_equal(ref, got), f"first diff at {np.argwhere(ref != got)[:4].ravel()}"
+
+
+@needs_ref
+@pytest.mark.parametrize("alpha_out", [10, 11])
+@pytest.mark.parametrize("nclx", [(1, 13, 6, 1), (1, 13, 6, 0)])
+def test_alpha_plane(alpha_out, nclx):
+    y, cb, cr, a = random_ycbcr(77, 36, 20, 1, 8, alpha=True)
+    ref, rw, rh, _ = ref_postprocess(y, cb, cr, a, 1, 8, nclx, [], alpha_out)
+    got, ow, oh = oracle_postprocess(y, cb, cr, a if alpha_out == 11 else None, 1, 8, nclx, [], alpha_out)
+    assert np.array_equal(ref, got)
+
+
+GEOM = [[(1, 90)], [(1, 180)], [(1, 270)], [(2, 0)], [(2, 1)], [(3, 2, 21, 4, 17)], [(1, 90), (2, 1)],
+        [(3, 4, 27, 2, 13), (1, 270)], [(2, 0), (1, 90), (3, 0, 9, 0, 15)]]
+
+
+@needs_ref
+@pytest.mark.parametrize("ops", GEOM)
+@pytest.mark.parametrize("fmt", [(1, 8, (1, 13, 6, 0), 10), (1, 10, (9, 16, 9, 0), 14), (3, 8, (1, 13, 6, 1), 11)])
+def test_geometry_then_colour(ops, fmt):
+    chroma, bpp, nclx, outc = fmt
+    y, cb, cr, _ = random_ycbcr(1234, 32, 24, chroma, bpp)
+    ref, rw, rh, _ = ref_postprocess(y, cb, cr, None, chroma, bpp, nclx, ops, outc)
+    got, ow, oh = oracle_postprocess(y, cb, cr, None, chroma, bpp, nclx, ops, outc)
+    assert (ow, oh) == (rw, rh)
+    assert np.array_equal(ref, got)
