@@ -97,6 +97,43 @@ int b200_color_convert_host(const b200_planes* in, const b200_geometry* geom, co
 /* nclx helper: the 4 float coefficients exactly as nclx.cc:84-173 derives them */
 void b200_ycbcr_to_rgb_coefficients(int matrix_coefficients, int colour_primaries, float out_coeffs[4] /* r_cr,g_cb,g_cr,b_cb */);
 
+/* ------------------------------------------------------------------------------------------------
+ * HEVC intra encoder (host): produces the synthetic inputs of BASELINE configs 2-5 and backs the
+ * heif_encoder_plugin (libheif/api/libheif/heif_plugin.h:192-313) exported by this library.
+ * Role of: x265 behind libheif/plugins/encoder_x265.cc:752-1051 (encode_image) and :1186-1244
+ * (get_compressed_data: one NAL per call, no start code), driven by libheif/codecs/hevc_enc.cc:33-115.
+ * Output here: every NAL of the access unit (VPS, SPS, PPS, slice segments), each prefixed by its
+ * uint32 big-endian length -- the framing libheif pushes into a decoder plugin.
+ * ------------------------------------------------------------------------------------------------ */
+typedef struct b200_hevc_enc_params {
+  int width, height;                 /* luma size; coded size is rounded up to 8 and cropped by the conformance window */
+  int bit_depth;                     /* 8, 10, 12 */
+  int chroma_format_idc;             /* 1 = 4:2:0, 0 = 4:0:0 */
+  int log2_ctb_size;                 /* 4, 5, 6 */
+  int qp, init_qp;                   /* slice QP target and pps init_qp_minus26 + 26 */
+  int max_transform_hierarchy_depth_intra;
+  int sao, sign_data_hiding, transform_skip, strong_intra_smoothing;
+  int cu_qp_delta, diff_cu_qp_delta_depth, dqp_range;
+  int cb_qp_offset, cr_qp_offset, slice_chroma_qp_offsets, slice_cb_qp_offset, slice_cr_qp_offset;
+  int wpp;                           /* entropy_coding_sync_enabled_flag + entry points */
+  int slice_ctb_rows;                /* > 0: start a new slice every N CTB rows */
+  int dependent_slice_segments;      /* with slice_ctb_rows > 1 and !wpp: one dependent segment per CTB row */
+  int loop_filter_across_slices, slice_loop_filter_across_slices;
+  int deblocking_disabled, beta_offset_div2, tc_offset_div2;
+  int slice_deblocking_override, slice_deblocking_disabled, slice_beta_offset_div2, slice_tc_offset_div2;
+  int mode_decision;                 /* 0 = pseudo-random modes/partitions (syntax coverage), 1 = SAD-based choice */
+  int split_threshold;               /* activity threshold of the CU split heuristic */
+  int still_picture;                 /* Main Still Picture profile signalling for 8-bit 4:2:0 */
+  int vui_present, colour_description_present, colour_primaries, transfer_characteristics, matrix_coefficients, full_range;
+  uint32_t seed;                     /* LCG seed (0xB200 + tile index) */
+} b200_hevc_enc_params;
+
+void b200_hevc_enc_params_default(b200_hevc_enc_params* p);
+/* planes: uint8 (bit_depth 8) or native-endian uint16; *out_data is malloc'ed, release with b200_free */
+int b200_hevc_encode_intra(const b200_hevc_enc_params* p, const void* y, const void* cb, const void* cr, size_t y_stride,
+                           size_t c_stride, uint8_t** out_data, size_t* out_size);
+void b200_free(void* p);
+
 #ifdef __cplusplus
 }
 #endif

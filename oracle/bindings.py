@@ -47,7 +47,7 @@ def lib():
         path = os.path.join(REF, "liboracle.so")
         if not os.path.exists(path):
             raise RuntimeError("oracle/_ref/liboracle.so missing: run `make -C oracle` (or __graft_entry__.build())")
-        _lib = C.CDLL(path, mode=C.RTLD_GLOBAL)
+        _lib = C.CDLL(path)
         _lib.ffhevc_init.argtypes = [C.c_char_p]
         _lib.ffhevc_decode.argtypes = [C.c_char_p, C.c_size_t, C.c_int, C.POINTER(_FFPic)]
         _lib.hevc_oracle_decode.argtypes = [C.c_char_p, C.c_size_t, C.c_int, C.POINTER(_HOPic)]

@@ -1221,6 +1221,7 @@ static void sao_picture(dec_t* d) {
           int ei = 2 + (v > a) - (v < a) + (v > b2) - (v < b2);
           idx = ei == 2 ? 0 : (ei < 2 ? ei + 1 : ei);
         }
+        if (getenv("HO_SAO_DBG")) { int dc, dx, dy; sscanf(getenv("HO_SAO_DBG"), "%d,%d,%d", &dc, &dx, &dy); if (dc == c && dx == x && dy == y) fprintf(stderr, "sao c=%d (%d,%d) type=%d class=%d band=%d idx=%d off=[%d %d %d %d] v=%d\n", c, x, y, sp->type[c], sp->eo_class[c], sp->band_pos[c], idx, sp->offset[c][1], sp->offset[c][2], sp->offset[c][3], sp->offset[c][4], v); }
         d->pl[c][y * st + x] = (uint16_t)clip3(0, maxv, v + sp->offset[c][idx]);
       }
     }

@@ -64,8 +64,8 @@ def ref_plugin():
         if not os.path.exists(p) or not os.path.exists(os.path.join(ob.REF, "libheif_ref.so")):
             return None
         ob.lib()
-        C.CDLL(os.path.join(ob.REF, "libheif_ref.so"), mode=C.RTLD_GLOBAL)
-        _plugin = C.CDLL(p, mode=C.RTLD_GLOBAL)
+        # RTLD_LOCAL on purpose: libheif_ref.so exports thousands of C++ symbols that must not interpose on torch
+        _plugin = C.CDLL(p)
     return _plugin
 
 
