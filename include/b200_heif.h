@@ -134,6 +134,61 @@ int b200_hevc_encode_intra(const b200_hevc_enc_params* p, const void* y, const v
                            size_t c_stride, uint8_t** out_data, size_t* out_size);
 void b200_free(void* p);
 
+/* ------------------------------------------------------------------------------------------------
+ * HEVC intra decoder: host CABAC front-end + sm_100a reconstruction / deblocking / SAO kernels.
+ * Replaces: the libde265 calls of libheif/plugins/decoder_libde265.cc -- de265_new_decoder :181,
+ *   de265_push_NAL :360, de265_decode :402, de265_get_next_picture :410, de265_get_image_plane :137,
+ *   de265_get_image_{colour_primaries,transfer_characteristics,matrix_coefficients,full_range_flag} :428-446,
+ *   de265_free_decoder :233 -- and, for grids, the per-tile paste HeifPixelImage::copy_image_to
+ *   (libheif/image/pixelimage.cc:1115-1172) driven by ImageItem_Grid::decode_and_paste_tile_image
+ *   (libheif/image-items/grid.cc:482-577).
+ * Input framing: every access unit is [uint32 BE length][NAL]... exactly as Decoder::get_compressed_data
+ * (libheif/codecs/decoder.cc:275-308) hands it to push_data2.
+ * ------------------------------------------------------------------------------------------------ */
+typedef struct b200_decoder b200_decoder;
+
+typedef struct b200_image_info {
+  int width, height;          /* canvas size (single image: conformance-cropped picture size) */
+  int tile_width, tile_height;
+  int chroma;                 /* B200_CHROMA_MONO or B200_CHROMA_420 */
+  int bit_depth;
+  int colour_primaries, transfer_characteristics, matrix_coefficients, full_range;   /* from the SPS VUI, defaults 2/2/2/0 */
+} b200_image_info;
+
+typedef struct b200_decode_stats {
+  double parse_ms, pack_ms, h2d_ms, gpu_ms, total_ms;   /* host wall-clock of the last decode call (gpu_ms: CUDA events) */
+  double recon_ms, deblock_ms, sao_ms;                  /* per-kernel device times of the last call */
+  uint64_t bitstream_bytes, command_bytes, coefficient_entries, transform_units, ctus, h2d_bytes, pixels;
+  int kernel_launches;
+} b200_decode_stats;
+
+/* host_threads: CABAC parser threads (0 = number of online cores).  The CUDA device is the current one. */
+int b200_decoder_create(b200_decoder** dec, int host_threads);
+void b200_decoder_destroy(b200_decoder* dec);
+
+/* Decode cols*rows independent access units (row-major grid tiles; 1x1 = a single image) into the decoder's
+   device canvas (planar Y/Cb/Cr, 4:2:0 or 4:0:0).  canvas_w/h = 0 -> cols*tile_w x rows*tile_h.  Tiles overhanging
+   the canvas are clipped like HeifPixelImage::copy_image_to does.  max_image_size_pixels = 0 -> unlimited
+   (heif_security_limits, enforced per coded picture like decoder_libde265.cc:189-198).
+   Asynchronous with respect to `stream` unless stats are requested (b200_decoder_get_stats synchronises). */
+int b200_decoder_decode_grid(b200_decoder* dec, int cols, int rows, const uint8_t* const* au, const size_t* au_size,
+                             uint64_t max_image_size_pixels, int canvas_w, int canvas_h, b200_image_info* info, void* stream);
+
+/* Device planes of the canvas (valid until the next decode call on this decoder). */
+int b200_decoder_get_planes(b200_decoder* dec, b200_planes* out);
+/* Copy the canvas planes to host memory (D2H + synchronise).  cb/cr may be NULL for 4:0:0. */
+int b200_decoder_read_planes(b200_decoder* dec, void* y, size_t y_stride, void* cb, void* cr, size_t c_stride, void* stream);
+/* Reconstruction planes of tile `index` before/after deblocking (debug / parity of intermediate stages):
+   stage 1 = before deblocking, 2 = after deblocking (coded size, no conformance crop).  Host copies. */
+int b200_decoder_debug_read_tile(b200_decoder* dec, int index, int stage, void* y, void* cb, void* cr);
+int b200_decoder_set_debug_stage(b200_decoder* dec, int stage /* 0 = full pipeline, 1 = stop after reconstruction, 2 = stop after deblocking */);
+int b200_decoder_get_stats(b200_decoder* dec, b200_decode_stats* out);
+
+/* Fused convenience: decode grid -> geometry -> colour conversion -> interleaved RGB in HOST memory. */
+int b200_decode_grid_to_rgb_host(b200_decoder* dec, int cols, int rows, const uint8_t* const* au, const size_t* au_size,
+                                 uint64_t max_image_size_pixels, int canvas_w, int canvas_h, const b200_geometry* geom /* NULL = identity */,
+                                 const b200_color_options* opt, void* out, size_t out_stride, b200_image_info* info);
+
 #ifdef __cplusplus
 }
 #endif

@@ -9,3 +9,5 @@ from .color import (Geometry, YCbCrImage, convert_colorspace, convert_colorspace
                     CHROMA_420, CHROMA_422, CHROMA_444, CHROMA_MONO, CHROMA_INTERLEAVED_RGB, CHROMA_INTERLEAVED_RGBA,
                     CHROMA_INTERLEAVED_RRGGBB_BE, CHROMA_INTERLEAVED_RRGGBBAA_BE, CHROMA_INTERLEAVED_RRGGBB_LE,
                     CHROMA_INTERLEAVED_RRGGBBAA_LE)
+from .decoder import Decoder, ImageInfo, DecodeStats  # noqa: F401,E402
+from . import hevc_enc  # noqa: F401,E402

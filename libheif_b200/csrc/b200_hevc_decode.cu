@@ -1,0 +1,351 @@
+// b200_hevc_decode.cu -- decoder object behind the C ABI: parallel host CABAC front-end, staging into pinned
+// memory, one H2D per array, then the reconstruction / deblocking / SAO kernels for the whole batch of tiles.
+//
+// Mirrors the call order libheif uses on a decoder plugin instance (new_decoder2 -> push_data2 -> flush_data ->
+// decode_next_image2 -> free_decoder, libheif/codecs/decoder.cc:388-405,441-446,458-460,487-493), but for N
+// independent tiles at once, which is how ImageItem_Grid::decode_full_grid_image (libheif/image-items/grid.cc:250-468)
+// consumes it.  All expensive state (device arenas, pinned staging, streams, events) lives here and is reused.
+#include "b200_hevc.h"
+#include <atomic>
+#include <chrono>
+#include <condition_variable>
+#include <functional>
+#include <mutex>
+#include <string>
+#include <thread>
+#include <unistd.h>
+
+using namespace b200;
+
+namespace {
+
+double now_ms() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
+
+// minimal persistent thread pool: parallel_for over [0, n)
+class Pool {
+ public:
+  explicit Pool(int n) : stop_(false), gen_(0), next_(0), total_(0), pending_(0) { for (int i = 0; i < n; i++) th_.emplace_back([this] { run(); }); }
+  ~Pool() { { std::lock_guard<std::mutex> l(mu_); stop_ = true; } cv_.notify_all(); for (auto& t : th_) t.join(); }
+  int size() const { return (int)th_.size(); }
+  void parallel_for(int n, const std::function<void(int)>& fn) {
+    if (n <= 0) return;
+    if (th_.empty() || n == 1) { for (int i = 0; i < n; i++) fn(i); return; }
+    { std::lock_guard<std::mutex> l(mu_); fn_ = &fn; total_ = n; next_.store(0); pending_ = (int)th_.size(); gen_++; }
+    cv_.notify_all();
+    std::unique_lock<std::mutex> l(mu_);
+    done_.wait(l, [this] { return pending_ == 0; });
+  }
+ private:
+  void run() {
+    unsigned seen = 0;
+    for (;;) {
+      const std::function<void(int)>* fn; int total;
+      { std::unique_lock<std::mutex> l(mu_); cv_.wait(l, [&] { return stop_ || gen_ != seen; }); if (stop_) return; seen = gen_; fn = fn_; total = total_; }
+      for (;;) { int i = next_.fetch_add(1); if (i >= total) break; (*fn)(i); }
+      { std::lock_guard<std::mutex> l(mu_); if (--pending_ == 0) done_.notify_all(); }
+    }
+  }
+  std::vector<std::thread> th_; std::mutex mu_; std::condition_variable cv_, done_;
+  bool stop_; unsigned gen_; std::atomic<int> next_; int total_, pending_; const std::function<void(int)>* fn_ = nullptr;
+};
+
+template <typename T>
+struct DevBuf {   // grow-only device + pinned host pair
+  T* d = nullptr; T* h = nullptr; size_t cap = 0;
+  int reserve(size_t n, bool host = true) {
+    if (n <= cap) return B200_OK;
+    size_t nc = n + n / 4 + 1024;
+    if (d) cudaFree(d);
+    if (h) cudaFreeHost(h);
+    d = nullptr; h = nullptr; cap = 0;
+    B200_CUDA_CHECK(cudaMalloc(&d, nc * sizeof(T)));
+    if (host) B200_CUDA_CHECK(cudaMallocHost(&h, nc * sizeof(T)));
+    cap = nc;
+    return B200_OK;
+  }
+  void release() { if (d) cudaFree(d); if (h) cudaFreeHost(h); d = nullptr; h = nullptr; cap = 0; }
+};
+
+}  // namespace
+
+struct b200_decoder {
+  Pool* pool = nullptr;
+  std::vector<ParsedPicture> parsed;
+  std::vector<int> parse_rc; std::vector<std::string> parse_msg;
+  DevBuf<PicDesc> pics; DevBuf<CtuInfo> ctus; DevBuf<TuCmd> tus; DevBuf<CoefEntry> coefs; DevBuf<SliceInfo> slices;
+  DevBuf<int8_t> qp8; DevBuf<uint8_t> edge8; DevBuf<uint2> rows; DevBuf<unsigned> sync;   // sync: [0] ticket, [1] error flag, [2..] progress
+  DevBuf<uint8_t> rec; DevBuf<uint8_t> canvas;
+  size_t canvas_off[3] = {0, 0, 0}; size_t canvas_pitch[3] = {0, 0, 0};
+  b200_image_info info{};
+  b200_decode_stats stats{};
+  std::vector<size_t> rec_off; int npics = 0;
+  cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+  cudaStream_t last_stream = nullptr;
+  bool have_result = false;
+  int debug_stage = 0;
+  ~b200_decoder() {
+    delete pool;
+    pics.release(); ctus.release(); tus.release(); coefs.release(); slices.release(); qp8.release(); edge8.release(); rows.release();
+    sync.release(); rec.release(); canvas.release();
+    for (auto& e : ev) if (e) cudaEventDestroy(e);
+  }
+};
+
+static int check_device_error(b200_decoder* d) {
+  unsigned flag = 0;
+  B200_CUDA_CHECK(cudaMemcpy(&flag, d->sync.d + 1, sizeof flag, cudaMemcpyDeviceToHost));
+  if (flag) return set_error(B200_E_CUDA, "reconstruction kernel gave up waiting for a CTB row dependency");
+  return B200_OK;
+}
+
+extern "C" {
+
+int b200_decoder_create(b200_decoder** out, int host_threads) {
+  if (!out) return set_error(B200_E_INVALID, "null argument");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return set_error(B200_E_CUDA, "no CUDA device: libb200heif has no CPU fallback");
+  if (host_threads <= 0) { long n = sysconf(_SC_NPROCESSORS_ONLN); host_threads = n > 0 ? (int)n : 1; }
+  b200_decoder* d = new b200_decoder;
+  d->pool = new Pool(host_threads);
+  for (auto& e : d->ev) if (cudaEventCreate(&e) != cudaSuccess) { delete d; return set_error(B200_E_CUDA, "cudaEventCreate failed"); }
+  *out = d;
+  return B200_OK;
+}
+
+void b200_decoder_destroy(b200_decoder* d) { delete d; }
+
+int b200_decoder_set_debug_stage(b200_decoder* d, int stage) { if (!d) return B200_E_INVALID; d->debug_stage = stage; return B200_OK; }
+
+int b200_decoder_decode_grid(b200_decoder* d, int cols, int rows, const uint8_t* const* au, const size_t* au_size,
+                             uint64_t max_pixels, int canvas_w, int canvas_h, b200_image_info* info, void* stream_) {
+  if (!d || !au || !au_size || cols <= 0 || rows <= 0) return set_error(B200_E_INVALID, "bad argument");
+  cudaStream_t s = (cudaStream_t)stream_;
+  const int n = cols * rows;
+  const double t0 = now_ms();
+  d->have_result = false;
+  d->parsed.resize((size_t)n); d->parse_rc.assign((size_t)n, 0); d->parse_msg.assign((size_t)n, std::string());
+  ParseLimits lim; lim.max_image_size_pixels = max_pixels;
+  // ---- 1. host front-end: one tile per task (CABAC is serial per sub-stream, tiles are independent)
+  d->pool->parallel_for(n, [&](int i) {
+    int rc = parse_access_unit(au[i], au_size[i], lim, d->parsed[(size_t)i]);
+    d->parse_rc[(size_t)i] = rc;
+    if (rc) d->parse_msg[(size_t)i] = b200_last_error();
+  });
+  for (int i = 0; i < n; i++) if (d->parse_rc[(size_t)i]) return set_error(d->parse_rc[(size_t)i], "tile %d: %s", i, d->parse_msg[(size_t)i].c_str());
+  const double t1 = now_ms();
+  // ---- 2. layout
+  const PicDesc& p0 = d->parsed[0].desc;
+  const int tw = p0.out_w, th = p0.out_h, bd = p0.bit_depth, chroma = p0.chroma, bps = bd > 8 ? 2 : 1;
+  for (int i = 1; i < n; i++) {
+    const PicDesc& p = d->parsed[(size_t)i].desc;
+    if (p.out_w != tw || p.out_h != th || p.bit_depth != bd || p.chroma != chroma)
+      return set_error(B200_E_UNSUPPORTED, "grid tiles differ in size or format (tile %d)", i);   // grid.cc:261-375 requires equal tiles
+  }
+  if (chroma && ((tw | th) & 1) && n > 1) return set_error(B200_E_UNSUPPORTED, "odd-sized 4:2:0 grid tiles");
+  const int cw = canvas_w > 0 ? canvas_w : tw * cols, chh = canvas_h > 0 ? canvas_h : th * rows;
+  size_t n_ctu = 0, n_tu = 0, n_coef = 0, n_slice = 0, n_map = 0, n_rows = 0, rec_bytes = 0, bits = 0;
+  d->rec_off.resize((size_t)n * 3);
+  for (int i = 0; i < n; i++) {
+    ParsedPicture& pp = d->parsed[(size_t)i]; PicDesc& p = pp.desc;
+    p.ctu_base = (uint32_t)n_ctu; p.tu_base = (uint32_t)n_tu; p.coef_base = n_coef; p.slice_base = (uint32_t)n_slice; p.map8_base = (uint32_t)n_map;
+    p.progress_base = (uint32_t)n_rows;
+    n_ctu += pp.ctus.size(); n_tu += pp.tus.size(); n_coef += pp.coefs.size(); n_slice += pp.slices.size(); n_map += pp.qp8.size(); n_rows += (size_t)p.hctb;
+    bits += au_size[i];
+    for (int c = 0; c < (chroma ? 3 : 1); c++) {
+      const int w = c ? p.width >> 1 : p.width, h = c ? p.height >> 1 : p.height;
+      const int st = (w + 63) & ~63;
+      p.rec_stride[c] = st;
+      d->rec_off[(size_t)i * 3 + c] = rec_bytes;
+      rec_bytes += (size_t)st * h * bps; rec_bytes = (rec_bytes + 255) & ~(size_t)255;
+    }
+  }
+  if (n_tu > 0xffffffffull) return set_error(B200_E_UNSUPPORTED, "batch too large");
+  int rc;
+  if ((rc = d->pics.reserve((size_t)n)) || (rc = d->ctus.reserve(n_ctu)) || (rc = d->tus.reserve(n_tu)) || (rc = d->coefs.reserve(n_coef + 1)) ||
+      (rc = d->slices.reserve(n_slice)) || (rc = d->qp8.reserve(n_map)) || (rc = d->edge8.reserve(n_map)) || (rc = d->rows.reserve(n_rows)) ||
+      (rc = d->sync.reserve(n_rows + 2, false)) || (rc = d->rec.reserve(rec_bytes, false)))
+    return rc;
+  // canvas planes
+  size_t cbytes = 0;
+  for (int c = 0; c < (chroma ? 3 : 1); c++) {
+    const int w = c ? (cw + 1) >> 1 : cw, h = c ? (chh + 1) >> 1 : chh;
+    d->canvas_pitch[c] = (((size_t)w * bps) + 255) & ~(size_t)255;
+    d->canvas_off[c] = cbytes; cbytes += d->canvas_pitch[c] * h;
+  }
+  const bool canvas_fully_covered = tw * cols >= cw && th * rows >= chh;
+  if ((rc = d->canvas.reserve(cbytes, false))) return rc;
+  // ---- 3. pack into pinned staging (parallel) and fix up device pointers
+  size_t row_cursor = 0;
+  for (int i = 0; i < n; i++) {
+    ParsedPicture& pp = d->parsed[(size_t)i]; PicDesc& p = pp.desc;
+    const int col = i % cols, row = i / cols;
+    const int px = col * tw, py = row * th;
+    p.out_w = std::max(0, std::min(tw, cw - px)); p.out_h = std::max(0, std::min(th, chh - py));     // clip like copy_image_to
+    for (int c = 0; c < 3; c++) {
+      if (c && !chroma) { p.rec[c] = nullptr; p.dst[c] = nullptr; continue; }
+      p.rec[c] = d->rec.d + d->rec_off[(size_t)i * 3 + c];
+      const int sx = c ? px >> 1 : px, sy = c ? py >> 1 : py;
+      p.dst[c] = d->canvas.d + d->canvas_off[c] + (size_t)sy * d->canvas_pitch[c] + (size_t)sx * bps;
+      p.dst_stride[c] = (int)(d->canvas_pitch[c] / bps);
+    }
+    for (int r = 0; r < p.hctb; r++) d->rows.h[row_cursor++] = make_uint2((unsigned)i, (unsigned)r);
+    d->pics.h[i] = p;
+  }
+  d->pool->parallel_for(n, [&](int i) {
+    const ParsedPicture& pp = d->parsed[(size_t)i]; const PicDesc& p = pp.desc;
+    memcpy(d->ctus.h + p.ctu_base, pp.ctus.data(), pp.ctus.size() * sizeof(CtuInfo));
+    memcpy(d->tus.h + p.tu_base, pp.tus.data(), pp.tus.size() * sizeof(TuCmd));
+    memcpy(d->coefs.h + p.coef_base, pp.coefs.data(), pp.coefs.size() * sizeof(CoefEntry));
+    memcpy(d->slices.h + p.slice_base, pp.slices.data(), pp.slices.size() * sizeof(SliceInfo));
+    memcpy(d->qp8.h + p.map8_base, pp.qp8.data(), pp.qp8.size());
+    memcpy(d->edge8.h + p.map8_base, pp.edge8.data(), pp.edge8.size());
+  });
+  const double t2 = now_ms();
+  // ---- 4. H2D + kernels
+  cudaEventRecord(d->ev[0], s);
+  B200_CUDA_CHECK(cudaMemcpyAsync(d->pics.d, d->pics.h, (size_t)n * sizeof(PicDesc), cudaMemcpyHostToDevice, s));
+  B200_CUDA_CHECK(cudaMemcpyAsync(d->ctus.d, d->ctus.h, n_ctu * sizeof(CtuInfo), cudaMemcpyHostToDevice, s));
+  B200_CUDA_CHECK(cudaMemcpyAsync(d->tus.d, d->tus.h, n_tu * sizeof(TuCmd), cudaMemcpyHostToDevice, s));
+  B200_CUDA_CHECK(cudaMemcpyAsync(d->coefs.d, d->coefs.h, n_coef * sizeof(CoefEntry), cudaMemcpyHostToDevice, s));
+  B200_CUDA_CHECK(cudaMemcpyAsync(d->slices.d, d->slices.h, n_slice * sizeof(SliceInfo), cudaMemcpyHostToDevice, s));
+  B200_CUDA_CHECK(cudaMemcpyAsync(d->qp8.d, d->qp8.h, n_map, cudaMemcpyHostToDevice, s));
+  B200_CUDA_CHECK(cudaMemcpyAsync(d->edge8.d, d->edge8.h, n_map, cudaMemcpyHostToDevice, s));
+  B200_CUDA_CHECK(cudaMemcpyAsync(d->rows.d, d->rows.h, n_rows * sizeof(uint2), cudaMemcpyHostToDevice, s));
+  B200_CUDA_CHECK(cudaMemsetAsync(d->sync.d, 0, (n_rows + 2) * sizeof(unsigned), s));
+  if (!canvas_fully_covered) B200_CUDA_CHECK(cudaMemsetAsync(d->canvas.d, 0, cbytes, s));     // uncovered canvas stays zero (calloc in the reference)
+  cudaEventRecord(d->ev[1], s);
+  DeviceBatch b{};
+  b.pics = d->pics.d; b.npics = n; b.ctus = d->ctus.d; b.tus = d->tus.d; b.coefs = d->coefs.d; b.slices = d->slices.d;
+  b.qp8 = d->qp8.d; b.edge8 = d->edge8.d; b.ticket = d->sync.d; b.error_flag = d->sync.d + 1; b.progress = d->sync.d + 2; b.row_list = d->rows.d; b.nrows = (int)n_rows;
+  if ((rc = launch_recon(b, s))) return rc;
+  cudaEventRecord(d->ev[2], s);
+  int launches = 1;
+  if (d->debug_stage != 1) { if ((rc = launch_deblock(b, d->pics.h, s))) return rc; launches += 2; }
+  cudaEventRecord(d->ev[3], s);
+  if (d->debug_stage == 0) { if ((rc = launch_sao(b, d->pics.h, s))) return rc; launches += 1; }
+  cudaEventRecord(d->ev[4], s);
+  d->npics = n; d->last_stream = s; d->have_result = true;
+  b200_image_info& inf = d->info;
+  inf.width = cw; inf.height = chh; inf.tile_width = tw; inf.tile_height = th; inf.chroma = chroma ? B200_CHROMA_420 : B200_CHROMA_MONO; inf.bit_depth = bd;
+  inf.colour_primaries = d->parsed[0].colour_primaries; inf.transfer_characteristics = d->parsed[0].transfer_characteristics;
+  inf.matrix_coefficients = d->parsed[0].matrix_coefficients; inf.full_range = d->parsed[0].full_range;
+  if (info) *info = inf;
+  b200_decode_stats& st = d->stats;
+  memset(&st, 0, sizeof st);
+  st.parse_ms = t1 - t0; st.pack_ms = t2 - t1; st.total_ms = now_ms() - t0;
+  st.bitstream_bytes = bits; st.coefficient_entries = n_coef; st.transform_units = n_tu; st.ctus = n_ctu;
+  st.command_bytes = n_ctu * sizeof(CtuInfo) + n_tu * sizeof(TuCmd) + n_coef * sizeof(CoefEntry) + n_slice * sizeof(SliceInfo) + 2 * n_map + (size_t)n * sizeof(PicDesc);
+  st.h2d_bytes = st.command_bytes + n_rows * sizeof(uint2);
+  st.pixels = (uint64_t)cw * chh; st.kernel_launches = launches;
+  return B200_OK;
+}
+
+int b200_decoder_get_stats(b200_decoder* d, b200_decode_stats* out) {
+  if (!d || !out || !d->have_result) return set_error(B200_E_INVALID, "no decode result");
+  B200_CUDA_CHECK(cudaEventSynchronize(d->ev[4]));
+  float a = 0, b = 0, c = 0, e = 0;
+  cudaEventElapsedTime(&a, d->ev[0], d->ev[1]); cudaEventElapsedTime(&b, d->ev[1], d->ev[2]);
+  cudaEventElapsedTime(&c, d->ev[2], d->ev[3]); cudaEventElapsedTime(&e, d->ev[3], d->ev[4]);
+  d->stats.h2d_ms = a; d->stats.recon_ms = b; d->stats.deblock_ms = c; d->stats.sao_ms = e; d->stats.gpu_ms = b + c + e;
+  *out = d->stats;
+  return B200_OK;
+}
+
+int b200_decoder_get_planes(b200_decoder* d, b200_planes* out) {
+  if (!d || !out || !d->have_result) return set_error(B200_E_INVALID, "no decode result");
+  memset(out, 0, sizeof *out);
+  out->y = d->canvas.d + d->canvas_off[0]; out->y_stride = d->canvas_pitch[0];
+  if (d->info.chroma != B200_CHROMA_MONO) { out->cb = d->canvas.d + d->canvas_off[1]; out->cr = d->canvas.d + d->canvas_off[2]; out->c_stride = d->canvas_pitch[1]; }
+  out->width = d->info.width; out->height = d->info.height; out->chroma = d->info.chroma; out->bit_depth = d->info.bit_depth;
+  out->colour_primaries = d->info.colour_primaries; out->transfer_characteristics = d->info.transfer_characteristics;
+  out->matrix_coefficients = d->info.matrix_coefficients; out->full_range = d->info.full_range;
+  return B200_OK;
+}
+
+int b200_decoder_read_planes(b200_decoder* d, void* y, size_t ys, void* cb, void* cr, size_t cs, void* stream_) {
+  if (!d || !y || !d->have_result) return set_error(B200_E_INVALID, "no decode result");
+  cudaStream_t s = (cudaStream_t)stream_;
+  const int bps = d->info.bit_depth > 8 ? 2 : 1, w = d->info.width, h = d->info.height;
+  B200_CUDA_CHECK(cudaMemcpy2DAsync(y, ys, d->canvas.d + d->canvas_off[0], d->canvas_pitch[0], (size_t)w * bps, h, cudaMemcpyDeviceToHost, s));
+  if (d->info.chroma != B200_CHROMA_MONO && cb && cr) {
+    const int cw = (w + 1) >> 1, ch = (h + 1) >> 1;
+    B200_CUDA_CHECK(cudaMemcpy2DAsync(cb, cs, d->canvas.d + d->canvas_off[1], d->canvas_pitch[1], (size_t)cw * bps, ch, cudaMemcpyDeviceToHost, s));
+    B200_CUDA_CHECK(cudaMemcpy2DAsync(cr, cs, d->canvas.d + d->canvas_off[2], d->canvas_pitch[2], (size_t)cw * bps, ch, cudaMemcpyDeviceToHost, s));
+  }
+  B200_CUDA_CHECK(cudaStreamSynchronize(s));
+  return check_device_error(d);
+}
+
+int b200_decoder_debug_read_tile(b200_decoder* d, int index, int stage, void* y, void* cb, void* cr) {
+  if (!d || !d->have_result || index < 0 || index >= d->npics) return set_error(B200_E_INVALID, "bad tile index");
+  (void)stage;
+  const PicDesc& p = d->pics.h[index];
+  const int bps = p.bit_depth > 8 ? 2 : 1;
+  void* outs[3] = {y, cb, cr};
+  B200_CUDA_CHECK(cudaStreamSynchronize(d->last_stream));
+  for (int c = 0; c < (p.chroma ? 3 : 1); c++) {
+    if (!outs[c]) continue;
+    const int w = c ? p.width >> 1 : p.width, h = c ? p.height >> 1 : p.height;
+    B200_CUDA_CHECK(cudaMemcpy2D(outs[c], (size_t)w * bps, p.rec[c], (size_t)p.rec_stride[c] * bps, (size_t)w * bps, h, cudaMemcpyDeviceToHost));
+  }
+  return B200_OK;
+}
+
+int b200_decode_grid_to_rgb_host(b200_decoder* d, int cols, int rows, const uint8_t* const* au, const size_t* au_size,
+                                 uint64_t max_pixels, int canvas_w, int canvas_h, const b200_geometry* geom,
+                                 const b200_color_options* opt, void* out, size_t out_stride, b200_image_info* info) {
+  if (!d || !opt || !out) return set_error(B200_E_INVALID, "null argument");
+  b200_image_info inf;
+  int rc = b200_decoder_decode_grid(d, cols, rows, au, au_size, max_pixels, canvas_w, canvas_h, &inf, nullptr);
+  if (rc) return rc;
+  if (info) *info = inf;
+  b200_planes pl; if ((rc = b200_decoder_get_planes(d, &pl))) return rc;
+  b200_geometry g; if (geom) g = *geom; else b200_geometry_identity(inf.width, inf.height, &g);
+  size_t bpp;
+  switch (opt->out_chroma) {
+    case B200_CHROMA_INTERLEAVED_RGB: bpp = 3; break; case B200_CHROMA_INTERLEAVED_RGBA: bpp = 4; break;
+    case B200_CHROMA_INTERLEAVED_RRGGBB_BE: case B200_CHROMA_INTERLEAVED_RRGGBB_LE: bpp = 6; break;
+    case B200_CHROMA_INTERLEAVED_RRGGBBAA_BE: case B200_CHROMA_INTERLEAVED_RRGGBBAA_LE: bpp = 8; break;
+    default: return set_error(B200_E_UNSUPPORTED, "b200_decode_grid_to_rgb_host needs an interleaved target");
+  }
+  const size_t rowb = (size_t)g.out_w * bpp, pitch = (rowb + 255) & ~(size_t)255;
+  static thread_local DevBuf<uint8_t> rgb;
+  if ((rc = rgb.reserve(pitch * g.out_h, false))) return rc;
+  if ((rc = b200_color_convert_device(&pl, &g, opt, rgb.d, nullptr, nullptr, pitch, nullptr, nullptr))) return rc;
+  B200_CUDA_CHECK(cudaMemcpy2D(out, out_stride, rgb.d, pitch, rowb, g.out_h, cudaMemcpyDeviceToHost));
+  return check_device_error(d);
+}
+
+}  // extern "C"
+
+// Host-only introspection of the front-end (no CUDA involved): lets tests pin the CABAC/syntax layer on machines
+// without a GPU.  Outputs: per 8x8 block QpY / filterEdgeFlags, per 4x4 block luma and chroma intra mode, and
+// {order-independent coefficient hash, coefficient count, TU count, W, H}.
+extern "C" int b200_debug_parse(const uint8_t* au, size_t size, int8_t* qp8, uint8_t* edge8, uint8_t* lmode4, uint8_t* cmode4,
+                                unsigned long long* out5) {
+  ParsedPicture pp; ParseLimits lim;
+  int rc = parse_access_unit(au, size, lim, pp);
+  if (rc) return rc;
+  const PicDesc& p = pp.desc;
+  const int w4 = p.width >> 2;
+  memcpy(qp8, pp.qp8.data(), pp.qp8.size()); memcpy(edge8, pp.edge8.data(), pp.edge8.size());
+  unsigned long long hash = 0;
+  for (const TuCmd& t : pp.tus) {
+    const int x4 = t.w0 & 0xfff, y4 = (t.w0 >> 12) & 0xfff, log2n = 2 + ((t.w0 >> 24) & 3), n4 = 1 << (log2n - 2);
+    const int lm = t.w1 & 63, cm = (t.w1 >> 6) & 63;
+    for (int y = 0; y < n4; y++) for (int x = 0; x < n4; x++) { lmode4[(size_t)(y4 + y) * w4 + x4 + x] = (uint8_t)lm; cmode4[(size_t)(y4 + y) * w4 + x4 + x] = (uint8_t)cm; }
+    const int nl = ((t.w0 >> 26) & 1) ? (int)(t.w3 & 0x7ff) : 0, ncb = ((t.w0 >> 27) & 1) ? (int)((t.w3 >> 11) & 0x3ff) : 0, ncr = ((t.w0 >> 28) & 1) ? (int)((t.w3 >> 21) & 0x3ff) : 0;
+    const CoefEntry* ce = pp.coefs.data() + t.w2;
+    int cx = x4 << 2, cy = y4 << 2;
+    if (log2n == 2) { cx -= 4; cy -= 4; }     // chroma of the parent 8x8 node
+    for (int k = 0; k < nl + ncb + ncr; k++) {
+      const int c = k < nl ? 0 : (k < nl + ncb ? 1 : 2);
+      const unsigned long long bx = c ? (unsigned long long)cx : (unsigned long long)(x4 << 2), by = c ? (unsigned long long)cy : (unsigned long long)(y4 << 2);
+      unsigned long long hh = (bx * 1000003ULL + by) * 1000003ULL + (unsigned long long)c;
+      hh = hh * 1000003ULL + ce[k].pos; hh = hh * 1000003ULL + (unsigned long long)(unsigned short)ce[k].level;
+      hh ^= hh >> 29; hh *= 0x9E3779B97F4A7C15ULL; hash += hh;
+    }
+  }
+  out5[0] = hash; out5[1] = pp.coefs.size(); out5[2] = pp.tus.size(); out5[3] = (unsigned long long)p.width; out5[4] = (unsigned long long)p.height;
+  return B200_OK;
+}

@@ -360,6 +360,8 @@ typedef struct {
   int cur_qpy;
   int picture_started;
   int err;
+  unsigned long long coef_hash, coef_count, tu_count;   /* debug: order-independent digest of the parsed levels */
+  uint8_t* cmode4;                                      /* debug: chroma mode per 4x4 */
 } dec_t;
 
 /* ------------------------------------------------------------------------------------------ CABAC */
@@ -709,6 +711,7 @@ static void residual_coding(dec_t* d, int x0, int y0, int log2n, int c, int pred
       if (sign_hidden) { sum_abs += absl; if (k == first_sig && (sum_abs & 1)) v = -v; }
       int xc = (xs << 2) + px[k], yc = (ys << 2) + py[k];
       coef[yc * n + xc] = (int16_t)clip3(-32768, 32767, v);
+      { unsigned long long hh = ((unsigned long long)(x0 << (c ? 1 : 0)) * 1000003ULL + (unsigned long long)(y0 << (c ? 1 : 0))) * 1000003ULL + (unsigned long long)c; hh = hh * 1000003ULL + (unsigned long long)(yc * n + xc); hh = hh * 1000003ULL + (unsigned long long)(unsigned short)coef[yc * n + xc]; hh ^= hh >> 29; hh *= 0x9E3779B97F4A7C15ULL; d->coef_hash += hh; d->coef_count++; }
       nsig++;
     }
   }
@@ -776,6 +779,8 @@ static void transform_unit(dec_t* d, cu_t* cu, int x0, int y0, int xb, int yb, i
   }
   int pu = cu->part_nxn ? ((y0 >= cu->y0 + (1 << (cu->log2cb - 1))) ? 2 : 0) + ((x0 >= cu->x0 + (1 << (cu->log2cb - 1))) ? 1 : 0) : 0;
   int lmode = cu->luma_mode[pu];
+  d->tu_count++;
+  { int n4 = 1 << (log2n - 2); for (int yy = 0; yy < n4; yy++) for (int xx = 0; xx < n4; xx++) d->cmode4[((y0 >> 2) + yy) * d->w4 + (x0 >> 2) + xx] = (uint8_t)cu->chroma_mode; }
   /* luma: 8.4.4.1 predict, then residual */
   intra_predict(d, 0, x0, y0, log2n, lmode);
   if (cbf_luma) residual_coding(d, x0, y0, log2n, 0, lmode);
@@ -984,6 +989,7 @@ static int alloc_picture(dec_t* d) {
   d->slice_of4 = (uint16_t*)calloc(n4, 2);
   d->ipm4 = (uint8_t*)calloc(n4, 1); d->qp4 = (int8_t*)calloc(n4, 1);
   d->tu_edge4 = (uint8_t*)calloc(n4, 1); d->cd4 = (uint8_t*)calloc(n4, 1);
+  d->cmode4 = (uint8_t*)calloc(n4, 1);
   d->sao = (sao_params*)calloc((size_t)d->wctb * d->hctb, sizeof(sao_params));
   d->ctb_slice_sao = (uint8_t*)calloc((size_t)d->wctb * d->hctb, 1);
   d->nslices = 0;
@@ -1232,7 +1238,7 @@ static void sao_picture(dec_t* d) {
 /* --------------------------------------------------------------------------------------- top level */
 static void free_dec(dec_t* d) {
   for (int c = 0; c < 3; c++) free(d->pl[c]);
-  free(d->slice_of4); free(d->ipm4); free(d->qp4); free(d->tu_edge4); free(d->cd4); free(d->sao); free(d->ctb_slice_sao);
+  free(d->cmode4); free(d->slice_of4); free(d->ipm4); free(d->qp4); free(d->tu_edge4); free(d->cd4); free(d->sao); free(d->ctb_slice_sao);
 }
 
 void hevc_oracle_free_picture(hevc_oracle_picture* p) { for (int c = 0; c < 3; c++) { free(p->plane[c]); p->plane[c] = NULL; } }
@@ -1322,5 +1328,44 @@ int hevc_oracle_parse_vui(const uint8_t* data, size_t size, int out[4]) {
     p += n;
   }
   free(rbsp);
+  return rc;
+}
+
+/* Debug digest of the syntax-level decoding state, used by tests/test_parser.py to pin the product's host front-end
+   (which emits a command stream instead of pixels) without a GPU: per 8x8 block QpY and filterEdgeFlags, per 4x4 block
+   luma / chroma intra mode, and an order-independent hash over every parsed coefficient level. */
+int hevc_oracle_debug_maps(const uint8_t* data, size_t size, int8_t* qp8, uint8_t* edge8, uint8_t* lmode4, uint8_t* cmode4,
+                           unsigned long long* out3 /* hash, coef count, tu count */, int* dims /* W, H */) {
+  init_scans();
+  dec_t* d = (dec_t*)calloc(1, sizeof(dec_t));
+  uint8_t* rbsp = (uint8_t*)malloc(size + 16);
+  int rc = HO_OK; size_t p = 0;
+  while (p + 4 <= size && rc == HO_OK) {
+    uint32_t n = ((uint32_t)data[p] << 24) | (data[p + 1] << 16) | (data[p + 2] << 8) | data[p + 3];
+    p += 4;
+    if (n > size - p) { rc = HO_ERROR; break; }
+    if (n >= 2) {
+      int type = (data[p] >> 1) & 0x3f;
+      size_t rn = nal_to_rbsp(data + p, n, rbsp);
+      memset(rbsp + rn, 0, 8);
+      if (type == 33) { sps_t s; rc = parse_sps(rbsp, rn, &s); if (rc == HO_OK) { bitrd b = {rbsp, rn, 16}; rd_bits(&b, 4); int msl = rd_bits(&b, 3); rd_bit(&b); skip_profile_tier_level(&b, msl); unsigned id = rd_ue(&b); if (id < 16) d->sps[id] = s; } }
+      else if (type == 34) { pps_t pp; rc = parse_pps(rbsp, rn, &pp); if (rc == HO_OK) { bitrd b = {rbsp, rn, 16}; unsigned id = rd_ue(&b); if (id < 64) d->pps[id] = pp; } }
+      else if (type >= 16 && type <= 21) rc = decode_slice(d, rbsp, rn, type);
+    }
+    p += n;
+  }
+  if (rc == HO_OK && d->picture_started) {
+    dims[0] = d->W; dims[1] = d->H;
+    int w8 = d->W >> 3, h8 = d->H >> 3;
+    for (int by = 0; by < h8; by++) for (int bx = 0; bx < w8; bx++) {
+      qp8[by * w8 + bx] = d->qp4[(by * 2) * d->w4 + bx * 2];
+      edge8[by * w8 + bx] = (uint8_t)((edge_filtered(d, bx * 8, by * 8, 1) ? 1 : 0) | (edge_filtered(d, bx * 8, by * 8, 0) ? 2 : 0));
+    }
+    memcpy(lmode4, d->ipm4, (size_t)d->w4 * d->h4);
+    memcpy(cmode4, d->cmode4, (size_t)d->w4 * d->h4);
+    out3[0] = d->coef_hash; out3[1] = d->coef_count; out3[2] = d->tu_count;
+  } else if (rc == HO_OK) rc = HO_ERROR;
+  if (d->picture_started) free_dec(d);
+  free(d); free(rbsp);
   return rc;
 }

@@ -1,0 +1,63 @@
+"""Shared list of HEVC streams for the parser / decoder parity tests: the reference's own fixtures (harvested
+through oracle/ref_plugin.cc's dump hook from examples/example.heic, tests/data/rainbow-451x461.heic and
+fuzzing/data/corpus/*.heic) plus synthetic streams from the product's encoder covering every supported tool."""
+import glob
+import os
+
+from libheif_b200 import hevc_enc
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def fixture_streams():
+    out = []
+    for f in sorted(glob.glob(os.path.join(HERE, "golden", "streams", "*.au"))):
+        out.append((os.path.basename(f), open(f, "rb").read()))
+    return out
+
+
+# (name, width, height, bit_depth, chroma, encoder options)
+SYNTH = [
+    ("ctb16_basic", 64, 64, 8, True, dict(log2_ctb_size=4)),
+    ("ctb16_nofilters", 64, 64, 8, True, dict(log2_ctb_size=4, sao=0, cu_qp_delta=0, sign_data_hiding=0, deblocking_disabled=1)),
+    ("ctb32", 128, 96, 8, True, dict(log2_ctb_size=5)),
+    ("ctb64", 256, 256, 8, True, dict(log2_ctb_size=6)),
+    ("ctb16_wpp_nosao", 200, 120, 8, True, dict(log2_ctb_size=4, wpp=1, sao=0)),
+    ("ctb32_wpp_deep", 200, 120, 8, True, dict(log2_ctb_size=5, wpp=1, max_transform_hierarchy_depth_intra=3)),
+    ("ctb64_wpp_random", 264, 200, 8, True, dict(log2_ctb_size=6, wpp=1, mode_decision=0)),
+    ("slices", 256, 192, 8, True, dict(log2_ctb_size=5, slice_ctb_rows=2)),
+    ("slices_nolf", 256, 192, 8, True, dict(log2_ctb_size=5, slice_ctb_rows=2, slice_loop_filter_across_slices=0)),
+    ("dependent_slices", 256, 192, 8, True, dict(log2_ctb_size=5, slice_ctb_rows=3, dependent_slice_segments=1)),
+    ("slices_wpp", 256, 192, 8, True, dict(log2_ctb_size=5, slice_ctb_rows=2, wpp=1)),
+    ("main10", 160, 160, 10, True, dict(log2_ctb_size=5)),
+    ("main12_wpp", 160, 160, 12, True, dict(log2_ctb_size=6, wpp=1)),
+    ("mono8", 160, 96, 8, False, dict(log2_ctb_size=5)),
+    ("mono10_ctb16_wpp", 160, 96, 10, False, dict(log2_ctb_size=4, wpp=1)),
+    ("transform_skip", 128, 128, 8, True, dict(log2_ctb_size=5, transform_skip=1, mode_decision=0)),
+    ("chroma_qp_offsets", 128, 128, 8, True, dict(log2_ctb_size=5, cb_qp_offset=3, cr_qp_offset=-4, slice_chroma_qp_offsets=1, slice_cb_qp_offset=-2, slice_cr_qp_offset=5)),
+    ("deblock_offsets", 128, 128, 8, True, dict(log2_ctb_size=5, beta_offset_div2=2, tc_offset_div2=-3)),
+    ("deblock_slice_override", 128, 128, 8, True, dict(log2_ctb_size=5, slice_deblocking_override=1, slice_beta_offset_div2=-4, slice_tc_offset_div2=5, slice_ctb_rows=2)),
+    ("deblock_slice_disabled", 128, 128, 8, True, dict(log2_ctb_size=5, slice_deblocking_override=1, slice_deblocking_disabled=1)),
+    ("odd_size_random", 130, 70, 8, True, dict(log2_ctb_size=5, mode_decision=0, max_transform_hierarchy_depth_intra=2)),
+    ("big_qp22", 1000, 600, 8, True, dict(log2_ctb_size=6, wpp=1, qp=22, dqp_range=6, diff_cu_qp_delta_depth=2)),
+    ("big_qp37_vui", 1000, 600, 8, True, dict(log2_ctb_size=5, qp=37, strong_intra_smoothing=0, vui_present=1, colour_description_present=1,
+                                              colour_primaries=1, transfer_characteristics=13, matrix_coefficients=6, full_range=1)),
+    ("lowqp_deep", 72, 40, 8, True, dict(log2_ctb_size=6, qp=10, dqp_range=10, mode_decision=0, max_transform_hierarchy_depth_intra=4)),
+    ("highqp", 72, 40, 8, True, dict(log2_ctb_size=6, qp=48, dqp_range=3, mode_decision=0)),
+    ("tile_1024_like", 512, 512, 8, True, dict(log2_ctb_size=5, qp=27, wpp=1)),
+]
+
+_cache = {}
+
+
+def synth_stream(name):
+    if name not in _cache:
+        for (nm, w, h, bd, chroma, opts) in SYNTH:
+            if nm == name:
+                y, cb, cr = hevc_enc.synthetic_image(0xB200 + w + h, w, h, bd, chroma)
+                _cache[name] = hevc_enc.encode_intra(y, cb, cr, bit_depth=bd, **opts)
+    return _cache[name]
+
+
+def all_streams():
+    return fixture_streams() + [(s[0], synth_stream(s[0])) for s in SYNTH]

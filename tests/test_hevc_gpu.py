@@ -1,0 +1,106 @@
+"""GPU parity: the sm_100a HEVC intra decoder (host front-end + reconstruction / deblocking / SAO kernels, through the
+C ABI) vs the C restatement (oracle/hevc_oracle.c, pinned on FFmpeg) -- bit-exact on every plane, every stream,
+including the intermediate stages (before deblocking, after deblocking) to localise mismatches."""
+import hashlib
+
+import numpy as np
+import pytest
+
+import libheif_b200 as lb
+from hevc_cases import SYNTH, all_streams, synth_stream
+from oracle import bindings as ob
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def dec(cuda):
+    d = lb.Decoder(host_threads=8)
+    yield d
+    d.close()
+
+
+@pytest.mark.parametrize("name,au", all_streams(), ids=[s[0] for s in all_streams()])
+def test_single_picture_matches_oracle(dec, name, au):
+    want, info = ob.restatement_decode(au)
+    dec.set_debug_stage(0)
+    i = dec.decode_image(au)
+    got = dec.planes_host()
+    assert (i.width, i.height, i.bit_depth) == (want[0].shape[1], want[0].shape[0], info["bit_depth"])
+    assert (i.colour_primaries, i.transfer_characteristics, i.matrix_coefficients, i.full_range) == (info["cp"], info["tc"], info["mc"], info["full_range"])
+    for c in range(len(want)):
+        assert np.array_equal(got[c], want[c]), f"{name}: plane {c} first diffs {np.argwhere(got[c] != want[c])[:4].tolist()}"
+
+
+@pytest.mark.parametrize("name", ["ctb32", "ctb64_wpp_random", "main10", "slices_nolf", "rainbow_452x462.au"])
+@pytest.mark.parametrize("stage", [1, 2])
+def test_intermediate_stages(dec, name, stage):
+    au = dict(all_streams())[name]
+    want, info = ob.restatement_decode(au, stage)          # cropped to the conformance window
+    dec.set_debug_stage(stage)
+    try:
+        dec.decode_image(au)
+        h, w = want[0].shape
+        cw, ch = (w + 7) & ~7, (h + 7) & ~7
+        got = dec.debug_tile(0, cw, ch)
+        for c in range(len(want)):
+            hh, ww = want[c].shape
+            assert np.array_equal(got[c][:hh, :ww], want[c]), f"stage {stage} plane {c}"
+    finally:
+        dec.set_debug_stage(0)
+
+
+def test_grid_of_tiles_matches_per_tile_oracle(dec):
+    """3x2 grid of independent tiles pasted into one canvas (ImageItem_Grid semantics) incl. a canvas smaller than the
+    tile area (tiles overhanging the right/bottom border are clipped like HeifPixelImage::copy_image_to)."""
+    tiles = []
+    for k in range(6):
+        y, cb, cr = lb.hevc_enc.synthetic_image(0xB200 + k, 128, 64, 8, True)
+        tiles.append(lb.hevc_enc.encode_intra(y, cb, cr, log2_ctb_size=5, wpp=k % 2, seed=0xB200 + k))
+    ref = [ob.restatement_decode(t)[0] for t in tiles]
+    for canvas in [(0, 0), (350, 100)]:
+        i = dec.decode_grid(tiles, cols=3, rows=2, canvas=canvas)
+        got = dec.planes_host()
+        W, H = (384, 128) if canvas == (0, 0) else canvas
+        assert (i.width, i.height) == (W, H)
+        want = [np.zeros((H, W), np.uint16), np.zeros(((H + 1) // 2, (W + 1) // 2), np.uint16), np.zeros(((H + 1) // 2, (W + 1) // 2), np.uint16)]
+        for k in range(6):
+            col, row = k % 3, k // 3
+            for c in range(3):
+                s = 1 if c == 0 else 2
+                x0, y0 = col * 128 // s, row * 64 // s
+                hh, ww = want[c].shape
+                t = ref[k][c][:max(0, hh - y0), :max(0, ww - x0)]
+                want[c][y0:y0 + t.shape[0], x0:x0 + t.shape[1]] = t
+        for c in range(3):
+            assert np.array_equal(got[c], want[c]), f"canvas {canvas} plane {c}"
+
+
+def test_decode_to_rgb_end_to_end(dec):
+    """HEVC tiles (host) -> RGB24 (host) through the fused C-ABI entry; equals restatement planes + colour oracle."""
+    from util import oracle_postprocess
+    au = synth_stream("big_qp37_vui")                      # VUI 1/13/6 full range -> integer colour path
+    planes, info = ob.restatement_decode(au)
+    want, ow, oh = oracle_postprocess(planes[0], planes[1], planes[2], None, 1, 8, (info["cp"], info["tc"], info["mc"], info["full_range"]), [], 10)
+    out = np.empty((oh, ow * 3), np.uint8)
+    dec.decode_grid_to_rgb_host([au], 1, 1, lb.CHROMA_INTERLEAVED_RGB, out=out)
+    assert np.array_equal(out.reshape(-1), want)
+
+
+def test_example_heic_rgb_md5(dec):
+    """BASELINE config 1 / SURVEY Appendix C: examples/example.heic primary item -> RGB24 md5 of the reference
+    (heif_decode_image with the CPU plugin) = 01672ec0cdf97b977628957cd6533dc2."""
+    au = dict(all_streams())["example_primary_1280x854.au"]
+    out = np.empty((854, 1280 * 3), np.uint8)
+    dec.decode_grid_to_rgb_host([au], 1, 1, lb.CHROMA_INTERLEAVED_RGB, out=out)
+    assert hashlib.md5(out.tobytes()).hexdigest() == "01672ec0cdf97b977628957cd6533dc2"
+
+
+def test_unsupported_and_corrupt_streams_fail_cleanly(dec):
+    au = bytearray(synth_stream("ctb32"))
+    with pytest.raises(lb.B200Error):
+        dec.decode_image(bytes(au[:len(au) // 2]))          # truncated slice data
+    with pytest.raises(lb.B200Error):
+        dec.decode_image(synth_stream("ctb64"), max_image_size_pixels=1000)   # security limit (decoder_libde265.cc:189-198)
+    i = dec.decode_image(synth_stream("ctb32"))            # decoder still usable afterwards
+    assert i.width == 128
