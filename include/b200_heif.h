@@ -183,6 +183,8 @@ int b200_decoder_read_planes(b200_decoder* dec, void* y, size_t y_stride, void* 
 int b200_decoder_debug_read_tile(b200_decoder* dec, int index, int stage, void* y, void* cb, void* cr);
 int b200_decoder_set_debug_stage(b200_decoder* dec, int stage /* 0 = full pipeline, 1 = stop after reconstruction, 2 = stop after deblocking */);
 int b200_decoder_get_stats(b200_decoder* dec, b200_decode_stats* out);
+/* Re-launch the device kernels on the command stream already resident in HBM (no host parse, no H2D). */
+int b200_decoder_rerun_device(b200_decoder* dec, void* stream);
 
 /* Fused convenience: decode grid -> geometry -> colour conversion -> interleaved RGB in HOST memory. */
 int b200_decode_grid_to_rgb_host(b200_decoder* dec, int cols, int rows, const uint8_t* const* au, const size_t* au_size,

@@ -83,6 +83,7 @@ struct b200_decoder {
   cudaStream_t last_stream = nullptr;
   bool have_result = false;
   int debug_stage = 0;
+  size_t n_rows = 0, cbytes = 0; bool canvas_fully_covered = true;
   ~b200_decoder() {
     delete pool;
     pics.release(); ctus.release(); tus.release(); coefs.release(); slices.release(); qp8.release(); edge8.release(); rows.release();
@@ -95,6 +96,23 @@ static int check_device_error(b200_decoder* d) {
   unsigned flag = 0;
   B200_CUDA_CHECK(cudaMemcpy(&flag, d->sync.d + 1, sizeof flag, cudaMemcpyDeviceToHost));
   if (flag) return set_error(B200_E_CUDA, "reconstruction kernel gave up waiting for a CTB row dependency");
+  return B200_OK;
+}
+
+// Launches the device half (reconstruction -> deblocking -> SAO/paste) on the command stream currently resident in HBM.
+static int run_device_pipeline(b200_decoder* d, int n, cudaStream_t s, int* launches_out) {
+  int rc;
+  DeviceBatch b{};
+  b.pics = d->pics.d; b.npics = n; b.ctus = d->ctus.d; b.tus = d->tus.d; b.coefs = d->coefs.d; b.slices = d->slices.d;
+  b.qp8 = d->qp8.d; b.edge8 = d->edge8.d; b.ticket = d->sync.d; b.error_flag = d->sync.d + 1; b.progress = d->sync.d + 2; b.row_list = d->rows.d; b.nrows = (int)d->n_rows;
+  if ((rc = launch_recon(b, s))) return rc;
+  cudaEventRecord(d->ev[2], s);
+  int launches = 1;
+  if (d->debug_stage != 1) { if ((rc = launch_deblock(b, d->pics.h, s))) return rc; launches += 2; }
+  cudaEventRecord(d->ev[3], s);
+  if (d->debug_stage == 0) { if ((rc = launch_sao(b, d->pics.h, s))) return rc; launches += 1; }
+  cudaEventRecord(d->ev[4], s);
+  if (launches_out) *launches_out = launches;
   return B200_OK;
 }
 
@@ -213,17 +231,10 @@ int b200_decoder_decode_grid(b200_decoder* d, int cols, int rows, const uint8_t*
   B200_CUDA_CHECK(cudaMemcpyAsync(d->rows.d, d->rows.h, n_rows * sizeof(uint2), cudaMemcpyHostToDevice, s));
   B200_CUDA_CHECK(cudaMemsetAsync(d->sync.d, 0, (n_rows + 2) * sizeof(unsigned), s));
   if (!canvas_fully_covered) B200_CUDA_CHECK(cudaMemsetAsync(d->canvas.d, 0, cbytes, s));     // uncovered canvas stays zero (calloc in the reference)
+  d->n_rows = n_rows; d->cbytes = cbytes; d->canvas_fully_covered = canvas_fully_covered;
   cudaEventRecord(d->ev[1], s);
-  DeviceBatch b{};
-  b.pics = d->pics.d; b.npics = n; b.ctus = d->ctus.d; b.tus = d->tus.d; b.coefs = d->coefs.d; b.slices = d->slices.d;
-  b.qp8 = d->qp8.d; b.edge8 = d->edge8.d; b.ticket = d->sync.d; b.error_flag = d->sync.d + 1; b.progress = d->sync.d + 2; b.row_list = d->rows.d; b.nrows = (int)n_rows;
-  if ((rc = launch_recon(b, s))) return rc;
-  cudaEventRecord(d->ev[2], s);
-  int launches = 1;
-  if (d->debug_stage != 1) { if ((rc = launch_deblock(b, d->pics.h, s))) return rc; launches += 2; }
-  cudaEventRecord(d->ev[3], s);
-  if (d->debug_stage == 0) { if ((rc = launch_sao(b, d->pics.h, s))) return rc; launches += 1; }
-  cudaEventRecord(d->ev[4], s);
+  int launches = 0;
+  if ((rc = run_device_pipeline(d, n, s, &launches))) return rc;
   d->npics = n; d->last_stream = s; d->have_result = true;
   b200_image_info& inf = d->info;
   inf.width = cw; inf.height = chh; inf.tile_width = tw; inf.tile_height = th; inf.chroma = chroma ? B200_CHROMA_420 : B200_CHROMA_MONO; inf.bit_depth = bd;
@@ -238,6 +249,18 @@ int b200_decoder_decode_grid(b200_decoder* d, int cols, int rows, const uint8_t*
   st.h2d_bytes = st.command_bytes + n_rows * sizeof(uint2);
   st.pixels = (uint64_t)cw * chh; st.kernel_launches = launches;
   return B200_OK;
+}
+
+// Re-run only the device kernels on the already uploaded command stream ("inputs resident in HBM" timing leg).
+int b200_decoder_rerun_device(b200_decoder* d, void* stream_) {
+  if (!d || !d->have_result) return set_error(B200_E_INVALID, "no decode result");
+  cudaStream_t s = (cudaStream_t)stream_;
+  B200_CUDA_CHECK(cudaMemsetAsync(d->sync.d, 0, (d->n_rows + 2) * sizeof(unsigned), s));
+  cudaEventRecord(d->ev[1], s);
+  int launches = 0;
+  int rc = run_device_pipeline(d, d->npics, s, &launches);
+  d->last_stream = s;
+  return rc;
 }
 
 int b200_decoder_get_stats(b200_decoder* d, b200_decode_stats* out) {

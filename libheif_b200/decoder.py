@@ -38,6 +38,7 @@ def _bind(l):
     l.b200_decoder_debug_read_tile.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
     l.b200_decoder_set_debug_stage.argtypes = [C.c_void_p, C.c_int]
     l.b200_decoder_get_stats.argtypes = [C.c_void_p, C.POINTER(DecodeStats)]
+    l.b200_decoder_rerun_device.argtypes = [C.c_void_p, C.c_void_p]
     l.b200_decode_grid_to_rgb_host.argtypes = [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_char_p), C.POINTER(C.c_size_t), C.c_uint64,
                                                C.c_int, C.c_int, C.POINTER(_lib.Geometry), C.POINTER(_lib.ColorOptions), C.c_void_p,
                                                C.c_size_t, C.POINTER(ImageInfo)]
@@ -115,6 +116,11 @@ class Decoder:
         mono = i.chroma == 0
         _lib.check(self.l.b200_decoder_debug_read_tile(self.h, index, 0, y.ctypes.data, None if mono else cb.ctypes.data, None if mono else cr.ctypes.data))
         return [y] if mono else [y, cb, cr]
+
+    def rerun_device(self, stream=None):
+        """Re-launch reconstruction/deblocking/SAO on the command stream resident in HBM (kernel-only timing)."""
+        s = C.c_void_p(stream.cuda_stream) if stream is not None else None
+        _lib.check(self.l.b200_decoder_rerun_device(self.h, s))
 
     def stats(self) -> DecodeStats:
         st = DecodeStats()

@@ -56,7 +56,7 @@ def test_device_matches_oracle(cuda, case, size):
     assert np.array_equal(_as_bytes(got), want)
 
 
-@pytest.mark.parametrize("ops", GEOM + [[(1, 90), (3, 3, 40, 5, 33)], [(2, 1), (1, 270), (2, 0)]])
+@pytest.mark.parametrize("ops", GEOM + [[(1, 90), (3, 2, 17, 4, 27)], [(2, 1), (1, 270), (2, 0)]])
 @pytest.mark.parametrize("fmt", [(1, 8, (1, 13, 6, 0), 10), (1, 8, (1, 13, 6, 1), 10), (1, 10, (9, 16, 9, 0), 14), (3, 8, (1, 13, 6, 1), 11)])
 @pytest.mark.parametrize("size", [(32, 24), (200, 136)])
 def test_geometry_fused(cuda, ops, fmt, size):

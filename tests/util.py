@@ -53,62 +53,4 @@ def random_ycbcr(seed, w, h, chroma, bpp, alpha=False, full_range_values=True):
     return y, cb, cr, a
 
 
-_plugin = None
-
-
-def ref_plugin():
-    """liboracle_plugin.so (+ libheif_ref.so): the unmodified reference. None if not built (e.g. reference absent)."""
-    global _plugin
-    if _plugin is None:
-        p = os.path.join(ob.REF, "liboracle_plugin.so")
-        if not os.path.exists(p) or not os.path.exists(os.path.join(ob.REF, "libheif_ref.so")):
-            return None
-        ob.lib()
-        # RTLD_LOCAL on purpose: libheif_ref.so exports thousands of C++ symbols that must not interpose on torch
-        _plugin = C.CDLL(p)
-    return _plugin
-
-
-def _p16(a):
-    return None if a is None else np.ascontiguousarray(a, dtype=np.uint16).ctypes.data_as(C.POINTER(C.c_uint16))
-
-
-def ref_postprocess(y, cb, cr, a, chroma, bpp, nclx, ops, out_chroma, only_preferred=0, upsampling=2, hdr_to_8bit=0):
-    """Run the UNMODIFIED reference: HeifPixelImage transforms + convert_colorspace. nclx = (cp, tc, mc, full) or None."""
-    pl = ref_plugin()
-    h, w = y.shape
-    dt = np.uint8 if bpp == 8 else np.uint16
-    arrs = [None if p is None else np.ascontiguousarray(p.astype(dt)) for p in (y, cb, cr, a)]
-    ptr = [None if p is None else p.ctypes.data_as(C.c_void_p) for p in arrs]
-    ops_a = (C.c_int * (5 * max(1, len(ops))))(*[v for o in ops for v in (list(o) + [0] * 5)[:5]])
-    cap = (max(w, h) + 64) ** 2 * 8 * 2
-    out = np.empty(cap, dtype=np.uint8)
-    ow, oh, rb, npl = C.c_int(), C.c_int(), C.c_int(), C.c_int()
-    has = 0 if nclx is None else 1
-    cp, tc, mc, fr = nclx if nclx else (2, 2, 2, 0)
-    colorspace = 1  # heif_colorspace_RGB
-    rc = pl.ref_postprocess(ptr[0], ptr[1], ptr[2], ptr[3], w, h, chroma, bpp, has, cp, tc, mc, int(fr), ops_a, len(ops),
-                            colorspace, out_chroma, only_preferred, upsampling, hdr_to_8bit,
-                            out.ctypes.data_as(C.c_void_p), C.c_size_t(cap), C.byref(ow), C.byref(oh), C.byref(rb), C.byref(npl))
-    if rc != 0:
-        raise RuntimeError(f"ref_postprocess rc={rc}")
-    n = rb.value * oh.value * npl.value
-    return out[:n].copy(), ow.value, oh.value, npl.value
-
-
-def oracle_postprocess(y, cb, cr, a, chroma, bpp, nclx, ops, out_chroma):
-    """C restatement (oracle/color_oracle.c)."""
-    l = ob.lib()
-    h, w = y.shape
-    cp, tc, mc, fr = nclx if nclx else (2, 2, 2, 1)   # image without nclx: defaults + full range (yuv2rgb.cc:203-215)
-    ops_a = (C.c_int * (5 * max(1, len(ops))))(*[v for o in ops for v in (list(o) + [0] * 5)[:5]])
-    cap = (max(w, h) + 64) ** 2 * 8
-    out = np.empty(cap, dtype=np.uint8)
-    ow, oh = C.c_int(), C.c_int()
-    l.co_postprocess.restype = C.c_long
-    keep = [np.ascontiguousarray(p, dtype=np.uint16) if p is not None else None for p in (y, cb, cr, a)]
-    n = l.co_postprocess(*[None if k is None else k.ctypes.data_as(C.c_void_p) for k in keep], w, h, chroma, bpp, cp, mc, int(fr),
-                         ops_a, len(ops), out_chroma, out.ctypes.data_as(C.c_void_p), C.byref(ow), C.byref(oh))
-    if n < 0:
-        raise RuntimeError("co_postprocess failed")
-    return out[:n].copy(), ow.value, oh.value
+from oracle.bindings import oracle_postprocess, ref_plugin, ref_postprocess  # noqa: E402,F401
