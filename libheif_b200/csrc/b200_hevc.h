@@ -33,6 +33,7 @@ struct DeviceBatch {
   unsigned int* error_flag;      // set by a kernel that gave up waiting (zeroed before launch)
   const uint2* row_list;         // (picture, ctb row) in launch order
   int nrows;
+  int max_log2_ctb;              // largest CTB size of the batch (sizes the per-warp shared memory)
 };
 int launch_recon(const DeviceBatch& b, cudaStream_t s);
 int launch_deblock(const DeviceBatch& b, const PicDesc* host_pics, cudaStream_t s);

@@ -83,7 +83,7 @@ struct b200_decoder {
   cudaStream_t last_stream = nullptr;
   bool have_result = false;
   int debug_stage = 0;
-  size_t n_rows = 0, cbytes = 0; bool canvas_fully_covered = true;
+  size_t n_rows = 0, cbytes = 0; bool canvas_fully_covered = true; int max_log2_ctb = 6;
   ~b200_decoder() {
     delete pool;
     pics.release(); ctus.release(); tus.release(); coefs.release(); slices.release(); qp8.release(); edge8.release(); rows.release();
@@ -104,7 +104,7 @@ static int run_device_pipeline(b200_decoder* d, int n, cudaStream_t s, int* laun
   int rc;
   DeviceBatch b{};
   b.pics = d->pics.d; b.npics = n; b.ctus = d->ctus.d; b.tus = d->tus.d; b.coefs = d->coefs.d; b.slices = d->slices.d;
-  b.qp8 = d->qp8.d; b.edge8 = d->edge8.d; b.ticket = d->sync.d; b.error_flag = d->sync.d + 1; b.progress = d->sync.d + 2; b.row_list = d->rows.d; b.nrows = (int)d->n_rows;
+  b.qp8 = d->qp8.d; b.edge8 = d->edge8.d; b.ticket = d->sync.d; b.error_flag = d->sync.d + 1; b.progress = d->sync.d + 2; b.row_list = d->rows.d; b.nrows = (int)d->n_rows; b.max_log2_ctb = d->max_log2_ctb;
   if ((rc = launch_recon(b, s))) return rc;
   cudaEventRecord(d->ev[2], s);
   int launches = 1;
@@ -206,9 +206,14 @@ int b200_decoder_decode_grid(b200_decoder* d, int cols, int rows, const uint8_t*
       p.dst[c] = d->canvas.d + d->canvas_off[c] + (size_t)sy * d->canvas_pitch[c] + (size_t)sx * bps;
       p.dst_stride[c] = (int)(d->canvas_pitch[c] / bps);
     }
-    for (int r = 0; r < p.hctb; r++) d->rows.h[row_cursor++] = make_uint2((unsigned)i, (unsigned)r);
     d->pics.h[i] = p;
   }
+  // Launch order of the CTB rows: row-major ACROSS pictures (all first rows, then all second rows, ...).  A row's
+  // predecessor always holds a smaller ticket (deadlock freedom), and the resident warps spread over every tile's
+  // wavefront instead of idling behind one tile's 2-CTB stagger.
+  { int max_h = 0; d->max_log2_ctb = 4;
+    for (int i = 0; i < n; i++) { max_h = std::max(max_h, d->parsed[(size_t)i].desc.hctb); d->max_log2_ctb = std::max(d->max_log2_ctb, d->parsed[(size_t)i].desc.log2_ctb); }
+    for (int r = 0; r < max_h; r++) for (int i = 0; i < n; i++) if (r < d->parsed[(size_t)i].desc.hctb) d->rows.h[row_cursor++] = make_uint2((unsigned)i, (unsigned)r); }
   d->pool->parallel_for(n, [&](int i) {
     const ParsedPicture& pp = d->parsed[(size_t)i]; const PicDesc& p = pp.desc;
     memcpy(d->ctus.h + p.ctu_base, pp.ctus.data(), pp.ctus.size() * sizeof(CtuInfo));
@@ -370,5 +375,24 @@ extern "C" int b200_debug_parse(const uint8_t* au, size_t size, int8_t* qp8, uin
     }
   }
   out5[0] = hash; out5[1] = pp.coefs.size(); out5[2] = pp.tus.size(); out5[3] = (unsigned long long)p.width; out5[4] = (unsigned long long)p.height;
+  return B200_OK;
+}
+
+// Host-only: parse n access units with `threads` parser threads (the decoder's front-end stage in isolation).
+// Returns the wall-clock milliseconds of the parallel parse in *ms_out.  Used by tests and for tuning on CPU-only hosts.
+extern "C" int b200_debug_parse_many(const uint8_t* const* au, const size_t* au_size, int n, int threads, int repeat, double* ms_out) {
+  if (!au || !au_size || n <= 0) return set_error(B200_E_INVALID, "bad argument");
+  Pool pool(threads > 0 ? threads : 1);
+  std::vector<ParsedPicture> parsed((size_t)n);
+  std::vector<int> rcs((size_t)n, 0);
+  ParseLimits lim;
+  double best = 1e30;
+  for (int r = 0; r < (repeat > 0 ? repeat : 1); r++) {
+    const double t0 = now_ms();
+    pool.parallel_for(n, [&](int i) { rcs[(size_t)i] = parse_access_unit(au[i], au_size[i], lim, parsed[(size_t)i]); });
+    best = std::min(best, now_ms() - t0);
+  }
+  for (int i = 0; i < n; i++) if (rcs[(size_t)i]) return rcs[(size_t)i];
+  if (ms_out) *ms_out = best;
   return B200_OK;
 }

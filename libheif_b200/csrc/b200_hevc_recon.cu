@@ -18,19 +18,41 @@
 namespace b200 {
 
 constexpr int WARPS = 4;                       // warps (= CTB rows in flight) per CTA
-constexpr int TS = 64, TSC = 32;               // tile strides (luma, chroma)
 
-struct __align__(16) WarpMem {
-  uint16_t tile_y[64 * 64];
-  uint16_t tile_c[2][32 * 32];
-  int16_t coef[32 * 32];                       // scaled coefficients [k][x]
-  int16_t tmp[32 * 32];                        // first-stage output, transposed: [x][y]
-  uint16_t top_y[1 + 128 + 3];                 // [0] = above-left corner, [1 + x]
-  uint16_t left_y[64];
-  uint16_t top_c[2][1 + 64 + 3];
-  uint16_t left_c[2][32];
-  int16_t ref_a[132], ref_b[132];              // neighbour array (index 0 = bottom of left column), unfiltered / filtered
+// Per-warp shared-memory working set; sized at launch from the largest CTB of the batch so that small CTBs buy
+// occupancy (CTB 64: 17.7 KB per warp, CTB 32: 7.6 KB, CTB 16: 2.5 KB).
+struct WarpMem {
+  uint16_t* tile_y; uint16_t* tile_c[2];       // current CTB, stride ts / tsc
+  int16_t* coef;                               // scaled coefficients [k][x]
+  int16_t* tmp;                                // first-stage output, transposed: [x][y]
+  uint16_t* top_y; uint16_t* left_y;           // halo: top_y[0] = above-left corner, top_y[1 + x], x < 2 * ctb
+  uint16_t* top_c[2]; uint16_t* left_c[2];
+  int16_t* ref_a; int16_t* ref_b;              // neighbour array (index 0 = bottom of left column), unfiltered / filtered
+  int ts, tsc;
 };
+__host__ __device__ inline size_t warp_mem_bytes(int log2ctb) {
+  const int ctb = 1 << log2ctb, tb = ctb < 32 ? ctb : 32;
+  size_t n = (size_t)ctb * ctb + 2 * (size_t)(ctb / 2) * (ctb / 2)      // tiles
+           + 2 * (size_t)tb * tb                                         // coef + tmp
+           + (1 + 2 * ctb + 3) + ctb + 2 * (1 + ctb + 3) + 2 * (ctb / 2) // halos
+           + 2 * 136;                                                    // ref_a, ref_b
+  return (n * 2 + 15) & ~(size_t)15;
+}
+__device__ inline void warp_mem_init(WarpMem& m, unsigned char* base, int log2ctb) {
+  const int ctb = 1 << log2ctb, tb = ctb < 32 ? ctb : 32, cc = ctb / 2;
+  uint16_t* p = reinterpret_cast<uint16_t*>(base);
+  m.ts = ctb; m.tsc = cc;
+  m.tile_y = p; p += ctb * ctb;
+  m.tile_c[0] = p; p += cc * cc; m.tile_c[1] = p; p += cc * cc;
+  m.coef = reinterpret_cast<int16_t*>(p); p += tb * tb;
+  m.tmp = reinterpret_cast<int16_t*>(p); p += tb * tb;
+  m.top_y = p; p += 1 + 2 * ctb + 3;
+  m.left_y = p; p += ctb;
+  m.top_c[0] = p; p += 1 + ctb + 3; m.top_c[1] = p; p += 1 + ctb + 3;
+  m.left_c[0] = p; p += cc; m.left_c[1] = p; p += cc;
+  m.ref_a = reinterpret_cast<int16_t*>(p); p += 136;
+  m.ref_b = reinterpret_cast<int16_t*>(p);
+}
 
 __constant__ int8_t c_dct[32] = {64, 90, 90, 90, 89, 88, 87, 85, 83, 82, 80, 78, 75, 73, 70, 67,
                                  64, 61, 57, 54, 50, 46, 43, 38, 36, 31, 25, 22, 18, 13, 9, 4};
@@ -60,6 +82,7 @@ struct RowCtx {             // warp-uniform state of the CTB row being decoded
   int W, H, log2ctb, ctb, wctb, bd, chroma, strong;
   int rx, ry, x0, y0;       // current CTB
   int cur_slice;
+  int nb_slice[4];          // slice of the left, above-left, above, above-right CTB (-1: outside / not decoded)
 };
 
 // Availability of the luma location (xn, yn) for a block whose first luma sample is (xc, yc) -- H.265 6.4.1 restated
@@ -75,15 +98,17 @@ __device__ __forceinline__ bool available(const RowCtx& r, int xn, int yn, int x
       return morton4((xn & m) >> 2, (yn & m) >> 2) < morton4((xc & m) >> 2, (yc & m) >> 2);
     }
   }
-  return r.ctus[ncy * r.wctb + ncx].slice_idx == r.cur_slice;
+  // neighbouring CTB: only left, above-left, above and above-right can be referenced (extent <= 2 * nTbS <= CTB size)
+  const int k = ncy == r.ry ? 0 : 1 + (ncx - r.rx + 1);
+  return r.nb_slice[k] == r.cur_slice;
 }
 
 // sample of component c at tile-relative position (tx, ty); tx in [-1, 2*ctb), ty in [-1, ctb)
 __device__ __forceinline__ int tile_sample(const WarpMem& m, int c, int tx, int ty) {
-  if (c == 0) { if (ty < 0) return m.top_y[tx + 1]; if (tx < 0) return m.left_y[ty]; return m.tile_y[ty * TS + tx]; }
+  if (c == 0) { if (ty < 0) return m.top_y[tx + 1]; if (tx < 0) return m.left_y[ty]; return m.tile_y[ty * m.ts + tx]; }
   if (ty < 0) return m.top_c[c - 1][tx + 1];
   if (tx < 0) return m.left_c[c - 1][ty];
-  return m.tile_c[c - 1][ty * TSC + tx];
+  return m.tile_c[c - 1][ty * m.tsc + tx];
 }
 
 // One transform block: 8.4.4.2 prediction into the tile, then (if coded) 8.6.3 scaling + 8.6.4 inverse transform
@@ -158,7 +183,7 @@ __device__ void process_tb(WarpMem& m, const int8_t* __restrict__ mat, const Row
   }
   // ---- prediction (8.4.4.2.4 - 8.4.4.2.6) written straight into the tile
   uint16_t* tile = c == 0 ? m.tile_y : m.tile_c[c - 1];
-  const int ts = c == 0 ? TS : TSC;
+  const int ts = c == 0 ? m.ts : m.tsc;
   const int maxv = (1 << bd) - 1;
 #define LEFT(y) ((int)ref[2 * n - 1 - (y)])
 #define TOP(x) ((int)ref[2 * n + 1 + (x)])
@@ -268,7 +293,6 @@ __device__ __forceinline__ int chroma_qp(int qpy, int off, int bd) {       // 8.
 __global__ void __launch_bounds__(WARPS * 32) hevc_recon_kernel(const DeviceBatch b) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   int8_t* mat = reinterpret_cast<int8_t*>(smem_raw);                       // 32x32 DCT matrix, shared by the CTA
-  WarpMem* wm = reinterpret_cast<WarpMem*>(smem_raw + 1024);
   for (int i = threadIdx.x; i < 1024; i += blockDim.x) {
     const int k = i >> 5, x = i & 31;
     int v;
@@ -278,7 +302,8 @@ __global__ void __launch_bounds__(WARPS * 32) hevc_recon_kernel(const DeviceBatc
   }
   __syncthreads();
   const int lane = threadIdx.x & 31;
-  WarpMem& m = wm[threadIdx.x >> 5];
+  WarpMem m;
+  warp_mem_init(m, smem_raw + 1024 + (threadIdx.x >> 5) * warp_mem_bytes(b.max_log2_ctb), b.max_log2_ctb);
 
   for (;;) {
     unsigned t = 0;
@@ -303,6 +328,11 @@ __global__ void __launch_bounds__(WARPS * 32) hevc_recon_kernel(const DeviceBatc
       r.x0 = r.rx << r.log2ctb;
       const CtuInfo ci = r.ctus[r.ry * r.wctb + r.rx];
       r.cur_slice = ci.slice_idx;
+      r.nb_slice[0] = r.rx > 0 ? r.ctus[r.ry * r.wctb + r.rx - 1].slice_idx : -1;
+      r.nb_slice[1] = (r.rx > 0 && r.ry > 0) ? r.ctus[(r.ry - 1) * r.wctb + r.rx - 1].slice_idx : -1;
+      r.nb_slice[2] = r.ry > 0 ? r.ctus[(r.ry - 1) * r.wctb + r.rx].slice_idx : -1;
+      r.nb_slice[3] = (r.ry > 0 && r.rx + 1 < r.wctb) ? r.ctus[(r.ry - 1) * r.wctb + r.rx + 1].slice_idx : -1;
+      TuCmd next_cmd = ci.tu_count ? tus[ci.tu_start] : TuCmd{0, 0, 0, 0};
       if (r.ry > 0) {
         // wait for the above-right CTB (wavefront, lag 2), then fetch the halo row above from HBM/L2
         const unsigned need = (unsigned)min(r.rx + 2, r.wctb);
@@ -331,7 +361,8 @@ __global__ void __launch_bounds__(WARPS * 32) hevc_recon_kernel(const DeviceBatc
       }
       const SliceInfo sl = r.slices[ci.slice_idx];
       for (unsigned ti = 0; ti < ci.tu_count; ti++) {
-        const TuCmd cmd = tus[ci.tu_start + ti];
+        const TuCmd cmd = next_cmd;
+        if (ti + 1 < ci.tu_count) next_cmd = tus[ci.tu_start + ti + 1];      // prefetch: hides one dependent HBM/L2 round trip per TU
         const int x4 = cmd.w0 & 0xfff, y4 = (cmd.w0 >> 12) & 0xfff, log2n = 2 + ((cmd.w0 >> 24) & 3);
         const int lmode = cmd.w1 & 63, cmode = (cmd.w1 >> 6) & 63, qpy = (int)((cmd.w1 >> 12) & 0xff) - 64;
         const int nl = cmd.w3 & 0x7ff, ncb = (cmd.w3 >> 11) & 0x3ff, ncr = (cmd.w3 >> 21) & 0x3ff;
@@ -350,7 +381,7 @@ __global__ void __launch_bounds__(WARPS * 32) hevc_recon_kernel(const DeviceBatc
         const int cw = c ? r.W >> 1 : r.W, chh = c ? r.H >> 1 : r.H, st = pic->rec_stride[c];
         const int gx0 = c ? r.x0 >> 1 : r.x0, gy0 = c ? r.y0 >> 1 : r.y0, sz = c ? ctbc : r.ctb, lg = c ? r.log2ctb - 1 : r.log2ctb;
         const uint16_t* tile = c == 0 ? m.tile_y : m.tile_c[c - 1];
-        const int ts = c == 0 ? TS : TSC;
+        const int ts = c == 0 ? m.ts : m.tsc;
         const int w = min(sz, cw - gx0), h = min(sz, chh - gy0);
         for (int i = lane; i < sz * h; i += 32) {
           const int x = i & (sz - 1), y = i >> lg;
@@ -372,12 +403,8 @@ __global__ void __launch_bounds__(WARPS * 32) hevc_recon_kernel(const DeviceBatc
 
 int launch_recon(const DeviceBatch& b, cudaStream_t s) {
   if (b.nrows <= 0) return B200_OK;
-  const size_t smem = 1024 + sizeof(WarpMem) * WARPS;
-  static bool attr_done = false;
-  if (!attr_done) {
-    B200_CUDA_CHECK(cudaFuncSetAttribute(hevc_recon_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_done = true;
-  }
+  const size_t smem = 1024 + warp_mem_bytes(b.max_log2_ctb) * WARPS;
+  B200_CUDA_CHECK(cudaFuncSetAttribute(hevc_recon_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(1024 + warp_mem_bytes(6) * WARPS)));
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
