@@ -45,7 +45,7 @@ def make_tile(idx, tile=TILE):
 
 
 def make_tiles(indices, tile=TILE, workers=None):
-    workers = workers or min(64, os.cpu_count() or 8)
+    workers = workers or min(64, effective_cores())
     with ThreadPoolExecutor(workers) as ex:
         return list(ex.map(lambda i: make_tile(i, tile), indices))
 
@@ -91,6 +91,22 @@ class ClockSampler:
                 if v.lower().startswith("active"):
                     reasons.add(name)
         return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": int(float(self.samples[0][1])), "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def effective_cores():
+    """Host cores this process may actually use: min(visible CPUs, cgroup CPU quota)."""
+    n = os.cpu_count() or 1
+    try:
+        q, p = open("/sys/fs/cgroup/cpu.max").read().split()
+        if q != "max":
+            n = min(n, max(1, int(int(q) / int(p))))
+    except Exception:
+        pass
+    try:
+        n = min(n, len(os.sched_getaffinity(0)))
+    except Exception:
+        pass
+    return n
 
 
 def measured_peak():
@@ -148,7 +164,7 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     side = args.tiles_side
-    cores = os.cpu_count() or 8
+    cores = effective_cores()
     workload = f"{side * TILE}x{side * TILE} HEIC grid, {side * side} x {TILE}x{TILE} HEVC-intra tiles, 8-bit 4:2:0 -> RGB24, QP {QP}, CTB 32, WPP, SAO+deblock"
 
     if args.impl == "reference":
@@ -173,10 +189,9 @@ def main():
     dev = torch.device("cuda", local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
-    # ---- shard: contiguous tile-row bands per rank
-    rows_per = [side // world + (1 if r < side % world else 0) for r in range(world)]
-    r0 = sum(rows_per[:rank]); nrows = rows_per[rank]
-    my_idx = [r * side + c for r in range(r0, r0 + nrows) for c in range(side)]
+    # ---- shard: contiguous tile-row bands per rank (libheif_b200/sharding.py, gloo-tested in tests/test_sharding.py)
+    from libheif_b200 import sharding
+    r0, nrows, my_idx = sharding.my_band(side, side, world, rank)
     t_gen = time.perf_counter()
     tiles = make_tiles(my_idx, workers=max(4, cores // world))
     t_gen = time.perf_counter() - t_gen
@@ -189,21 +204,7 @@ def main():
     stream = torch.cuda.current_stream()
 
     def gather():
-        if world == 1:
-            return band
-        # bands can differ by one tile row when side % world != 0: gather through equal-sized padded chunks otherwise
-        if side % world == 0:
-            dist.gather(band, list(full.view(world, band_h, W * 3).unbind(0)) if rank == 0 else None, dst=0)
-        else:
-            mx = max(rows_per) * TILE
-            pad = torch.zeros((mx, W * 3), dtype=torch.uint8, device=dev); pad[:band_h] = band
-            outs = [torch.empty_like(pad) for _ in range(world)] if rank == 0 else None
-            dist.gather(pad, outs, dst=0)
-            if rank == 0:
-                y0 = 0
-                for r in range(world):
-                    full[y0:y0 + rows_per[r] * TILE] = outs[r][:rows_per[r] * TILE]; y0 += rows_per[r] * TILE
-        return full
+        return sharding.gather_bands(band, side, TILE, world, rank, full) if world > 1 else band
 
     def device_step():
         if nrows:
