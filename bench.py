@@ -158,6 +158,7 @@ def main():
     ap.add_argument("--tiles-side", type=int, default=16, help="grid is tiles-side x tiles-side tiles of 1024x1024 (16 = BASELINE config)")
     ap.add_argument("--ref-sample-side", type=int, default=6)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--front-end", default="device", choices=["device", "host"], help="where CABAC runs: GPU (one warp per WPP sub-stream) or host cores")
     args = ap.parse_args()
     warmup = max(3, args.warmup)
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -198,6 +199,7 @@ def main():
     W, H = side * TILE, side * TILE
     band_h = nrows * TILE
     dec = lb.Decoder(host_threads=max(1, cores // world))
+    dec.set_front_end(args.front_end == "device")
     band = torch.empty((max(band_h, 1), W * 3), dtype=torch.uint8, device=dev)
     full = torch.empty((H, W * 3), dtype=torch.uint8, device=dev) if (rank == 0 and world > 1) else None
     host_out = torch.empty((H, W * 3), dtype=torch.uint8, pin_memory=True) if rank == 0 else None
@@ -257,7 +259,7 @@ def main():
         barrier()
         e2e_ms = max_over_ranks((time.perf_counter() - t0) * 1e3) / args.steps
     # ---- per-kernel device times (outside the timed regions): average over a few launches, CUDA events
-    kern = {"recon": 0.0, "deblock": 0.0, "sao_paste": 0.0, "k6_colour": 0.0}
+    kern = {"entropy": 0.0, "recon": 0.0, "deblock": 0.0, "sao_paste": 0.0, "k6_colour": 0.0}
     nk = 5
     if nrows:
         for _ in range(nk):
@@ -266,7 +268,7 @@ def main():
             k0.record(stream); dec.to_rgb_device(lb.CHROMA_INTERLEAVED_RGB, out=band, stream=stream); k1.record(stream)
             torch.cuda.synchronize()
             s = dec.stats()
-            kern["recon"] += s.recon_ms / nk; kern["deblock"] += s.deblock_ms / nk; kern["sao_paste"] += s.sao_ms / nk; kern["k6_colour"] += k0.elapsed_time(k1) / nk
+            kern["entropy"] += s.entropy_ms / nk; kern["recon"] += s.recon_ms / nk; kern["deblock"] += s.deblock_ms / nk; kern["sao_paste"] += s.sao_ms / nk; kern["k6_colour"] += k0.elapsed_time(k1) / nk
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -276,7 +278,11 @@ def main():
     my_px = band_h * W
     peak, peak_src = measured_peak()
     C = st0.command_bytes / my_px                                     # measured command-stream bytes per pixel
-    alg = {"recon": 1.5 + C, "deblock": 3.0, "sao_paste": 3.0, "k6_colour": 4.5}     # B/px, SURVEY.md 8(d), 8-bit
+    bpp = st0.bitstream_bytes / my_px
+    # algorithmic B/px: entropy reads the bitstream and writes the command stream once
+    alg = {"entropy": bpp + C, "recon": 1.5 + C, "deblock": 3.0, "sao_paste": 3.0, "k6_colour": 4.5}
+    if args.front_end == "host":
+        kern.pop("entropy")
     dom = max(kern, key=kern.get)
     ach = alg[dom] * my_px / (kern[dom] * 1e-3) / 1e9
     stats_e2e = dec.stats()
@@ -286,10 +292,10 @@ def main():
         "dtype": "u8", "data": "synthetic",
         "config": {"workload": workload, "sharding": f"{world} x contiguous tile-row bands, NCCL gather of RGB bands to rank 0" if world > 1 else "single GPU",
                    "l2": "inputs larger than L2 (command stream + planes > 126 MB per GPU)" if st0.command_bytes + my_px * 1.5 > 126e6 else "flush not needed: see note",
-                   "bits_per_pixel": 8.0 * st0.bitstream_bytes / my_px, "command_bytes_per_pixel": C, "host_parser_threads": max(1, cores // world)},
+                   "bits_per_pixel": 8.0 * st0.bitstream_bytes / my_px, "command_bytes_per_pixel": C, "host_parser_threads": max(1, cores // world), "front_end": args.front_end + (" (CABAC on the GPU, one warp per WPP sub-stream)" if args.front_end == "device" else " (CABAC on the host cores)")},
         "e2e": {"value": pixels / 1e6 / (e2e_ms / 1e3), "unit": "MP/s", "ms_per_step": e2e_ms, "h2d_bytes_per_step": int(stats_e2e.h2d_bytes * (pixels / my_px)),
                 "d2h_bytes_per_step": pixels * 3, "host_parse_ms": stats_e2e.parse_ms, "host_pack_ms": stats_e2e.pack_ms},
-        "gpu_launches": (4 + 1) * args.steps,
+        "gpu_launches": ((6 if args.front_end == "device" else 4) + 1) * args.steps,
         "clocks": clk.summary(),
         "roofline": {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
                      "peak_source": peak_src, "algorithmic_bytes_per_pixel": alg[dom],

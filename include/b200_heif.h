@@ -157,9 +157,10 @@ typedef struct b200_image_info {
 
 typedef struct b200_decode_stats {
   double parse_ms, pack_ms, h2d_ms, gpu_ms, total_ms;   /* host wall-clock of the last decode call (gpu_ms: CUDA events) */
-  double recon_ms, deblock_ms, sao_ms;                  /* per-kernel device times of the last call */
+  double entropy_ms, recon_ms, deblock_ms, sao_ms;      /* per-kernel device times of the last call (entropy_ms: device front-end only) */
   uint64_t bitstream_bytes, command_bytes, coefficient_entries, transform_units, ctus, h2d_bytes, pixels;
   int kernel_launches;
+  int front_end;                                        /* 1 = CABAC decoded on the GPU, 0 = on the host cores */
 } b200_decode_stats;
 
 /* host_threads: CABAC parser threads (0 = number of online cores).  The CUDA device is the current one. */
@@ -181,6 +182,9 @@ int b200_decoder_read_planes(b200_decoder* dec, void* y, size_t y_stride, void* 
 /* Reconstruction planes of tile `index` before/after deblocking (debug / parity of intermediate stages):
    stage 1 = before deblocking, 2 = after deblocking (coded size, no conformance crop).  Host copies. */
 int b200_decoder_debug_read_tile(b200_decoder* dec, int index, int stage, void* y, void* cb, void* cr);
+/* Where CABAC + slice-data syntax run: 1 (default) = on the GPU, one warp per WPP sub-stream / slice segment;
+   0 = on the host cores (BASELINE north_star wording), host_threads parser threads.  Same command stream either way. */
+int b200_decoder_set_front_end(b200_decoder* dec, int device);
 int b200_decoder_set_debug_stage(b200_decoder* dec, int stage /* 0 = full pipeline, 1 = stop after reconstruction, 2 = stop after deblocking */);
 int b200_decoder_get_stats(b200_decoder* dec, b200_decode_stats* out);
 /* Re-launch the device kernels on the command stream already resident in HBM (no host parse, no H2D). */

@@ -2,25 +2,38 @@
 #pragma once
 #include "b200_internal.h"
 #include "b200_hevc_types.h"
+#include "b200_hevc_syntax.h"
 #include <vector>
 
 namespace b200 {
 
 struct ParseLimits { uint64_t max_image_size_pixels = 0; };   // heif_security_limits.max_image_size_pixels (0 = unlimited)
 
-struct ParsedPicture {
-  PicDesc desc;
-  std::vector<CtuInfo> ctus;
-  std::vector<TuCmd> tus;
-  std::vector<CoefEntry> coefs;
+// Everything the slice data depends on, produced by the host from the headers alone (cheap, serial).
+struct PictureHeaders {
+  PicDesc desc;                          // dimensions, conformance window, tool flags (device pointers filled later)
+  syn::SeqParams sp;
   std::vector<SliceInfo> slices;
-  std::vector<int8_t> qp8;
-  std::vector<uint8_t> edge8;
+  std::vector<syn::Substream> subs;      // CABAC sub-streams in decoding order
+  std::vector<uint8_t> rbsp;             // slice-segment data of the picture, emulation prevention removed, zero padded
+  std::vector<uint16_t> ctu_slice;       // slice index per CTB
   // VUI colour description as the libde265 plugin reports it (decoder_libde265.cc:426-448)
   int colour_primaries = 2, transfer_characteristics = 2, matrix_coefficients = 2, full_range = 0;
 };
 
-// Host front-end: length-prefixed NAL units of one access unit -> command stream.  Thread-safe (no shared state).
+struct ParsedPicture {                   // host front-end result: headers + dense command stream
+  PictureHeaders hdr;
+  PicDesc desc;
+  std::vector<CtuInfo> ctus;
+  std::vector<TuCmd> tus; size_t n_tus = 0;          // vectors are capacity buffers; n_* entries are valid
+  std::vector<CoefEntry> coefs; size_t n_coefs = 0;
+  std::vector<SliceInfo> slices;
+  std::vector<int8_t> qp8;
+  std::vector<uint8_t> edge8, ipm4, cd8, wpp_ctx, end_state;
+};
+
+// Host front-end.  Thread-safe (no shared state).
+int parse_headers(const uint8_t* data, size_t size, const ParseLimits& limits, PictureHeaders& out);
 int parse_access_unit(const uint8_t* data, size_t size, const ParseLimits& limits, ParsedPicture& out);
 
 // Device back-end (b200_hevc_recon.cu / b200_hevc_filters.cu).  All arrays are batch-wide device buffers.
@@ -35,6 +48,17 @@ struct DeviceBatch {
   int nrows;
   int max_log2_ctb;              // largest CTB size of the batch (sizes the per-warp shared memory)
 };
+// Device front-end (b200_hevc_entropy.cu)
+struct EntropyPic { syn::SeqParams sp; syn::PicBuffers pb; uint32_t progress_base, sub_base; };
+struct EntropyBatch {
+  const EntropyPic* pics; int npics;
+  const syn::Substream* subs;    // batch-wide, grouped per picture (EntropyPic::sub_base)
+  const uint2* order;            // (picture, local sub-stream index) in ticket order
+  int nsubs;
+  unsigned int* ticket; unsigned int* progress; unsigned int* sub_done; unsigned int* error_flag;
+};
+int launch_entropy(const EntropyBatch& b, cudaStream_t s);
+int launch_entropy_stats(const EntropyBatch& b, unsigned long long* out2, cudaStream_t s);
 int launch_recon(const DeviceBatch& b, cudaStream_t s);
 int launch_deblock(const DeviceBatch& b, const PicDesc* host_pics, cudaStream_t s);
 int launch_sao(const DeviceBatch& b, const PicDesc* host_pics, cudaStream_t s);

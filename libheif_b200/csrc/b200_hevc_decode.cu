@@ -50,20 +50,25 @@ class Pool {
 };
 
 template <typename T>
-struct DevBuf {   // grow-only device + pinned host pair
-  T* d = nullptr; T* h = nullptr; size_t cap = 0;
+struct DevBuf {   // grow-only device buffer with optional pinned host staging of the same capacity
+  T* d = nullptr; T* h = nullptr; size_t cap = 0, hcap = 0;
   int reserve(size_t n, bool host = true) {
-    if (n <= cap) return B200_OK;
-    size_t nc = n + n / 4 + 1024;
-    if (d) cudaFree(d);
-    if (h) cudaFreeHost(h);
-    d = nullptr; h = nullptr; cap = 0;
-    B200_CUDA_CHECK(cudaMalloc(&d, nc * sizeof(T)));
-    if (host) B200_CUDA_CHECK(cudaMallocHost(&h, nc * sizeof(T)));
-    cap = nc;
+    if (n > cap) {
+      const size_t nc = n + n / 4 + 1024;
+      if (d) cudaFree(d);
+      d = nullptr; cap = 0;
+      B200_CUDA_CHECK(cudaMalloc(&d, nc * sizeof(T)));
+      cap = nc;
+    }
+    if (host && n > hcap) {
+      if (h) cudaFreeHost(h);
+      h = nullptr; hcap = 0;
+      B200_CUDA_CHECK(cudaMallocHost(&h, cap * sizeof(T)));
+      hcap = cap;
+    }
     return B200_OK;
   }
-  void release() { if (d) cudaFree(d); if (h) cudaFreeHost(h); d = nullptr; h = nullptr; cap = 0; }
+  void release() { if (d) cudaFree(d); if (h) cudaFreeHost(h); d = nullptr; h = nullptr; cap = hcap = 0; }
 };
 
 }  // namespace
@@ -75,11 +80,16 @@ struct b200_decoder {
   DevBuf<PicDesc> pics; DevBuf<CtuInfo> ctus; DevBuf<TuCmd> tus; DevBuf<CoefEntry> coefs; DevBuf<SliceInfo> slices;
   DevBuf<int8_t> qp8; DevBuf<uint8_t> edge8; DevBuf<uint2> rows; DevBuf<unsigned> sync;   // sync: [0] ticket, [1] error flag, [2..] progress
   DevBuf<uint8_t> rec; DevBuf<uint8_t> canvas;
+  // device front-end (entropy decoding on the GPU)
+  DevBuf<uint8_t> rbsp; DevBuf<syn::Substream> subs; DevBuf<uint2> sub_order; DevBuf<uint16_t> ctu_slice; DevBuf<EntropyPic> epics;
+  DevBuf<uint8_t> ipm4, cd8, wpp_ctx, end_state; DevBuf<unsigned> esync; DevBuf<unsigned long long> ecount;
+  int front_end = 1;               // 1 = CABAC on the GPU (default), 0 = CABAC on the host cores
+  bool used_device_front_end = false; size_t n_subs = 0;
   size_t canvas_off[3] = {0, 0, 0}; size_t canvas_pitch[3] = {0, 0, 0};
   b200_image_info info{};
   b200_decode_stats stats{};
   std::vector<size_t> rec_off; int npics = 0;
-  cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+  cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};   // 0 start, 1 after H2D, 5 after entropy, 2 after recon, 3 after deblock, 4 after SAO
   cudaStream_t last_stream = nullptr;
   bool have_result = false;
   int debug_stage = 0;
@@ -88,6 +98,8 @@ struct b200_decoder {
     delete pool;
     pics.release(); ctus.release(); tus.release(); coefs.release(); slices.release(); qp8.release(); edge8.release(); rows.release();
     sync.release(); rec.release(); canvas.release();
+    rbsp.release(); subs.release(); sub_order.release(); ctu_slice.release(); epics.release(); ipm4.release(); cd8.release(); wpp_ctx.release();
+    end_state.release(); esync.release(); ecount.release();
     for (auto& e : ev) if (e) cudaEventDestroy(e);
   }
 };
@@ -97,6 +109,16 @@ static int check_device_error(b200_decoder* d) {
   B200_CUDA_CHECK(cudaMemcpy(&flag, d->sync.d + 1, sizeof flag, cudaMemcpyDeviceToHost));
   if (flag) return set_error(B200_E_CUDA, "reconstruction kernel gave up waiting for a CTB row dependency");
   return B200_OK;
+}
+
+// Device front-end: entropy decoding of every sub-stream of the batch (K0).
+static int run_entropy(b200_decoder* d, cudaStream_t s) {
+  EntropyBatch e{};
+  e.pics = d->epics.d; e.npics = d->npics; e.subs = d->subs.d; e.order = d->sub_order.d; e.nsubs = (int)d->n_subs;
+  e.ticket = d->esync.d; e.progress = d->esync.d + 1; e.sub_done = d->esync.d + 1 + d->n_rows; e.error_flag = d->sync.d + 1;
+  int rc = launch_entropy(e, s);
+  if (rc) return rc;
+  return launch_entropy_stats(e, d->ecount.d, s);
 }
 
 // Launches the device half (reconstruction -> deblocking -> SAO/paste) on the command stream currently resident in HBM.
@@ -134,18 +156,24 @@ void b200_decoder_destroy(b200_decoder* d) { delete d; }
 
 int b200_decoder_set_debug_stage(b200_decoder* d, int stage) { if (!d) return B200_E_INVALID; d->debug_stage = stage; return B200_OK; }
 
+int b200_decoder_set_front_end(b200_decoder* d, int device) { if (!d) return B200_E_INVALID; d->front_end = device ? 1 : 0; return B200_OK; }
+
 int b200_decoder_decode_grid(b200_decoder* d, int cols, int rows, const uint8_t* const* au, const size_t* au_size,
                              uint64_t max_pixels, int canvas_w, int canvas_h, b200_image_info* info, void* stream_) {
   if (!d || !au || !au_size || cols <= 0 || rows <= 0) return set_error(B200_E_INVALID, "bad argument");
   cudaStream_t s = (cudaStream_t)stream_;
   const int n = cols * rows;
   const double t0 = now_ms();
+  const bool devfe = d->front_end != 0;
   d->have_result = false;
   d->parsed.resize((size_t)n); d->parse_rc.assign((size_t)n, 0); d->parse_msg.assign((size_t)n, std::string());
   ParseLimits lim; lim.max_image_size_pixels = max_pixels;
-  // ---- 1. host front-end: one tile per task (CABAC is serial per sub-stream, tiles are independent)
+  // ---- 1. host stage, one tile per task.  Host front-end: headers + CABAC + syntax (serial per sub-stream).
+  //         Device front-end: headers only (NAL split, emulation prevention removal, parameter sets, entry points).
   d->pool->parallel_for(n, [&](int i) {
-    int rc = parse_access_unit(au[i], au_size[i], lim, d->parsed[(size_t)i]);
+    ParsedPicture& pp = d->parsed[(size_t)i];
+    int rc = devfe ? parse_headers(au[i], au_size[i], lim, pp.hdr) : parse_access_unit(au[i], au_size[i], lim, pp);
+    if (!rc && devfe) pp.desc = pp.hdr.desc;
     d->parse_rc[(size_t)i] = rc;
     if (rc) d->parse_msg[(size_t)i] = b200_last_error();
   });
@@ -161,13 +189,18 @@ int b200_decoder_decode_grid(b200_decoder* d, int cols, int rows, const uint8_t*
   }
   if (chroma && ((tw | th) & 1) && n > 1) return set_error(B200_E_UNSUPPORTED, "odd-sized 4:2:0 grid tiles");
   const int cw = canvas_w > 0 ? canvas_w : tw * cols, chh = canvas_h > 0 ? canvas_h : th * rows;
-  size_t n_ctu = 0, n_tu = 0, n_coef = 0, n_slice = 0, n_map = 0, n_rows = 0, rec_bytes = 0, bits = 0;
+  size_t n_ctu = 0, n_tu = 0, n_coef = 0, n_slice = 0, n_map = 0, n_rows = 0, rec_bytes = 0, bits = 0, n_rbsp = 0, n_subs = 0, n_map4 = 0;
   d->rec_off.resize((size_t)n * 3);
+  std::vector<size_t> rbsp_off((size_t)n), sub_off((size_t)n), map4_off((size_t)n);
   for (int i = 0; i < n; i++) {
     ParsedPicture& pp = d->parsed[(size_t)i]; PicDesc& p = pp.desc;
+    const size_t nctb = (size_t)p.wctb * p.hctb;
     p.ctu_base = (uint32_t)n_ctu; p.tu_base = (uint32_t)n_tu; p.coef_base = n_coef; p.slice_base = (uint32_t)n_slice; p.map8_base = (uint32_t)n_map;
     p.progress_base = (uint32_t)n_rows;
-    n_ctu += pp.ctus.size(); n_tu += pp.tus.size(); n_coef += pp.coefs.size(); n_slice += pp.slices.size(); n_map += pp.qp8.size(); n_rows += (size_t)p.hctb;
+    rbsp_off[(size_t)i] = n_rbsp; sub_off[(size_t)i] = n_subs; map4_off[(size_t)i] = n_map4;
+    n_ctu += nctb; n_slice += (devfe ? pp.hdr.slices.size() : pp.slices.size()); n_map += (size_t)p.w8 * p.h8; n_map4 += (size_t)p.w8 * p.h8 * 4; n_rows += (size_t)p.hctb;
+    if (devfe) { n_tu += nctb * (size_t)pp.hdr.sp.tu_slots; n_coef += nctb * (size_t)pp.hdr.sp.coef_slots; n_rbsp += (pp.hdr.rbsp.size() + 15) & ~(size_t)15; n_subs += pp.hdr.subs.size(); }
+    else { n_tu += pp.n_tus; n_coef += pp.n_coefs; }
     bits += au_size[i];
     for (int c = 0; c < (chroma ? 3 : 1); c++) {
       const int w = c ? p.width >> 1 : p.width, h = c ? p.height >> 1 : p.height;
@@ -179,9 +212,14 @@ int b200_decoder_decode_grid(b200_decoder* d, int cols, int rows, const uint8_t*
   }
   if (n_tu > 0xffffffffull) return set_error(B200_E_UNSUPPORTED, "batch too large");
   int rc;
-  if ((rc = d->pics.reserve((size_t)n)) || (rc = d->ctus.reserve(n_ctu)) || (rc = d->tus.reserve(n_tu)) || (rc = d->coefs.reserve(n_coef + 1)) ||
-      (rc = d->slices.reserve(n_slice)) || (rc = d->qp8.reserve(n_map)) || (rc = d->edge8.reserve(n_map)) || (rc = d->rows.reserve(n_rows)) ||
+  if ((rc = d->pics.reserve((size_t)n)) || (rc = d->ctus.reserve(n_ctu, !devfe)) || (rc = d->tus.reserve(n_tu, !devfe)) || (rc = d->coefs.reserve(n_coef + 1, !devfe)) ||
+      (rc = d->slices.reserve(n_slice)) || (rc = d->qp8.reserve(n_map, !devfe)) || (rc = d->edge8.reserve(n_map, !devfe)) || (rc = d->rows.reserve(n_rows)) ||
       (rc = d->sync.reserve(n_rows + 2, false)) || (rc = d->rec.reserve(rec_bytes, false)))
+    return rc;
+  if (devfe && ((rc = d->rbsp.reserve(n_rbsp + 16)) || (rc = d->subs.reserve(n_subs)) || (rc = d->sub_order.reserve(n_subs)) || (rc = d->ctu_slice.reserve(n_ctu)) ||
+                (rc = d->epics.reserve((size_t)n)) || (rc = d->ipm4.reserve(n_map4, false)) || (rc = d->cd8.reserve(n_map, false)) ||
+                (rc = d->wpp_ctx.reserve(n_rows * syn::CTX_STRIDE, false)) || (rc = d->end_state.reserve(n_subs * syn::CTX_STRIDE + 16, false)) ||
+                (rc = d->esync.reserve(1 + n_rows + n_subs, false)) || (rc = d->ecount.reserve(2, true))))
     return rc;
   // canvas planes
   size_t cbytes = 0;
@@ -193,7 +231,6 @@ int b200_decoder_decode_grid(b200_decoder* d, int cols, int rows, const uint8_t*
   const bool canvas_fully_covered = tw * cols >= cw && th * rows >= chh;
   if ((rc = d->canvas.reserve(cbytes, false))) return rc;
   // ---- 3. pack into pinned staging (parallel) and fix up device pointers
-  size_t row_cursor = 0;
   for (int i = 0; i < n; i++) {
     ParsedPicture& pp = d->parsed[(size_t)i]; PicDesc& p = pp.desc;
     const int col = i % cols, row = i / cols;
@@ -211,47 +248,93 @@ int b200_decoder_decode_grid(b200_decoder* d, int cols, int rows, const uint8_t*
   // Launch order of the CTB rows: row-major ACROSS pictures (all first rows, then all second rows, ...).  A row's
   // predecessor always holds a smaller ticket (deadlock freedom), and the resident warps spread over every tile's
   // wavefront instead of idling behind one tile's 2-CTB stagger.
-  { int max_h = 0; d->max_log2_ctb = 4;
+  { size_t row_cursor = 0; int max_h = 0; d->max_log2_ctb = 4;
     for (int i = 0; i < n; i++) { max_h = std::max(max_h, d->parsed[(size_t)i].desc.hctb); d->max_log2_ctb = std::max(d->max_log2_ctb, d->parsed[(size_t)i].desc.log2_ctb); }
     for (int r = 0; r < max_h; r++) for (int i = 0; i < n; i++) if (r < d->parsed[(size_t)i].desc.hctb) d->rows.h[row_cursor++] = make_uint2((unsigned)i, (unsigned)r); }
+  if (devfe) {
+    // sub-stream ticket order: k-th sub-stream of every picture, k = 0, 1, ... (same argument as for the rows)
+    size_t cur = 0, maxs = 0;
+    for (int i = 0; i < n; i++) maxs = std::max(maxs, d->parsed[(size_t)i].hdr.subs.size());
+    for (size_t k = 0; k < maxs; k++) for (int i = 0; i < n; i++) if (k < d->parsed[(size_t)i].hdr.subs.size()) d->sub_order.h[cur++] = make_uint2((unsigned)i, (unsigned)k);
+  }
   d->pool->parallel_for(n, [&](int i) {
     const ParsedPicture& pp = d->parsed[(size_t)i]; const PicDesc& p = pp.desc;
-    memcpy(d->ctus.h + p.ctu_base, pp.ctus.data(), pp.ctus.size() * sizeof(CtuInfo));
-    memcpy(d->tus.h + p.tu_base, pp.tus.data(), pp.tus.size() * sizeof(TuCmd));
-    memcpy(d->coefs.h + p.coef_base, pp.coefs.data(), pp.coefs.size() * sizeof(CoefEntry));
-    memcpy(d->slices.h + p.slice_base, pp.slices.data(), pp.slices.size() * sizeof(SliceInfo));
-    memcpy(d->qp8.h + p.map8_base, pp.qp8.data(), pp.qp8.size());
-    memcpy(d->edge8.h + p.map8_base, pp.edge8.data(), pp.edge8.size());
+    if (!devfe) {
+      memcpy(d->ctus.h + p.ctu_base, pp.ctus.data(), (size_t)p.wctb * p.hctb * sizeof(CtuInfo));
+      memcpy(d->tus.h + p.tu_base, pp.tus.data(), pp.n_tus * sizeof(TuCmd));
+      memcpy(d->coefs.h + p.coef_base, pp.coefs.data(), pp.n_coefs * sizeof(CoefEntry));
+      memcpy(d->slices.h + p.slice_base, pp.slices.data(), pp.slices.size() * sizeof(SliceInfo));
+      memcpy(d->qp8.h + p.map8_base, pp.qp8.data(), (size_t)p.w8 * p.h8);
+      memcpy(d->edge8.h + p.map8_base, pp.edge8.data(), (size_t)p.w8 * p.h8);
+    } else {
+      const PictureHeaders& H = pp.hdr;
+      memcpy(d->slices.h + p.slice_base, H.slices.data(), H.slices.size() * sizeof(SliceInfo));
+      memcpy(d->rbsp.h + rbsp_off[(size_t)i], H.rbsp.data(), H.rbsp.size());
+      memcpy(d->ctu_slice.h + p.ctu_base, H.ctu_slice.data(), H.ctu_slice.size() * sizeof(uint16_t));
+      for (size_t k = 0; k < H.subs.size(); k++) { syn::Substream ss = H.subs[k]; ss.pic = (uint32_t)i; d->subs.h[sub_off[(size_t)i] + k] = ss; }
+      EntropyPic ep{};
+      ep.sp = H.sp; ep.sp.dense = 0;
+      ep.pb.rbsp = d->rbsp.d + rbsp_off[(size_t)i]; ep.pb.rbsp_size = (uint32_t)H.rbsp.size();
+      ep.pb.tus = d->tus.d + p.tu_base; ep.pb.coefs = d->coefs.d + p.coef_base; ep.pb.ctus = d->ctus.d + p.ctu_base; ep.pb.slices = d->slices.d + p.slice_base;
+      ep.pb.ctu_slice = d->ctu_slice.d + p.ctu_base; ep.pb.qp8 = d->qp8.d + p.map8_base; ep.pb.edge8 = d->edge8.d + p.map8_base;
+      ep.pb.ipm4 = d->ipm4.d + map4_off[(size_t)i]; ep.pb.cd8 = d->cd8.d + p.map8_base;
+      ep.pb.wpp_ctx = d->wpp_ctx.d + (size_t)p.progress_base * syn::CTX_STRIDE; ep.pb.end_state = d->end_state.d + sub_off[(size_t)i] * syn::CTX_STRIDE;
+      ep.progress_base = p.progress_base; ep.sub_base = (uint32_t)sub_off[(size_t)i];
+      d->epics.h[i] = ep;
+    }
   });
   const double t2 = now_ms();
   // ---- 4. H2D + kernels
   cudaEventRecord(d->ev[0], s);
   B200_CUDA_CHECK(cudaMemcpyAsync(d->pics.d, d->pics.h, (size_t)n * sizeof(PicDesc), cudaMemcpyHostToDevice, s));
-  B200_CUDA_CHECK(cudaMemcpyAsync(d->ctus.d, d->ctus.h, n_ctu * sizeof(CtuInfo), cudaMemcpyHostToDevice, s));
-  B200_CUDA_CHECK(cudaMemcpyAsync(d->tus.d, d->tus.h, n_tu * sizeof(TuCmd), cudaMemcpyHostToDevice, s));
-  B200_CUDA_CHECK(cudaMemcpyAsync(d->coefs.d, d->coefs.h, n_coef * sizeof(CoefEntry), cudaMemcpyHostToDevice, s));
   B200_CUDA_CHECK(cudaMemcpyAsync(d->slices.d, d->slices.h, n_slice * sizeof(SliceInfo), cudaMemcpyHostToDevice, s));
-  B200_CUDA_CHECK(cudaMemcpyAsync(d->qp8.d, d->qp8.h, n_map, cudaMemcpyHostToDevice, s));
-  B200_CUDA_CHECK(cudaMemcpyAsync(d->edge8.d, d->edge8.h, n_map, cudaMemcpyHostToDevice, s));
   B200_CUDA_CHECK(cudaMemcpyAsync(d->rows.d, d->rows.h, n_rows * sizeof(uint2), cudaMemcpyHostToDevice, s));
+  size_t h2d = (size_t)n * sizeof(PicDesc) + n_slice * sizeof(SliceInfo) + n_rows * sizeof(uint2);
+  if (!devfe) {
+    B200_CUDA_CHECK(cudaMemcpyAsync(d->ctus.d, d->ctus.h, n_ctu * sizeof(CtuInfo), cudaMemcpyHostToDevice, s));
+    B200_CUDA_CHECK(cudaMemcpyAsync(d->tus.d, d->tus.h, n_tu * sizeof(TuCmd), cudaMemcpyHostToDevice, s));
+    B200_CUDA_CHECK(cudaMemcpyAsync(d->coefs.d, d->coefs.h, n_coef * sizeof(CoefEntry), cudaMemcpyHostToDevice, s));
+    B200_CUDA_CHECK(cudaMemcpyAsync(d->qp8.d, d->qp8.h, n_map, cudaMemcpyHostToDevice, s));
+    B200_CUDA_CHECK(cudaMemcpyAsync(d->edge8.d, d->edge8.h, n_map, cudaMemcpyHostToDevice, s));
+    h2d += n_ctu * sizeof(CtuInfo) + n_tu * sizeof(TuCmd) + n_coef * sizeof(CoefEntry) + 2 * n_map;
+  } else {
+    B200_CUDA_CHECK(cudaMemcpyAsync(d->rbsp.d, d->rbsp.h, n_rbsp, cudaMemcpyHostToDevice, s));
+    B200_CUDA_CHECK(cudaMemcpyAsync(d->subs.d, d->subs.h, n_subs * sizeof(syn::Substream), cudaMemcpyHostToDevice, s));
+    B200_CUDA_CHECK(cudaMemcpyAsync(d->sub_order.d, d->sub_order.h, n_subs * sizeof(uint2), cudaMemcpyHostToDevice, s));
+    B200_CUDA_CHECK(cudaMemcpyAsync(d->ctu_slice.d, d->ctu_slice.h, n_ctu * sizeof(uint16_t), cudaMemcpyHostToDevice, s));
+    B200_CUDA_CHECK(cudaMemcpyAsync(d->epics.d, d->epics.h, (size_t)n * sizeof(EntropyPic), cudaMemcpyHostToDevice, s));
+    B200_CUDA_CHECK(cudaMemsetAsync(d->esync.d, 0, (1 + n_rows + n_subs) * sizeof(unsigned), s));
+    B200_CUDA_CHECK(cudaMemsetAsync(d->ecount.d, 0, 2 * sizeof(unsigned long long), s));
+    h2d += n_rbsp + n_subs * (sizeof(syn::Substream) + sizeof(uint2)) + n_ctu * sizeof(uint16_t) + (size_t)n * sizeof(EntropyPic);
+  }
   B200_CUDA_CHECK(cudaMemsetAsync(d->sync.d, 0, (n_rows + 2) * sizeof(unsigned), s));
   if (!canvas_fully_covered) B200_CUDA_CHECK(cudaMemsetAsync(d->canvas.d, 0, cbytes, s));     // uncovered canvas stays zero (calloc in the reference)
-  d->n_rows = n_rows; d->cbytes = cbytes; d->canvas_fully_covered = canvas_fully_covered;
+  d->n_rows = n_rows; d->cbytes = cbytes; d->canvas_fully_covered = canvas_fully_covered; d->npics = n; d->n_subs = n_subs; d->used_device_front_end = devfe;
   cudaEventRecord(d->ev[1], s);
   int launches = 0;
-  if ((rc = run_device_pipeline(d, n, s, &launches))) return rc;
-  d->npics = n; d->last_stream = s; d->have_result = true;
+  if (devfe) {
+    if ((rc = run_entropy(d, s))) return rc;
+    launches += 1;
+  }
+  cudaEventRecord(d->ev[5], s);
+  int l2 = 0;
+  if ((rc = run_device_pipeline(d, n, s, &l2))) return rc;
+  launches += l2;
+  d->last_stream = s; d->have_result = true;
   b200_image_info& inf = d->info;
   inf.width = cw; inf.height = chh; inf.tile_width = tw; inf.tile_height = th; inf.chroma = chroma ? B200_CHROMA_420 : B200_CHROMA_MONO; inf.bit_depth = bd;
-  inf.colour_primaries = d->parsed[0].colour_primaries; inf.transfer_characteristics = d->parsed[0].transfer_characteristics;
-  inf.matrix_coefficients = d->parsed[0].matrix_coefficients; inf.full_range = d->parsed[0].full_range;
+  inf.colour_primaries = d->parsed[0].hdr.colour_primaries; inf.transfer_characteristics = d->parsed[0].hdr.transfer_characteristics;
+  inf.matrix_coefficients = d->parsed[0].hdr.matrix_coefficients; inf.full_range = d->parsed[0].hdr.full_range;
   if (info) *info = inf;
   b200_decode_stats& st = d->stats;
   memset(&st, 0, sizeof st);
   st.parse_ms = t1 - t0; st.pack_ms = t2 - t1; st.total_ms = now_ms() - t0;
-  st.bitstream_bytes = bits; st.coefficient_entries = n_coef; st.transform_units = n_tu; st.ctus = n_ctu;
-  st.command_bytes = n_ctu * sizeof(CtuInfo) + n_tu * sizeof(TuCmd) + n_coef * sizeof(CoefEntry) + n_slice * sizeof(SliceInfo) + 2 * n_map + (size_t)n * sizeof(PicDesc);
-  st.h2d_bytes = st.command_bytes + n_rows * sizeof(uint2);
+  st.bitstream_bytes = bits; st.ctus = n_ctu;
+  if (!devfe) {
+    st.coefficient_entries = n_coef; st.transform_units = n_tu;
+    st.command_bytes = n_ctu * sizeof(CtuInfo) + n_tu * sizeof(TuCmd) + n_coef * sizeof(CoefEntry) + n_slice * sizeof(SliceInfo) + 2 * n_map + (size_t)n * sizeof(PicDesc);
+  }
+  st.h2d_bytes = h2d;
   st.pixels = (uint64_t)cw * chh; st.kernel_launches = launches;
   return B200_OK;
 }
@@ -261,9 +344,16 @@ int b200_decoder_rerun_device(b200_decoder* d, void* stream_) {
   if (!d || !d->have_result) return set_error(B200_E_INVALID, "no decode result");
   cudaStream_t s = (cudaStream_t)stream_;
   B200_CUDA_CHECK(cudaMemsetAsync(d->sync.d, 0, (d->n_rows + 2) * sizeof(unsigned), s));
+  if (d->used_device_front_end) {
+    B200_CUDA_CHECK(cudaMemsetAsync(d->esync.d, 0, (1 + d->n_rows + d->n_subs) * sizeof(unsigned), s));
+    B200_CUDA_CHECK(cudaMemsetAsync(d->ecount.d, 0, 2 * sizeof(unsigned long long), s));
+  }
   cudaEventRecord(d->ev[1], s);
+  int rc;
+  if (d->used_device_front_end && (rc = run_entropy(d, s))) return rc;
+  cudaEventRecord(d->ev[5], s);
   int launches = 0;
-  int rc = run_device_pipeline(d, d->npics, s, &launches);
+  rc = run_device_pipeline(d, d->npics, s, &launches);
   d->last_stream = s;
   return rc;
 }
@@ -271,10 +361,16 @@ int b200_decoder_rerun_device(b200_decoder* d, void* stream_) {
 int b200_decoder_get_stats(b200_decoder* d, b200_decode_stats* out) {
   if (!d || !out || !d->have_result) return set_error(B200_E_INVALID, "no decode result");
   B200_CUDA_CHECK(cudaEventSynchronize(d->ev[4]));
-  float a = 0, b = 0, c = 0, e = 0;
-  cudaEventElapsedTime(&a, d->ev[0], d->ev[1]); cudaEventElapsedTime(&b, d->ev[1], d->ev[2]);
+  float a = 0, en = 0, b = 0, c = 0, e = 0;
+  cudaEventElapsedTime(&a, d->ev[0], d->ev[1]); cudaEventElapsedTime(&en, d->ev[1], d->ev[5]); cudaEventElapsedTime(&b, d->ev[5], d->ev[2]);
   cudaEventElapsedTime(&c, d->ev[2], d->ev[3]); cudaEventElapsedTime(&e, d->ev[3], d->ev[4]);
-  d->stats.h2d_ms = a; d->stats.recon_ms = b; d->stats.deblock_ms = c; d->stats.sao_ms = e; d->stats.gpu_ms = b + c + e;
+  d->stats.h2d_ms = a; d->stats.entropy_ms = en; d->stats.recon_ms = b; d->stats.deblock_ms = c; d->stats.sao_ms = e; d->stats.gpu_ms = en + b + c + e;
+  d->stats.front_end = d->used_device_front_end ? 1 : 0;
+  if (d->used_device_front_end) {
+    B200_CUDA_CHECK(cudaMemcpy(d->ecount.h, d->ecount.d, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+    d->stats.transform_units = d->ecount.h[0]; d->stats.coefficient_entries = d->ecount.h[1];
+    d->stats.command_bytes = d->stats.ctus * sizeof(CtuInfo) + d->ecount.h[0] * sizeof(TuCmd) + d->ecount.h[1] * sizeof(CoefEntry) + 2 * (d->stats.pixels / 64);
+  }
   *out = d->stats;
   return B200_OK;
 }
@@ -356,9 +452,10 @@ extern "C" int b200_debug_parse(const uint8_t* au, size_t size, int8_t* qp8, uin
   if (rc) return rc;
   const PicDesc& p = pp.desc;
   const int w4 = p.width >> 2;
-  memcpy(qp8, pp.qp8.data(), pp.qp8.size()); memcpy(edge8, pp.edge8.data(), pp.edge8.size());
+  memcpy(qp8, pp.qp8.data(), (size_t)p.w8 * p.h8); memcpy(edge8, pp.edge8.data(), (size_t)p.w8 * p.h8);
   unsigned long long hash = 0;
-  for (const TuCmd& t : pp.tus) {
+  for (size_t ti = 0; ti < pp.n_tus; ti++) {
+    const TuCmd& t = pp.tus[ti];
     const int x4 = t.w0 & 0xfff, y4 = (t.w0 >> 12) & 0xfff, log2n = 2 + ((t.w0 >> 24) & 3), n4 = 1 << (log2n - 2);
     const int lm = t.w1 & 63, cm = (t.w1 >> 6) & 63;
     for (int y = 0; y < n4; y++) for (int x = 0; x < n4; x++) { lmode4[(size_t)(y4 + y) * w4 + x4 + x] = (uint8_t)lm; cmode4[(size_t)(y4 + y) * w4 + x4 + x] = (uint8_t)cm; }
@@ -374,7 +471,7 @@ extern "C" int b200_debug_parse(const uint8_t* au, size_t size, int8_t* qp8, uin
       hh ^= hh >> 29; hh *= 0x9E3779B97F4A7C15ULL; hash += hh;
     }
   }
-  out5[0] = hash; out5[1] = pp.coefs.size(); out5[2] = pp.tus.size(); out5[3] = (unsigned long long)p.width; out5[4] = (unsigned long long)p.height;
+  out5[0] = hash; out5[1] = pp.n_coefs; out5[2] = pp.n_tus; out5[3] = (unsigned long long)p.width; out5[4] = (unsigned long long)p.height;
   return B200_OK;
 }
 

@@ -1,0 +1,100 @@
+// b200_hevc_entropy.cu -- K0: CABAC entropy decoding + slice-data syntax on the GPU.
+//
+// The serial half of libde265's decode (H.265 9.3 CABAC, 7.3.8 coding-quadtree syntax, 8.4.2 / 8.6.1 derivations) for
+// a whole batch of tiles at once: ONE WARP PER CABAC SUB-STREAM (lane 0 runs the shared syntax decoder of
+// b200_hevc_syntax.h, the same source the host front-end uses).  With entropy_coding_sync every CTB row is its own
+// sub-stream, located by the slice header's entry points, so a 16384x16384 grid of 1024x1024 tiles exposes 8192
+// independent-ish streams: rows of one picture advance as a wavefront (context hand-over after the 2nd CTB of the row
+// above, 9.3.2.2), pictures are independent.  Sub-streams are handed out by a global ticket in "k-th sub-stream of every
+// picture" order, so a dependency always holds a smaller ticket (no deadlock, no co-residency requirement).
+// Output: the command stream of b200_hevc_types.h, written into fixed per-CTB slots in HBM (worst-case sized; only the
+// used entries are ever touched).  Why on the GPU: the host has 16 usable cores on the target box and CABAC is the
+// end-to-end bottleneck there; the arithmetic decoder is serial per sub-stream but there are thousands of sub-streams.
+#include "b200_hevc.h"
+
+namespace b200 {
+
+constexpr int EWARPS = 4;
+
+__device__ __forceinline__ unsigned e_ld_acquire(const unsigned* p) {
+  unsigned v; asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory"); return v;
+}
+__device__ __forceinline__ void e_st_release(unsigned* p, unsigned v) {
+  asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+struct DevSync {
+  unsigned* progress;      // per CTB row of this picture
+  unsigned* sub_done;      // per sub-stream of this picture
+  unsigned* error_flag;
+  uint32_t dense_tu, dense_coef, dense_tu_cap, dense_coef_cap;   // unused on the device (fixed slots)
+  uint64_t end_bit_position;
+  __device__ void wait_row(int row, int need) {
+    unsigned spins = 0;
+    while (e_ld_acquire(progress + row) < (unsigned)need) { __nanosleep(64); if (++spins > (1u << 26)) { atomicExch(error_flag, 3u); break; } }
+  }
+  __device__ void publish_row(int row, int done) { __threadfence(); e_st_release(progress + row, (unsigned)done); }
+  __device__ void wait_substream(int idx) {
+    unsigned spins = 0;
+    while (e_ld_acquire(sub_done + idx) == 0u) { __nanosleep(64); if (++spins > (1u << 26)) { atomicExch(error_flag, 3u); break; } }
+  }
+  __device__ void finish_substream(int idx, int err) {
+    __threadfence(); e_st_release(sub_done + idx, 1u);
+    if (err) atomicExch(error_flag, (unsigned)err);
+  }
+};
+
+__global__ void __launch_bounds__(EWARPS * 32) hevc_entropy_kernel(const EntropyBatch b) {
+  __shared__ uint8_t s_ctx[EWARPS][syn::CTX_STRIDE];
+  if ((threadIdx.x & 31) != 0) return;                      // lane 0 of every warp decodes; CABAC is serial per sub-stream
+  uint8_t* ctx = s_ctx[threadIdx.x >> 5];
+  for (;;) {
+    const unsigned t = atomicAdd(b.ticket, 1u);
+    if (t >= (unsigned)b.nsubs) break;
+    const uint2 ref = b.order[t];                            // (picture, local sub-stream index)
+    const EntropyPic& ep = b.pics[ref.x];
+    DevSync sync;
+    sync.progress = b.progress + ep.progress_base; sync.sub_done = b.sub_done + ep.sub_base; sync.error_flag = b.error_flag;
+    sync.dense_tu = sync.dense_coef = sync.dense_tu_cap = sync.dense_coef_cap = 0; sync.end_bit_position = 0;
+    syn::run_substream(ep.sp, ep.pb, b.subs + ep.sub_base, (int)ref.y, ctx, sync);
+  }
+}
+
+// sums the per-CTB TU / coefficient counts (statistics only: command-stream bytes actually produced)
+__global__ void entropy_stats_kernel(const EntropyBatch b, unsigned long long* out2) {
+  const int pi = blockIdx.y;
+  const EntropyPic& ep = b.pics[pi];
+  const int nctb = ep.sp.wctb * ep.sp.hctb;
+  unsigned long long tus = 0, coefs = 0;
+  for (int a = blockIdx.x * blockDim.x + threadIdx.x; a < nctb; a += gridDim.x * blockDim.x) {
+    const CtuInfo ci = ep.pb.ctus[a];
+    tus += ci.tu_count;
+    for (unsigned k = 0; k < ci.tu_count; k++) { const TuCmd t = ep.pb.tus[ci.tu_start + k]; coefs += (t.w3 & 0x7ff) + ((t.w3 >> 11) & 0x3ff) + ((t.w3 >> 21) & 0x3ff); }
+  }
+  atomicAdd(out2, tus); atomicAdd(out2 + 1, coefs);
+}
+
+int launch_entropy(const EntropyBatch& b, cudaStream_t s) {
+  if (b.nsubs <= 0) return B200_OK;
+  static bool limit_set = false;
+  if (!limit_set) { cudaDeviceSetLimit(cudaLimitStackSize, 8192); limit_set = true; }   // recursion of the quadtree / transform tree
+  int dev = 0, sms = 148; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  int occ = 1; cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, hevc_entropy_kernel, EWARPS * 32, 0);
+  if (occ < 1) occ = 1;
+  const int want = (b.nsubs + EWARPS - 1) / EWARPS;
+  const int grid = want < sms * occ ? want : sms * occ;
+  hevc_entropy_kernel<<<grid, EWARPS * 32, 0, s>>>(b);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return set_error(B200_E_CUDA, "entropy launch: %s", cudaGetErrorString(e));
+  return B200_OK;
+}
+
+int launch_entropy_stats(const EntropyBatch& b, unsigned long long* out2, cudaStream_t s) {
+  if (b.npics <= 0) return B200_OK;
+  entropy_stats_kernel<<<dim3(8, b.npics), 128, 0, s>>>(b, out2);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return set_error(B200_E_CUDA, "entropy stats launch: %s", cudaGetErrorString(e));
+  return B200_OK;
+}
+
+}  // namespace b200

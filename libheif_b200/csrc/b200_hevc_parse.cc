@@ -1,17 +1,19 @@
-// b200_hevc_parse.cc -- host HEVC front-end: NAL units -> command stream for the sm_100a reconstruction kernels.
+// b200_hevc_parse.cc -- host HEVC front-end: NAL units -> headers -> (optionally) command stream.
 //
 // Replaces the serial half of what libde265 does behind libheif/plugins/decoder_libde265.cc:322-457
-// (de265_push_NAL / de265_decode): emulation-prevention removal, VPS/SPS/PPS/slice-header parsing (H.265 7.3.1-7.3.6),
-// CABAC (9.3) and the coding-quadtree syntax (7.3.8), intra-mode derivation (8.4.2) and QP derivation (8.6.1).
+// (de265_push_NAL / de265_decode).  Two stages:
+//   parse_headers()      emulation-prevention removal, VPS/SPS/PPS/slice-segment headers (H.265 7.3.1-7.3.6), security
+//                        limit, and the split of every slice segment into CABAC sub-streams (entry points, 7.3.6.1).
+//   parse_access_unit()  = parse_headers() + slice data decoded on the host with the shared syntax decoder
+//                        (b200_hevc_syntax.h), sequentially; the device front-end (b200_hevc_entropy.cu) runs the very
+//                        same code with one warp per sub-stream instead.
 // Input framing is libheif's: [uint32 BE length][NAL]... (libheif/codecs/decoder.cc:275-308).
-// No pixel is touched here; see b200_hevc_types.h for the division of labour.
 #include "b200_hevc.h"
 #include <algorithm>
 
 namespace b200 {
 namespace {
 
-// ---------------------------------------------------------------------------------------------- bit reader
 struct BitRd {
   const uint8_t* d; size_t n; size_t pos;
   unsigned bit() { unsigned v = (pos >> 3) < n ? (d[pos >> 3] >> (7 - (pos & 7))) & 1 : 0; pos++; return v; }
@@ -34,122 +36,25 @@ struct Pps {
   int beta_offset = 0, tc_offset = 0, slice_ext_present = 0, log2_sao_scale_luma = 0, log2_sao_scale_chroma = 0;
 };
 
-enum { CTX_SAO_MERGE = 0, CTX_SAO_TYPE = 1, CTX_SPLIT_CU = 2, CTX_PART_MODE = 5, CTX_PREV_INTRA = 6,
-       CTX_CHROMA_PRED = 7, CTX_SPLIT_TR = 8, CTX_CBF_LUMA = 11, CTX_CBF_CHROMA = 13, CTX_QP_DELTA = 18,
-       CTX_TSKIP = 20, CTX_LAST_X = 22, CTX_LAST_Y = 40, CTX_CSBF = 58, CTX_SIG = 62, CTX_GT1 = 104,
-       CTX_GT2 = 128, CTX_COUNT = 134 };
-
-const uint8_t kInitI[CTX_COUNT] = {
-  153, 200, 139, 141, 157, 184, 184, 63, 153, 138, 138, 111, 141, 94, 138, 182, 154, 154, 154, 154, 139, 139,
-  110, 110, 124, 125, 140, 153, 125, 127, 140, 109, 111, 143, 127, 111, 79, 108, 123, 63,
-  110, 110, 124, 125, 140, 153, 125, 127, 140, 109, 111, 143, 127, 111, 79, 108, 123, 63,
-  91, 171, 134, 141,
-  111, 111, 125, 110, 110, 94, 124, 108, 124, 107, 125, 141, 179, 153, 125, 107, 125, 141, 179, 153, 125,
-  107, 125, 141, 179, 153, 125, 140, 139, 182, 182, 152, 136, 152, 136, 153, 136, 139, 111, 136, 139, 111,
-  140, 92, 137, 138, 140, 152, 138, 139, 153, 74, 149, 92, 139, 107, 122, 152, 140, 179, 166, 182, 140, 227, 122, 197,
-  138, 153, 136, 167, 152, 152};
-const uint8_t kLps[64][4] = {
-  {128,176,208,240},{128,167,197,227},{128,158,187,216},{123,150,178,205},{116,142,169,195},{111,135,160,185},
-  {105,128,152,175},{100,122,144,166},{95,116,137,158},{90,110,130,150},{85,104,123,142},{81,99,117,135},
-  {77,94,111,128},{73,89,105,122},{69,85,100,116},{66,80,95,110},{62,76,90,104},{59,72,86,99},{56,69,81,94},
-  {53,65,77,89},{51,62,73,85},{48,59,69,80},{46,56,66,76},{43,53,63,72},{41,50,59,69},{39,48,56,65},
-  {37,45,54,62},{35,43,51,59},{33,41,48,56},{32,39,46,53},{30,37,43,50},{29,35,41,48},{27,33,39,45},
-  {26,31,37,43},{24,30,35,41},{23,28,33,39},{22,27,32,37},{21,26,30,35},{20,24,29,33},{19,23,27,31},
-  {18,22,26,30},{17,21,25,28},{16,20,23,27},{15,19,22,25},{14,18,21,24},{14,17,20,23},{13,16,19,22},
-  {12,15,18,21},{12,14,17,20},{11,14,16,19},{11,13,15,18},{10,12,15,17},{10,12,14,16},{9,11,13,15},
-  {9,11,12,14},{8,10,12,14},{8,9,11,13},{7,9,11,12},{7,9,10,12},{7,8,10,11},{6,8,9,11},{6,7,9,10},
-  {6,7,8,9},{2,2,2,2}};
-const uint8_t kTransLps[64] = {0,0,1,2,2,4,4,5,6,7,8,9,9,11,11,12,13,13,15,15,16,16,18,18,19,19,21,21,22,22,23,24,
-  24,25,26,26,27,27,28,29,29,30,30,30,31,32,32,33,33,33,34,34,35,35,35,36,36,36,37,37,37,38,38,63};
-const uint8_t kSigMap4[16] = {0, 1, 4, 5, 2, 3, 4, 5, 6, 6, 8, 8, 7, 7, 8, 8};
-
-uint8_t g_sx[4][3][64], g_sy[4][3][64];
-bool g_scan_ready = false;
-void init_scans() {
-  if (g_scan_ready) return;
-  for (int l = 0; l <= 3; l++) {
-    int n = 1 << l, i = 0, x = 0, y = 0; bool stop = false;
-    while (!stop) {
-      while (y >= 0) { if (x < n && y < n) { g_sx[l][0][i] = (uint8_t)x; g_sy[l][0][i] = (uint8_t)y; i++; } y--; x++; }
-      y = x; x = 0; if (i >= n * n) stop = true;
-    }
-    i = 0; for (y = 0; y < n; y++) for (x = 0; x < n; x++) { g_sx[l][1][i] = (uint8_t)x; g_sy[l][1][i] = (uint8_t)y; i++; }
-    i = 0; for (x = 0; x < n; x++) for (y = 0; y < n; y++) { g_sx[l][2][i] = (uint8_t)x; g_sy[l][2][i] = (uint8_t)y; i++; }
-  }
-  g_scan_ready = true;
-}
-struct ScanInit { ScanInit() { init_scans(); } } g_scan_init;
-
 inline int clip3(int lo, int hi, int v) { return v < lo ? lo : (v > hi ? hi : v); }
 int ceil_log2(unsigned v) { int r = 0; while ((1u << r) < v) r++; return r; }
 
-size_t unescape(const uint8_t* in, size_t n, uint8_t* out) {
+// 7.4.2: strip emulation_prevention_three_byte; records the NAL offsets of the removed bytes
+size_t unescape(const uint8_t* in, size_t n, uint8_t* out, std::vector<uint32_t>* epb) {
   size_t o = 0; int zeros = 0;
   for (size_t i = 0; i < n; i++) {
-    if (zeros >= 2 && in[i] == 3) { zeros = 0; continue; }
+    if (zeros >= 2 && in[i] == 3) { zeros = 0; if (epb) epb->push_back((uint32_t)i); continue; }
     out[o++] = in[i];
     zeros = in[i] == 0 ? zeros + 1 : 0;
   }
   return o;
 }
 
-// ---------------------------------------------------------------------------------------------- CABAC (9.3.4.3)
-// Literal 9-bit-offset arithmetic decoder with a 64-bit bit reservoir, so that the bit position after a terminating
-// bin is the one the specification defines (needed to find the next WPP sub-stream without trusting entry points).
-struct Cabac {
-  const uint8_t* d; size_t n; size_t byte_pos; uint64_t res; int avail; unsigned range, offset;
-  void start(const uint8_t* data, size_t size, size_t start_byte) { d = data; n = size; byte_pos = start_byte; res = 0; avail = 0; range = 510; offset = take(9); }
-  inline void refill() { while (avail <= 56) { uint64_t b = byte_pos < n ? d[byte_pos] : 0; byte_pos++; res |= b << (56 - avail); avail += 8; } }
-  inline unsigned take(int k) { if (avail < k) refill(); unsigned v = (unsigned)(res >> (64 - k)); res <<= k; avail -= k; return v; }
-  size_t bit_position() const { return byte_pos * 8 - (size_t)avail; }
-  inline int bin(uint8_t& c) {
-    unsigned state = c >> 1, mps = c & 1;
-    unsigned lps = kLps[state][(range >> 6) & 3];
-    range -= lps;
-    int b;
-    if (offset >= range) {
-      b = !mps; offset -= range; range = lps;
-      if (state == 0) mps ^= 1;
-      c = (uint8_t)((kTransLps[state] << 1) | mps);
-      int sh = __builtin_clz(range) - 23;
-      range <<= sh; offset = (offset << sh) | take(sh);
-    } else {
-      b = (int)mps;
-      if (state < 62) c = (uint8_t)(c + 2);
-      if (range < 256) { range <<= 1; offset = (offset << 1) | take(1); }
-    }
-    return b;
-  }
-  inline int bypass() { offset = (offset << 1) | take(1); if (offset >= range) { offset -= range; return 1; } return 0; }
-  inline unsigned bypass_bits(int k) { unsigned v = 0; while (k-- > 0) v = (v << 1) | (unsigned)bypass(); return v; }
-  inline int terminate() {
-    range -= 2;
-    if (offset >= range) return 1;
-    if (range < 256) { range <<= 1; offset = (offset << 1) | take(1); }
-    return 0;
-  }
-  // after a terminating bin == 1 every bit written by the encoder's flush has been consumed: next sub-stream starts
-  // at the next byte boundary
-  void restart_aligned() { size_t p = (bit_position() + 7) >> 3; start(d, n, p); }
-};
-
-void init_ctx(uint8_t* ctx, int slice_qp) {
-  int qp = clip3(0, 51, slice_qp);
-  for (int i = 0; i < CTX_COUNT; i++) {
-    int iv = kInitI[i], m = (iv >> 4) * 5 - 45, nn = ((iv & 15) << 3) - 16;
-    int pre = clip3(1, 126, ((m * qp) >> 4) + nn);
-    int mps = pre > 63, st = mps ? pre - 64 : 63 - pre;
-    ctx[i] = (uint8_t)((st << 1) | mps);
-  }
-}
-
-struct SaoRaw { int type[3], band[3], eo[3], off[3][4]; };
-
-// ---------------------------------------------------------------------------------------------- parser
-class Parser {
+class HeaderParser {
  public:
-  Parser(ParsedPicture& out, const ParseLimits& lim) : P(out), L(lim) {}
+  HeaderParser(PictureHeaders& out, const ParseLimits& lim) : P(out), L(lim) {}
   int run(const uint8_t* data, size_t size) {
+    P.slices.clear(); P.subs.clear(); P.rbsp.clear(); P.ctu_slice.clear();
     std::vector<uint8_t> rbsp(size + 16);
     size_t p = 0; int rc = B200_OK;
     while (p + 4 <= size && rc == B200_OK) {
@@ -159,7 +64,8 @@ class Parser {
       if (n >= 2) {
         int type = (data[p] >> 1) & 0x3f;
         if (type == 33 || type == 34 || (type >= 16 && type <= 21) || type <= 9) {
-          size_t rn = unescape(data + p, n, rbsp.data());
+          epb.clear();
+          size_t rn = unescape(data + p, n, rbsp.data(), &epb);
           memset(rbsp.data() + rn, 0, 8);
           if (type == 33) rc = parse_sps(rbsp.data(), rn);
           else if (type == 34) rc = parse_pps(rbsp.data(), rn);
@@ -171,33 +77,20 @@ class Parser {
     }
     if (rc != B200_OK) return rc;
     if (!started) return set_error(B200_E_BITSTREAM, "no picture in access unit");
-    for (size_t i = 0; i < slice_of4.size(); i++) if (!slice_of4[i]) return set_error(B200_E_BITSTREAM, "picture incomplete (missing slice segments)");
-    finalize();
-    return B200_OK;
+    return finish();
   }
 
  private:
-  ParsedPicture& P; const ParseLimits& L;
+  PictureHeaders& P; const ParseLimits& L;
   Sps sps_tab[16]; Pps pps_tab[64];
   const Sps* S = nullptr; const Pps* PP = nullptr;
   bool started = false;
-  int W = 0, H = 0, log2ctb = 0, ctb = 0, wctb = 0, hctb = 0, w4 = 0, h4 = 0, w8 = 0, h8 = 0, chroma = 0, bd = 8;
-  std::vector<uint16_t> slice_of4; std::vector<uint8_t> ipm4, cd4, edge4; std::vector<int8_t> qp4;
-  std::vector<SaoRaw> sao_raw;
-  Cabac cabac; uint8_t ctx[CTX_COUNT], ctx_wpp[CTX_COUNT];
-  int slice_qp = 26, sao_luma = 0, sao_chroma = 0, slice_idx = -1, slice_addr_rs = 0, cur_cb_off = 0, cur_cr_off = 0;
-  int qg_log2 = 3, is_dqp_coded = 0, dqp_val = 0, qpy_prev_qg = 0, last_cu_qpy = 0, first_qg = 1, cur_qpy = 26;
-  int err = B200_OK;
+  std::vector<uint32_t> epb;
+  int slice_idx = -1, slice_addr_rs = 0, slice_qp = 26, sao_luma = 0, sao_chroma = 0, last_seg_sub = -1;
+  int total = 0;
+  struct Seg { int addr; int first_sub; int nsubs; };
+  std::vector<Seg> segs;
 
-  struct Cu { int x0, y0, log2cb, nxn, lmode[4], cmode; };
-
-  bool avail(int x, int y) const {
-    if (x < 0 || y < 0 || x >= W || y >= H) return false;
-    unsigned s = slice_of4[(size_t)(y >> 2) * w4 + (x >> 2)];
-    return s != 0 && s == (unsigned)(slice_idx + 1);
-  }
-
-  // -------- parameter sets (7.3.2.2 / 7.3.2.3)
   static void skip_ptl(BitRd& b, int msl) {
     b.bits(8); b.bits(32); b.bits(4); b.bits(32); b.bits(11); b.bit(); b.bits(8);
     int pp[8], lp[8];
@@ -226,7 +119,7 @@ class Parser {
       for (int k = 0; k < nal + vcl; k++) for (int c = 0; c <= cnt; c++) { b.ue(); b.ue(); if (sub) { b.ue(); b.ue(); } b.bit(); }
     }
   }
-  int parse_sps(const uint8_t* r, size_t n) {
+  int parse_sps(const uint8_t* r, size_t n) {                                  // 7.3.2.2
     BitRd b{r, n, 16}; Sps s;
     b.bits(4); int msl = b.bits(3); b.bit();
     skip_ptl(b, msl);
@@ -267,13 +160,13 @@ class Parser {
     }
     if (s.chroma_format_idc > 1) return set_error(B200_E_UNSUPPORTED, "chroma_format_idc %d (only 4:2:0 and 4:0:0)", s.chroma_format_idc);
     if (s.bit_depth != bdc || s.bit_depth > 12) return set_error(B200_E_UNSUPPORTED, "bit depth luma %d chroma %d", s.bit_depth, bdc);
-    if (s.log2_ctb > 6 || s.log2_ctb < 4 || s.log2_max_tb > 5 || s.log2_min_cb > s.log2_ctb) return set_error(B200_E_BITSTREAM, "block size configuration");
+    if (s.log2_ctb > 6 || s.log2_ctb < 4 || s.log2_max_tb > 5 || s.log2_min_cb > s.log2_ctb || s.log2_max_tb > s.log2_ctb) return set_error(B200_E_BITSTREAM, "block size configuration");
     if (s.width <= 0 || s.height <= 0 || s.width > 16384 || s.height > 16384 || (s.width & ((1 << s.log2_min_cb) - 1)) || (s.height & ((1 << s.log2_min_cb) - 1)))
       return set_error(B200_E_BITSTREAM, "picture size %dx%d", s.width, s.height);
     s.valid = true; sps_tab[id] = s;
     return B200_OK;
   }
-  int parse_pps(const uint8_t* r, size_t n) {
+  int parse_pps(const uint8_t* r, size_t n) {                                  // 7.3.2.3
     BitRd b{r, n, 16}; Pps p;
     unsigned id = b.ue(); if (id > 63) return set_error(B200_E_BITSTREAM, "pps id");
     p.sps_id = b.ue(); if (p.sps_id > 15) return set_error(B200_E_BITSTREAM, "pps sps id");
@@ -305,30 +198,38 @@ class Parser {
   }
 
   int start_picture() {
-    W = S->width; H = S->height; log2ctb = S->log2_ctb; ctb = 1 << log2ctb; chroma = S->chroma_format_idc; bd = S->bit_depth;
+    const int W = S->width, H = S->height, log2ctb = S->log2_ctb, ctb = 1 << log2ctb;
     if (L.max_image_size_pixels && (uint64_t)W * H > L.max_image_size_pixels)
       return set_error(B200_E_LIMIT, "coded picture %dx%d exceeds the security limit of %llu pixels", W, H, (unsigned long long)L.max_image_size_pixels);
-    wctb = (W + ctb - 1) >> log2ctb; hctb = (H + ctb - 1) >> log2ctb; w4 = W >> 2; h4 = H >> 2; w8 = W >> 3; h8 = H >> 3;
-    size_t n4 = (size_t)w4 * h4;
-    slice_of4.assign(n4, 0); ipm4.assign(n4, 1); cd4.assign(n4, 0); edge4.assign(n4, 0); qp4.assign(n4, 0);
-    sao_raw.assign((size_t)wctb * hctb, SaoRaw{});
-    P.ctus.assign((size_t)wctb * hctb, CtuInfo{});
-    P.tus.clear(); P.coefs.clear(); P.slices.clear();
-    P.tus.reserve((size_t)W * H / 96); P.coefs.reserve((size_t)W * H / 6);
     PicDesc& d = P.desc; memset(&d, 0, sizeof d);
-    d.width = W; d.height = H; d.log2_ctb = log2ctb; d.wctb = wctb; d.hctb = hctb; d.bit_depth = bd; d.chroma = chroma;
-    int sub = chroma ? 2 : 1;
+    d.width = W; d.height = H; d.log2_ctb = log2ctb; d.wctb = (W + ctb - 1) >> log2ctb; d.hctb = (H + ctb - 1) >> log2ctb;
+    d.bit_depth = S->bit_depth; d.chroma = S->chroma_format_idc;
+    const int sub = d.chroma ? 2 : 1;
     d.crop_x = S->conf_l * sub; d.crop_y = S->conf_t * sub;
     d.out_w = W - (S->conf_l + S->conf_r) * sub; d.out_h = H - (S->conf_t + S->conf_b) * sub;
     if (d.out_w <= 0 || d.out_h <= 0) return set_error(B200_E_BITSTREAM, "conformance window");
-    d.strong_intra = S->strong_intra; d.sao_enabled = S->sao; d.w8 = w8; d.h8 = h8;
+    d.strong_intra = S->strong_intra; d.sao_enabled = S->sao; d.w8 = W >> 3; d.h8 = H >> 3;
+    total = d.wctb * d.hctb;
+    P.ctu_slice.assign((size_t)total, 0xffff);
     P.colour_primaries = S->vui_colour ? S->vui_cp : 2; P.transfer_characteristics = S->vui_colour ? S->vui_tc : 2;
     P.matrix_coefficients = S->vui_colour ? S->vui_mc : 2; P.full_range = S->vui_signal ? S->vui_full_range : 0;
     started = true;
     return B200_OK;
   }
 
-  // -------- slice segment (7.3.6.1, 7.3.8.1)
+  void fill_seq_params() {
+    syn::SeqParams& q = P.sp; memset(&q, 0, sizeof q);
+    const PicDesc& d = P.desc;
+    q.W = d.width; q.H = d.height; q.log2ctb = d.log2_ctb; q.wctb = d.wctb; q.hctb = d.hctb; q.w4 = d.width >> 2; q.w8 = d.w8; q.h8 = d.h8;
+    q.chroma = d.chroma; q.bd = d.bit_depth;
+    q.log2_min_cb = S->log2_min_cb; q.log2_min_tb = S->log2_min_tb; q.log2_max_tb = S->log2_max_tb; q.max_th_depth_intra = S->max_th_depth_intra;
+    q.sao_enabled = S->sao; q.transform_skip = PP->transform_skip; q.cu_qp_delta = PP->cu_qp_delta; q.qg_log2 = d.log2_ctb - PP->diff_cu_qp_delta_depth;
+    q.sign_hiding = PP->sign_hiding; q.wpp = PP->wpp; q.sao_scale_luma = PP->log2_sao_scale_luma; q.sao_scale_chroma = PP->log2_sao_scale_chroma;
+    const int ctb = 1 << d.log2_ctb;
+    q.tu_slots = (ctb / 4) * (ctb / 4); q.coef_slots = ctb * ctb * (d.chroma ? 3 : 2) / 2;
+  }
+
+  // 7.3.6.1 slice_segment_header; then the split of the segment data into sub-streams
   int slice_segment(const uint8_t* r, size_t n, int nal_type) {
     BitRd b{r, n, 16};
     int first = b.bit();
@@ -336,13 +237,19 @@ class Parser {
     unsigned pid = b.ue();
     if (pid > 63 || !pps_tab[pid].valid || !sps_tab[pps_tab[pid].sps_id].valid) return set_error(B200_E_BITSTREAM, "slice refers to missing parameter sets");
     const Pps* p = &pps_tab[pid]; const Sps* s = &sps_tab[p->sps_id];
-    if (first) { if (started) return set_error(B200_E_UNSUPPORTED, "more than one picture in the access unit"); S = s; PP = p; int rc = start_picture(); if (rc) return rc; }
-    else if (!started) return set_error(B200_E_BITSTREAM, "slice segment before the first one of the picture");
-    PP = p;
+    if (first) {
+      if (started) return set_error(B200_E_UNSUPPORTED, "more than one picture in the access unit");
+      S = s; PP = p; int rc = start_picture(); if (rc) return rc;
+      fill_seq_params();
+      if (P.sp.qg_log2 < 3) return set_error(B200_E_BITSTREAM, "diff_cu_qp_delta_depth");
+    } else if (!started) return set_error(B200_E_BITSTREAM, "slice segment before the first one of the picture");
+    else if (p != PP) return set_error(B200_E_UNSUPPORTED, "slice segments of one picture use different PPS");
     P.desc.pps_cb_qp_offset = p->cb_qp_offset; P.desc.pps_cr_qp_offset = p->cr_qp_offset;
     P.desc.log2_sao_scale_luma = p->log2_sao_scale_luma; P.desc.log2_sao_scale_chroma = p->log2_sao_scale_chroma;
-    int dependent = 0, seg_addr = 0, total = wctb * hctb;
+    const int wctb = P.desc.wctb;
+    int dependent = 0, seg_addr = 0;
     if (!first) { if (p->dependent_slices) dependent = b.bit(); seg_addr = b.bits(ceil_log2((unsigned)total)); if (seg_addr >= total) return set_error(B200_E_BITSTREAM, "slice_segment_address"); }
+    if (!segs.empty() && seg_addr <= segs.back().addr) return set_error(B200_E_BITSTREAM, "slice segments out of order");
     if (!dependent) {
       b.bits(p->num_extra_bits);
       if (b.ue() != 2) return set_error(B200_E_UNSUPPORTED, "P/B slices are not supported (intra-only decoder)");
@@ -362,356 +269,162 @@ class Parser {
         if (S->temporal_mvp) b.bit();
       }
       sao_luma = sao_chroma = 0;
-      if (S->sao) { sao_luma = b.bit(); if (chroma) sao_chroma = b.bit(); }
+      if (S->sao) { sao_luma = b.bit(); if (P.desc.chroma) sao_chroma = b.bit(); }
       slice_qp = p->init_qp + b.se();
-      cur_cb_off = cur_cr_off = 0;
-      if (p->slice_chroma_qp_offsets) { cur_cb_off = b.se(); cur_cr_off = b.se(); }
+      int cb_off = 0, cr_off = 0;
+      if (p->slice_chroma_qp_offsets) { cb_off = b.se(); cr_off = b.se(); }
       int dis = p->deblock_disabled, beta = p->beta_offset, tc = p->tc_offset, ovr = 0;
       if (p->deblock_override_enabled) ovr = b.bit();
       if (ovr) { dis = b.bit(); if (!dis) { beta = 2 * b.se(); tc = 2 * b.se(); } }
       int across = p->lf_across_slices;
       if (p->lf_across_slices && (sao_luma || sao_chroma || !dis)) across = b.bit();
       if (P.slices.size() >= 65000) return set_error(B200_E_UNSUPPORTED, "too many slices");
-      SliceInfo si{}; si.cb_qp_offset = (int8_t)clip3(-24, 24, p->cb_qp_offset + cur_cb_off); si.cr_qp_offset = (int8_t)clip3(-24, 24, p->cr_qp_offset + cur_cr_off);
+      SliceInfo si{}; si.cb_qp_offset = (int8_t)clip3(-24, 24, p->cb_qp_offset + cb_off); si.cr_qp_offset = (int8_t)clip3(-24, 24, p->cr_qp_offset + cr_off);
       si.beta_offset = (int8_t)clip3(-12, 12, beta); si.tc_offset = (int8_t)clip3(-12, 12, tc);
       si.deblocking_disabled = (uint8_t)dis; si.lf_across_slices = (uint8_t)across; si.first_ctb_rs = (uint32_t)seg_addr;
       P.slices.push_back(si);
       slice_idx = (int)P.slices.size() - 1; slice_addr_rs = seg_addr;
     } else if (slice_idx < 0) return set_error(B200_E_BITSTREAM, "dependent slice segment without a slice");
-    if (p->wpp) { int ne = b.ue(); if (ne > 0) { int len = b.ue() + 1; for (int i = 0; i < ne; i++) b.bits(len); } }
+    std::vector<uint32_t> entry;
+    if (p->wpp) { int ne = b.ue(); if (ne > total) return set_error(B200_E_BITSTREAM, "num_entry_point_offsets"); if (ne > 0) { int len = b.ue() + 1; if (len > 32) return set_error(B200_E_BITSTREAM, "offset_len_minus1"); for (int i = 0; i < ne; i++) entry.push_back(b.bits(len) + 1); } }
     if (p->slice_ext_present) { int len = b.ue(); for (int i = 0; i < len; i++) b.bits(8); }
     b.bit(); b.pos = (b.pos + 7) & ~(size_t)7;
-    qg_log2 = log2ctb - p->diff_cu_qp_delta_depth;
-    if (qg_log2 < 3) return set_error(B200_E_BITSTREAM, "diff_cu_qp_delta_depth");
-    if (!dependent) { init_ctx(ctx, slice_qp); last_cu_qpy = slice_qp; first_qg = 1; }
-    cabac.start(r, n, b.pos >> 3);
-    int a = seg_addr;
-    for (;;) {
-      int rx = a % wctb, ry = a / wctb;
-      if (p->wpp && rx == 0 && (a != seg_addr || (dependent && ry > 0))) {
-        if (avail(ctb, (ry - 1) << log2ctb)) memcpy(ctx, ctx_wpp, sizeof ctx);
-        else if (a != seg_addr) init_ctx(ctx, slice_qp);
-        first_qg = 1;
+    const size_t hdr_rbsp = b.pos >> 3;
+    if (hdr_rbsp > n) return set_error(B200_E_BITSTREAM, "slice header runs past the NAL");
+    // ---- append the segment's data to the picture's RBSP buffer (4-byte aligned start)
+    while (P.rbsp.size() & 3) P.rbsp.push_back(0);
+    const uint32_t base = (uint32_t)P.rbsp.size();
+    P.rbsp.insert(P.rbsp.end(), r + hdr_rbsp, r + n);
+    const uint32_t data_len = (uint32_t)(n - hdr_rbsp);
+    // ---- sub-streams: with WPP one per CTB row of the segment, located by the entry points (NAL offsets include the
+    // emulation prevention bytes, 7.4.7.1: convert to RBSP offsets)
+    size_t hdr_epb = 0;
+    { size_t nal_pos = 0, k = 0; // number of removed bytes inside the header: NAL position of RBSP byte hdr_rbsp
+      for (nal_pos = hdr_rbsp; k < epb.size() && epb[k] < nal_pos + 1; k++) nal_pos++;
+      hdr_epb = k; }
+    const size_t hdr_nal = hdr_rbsp + hdr_epb;
+    Seg sg; sg.addr = seg_addr; sg.first_sub = (int)P.subs.size(); sg.nsubs = 0;
+    auto add_sub = [&](uint32_t cb, uint32_t ce, uint32_t byte_begin, bool first_sub) {
+      syn::Substream ss{}; ss.pic = 0; ss.byte_begin = base + byte_begin; ss.byte_end = base + data_len; ss.ctb_begin = cb; ss.ctb_end = ce;
+      ss.slice_addr_rs = (uint32_t)slice_addr_rs; ss.slice_idx = slice_idx; ss.slice_qp = slice_qp; ss.sao_luma = (uint8_t)sao_luma; ss.sao_chroma = (uint8_t)sao_chroma;
+      ss.init_contexts = (uint8_t)(first_sub && !dependent); ss.last_of_segment = 0;
+      ss.prev = (first_sub && dependent) ? last_seg_sub : -1;
+      P.subs.push_back(ss); sg.nsubs++;
+    };
+    if (p->wpp) {
+      // rows covered by this segment are only known once the next segment's address is: create row sub-streams lazily
+      // from the entry points (row k of the segment <-> entry k-1)
+      uint32_t nal_off = 0;
+      uint32_t cb = (uint32_t)seg_addr;
+      for (size_t k = 0; k <= entry.size(); k++) {
+        const uint32_t row_end = (cb / (uint32_t)wctb + 1) * (uint32_t)wctb;
+        size_t abs_nal = hdr_nal + nal_off, cnt = 0;
+        while (cnt < epb.size() && epb[cnt] < abs_nal) cnt++;
+        const uint32_t rb = (uint32_t)(abs_nal - cnt - hdr_rbsp);
+        if (rb > data_len) return set_error(B200_E_BITSTREAM, "entry point beyond the slice segment data");
+        add_sub(cb, row_end, rb, k == 0);
+        if (k < entry.size()) nal_off += entry[k];
+        cb = row_end;
+        if (cb >= (uint32_t)total) break;
       }
-      CtuInfo& ci = P.ctus[a];
-      ci.tu_start = (uint32_t)P.tus.size(); ci.slice_idx = (uint16_t)slice_idx;
-      if (S->sao) parse_sao(rx, ry);
-      coding_quadtree(rx << log2ctb, ry << log2ctb, log2ctb, 0);
-      if (err) return err;
-      size_t cnt = P.tus.size() - ci.tu_start;
-      ci.tu_count = (uint16_t)cnt;
-      if (p->wpp && rx == 1) memcpy(ctx_wpp, ctx, sizeof ctx);
-      int end = cabac.terminate();
-      a++;
-      if (end) break;
-      if (a >= total) return set_error(B200_E_BITSTREAM, "slice data runs past the picture");
-      if (p->wpp && a % wctb == 0) { if (!cabac.terminate()) return set_error(B200_E_BITSTREAM, "end_of_subset_one_bit"); cabac.restart_aligned(); }
-      if (cabac.byte_pos > n + 16) return set_error(B200_E_BITSTREAM, "slice data truncated");
-    }
+    } else add_sub((uint32_t)seg_addr, (uint32_t)total, 0, true);
+    segs.push_back(sg);
+    last_seg_sub = (int)P.subs.size() - 1;
     return B200_OK;
   }
 
-  // -------- SAO (7.3.8.3)
-  void parse_sao(int rx, int ry) {
-    int addr = ry * wctb + rx;
-    SaoRaw& sp = sao_raw[addr]; sp = SaoRaw{};
-    if (!sao_luma && !sao_chroma) return;
-    int ml = 0, mu = 0;
-    if (rx > 0 && addr - 1 >= slice_addr_rs) ml = cabac.bin(ctx[CTX_SAO_MERGE]);
-    if (ry > 0 && !ml && addr - wctb >= slice_addr_rs) mu = cabac.bin(ctx[CTX_SAO_MERGE]);
-    if (ml) { sp = sao_raw[addr - 1]; return; }
-    if (mu) { sp = sao_raw[addr - wctb]; return; }
-    for (int c = 0; c < (chroma ? 3 : 1); c++) {
-      if ((c == 0 && !sao_luma) || (c > 0 && !sao_chroma)) continue;
-      if (c < 2) { int t = 0; if (cabac.bin(ctx[CTX_SAO_TYPE])) t = cabac.bypass() ? 2 : 1; sp.type[c] = t; } else sp.type[2] = sp.type[1];
-      if (!sp.type[c]) continue;
-      int cmax = (1 << (std::min(bd, 10) - 5)) - 1, av[4];
-      for (int i = 0; i < 4; i++) { int v = 0; while (v < cmax && cabac.bypass()) v++; av[i] = v; }
-      int sc = c == 0 ? PP->log2_sao_scale_luma : PP->log2_sao_scale_chroma;
-      if (sp.type[c] == 1) {
-        for (int i = 0; i < 4; i++) if (av[i] && cabac.bypass()) av[i] = -av[i];
-        sp.band[c] = (int)cabac.bypass_bits(5);
-        for (int i = 0; i < 4; i++) sp.off[c][i] = av[i] * (1 << sc);
-      } else {
-        if (c == 0) sp.eo[0] = (int)cabac.bypass_bits(2); else if (c == 1) sp.eo[1] = (int)cabac.bypass_bits(2); else sp.eo[2] = sp.eo[1];
-        sp.off[c][0] = av[0] << sc; sp.off[c][1] = av[1] << sc; sp.off[c][2] = -(av[2] << sc); sp.off[c][3] = -(av[3] << sc);
+  // Close the segments (each ends where the next begins), fix the CTB ranges of the sub-streams, fill ctu_slice.
+  int finish() {
+    for (size_t si = 0; si < segs.size(); si++) {
+      const uint32_t seg_end = si + 1 < segs.size() ? (uint32_t)segs[si + 1].addr : (uint32_t)total;
+      Seg& sg = segs[si];
+      int keep = 0;
+      for (int k = 0; k < sg.nsubs; k++) {
+        syn::Substream& ss = P.subs[(size_t)sg.first_sub + k];
+        if (ss.ctb_begin >= seg_end) break;
+        if (ss.ctb_end > seg_end) ss.ctb_end = seg_end;
+        keep++;
       }
-    }
-  }
-
-  // -------- QP (8.6.1)
-  void derive_qpy(int xcb, int ycb) {
-    int mask = (1 << qg_log2) - 1, xqg = xcb & ~mask, yqg = ycb & ~mask, cm = ~(ctb - 1);
-    int qa = qpy_prev_qg, qb = qpy_prev_qg;
-    if (avail(xqg - 1, yqg) && ((xqg - 1) & cm) == (xqg & cm)) qa = qp4[(size_t)(yqg >> 2) * w4 + ((xqg - 1) >> 2)];
-    if (avail(xqg, yqg - 1) && ((yqg - 1) & cm) == (yqg & cm)) qb = qp4[(size_t)((yqg - 1) >> 2) * w4 + (xqg >> 2)];
-    int pred = (qa + qb + 1) >> 1, qbd = 6 * (bd - 8);
-    cur_qpy = ((pred + dqp_val + 52 + 2 * qbd) % (52 + qbd)) - qbd;
-  }
-
-  // -------- residual_coding (7.3.8.11): emits sparse (pos, level) entries; returns the number of coefficients
-  int residual(int log2n, int c, int mode, int& tskip) {
-    const int n = 1 << log2n;
-    tskip = 0;
-    if (PP->transform_skip && log2n == 2) tskip = cabac.bin(ctx[CTX_TSKIP + (c ? 1 : 0)]);
-    int cmax = (log2n << 1) - 1, off, shift;
-    if (c == 0) { off = 3 * (log2n - 2) + ((log2n - 1) >> 2); shift = (log2n + 1) >> 2; } else { off = 15; shift = log2n - 2; }
-    int lx = 0, ly = 0;
-    while (lx < cmax && cabac.bin(ctx[CTX_LAST_X + off + (lx >> shift)])) lx++;
-    while (ly < cmax && cabac.bin(ctx[CTX_LAST_Y + off + (ly >> shift)])) ly++;
-    if (lx > 3) { int nb = (lx >> 1) - 1; lx = (1 << nb) * (2 + (lx & 1)) + (int)cabac.bypass_bits(nb); }
-    if (ly > 3) { int nb = (ly >> 1) - 1; ly = (1 << nb) * (2 + (ly & 1)) + (int)cabac.bypass_bits(nb); }
-    int scan = 0;
-    if (log2n == 2 || (log2n == 3 && c == 0)) { if (mode >= 6 && mode <= 14) scan = 2; else if (mode >= 22 && mode <= 30) scan = 1; }
-    if (scan == 2) std::swap(lx, ly);
-    if (lx >= n || ly >= n) { err = set_error(B200_E_BITSTREAM, "last significant coefficient outside the block"); return 0; }
-    const int l2sb = log2n - 2;
-    const uint8_t *sbx = g_sx[l2sb][scan], *sby = g_sy[l2sb][scan], *px = g_sx[2][scan], *py = g_sy[2][scan];
-    int last_sb = 0, last_pos = 0;
-    { int xs = lx >> 2, ys = ly >> 2, xp = lx & 3, yp = ly & 3, nsb = 1 << (2 * l2sb);
-      for (int i = 0; i < nsb; i++) if (sbx[i] == xs && sby[i] == ys) { last_sb = i; break; }
-      for (int k = 0; k < 16; k++) if (px[k] == xp && py[k] == yp) { last_pos = k; break; } }
-    uint8_t csbf[8][8]; memset(csbf, 0, sizeof csbf);
-    int carry = 1, count = 0; bool first_done = false;
-    for (int i = last_sb; i >= 0; i--) {
-      int xs = sbx[i], ys = sby[i], infer_dc = 0, coded;
-      if (i < last_sb && i > 0) {
-        int cs = 0;
-        if (xs + 1 < (1 << l2sb)) cs |= csbf[ys][xs + 1];
-        if (ys + 1 < (1 << l2sb)) cs |= csbf[ys + 1][xs];
-        coded = cabac.bin(ctx[CTX_CSBF + (cs ? 1 : 0) + (c ? 2 : 0)]);
-        infer_dc = 1;
-      } else coded = 1;
-      csbf[ys][xs] = (uint8_t)coded;
-      if (!coded) continue;
-      uint8_t sig[16] = {0};
-      int prev = 0;
-      if (xs + 1 < (1 << l2sb)) prev |= csbf[ys][xs + 1];
-      if (ys + 1 < (1 << l2sb)) prev |= csbf[ys + 1][xs] << 1;
-      int start = i == last_sb ? last_pos - 1 : 15;
-      if (i == last_sb) sig[last_pos] = 1;
-      for (int k = start; k >= 0; k--) {
-        if (k > 0 || !infer_dc) {
-          int xc = (xs << 2) + px[k], yc = (ys << 2) + py[k], sc;
-          if (log2n == 2) sc = kSigMap4[(yc << 2) + xc];
-          else if (xc + yc == 0) sc = 0;
-          else {
-            int xp = xc & 3, yp = yc & 3;
-            if (prev == 0) sc = (xp + yp == 0) ? 2 : (xp + yp < 3) ? 1 : 0;
-            else if (prev == 1) sc = yp == 0 ? 2 : (yp == 1 ? 1 : 0);
-            else if (prev == 2) sc = xp == 0 ? 2 : (xp == 1 ? 1 : 0);
-            else sc = 2;
-            if (c == 0) { if (xs || ys) sc += 3; sc += log2n == 3 ? (scan == 0 ? 9 : 15) : 21; } else sc += log2n == 3 ? 9 : 12;
-          }
-          sig[k] = (uint8_t)cabac.bin(ctx[CTX_SIG + (c == 0 ? sc : 27 + sc)]);
-          if (sig[k]) infer_dc = 0;
-        } else sig[k] = 1;
+      if (keep == 0) return set_error(B200_E_BITSTREAM, "empty slice segment");
+      if (PP->wpp) {
+        // every CTB row of the segment needs its own entry point
+        const syn::Substream& lastk = P.subs[(size_t)sg.first_sub + keep - 1];
+        if (lastk.ctb_end != seg_end) return set_error(B200_E_BITSTREAM, "missing entry points for WPP rows");
       }
-      uint8_t g1[16] = {0};
-      int first_sig = 16, last_sig = -1, ng1 = 0, last_g1 = -1, g1ctx = 1, g2 = 0;
-      int ctx_set = (i == 0 || c > 0) ? 0 : 2;
-      if (first_done && carry == 0) ctx_set++;
-      first_done = true;
-      bool any = false;
-      for (int k = 15; k >= 0; k--) if (sig[k]) {
-        any = true;
-        if (ng1 < 8) {
-          g1[k] = (uint8_t)cabac.bin(ctx[CTX_GT1 + ctx_set * 4 + std::min(3, g1ctx) + (c ? 16 : 0)]);
-          ng1++;
-          if (g1[k]) { g1ctx = 0; if (last_g1 < 0) last_g1 = k; } else if (g1ctx > 0) g1ctx++;
-        }
-        if (last_sig < 0) last_sig = k;
-        first_sig = k;
-      }
-      if (any) carry = g1ctx;
-      bool hidden = PP->sign_hiding && (last_sig - first_sig > 3);
-      if (last_g1 >= 0) g2 = cabac.bin(ctx[CTX_GT2 + ctx_set + (c ? 4 : 0)]);
-      unsigned signs = 0; int nsign = 0;
-      for (int k = 15; k >= 0; k--) if (sig[k] && (!hidden || k != first_sig)) nsign++;
-      signs = cabac.bypass_bits(nsign);
-      int nsig = 0, sum = 0, rice = 0, sidx = nsign;
-      for (int k = 15; k >= 0; k--) if (sig[k]) {
-        int base = 1 + g1[k] + (k == last_g1 ? g2 : 0), a = base;
-        if (base == ((nsig < 8) ? ((k == last_g1) ? 3 : 2) : 1)) {
-          int pre = 0; while (pre < 32 && cabac.bypass()) pre++;
-          int rem = pre <= 3 ? (pre << rice) + (int)cabac.bypass_bits(rice) : (((1 << (pre - 3)) + 3 - 1) << rice) + (int)cabac.bypass_bits(pre - 3 + rice);
-          a = base + rem;
-          if (a > 3 * (1 << rice)) rice = std::min(rice + 1, 4);
-        }
-        int neg = 0;
-        if (!hidden || k != first_sig) { sidx--; neg = (signs >> sidx) & 1; }
-        int v = neg ? -a : a;
-        if (hidden) { sum += a; if (k == first_sig && (sum & 1)) v = -v; }
-        CoefEntry e; e.pos = (uint16_t)((((ys << 2) + py[k]) << log2n) + (xs << 2) + px[k]); e.level = (int16_t)clip3(-32768, 32767, v);
-        P.coefs.push_back(e); count++;
-        nsig++;
-      }
+      for (int k = keep; k < sg.nsubs; k++) P.subs[(size_t)sg.first_sub + k].ctb_begin = P.subs[(size_t)sg.first_sub + k].ctb_end = 0;   // unused
+      P.subs[(size_t)sg.first_sub + keep - 1].last_of_segment = 1;
+      sg.nsubs = keep;
+      for (uint32_t a = (uint32_t)sg.addr; a < seg_end; a++) P.ctu_slice[a] = (uint16_t)P.subs[(size_t)sg.first_sub].slice_idx;
     }
-    return count;
-  }
-
-  // -------- transform tree / unit (7.3.8.8, 7.3.8.10)
-  void mark_tu(int x0, int y0, int log2n) {
-    int n4 = 1 << (log2n - 2), bx = x0 >> 2, by = y0 >> 2;
-    for (int y = 0; y < n4; y++) for (int x = 0; x < n4; x++) {
-      size_t i = (size_t)(by + y) * w4 + bx + x;
-      slice_of4[i] = (uint16_t)(slice_idx + 1); qp4[i] = (int8_t)cur_qpy;
-      if (x == 0) edge4[i] |= 1;
-      if (y == 0) edge4[i] |= 2;
-    }
-  }
-
-  void transform_unit(const Cu& cu, int x0, int y0, int log2n, int blk, int cbf_l, int cbf_cb, int cbf_cr, int pcb, int pcr) {
-    int cbf_c = chroma ? (log2n > 2 ? (cbf_cb | cbf_cr) : (pcb | pcr)) : 0;
-    if ((cbf_l || cbf_c) && PP->cu_qp_delta && !is_dqp_coded) {
-      int v = 0;
-      while (v < 5 && cabac.bin(ctx[CTX_QP_DELTA + (v ? 1 : 0)])) v++;
-      if (v == 5) { int k = 0; while (k < 16 && cabac.bypass()) { v += 1 << k; k++; } v += (int)cabac.bypass_bits(k); }
-      if (v && cabac.bypass()) v = -v;
-      is_dqp_coded = 1; dqp_val = v;
-      derive_qpy(cu.x0, cu.y0);
-    }
-    int pu = cu.nxn ? ((y0 >= cu.y0 + (1 << (cu.log2cb - 1))) ? 2 : 0) + ((x0 >= cu.x0 + (1 << (cu.log2cb - 1))) ? 1 : 0) : 0;
-    int lmode = cu.lmode[pu];
-    TuCmd t{};
-    size_t coef0 = P.coefs.size();
-    int ts_l = 0, ts_cb = 0, ts_cr = 0, nl = 0, ncb = 0, ncr = 0;
-    if (cbf_l) nl = residual(log2n, 0, lmode, ts_l);
-    int chroma_here = 0, ccb = 0, ccr = 0;
-    if (chroma) {
-      if (log2n > 2) { chroma_here = 1; ccb = cbf_cb; ccr = cbf_cr; if (ccb) ncb = residual(log2n - 1, 1, cu.cmode, ts_cb); if (ccr) ncr = residual(log2n - 1, 2, cu.cmode, ts_cr); }
-      else if (blk == 3) { chroma_here = 1; ccb = pcb; ccr = pcr; if (ccb) ncb = residual(2, 1, cu.cmode, ts_cb); if (ccr) ncr = residual(2, 2, cu.cmode, ts_cr); }
-    }
-    mark_tu(x0, y0, log2n);
-    t.w0 = (uint32_t)(x0 >> 2) | ((uint32_t)(y0 >> 2) << 12) | ((uint32_t)(log2n - 2) << 24) | ((uint32_t)cbf_l << 26) | ((uint32_t)ccb << 27) |
-           ((uint32_t)ccr << 28) | ((uint32_t)chroma_here << 29) | ((uint32_t)ts_l << 30) | ((uint32_t)ts_cb << 31);
-    t.w1 = (uint32_t)lmode | ((uint32_t)cu.cmode << 6) | ((uint32_t)(cur_qpy + 64) << 12) | ((uint32_t)ts_cr << 20);
-    t.w2 = (uint32_t)coef0;
-    t.w3 = (uint32_t)nl | ((uint32_t)ncb << 11) | ((uint32_t)ncr << 21);
-    P.tus.push_back(t);
-  }
-
-  void transform_tree(const Cu& cu, int x0, int y0, int log2n, int depth, int blk, int pcb, int pcr, int max_depth) {
-    if (err) return;
-    int split;
-    if (log2n <= S->log2_max_tb && log2n > S->log2_min_tb && depth < max_depth && !(cu.nxn && depth == 0)) split = cabac.bin(ctx[CTX_SPLIT_TR + 5 - log2n]);
-    else split = (log2n > S->log2_max_tb || (cu.nxn && depth == 0)) ? 1 : 0;
-    if (split && log2n <= 2) { err = set_error(B200_E_BITSTREAM, "transform split below 4x4"); return; }
-    int cb = 0, cr = 0;
-    if (chroma) {
-      if (log2n > 2) { if (depth == 0 || pcb) cb = cabac.bin(ctx[CTX_CBF_CHROMA + depth]); if (depth == 0 || pcr) cr = cabac.bin(ctx[CTX_CBF_CHROMA + depth]); }
-      else { cb = pcb; cr = pcr; }
-    }
-    if (split) {
-      int h = 1 << (log2n - 1);
-      for (int k = 0; k < 4; k++) transform_tree(cu, x0 + (k & 1) * h, y0 + (k >> 1) * h, log2n - 1, depth + 1, k, cb, cr, max_depth);
-    } else {
-      int cl = cabac.bin(ctx[CTX_CBF_LUMA + (depth == 0 ? 1 : 0)]);
-      if (log2n > 2) transform_unit(cu, x0, y0, log2n, blk, cl, cb, cr, 0, 0);
-      else transform_unit(cu, x0, y0, log2n, blk, cl, 0, 0, pcb, pcr);
-    }
-  }
-
-  int luma_mode(int x, int y, int prev, int mpm_idx, int rem) const {
-    int ca = 1, cb = 1;
-    if (avail(x - 1, y)) ca = ipm4[(size_t)(y >> 2) * w4 + ((x - 1) >> 2)];
-    if (avail(x, y - 1) && (y - 1) >= ((y >> log2ctb) << log2ctb)) cb = ipm4[(size_t)((y - 1) >> 2) * w4 + (x >> 2)];
-    int cand[3];
-    if (ca == cb) { if (ca < 2) { cand[0] = 0; cand[1] = 1; cand[2] = 26; } else { cand[0] = ca; cand[1] = 2 + ((ca + 29) % 32); cand[2] = 2 + ((ca - 2 + 1) % 32); } }
-    else { cand[0] = ca; cand[1] = cb; if (ca != 0 && cb != 0) cand[2] = 0; else if (ca != 1 && cb != 1) cand[2] = 1; else cand[2] = 26; }
-    if (prev) return cand[mpm_idx];
-    if (cand[0] > cand[1]) std::swap(cand[0], cand[1]);
-    if (cand[0] > cand[2]) std::swap(cand[0], cand[2]);
-    if (cand[1] > cand[2]) std::swap(cand[1], cand[2]);
-    int m = rem;
-    for (int i = 0; i < 3; i++) if (m >= cand[i]) m++;
-    return m;
-  }
-
-  void coding_unit(int x0, int y0, int log2cb, int depth) {
-    Cu cu{}; cu.x0 = x0; cu.y0 = y0; cu.log2cb = log2cb;
-    int n = 1 << log2cb;
-    if (log2cb == S->log2_min_cb) cu.nxn = !cabac.bin(ctx[CTX_PART_MODE]);
-    if (cu.nxn && log2cb == 3 && S->log2_min_tb > 2) { err = set_error(B200_E_BITSTREAM, "NxN partition with 8x8 minimum transform"); return; }
-    int np = cu.nxn ? 4 : 1, pb = cu.nxn ? n / 2 : n, prev[4], mi[4] = {0}, rem[4] = {0};
-    for (int i = 0; i < np; i++) prev[i] = cabac.bin(ctx[CTX_PREV_INTRA]);
-    for (int i = 0; i < np; i++) { if (prev[i]) { mi[i] = cabac.bypass(); if (mi[i]) mi[i] += cabac.bypass(); } else rem[i] = (int)cabac.bypass_bits(5); }
-    for (int i = 0; i < np; i++) {
-      int px = x0 + (i & 1) * pb, py = y0 + (i >> 1) * pb;
-      int m = luma_mode(px, py, prev[i], mi[i], rem[i]);
-      cu.lmode[i] = m;
-      for (int yy = 0; yy < pb; yy += 4) for (int xx = 0; xx < pb; xx += 4) {
-        size_t idx = (size_t)((py + yy) >> 2) * w4 + ((px + xx) >> 2);
-        ipm4[idx] = (uint8_t)m; slice_of4[idx] = (uint16_t)(slice_idx + 1);   // earlier PUs of this CU are available (6.4.2)
-      }
-    }
-    if (chroma) {
-      int v = 4; if (cabac.bin(ctx[CTX_CHROMA_PRED])) v = (int)cabac.bypass_bits(2);
-      static const uint8_t tab[4] = {0, 26, 10, 1};
-      if (v == 4) cu.cmode = cu.lmode[0]; else { cu.cmode = tab[v]; if (cu.cmode == cu.lmode[0]) cu.cmode = 34; }
-    }
-    for (int yy = 0; yy < n; yy += 4) for (int xx = 0; xx < n; xx += 4) {
-      size_t idx = (size_t)((y0 + yy) >> 2) * w4 + ((x0 + xx) >> 2);
-      slice_of4[idx] = 0; cd4[idx] = (uint8_t)depth;
-    }
-    if (!PP->cu_qp_delta) cur_qpy = slice_qp; else derive_qpy(x0, y0);
-    transform_tree(cu, x0, y0, log2cb, 0, 0, 0, 0, S->max_th_depth_intra + cu.nxn);
-    for (int yy = 0; yy < n; yy += 4) for (int xx = 0; xx < n; xx += 4) qp4[(size_t)((y0 + yy) >> 2) * w4 + ((x0 + xx) >> 2)] = (int8_t)cur_qpy;
-    last_cu_qpy = cur_qpy;
-  }
-
-  void coding_quadtree(int x0, int y0, int log2cb, int depth) {
-    if (err) return;
-    int n = 1 << log2cb, split;
-    if (x0 + n <= W && y0 + n <= H && log2cb > S->log2_min_cb) {
-      int inc = 0;
-      if (avail(x0 - 1, y0) && cd4[(size_t)(y0 >> 2) * w4 + ((x0 - 1) >> 2)] > depth) inc++;
-      if (avail(x0, y0 - 1) && cd4[(size_t)((y0 - 1) >> 2) * w4 + (x0 >> 2)] > depth) inc++;
-      split = cabac.bin(ctx[CTX_SPLIT_CU + inc]);
-    } else split = log2cb > S->log2_min_cb;
-    if (PP->cu_qp_delta && log2cb >= qg_log2) {
-      is_dqp_coded = 0; dqp_val = 0;
-      if (!split || log2cb == qg_log2) { if (first_qg) { qpy_prev_qg = slice_qp; first_qg = 0; } else qpy_prev_qg = last_cu_qpy; }
-    }
-    if (split) {
-      int h = n >> 1;
-      for (int k = 0; k < 4; k++) { int x1 = x0 + (k & 1) * h, y1 = y0 + (k >> 1) * h; if (x1 < W && y1 < H) coding_quadtree(x1, y1, log2cb - 1, depth + 1); }
-    } else coding_unit(x0, y0, log2cb, depth);
-  }
-
-  // -------- per-picture maps for the in-loop filters
-  void finalize() {
+    // drop unused sub-streams (entry points past the segment end) while keeping `prev` links valid
+    std::vector<int> remap(P.subs.size(), -1); std::vector<syn::Substream> out;
+    for (size_t i = 0; i < P.subs.size(); i++) if (P.subs[i].ctb_end > P.subs[i].ctb_begin) { remap[i] = (int)out.size(); out.push_back(P.subs[i]); }
+    for (auto& ss : out) if (ss.prev >= 0) { int pr = ss.prev; while (pr >= 0 && remap[(size_t)pr] < 0) pr--; ss.prev = pr >= 0 ? remap[(size_t)pr] : -1; }
+    P.subs.swap(out);
+    if (segs.empty() || segs[0].addr != 0) return set_error(B200_E_BITSTREAM, "first slice segment missing");
+    for (int a = 0; a < total; a++) if (P.ctu_slice[(size_t)a] == 0xffff) return set_error(B200_E_BITSTREAM, "picture incomplete (missing slice segments)");
     P.desc.nslices = (int)P.slices.size();
-    P.qp8.resize((size_t)w8 * h8); P.edge8.resize((size_t)w8 * h8);
-    for (int by = 0; by < h8; by++) for (int bx = 0; bx < w8; bx++) {
-      size_t i4 = (size_t)(by * 2) * w4 + bx * 2;
-      P.qp8[(size_t)by * w8 + bx] = qp4[i4];
-      uint8_t e = 0;
-      int sq = slice_of4[i4] - 1;
-      const SliceInfo& sl = P.slices[sq];
-      if (!sl.deblocking_disabled) {                       // 8.7.2.3: filterEdgeFlag
-        if ((edge4[i4] & 1) && bx > 0) { int sp = slice_of4[i4 - 1] - 1; if (sp == sq || sl.lf_across_slices) e |= 1; }
-        if ((edge4[i4] & 2) && by > 0) { int sp = slice_of4[i4 - (size_t)w4] - 1; if (sp == sq || sl.lf_across_slices) e |= 2; }
-      }
-      P.edge8[(size_t)by * w8 + bx] = e;
-    }
-    for (int a = 0; a < wctb * hctb; a++) {
-      const SaoRaw& r = sao_raw[a]; CtuInfo& ci = P.ctus[a];
-      for (int c = 0; c < 3; c++) {
-        ci.sao[c].type = (uint8_t)r.type[c];
-        ci.sao[c].band_or_class = (uint8_t)(r.type[c] == 1 ? r.band[c] : r.eo[c]);
-        for (int k = 0; k < 4; k++) ci.sao[c].offset[k] = (int8_t)clip3(-128, 127, r.off[c][k]);
-      }
-    }
+    for (int k = 0; k < 16; k++) P.rbsp.push_back(0);
+    return B200_OK;
   }
+};
+
+struct HostSync {      // sequential execution: every dependency is already satisfied
+  uint32_t dense_tu = 0, dense_coef = 0, dense_tu_cap = 0, dense_coef_cap = 0;
+  uint64_t end_bit_position = 0;
+  int err = 0;
+  B200_HD void wait_row(int, int) {}
+  B200_HD void publish_row(int, int) {}
+  B200_HD void wait_substream(int) {}
+  B200_HD void finish_substream(int, int e) { if (e && !err) err = e; }
 };
 
 }  // namespace
 
-int parse_access_unit(const uint8_t* data, size_t size, const ParseLimits& limits, ParsedPicture& out) {
+int parse_headers(const uint8_t* data, size_t size, const ParseLimits& limits, PictureHeaders& out) {
   if (!data || size < 6) return set_error(B200_E_BITSTREAM, "empty access unit");
-  Parser p(out, limits);
+  HeaderParser p(out, limits);
   return p.run(data, size);
+}
+
+int parse_access_unit(const uint8_t* data, size_t size, const ParseLimits& limits, ParsedPicture& out) {
+  int rc = parse_headers(data, size, limits, out.hdr);
+  if (rc) return rc;
+  const PictureHeaders& H = out.hdr;
+  out.desc = H.desc;
+  syn::SeqParams sp = H.sp; sp.dense = 1;
+  const size_t nctb = (size_t)H.desc.wctb * H.desc.hctb, n8 = (size_t)H.desc.w8 * H.desc.h8, n4 = n8 * 4;
+  const size_t tu_cap = (size_t)H.desc.width * H.desc.height / 16, coef_cap = (size_t)H.desc.width * H.desc.height * (H.desc.chroma ? 3 : 2) / 2;
+  if (out.ctus.size() < nctb) out.ctus.resize(nctb);
+  if (out.tus.size() < tu_cap) out.tus.resize(tu_cap);
+  if (out.coefs.size() < coef_cap) out.coefs.resize(coef_cap);
+  if (out.qp8.size() < n8) out.qp8.resize(n8);
+  if (out.edge8.size() < n8) out.edge8.resize(n8);
+  if (out.ipm4.size() < n4) out.ipm4.resize(n4);
+  if (out.cd8.size() < n8) out.cd8.resize(n8);
+  out.wpp_ctx.resize((size_t)H.desc.hctb * syn::CTX_STRIDE);
+  out.end_state.resize(H.subs.size() * syn::CTX_STRIDE);
+  out.slices = H.slices;
+  syn::PicBuffers pb{};
+  pb.rbsp = H.rbsp.data(); pb.rbsp_size = (uint32_t)H.rbsp.size();
+  pb.tus = out.tus.data(); pb.coefs = out.coefs.data(); pb.ctus = out.ctus.data(); pb.slices = out.slices.data(); pb.ctu_slice = H.ctu_slice.data();
+  pb.qp8 = out.qp8.data(); pb.edge8 = out.edge8.data(); pb.ipm4 = out.ipm4.data(); pb.cd8 = out.cd8.data();
+  pb.wpp_ctx = out.wpp_ctx.data(); pb.end_state = out.end_state.data();
+  for (size_t a = 0; a < nctb; a++) out.ctus[a].slice_idx = H.ctu_slice[a];
+  HostSync sync; sync.dense_tu_cap = (uint32_t)tu_cap; sync.dense_coef_cap = (uint32_t)coef_cap;
+  uint8_t ctx[syn::CTX_STRIDE];
+  for (size_t i = 0; i < H.subs.size(); i++) {
+    int e = syn::run_substream(sp, pb, H.subs.data(), (int)i, ctx, sync);
+    if (e == syn::SYN_E_OVERFLOW) return set_error(B200_E_BITSTREAM, "slice data produces more transform units / coefficients than the picture can hold");
+    if (e) return set_error(B200_E_BITSTREAM, "corrupt slice data (sub-stream %zu, CTB %u..%u)", i, H.subs[i].ctb_begin, H.subs[i].ctb_end);
+    // cross-check of the entry points: the next sub-stream of the same segment starts where this one ended
+    if (!H.subs[i].last_of_segment && i + 1 < H.subs.size()) {
+      const uint64_t next = ((sync.end_bit_position + 7) >> 3);
+      if (next != H.subs[i + 1].byte_begin) return set_error(B200_E_BITSTREAM, "entry point offset does not match the end of the previous sub-stream");
+    }
+  }
+  out.n_tus = sync.dense_tu; out.n_coefs = sync.dense_coef;
+  return B200_OK;
 }
 
 }  // namespace b200

@@ -1,0 +1,552 @@
+// b200_hevc_syntax.h -- HEVC slice-data decoding (CABAC 9.3 + coding-quadtree syntax 7.3.8 + intra-mode 8.4.2 and
+// QP 8.6.1 derivation) as ONE piece of source compiled for both the host front-end (b200_hevc_parse.cc) and the
+// device entropy-decoding kernel (b200_hevc_entropy.cu).  One instance decodes one CABAC sub-stream: a slice segment,
+// or -- with entropy_coding_sync (WPP) -- one CTB row of it; sub-streams of a picture run concurrently on the GPU as a
+// wavefront (context hand-over after the 2nd CTB of the row above, 9.3.2.2), sequentially on the host.
+// Output = the command stream of b200_hevc_types.h.  No pixel is touched here.
+#pragma once
+#include <cstdint>
+#include <cstring>
+#include "b200_hevc_types.h"
+
+#ifdef __CUDACC__
+#define B200_HD __host__ __device__
+#define B200_TABLE(type, name, dims, ...) static const type h_##name dims = __VA_ARGS__; static __device__ const type d_##name dims = __VA_ARGS__;
+#else
+#define B200_HD
+#define B200_TABLE(type, name, dims, ...) static const type h_##name dims = __VA_ARGS__;
+#endif
+#ifdef __CUDA_ARCH__
+#define B200_T(name) d_##name
+// data written by ANOTHER sub-stream's thread (possibly on another SM): bypass the non-coherent L1
+#define B200_LD_SHARED(p) __ldcg(p)
+#else
+#define B200_T(name) h_##name
+#define B200_LD_SHARED(p) (*(p))
+#endif
+
+namespace b200 {
+namespace syn {
+
+enum { CTX_SAO_MERGE = 0, CTX_SAO_TYPE = 1, CTX_SPLIT_CU = 2, CTX_PART_MODE = 5, CTX_PREV_INTRA = 6,
+       CTX_CHROMA_PRED = 7, CTX_SPLIT_TR = 8, CTX_CBF_LUMA = 11, CTX_CBF_CHROMA = 13, CTX_QP_DELTA = 18,
+       CTX_TSKIP = 20, CTX_LAST_X = 22, CTX_LAST_Y = 40, CTX_CSBF = 58, CTX_SIG = 62, CTX_GT1 = 104,
+       CTX_GT2 = 128, CTX_COUNT = 134, CTX_STRIDE = 144 };
+
+// Tables 9-5 .. 9-37, initType 0 (I slices)
+B200_TABLE(uint8_t, kInitI, [CTX_COUNT], {
+  153, 200, 139, 141, 157, 184, 184, 63, 153, 138, 138, 111, 141, 94, 138, 182, 154, 154, 154, 154, 139, 139,
+  110, 110, 124, 125, 140, 153, 125, 127, 140, 109, 111, 143, 127, 111, 79, 108, 123, 63,
+  110, 110, 124, 125, 140, 153, 125, 127, 140, 109, 111, 143, 127, 111, 79, 108, 123, 63,
+  91, 171, 134, 141,
+  111, 111, 125, 110, 110, 94, 124, 108, 124, 107, 125, 141, 179, 153, 125, 107, 125, 141, 179, 153, 125,
+  107, 125, 141, 179, 153, 125, 140, 139, 182, 182, 152, 136, 152, 136, 153, 136, 139, 111, 136, 139, 111,
+  140, 92, 137, 138, 140, 152, 138, 139, 153, 74, 149, 92, 139, 107, 122, 152, 140, 179, 166, 182, 140, 227, 122, 197,
+  138, 153, 136, 167, 152, 152})
+// Table 9-46 (rangeTabLps) and 9-47 (transIdxLps)
+B200_TABLE(uint8_t, kLps, [64][4], {
+  {128,176,208,240},{128,167,197,227},{128,158,187,216},{123,150,178,205},{116,142,169,195},{111,135,160,185},
+  {105,128,152,175},{100,122,144,166},{95,116,137,158},{90,110,130,150},{85,104,123,142},{81,99,117,135},
+  {77,94,111,128},{73,89,105,122},{69,85,100,116},{66,80,95,110},{62,76,90,104},{59,72,86,99},{56,69,81,94},
+  {53,65,77,89},{51,62,73,85},{48,59,69,80},{46,56,66,76},{43,53,63,72},{41,50,59,69},{39,48,56,65},
+  {37,45,54,62},{35,43,51,59},{33,41,48,56},{32,39,46,53},{30,37,43,50},{29,35,41,48},{27,33,39,45},
+  {26,31,37,43},{24,30,35,41},{23,28,33,39},{22,27,32,37},{21,26,30,35},{20,24,29,33},{19,23,27,31},
+  {18,22,26,30},{17,21,25,28},{16,20,23,27},{15,19,22,25},{14,18,21,24},{14,17,20,23},{13,16,19,22},
+  {12,15,18,21},{12,14,17,20},{11,14,16,19},{11,13,15,18},{10,12,15,17},{10,12,14,16},{9,11,13,15},
+  {9,11,12,14},{8,10,12,14},{8,9,11,13},{7,9,11,12},{7,9,10,12},{7,8,10,11},{6,8,9,11},{6,7,9,10},
+  {6,7,8,9},{2,2,2,2}})
+B200_TABLE(uint8_t, kTransLps, [64], {0,0,1,2,2,4,4,5,6,7,8,9,9,11,11,12,13,13,15,15,16,16,18,18,19,19,21,21,22,22,23,24,
+  24,25,26,26,27,27,28,29,29,30,30,30,31,32,32,33,33,33,34,34,35,35,35,36,36,36,37,37,37,38,38,63})
+B200_TABLE(uint8_t, kSigMap4, [16], {0, 1, 4, 5, 2, 3, 4, 5, 6, 6, 8, 8, 7, 7, 8, 8})
+B200_TABLE(uint8_t, kChromaTab, [4], {0, 26, 10, 1})
+// scan orders 6.5.3-6.5.5: [log2 block size 0..3][diagonal, horizontal, vertical][position] -> x / y
+B200_TABLE(uint8_t, kScanX, [4][3][64], {{{0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0},{0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0},{0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0}},{{0,0,1,1,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0},{0,1,0,1,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0},{0,0,1,1,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0}},{{0,0,1,0,1,2,0,1,2,3,1,2,3,2,3,3,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0},{0,1,2,3,0,1,2,3,0,1,2,3,0,1,2,3,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0},{0,0,0,0,1,1,1,1,2,2,2,2,3,3,3,3,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0}},{{0,0,1,0,1,2,0,1,2,3,0,1,2,3,4,0,1,2,3,4,5,0,1,2,3,4,5,6,0,1,2,3,4,5,6,7,1,2,3,4,5,6,7,2,3,4,5,6,7,3,4,5,6,7,4,5,6,7,5,6,7,6,7,7},{0,1,2,3,4,5,6,7,0,1,2,3,4,5,6,7,0,1,2,3,4,5,6,7,0,1,2,3,4,5,6,7,0,1,2,3,4,5,6,7,0,1,2,3,4,5,6,7,0,1,2,3,4,5,6,7,0,1,2,3,4,5,6,7},{0,0,0,0,0,0,0,0,1,1,1,1,1,1,1,1,2,2,2,2,2,2,2,2,3,3,3,3,3,3,3,3,4,4,4,4,4,4,4,4,5,5,5,5,5,5,5,5,6,6,6,6,6,6,6,6,7,7,7,7,7,7,7,7}}})
+B200_TABLE(uint8_t, kScanY, [4][3][64], {{{0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0},{0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0},{0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0}},{{0,1,0,1,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0},{0,0,1,1,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0},{0,1,0,1,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0}},{{0,1,0,2,1,0,3,2,1,0,3,2,1,3,2,3,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0},{0,0,0,0,1,1,1,1,2,2,2,2,3,3,3,3,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0},{0,1,2,3,0,1,2,3,0,1,2,3,0,1,2,3,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0}},{{0,1,0,2,1,0,3,2,1,0,4,3,2,1,0,5,4,3,2,1,0,6,5,4,3,2,1,0,7,6,5,4,3,2,1,0,7,6,5,4,3,2,1,7,6,5,4,3,2,7,6,5,4,3,7,6,5,4,7,6,5,7,6,7},{0,0,0,0,0,0,0,0,1,1,1,1,1,1,1,1,2,2,2,2,2,2,2,2,3,3,3,3,3,3,3,3,4,4,4,4,4,4,4,4,5,5,5,5,5,5,5,5,6,6,6,6,6,6,6,6,7,7,7,7,7,7,7,7},{0,1,2,3,4,5,6,7,0,1,2,3,4,5,6,7,0,1,2,3,4,5,6,7,0,1,2,3,4,5,6,7,0,1,2,3,4,5,6,7,0,1,2,3,4,5,6,7,0,1,2,3,4,5,6,7,0,1,2,3,4,5,6,7}}})
+
+B200_HD inline int clip3(int lo, int hi, int v) { return v < lo ? lo : (v > hi ? hi : v); }
+B200_HD inline int imin(int a, int b) { return a < b ? a : b; }
+
+// Sequence / picture level parameters the slice data depends on (filled by the host from SPS + PPS).
+struct SeqParams {
+  int32_t W, H, log2ctb, wctb, hctb, w4, w8, h8, chroma, bd;
+  int32_t log2_min_cb, log2_min_tb, log2_max_tb, max_th_depth_intra;
+  int32_t sao_enabled, transform_skip, cu_qp_delta, qg_log2, sign_hiding, wpp, sao_scale_luma, sao_scale_chroma;
+  int32_t dense;                 // 1: outputs appended densely (host, sequential); 0: fixed per-CTB slots (device, concurrent)
+  int32_t tu_slots, coef_slots;  // per-CTB capacity when !dense
+};
+
+// One CABAC sub-stream.
+struct Substream {
+  uint32_t pic;                  // picture (tile) index in the batch
+  uint32_t byte_begin, byte_end; // inside the picture's RBSP buffer (byte_begin need not be aligned)
+  uint32_t ctb_begin, ctb_end;   // raster CTB addresses [begin, end)
+  uint32_t slice_addr_rs;        // first CTB of the slice (not segment) this sub-stream belongs to
+  int32_t slice_idx;
+  int32_t slice_qp;
+  uint8_t sao_luma, sao_chroma;
+  uint8_t init_contexts;         // 1: first sub-stream of an independent slice segment
+  uint8_t last_of_segment;       // 1: end_of_slice_segment_flag must be 1 at ctb_end - 1
+  int32_t prev;                  // sub-stream whose end state this one continues (dependent slice segment), else -1
+};
+
+struct PicBuffers {              // per-picture arrays (host memory on the host path, HBM on the device path)
+  const uint8_t* rbsp; uint32_t rbsp_size;   // padded with >= 8 zero bytes
+  TuCmd* tus; CoefEntry* coefs; CtuInfo* ctus; const SliceInfo* slices;
+  const uint16_t* ctu_slice;     // slice index of every CTB, filled by the host from the slice headers BEFORE decoding (read-only)
+  int8_t* qp8; uint8_t* edge8;   // outputs for deblocking (and QP prediction)
+  uint8_t* ipm4;                 // luma intra mode per 4x4 (MPM derivation)
+  uint8_t* cd8;                  // coding quadtree depth per 8x8 (split_cu_flag context)
+  uint8_t* wpp_ctx;              // hctb x CTX_STRIDE: context state after the 2nd CTB of each row
+  uint8_t* end_state;            // per sub-stream x CTX_STRIDE: contexts (+ last QpY in byte CTX_COUNT) at its end
+};
+
+// ---------------------------------------------------------------------------------------------- CABAC (9.3.4.3)
+// Literal 9-bit-offset arithmetic decoder over 32-bit big-endian words with a 64-bit reservoir; the bit position after
+// a terminating bin is the one the specification defines.
+struct Cabac {
+  const uint8_t* d; uint32_t n; uint32_t word; uint64_t res; int avail; unsigned range, offset;
+  B200_HD inline uint32_t load_be32(uint32_t w) const {
+    const uint32_t b = w * 4;
+    if (b + 4 <= n) {
+#ifdef __CUDA_ARCH__
+      const uint32_t v = *reinterpret_cast<const uint32_t*>(d + b);
+      return __byte_perm(v, 0, 0x0123);
+#else
+      return ((uint32_t)d[b] << 24) | ((uint32_t)d[b + 1] << 16) | ((uint32_t)d[b + 2] << 8) | d[b + 3];
+#endif
+    }
+    uint32_t v = 0;
+    for (int k = 0; k < 4; k++) v = (v << 8) | (b + k < n ? d[b + k] : 0u);
+    return v;
+  }
+  B200_HD inline void refill() { if (avail <= 32) { res |= (uint64_t)load_be32(word++) << (32 - avail); avail += 32; } }
+  B200_HD inline unsigned take(int k) { refill(); unsigned v = k ? (unsigned)(res >> (64 - k)) : 0u; res <<= k; avail -= k; return v; }
+  B200_HD inline void start(const uint8_t* data, uint32_t size, uint32_t start_byte) {
+    d = data; n = size; word = start_byte >> 2; res = 0; avail = 0;
+    const int skip = (int)(start_byte & 3) * 8;
+    refill(); res <<= skip; avail -= skip;
+    range = 510; offset = take(9);
+  }
+  B200_HD inline uint64_t bit_position() const { return (uint64_t)word * 32 - (uint64_t)avail; }
+  B200_HD inline int bin(uint8_t& c) {
+    const unsigned state = c >> 1; unsigned mps = c & 1;
+    const unsigned lps = B200_T(kLps)[state][(range >> 6) & 3];
+    range -= lps;
+    int b;
+    if (offset >= range) {
+      b = !mps; offset -= range; range = lps;
+      if (state == 0) mps ^= 1;
+      c = (uint8_t)((B200_T(kTransLps)[state] << 1) | mps);
+#ifdef __CUDA_ARCH__
+      const int sh = __clz((int)range) - 23;
+#else
+      const int sh = __builtin_clz(range) - 23;
+#endif
+      range <<= sh; offset = (offset << sh) | take(sh);
+    } else {
+      b = (int)mps;
+      if (state < 62) c = (uint8_t)(c + 2);
+      if (range < 256) { range <<= 1; offset = (offset << 1) | take(1); }
+    }
+    return b;
+  }
+  B200_HD inline int bypass() { offset = (offset << 1) | take(1); if (offset >= range) { offset -= range; return 1; } return 0; }
+  B200_HD inline unsigned bypass_bits(int k) { unsigned v = 0; while (k-- > 0) v = (v << 1) | (unsigned)bypass(); return v; }
+  B200_HD inline int terminate() {
+    range -= 2;
+    if (offset >= range) return 1;
+    if (range < 256) { range <<= 1; offset = (offset << 1) | take(1); }
+    return 0;
+  }
+};
+
+B200_HD inline void init_contexts(uint8_t* ctx, int slice_qp) {          // 9.3.2.2
+  const int qp = clip3(0, 51, slice_qp);
+  for (int i = 0; i < CTX_COUNT; i++) {
+    const int iv = B200_T(kInitI)[i], m = (iv >> 4) * 5 - 45, nn = ((iv & 15) << 3) - 16;
+    const int pre = clip3(1, 126, ((m * qp) >> 4) + nn);
+    const int mps = pre > 63, st = mps ? pre - 64 : 63 - pre;
+    ctx[i] = (uint8_t)((st << 1) | mps);
+  }
+}
+
+enum { SYN_OK = 0, SYN_E_BITSTREAM = 1, SYN_E_OVERFLOW = 2 };
+
+struct SaoRaw { int8_t type[3], band[3], eo[3]; int8_t off[3][4]; };
+
+// ---------------------------------------------------------------------------------------------- sub-stream decoder
+struct Decoder {
+  const SeqParams* sp; PicBuffers pb; const Substream* ss;
+  Cabac cabac; uint8_t* ctx;                      // CTX_COUNT bytes (caller-provided storage)
+  int is_dqp_coded, dqp_val, qpy_prev_qg, last_cu_qpy, first_qg, cur_qpy, err;
+  uint32_t tu_n, coef_n, tu_cap, coef_cap;        // write cursors / limits of the current CTB (or of the picture when dense)
+  int cur_ctb_x, cur_ctb_y;
+  struct Cu { int x0, y0, log2cb, nxn, lmode[4], cmode; };
+
+  // 6.4.1 for a left / above neighbour of the current block: those always precede it in decoding order, so they are
+  // available iff they lie inside the picture and in the same slice (HEVC tiles are not supported).
+  B200_HD inline bool avail(int x, int y) const {
+    if (x < 0 || y < 0 || x >= sp->W || y >= sp->H) return false;
+    return pb.ctu_slice[(y >> sp->log2ctb) * sp->wctb + (x >> sp->log2ctb)] == (uint16_t)ss->slice_idx;
+  }
+
+  // -------- SAO (7.3.8.3)
+  B200_HD void parse_sao(int rx, int ry, CtuInfo& ci) {
+    const int addr = ry * sp->wctb + rx;
+    for (int c = 0; c < 3; c++) { ci.sao[c].type = 0; ci.sao[c].band_or_class = 0; for (int k = 0; k < 4; k++) ci.sao[c].offset[k] = 0; }
+    if (!ss->sao_luma && !ss->sao_chroma) return;
+    int ml = 0, mu = 0;
+    if (rx > 0 && (uint32_t)(addr - 1) >= ss->slice_addr_rs) ml = cabac.bin(ctx[CTX_SAO_MERGE]);
+    if (ry > 0 && !ml && addr - sp->wctb >= (int)ss->slice_addr_rs) mu = cabac.bin(ctx[CTX_SAO_MERGE]);
+    if (ml || mu) {
+      const unsigned long long* o = reinterpret_cast<const unsigned long long*>(pb.ctus[ml ? addr - 1 : addr - sp->wctb].sao);   // 3 x 8 bytes
+      unsigned long long* dsto = reinterpret_cast<unsigned long long*>(ci.sao);
+      for (int c = 0; c < 3; c++) dsto[c] = B200_LD_SHARED(o + c);
+      return;
+    }
+    for (int c = 0; c < (sp->chroma ? 3 : 1); c++) {
+      if ((c == 0 && !ss->sao_luma) || (c > 0 && !ss->sao_chroma)) continue;
+      if (c < 2) { int t = 0; if (cabac.bin(ctx[CTX_SAO_TYPE])) t = cabac.bypass() ? 2 : 1; ci.sao[c].type = (uint8_t)t; } else ci.sao[2].type = ci.sao[1].type;
+      if (!ci.sao[c].type) continue;
+      const int cmax = (1 << (imin(sp->bd, 10) - 5)) - 1;
+      int av[4];
+      for (int i = 0; i < 4; i++) { int v = 0; while (v < cmax && cabac.bypass()) v++; av[i] = v; }
+      const int sc = c == 0 ? sp->sao_scale_luma : sp->sao_scale_chroma;
+      if (ci.sao[c].type == 1) {
+        for (int i = 0; i < 4; i++) if (av[i] && cabac.bypass()) av[i] = -av[i];
+        ci.sao[c].band_or_class = (uint8_t)cabac.bypass_bits(5);
+        for (int i = 0; i < 4; i++) ci.sao[c].offset[i] = (int8_t)clip3(-128, 127, av[i] * (1 << sc));
+      } else {
+        if (c < 2) ci.sao[c].band_or_class = (uint8_t)cabac.bypass_bits(2); else ci.sao[2].band_or_class = ci.sao[1].band_or_class;
+        ci.sao[c].offset[0] = (int8_t)clip3(-128, 127, av[0] << sc); ci.sao[c].offset[1] = (int8_t)clip3(-128, 127, av[1] << sc);
+        ci.sao[c].offset[2] = (int8_t)clip3(-128, 127, -(av[2] << sc)); ci.sao[c].offset[3] = (int8_t)clip3(-128, 127, -(av[3] << sc));
+      }
+    }
+  }
+
+  // -------- QP (8.6.1); QpY is kept per 8x8 block (coding blocks are >= 8x8)
+  B200_HD void derive_qpy(int xcb, int ycb) {
+    const int mask = (1 << sp->qg_log2) - 1, xqg = xcb & ~mask, yqg = ycb & ~mask, cm = ~((1 << sp->log2ctb) - 1);
+    int qa = qpy_prev_qg, qb = qpy_prev_qg;
+    if (avail(xqg - 1, yqg) && ((xqg - 1) & cm) == (xqg & cm)) qa = pb.qp8[(yqg >> 3) * sp->w8 + ((xqg - 1) >> 3)];
+    if (avail(xqg, yqg - 1) && ((yqg - 1) & cm) == (yqg & cm)) qb = pb.qp8[((yqg - 1) >> 3) * sp->w8 + (xqg >> 3)];
+    const int pred = (qa + qb + 1) >> 1, qbd = 6 * (sp->bd - 8);
+    cur_qpy = ((pred + dqp_val + 52 + 2 * qbd) % (52 + qbd)) - qbd;
+  }
+
+  // -------- residual_coding (7.3.8.11): emits sparse (pos, level) entries; returns the number of coefficients
+  B200_HD int residual(int log2n, int c, int mode, int& tskip) {
+    const int n = 1 << log2n;
+    tskip = 0;
+    if (sp->transform_skip && log2n == 2) tskip = cabac.bin(ctx[CTX_TSKIP + (c ? 1 : 0)]);
+    const int cmax = (log2n << 1) - 1;
+    int off, shift;
+    if (c == 0) { off = 3 * (log2n - 2) + ((log2n - 1) >> 2); shift = (log2n + 1) >> 2; } else { off = 15; shift = log2n - 2; }
+    int lx = 0, ly = 0;
+    while (lx < cmax && cabac.bin(ctx[CTX_LAST_X + off + (lx >> shift)])) lx++;
+    while (ly < cmax && cabac.bin(ctx[CTX_LAST_Y + off + (ly >> shift)])) ly++;
+    if (lx > 3) { const int nb = (lx >> 1) - 1; lx = (1 << nb) * (2 + (lx & 1)) + (int)cabac.bypass_bits(nb); }
+    if (ly > 3) { const int nb = (ly >> 1) - 1; ly = (1 << nb) * (2 + (ly & 1)) + (int)cabac.bypass_bits(nb); }
+    int scan = 0;
+    if (log2n == 2 || (log2n == 3 && c == 0)) { if (mode >= 6 && mode <= 14) scan = 2; else if (mode >= 22 && mode <= 30) scan = 1; }
+    if (scan == 2) { const int t = lx; lx = ly; ly = t; }
+    if (lx >= n || ly >= n) { err = SYN_E_BITSTREAM; return 0; }
+    const int l2sb = log2n - 2;
+    const uint8_t *sbx = B200_T(kScanX)[l2sb][scan], *sby = B200_T(kScanY)[l2sb][scan], *px = B200_T(kScanX)[2][scan], *py = B200_T(kScanY)[2][scan];
+    int last_sb = 0, last_pos = 0;
+    { const int xs = lx >> 2, ys = ly >> 2, xp = lx & 3, yp = ly & 3, nsb = 1 << (2 * l2sb);
+      for (int i = 0; i < nsb; i++) if (sbx[i] == xs && sby[i] == ys) { last_sb = i; break; }
+      for (int k = 0; k < 16; k++) if (px[k] == xp && py[k] == yp) { last_pos = k; break; } }
+    uint64_t csbf = 0;                                  // coded_sub_block_flag, bit (ys * 8 + xs)
+    int carry = 1, count = 0; bool first_done = false;
+    const int nsbw = 1 << l2sb;
+    for (int i = last_sb; i >= 0; i--) {
+      const int xs = sbx[i], ys = sby[i];
+      const int right = (xs + 1 < nsbw) ? (int)((csbf >> (ys * 8 + xs + 1)) & 1) : 0;
+      const int below = (ys + 1 < nsbw) ? (int)((csbf >> ((ys + 1) * 8 + xs)) & 1) : 0;
+      int infer_dc = 0, coded;
+      if (i < last_sb && i > 0) { coded = cabac.bin(ctx[CTX_CSBF + ((right | below) ? 1 : 0) + (c ? 2 : 0)]); infer_dc = 1; } else coded = 1;
+      if (!coded) continue;
+      csbf |= 1ull << (ys * 8 + xs);
+      const int prev = right | (below << 1);
+      unsigned sig = 0;
+      const int start = i == last_sb ? last_pos - 1 : 15;
+      if (i == last_sb) sig |= 1u << last_pos;
+      for (int k = start; k >= 0; k--) {
+        if (k > 0 || !infer_dc) {
+          const int xc = (xs << 2) + px[k], yc = (ys << 2) + py[k];
+          int sc;
+          if (log2n == 2) sc = B200_T(kSigMap4)[(yc << 2) + xc];
+          else if (xc + yc == 0) sc = 0;
+          else {
+            const int xp = xc & 3, yp = yc & 3;
+            if (prev == 0) sc = (xp + yp == 0) ? 2 : (xp + yp < 3) ? 1 : 0;
+            else if (prev == 1) sc = yp == 0 ? 2 : (yp == 1 ? 1 : 0);
+            else if (prev == 2) sc = xp == 0 ? 2 : (xp == 1 ? 1 : 0);
+            else sc = 2;
+            if (c == 0) { if (xs || ys) sc += 3; sc += log2n == 3 ? (scan == 0 ? 9 : 15) : 21; } else sc += log2n == 3 ? 9 : 12;
+          }
+          if (cabac.bin(ctx[CTX_SIG + (c == 0 ? sc : 27 + sc)])) { sig |= 1u << k; infer_dc = 0; }
+        } else sig |= 1u;
+      }
+      if (!sig) continue;
+      unsigned g1 = 0;
+      int ng1 = 0, last_g1 = -1, g1ctx = 1, g2 = 0;
+      int ctx_set = (i == 0 || c > 0) ? 0 : 2;
+      if (first_done && carry == 0) ctx_set++;
+      first_done = true;
+      int last_sig = -1, first_sig = 16;
+      for (int k = 15; k >= 0; k--) if ((sig >> k) & 1) {
+        if (ng1 < 8) {
+          const int g = cabac.bin(ctx[CTX_GT1 + ctx_set * 4 + imin(3, g1ctx) + (c ? 16 : 0)]);
+          ng1++;
+          if (g) { g1 |= 1u << k; g1ctx = 0; if (last_g1 < 0) last_g1 = k; } else if (g1ctx > 0) g1ctx++;
+        }
+        if (last_sig < 0) last_sig = k;
+        first_sig = k;
+      }
+      carry = g1ctx;
+      const bool hidden = sp->sign_hiding && (last_sig - first_sig > 3);
+      if (last_g1 >= 0) g2 = cabac.bin(ctx[CTX_GT2 + ctx_set + (c ? 4 : 0)]);
+      int nsign = 0;
+      for (int k = 15; k >= 0; k--) if (((sig >> k) & 1) && (!hidden || k != first_sig)) nsign++;
+      const unsigned signs = cabac.bypass_bits(nsign);
+      int nsig = 0, sum = 0, rice = 0, sidx = nsign;
+      for (int k = 15; k >= 0; k--) if ((sig >> k) & 1) {
+        const int base = 1 + (int)((g1 >> k) & 1) + (k == last_g1 ? g2 : 0);
+        int a = base;
+        if (base == ((nsig < 8) ? ((k == last_g1) ? 3 : 2) : 1)) {
+          int pre = 0; while (pre < 32 && cabac.bypass()) pre++;
+          const int rem = pre <= 3 ? (pre << rice) + (int)cabac.bypass_bits(rice) : (((1 << (pre - 3)) + 3 - 1) << rice) + (int)cabac.bypass_bits(pre - 3 + rice);
+          a = base + rem;
+          if (a > 3 * (1 << rice)) rice = imin(rice + 1, 4);
+        }
+        int neg = 0;
+        if (!hidden || k != first_sig) { sidx--; neg = (int)((signs >> sidx) & 1); }
+        int v = neg ? -a : a;
+        if (hidden) { sum += a; if (k == first_sig && (sum & 1)) v = -v; }
+        if (coef_n >= coef_cap) { err = SYN_E_OVERFLOW; return count; }
+        CoefEntry e; e.pos = (uint16_t)((((ys << 2) + py[k]) << log2n) + (xs << 2) + px[k]); e.level = (int16_t)clip3(-32768, 32767, v);
+        pb.coefs[coef_n++] = e; count++;
+        nsig++;
+      }
+    }
+    return count;
+  }
+
+  // -------- transform tree / unit (7.3.8.8, 7.3.8.10)
+  B200_HD void mark_tu(int x0, int y0, int log2n) {
+    // QpY map + filterEdgeFlag (8.7.2.3, bS = 2 on every transform edge of the 8x8 grid) for the deblocking kernel
+    const SliceInfo& sl = pb.slices[ss->slice_idx];
+    const int n8 = log2n > 3 ? 1 << (log2n - 3) : 1, bx = x0 >> 3, by = y0 >> 3;
+    uint8_t left = 0, top = 0;
+    if (!sl.deblocking_disabled) {
+      if ((x0 & 7) == 0 && x0 > 0 && (avail(x0 - 1, y0) || (sl.lf_across_slices && x0 - 1 >= 0))) left = 1;
+      if ((y0 & 7) == 0 && y0 > 0 && (avail(x0, y0 - 1) || sl.lf_across_slices)) top = 2;
+    }
+    for (int y = 0; y < n8; y++) for (int x = 0; x < n8; x++) {
+      const int i = (by + y) * sp->w8 + bx + x;
+      pb.qp8[i] = (int8_t)cur_qpy;
+      if (log2n >= 3) pb.edge8[i] = (uint8_t)((x == 0 ? left : 0) | (y == 0 ? top : 0));
+      else pb.edge8[i] |= (uint8_t)(left | top);
+    }
+  }
+
+  B200_HD void transform_unit(const Cu& cu, int x0, int y0, int log2n, int blk, int cbf_l, int cbf_cb, int cbf_cr, int pcb, int pcr) {
+    const int cbf_c = sp->chroma ? (log2n > 2 ? (cbf_cb | cbf_cr) : (pcb | pcr)) : 0;
+    if ((cbf_l || cbf_c) && sp->cu_qp_delta && !is_dqp_coded) {
+      int v = 0;
+      while (v < 5 && cabac.bin(ctx[CTX_QP_DELTA + (v ? 1 : 0)])) v++;
+      if (v == 5) { int k = 0; while (k < 16 && cabac.bypass()) { v += 1 << k; k++; } v += (int)cabac.bypass_bits(k); }
+      if (v && cabac.bypass()) v = -v;
+      is_dqp_coded = 1; dqp_val = v;
+      derive_qpy(cu.x0, cu.y0);
+    }
+    const int pu = cu.nxn ? ((y0 >= cu.y0 + (1 << (cu.log2cb - 1))) ? 2 : 0) + ((x0 >= cu.x0 + (1 << (cu.log2cb - 1))) ? 1 : 0) : 0;
+    const int lmode = cu.lmode[pu];
+    const uint32_t coef0 = coef_n;
+    int ts_l = 0, ts_cb = 0, ts_cr = 0, nl = 0, ncb = 0, ncr = 0;
+    if (cbf_l) nl = residual(log2n, 0, lmode, ts_l);
+    int chroma_here = 0, ccb = 0, ccr = 0;
+    if (sp->chroma) {
+      if (log2n > 2) { chroma_here = 1; ccb = cbf_cb; ccr = cbf_cr; if (ccb) ncb = residual(log2n - 1, 1, cu.cmode, ts_cb); if (ccr) ncr = residual(log2n - 1, 2, cu.cmode, ts_cr); }
+      else if (blk == 3) { chroma_here = 1; ccb = pcb; ccr = pcr; if (ccb) ncb = residual(2, 1, cu.cmode, ts_cb); if (ccr) ncr = residual(2, 2, cu.cmode, ts_cr); }
+    }
+    mark_tu(x0, y0, log2n);
+    if (tu_n >= tu_cap) { err = SYN_E_OVERFLOW; return; }
+    TuCmd t;
+    t.w0 = (uint32_t)(x0 >> 2) | ((uint32_t)(y0 >> 2) << 12) | ((uint32_t)(log2n - 2) << 24) | ((uint32_t)cbf_l << 26) | ((uint32_t)ccb << 27) |
+           ((uint32_t)ccr << 28) | ((uint32_t)chroma_here << 29) | ((uint32_t)ts_l << 30) | ((uint32_t)ts_cb << 31);
+    t.w1 = (uint32_t)lmode | ((uint32_t)cu.cmode << 6) | ((uint32_t)(cur_qpy + 64) << 12) | ((uint32_t)ts_cr << 20);
+    t.w2 = coef0;
+    t.w3 = (uint32_t)nl | ((uint32_t)ncb << 11) | ((uint32_t)ncr << 21);
+    pb.tus[tu_n++] = t;
+  }
+
+  B200_HD void transform_tree(const Cu& cu, int x0, int y0, int log2n, int depth, int blk, int pcb, int pcr, int max_depth) {
+    if (err) return;
+    int split;
+    if (log2n <= sp->log2_max_tb && log2n > sp->log2_min_tb && depth < max_depth && !(cu.nxn && depth == 0)) split = cabac.bin(ctx[CTX_SPLIT_TR + 5 - log2n]);
+    else split = (log2n > sp->log2_max_tb || (cu.nxn && depth == 0)) ? 1 : 0;
+    if (split && log2n <= 2) { err = SYN_E_BITSTREAM; return; }
+    int cb = 0, cr = 0;
+    if (sp->chroma) {
+      if (log2n > 2) { if (depth == 0 || pcb) cb = cabac.bin(ctx[CTX_CBF_CHROMA + depth]); if (depth == 0 || pcr) cr = cabac.bin(ctx[CTX_CBF_CHROMA + depth]); }
+      else { cb = pcb; cr = pcr; }
+    }
+    if (split) {
+      const int h = 1 << (log2n - 1);
+      for (int k = 0; k < 4; k++) transform_tree(cu, x0 + (k & 1) * h, y0 + (k >> 1) * h, log2n - 1, depth + 1, k, cb, cr, max_depth);
+    } else {
+      const int cl = cabac.bin(ctx[CTX_CBF_LUMA + (depth == 0 ? 1 : 0)]);
+      if (log2n > 2) transform_unit(cu, x0, y0, log2n, blk, cl, cb, cr, 0, 0);
+      else transform_unit(cu, x0, y0, log2n, blk, cl, 0, 0, pcb, pcr);
+    }
+  }
+
+  // -------- 8.4.2
+  B200_HD int luma_mode(int x, int y, int prev, int mpm_idx, int rem) const {
+    int ca = 1, cb = 1;
+    if (avail(x - 1, y)) ca = pb.ipm4[(y >> 2) * sp->w4 + ((x - 1) >> 2)];
+    if (avail(x, y - 1) && (y - 1) >= ((y >> sp->log2ctb) << sp->log2ctb)) cb = pb.ipm4[((y - 1) >> 2) * sp->w4 + (x >> 2)];
+    int c0, c1, c2;
+    if (ca == cb) { if (ca < 2) { c0 = 0; c1 = 1; c2 = 26; } else { c0 = ca; c1 = 2 + ((ca + 29) % 32); c2 = 2 + ((ca - 2 + 1) % 32); } }
+    else { c0 = ca; c1 = cb; if (ca != 0 && cb != 0) c2 = 0; else if (ca != 1 && cb != 1) c2 = 1; else c2 = 26; }
+    if (prev) return mpm_idx == 0 ? c0 : (mpm_idx == 1 ? c1 : c2);
+    int t;
+    if (c0 > c1) { t = c0; c0 = c1; c1 = t; }
+    if (c0 > c2) { t = c0; c0 = c2; c2 = t; }
+    if (c1 > c2) { t = c1; c1 = c2; c2 = t; }
+    int m = rem;
+    if (m >= c0) m++;
+    if (m >= c1) m++;
+    if (m >= c2) m++;
+    return m;
+  }
+
+  // -------- 7.3.8.5
+  B200_HD void coding_unit(int x0, int y0, int log2cb, int depth) {
+    Cu cu; cu.x0 = x0; cu.y0 = y0; cu.log2cb = log2cb; cu.nxn = 0; cu.cmode = 0;
+    const int n = 1 << log2cb;
+    if (log2cb == sp->log2_min_cb) cu.nxn = !cabac.bin(ctx[CTX_PART_MODE]);
+    if (cu.nxn && log2cb == 3 && sp->log2_min_tb > 2) { err = SYN_E_BITSTREAM; return; }
+    const int np = cu.nxn ? 4 : 1, pbs = cu.nxn ? n / 2 : n;
+    int prev[4], mi[4] = {0, 0, 0, 0}, rem[4] = {0, 0, 0, 0};
+    for (int i = 0; i < np; i++) prev[i] = cabac.bin(ctx[CTX_PREV_INTRA]);
+    for (int i = 0; i < np; i++) { if (prev[i]) { mi[i] = cabac.bypass(); if (mi[i]) mi[i] += cabac.bypass(); } else rem[i] = (int)cabac.bypass_bits(5); }
+    for (int i = 0; i < np; i++) {
+      const int px = x0 + (i & 1) * pbs, py = y0 + (i >> 1) * pbs;
+      const int m = luma_mode(px, py, prev[i], mi[i], rem[i]);
+      cu.lmode[i] = m;
+      for (int yy = 0; yy < pbs; yy += 4) for (int xx = 0; xx < pbs; xx += 4) pb.ipm4[((py + yy) >> 2) * sp->w4 + ((px + xx) >> 2)] = (uint8_t)m;
+    }
+    if (sp->chroma) {
+      int v = 4; if (cabac.bin(ctx[CTX_CHROMA_PRED])) v = (int)cabac.bypass_bits(2);
+      if (v == 4) cu.cmode = cu.lmode[0]; else { cu.cmode = B200_T(kChromaTab)[v]; if (cu.cmode == cu.lmode[0]) cu.cmode = 34; }
+    }
+    for (int yy = 0; yy < n; yy += 8) for (int xx = 0; xx < n; xx += 8) pb.cd8[((y0 + yy) >> 3) * sp->w8 + ((x0 + xx) >> 3)] = (uint8_t)depth;
+    if (!sp->cu_qp_delta) cur_qpy = ss->slice_qp; else derive_qpy(x0, y0);
+    transform_tree(cu, x0, y0, log2cb, 0, 0, 0, 0, sp->max_th_depth_intra + cu.nxn);
+    for (int yy = 0; yy < n; yy += 8) for (int xx = 0; xx < n; xx += 8) pb.qp8[((y0 + yy) >> 3) * sp->w8 + ((x0 + xx) >> 3)] = (int8_t)cur_qpy;
+    last_cu_qpy = cur_qpy;
+  }
+
+  // -------- 7.3.8.4
+  B200_HD void coding_quadtree(int x0, int y0, int log2cb, int depth) {
+    if (err) return;
+    const int n = 1 << log2cb;
+    int split;
+    if (x0 + n <= sp->W && y0 + n <= sp->H && log2cb > sp->log2_min_cb) {
+      int inc = 0;
+      if (avail(x0 - 1, y0) && pb.cd8[(y0 >> 3) * sp->w8 + ((x0 - 1) >> 3)] > depth) inc++;
+      if (avail(x0, y0 - 1) && B200_LD_SHARED(pb.cd8 + ((y0 - 1) >> 3) * sp->w8 + (x0 >> 3)) > depth) inc++;
+      split = cabac.bin(ctx[CTX_SPLIT_CU + inc]);
+    } else split = log2cb > sp->log2_min_cb;
+    if (sp->cu_qp_delta && log2cb >= sp->qg_log2) {
+      is_dqp_coded = 0; dqp_val = 0;
+      if (!split || log2cb == sp->qg_log2) { if (first_qg) { qpy_prev_qg = ss->slice_qp; first_qg = 0; } else qpy_prev_qg = last_cu_qpy; }
+    }
+    if (split) {
+      const int h = n >> 1;
+      for (int k = 0; k < 4; k++) { const int x1 = x0 + (k & 1) * h, y1 = y0 + (k >> 1) * h; if (x1 < sp->W && y1 < sp->H) coding_quadtree(x1, y1, log2cb - 1, depth + 1); }
+    } else coding_unit(x0, y0, log2cb, depth);
+  }
+
+  // One coding tree unit (7.3.8.2): SAO syntax + coding quadtree; fills its CtuInfo.
+  B200_HD void decode_ctb(int addr) {
+    const int rx = addr % sp->wctb, ry = addr / sp->wctb;
+    cur_ctb_x = rx; cur_ctb_y = ry;
+    CtuInfo& ci = pb.ctus[addr];
+    ci.slice_idx = (uint16_t)ss->slice_idx;
+    if (!sp->dense) { tu_n = (uint32_t)addr * (uint32_t)sp->tu_slots; tu_cap = tu_n + (uint32_t)sp->tu_slots; coef_n = (uint32_t)addr * (uint32_t)sp->coef_slots; coef_cap = coef_n + (uint32_t)sp->coef_slots; }
+    const uint32_t t0 = tu_n;
+    if (sp->sao_enabled) parse_sao(rx, ry, ci);
+    else for (int c = 0; c < 3; c++) { ci.sao[c].type = 0; ci.sao[c].band_or_class = 0; for (int k = 0; k < 4; k++) ci.sao[c].offset[k] = 0; }
+    // 4x4 luma transform units only OR their edge bits: clear this CTB's flags first
+    { const int b0x = rx << (sp->log2ctb - 3), b0y = ry << (sp->log2ctb - 3), nb = 1 << (sp->log2ctb - 3);
+      for (int y = 0; y < nb && b0y + y < sp->h8; y++) for (int x = 0; x < nb && b0x + x < sp->w8; x++) pb.edge8[(b0y + y) * sp->w8 + b0x + x] = 0; }
+    coding_quadtree(rx << sp->log2ctb, ry << sp->log2ctb, sp->log2ctb, 0);
+    ci.tu_start = t0; ci.tu_count = (uint16_t)(tu_n - t0);
+  }
+};
+
+// Decodes one sub-stream.  `Sync` supplies wait_row(row, need) -- block until `need` CTBs of CTB row `row` are done --
+// publish_row(row, done) and wait_substream(index); on the host (sequential order) they are no-ops.
+template <class Sync>
+B200_HD int run_substream(const SeqParams& sp, const PicBuffers& pb, const Substream* all, int index, uint8_t* ctx, Sync& sync) {
+  const Substream& ss = all[index];
+  Decoder d;
+  d.sp = &sp; d.pb = pb; d.ss = &ss; d.ctx = ctx; d.err = SYN_OK;
+  d.is_dqp_coded = 0; d.dqp_val = 0; d.qpy_prev_qg = ss.slice_qp; d.last_cu_qpy = ss.slice_qp; d.first_qg = 1; d.cur_qpy = ss.slice_qp;
+  d.tu_n = 0; d.coef_n = 0; d.tu_cap = 0; d.coef_cap = 0;
+  if (sp.dense) {                                             // host: continue the picture-wide cursors
+    d.tu_n = sync.dense_tu; d.coef_n = sync.dense_coef; d.tu_cap = sync.dense_tu_cap; d.coef_cap = sync.dense_coef_cap;
+  }
+  const int rx0 = (int)(ss.ctb_begin % (uint32_t)sp.wctb), ry0 = (int)(ss.ctb_begin / (uint32_t)sp.wctb);
+  // ---- context initialisation / synchronisation (9.3.1)
+  if (ss.prev >= 0) {                                         // dependent slice segment: continue from the previous segment's end state
+    sync.wait_substream(ss.prev);
+    const uint8_t* st = pb.end_state + (size_t)ss.prev * CTX_STRIDE;
+    for (int i = 0; i < CTX_COUNT; i++) ctx[i] = B200_LD_SHARED(st + i);
+    d.last_cu_qpy = (int)(int8_t)B200_LD_SHARED(st + CTX_COUNT); d.first_qg = 0;
+  }
+  if (ss.init_contexts) init_contexts(ctx, ss.slice_qp);
+  if (sp.wpp && rx0 == 0 && (!ss.init_contexts || ss.prev >= 0) && ss.ctb_begin != ss.slice_addr_rs) {
+    // first CTB of a row inside a slice: take the state stored after the 2nd CTB of the row above when that CTB is
+    // available (same slice), otherwise initialise (or, for a dependent segment, keep the inherited state)
+    const int xn = 1 << sp.log2ctb, yn = (ry0 - 1) << sp.log2ctb;
+    bool tr = ry0 > 0 && xn < sp.W && pb.ctu_slice[(ry0 - 1) * sp.wctb + 1] == (uint16_t)ss.slice_idx;
+    (void)yn;
+    if (tr) { sync.wait_row(ry0 - 1, 2); const uint8_t* st = pb.wpp_ctx + (size_t)(ry0 - 1) * CTX_STRIDE; for (int i = 0; i < CTX_COUNT; i++) ctx[i] = B200_LD_SHARED(st + i); }
+    else if (ss.prev < 0) init_contexts(ctx, ss.slice_qp);
+    d.first_qg = 1;
+  }
+  d.cabac.start(pb.rbsp, pb.rbsp_size, ss.byte_begin);
+  for (uint32_t a = ss.ctb_begin; a < ss.ctb_end; a++) {
+    const int rx = (int)(a % (uint32_t)sp.wctb), ry = (int)(a / (uint32_t)sp.wctb);
+    if (ry > 0) sync.wait_row(ry - 1, imin(rx + 2, sp.wctb));     // split_cu_flag context / SAO merge-up read the row above
+    if (sp.wpp && rx == 0 && a != ss.ctb_begin) {
+      // only reached without WPP sub-stream splitting (never: WPP rows are separate sub-streams); kept for safety
+      d.first_qg = 1;
+    }
+    if (!sp.wpp && rx == 0 && a != ss.ctb_begin) { /* QG state simply continues */ }
+    d.decode_ctb((int)a);
+    if (d.err) break;
+    if (sp.wpp && rx == 1) { uint8_t* st = pb.wpp_ctx + (size_t)ry * CTX_STRIDE; for (int i = 0; i < CTX_COUNT; i++) st[i] = ctx[i]; }
+    const int end = d.cabac.terminate();                          // end_of_slice_segment_flag
+    const bool last = a + 1 == ss.ctb_end;
+    if (end != ((last && ss.last_of_segment) ? 1 : 0)) { d.err = SYN_E_BITSTREAM; break; }
+    if (last && !ss.last_of_segment) { if (!d.cabac.terminate()) { d.err = SYN_E_BITSTREAM; break; } }   // end_of_subset_one_bit
+    sync.publish_row(ry, rx + 1);
+    if (d.cabac.word * 4 > pb.rbsp_size + 16) { d.err = SYN_E_BITSTREAM; break; }
+  }
+  // end state for a dependent continuation + dense cursors
+  { uint8_t* st = pb.end_state + (size_t)index * CTX_STRIDE; for (int i = 0; i < CTX_COUNT; i++) st[i] = ctx[i]; st[CTX_COUNT] = (uint8_t)(int8_t)d.last_cu_qpy; }
+  if (sp.dense) { sync.dense_tu = d.tu_n; sync.dense_coef = d.coef_n; }
+  sync.end_bit_position = d.cabac.bit_position();
+  sync.finish_substream(index, d.err);
+  return d.err;
+}
+
+}  // namespace syn
+}  // namespace b200

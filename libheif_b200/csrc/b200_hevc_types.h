@@ -26,7 +26,7 @@ struct CoefEntry { uint16_t pos; int16_t level; };
 struct SaoComp { uint8_t type; uint8_t band_or_class; int8_t offset[4]; uint8_t pad[2]; };
 
 // One CTU: 40 bytes.
-struct CtuInfo {
+struct alignas(8) CtuInfo {
   uint32_t tu_start;     // first TuCmd of this CTU, relative to the picture's TU base
   uint16_t tu_count;
   uint16_t slice_idx;    // index into the picture's slice table

@@ -20,9 +20,9 @@ class ImageInfo(C.Structure):
 
 
 class DecodeStats(C.Structure):
-    _fields_ = [(n, C.c_double) for n in ("parse_ms", "pack_ms", "h2d_ms", "gpu_ms", "total_ms", "recon_ms", "deblock_ms", "sao_ms")] + \
+    _fields_ = [(n, C.c_double) for n in ("parse_ms", "pack_ms", "h2d_ms", "gpu_ms", "total_ms", "entropy_ms", "recon_ms", "deblock_ms", "sao_ms")] + \
                [(n, C.c_uint64) for n in ("bitstream_bytes", "command_bytes", "coefficient_entries", "transform_units", "ctus", "h2d_bytes", "pixels")] + \
-               [("kernel_launches", C.c_int)]
+               [("kernel_launches", C.c_int), ("front_end", C.c_int)]
 
 
 def _bind(l):
@@ -37,6 +37,7 @@ def _bind(l):
     l.b200_decoder_read_planes.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]
     l.b200_decoder_debug_read_tile.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
     l.b200_decoder_set_debug_stage.argtypes = [C.c_void_p, C.c_int]
+    l.b200_decoder_set_front_end.argtypes = [C.c_void_p, C.c_int]
     l.b200_decoder_get_stats.argtypes = [C.c_void_p, C.POINTER(DecodeStats)]
     l.b200_decoder_rerun_device.argtypes = [C.c_void_p, C.c_void_p]
     l.b200_decode_grid_to_rgb_host.argtypes = [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_char_p), C.POINTER(C.c_size_t), C.c_uint64,
@@ -103,6 +104,10 @@ class Decoder:
         p = _lib.Planes()
         _lib.check(self.l.b200_decoder_get_planes(self.h, C.byref(p)))
         return p
+
+    def set_front_end(self, device: bool):
+        """True (default): CABAC + syntax on the GPU; False: on the host cores."""
+        _lib.check(self.l.b200_decoder_set_front_end(self.h, 1 if device else 0))
 
     def set_debug_stage(self, stage: int):
         _lib.check(self.l.b200_decoder_set_debug_stage(self.h, stage))

@@ -13,9 +13,11 @@ from oracle import bindings as ob
 pytestmark = pytest.mark.gpu
 
 
-@pytest.fixture(scope="module")
-def dec(cuda):
+@pytest.fixture(scope="module", params=["device", "host"])
+def dec(cuda, request):
+    """Both front-ends must give identical results: CABAC on the GPU (default) and CABAC on the host cores."""
     d = lb.Decoder(host_threads=8)
+    d.set_front_end(request.param == "device")
     yield d
     d.close()
 
