@@ -10,14 +10,32 @@
 // Output: the command stream of b200_hevc_types.h, written into fixed per-CTB slots in HBM (worst-case sized; only the
 // used entries are ever touched).  Why on the GPU: the host has 16 usable cores on the target box and CABAC is the
 // end-to-end bottleneck there; the arithmetic decoder is serial per sub-stream but there are thousands of sub-streams.
+#include <cstdint>
+// The syntax decoder's lookup tables live in SHARED memory on the device (the dependent table look-ups of every CABAC
+// bin would otherwise go through L1/L2): file-scope __shared__ copies, filled at kernel start, reached through B200_T.
+namespace b200 { namespace syn {
+__shared__ uint32_t s_kLps4[64];
+__shared__ uint8_t s_kTransLps[64];
+__shared__ uint8_t s_kInitI[134];
+__shared__ uint8_t s_kSigMap4[16];
+__shared__ uint8_t s_kChromaTab[4];
+__shared__ uint8_t s_kScanX[4][3][64];
+__shared__ uint8_t s_kScanY[4][3][64];
+} }
+#ifdef __CUDA_ARCH__
+#define B200_T(name) s_##name
+#endif
 #include "b200_hevc.h"
 
 namespace b200 {
 
 constexpr int EWARPS = 4;
 
+// Polling load: relaxed + gpu scope (served by L2).  ld.acquire would make ptxas emit CCTL.IVALL -- an SM-wide L1 invalidation --
+// on EVERY poll (measured: 43 % of all stall samples of the first version); ordering is obtained instead by reading every
+// piece of cross-thread data with L1-bypassing loads (B200_LD_SHARED / __ldcg) after the control-dependent loop exit.
 __device__ __forceinline__ unsigned e_ld_acquire(const unsigned* p) {
-  unsigned v; asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory"); return v;
+  unsigned v; asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory"); return v;
 }
 __device__ __forceinline__ void e_st_release(unsigned* p, unsigned v) {
   asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
@@ -31,21 +49,27 @@ struct DevSync {
   uint64_t end_bit_position;
   __device__ void wait_row(int row, int need) {
     unsigned spins = 0;
-    while (e_ld_acquire(progress + row) < (unsigned)need) { __nanosleep(64); if (++spins > (1u << 26)) { atomicExch(error_flag, 3u); break; } }
+    while (e_ld_acquire(progress + row) < (unsigned)need) { __nanosleep(200); if (++spins > (1u << 24)) { atomicExch(error_flag, 3u); break; } }
   }
-  __device__ void publish_row(int row, int done) { __threadfence(); e_st_release(progress + row, (unsigned)done); }
+  __device__ void publish_row(int row, int done) { e_st_release(progress + row, (unsigned)done); }
   __device__ void wait_substream(int idx) {
     unsigned spins = 0;
-    while (e_ld_acquire(sub_done + idx) == 0u) { __nanosleep(64); if (++spins > (1u << 26)) { atomicExch(error_flag, 3u); break; } }
+    while (e_ld_acquire(sub_done + idx) == 0u) { __nanosleep(200); if (++spins > (1u << 24)) { atomicExch(error_flag, 3u); break; } }
   }
   __device__ void finish_substream(int idx, int err) {
-    __threadfence(); e_st_release(sub_done + idx, 1u);
+    e_st_release(sub_done + idx, 1u);
     if (err) atomicExch(error_flag, (unsigned)err);
   }
 };
 
 __global__ void __launch_bounds__(EWARPS * 32) hevc_entropy_kernel(const EntropyBatch b) {
   __shared__ uint8_t s_ctx[EWARPS][syn::CTX_STRIDE];
+  for (int i = threadIdx.x; i < 64; i += blockDim.x) { syn::s_kLps4[i] = syn::d_kLps4[i]; syn::s_kTransLps[i] = syn::d_kTransLps[i]; }
+  for (int i = threadIdx.x; i < 134; i += blockDim.x) syn::s_kInitI[i] = syn::d_kInitI[i];
+  for (int i = threadIdx.x; i < 16; i += blockDim.x) syn::s_kSigMap4[i] = syn::d_kSigMap4[i];
+  for (int i = threadIdx.x; i < 4; i += blockDim.x) syn::s_kChromaTab[i] = syn::d_kChromaTab[i];
+  for (int i = threadIdx.x; i < 4 * 3 * 64; i += blockDim.x) { (&syn::s_kScanX[0][0][0])[i] = (&syn::d_kScanX[0][0][0])[i]; (&syn::s_kScanY[0][0][0])[i] = (&syn::d_kScanY[0][0][0])[i]; }
+  __syncthreads();
   if ((threadIdx.x & 31) != 0) return;                      // lane 0 of every warp decodes; CABAC is serial per sub-stream
   uint8_t* ctx = s_ctx[threadIdx.x >> 5];
   for (;;) {

@@ -71,7 +71,7 @@ __device__ __forceinline__ unsigned morton4(unsigned x, unsigned y) {   // z-ord
   return sx | (sy << 1);
 }
 __device__ __forceinline__ unsigned ld_acquire(const unsigned* p) {
-  unsigned v; asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory"); return v;
+  unsigned v; asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory"); return v;
 }
 __device__ __forceinline__ void st_release(unsigned* p, unsigned v) {
   asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
@@ -119,20 +119,40 @@ __device__ void process_tb(WarpMem& m, const int8_t* __restrict__ mat, const Row
   const int cx0 = c ? r.x0 >> 1 : r.x0, cy0 = c ? r.y0 >> 1 : r.y0;      // tile origin in component samples
   const int xl = (cx0 + bx) << sh, yl = (cy0 + by) << sh;                 // luma location of the block
   // ---- neighbour array with availability, then substitution (8.4.4.2.2)
+  // The left / below-left / corner / above / above-right neighbour regions each lie inside ONE aligned block of the
+  // current block's size, so z-scan availability (6.4.1) is decided per region (5 tests per block, done by lanes 0..4)
+  // and per sample only the picture bounds remain.
+  unsigned regions;
+  {
+    const int nl = n << sh;
+    bool f = false;
+    if (lane < 5) {
+      const int xn = lane == 4 ? xl + nl : (lane == 3 ? xl : xl - 1);
+      const int yn = lane == 0 ? yl : (lane == 1 ? yl + nl : yl - 1);      // 0: left, 1: below-left, 2: corner, 3: above, 4: above-right
+      f = available(r, xn, yn, xl, yl);
+    }
+    regions = __ballot_sync(0xffffffffu, f);
+  }
+  const int wc = c ? r.W >> 1 : r.W, hc = c ? r.H >> 1 : r.H;
+  const int nk = (4 * n + 32) >> 5;                 // 32-entry chunks that hold the 4n+1 neighbours
   unsigned ball[5]; int val[5];
 #pragma unroll
   for (int k = 0; k < 5; k++) {
-    const int i = lane + 32 * k;
-    bool av = false; int v = 0;
-    if (i <= 4 * n) {
-      int px, py;
-      if (i < 2 * n) { px = bx - 1; py = by + 2 * n - 1 - i; } else if (i == 2 * n) { px = bx - 1; py = by - 1; } else { px = bx + (i - 2 * n - 1); py = by - 1; }
-      av = available(r, (cx0 + px) << sh, (cy0 + py) << sh, xl, yl);
-      if (av) v = tile_sample(m, c, px, py);
+    ball[k] = 0; val[k] = 0;
+    if (k < nk) {
+      const int i = lane + 32 * k;
+      bool av = false; int v = 0;
+      if (i <= 4 * n) {
+        int px, py;
+        if (i < 2 * n) { const int y = 2 * n - 1 - i; px = bx - 1; py = by + y; av = ((regions >> (y < n ? 0 : 1)) & 1) && (cy0 + py < hc); }
+        else if (i == 2 * n) { px = bx - 1; py = by - 1; av = (regions >> 2) & 1; }
+        else { const int x = i - 2 * n - 1; px = bx + x; py = by - 1; av = ((regions >> (x < n ? 3 : 4)) & 1) && (cx0 + px < wc); }
+        if (av) v = tile_sample(m, c, px, py);
+      }
+      ball[k] = __ballot_sync(0xffffffffu, av);
+      val[k] = v;
+      if (av) m.ref_a[i] = (int16_t)v;
     }
-    ball[k] = __ballot_sync(0xffffffffu, av);
-    val[k] = v;
-    if (av) m.ref_a[i] = (int16_t)v;
   }
   __syncwarp();
   {
@@ -141,7 +161,7 @@ __device__ void process_tb(WarpMem& m, const int8_t* __restrict__ mat, const Row
     for (int k = 4; k >= 0; k--) if (ball[k]) first = 32 * k + __ffs(ball[k]) - 1;
     int carry = -1;                                   // highest available index in earlier chunks
 #pragma unroll
-    for (int k = 0; k < 5; k++) {
+    for (int k = 0; k < 5; k++) if (k < nk) {
       const int i = lane + 32 * k;
       const unsigned le = ball[k] & (0xffffffffu >> (31 - lane));
       int j = le ? 32 * k + 31 - __clz(le) : carry;
@@ -151,7 +171,7 @@ __device__ void process_tb(WarpMem& m, const int8_t* __restrict__ mat, const Row
     }
     __syncwarp();
 #pragma unroll
-    for (int k = 0; k < 5; k++) { const int i = lane + 32 * k; if (i <= 4 * n) m.ref_a[i] = (int16_t)val[k]; }
+    for (int k = 0; k < 5; k++) if (k < nk) { const int i = lane + 32 * k; if (i <= 4 * n) m.ref_a[i] = (int16_t)val[k]; }
     __syncwarp();
   }
   // ---- smoothing of the neighbours (8.4.4.2.3): luma only in 4:2:0
@@ -164,7 +184,7 @@ __device__ void process_tb(WarpMem& m, const int8_t* __restrict__ mat, const Row
       const bool strong = r.strong && n == 32 && abs(corner + tr - 2 * m.ref_a[3 * n]) < (1 << (bd - 5)) &&
                           abs(corner + bl - 2 * m.ref_a[n]) < (1 << (bd - 5));
 #pragma unroll
-      for (int k = 0; k < 5; k++) {
+      for (int k = 0; k < 5; k++) if (k < nk) {
         const int i = lane + 32 * k;
         if (i <= 4 * n) {
           int v;
@@ -338,9 +358,9 @@ __global__ void __launch_bounds__(WARPS * 32) hevc_recon_kernel(const DeviceBatc
         const unsigned need = (unsigned)min(r.rx + 2, r.wctb);
         if (lane == 0) {
           unsigned spins = 0;
-          while (ld_acquire(&prog[r.ry - 1]) < need) {
-            __nanosleep(40);
-            if (++spins > (1u << 26)) { atomicExch(b.error_flag, 1u); break; }     // never observed; turns a would-be hang into an error
+          while (ld_acquire(&prog[r.ry - 1]) < need) {      // relaxed polling load (no L1 invalidation); the halo is read with __ldcg below
+            __nanosleep(100);
+            if (++spins > (1u << 25)) { atomicExch(b.error_flag, 1u); break; }     // never observed; turns a would-be hang into an error
           }
         }
         __syncwarp();
@@ -394,8 +414,7 @@ __global__ void __launch_bounds__(WARPS * 32) hevc_recon_kernel(const DeviceBatc
         uint16_t* left = c == 0 ? m.left_y : m.left_c[c - 1];
         for (int y = lane; y < sz; y += 32) left[y] = tile[y * ts + sz - 1];
       }
-      __threadfence();
-      __syncwarp();
+      __syncwarp();                                         // all lanes' stores precede lane 0's release store (cumulativity)
       if (lane == 0) st_release(&prog[r.ry], (unsigned)(r.rx + 1));
     }
   }

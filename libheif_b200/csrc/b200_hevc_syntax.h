@@ -16,12 +16,16 @@
 #define B200_HD
 #define B200_TABLE(type, name, dims, ...) static const type h_##name dims = __VA_ARGS__;
 #endif
-#ifdef __CUDA_ARCH__
+#if defined(__CUDA_ARCH__) && !defined(B200_T)
 #define B200_T(name) d_##name
+#endif
+#ifdef __CUDA_ARCH__
 // data written by ANOTHER sub-stream's thread (possibly on another SM): bypass the non-coherent L1
 #define B200_LD_SHARED(p) __ldcg(p)
 #else
+#ifndef B200_T
 #define B200_T(name) h_##name
+#endif
 #define B200_LD_SHARED(p) (*(p))
 #endif
 
@@ -44,17 +48,7 @@ B200_TABLE(uint8_t, kInitI, [CTX_COUNT], {
   140, 92, 137, 138, 140, 152, 138, 139, 153, 74, 149, 92, 139, 107, 122, 152, 140, 179, 166, 182, 140, 227, 122, 197,
   138, 153, 136, 167, 152, 152})
 // Table 9-46 (rangeTabLps) and 9-47 (transIdxLps)
-B200_TABLE(uint8_t, kLps, [64][4], {
-  {128,176,208,240},{128,167,197,227},{128,158,187,216},{123,150,178,205},{116,142,169,195},{111,135,160,185},
-  {105,128,152,175},{100,122,144,166},{95,116,137,158},{90,110,130,150},{85,104,123,142},{81,99,117,135},
-  {77,94,111,128},{73,89,105,122},{69,85,100,116},{66,80,95,110},{62,76,90,104},{59,72,86,99},{56,69,81,94},
-  {53,65,77,89},{51,62,73,85},{48,59,69,80},{46,56,66,76},{43,53,63,72},{41,50,59,69},{39,48,56,65},
-  {37,45,54,62},{35,43,51,59},{33,41,48,56},{32,39,46,53},{30,37,43,50},{29,35,41,48},{27,33,39,45},
-  {26,31,37,43},{24,30,35,41},{23,28,33,39},{22,27,32,37},{21,26,30,35},{20,24,29,33},{19,23,27,31},
-  {18,22,26,30},{17,21,25,28},{16,20,23,27},{15,19,22,25},{14,18,21,24},{14,17,20,23},{13,16,19,22},
-  {12,15,18,21},{12,14,17,20},{11,14,16,19},{11,13,15,18},{10,12,15,17},{10,12,14,16},{9,11,13,15},
-  {9,11,12,14},{8,10,12,14},{8,9,11,13},{7,9,11,12},{7,9,10,12},{7,8,10,11},{6,8,9,11},{6,7,9,10},
-  {6,7,8,9},{2,2,2,2}})
+B200_TABLE(uint32_t, kLps4, [64], {0xf0d0b080u, 0xe3c5a780u, 0xd8bb9e80u, 0xcdb2967bu, 0xc3a98e74u, 0xb9a0876fu, 0xaf988069u, 0xa6907a64u, 0x9e89745fu, 0x96826e5au, 0x8e7b6855u, 0x87756351u, 0x806f5e4du, 0x7a695949u, 0x74645545u, 0x6e5f5042u, 0x685a4c3eu, 0x6356483bu, 0x5e514538u, 0x594d4135u, 0x55493e33u, 0x50453b30u, 0x4c42382eu, 0x483f352bu, 0x453b3229u, 0x41383027u, 0x3e362d25u, 0x3b332b23u, 0x38302921u, 0x352e2720u, 0x322b251eu, 0x3029231du, 0x2d27211bu, 0x2b251f1au, 0x29231e18u, 0x27211c17u, 0x25201b16u, 0x231e1a15u, 0x211d1814u, 0x1f1b1713u, 0x1e1a1612u, 0x1c191511u, 0x1b171410u, 0x1916130fu, 0x1815120eu, 0x1714110eu, 0x1613100du, 0x15120f0cu, 0x14110e0cu, 0x13100e0bu, 0x120f0d0bu, 0x110f0c0au, 0x100e0c0au, 0x0f0d0b09u, 0x0e0c0b09u, 0x0e0c0a08u, 0x0d0b0908u, 0x0c0b0907u, 0x0c0a0907u, 0x0b0a0807u, 0x0b090806u, 0x0a090706u, 0x09080706u, 0x02020202u})   // rangeTabLps[state][0..3] packed little-endian
 B200_TABLE(uint8_t, kTransLps, [64], {0,0,1,2,2,4,4,5,6,7,8,9,9,11,11,12,13,13,15,15,16,16,18,18,19,19,21,21,22,22,23,24,
   24,25,26,26,27,27,28,29,29,30,30,30,31,32,32,33,33,33,34,34,35,35,35,36,36,36,37,37,37,38,38,63})
 B200_TABLE(uint8_t, kSigMap4, [16], {0, 1, 4, 5, 2, 3, 4, 5, 6, 6, 8, 8, 7, 7, 8, 8})
@@ -104,12 +98,12 @@ struct PicBuffers {              // per-picture arrays (host memory on the host 
 // Literal 9-bit-offset arithmetic decoder over 32-bit big-endian words with a 64-bit reservoir; the bit position after
 // a terminating bin is the one the specification defines.
 struct Cabac {
-  const uint8_t* d; uint32_t n; uint32_t word; uint64_t res; int avail; unsigned range, offset;
+  const uint8_t* d; uint32_t n; uint32_t word; uint32_t next_w; uint64_t res; int avail; unsigned range, offset;
   B200_HD inline uint32_t load_be32(uint32_t w) const {
     const uint32_t b = w * 4;
     if (b + 4 <= n) {
 #ifdef __CUDA_ARCH__
-      const uint32_t v = *reinterpret_cast<const uint32_t*>(d + b);
+      const uint32_t v = __ldg(reinterpret_cast<const uint32_t*>(d + b));
       return __byte_perm(v, 0, 0x0123);
 #else
       return ((uint32_t)d[b] << 24) | ((uint32_t)d[b + 1] << 16) | ((uint32_t)d[b + 2] << 8) | d[b + 3];
@@ -119,22 +113,25 @@ struct Cabac {
     for (int k = 0; k < 4; k++) v = (v << 8) | (b + k < n ? d[b + k] : 0u);
     return v;
   }
-  B200_HD inline void refill() { if (avail <= 32) { res |= (uint64_t)load_be32(word++) << (32 - avail); avail += 32; } }
+  // `next_w` always holds word `word`, fetched one refill ahead so the HBM/L2 latency is off the dependency chain
+  B200_HD inline void refill() { if (avail <= 32) { res |= (uint64_t)next_w << (32 - avail); avail += 32; word++; next_w = load_be32(word); } }
   B200_HD inline unsigned take(int k) { refill(); unsigned v = k ? (unsigned)(res >> (64 - k)) : 0u; res <<= k; avail -= k; return v; }
   B200_HD inline void start(const uint8_t* data, uint32_t size, uint32_t start_byte) {
     d = data; n = size; word = start_byte >> 2; res = 0; avail = 0;
+    next_w = load_be32(word);
     const int skip = (int)(start_byte & 3) * 8;
     refill(); res <<= skip; avail -= skip;
     range = 510; offset = take(9);
   }
   B200_HD inline uint64_t bit_position() const { return (uint64_t)word * 32 - (uint64_t)avail; }
   B200_HD inline int bin(uint8_t& c) {
-    const unsigned state = c >> 1; unsigned mps = c & 1;
-    const unsigned lps = B200_T(kLps)[state][(range >> 6) & 3];
+    const unsigned cv = c;
+    const unsigned state = cv >> 1; unsigned mps = cv & 1;
+    const unsigned lps = (B200_T(kLps4)[state] >> (((range >> 6) & 3) * 8)) & 0xff;
     range -= lps;
     int b;
     if (offset >= range) {
-      b = !mps; offset -= range; range = lps;
+      b = (int)(mps ^ 1); offset -= range; range = lps;
       if (state == 0) mps ^= 1;
       c = (uint8_t)((B200_T(kTransLps)[state] << 1) | mps);
 #ifdef __CUDA_ARCH__
@@ -145,7 +142,7 @@ struct Cabac {
       range <<= sh; offset = (offset << sh) | take(sh);
     } else {
       b = (int)mps;
-      if (state < 62) c = (uint8_t)(c + 2);
+      if (state < 62) c = (uint8_t)(cv + 2);
       if (range < 256) { range <<= 1; offset = (offset << 1) | take(1); }
     }
     return b;
@@ -228,8 +225,8 @@ struct Decoder {
   B200_HD void derive_qpy(int xcb, int ycb) {
     const int mask = (1 << sp->qg_log2) - 1, xqg = xcb & ~mask, yqg = ycb & ~mask, cm = ~((1 << sp->log2ctb) - 1);
     int qa = qpy_prev_qg, qb = qpy_prev_qg;
-    if (avail(xqg - 1, yqg) && ((xqg - 1) & cm) == (xqg & cm)) qa = pb.qp8[(yqg >> 3) * sp->w8 + ((xqg - 1) >> 3)];
-    if (avail(xqg, yqg - 1) && ((yqg - 1) & cm) == (yqg & cm)) qb = pb.qp8[((yqg - 1) >> 3) * sp->w8 + (xqg >> 3)];
+    if (avail(xqg - 1, yqg) && ((xqg - 1) & cm) == (xqg & cm)) qa = B200_LD_SHARED(pb.qp8 + (yqg >> 3) * sp->w8 + ((xqg - 1) >> 3));
+    if (avail(xqg, yqg - 1) && ((yqg - 1) & cm) == (yqg & cm)) qb = B200_LD_SHARED(pb.qp8 + ((yqg - 1) >> 3) * sp->w8 + (xqg >> 3));
     const int pred = (qa + qb + 1) >> 1, qbd = 6 * (sp->bd - 8);
     cur_qpy = ((pred + dqp_val + 52 + 2 * qbd) % (52 + qbd)) - qbd;
   }
@@ -237,20 +234,25 @@ struct Decoder {
   // -------- residual_coding (7.3.8.11): emits sparse (pos, level) entries; returns the number of coefficients
   B200_HD int residual(int log2n, int c, int mode, int& tskip) {
     const int n = 1 << log2n;
+    // Local copies: their addresses never escape, so they live in registers and need no reload after the byte stores
+    // into the context array (uint8_t stores may alias any member otherwise).
+    Cabac cb_ = cabac; uint8_t* const cx = ctx;
+    const int sign_hiding = sp->sign_hiding;
+    CoefEntry* const coef_out = pb.coefs; uint32_t cn = coef_n; const uint32_t ccap = coef_cap;
     tskip = 0;
-    if (sp->transform_skip && log2n == 2) tskip = cabac.bin(ctx[CTX_TSKIP + (c ? 1 : 0)]);
+    if (sp->transform_skip && log2n == 2) tskip = cb_.bin(cx[CTX_TSKIP + (c ? 1 : 0)]);
     const int cmax = (log2n << 1) - 1;
     int off, shift;
     if (c == 0) { off = 3 * (log2n - 2) + ((log2n - 1) >> 2); shift = (log2n + 1) >> 2; } else { off = 15; shift = log2n - 2; }
     int lx = 0, ly = 0;
-    while (lx < cmax && cabac.bin(ctx[CTX_LAST_X + off + (lx >> shift)])) lx++;
-    while (ly < cmax && cabac.bin(ctx[CTX_LAST_Y + off + (ly >> shift)])) ly++;
-    if (lx > 3) { const int nb = (lx >> 1) - 1; lx = (1 << nb) * (2 + (lx & 1)) + (int)cabac.bypass_bits(nb); }
-    if (ly > 3) { const int nb = (ly >> 1) - 1; ly = (1 << nb) * (2 + (ly & 1)) + (int)cabac.bypass_bits(nb); }
+    while (lx < cmax && cb_.bin(cx[CTX_LAST_X + off + (lx >> shift)])) lx++;
+    while (ly < cmax && cb_.bin(cx[CTX_LAST_Y + off + (ly >> shift)])) ly++;
+    if (lx > 3) { const int nb = (lx >> 1) - 1; lx = (1 << nb) * (2 + (lx & 1)) + (int)cb_.bypass_bits(nb); }
+    if (ly > 3) { const int nb = (ly >> 1) - 1; ly = (1 << nb) * (2 + (ly & 1)) + (int)cb_.bypass_bits(nb); }
     int scan = 0;
     if (log2n == 2 || (log2n == 3 && c == 0)) { if (mode >= 6 && mode <= 14) scan = 2; else if (mode >= 22 && mode <= 30) scan = 1; }
     if (scan == 2) { const int t = lx; lx = ly; ly = t; }
-    if (lx >= n || ly >= n) { err = SYN_E_BITSTREAM; return 0; }
+    if (lx >= n || ly >= n) { err = SYN_E_BITSTREAM; cabac = cb_; return 0; }
     const int l2sb = log2n - 2;
     const uint8_t *sbx = B200_T(kScanX)[l2sb][scan], *sby = B200_T(kScanY)[l2sb][scan], *px = B200_T(kScanX)[2][scan], *py = B200_T(kScanY)[2][scan];
     int last_sb = 0, last_pos = 0;
@@ -265,7 +267,7 @@ struct Decoder {
       const int right = (xs + 1 < nsbw) ? (int)((csbf >> (ys * 8 + xs + 1)) & 1) : 0;
       const int below = (ys + 1 < nsbw) ? (int)((csbf >> ((ys + 1) * 8 + xs)) & 1) : 0;
       int infer_dc = 0, coded;
-      if (i < last_sb && i > 0) { coded = cabac.bin(ctx[CTX_CSBF + ((right | below) ? 1 : 0) + (c ? 2 : 0)]); infer_dc = 1; } else coded = 1;
+      if (i < last_sb && i > 0) { coded = cb_.bin(cx[CTX_CSBF + ((right | below) ? 1 : 0) + (c ? 2 : 0)]); infer_dc = 1; } else coded = 1;
       if (!coded) continue;
       csbf |= 1ull << (ys * 8 + xs);
       const int prev = right | (below << 1);
@@ -286,7 +288,7 @@ struct Decoder {
             else sc = 2;
             if (c == 0) { if (xs || ys) sc += 3; sc += log2n == 3 ? (scan == 0 ? 9 : 15) : 21; } else sc += log2n == 3 ? 9 : 12;
           }
-          if (cabac.bin(ctx[CTX_SIG + (c == 0 ? sc : 27 + sc)])) { sig |= 1u << k; infer_dc = 0; }
+          if (cb_.bin(cx[CTX_SIG + (c == 0 ? sc : 27 + sc)])) { sig |= 1u << k; infer_dc = 0; }
         } else sig |= 1u;
       }
       if (!sig) continue;
@@ -298,7 +300,7 @@ struct Decoder {
       int last_sig = -1, first_sig = 16;
       for (int k = 15; k >= 0; k--) if ((sig >> k) & 1) {
         if (ng1 < 8) {
-          const int g = cabac.bin(ctx[CTX_GT1 + ctx_set * 4 + imin(3, g1ctx) + (c ? 16 : 0)]);
+          const int g = cb_.bin(cx[CTX_GT1 + ctx_set * 4 + imin(3, g1ctx) + (c ? 16 : 0)]);
           ng1++;
           if (g) { g1 |= 1u << k; g1ctx = 0; if (last_g1 < 0) last_g1 = k; } else if (g1ctx > 0) g1ctx++;
         }
@@ -306,18 +308,18 @@ struct Decoder {
         first_sig = k;
       }
       carry = g1ctx;
-      const bool hidden = sp->sign_hiding && (last_sig - first_sig > 3);
-      if (last_g1 >= 0) g2 = cabac.bin(ctx[CTX_GT2 + ctx_set + (c ? 4 : 0)]);
+      const bool hidden = sign_hiding && (last_sig - first_sig > 3);
+      if (last_g1 >= 0) g2 = cb_.bin(cx[CTX_GT2 + ctx_set + (c ? 4 : 0)]);
       int nsign = 0;
       for (int k = 15; k >= 0; k--) if (((sig >> k) & 1) && (!hidden || k != first_sig)) nsign++;
-      const unsigned signs = cabac.bypass_bits(nsign);
+      const unsigned signs = cb_.bypass_bits(nsign);
       int nsig = 0, sum = 0, rice = 0, sidx = nsign;
       for (int k = 15; k >= 0; k--) if ((sig >> k) & 1) {
         const int base = 1 + (int)((g1 >> k) & 1) + (k == last_g1 ? g2 : 0);
         int a = base;
         if (base == ((nsig < 8) ? ((k == last_g1) ? 3 : 2) : 1)) {
-          int pre = 0; while (pre < 32 && cabac.bypass()) pre++;
-          const int rem = pre <= 3 ? (pre << rice) + (int)cabac.bypass_bits(rice) : (((1 << (pre - 3)) + 3 - 1) << rice) + (int)cabac.bypass_bits(pre - 3 + rice);
+          int pre = 0; while (pre < 32 && cb_.bypass()) pre++;
+          const int rem = pre <= 3 ? (pre << rice) + (int)cb_.bypass_bits(rice) : (((1 << (pre - 3)) + 3 - 1) << rice) + (int)cb_.bypass_bits(pre - 3 + rice);
           a = base + rem;
           if (a > 3 * (1 << rice)) rice = imin(rice + 1, 4);
         }
@@ -325,12 +327,13 @@ struct Decoder {
         if (!hidden || k != first_sig) { sidx--; neg = (int)((signs >> sidx) & 1); }
         int v = neg ? -a : a;
         if (hidden) { sum += a; if (k == first_sig && (sum & 1)) v = -v; }
-        if (coef_n >= coef_cap) { err = SYN_E_OVERFLOW; return count; }
+        if (cn >= ccap) { err = SYN_E_OVERFLOW; cabac = cb_; coef_n = cn; return count; }
         CoefEntry e; e.pos = (uint16_t)((((ys << 2) + py[k]) << log2n) + (xs << 2) + px[k]); e.level = (int16_t)clip3(-32768, 32767, v);
-        pb.coefs[coef_n++] = e; count++;
+        coef_out[cn++] = e; count++;
         nsig++;
       }
     }
+    cabac = cb_; coef_n = cn;
     return count;
   }
 
@@ -407,8 +410,8 @@ struct Decoder {
   // -------- 8.4.2
   B200_HD int luma_mode(int x, int y, int prev, int mpm_idx, int rem) const {
     int ca = 1, cb = 1;
-    if (avail(x - 1, y)) ca = pb.ipm4[(y >> 2) * sp->w4 + ((x - 1) >> 2)];
-    if (avail(x, y - 1) && (y - 1) >= ((y >> sp->log2ctb) << sp->log2ctb)) cb = pb.ipm4[((y - 1) >> 2) * sp->w4 + (x >> 2)];
+    if (avail(x - 1, y)) ca = B200_LD_SHARED(pb.ipm4 + (y >> 2) * sp->w4 + ((x - 1) >> 2));
+    if (avail(x, y - 1) && (y - 1) >= ((y >> sp->log2ctb) << sp->log2ctb)) cb = B200_LD_SHARED(pb.ipm4 + ((y - 1) >> 2) * sp->w4 + (x >> 2));
     int c0, c1, c2;
     if (ca == cb) { if (ca < 2) { c0 = 0; c1 = 1; c2 = 26; } else { c0 = ca; c1 = 2 + ((ca + 29) % 32); c2 = 2 + ((ca - 2 + 1) % 32); } }
     else { c0 = ca; c1 = cb; if (ca != 0 && cb != 0) c2 = 0; else if (ca != 1 && cb != 1) c2 = 1; else c2 = 26; }
@@ -458,7 +461,7 @@ struct Decoder {
     int split;
     if (x0 + n <= sp->W && y0 + n <= sp->H && log2cb > sp->log2_min_cb) {
       int inc = 0;
-      if (avail(x0 - 1, y0) && pb.cd8[(y0 >> 3) * sp->w8 + ((x0 - 1) >> 3)] > depth) inc++;
+      if (avail(x0 - 1, y0) && B200_LD_SHARED(pb.cd8 + (y0 >> 3) * sp->w8 + ((x0 - 1) >> 3)) > depth) inc++;
       if (avail(x0, y0 - 1) && B200_LD_SHARED(pb.cd8 + ((y0 - 1) >> 3) * sp->w8 + (x0 >> 3)) > depth) inc++;
       split = cabac.bin(ctx[CTX_SPLIT_CU + inc]);
     } else split = log2cb > sp->log2_min_cb;
@@ -538,7 +541,7 @@ B200_HD int run_substream(const SeqParams& sp, const PicBuffers& pb, const Subst
     if (end != ((last && ss.last_of_segment) ? 1 : 0)) { d.err = SYN_E_BITSTREAM; break; }
     if (last && !ss.last_of_segment) { if (!d.cabac.terminate()) { d.err = SYN_E_BITSTREAM; break; } }   // end_of_subset_one_bit
     sync.publish_row(ry, rx + 1);
-    if (d.cabac.word * 4 > pb.rbsp_size + 16) { d.err = SYN_E_BITSTREAM; break; }
+    if (d.cabac.word * 4 > pb.rbsp_size + 32) { d.err = SYN_E_BITSTREAM; break; }
   }
   // end state for a dependent continuation + dense cursors
   { uint8_t* st = pb.end_state + (size_t)index * CTX_STRIDE; for (int i = 0; i < CTX_COUNT; i++) st[i] = ctx[i]; st[CTX_COUNT] = (uint8_t)(int8_t)d.last_cu_qpy; }
