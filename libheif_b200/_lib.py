@@ -6,7 +6,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-SO_PATH = os.path.join(HERE, "libb200heif.so")
+SO_PATH = os.environ.get("B200_LIB", os.path.join(HERE, "libb200heif.so"))   # B200_LIB: development override (kernel variants)
 
 
 class Planes(C.Structure):

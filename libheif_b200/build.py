@@ -24,19 +24,24 @@ def needs_build():
     return any(os.path.getmtime(p) > t for p in deps)
 
 
-def build(force=False, verbose=False):
-    if not force and not needs_build():
+def build(force=False, verbose=False, extra_flags=None, out=None, tag=""):
+    global OUT
+    if out:
+        OUT_local = out
+    else:
+        OUT_local = OUT
+    if not force and not extra_flags and not needs_build():
         return OUT
     objs = []
     os.makedirs(os.path.join(HERE, "build"), exist_ok=True)
     procs = []
     for src in sources():
-        obj = os.path.join(HERE, "build", os.path.basename(src) + ".o")
+        obj = os.path.join(HERE, "build", os.path.basename(src) + tag + ".o")
         objs.append(obj)
         if not force and os.path.exists(obj) and os.path.getmtime(obj) > max(
                 [os.path.getmtime(src)] + [os.path.getmtime(h) for h in glob.glob(os.path.join(CSRC, "*.h")) + glob.glob(os.path.join(HERE, "..", "include", "*.h"))]):
             continue
-        cmd = [NVCC] + FLAGS + ["-x", "cu", "-c", src, "-o", obj]
+        cmd = [NVCC] + FLAGS + (extra_flags or []) + ["-x", "cu", "-c", src, "-o", obj]
         procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
     for src, p in procs:
         out, _ = p.communicate()
@@ -46,12 +51,12 @@ def build(force=False, verbose=False):
             raise RuntimeError(f"nvcc failed on {src}")
         with open(os.path.join(HERE, "build", os.path.basename(src) + ".ptxas.txt"), "w") as f:
             f.write(out)
-    cmd = [NVCC, "-shared", "-o", OUT] + objs + ["-lpthread", "-ldl"]
+    cmd = [NVCC, "-shared", "-o", OUT_local] + objs + ["-lpthread", "-ldl"]
     r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     if r.returncode != 0:
         sys.stderr.write(r.stdout)
         raise RuntimeError("link failed")
-    return OUT
+    return OUT_local
 
 
 if __name__ == "__main__":

@@ -83,7 +83,7 @@ def _out_shape(out_chroma, w, h, bit_depth):
     return (h, w * _BYTES_PER_PIXEL[out_chroma]), np.uint8
 
 
-def convert_colorspace(img: YCbCrImage, out_chroma: int, geometry: Optional[Geometry] = None, out=None, stream=None):
+def convert_colorspace(img: YCbCrImage, out_chroma: int, geometry: Optional[Geometry] = None, out=None, stream=None, bilinear: bool = False):
     """Device -> device. `img` planes are CUDA torch tensors (uint8, or int16/uint16 for >8 bit).
 
     Returns a CUDA uint8 tensor [H, W*bytes_per_pixel] (interleaved) or [3, H, W] (planar RGB 4:4:4)."""
@@ -97,7 +97,7 @@ def convert_colorspace(img: YCbCrImage, out_chroma: int, geometry: Optional[Geom
     if out is None:
         out = torch.empty(shape, dtype=tdt, device=img.y.device)
     planes = _fill_planes(img, lambda t: t.data_ptr(), lambda t: t.stride(0) * t.element_size())
-    opt = _lib.ColorOptions(out_chroma, 0, 0)
+    opt = _lib.ColorOptions(out_chroma, 0, 1 if bilinear else 0)
     s = stream if stream is not None else torch.cuda.current_stream(img.y.device)
     pipe = C.c_int(0)
     if out_chroma == CHROMA_444:

@@ -200,6 +200,127 @@ __global__ void __launch_bounds__(256) k6_color_kernel(const K6Args p) {
   }
 }
 
+
+// ---------------------------------------------------------------------------------------------- bilinear chroma
+// Op_YCbCr420_bilinear_to_YCbCr444<T> (chroma_sampling.cc:623-700): one thread per full-resolution chroma sample.
+// Interior: weights 9/3/3/1 (+8)/16; borders: 3/1 (+2)/4 with the reference's source indexing (cx/2, cy/2); corners copied.
+template <typename T>
+__global__ void __launch_bounds__(256) bilinear_420_to_444_kernel(const T* __restrict__ in_cb, const T* __restrict__ in_cr, long long cs,
+                                                                  T* __restrict__ out_cb, T* __restrict__ out_cr, long long os, int w, int h) {
+  const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+  if (x >= w || y >= h) return;
+  const bool weven = (w & 1) == 0, heven = (h & 1) == 0;
+  for (int c = 0; c < 2; c++) {
+    const T* in = c ? in_cr : in_cb;
+    T* out = c ? out_cr : out_cb;
+    int v;
+    const bool top = y == 0, left = x == 0, right = weven && x == w - 1, bottom = heven && y == h - 1;
+    if ((top || bottom) && (left || right)) v = in[(long long)(top ? 0 : h / 2 - 1) * cs + (left ? 0 : w / 2 - 1)];
+    else if (top || bottom) {
+      const int cx = (x - 1) >> 1, row = top ? 0 : h / 2 - 1;
+      const int a = in[(long long)row * cs + cx / 2], b = in[(long long)row * cs + cx / 2 + 1];
+      v = (x & 1) ? (3 * a + b + 2) / 4 : (a + 3 * b + 2) / 4;
+    } else if (left || right) {
+      const int cy = (y - 1) >> 1, col = left ? 0 : w / 2 - 1;
+      const int a = in[(long long)(cy / 2) * cs + col], b = in[(long long)(cy / 2 + 1) * cs + col];
+      v = (y & 1) ? (3 * a + b + 2) / 4 : (a + 3 * b + 2) / 4;
+    } else {
+      const int cx = (x - 1) >> 1, cy = (y - 1) >> 1;
+      const int c00 = in[(long long)cy * cs + cx], c01 = in[(long long)cy * cs + cx + 1], c10 = in[(long long)(cy + 1) * cs + cx], c11 = in[(long long)(cy + 1) * cs + cx + 1];
+      const int wx0 = (x & 1) ? 3 : 1, wx1 = 4 - wx0, wy0 = (y & 1) ? 3 : 1, wy1 = 4 - wy0;
+      v = (c00 * wx0 * wy0 + c01 * wx1 * wy0 + c10 * wx0 * wy1 + c11 * wx1 * wy1 + 8) / 16;
+    }
+    out[(long long)y * os + x] = (T)v;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------- fast path
+// Identity geometry, 4:2:0, no alpha, 16-byte aligned rows: no shared-memory staging.  One thread = 16 x 2 output
+// pixels: 2 x 16 luma samples and 8 + 8 chroma samples come in with 128-bit / 64-bit loads, the chroma terms are
+// computed once per 2x2 block (identical values to the per-pixel evaluation of the reference: same float products,
+// same evaluation order), and each row leaves as NCH * BPS 128-bit streaming stores.
+template <typename T, int INT_MODE, int NCH, int BPS, int LE>
+__global__ void __launch_bounds__(256) k6_direct_kernel(const K6Args p) {
+  const int x16 = blockIdx.x * blockDim.x + threadIdx.x;
+  const int y2 = blockIdx.y * blockDim.y + threadIdx.y;
+  if (x16 * 16 >= p.out_w || y2 * 2 >= p.out_h) return;
+  const int x = x16 * 16, y = y2 * 2;
+  T Y[2][16], Cb[8], Cr[8];
+  if (sizeof(T) == 1) {
+    *reinterpret_cast<uint4*>(Y[0]) = __ldcs(reinterpret_cast<const uint4*>(static_cast<const char*>(p.y) + (long long)y * p.ys + x));
+    *reinterpret_cast<uint4*>(Y[1]) = __ldcs(reinterpret_cast<const uint4*>(static_cast<const char*>(p.y) + (long long)(y + 1) * p.ys + x));
+    *reinterpret_cast<uint2*>(Cb) = __ldcs(reinterpret_cast<const uint2*>(static_cast<const char*>(p.cb) + (long long)y2 * p.cs + x / 2));
+    *reinterpret_cast<uint2*>(Cr) = __ldcs(reinterpret_cast<const uint2*>(static_cast<const char*>(p.cr) + (long long)y2 * p.cs + x / 2));
+  } else {
+#pragma unroll
+    for (int r = 0; r < 2; r++) {
+      const uint4* src = reinterpret_cast<const uint4*>(static_cast<const char*>(p.y) + (long long)(y + r) * p.ys + x * 2);
+      reinterpret_cast<uint4*>(Y[r])[0] = __ldcs(src); reinterpret_cast<uint4*>(Y[r])[1] = __ldcs(src + 1);
+    }
+    *reinterpret_cast<uint4*>(Cb) = __ldcs(reinterpret_cast<const uint4*>(static_cast<const char*>(p.cb) + (long long)y2 * p.cs + x));
+    *reinterpret_cast<uint4*>(Cr) = __ldcs(reinterpret_cast<const uint4*>(static_cast<const char*>(p.cr) + (long long)y2 * p.cs + x));
+  }
+  const int bpp = p.bpp, half = 1 << (bpp - 1), maxv = (1 << bpp) - 1, pre = p.pre_shift, post = p.sdr_shift;
+  const float lro = (float)(16 << (bpp - 8));
+  const bool full = p.full_range != 0;
+  // per chroma sample terms
+  int ri[8], gi[8], bi[8]; float rf[8], g1f[8], g2f[8], bf[8];
+#pragma unroll
+  for (int i = 0; i < 8; i++) {
+    const int cbv = (int)Cb[i] >> pre, crv = (int)Cr[i] >> pre;
+    if (INT_MODE) {
+      const int cb = cbv - 128, cr = crv - 128;
+      ri[i] = (p.ci[0] * cr + 128) >> 8; gi[i] = (p.ci[1] * cb + p.ci[2] * cr + 128) >> 8; bi[i] = (p.ci[3] * cb + 128) >> 8;
+    } else {
+      float cb = (float)(cbv - half), cr = (float)(crv - half);
+      if (!full) { cb = __fmul_rn(cb, 1.1429f); cr = __fmul_rn(cr, 1.1429f); }
+      rf[i] = __fmul_rn(p.cf[0], cr); g1f[i] = __fmul_rn(p.cf[1], cb); g2f[i] = __fmul_rn(p.cf[2], cr); bf[i] = __fmul_rn(p.cf[3], cb);
+    }
+  }
+#pragma unroll
+  for (int r = 0; r < 2; r++) {
+    __align__(16) uint8_t buf[16 * NCH * BPS];
+#pragma unroll
+    for (int i = 0; i < 16; i++) {
+      const int yv0 = (int)Y[r][i] >> pre;
+      int R, G, B;
+      if (INT_MODE) { R = clip_u8(yv0 + ri[i >> 1]); G = clip_u8(yv0 + gi[i >> 1]); B = clip_u8(yv0 + bi[i >> 1]); }
+      else {
+        float yv = (float)yv0;
+        if (!full) yv = __fmul_rn(__fsub_rn(yv, lro), 1.1689f);
+        R = clip_f(__fadd_rn(yv, rf[i >> 1]), maxv) >> post;
+        G = clip_f(__fadd_rn(__fadd_rn(yv, g1f[i >> 1]), g2f[i >> 1]), maxv) >> post;
+        B = clip_f(__fadd_rn(yv, bf[i >> 1]), maxv) >> post;
+      }
+      if (BPS == 1) {
+        buf[NCH * i] = (uint8_t)R; buf[NCH * i + 1] = (uint8_t)G; buf[NCH * i + 2] = (uint8_t)B;
+        if (NCH == 4) buf[NCH * i + 3] = (uint8_t)p.alpha_fill;
+      } else {
+        const int v[4] = {R, G, B, p.alpha_fill};
+#pragma unroll
+        for (int c = 0; c < NCH; c++) { buf[(NCH * i + c) * 2 + (LE ? 1 : 0)] = (uint8_t)(v[c] >> 8); buf[(NCH * i + c) * 2 + (LE ? 0 : 1)] = (uint8_t)(v[c] & 0xff); }
+      }
+    }
+    uint4* dst = reinterpret_cast<uint4*>(static_cast<char*>(p.out[0]) + (long long)(y + r) * p.os + (long long)x * NCH * BPS);
+#pragma unroll
+    for (int k = 0; k < NCH * BPS; k++) __stcs(dst + k, reinterpret_cast<const uint4*>(buf)[k]);
+  }
+}
+
+template <typename T, int INT_MODE>
+static bool launch_direct(const K6Args& a, cudaStream_t s) {
+  dim3 blk(32, 8), grid((a.out_w / 16 + 31) / 32, (a.out_h / 2 + 7) / 8);
+  switch (a.out_fmt) {
+    case B200_CHROMA_INTERLEAVED_RGB: k6_direct_kernel<T, INT_MODE, 3, 1, 0><<<grid, blk, 0, s>>>(a); return true;
+    case B200_CHROMA_INTERLEAVED_RGBA: k6_direct_kernel<T, INT_MODE, 4, 1, 0><<<grid, blk, 0, s>>>(a); return true;
+    case B200_CHROMA_INTERLEAVED_RRGGBB_LE: if (INT_MODE) return false; k6_direct_kernel<T, 0, 3, 2, 1><<<grid, blk, 0, s>>>(a); return true;
+    case B200_CHROMA_INTERLEAVED_RRGGBB_BE: if (INT_MODE) return false; k6_direct_kernel<T, 0, 3, 2, 0><<<grid, blk, 0, s>>>(a); return true;
+    case B200_CHROMA_INTERLEAVED_RRGGBBAA_LE: if (INT_MODE) return false; k6_direct_kernel<T, 0, 4, 2, 1><<<grid, blk, 0, s>>>(a); return true;
+    case B200_CHROMA_INTERLEAVED_RRGGBBAA_BE: if (INT_MODE) return false; k6_direct_kernel<T, 0, 4, 2, 0><<<grid, blk, 0, s>>>(a); return true;
+    default: return false;
+  }
+}
+
 // ---------------------------------------------------------------------------------------------- host
 // nclx.cc:84-173, evaluated in float exactly as the reference does
 static void primaries_of(int idx, float p[8], bool& defined) {
@@ -264,6 +385,25 @@ int launch_color(const b200_planes* in, const b200_geometry* g, const b200_color
   if (in->chroma != B200_CHROMA_MONO && (mc == 0 || mc == 8 || mc == 11 || mc == 14 || mc == 16))
     return set_error(B200_E_UNSUPPORTED, "matrix_coefficients %d has no linear YCbCr->RGB path here", mc);
   if (interleaved16 && in->bit_depth == 8) return set_error(B200_E_UNSUPPORTED, "8-bit input to RRGGBB output");
+  if (opt->chroma_upsampling == 1 && in->chroma == B200_CHROMA_420) {
+    // heif_color_conversion_options.only_use_preferred_chroma_algorithm with bilinear upsampling: the reference runs
+    // Op_YCbCr420_bilinear_to_YCbCr444 first and converts from 4:4:4 with the generic float op.
+    const bool identity = g->m[0] == 1 && g->m[1] == 0 && g->m[2] == 0 && g->m[3] == 0 && g->m[4] == 1 && g->m[5] == 0 && g->out_w == in->width && g->out_h == in->height;
+    if (!identity) return set_error(B200_E_UNSUPPORTED, "bilinear chroma upsampling combined with rotate/mirror/crop");
+    const int bps = in->bit_depth > 8 ? 2 : 1;
+    const size_t pitch = (((size_t)in->width * bps) + 255) & ~(size_t)255;
+    char* tmp = nullptr;
+    B200_CUDA_CHECK(cudaMallocAsync(&tmp, 2 * pitch * in->height, stream));
+    dim3 grid((in->width + 255) / 256, in->height);
+    if (bps == 1) bilinear_420_to_444_kernel<uint8_t><<<grid, 256, 0, stream>>>((const uint8_t*)in->cb, (const uint8_t*)in->cr, (long long)in->c_stride, (uint8_t*)tmp, (uint8_t*)(tmp + pitch * in->height), (long long)pitch, in->width, in->height);
+    else bilinear_420_to_444_kernel<uint16_t><<<grid, 256, 0, stream>>>((const uint16_t*)in->cb, (const uint16_t*)in->cr, (long long)in->c_stride / 2, (uint16_t*)tmp, (uint16_t*)(tmp + pitch * in->height), (long long)pitch / 2, in->width, in->height);
+    b200_planes up = *in; up.cb = tmp; up.cr = tmp + pitch * in->height; up.c_stride = pitch; up.chroma = B200_CHROMA_444;
+    b200_color_options o2 = *opt; o2.chroma_upsampling = 0;
+    int rc = launch_color(&up, g, &o2, out, out_g, out_b, out_stride, stream, pipeline);
+    if (pipeline) *pipeline |= B200_PIPE_BILINEAR;
+    cudaFreeAsync(tmp, stream);
+    return rc;
+  }
   K6Args a{};
   a.y = in->y; a.cb = in->cb; a.cr = in->cr; a.a = in->alpha;
   a.ys = (long long)in->y_stride; a.cs = (long long)in->c_stride; a.as = (long long)in->alpha_stride;
@@ -300,6 +440,19 @@ int launch_color(const b200_planes* in, const b200_geometry* g, const b200_color
   if (fmt == B200_CHROMA_444 && (!out_g || !out_b)) return set_error(B200_E_INVALID, "planar output needs three planes");
   if (pipeline) *pipeline = pipe;
   if (g->out_w <= 0 || g->out_h <= 0) return B200_OK;
+  // fast path: identity geometry, 4:2:0, no alpha, everything 16-byte aligned (the grid / single-image decode case)
+  const bool identity = g->m[0] == 1 && g->m[1] == 0 && g->m[2] == 0 && g->m[3] == 0 && g->m[4] == 1 && g->m[5] == 0 && g->out_w == in->width && g->out_h == in->height;
+  const uintptr_t al = (uintptr_t)in->y | (uintptr_t)in->cb | (uintptr_t)in->cr | (uintptr_t)out | (uintptr_t)in->y_stride | (uintptr_t)in->c_stride | (uintptr_t)out_stride;
+  if (identity && in->chroma == B200_CHROMA_420 && !has_alpha && (al & 15) == 0 && in->width % 16 == 0 && in->height % 2 == 0 && fmt != B200_CHROMA_444 && !(a.sdr_shift && a.out_bytes == 2)) {
+    bool done;
+    if (in->bit_depth == 8) done = a.int_mode ? launch_direct<uint8_t, 1>(a, stream) : launch_direct<uint8_t, 0>(a, stream);
+    else done = a.int_mode ? launch_direct<uint16_t, 1>(a, stream) : launch_direct<uint16_t, 0>(a, stream);
+    if (done) {
+      cudaError_t e = cudaGetLastError();
+      if (e != cudaSuccess) return set_error(B200_E_CUDA, "k6 direct launch: %s", cudaGetErrorString(e));
+      return B200_OK;
+    }
+  }
   dim3 grid((g->out_w + TILE - 1) / TILE, (g->out_h + TILE - 1) / TILE);
   if (in->bit_depth == 8) {
     if (has_alpha) k6_color_kernel<uint8_t, true><<<grid, 256, 0, stream>>>(a);

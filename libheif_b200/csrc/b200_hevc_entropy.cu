@@ -16,6 +16,7 @@
 namespace b200 { namespace syn {
 __shared__ uint32_t s_kLps4[64];
 __shared__ uint8_t s_kTransLps[64];
+__shared__ uint8_t s_kNextState[256];
 __shared__ uint8_t s_kInitI[134];
 __shared__ uint8_t s_kSigMap4[16];
 __shared__ uint8_t s_kChromaTab[4];
@@ -66,6 +67,7 @@ __global__ void __launch_bounds__(EWARPS * 32) hevc_entropy_kernel(const Entropy
   __shared__ uint8_t s_ctx[EWARPS][syn::CTX_STRIDE];
   for (int i = threadIdx.x; i < 64; i += blockDim.x) { syn::s_kLps4[i] = syn::d_kLps4[i]; syn::s_kTransLps[i] = syn::d_kTransLps[i]; }
   for (int i = threadIdx.x; i < 134; i += blockDim.x) syn::s_kInitI[i] = syn::d_kInitI[i];
+  for (int i = threadIdx.x; i < 256; i += blockDim.x) syn::s_kNextState[i] = syn::d_kNextState[i];
   for (int i = threadIdx.x; i < 16; i += blockDim.x) syn::s_kSigMap4[i] = syn::d_kSigMap4[i];
   for (int i = threadIdx.x; i < 4; i += blockDim.x) syn::s_kChromaTab[i] = syn::d_kChromaTab[i];
   for (int i = threadIdx.x; i < 4 * 3 * 64; i += blockDim.x) { (&syn::s_kScanX[0][0][0])[i] = (&syn::d_kScanX[0][0][0])[i]; (&syn::s_kScanY[0][0][0])[i] = (&syn::d_kScanY[0][0][0])[i]; }

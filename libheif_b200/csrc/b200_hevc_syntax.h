@@ -10,9 +10,13 @@
 #include "b200_hevc_types.h"
 
 #ifdef __CUDACC__
+// B200_HDN: one out-of-line copy per function on the device.  Full inlining of the syntax tree blew the entropy kernel
+// up to 38k SASS instructions (0.6 MB): the instruction cache, not arithmetic, set the pace of the lone decoding lane.
+#define B200_HDN __host__ __device__ __noinline__
 #define B200_HD __host__ __device__
 #define B200_TABLE(type, name, dims, ...) static const type h_##name dims = __VA_ARGS__; static __device__ const type d_##name dims = __VA_ARGS__;
 #else
+#define B200_HDN
 #define B200_HD
 #define B200_TABLE(type, name, dims, ...) static const type h_##name dims = __VA_ARGS__;
 #endif
@@ -95,69 +99,106 @@ struct PicBuffers {              // per-picture arrays (host memory on the host 
 };
 
 // ---------------------------------------------------------------------------------------------- CABAC (9.3.4.3)
-// Literal 9-bit-offset arithmetic decoder over 32-bit big-endian words with a 64-bit reservoir; the bit position after
-// a terminating bin is the one the specification defines.
+// Arithmetic decoder in the "scaled window" form: `val` holds the specification's 9-bit ivlOffset in bits 31..16 (as
+// offset << 16) followed by up to 16 look-ahead bits; DecodeDecision / DecodeBypass / DecodeTerminate become a few
+// branch-free integer operations and two table look-ups (rangeTabLps packed per state, merged state-transition table).
+// The bit position after a terminating bin is reconstructed exactly (bits consumed = 9 + renormalisation shifts), which
+// the host front-end cross-checks against the entry points of every WPP stream it parses.
+B200_TABLE(uint8_t, kNextState, [256], {2,3,4,5,6,7,8,9,10,11,12,13,14,15,16,17,18,19,20,21,22,23,24,25,26,27,28,29,30,31,32,33,34,35,36,37,38,39,40,41,42,43,44,45,46,47,48,49,50,51,52,53,54,55,56,57,58,59,60,61,62,63,64,65,66,67,68,69,70,71,72,73,74,75,76,77,78,79,80,81,82,83,84,85,86,87,88,89,90,91,92,93,94,95,96,97,98,99,100,101,102,103,104,105,106,107,108,109,110,111,112,113,114,115,116,117,118,119,120,121,122,123,124,125,124,125,126,127,1,0,0,1,2,3,4,5,4,5,8,9,8,9,10,11,12,13,14,15,16,17,18,19,18,19,22,23,22,23,24,25,26,27,26,27,30,31,30,31,32,33,32,33,36,37,36,37,38,39,38,39,42,43,42,43,44,45,44,45,46,47,48,49,48,49,50,51,52,53,52,53,54,55,54,55,56,57,58,59,58,59,60,61,60,61,60,61,62,63,64,65,64,65,66,67,66,67,66,67,68,69,68,69,70,71,70,71,70,71,72,73,72,73,72,73,74,75,74,75,74,75,76,77,76,77,126,127})   // [ctx byte | lps << 7] -> next ctx byte ((pStateIdx << 1) | valMps)
+
 struct Cabac {
-  const uint8_t* d; uint32_t n; uint32_t word; uint32_t next_w; uint64_t res; int avail; unsigned range, offset;
+  const uint8_t* d; uint32_t nwords; uint32_t word;   // next 32-bit word to fetch
+  uint32_t next_w;                                    // word `word`, prefetched one step ahead (keeps the L2 latency off the chain)
+  uint32_t val, range; int bits;                      // bits: valid look-ahead bits below bit 16 of val, minus 16 pending
+  uint32_t stash; int stash_bits;                     // not-yet-used bits of the last fetched word
+  uint32_t consumed;                                  // bits shifted into the 9-bit window so far (position bookkeeping)
+  uint32_t start_bit;
   B200_HD inline uint32_t load_be32(uint32_t w) const {
-    const uint32_t b = w * 4;
-    if (b + 4 <= n) {
+    if (w >= nwords) return 0u;
 #ifdef __CUDA_ARCH__
-      const uint32_t v = __ldg(reinterpret_cast<const uint32_t*>(d + b));
-      return __byte_perm(v, 0, 0x0123);
+    return __byte_perm(__ldg(reinterpret_cast<const uint32_t*>(d) + w), 0, 0x0123);
 #else
-      return ((uint32_t)d[b] << 24) | ((uint32_t)d[b + 1] << 16) | ((uint32_t)d[b + 2] << 8) | d[b + 3];
+    const uint8_t* p = d + (size_t)w * 4;
+    return ((uint32_t)p[0] << 24) | ((uint32_t)p[1] << 16) | ((uint32_t)p[2] << 8) | p[3];
 #endif
+  }
+  B200_HD inline void start(const uint8_t* data, uint32_t size, uint32_t start_byte) {
+    d = data; nwords = size >> 2; word = start_byte >> 2;
+    next_w = load_be32(word); stash = 0; stash_bits = 0;
+    // align to the first byte: drop (start_byte & 3) bytes of the first word, 8 bits at a time
+    const int skip = (int)(start_byte & 3) * 8;
+    stash = next_w << skip; stash_bits = 32 - skip; word++; next_w = load_be32(word);
+    start_bit = start_byte * 8;
+    // initial window: 9 bits (9.3.2.5) + 16 look-ahead bits, assembled from up to 3 fetches of 16 (stash may hold 8/24 bits)
+    uint64_t acc = 0; int have = 0;
+    while (have < 25) {
+      if (stash_bits == 0) { stash = next_w; stash_bits = 32; word++; next_w = load_be32(word); }
+      const int t = stash_bits < 25 - have ? stash_bits : 25 - have;
+      acc = (acc << t) | (stash >> (32 - t)); stash = t < 32 ? stash << t : 0; stash_bits -= t; have += t;
     }
-    uint32_t v = 0;
-    for (int k = 0; k < 4; k++) v = (v << 8) | (b + k < n ? d[b + k] : 0u);
+    // acc holds 25 bits: 9 window bits then 16 look-ahead bits
+    val = (uint32_t)acc;                                  // = offset << 16 | look-ahead
+    bits = 16; range = 510; consumed = 9;
+  }
+  B200_HD inline uint64_t bit_position() const { return (uint64_t)start_bit + consumed; }
+  // shift the window left by n (n <= 16 per call), pulling fresh bits from the stream when the look-ahead is exhausted
+  B200_HD inline void shift(int n) {
+    val <<= n; bits -= n; consumed += (uint32_t)n;
+    if (bits < 0) { val |= take_bits16() << (-bits); bits += 16; }
+  }
+  B200_HD inline uint32_t take_bits16() {               // next 16 stream bits, stash alignment agnostic
+    if (stash_bits >= 16) { const uint32_t v = stash >> 16; stash <<= 16; stash_bits -= 16; return v; }
+    uint32_t v = stash_bits ? (stash >> (32 - stash_bits)) : 0u; const int have = stash_bits;
+    stash = next_w; stash_bits = 32; word++; next_w = load_be32(word);
+    const int need = 16 - have;
+    v = (v << need) | (stash >> (32 - need)); stash <<= need; stash_bits -= need;
     return v;
   }
-  // `next_w` always holds word `word`, fetched one refill ahead so the HBM/L2 latency is off the dependency chain
-  B200_HD inline void refill() { if (avail <= 32) { res |= (uint64_t)next_w << (32 - avail); avail += 32; word++; next_w = load_be32(word); } }
-  B200_HD inline unsigned take(int k) { refill(); unsigned v = k ? (unsigned)(res >> (64 - k)) : 0u; res <<= k; avail -= k; return v; }
-  B200_HD inline void start(const uint8_t* data, uint32_t size, uint32_t start_byte) {
-    d = data; n = size; word = start_byte >> 2; res = 0; avail = 0;
-    next_w = load_be32(word);
-    const int skip = (int)(start_byte & 3) * 8;
-    refill(); res <<= skip; avail -= skip;
-    range = 510; offset = take(9);
-  }
-  B200_HD inline uint64_t bit_position() const { return (uint64_t)word * 32 - (uint64_t)avail; }
   B200_HD inline int bin(uint8_t& c) {
-    const unsigned cv = c;
-    const unsigned state = cv >> 1; unsigned mps = cv & 1;
-    const unsigned lps = (B200_T(kLps4)[state] >> (((range >> 6) & 3) * 8)) & 0xff;
-    range -= lps;
-    int b;
-    if (offset >= range) {
-      b = (int)(mps ^ 1); offset -= range; range = lps;
-      if (state == 0) mps ^= 1;
-      c = (uint8_t)((B200_T(kTransLps)[state] << 1) | mps);
+    const uint32_t cv = c;
+    const uint32_t rlps = (B200_T(kLps4)[cv >> 1] >> (((range >> 6) & 3) * 8)) & 0xff;
+    const uint32_t rmps = range - rlps;
+    const uint32_t lps = (val >> 16) >= rmps ? 1u : 0u;
+    val -= lps ? (rmps << 16) : 0u;
+    range = lps ? rlps : rmps;
+    c = B200_T(kNextState)[cv | (lps << 7)];
 #ifdef __CUDA_ARCH__
-      const int sh = __clz((int)range) - 23;
+    const int n = __clz((int)range) - 23;
 #else
-      const int sh = __builtin_clz(range) - 23;
+    const int n = __builtin_clz(range) - 23;
 #endif
-      range <<= sh; offset = (offset << sh) | take(sh);
-    } else {
-      b = (int)mps;
-      if (state < 62) c = (uint8_t)(cv + 2);
-      if (range < 256) { range <<= 1; offset = (offset << 1) | take(1); }
-    }
-    return b;
+    range <<= n;
+    if (n) shift(n);
+    return (int)((cv & 1) ^ lps);
   }
-  B200_HD inline int bypass() { offset = (offset << 1) | take(1); if (offset >= range) { offset -= range; return 1; } return 0; }
-  B200_HD inline unsigned bypass_bits(int k) { unsigned v = 0; while (k-- > 0) v = (v << 1) | (unsigned)bypass(); return v; }
+  B200_HD inline int bypass() {
+    shift(1);
+    const uint32_t one = (val >> 16) >= range ? 1u : 0u;
+    val -= one ? (range << 16) : 0u;
+    return (int)one;
+  }
+  // k bypass bins at once (9.3.4.3.4 applied k times): offset < range, so (offset << k | bits) / range < 2^k is the bin string
+  B200_HD inline unsigned bypass_bits(int k) {
+    unsigned out = 0;
+    while (k > 0) {
+      const int t = k > 7 ? 7 : k;                       // window (9 bits) + t <= 16 bits: stays inside bits 31..16 of val
+      shift(t);
+      const uint32_t w = val >> 16;                      // (offset << t) | t fresh bits
+      const uint32_t q = w / range;
+      val -= (q * range) << 16;
+      out = (out << t) | q; k -= t;
+    }
+    return out;
+  }
   B200_HD inline int terminate() {
     range -= 2;
-    if (offset >= range) return 1;
-    if (range < 256) { range <<= 1; offset = (offset << 1) | take(1); }
+    if ((val >> 16) >= range) return 1;
+    if (range < 256) { range <<= 1; shift(1); }
     return 0;
   }
 };
 
-B200_HD inline void init_contexts(uint8_t* ctx, int slice_qp) {          // 9.3.2.2
+B200_HDN inline void init_contexts(uint8_t* ctx, int slice_qp) {          // 9.3.2.2
   const int qp = clip3(0, 51, slice_qp);
   for (int i = 0; i < CTX_COUNT; i++) {
     const int iv = B200_T(kInitI)[i], m = (iv >> 4) * 5 - 45, nn = ((iv & 15) << 3) - 16;
@@ -188,7 +229,7 @@ struct Decoder {
   }
 
   // -------- SAO (7.3.8.3)
-  B200_HD void parse_sao(int rx, int ry, CtuInfo& ci) {
+  B200_HDN void parse_sao(int rx, int ry, CtuInfo& ci) {
     const int addr = ry * sp->wctb + rx;
     for (int c = 0; c < 3; c++) { ci.sao[c].type = 0; ci.sao[c].band_or_class = 0; for (int k = 0; k < 4; k++) ci.sao[c].offset[k] = 0; }
     if (!ss->sao_luma && !ss->sao_chroma) return;
@@ -222,7 +263,7 @@ struct Decoder {
   }
 
   // -------- QP (8.6.1); QpY is kept per 8x8 block (coding blocks are >= 8x8)
-  B200_HD void derive_qpy(int xcb, int ycb) {
+  B200_HDN void derive_qpy(int xcb, int ycb) {
     const int mask = (1 << sp->qg_log2) - 1, xqg = xcb & ~mask, yqg = ycb & ~mask, cm = ~((1 << sp->log2ctb) - 1);
     int qa = qpy_prev_qg, qb = qpy_prev_qg;
     if (avail(xqg - 1, yqg) && ((xqg - 1) & cm) == (xqg & cm)) qa = B200_LD_SHARED(pb.qp8 + (yqg >> 3) * sp->w8 + ((xqg - 1) >> 3));
@@ -232,7 +273,7 @@ struct Decoder {
   }
 
   // -------- residual_coding (7.3.8.11): emits sparse (pos, level) entries; returns the number of coefficients
-  B200_HD int residual(int log2n, int c, int mode, int& tskip) {
+  B200_HDN int residual(int log2n, int c, int mode, int& tskip) {
     const int n = 1 << log2n;
     // Local copies: their addresses never escape, so they live in registers and need no reload after the byte stores
     // into the context array (uint8_t stores may alias any member otherwise).
@@ -338,7 +379,7 @@ struct Decoder {
   }
 
   // -------- transform tree / unit (7.3.8.8, 7.3.8.10)
-  B200_HD void mark_tu(int x0, int y0, int log2n) {
+  B200_HDN void mark_tu(int x0, int y0, int log2n) {
     // QpY map + filterEdgeFlag (8.7.2.3, bS = 2 on every transform edge of the 8x8 grid) for the deblocking kernel
     const SliceInfo& sl = pb.slices[ss->slice_idx];
     const int n8 = log2n > 3 ? 1 << (log2n - 3) : 1, bx = x0 >> 3, by = y0 >> 3;
@@ -355,7 +396,7 @@ struct Decoder {
     }
   }
 
-  B200_HD void transform_unit(const Cu& cu, int x0, int y0, int log2n, int blk, int cbf_l, int cbf_cb, int cbf_cr, int pcb, int pcr) {
+  B200_HDN void transform_unit(const Cu& cu, int x0, int y0, int log2n, int blk, int cbf_l, int cbf_cb, int cbf_cr, int pcb, int pcr) {
     const int cbf_c = sp->chroma ? (log2n > 2 ? (cbf_cb | cbf_cr) : (pcb | pcr)) : 0;
     if ((cbf_l || cbf_c) && sp->cu_qp_delta && !is_dqp_coded) {
       int v = 0;
@@ -386,7 +427,7 @@ struct Decoder {
     pb.tus[tu_n++] = t;
   }
 
-  B200_HD void transform_tree(const Cu& cu, int x0, int y0, int log2n, int depth, int blk, int pcb, int pcr, int max_depth) {
+  B200_HDN void transform_tree(const Cu& cu, int x0, int y0, int log2n, int depth, int blk, int pcb, int pcr, int max_depth) {
     if (err) return;
     int split;
     if (log2n <= sp->log2_max_tb && log2n > sp->log2_min_tb && depth < max_depth && !(cu.nxn && depth == 0)) split = cabac.bin(ctx[CTX_SPLIT_TR + 5 - log2n]);
@@ -408,7 +449,7 @@ struct Decoder {
   }
 
   // -------- 8.4.2
-  B200_HD int luma_mode(int x, int y, int prev, int mpm_idx, int rem) const {
+  B200_HDN int luma_mode(int x, int y, int prev, int mpm_idx, int rem) const {
     int ca = 1, cb = 1;
     if (avail(x - 1, y)) ca = B200_LD_SHARED(pb.ipm4 + (y >> 2) * sp->w4 + ((x - 1) >> 2));
     if (avail(x, y - 1) && (y - 1) >= ((y >> sp->log2ctb) << sp->log2ctb)) cb = B200_LD_SHARED(pb.ipm4 + ((y - 1) >> 2) * sp->w4 + (x >> 2));
@@ -428,7 +469,7 @@ struct Decoder {
   }
 
   // -------- 7.3.8.5
-  B200_HD void coding_unit(int x0, int y0, int log2cb, int depth) {
+  B200_HDN void coding_unit(int x0, int y0, int log2cb, int depth) {
     Cu cu; cu.x0 = x0; cu.y0 = y0; cu.log2cb = log2cb; cu.nxn = 0; cu.cmode = 0;
     const int n = 1 << log2cb;
     if (log2cb == sp->log2_min_cb) cu.nxn = !cabac.bin(ctx[CTX_PART_MODE]);
@@ -455,7 +496,7 @@ struct Decoder {
   }
 
   // -------- 7.3.8.4
-  B200_HD void coding_quadtree(int x0, int y0, int log2cb, int depth) {
+  B200_HDN void coding_quadtree(int x0, int y0, int log2cb, int depth) {
     if (err) return;
     const int n = 1 << log2cb;
     int split;
@@ -476,7 +517,7 @@ struct Decoder {
   }
 
   // One coding tree unit (7.3.8.2): SAO syntax + coding quadtree; fills its CtuInfo.
-  B200_HD void decode_ctb(int addr) {
+  B200_HDN void decode_ctb(int addr) {
     const int rx = addr % sp->wctb, ry = addr / sp->wctb;
     cur_ctb_x = rx; cur_ctb_y = ry;
     CtuInfo& ci = pb.ctus[addr];
@@ -541,7 +582,7 @@ B200_HD int run_substream(const SeqParams& sp, const PicBuffers& pb, const Subst
     if (end != ((last && ss.last_of_segment) ? 1 : 0)) { d.err = SYN_E_BITSTREAM; break; }
     if (last && !ss.last_of_segment) { if (!d.cabac.terminate()) { d.err = SYN_E_BITSTREAM; break; } }   // end_of_subset_one_bit
     sync.publish_row(ry, rx + 1);
-    if (d.cabac.word * 4 > pb.rbsp_size + 32) { d.err = SYN_E_BITSTREAM; break; }
+    if ((uint64_t)d.cabac.word * 4 > (uint64_t)pb.rbsp_size + 64) { d.err = SYN_E_BITSTREAM; break; }
   }
   // end state for a dependent continuation + dense cursors
   { uint8_t* st = pb.end_state + (size_t)index * CTX_STRIDE; for (int i = 0; i < CTX_COUNT; i++) st[i] = ctx[i]; st[CTX_COUNT] = (uint8_t)(int8_t)d.last_cu_qpy; }

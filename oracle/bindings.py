@@ -142,7 +142,7 @@ def ref_postprocess(y, cb, cr, a, chroma, bpp, nclx, ops, out_chroma, only_prefe
     return out[:n].copy(), ow.value, oh.value, npl.value
 
 
-def oracle_postprocess(y, cb, cr, a, chroma, bpp, nclx, ops, out_chroma):
+def oracle_postprocess(y, cb, cr, a, chroma, bpp, nclx, ops, out_chroma, bilinear=0):
     """C restatement (oracle/color_oracle.c)."""
     l = lib()
     h, w = y.shape
@@ -151,10 +151,10 @@ def oracle_postprocess(y, cb, cr, a, chroma, bpp, nclx, ops, out_chroma):
     cap = (max(w, h) + 64) ** 2 * 8
     out = np.empty(cap, dtype=np.uint8)
     ow, oh = C.c_int(), C.c_int()
-    l.co_postprocess.restype = C.c_long
+    l.co_postprocess2.restype = C.c_long
     keep = [np.ascontiguousarray(p, dtype=np.uint16) if p is not None else None for p in (y, cb, cr, a)]
-    n = l.co_postprocess(*[None if k is None else k.ctypes.data_as(C.c_void_p) for k in keep], w, h, chroma, bpp, cp, mc, int(fr),
-                         ops_a, len(ops), out_chroma, out.ctypes.data_as(C.c_void_p), C.byref(ow), C.byref(oh))
+    n = l.co_postprocess2(*[None if k is None else k.ctypes.data_as(C.c_void_p) for k in keep], w, h, chroma, bpp, cp, mc, int(fr),
+                          ops_a, len(ops), out_chroma, int(bilinear), out.ctypes.data_as(C.c_void_p), C.byref(ow), C.byref(oh))
     if n < 0:
         raise RuntimeError("co_postprocess failed")
     return out[:n].copy(), ow.value, oh.value

@@ -9,6 +9,7 @@
  *   Op_YCbCr420_to_RGB24 / RGB32 (integer arithmetic)       yuv2rgb.cc:345-426, :481-562
  *   Op_YCbCr420_to_RRGGBBaa                                 yuv2rgb.cc:622-734
  *   Op_RGB_to_RGB24_32, Op_to_sdr_planes                    rgb2rgb.cc:71-150, hdr_sdr.cc:147-200
+ *   Op_YCbCr420_bilinear_to_YCbCr444<T>                     chroma_sampling.cc:501-724 (incl. its border indexing)
  *   get_YCbCr_to_RGB_coefficients / get_Kr_Kb               nclx.cc:84-173
  *   HeifPixelImage::overlay, scale_nearest_neighbor         pixelimage.cc:1637-1780, :1783-1972
  * PINNED against the unmodified reference (oracle/_ref/libheif_ref.so through ref_postprocess() in
@@ -119,15 +120,49 @@ void co_coefficients(int matrix, int primaries, float out[4]) {
 static int clip_f_u16(float fx, int maxi) { int x = (int)(fx + 0.5f); return x < 0 ? 0 : (x > maxi ? maxi : x); }   /* common_utils.h:108-114 */
 static int clip_int_u8(int x) { return x < 0 ? 0 : (x > 255 ? 255 : x); }
 
+/* chroma_sampling.cc:623-700 restated loop for loop, including the border loops that index the source with cx/2, cy/2
+   (golden table tests/conversion.cc:697-724).  in: (w+1)/2 x (h+1)/2, out: w x h. */
+void co_bilinear_420_to_444(const uint16_t* in, int w, int h, uint16_t* out) {
+  const int cs = (w + 1) / 2, os = w;
+  out[0] = in[0];
+  for (int cx = 0; cx < (w - 1) / 2; cx++) {
+    out[2 * cx + 1] = (uint16_t)((3 * in[cx / 2] + 1 * in[cx / 2 + 1] + 2) / 4);
+    out[2 * cx + 2] = (uint16_t)((1 * in[cx / 2] + 3 * in[cx / 2 + 1] + 2) / 4);
+  }
+  if (w % 2 == 0) out[w - 1] = in[w / 2 - 1];
+  for (int cy = 0; cy < (h - 1) / 2; cy++) {
+    out[(2 * cy + 1) * os] = (uint16_t)((3 * in[cy / 2 * cs] + 1 * in[(cy / 2 + 1) * cs] + 2) / 4);
+    out[(2 * cy + 2) * os] = (uint16_t)((1 * in[cy / 2 * cs] + 3 * in[(cy / 2 + 1) * cs] + 2) / 4);
+  }
+  if (h % 2 == 0) out[(h - 1) * os] = in[(h / 2 - 1) * cs];
+  if (w % 2 == 0) for (int cy = 0; cy < (h - 1) / 2; cy++) {
+    out[(2 * cy + 1) * os + w - 1] = (uint16_t)((3 * in[cy / 2 * cs + w / 2 - 1] + 1 * in[(cy / 2 + 1) * cs + w / 2 - 1] + 2) / 4);
+    out[(2 * cy + 2) * os + w - 1] = (uint16_t)((1 * in[cy / 2 * cs + w / 2 - 1] + 3 * in[(cy / 2 + 1) * cs + w / 2 - 1] + 2) / 4);
+  }
+  if (h % 2 == 0) for (int cx = 0; cx < (w - 1) / 2; cx++) {
+    out[(h - 1) * os + 2 * cx + 1] = (uint16_t)((3 * in[(h / 2 - 1) * cs + cx / 2] + 1 * in[(h / 2 - 1) * cs + cx / 2 + 1] + 2) / 4);
+    out[(h - 1) * os + 2 * cx + 2] = (uint16_t)((1 * in[(h / 2 - 1) * cs + cx / 2] + 3 * in[(h / 2 - 1) * cs + cx / 2 + 1] + 2) / 4);
+  }
+  if (w % 2 == 0 && h % 2 == 0) out[(h - 1) * os + w - 1] = in[(h / 2 - 1) * cs + w / 2 - 1];
+  for (int y = 1; y < h - 1; y += 2) for (int x = 1; x < w - 1; x += 2) {
+    int cx = x / 2, cy = y / 2;
+    int c00 = in[cy * cs + cx], c01 = in[cy * cs + cx + 1], c10 = in[(cy + 1) * cs + cx], c11 = in[(cy + 1) * cs + cx + 1];
+    out[y * os + x] = (uint16_t)((c00 * 9 + c01 * 3 + c10 * 3 + c11 + 8) / 16);
+    out[y * os + x + 1] = (uint16_t)((c00 * 3 + c01 * 9 + c10 + c11 * 3 + 8) / 16);
+    out[(y + 1) * os + x] = (uint16_t)((c00 * 3 + c01 + c10 * 9 + c11 * 3 + 8) / 16);
+    out[(y + 1) * os + x + 1] = (uint16_t)((c00 + c01 * 3 + c10 * 3 + c11 * 9 + 8) / 16);
+  }
+}
+
 /*
  * The whole post-stage on tightly packed uint16 planes.
  *   ops: nops x 5 ints {kind (1 rotate_ccw, 2 mirror, 3 crop), a, b, c, d}
  *   out_chroma: 10 RGB, 11 RGBA, 12/13 RRGGBB(AA)_BE, 14/15 RRGGBB(AA)_LE, 3 planar RGB (uint8 or uint16 by depth)
  * Returns bytes written to out (rows tightly packed; planar: R,G,B planes one after the other) or <0.
  */
-long co_postprocess(const uint16_t* y, const uint16_t* cb, const uint16_t* cr, const uint16_t* alpha, int w, int h, int chroma,
-                    int bpp, int cp, int mc, int full_range, const int* ops, int nops, int out_chroma,
-                    uint8_t* out, int* out_w, int* out_h) {
+long co_postprocess2(const uint16_t* y, const uint16_t* cb, const uint16_t* cr, const uint16_t* alpha, int w, int h, int chroma,
+                     int bpp, int cp, int mc, int full_range, const int* ops, int nops, int out_chroma, int bilinear,
+                     uint8_t* out, int* out_w, int* out_h) {
   co_image im; memset(&im, 0, sizeof im);
   int sh = (chroma == 1 || chroma == 2) ? 1 : 0, sv = chroma == 1 ? 1 : 0;
   im.w = w; im.h = h; im.chroma = chroma; im.cw = chroma ? (w + sh) >> sh : 0; im.ch = chroma ? (h + sv) >> sv : 0;
@@ -139,6 +174,10 @@ long co_postprocess(const uint16_t* y, const uint16_t* cb, const uint16_t* cr, c
   }
   co_geometry(&im, ops, nops);
   w = im.w; h = im.h;
+  if (bilinear && im.chroma == 1) {          /* only_use_preferred_chroma_algorithm: Op_YCbCr420_bilinear_to_YCbCr444 first, then the generic float op */
+    for (int c = 1; c <= 2; c++) { uint16_t* up = (uint16_t*)malloc((size_t)w * h * 2 + 2); co_bilinear_420_to_444(im.p[c], w, h, up); free(im.p[c]); im.p[c] = up; }
+    im.chroma = 3; im.cw = w; im.ch = h; chroma = 3; sh = 0; sv = 0;
+  }
   *out_w = w; *out_h = h;
   float cf[4]; co_coefficients(mc, cp, cf);
   const int interleaved8 = out_chroma == 10 || out_chroma == 11;
@@ -197,4 +236,10 @@ long co_postprocess(const uint16_t* y, const uint16_t* cb, const uint16_t* cr, c
   co_free(&im);
   if (out_chroma == 3) return (long)((size_t)w * h * 3 * (out16 ? 2 : 1));
   return (long)pos;
+}
+
+long co_postprocess(const uint16_t* y, const uint16_t* cb, const uint16_t* cr, const uint16_t* alpha, int w, int h, int chroma,
+                    int bpp, int cp, int mc, int full_range, const int* ops, int nops, int out_chroma,
+                    uint8_t* out, int* out_w, int* out_h) {
+  return co_postprocess2(y, cb, cr, alpha, w, h, chroma, bpp, cp, mc, full_range, ops, nops, out_chroma, 0, out, out_w, out_h);
 }

@@ -108,3 +108,15 @@ def test_full_size_properties(cuda):
     assert np.array_equal(_as_bytes(tile), want)
     host, _ = lb.convert_colorspace_host(_img(y, cb, cr, None, 1, 8, (1, 13, 6, 0)), 10)
     assert hashlib.md5(host.tobytes()).hexdigest() == hashlib.md5(base.cpu().numpy().tobytes()).hexdigest()
+
+
+@pytest.mark.parametrize("case", [(1, 8, (1, 13, 6, 0), 10), (1, 8, (1, 13, 6, 1), 10), (1, 8, (1, 13, 1, 0), 11), (1, 10, (9, 16, 9, 0), 14), (1, 12, (9, 16, 9, 1), 14)])
+@pytest.mark.parametrize("size", [(4, 4), (34, 18), (33, 17), (130, 70), (512, 256)])
+def test_bilinear_chroma_upsampling(cuda, case, size):
+    """only_use_preferred_chroma_algorithm + bilinear (heif-dec -C bilinear): Op_YCbCr420_bilinear_to_YCbCr444 + float op."""
+    chroma, bpp, nclx, outc = case
+    w, h = size
+    y, cb, cr, _ = random_ycbcr(0xB200 + w * 7 + h, w, h, chroma, bpp)
+    want, ow, oh = oracle_postprocess(y, cb, cr, None, chroma, bpp, nclx, [], outc, bilinear=1)
+    got = lb.convert_colorspace(_img(y, cb, cr, None, chroma, bpp, nclx, cuda), outc, bilinear=True)
+    assert np.array_equal(_as_bytes(got), want)

@@ -58,3 +58,32 @@ def test_geometry_then_colour(ops, fmt):
     got, ow, oh = oracle_postprocess(y, cb, cr, None, chroma, bpp, nclx, ops, outc)
     assert (ow, oh) == (rw, rh)
     assert np.array_equal(ref, got)
+
+
+def test_bilinear_golden_table_of_reference_tests():
+    """tests/conversion.cc:697-724 ('Bilinear upsampling'): Cb {10,40;100,240}, Cr {255,200;50,0} -> 4x4 tables."""
+    import ctypes as C
+    from oracle import bindings as ob
+    l = ob.lib()
+    for src, want in (([10, 40, 100, 240], [10, 18, 33, 40, 33, 47, 76, 90, 78, 106, 162, 190, 100, 135, 205, 240]),
+                      ([255, 200, 50, 0], [255, 241, 214, 200, 204, 190, 163, 150, 101, 88, 63, 50, 50, 38, 13, 0])):
+        a = np.array(src, np.uint16); out = np.zeros(16, np.uint16)
+        l.co_bilinear_420_to_444(a.ctypes.data_as(C.c_void_p), 4, 4, out.ctypes.data_as(C.c_void_p))
+        assert out.tolist() == want
+
+
+BILINEAR_CASES = [(1, 8, (1, 13, 6, 0), 10), (1, 8, (1, 13, 6, 1), 10), (1, 8, (1, 13, 1, 0), 11), (1, 10, (9, 16, 9, 0), 14), (1, 12, (9, 16, 9, 1), 14)]
+
+
+@needs_ref
+@pytest.mark.parametrize("case", BILINEAR_CASES)
+@pytest.mark.parametrize("size", [(4, 4), (6, 4), (34, 18), (33, 17), (64, 64), (130, 70)])
+def test_bilinear_pipeline_matches_reference(case, size):
+    """heif-dec -C bilinear: only_use_preferred_chroma_algorithm=1, incl. the border indexing of the reference."""
+    chroma, bpp, nclx, outc = case
+    w, h = size
+    y, cb, cr, _ = random_ycbcr(0xB200 + w * 7 + h, w, h, chroma, bpp)
+    ref, rw, rh, _ = ref_postprocess(y, cb, cr, None, chroma, bpp, nclx, [], outc, only_preferred=1, upsampling=2)
+    got, ow, oh = oracle_postprocess(y, cb, cr, None, chroma, bpp, nclx, [], outc, bilinear=1)
+    assert (ow, oh) == (rw, rh)
+    assert np.array_equal(ref, got), f"first diff at {np.argwhere(ref != got)[:4].ravel()}"
