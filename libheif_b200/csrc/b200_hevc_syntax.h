@@ -13,10 +13,12 @@
 // B200_HDN: one out-of-line copy per function on the device.  Full inlining of the syntax tree blew the entropy kernel
 // up to 38k SASS instructions (0.6 MB): the instruction cache, not arithmetic, set the pace of the lone decoding lane.
 #define B200_HDN __host__ __device__ __noinline__
+#define B200_NOUNROLL _Pragma("unroll 1")
 #define B200_HD __host__ __device__
 #define B200_TABLE(type, name, dims, ...) static const type h_##name dims = __VA_ARGS__; static __device__ const type d_##name dims = __VA_ARGS__;
 #else
 #define B200_HDN
+#define B200_NOUNROLL
 #define B200_HD
 #define B200_TABLE(type, name, dims, ...) static const type h_##name dims = __VA_ARGS__;
 #endif
@@ -106,12 +108,12 @@ struct PicBuffers {              // per-picture arrays (host memory on the host 
 // the host front-end cross-checks against the entry points of every WPP stream it parses.
 B200_TABLE(uint8_t, kNextState, [256], {2,3,4,5,6,7,8,9,10,11,12,13,14,15,16,17,18,19,20,21,22,23,24,25,26,27,28,29,30,31,32,33,34,35,36,37,38,39,40,41,42,43,44,45,46,47,48,49,50,51,52,53,54,55,56,57,58,59,60,61,62,63,64,65,66,67,68,69,70,71,72,73,74,75,76,77,78,79,80,81,82,83,84,85,86,87,88,89,90,91,92,93,94,95,96,97,98,99,100,101,102,103,104,105,106,107,108,109,110,111,112,113,114,115,116,117,118,119,120,121,122,123,124,125,124,125,126,127,1,0,0,1,2,3,4,5,4,5,8,9,8,9,10,11,12,13,14,15,16,17,18,19,18,19,22,23,22,23,24,25,26,27,26,27,30,31,30,31,32,33,32,33,36,37,36,37,38,39,38,39,42,43,42,43,44,45,44,45,46,47,48,49,48,49,50,51,52,53,52,53,54,55,54,55,56,57,58,59,58,59,60,61,60,61,60,61,62,63,64,65,64,65,66,67,66,67,66,67,68,69,68,69,70,71,70,71,70,71,72,73,72,73,72,73,74,75,74,75,74,75,76,77,76,77,126,127})   // [ctx byte | lps << 7] -> next ctx byte ((pStateIdx << 1) | valMps)
 
-struct Cabac {
+// Cold half: stream position and the word stash (touched once per 16 consumed bits; lives in memory, out of line).
+struct CabacStream {
   const uint8_t* d; uint32_t nwords; uint32_t word;   // next 32-bit word to fetch
   uint32_t next_w;                                    // word `word`, prefetched one step ahead (keeps the L2 latency off the chain)
-  uint32_t val, range; int bits;                      // bits: valid look-ahead bits below bit 16 of val, minus 16 pending
   uint32_t stash; int stash_bits;                     // not-yet-used bits of the last fetched word
-  uint32_t consumed;                                  // bits shifted into the 9-bit window so far (position bookkeeping)
+  uint32_t fetched;                                   // stream bits moved into the decoder so far
   uint32_t start_bit;
   B200_HD inline uint32_t load_be32(uint32_t w) const {
     if (w >= nwords) return 0u;
@@ -122,37 +124,44 @@ struct Cabac {
     return ((uint32_t)p[0] << 24) | ((uint32_t)p[1] << 16) | ((uint32_t)p[2] << 8) | p[3];
 #endif
   }
-  B200_HD inline void start(const uint8_t* data, uint32_t size, uint32_t start_byte) {
-    d = data; nwords = size >> 2; word = start_byte >> 2;
-    next_w = load_be32(word); stash = 0; stash_bits = 0;
-    // align to the first byte: drop (start_byte & 3) bytes of the first word, 8 bits at a time
-    const int skip = (int)(start_byte & 3) * 8;
-    stash = next_w << skip; stash_bits = 32 - skip; word++; next_w = load_be32(word);
-    start_bit = start_byte * 8;
-    // initial window: 9 bits (9.3.2.5) + 16 look-ahead bits, assembled from up to 3 fetches of 16 (stash may hold 8/24 bits)
-    uint64_t acc = 0; int have = 0;
-    while (have < 25) {
-      if (stash_bits == 0) { stash = next_w; stash_bits = 32; word++; next_w = load_be32(word); }
-      const int t = stash_bits < 25 - have ? stash_bits : 25 - have;
-      acc = (acc << t) | (stash >> (32 - t)); stash = t < 32 ? stash << t : 0; stash_bits -= t; have += t;
-    }
-    // acc holds 25 bits: 9 window bits then 16 look-ahead bits
-    val = (uint32_t)acc;                                  // = offset << 16 | look-ahead
-    bits = 16; range = 510; consumed = 9;
-  }
-  B200_HD inline uint64_t bit_position() const { return (uint64_t)start_bit + consumed; }
-  // shift the window left by n (n <= 16 per call), pulling fresh bits from the stream when the look-ahead is exhausted
-  B200_HD inline void shift(int n) {
-    val <<= n; bits -= n; consumed += (uint32_t)n;
-    if (bits < 0) { val |= take_bits16() << (-bits); bits += 16; }
-  }
-  B200_HD inline uint32_t take_bits16() {               // next 16 stream bits, stash alignment agnostic
+  B200_HDN uint32_t take16() {                          // next 16 stream bits, stash alignment agnostic
+    fetched += 16;
     if (stash_bits >= 16) { const uint32_t v = stash >> 16; stash <<= 16; stash_bits -= 16; return v; }
     uint32_t v = stash_bits ? (stash >> (32 - stash_bits)) : 0u; const int have = stash_bits;
     stash = next_w; stash_bits = 32; word++; next_w = load_be32(word);
     const int need = 16 - have;
     v = (v << need) | (stash >> (32 - need)); stash <<= need; stash_bits -= need;
     return v;
+  }
+};
+
+// Hot half: three scalars that stay in registers inside the residual decoder.
+struct Cabac {
+  uint32_t val, range; int bits;                      // bits: valid look-ahead bits in the low half of val
+  CabacStream* st;
+  B200_HD inline void start(CabacStream* stream, const uint8_t* data, uint32_t size, uint32_t start_byte) {
+    st = stream;
+    st->d = data; st->nwords = size >> 2; st->word = start_byte >> 2;
+    st->next_w = st->load_be32(st->word);
+    const int skip = (int)(start_byte & 3) * 8;
+    st->stash = st->next_w << skip; st->stash_bits = 32 - skip; st->word++; st->next_w = st->load_be32(st->word);
+    st->start_bit = start_byte * 8; st->fetched = 0;
+    // initial window: 9 bits (9.3.2.5) + 16 look-ahead bits
+    uint64_t acc = 0; int have = 0;
+    while (have < 25) {
+      if (st->stash_bits == 0) { st->stash = st->next_w; st->stash_bits = 32; st->word++; st->next_w = st->load_be32(st->word); }
+      const int t = st->stash_bits < 25 - have ? st->stash_bits : 25 - have;
+      acc = (acc << t) | (st->stash >> (32 - t)); st->stash = t < 32 ? st->stash << t : 0; st->stash_bits -= t; have += t;
+    }
+    st->fetched = 25;
+    val = (uint32_t)acc;                                  // = offset << 16 | look-ahead
+    bits = 16; range = 510;
+  }
+  B200_HD inline uint64_t bit_position() const { return (uint64_t)st->start_bit + st->fetched - (uint32_t)bits; }
+  // shift the window left by n (n <= 7), pulling fresh bits from the stream when the look-ahead is exhausted
+  B200_HD inline void shift(int n) {
+    val <<= n; bits -= n;
+    if (bits < 0) { val |= st->take16() << (-bits); bits += 16; }
   }
   B200_HD inline int bin(uint8_t& c) {
     const uint32_t cv = c;
@@ -215,7 +224,7 @@ struct SaoRaw { int8_t type[3], band[3], eo[3]; int8_t off[3][4]; };
 // ---------------------------------------------------------------------------------------------- sub-stream decoder
 struct Decoder {
   const SeqParams* sp; PicBuffers pb; const Substream* ss;
-  Cabac cabac; uint8_t* ctx;                      // CTX_COUNT bytes (caller-provided storage)
+  Cabac cabac; CabacStream stream; uint8_t* ctx;  // ctx: CTX_COUNT bytes (caller-provided storage)
   int is_dqp_coded, dqp_val, qpy_prev_qg, last_cu_qpy, first_qg, cur_qpy, err;
   uint32_t tu_n, coef_n, tu_cap, coef_cap;        // write cursors / limits of the current CTB (or of the picture when dense)
   int cur_ctb_x, cur_ctb_y;
@@ -231,7 +240,7 @@ struct Decoder {
   // -------- SAO (7.3.8.3)
   B200_HDN void parse_sao(int rx, int ry, CtuInfo& ci) {
     const int addr = ry * sp->wctb + rx;
-    for (int c = 0; c < 3; c++) { ci.sao[c].type = 0; ci.sao[c].band_or_class = 0; for (int k = 0; k < 4; k++) ci.sao[c].offset[k] = 0; }
+    B200_NOUNROLL for (int c = 0; c < 3; c++) { ci.sao[c].type = 0; ci.sao[c].band_or_class = 0; B200_NOUNROLL for (int k = 0; k < 4; k++) ci.sao[c].offset[k] = 0; }
     if (!ss->sao_luma && !ss->sao_chroma) return;
     int ml = 0, mu = 0;
     if (rx > 0 && (uint32_t)(addr - 1) >= ss->slice_addr_rs) ml = cabac.bin(ctx[CTX_SAO_MERGE]);
@@ -239,21 +248,21 @@ struct Decoder {
     if (ml || mu) {
       const unsigned long long* o = reinterpret_cast<const unsigned long long*>(pb.ctus[ml ? addr - 1 : addr - sp->wctb].sao);   // 3 x 8 bytes
       unsigned long long* dsto = reinterpret_cast<unsigned long long*>(ci.sao);
-      for (int c = 0; c < 3; c++) dsto[c] = B200_LD_SHARED(o + c);
+      B200_NOUNROLL for (int c = 0; c < 3; c++) dsto[c] = B200_LD_SHARED(o + c);
       return;
     }
-    for (int c = 0; c < (sp->chroma ? 3 : 1); c++) {
+    B200_NOUNROLL for (int c = 0; c < (sp->chroma ? 3 : 1); c++) {
       if ((c == 0 && !ss->sao_luma) || (c > 0 && !ss->sao_chroma)) continue;
       if (c < 2) { int t = 0; if (cabac.bin(ctx[CTX_SAO_TYPE])) t = cabac.bypass() ? 2 : 1; ci.sao[c].type = (uint8_t)t; } else ci.sao[2].type = ci.sao[1].type;
       if (!ci.sao[c].type) continue;
       const int cmax = (1 << (imin(sp->bd, 10) - 5)) - 1;
       int av[4];
-      for (int i = 0; i < 4; i++) { int v = 0; while (v < cmax && cabac.bypass()) v++; av[i] = v; }
+      B200_NOUNROLL for (int i = 0; i < 4; i++) { int v = 0; B200_NOUNROLL while (v < cmax && cabac.bypass()) v++; av[i] = v; }
       const int sc = c == 0 ? sp->sao_scale_luma : sp->sao_scale_chroma;
       if (ci.sao[c].type == 1) {
-        for (int i = 0; i < 4; i++) if (av[i] && cabac.bypass()) av[i] = -av[i];
+        B200_NOUNROLL for (int i = 0; i < 4; i++) if (av[i] && cabac.bypass()) av[i] = -av[i];
         ci.sao[c].band_or_class = (uint8_t)cabac.bypass_bits(5);
-        for (int i = 0; i < 4; i++) ci.sao[c].offset[i] = (int8_t)clip3(-128, 127, av[i] * (1 << sc));
+        B200_NOUNROLL for (int i = 0; i < 4; i++) ci.sao[c].offset[i] = (int8_t)clip3(-128, 127, av[i] * (1 << sc));
       } else {
         if (c < 2) ci.sao[c].band_or_class = (uint8_t)cabac.bypass_bits(2); else ci.sao[2].band_or_class = ci.sao[1].band_or_class;
         ci.sao[c].offset[0] = (int8_t)clip3(-128, 127, av[0] << sc); ci.sao[c].offset[1] = (int8_t)clip3(-128, 127, av[1] << sc);
@@ -286,8 +295,8 @@ struct Decoder {
     int off, shift;
     if (c == 0) { off = 3 * (log2n - 2) + ((log2n - 1) >> 2); shift = (log2n + 1) >> 2; } else { off = 15; shift = log2n - 2; }
     int lx = 0, ly = 0;
-    while (lx < cmax && cb_.bin(cx[CTX_LAST_X + off + (lx >> shift)])) lx++;
-    while (ly < cmax && cb_.bin(cx[CTX_LAST_Y + off + (ly >> shift)])) ly++;
+    B200_NOUNROLL while (lx < cmax && cb_.bin(cx[CTX_LAST_X + off + (lx >> shift)])) lx++;
+    B200_NOUNROLL while (ly < cmax && cb_.bin(cx[CTX_LAST_Y + off + (ly >> shift)])) ly++;
     if (lx > 3) { const int nb = (lx >> 1) - 1; lx = (1 << nb) * (2 + (lx & 1)) + (int)cb_.bypass_bits(nb); }
     if (ly > 3) { const int nb = (ly >> 1) - 1; ly = (1 << nb) * (2 + (ly & 1)) + (int)cb_.bypass_bits(nb); }
     int scan = 0;
@@ -298,12 +307,12 @@ struct Decoder {
     const uint8_t *sbx = B200_T(kScanX)[l2sb][scan], *sby = B200_T(kScanY)[l2sb][scan], *px = B200_T(kScanX)[2][scan], *py = B200_T(kScanY)[2][scan];
     int last_sb = 0, last_pos = 0;
     { const int xs = lx >> 2, ys = ly >> 2, xp = lx & 3, yp = ly & 3, nsb = 1 << (2 * l2sb);
-      for (int i = 0; i < nsb; i++) if (sbx[i] == xs && sby[i] == ys) { last_sb = i; break; }
-      for (int k = 0; k < 16; k++) if (px[k] == xp && py[k] == yp) { last_pos = k; break; } }
+      B200_NOUNROLL for (int i = 0; i < nsb; i++) if (sbx[i] == xs && sby[i] == ys) { last_sb = i; break; }
+      B200_NOUNROLL for (int k = 0; k < 16; k++) if (px[k] == xp && py[k] == yp) { last_pos = k; break; } }
     uint64_t csbf = 0;                                  // coded_sub_block_flag, bit (ys * 8 + xs)
     int carry = 1, count = 0; bool first_done = false;
     const int nsbw = 1 << l2sb;
-    for (int i = last_sb; i >= 0; i--) {
+    B200_NOUNROLL for (int i = last_sb; i >= 0; i--) {
       const int xs = sbx[i], ys = sby[i];
       const int right = (xs + 1 < nsbw) ? (int)((csbf >> (ys * 8 + xs + 1)) & 1) : 0;
       const int below = (ys + 1 < nsbw) ? (int)((csbf >> ((ys + 1) * 8 + xs)) & 1) : 0;
@@ -315,7 +324,7 @@ struct Decoder {
       unsigned sig = 0;
       const int start = i == last_sb ? last_pos - 1 : 15;
       if (i == last_sb) sig |= 1u << last_pos;
-      for (int k = start; k >= 0; k--) {
+      B200_NOUNROLL for (int k = start; k >= 0; k--) {
         if (k > 0 || !infer_dc) {
           const int xc = (xs << 2) + px[k], yc = (ys << 2) + py[k];
           int sc;
@@ -339,7 +348,7 @@ struct Decoder {
       if (first_done && carry == 0) ctx_set++;
       first_done = true;
       int last_sig = -1, first_sig = 16;
-      for (int k = 15; k >= 0; k--) if ((sig >> k) & 1) {
+      B200_NOUNROLL for (int k = 15; k >= 0; k--) if ((sig >> k) & 1) {
         if (ng1 < 8) {
           const int g = cb_.bin(cx[CTX_GT1 + ctx_set * 4 + imin(3, g1ctx) + (c ? 16 : 0)]);
           ng1++;
@@ -352,14 +361,14 @@ struct Decoder {
       const bool hidden = sign_hiding && (last_sig - first_sig > 3);
       if (last_g1 >= 0) g2 = cb_.bin(cx[CTX_GT2 + ctx_set + (c ? 4 : 0)]);
       int nsign = 0;
-      for (int k = 15; k >= 0; k--) if (((sig >> k) & 1) && (!hidden || k != first_sig)) nsign++;
+      B200_NOUNROLL for (int k = 15; k >= 0; k--) if (((sig >> k) & 1) && (!hidden || k != first_sig)) nsign++;
       const unsigned signs = cb_.bypass_bits(nsign);
       int nsig = 0, sum = 0, rice = 0, sidx = nsign;
-      for (int k = 15; k >= 0; k--) if ((sig >> k) & 1) {
+      B200_NOUNROLL for (int k = 15; k >= 0; k--) if ((sig >> k) & 1) {
         const int base = 1 + (int)((g1 >> k) & 1) + (k == last_g1 ? g2 : 0);
         int a = base;
         if (base == ((nsig < 8) ? ((k == last_g1) ? 3 : 2) : 1)) {
-          int pre = 0; while (pre < 32 && cb_.bypass()) pre++;
+          int pre = 0; B200_NOUNROLL while (pre < 32 && cb_.bypass()) pre++;
           const int rem = pre <= 3 ? (pre << rice) + (int)cb_.bypass_bits(rice) : (((1 << (pre - 3)) + 3 - 1) << rice) + (int)cb_.bypass_bits(pre - 3 + rice);
           a = base + rem;
           if (a > 3 * (1 << rice)) rice = imin(rice + 1, 4);
@@ -388,7 +397,7 @@ struct Decoder {
       if ((x0 & 7) == 0 && x0 > 0 && (avail(x0 - 1, y0) || (sl.lf_across_slices && x0 - 1 >= 0))) left = 1;
       if ((y0 & 7) == 0 && y0 > 0 && (avail(x0, y0 - 1) || sl.lf_across_slices)) top = 2;
     }
-    for (int y = 0; y < n8; y++) for (int x = 0; x < n8; x++) {
+    B200_NOUNROLL for (int y = 0; y < n8; y++) B200_NOUNROLL for (int x = 0; x < n8; x++) {
       const int i = (by + y) * sp->w8 + bx + x;
       pb.qp8[i] = (int8_t)cur_qpy;
       if (log2n >= 3) pb.edge8[i] = (uint8_t)((x == 0 ? left : 0) | (y == 0 ? top : 0));
@@ -400,8 +409,8 @@ struct Decoder {
     const int cbf_c = sp->chroma ? (log2n > 2 ? (cbf_cb | cbf_cr) : (pcb | pcr)) : 0;
     if ((cbf_l || cbf_c) && sp->cu_qp_delta && !is_dqp_coded) {
       int v = 0;
-      while (v < 5 && cabac.bin(ctx[CTX_QP_DELTA + (v ? 1 : 0)])) v++;
-      if (v == 5) { int k = 0; while (k < 16 && cabac.bypass()) { v += 1 << k; k++; } v += (int)cabac.bypass_bits(k); }
+      B200_NOUNROLL while (v < 5 && cabac.bin(ctx[CTX_QP_DELTA + (v ? 1 : 0)])) v++;
+      if (v == 5) { int k = 0; B200_NOUNROLL while (k < 16 && cabac.bypass()) { v += 1 << k; k++; } v += (int)cabac.bypass_bits(k); }
       if (v && cabac.bypass()) v = -v;
       is_dqp_coded = 1; dqp_val = v;
       derive_qpy(cu.x0, cu.y0);
@@ -440,7 +449,7 @@ struct Decoder {
     }
     if (split) {
       const int h = 1 << (log2n - 1);
-      for (int k = 0; k < 4; k++) transform_tree(cu, x0 + (k & 1) * h, y0 + (k >> 1) * h, log2n - 1, depth + 1, k, cb, cr, max_depth);
+      B200_NOUNROLL for (int k = 0; k < 4; k++) transform_tree(cu, x0 + (k & 1) * h, y0 + (k >> 1) * h, log2n - 1, depth + 1, k, cb, cr, max_depth);
     } else {
       const int cl = cabac.bin(ctx[CTX_CBF_LUMA + (depth == 0 ? 1 : 0)]);
       if (log2n > 2) transform_unit(cu, x0, y0, log2n, blk, cl, cb, cr, 0, 0);
@@ -476,22 +485,22 @@ struct Decoder {
     if (cu.nxn && log2cb == 3 && sp->log2_min_tb > 2) { err = SYN_E_BITSTREAM; return; }
     const int np = cu.nxn ? 4 : 1, pbs = cu.nxn ? n / 2 : n;
     int prev[4], mi[4] = {0, 0, 0, 0}, rem[4] = {0, 0, 0, 0};
-    for (int i = 0; i < np; i++) prev[i] = cabac.bin(ctx[CTX_PREV_INTRA]);
-    for (int i = 0; i < np; i++) { if (prev[i]) { mi[i] = cabac.bypass(); if (mi[i]) mi[i] += cabac.bypass(); } else rem[i] = (int)cabac.bypass_bits(5); }
-    for (int i = 0; i < np; i++) {
+    B200_NOUNROLL for (int i = 0; i < np; i++) prev[i] = cabac.bin(ctx[CTX_PREV_INTRA]);
+    B200_NOUNROLL for (int i = 0; i < np; i++) { if (prev[i]) { mi[i] = cabac.bypass(); if (mi[i]) mi[i] += cabac.bypass(); } else rem[i] = (int)cabac.bypass_bits(5); }
+    B200_NOUNROLL for (int i = 0; i < np; i++) {
       const int px = x0 + (i & 1) * pbs, py = y0 + (i >> 1) * pbs;
       const int m = luma_mode(px, py, prev[i], mi[i], rem[i]);
       cu.lmode[i] = m;
-      for (int yy = 0; yy < pbs; yy += 4) for (int xx = 0; xx < pbs; xx += 4) pb.ipm4[((py + yy) >> 2) * sp->w4 + ((px + xx) >> 2)] = (uint8_t)m;
+      B200_NOUNROLL for (int yy = 0; yy < pbs; yy += 4) B200_NOUNROLL for (int xx = 0; xx < pbs; xx += 4) pb.ipm4[((py + yy) >> 2) * sp->w4 + ((px + xx) >> 2)] = (uint8_t)m;
     }
     if (sp->chroma) {
       int v = 4; if (cabac.bin(ctx[CTX_CHROMA_PRED])) v = (int)cabac.bypass_bits(2);
       if (v == 4) cu.cmode = cu.lmode[0]; else { cu.cmode = B200_T(kChromaTab)[v]; if (cu.cmode == cu.lmode[0]) cu.cmode = 34; }
     }
-    for (int yy = 0; yy < n; yy += 8) for (int xx = 0; xx < n; xx += 8) pb.cd8[((y0 + yy) >> 3) * sp->w8 + ((x0 + xx) >> 3)] = (uint8_t)depth;
+    B200_NOUNROLL for (int yy = 0; yy < n; yy += 8) B200_NOUNROLL for (int xx = 0; xx < n; xx += 8) pb.cd8[((y0 + yy) >> 3) * sp->w8 + ((x0 + xx) >> 3)] = (uint8_t)depth;
     if (!sp->cu_qp_delta) cur_qpy = ss->slice_qp; else derive_qpy(x0, y0);
     transform_tree(cu, x0, y0, log2cb, 0, 0, 0, 0, sp->max_th_depth_intra + cu.nxn);
-    for (int yy = 0; yy < n; yy += 8) for (int xx = 0; xx < n; xx += 8) pb.qp8[((y0 + yy) >> 3) * sp->w8 + ((x0 + xx) >> 3)] = (int8_t)cur_qpy;
+    B200_NOUNROLL for (int yy = 0; yy < n; yy += 8) B200_NOUNROLL for (int xx = 0; xx < n; xx += 8) pb.qp8[((y0 + yy) >> 3) * sp->w8 + ((x0 + xx) >> 3)] = (int8_t)cur_qpy;
     last_cu_qpy = cur_qpy;
   }
 
@@ -512,7 +521,7 @@ struct Decoder {
     }
     if (split) {
       const int h = n >> 1;
-      for (int k = 0; k < 4; k++) { const int x1 = x0 + (k & 1) * h, y1 = y0 + (k >> 1) * h; if (x1 < sp->W && y1 < sp->H) coding_quadtree(x1, y1, log2cb - 1, depth + 1); }
+      B200_NOUNROLL for (int k = 0; k < 4; k++) { const int x1 = x0 + (k & 1) * h, y1 = y0 + (k >> 1) * h; if (x1 < sp->W && y1 < sp->H) coding_quadtree(x1, y1, log2cb - 1, depth + 1); }
     } else coding_unit(x0, y0, log2cb, depth);
   }
 
@@ -525,10 +534,10 @@ struct Decoder {
     if (!sp->dense) { tu_n = (uint32_t)addr * (uint32_t)sp->tu_slots; tu_cap = tu_n + (uint32_t)sp->tu_slots; coef_n = (uint32_t)addr * (uint32_t)sp->coef_slots; coef_cap = coef_n + (uint32_t)sp->coef_slots; }
     const uint32_t t0 = tu_n;
     if (sp->sao_enabled) parse_sao(rx, ry, ci);
-    else for (int c = 0; c < 3; c++) { ci.sao[c].type = 0; ci.sao[c].band_or_class = 0; for (int k = 0; k < 4; k++) ci.sao[c].offset[k] = 0; }
+    else for (int c = 0; c < 3; c++) { ci.sao[c].type = 0; ci.sao[c].band_or_class = 0; B200_NOUNROLL for (int k = 0; k < 4; k++) ci.sao[c].offset[k] = 0; }
     // 4x4 luma transform units only OR their edge bits: clear this CTB's flags first
     { const int b0x = rx << (sp->log2ctb - 3), b0y = ry << (sp->log2ctb - 3), nb = 1 << (sp->log2ctb - 3);
-      for (int y = 0; y < nb && b0y + y < sp->h8; y++) for (int x = 0; x < nb && b0x + x < sp->w8; x++) pb.edge8[(b0y + y) * sp->w8 + b0x + x] = 0; }
+      B200_NOUNROLL for (int y = 0; y < nb && b0y + y < sp->h8; y++) B200_NOUNROLL for (int x = 0; x < nb && b0x + x < sp->w8; x++) pb.edge8[(b0y + y) * sp->w8 + b0x + x] = 0; }
     coding_quadtree(rx << sp->log2ctb, ry << sp->log2ctb, sp->log2ctb, 0);
     ci.tu_start = t0; ci.tu_count = (uint16_t)(tu_n - t0);
   }
@@ -551,7 +560,7 @@ B200_HD int run_substream(const SeqParams& sp, const PicBuffers& pb, const Subst
   if (ss.prev >= 0) {                                         // dependent slice segment: continue from the previous segment's end state
     sync.wait_substream(ss.prev);
     const uint8_t* st = pb.end_state + (size_t)ss.prev * CTX_STRIDE;
-    for (int i = 0; i < CTX_COUNT; i++) ctx[i] = B200_LD_SHARED(st + i);
+    B200_NOUNROLL for (int i = 0; i < CTX_COUNT; i++) ctx[i] = B200_LD_SHARED(st + i);
     d.last_cu_qpy = (int)(int8_t)B200_LD_SHARED(st + CTX_COUNT); d.first_qg = 0;
   }
   if (ss.init_contexts) init_contexts(ctx, ss.slice_qp);
@@ -561,12 +570,12 @@ B200_HD int run_substream(const SeqParams& sp, const PicBuffers& pb, const Subst
     const int xn = 1 << sp.log2ctb, yn = (ry0 - 1) << sp.log2ctb;
     bool tr = ry0 > 0 && xn < sp.W && pb.ctu_slice[(ry0 - 1) * sp.wctb + 1] == (uint16_t)ss.slice_idx;
     (void)yn;
-    if (tr) { sync.wait_row(ry0 - 1, 2); const uint8_t* st = pb.wpp_ctx + (size_t)(ry0 - 1) * CTX_STRIDE; for (int i = 0; i < CTX_COUNT; i++) ctx[i] = B200_LD_SHARED(st + i); }
+    if (tr) { sync.wait_row(ry0 - 1, 2); const uint8_t* st = pb.wpp_ctx + (size_t)(ry0 - 1) * CTX_STRIDE; B200_NOUNROLL for (int i = 0; i < CTX_COUNT; i++) ctx[i] = B200_LD_SHARED(st + i); }
     else if (ss.prev < 0) init_contexts(ctx, ss.slice_qp);
     d.first_qg = 1;
   }
-  d.cabac.start(pb.rbsp, pb.rbsp_size, ss.byte_begin);
-  for (uint32_t a = ss.ctb_begin; a < ss.ctb_end; a++) {
+  d.cabac.start(&d.stream, pb.rbsp, pb.rbsp_size, ss.byte_begin);
+  B200_NOUNROLL for (uint32_t a = ss.ctb_begin; a < ss.ctb_end; a++) {
     const int rx = (int)(a % (uint32_t)sp.wctb), ry = (int)(a / (uint32_t)sp.wctb);
     if (ry > 0) sync.wait_row(ry - 1, imin(rx + 2, sp.wctb));     // split_cu_flag context / SAO merge-up read the row above
     if (sp.wpp && rx == 0 && a != ss.ctb_begin) {
@@ -576,16 +585,16 @@ B200_HD int run_substream(const SeqParams& sp, const PicBuffers& pb, const Subst
     if (!sp.wpp && rx == 0 && a != ss.ctb_begin) { /* QG state simply continues */ }
     d.decode_ctb((int)a);
     if (d.err) break;
-    if (sp.wpp && rx == 1) { uint8_t* st = pb.wpp_ctx + (size_t)ry * CTX_STRIDE; for (int i = 0; i < CTX_COUNT; i++) st[i] = ctx[i]; }
+    if (sp.wpp && rx == 1) { uint8_t* st = pb.wpp_ctx + (size_t)ry * CTX_STRIDE; B200_NOUNROLL for (int i = 0; i < CTX_COUNT; i++) st[i] = ctx[i]; }
     const int end = d.cabac.terminate();                          // end_of_slice_segment_flag
     const bool last = a + 1 == ss.ctb_end;
     if (end != ((last && ss.last_of_segment) ? 1 : 0)) { d.err = SYN_E_BITSTREAM; break; }
     if (last && !ss.last_of_segment) { if (!d.cabac.terminate()) { d.err = SYN_E_BITSTREAM; break; } }   // end_of_subset_one_bit
     sync.publish_row(ry, rx + 1);
-    if ((uint64_t)d.cabac.word * 4 > (uint64_t)pb.rbsp_size + 64) { d.err = SYN_E_BITSTREAM; break; }
+    if ((uint64_t)d.stream.word * 4 > (uint64_t)pb.rbsp_size + 64) { d.err = SYN_E_BITSTREAM; break; }
   }
   // end state for a dependent continuation + dense cursors
-  { uint8_t* st = pb.end_state + (size_t)index * CTX_STRIDE; for (int i = 0; i < CTX_COUNT; i++) st[i] = ctx[i]; st[CTX_COUNT] = (uint8_t)(int8_t)d.last_cu_qpy; }
+  { uint8_t* st = pb.end_state + (size_t)index * CTX_STRIDE; B200_NOUNROLL for (int i = 0; i < CTX_COUNT; i++) st[i] = ctx[i]; st[CTX_COUNT] = (uint8_t)(int8_t)d.last_cu_qpy; }
   if (sp.dense) { sync.dense_tu = d.tu_n; sync.dense_coef = d.coef_n; }
   sync.end_bit_position = d.cabac.bit_position();
   sync.finish_substream(index, d.err);
