@@ -49,13 +49,14 @@ struct DevSync {
   uint32_t dense_tu, dense_coef, dense_tu_cap, dense_coef_cap;   // unused on the device (fixed slots)
   uint64_t end_bit_position;
   __device__ void wait_row(int row, int need) {
-    unsigned spins = 0;
-    while (e_ld_acquire(progress + row) < (unsigned)need) { __nanosleep(200); if (++spins > (1u << 24)) { atomicExch(error_flag, 3u); break; } }
+    // a CTB takes ~0.5 ms; back off to microseconds so thousands of waiting warps do not flood L2 with polls
+    unsigned spins = 0, ns = 500;
+    while (e_ld_acquire(progress + row) < (unsigned)need) { __nanosleep(ns); if (ns < 4000) ns <<= 1; if (++spins > (1u << 21)) { atomicExch(error_flag, 3u); break; } }
   }
   __device__ void publish_row(int row, int done) { e_st_release(progress + row, (unsigned)done); }
   __device__ void wait_substream(int idx) {
-    unsigned spins = 0;
-    while (e_ld_acquire(sub_done + idx) == 0u) { __nanosleep(200); if (++spins > (1u << 24)) { atomicExch(error_flag, 3u); break; } }
+    unsigned spins = 0, ns = 500;
+    while (e_ld_acquire(sub_done + idx) == 0u) { __nanosleep(ns); if (ns < 4000) ns <<= 1; if (++spins > (1u << 21)) { atomicExch(error_flag, 3u); break; } }
   }
   __device__ void finish_substream(int idx, int err) {
     e_st_release(sub_done + idx, 1u);

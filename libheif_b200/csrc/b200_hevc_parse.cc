@@ -364,7 +364,8 @@ class HeaderParser {
     if (segs.empty() || segs[0].addr != 0) return set_error(B200_E_BITSTREAM, "first slice segment missing");
     for (int a = 0; a < total; a++) if (P.ctu_slice[(size_t)a] == 0xffff) return set_error(B200_E_BITSTREAM, "picture incomplete (missing slice segments)");
     P.desc.nslices = (int)P.slices.size();
-    for (int k = 0; k < 16; k++) P.rbsp.push_back(0);
+    while (P.rbsp.size() & 3) P.rbsp.push_back(0);
+    for (int k = 0; k < 16; k++) P.rbsp.push_back(0);              // zero tail the CABAC refill may read (even size)
     return B200_OK;
   }
 };

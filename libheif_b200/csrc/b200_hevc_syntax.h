@@ -108,62 +108,42 @@ struct PicBuffers {              // per-picture arrays (host memory on the host 
 // the host front-end cross-checks against the entry points of every WPP stream it parses.
 B200_TABLE(uint8_t, kNextState, [256], {2,3,4,5,6,7,8,9,10,11,12,13,14,15,16,17,18,19,20,21,22,23,24,25,26,27,28,29,30,31,32,33,34,35,36,37,38,39,40,41,42,43,44,45,46,47,48,49,50,51,52,53,54,55,56,57,58,59,60,61,62,63,64,65,66,67,68,69,70,71,72,73,74,75,76,77,78,79,80,81,82,83,84,85,86,87,88,89,90,91,92,93,94,95,96,97,98,99,100,101,102,103,104,105,106,107,108,109,110,111,112,113,114,115,116,117,118,119,120,121,122,123,124,125,124,125,126,127,1,0,0,1,2,3,4,5,4,5,8,9,8,9,10,11,12,13,14,15,16,17,18,19,18,19,22,23,22,23,24,25,26,27,26,27,30,31,30,31,32,33,32,33,36,37,36,37,38,39,38,39,42,43,42,43,44,45,44,45,46,47,48,49,48,49,50,51,52,53,52,53,54,55,54,55,56,57,58,59,58,59,60,61,60,61,60,61,62,63,64,65,64,65,66,67,66,67,66,67,68,69,68,69,70,71,70,71,70,71,72,73,72,73,72,73,74,75,74,75,74,75,76,77,76,77,126,127})   // [ctx byte | lps << 7] -> next ctx byte ((pStateIdx << 1) | valMps)
 
-// Cold half: stream position and the word stash (touched once per 16 consumed bits; lives in memory, out of line).
-struct CabacStream {
-  const uint8_t* d; uint32_t nwords; uint32_t word;   // next 32-bit word to fetch
-  uint32_t next_w;                                    // word `word`, prefetched one step ahead (keeps the L2 latency off the chain)
-  uint32_t stash; int stash_bits;                     // not-yet-used bits of the last fetched word
-  uint32_t fetched;                                   // stream bits moved into the decoder so far
-  uint32_t start_bit;
-  B200_HD inline uint32_t load_be32(uint32_t w) const {
-    if (w >= nwords) return 0u;
-#ifdef __CUDA_ARCH__
-    return __byte_perm(__ldg(reinterpret_cast<const uint32_t*>(d) + w), 0, 0x0123);
-#else
-    const uint8_t* p = d + (size_t)w * 4;
-    return ((uint32_t)p[0] << 24) | ((uint32_t)p[1] << 16) | ((uint32_t)p[2] << 8) | p[3];
-#endif
-  }
-  B200_HDN uint32_t take16() {                          // next 16 stream bits, stash alignment agnostic
-    fetched += 16;
-    if (stash_bits >= 16) { const uint32_t v = stash >> 16; stash <<= 16; stash_bits -= 16; return v; }
-    uint32_t v = stash_bits ? (stash >> (32 - stash_bits)) : 0u; const int have = stash_bits;
-    stash = next_w; stash_bits = 32; word++; next_w = load_be32(word);
-    const int need = 16 - have;
-    v = (v << need) | (stash >> (32 - need)); stash <<= need; stash_bits -= need;
-    return v;
-  }
-};
+// The sub-stream's bytes (cold: touched once per 16 consumed bits).
+struct CabacStream { const uint8_t* d; uint32_t size; };
 
-// Hot half: three scalars that stay in registers inside the residual decoder.
+// Arithmetic decoder (9.3.4.3) in scaled-window form: val = offset << 16 | look-ahead bits; five scalars that stay in
+// registers inside the residual decoder.  The stream is consumed 16 bits at a time and the next 16 bits are always
+// already loaded (next16), so the load latency never sits on the bin-to-bin dependency chain.
 struct Cabac {
   uint32_t val, range; int bits;                      // bits: valid look-ahead bits in the low half of val
-  CabacStream* st;
-  B200_HD inline void start(CabacStream* stream, const uint8_t* data, uint32_t size, uint32_t start_byte) {
-    st = stream;
-    st->d = data; st->nwords = size >> 2; st->word = start_byte >> 2;
-    st->next_w = st->load_be32(st->word);
-    const int skip = (int)(start_byte & 3) * 8;
-    st->stash = st->next_w << skip; st->stash_bits = 32 - skip; st->word++; st->next_w = st->load_be32(st->word);
-    st->start_bit = start_byte * 8; st->fetched = 0;
-    // initial window: 9 bits (9.3.2.5) + 16 look-ahead bits
-    uint64_t acc = 0; int have = 0;
-    while (have < 25) {
-      if (st->stash_bits == 0) { st->stash = st->next_w; st->stash_bits = 32; st->word++; st->next_w = st->load_be32(st->word); }
-      const int t = st->stash_bits < 25 - have ? st->stash_bits : 25 - have;
-      acc = (acc << t) | (st->stash >> (32 - t)); st->stash = t < 32 ? st->stash << t : 0; st->stash_bits -= t; have += t;
+  uint32_t pos, next16;                               // byte offset of the 16 bits that follow next16's
+  // big-endian 16 bits at EVEN byte offset p; offsets past the end read the zero padding the buffer ends in (>= 2 bytes, size even)
+  B200_HD static inline uint32_t fetch16(const CabacStream& st, uint32_t p) {
+    const uint32_t q = p < st.size - 2 ? p : st.size - 2;
+#ifdef __CUDA_ARCH__
+    return __byte_perm((uint32_t)__ldg(reinterpret_cast<const unsigned short*>(st.d + q)), 0, 0x4401);
+#else
+    return ((uint32_t)st.d[q] << 8) | st.d[q + 1];
+#endif
+  }
+  B200_HD inline void start(const CabacStream& st, uint32_t start_byte) {
+    // initial window: the 9 bits of 9.3.2.5 + look-ahead up to the next even byte offset (2 or 3 bytes), so that every
+    // later refill is one aligned 16-bit load
+    if (start_byte & 1) {
+      const uint32_t b0 = fetch16(st, start_byte - 1) & 0xffu, w1 = fetch16(st, start_byte + 1);
+      val = ((b0 << 16) | w1) << 1; bits = 15; pos = start_byte + 3;
+    } else {
+      val = fetch16(st, start_byte) << 9; bits = 7; pos = start_byte + 2;
     }
-    st->fetched = 25;
-    val = (uint32_t)acc;                                  // = offset << 16 | look-ahead
-    bits = 16; range = 510;
+    range = 510; next16 = fetch16(st, pos);
   }
-  B200_HD inline uint64_t bit_position() const { return (uint64_t)st->start_bit + st->fetched - (uint32_t)bits; }
-  // shift the window left by n (n <= 7), pulling fresh bits from the stream when the look-ahead is exhausted
-  B200_HD inline void shift(int n) {
+  B200_HD inline uint64_t bit_position() const { return (uint64_t)pos * 8 - (uint32_t)bits; }
+  // shift the window left by n (n <= 7), merging the prefetched 16 bits when the look-ahead is exhausted
+  B200_HD inline void shift(int n, const CabacStream& st) {
     val <<= n; bits -= n;
-    if (bits < 0) { val |= st->take16() << (-bits); bits += 16; }
+    if (bits < 0) { val |= next16 << (-bits); bits += 16; pos += 2; next16 = fetch16(st, pos); }
   }
-  B200_HD inline int bin(uint8_t& c) {
+  B200_HD inline int bin(uint8_t& c, const CabacStream& st) {
     const uint32_t cv = c;
     const uint32_t rlps = (B200_T(kLps4)[cv >> 1] >> (((range >> 6) & 3) * 8)) & 0xff;
     const uint32_t rmps = range - rlps;
@@ -177,32 +157,39 @@ struct Cabac {
     const int n = __builtin_clz(range) - 23;
 #endif
     range <<= n;
-    if (n) shift(n);
+    shift(n, st);
     return (int)((cv & 1) ^ lps);
   }
-  B200_HD inline int bypass() {
-    shift(1);
+  B200_HD inline int bypass(const CabacStream& st) {
+    shift(1, st);
     const uint32_t one = (val >> 16) >= range ? 1u : 0u;
     val -= one ? (range << 16) : 0u;
     return (int)one;
   }
   // k bypass bins at once (9.3.4.3.4 applied k times): offset < range, so (offset << k | bits) / range < 2^k is the bin string
-  B200_HD inline unsigned bypass_bits(int k) {
+  B200_HD inline unsigned bypass_bits(int k, const CabacStream& st) {
     unsigned out = 0;
-    while (k > 0) {
+    B200_NOUNROLL while (k > 0) {
       const int t = k > 7 ? 7 : k;                       // window (9 bits) + t <= 16 bits: stays inside bits 31..16 of val
-      shift(t);
-      const uint32_t w = val >> 16;                      // (offset << t) | t fresh bits
+      shift(t, st);
+      const uint32_t w = val >> 16;                      // (offset << t) | t fresh bits, < 2^16
+#ifdef __CUDA_ARCH__
+      uint32_t q = (uint32_t)__float2int_rz(__fdividef((float)w, (float)range));   // within 1 of the quotient; fixed up exactly below
+      int r = (int)w - (int)(q * range);
+      if (r < 0) { q--; r += (int)range; } else if (r >= (int)range) { q++; r -= (int)range; }
+      val = ((uint32_t)r << 16) | (val & 0xffffu);
+#else
       const uint32_t q = w / range;
       val -= (q * range) << 16;
+#endif
       out = (out << t) | q; k -= t;
     }
     return out;
   }
-  B200_HD inline int terminate() {
+  B200_HD inline int terminate(const CabacStream& st) {
     range -= 2;
     if ((val >> 16) >= range) return 1;
-    if (range < 256) { range <<= 1; shift(1); }
+    if (range < 256) { range <<= 1; shift(1, st); }
     return 0;
   }
 };
@@ -243,8 +230,8 @@ struct Decoder {
     B200_NOUNROLL for (int c = 0; c < 3; c++) { ci.sao[c].type = 0; ci.sao[c].band_or_class = 0; B200_NOUNROLL for (int k = 0; k < 4; k++) ci.sao[c].offset[k] = 0; }
     if (!ss->sao_luma && !ss->sao_chroma) return;
     int ml = 0, mu = 0;
-    if (rx > 0 && (uint32_t)(addr - 1) >= ss->slice_addr_rs) ml = cabac.bin(ctx[CTX_SAO_MERGE]);
-    if (ry > 0 && !ml && addr - sp->wctb >= (int)ss->slice_addr_rs) mu = cabac.bin(ctx[CTX_SAO_MERGE]);
+    if (rx > 0 && (uint32_t)(addr - 1) >= ss->slice_addr_rs) ml = cabac.bin(ctx[CTX_SAO_MERGE], stream);
+    if (ry > 0 && !ml && addr - sp->wctb >= (int)ss->slice_addr_rs) mu = cabac.bin(ctx[CTX_SAO_MERGE], stream);
     if (ml || mu) {
       const unsigned long long* o = reinterpret_cast<const unsigned long long*>(pb.ctus[ml ? addr - 1 : addr - sp->wctb].sao);   // 3 x 8 bytes
       unsigned long long* dsto = reinterpret_cast<unsigned long long*>(ci.sao);
@@ -253,18 +240,18 @@ struct Decoder {
     }
     B200_NOUNROLL for (int c = 0; c < (sp->chroma ? 3 : 1); c++) {
       if ((c == 0 && !ss->sao_luma) || (c > 0 && !ss->sao_chroma)) continue;
-      if (c < 2) { int t = 0; if (cabac.bin(ctx[CTX_SAO_TYPE])) t = cabac.bypass() ? 2 : 1; ci.sao[c].type = (uint8_t)t; } else ci.sao[2].type = ci.sao[1].type;
+      if (c < 2) { int t = 0; if (cabac.bin(ctx[CTX_SAO_TYPE], stream)) t = cabac.bypass(stream) ? 2 : 1; ci.sao[c].type = (uint8_t)t; } else ci.sao[2].type = ci.sao[1].type;
       if (!ci.sao[c].type) continue;
       const int cmax = (1 << (imin(sp->bd, 10) - 5)) - 1;
       int av[4];
-      B200_NOUNROLL for (int i = 0; i < 4; i++) { int v = 0; B200_NOUNROLL while (v < cmax && cabac.bypass()) v++; av[i] = v; }
+      B200_NOUNROLL for (int i = 0; i < 4; i++) { int v = 0; B200_NOUNROLL while (v < cmax && cabac.bypass(stream)) v++; av[i] = v; }
       const int sc = c == 0 ? sp->sao_scale_luma : sp->sao_scale_chroma;
       if (ci.sao[c].type == 1) {
-        B200_NOUNROLL for (int i = 0; i < 4; i++) if (av[i] && cabac.bypass()) av[i] = -av[i];
-        ci.sao[c].band_or_class = (uint8_t)cabac.bypass_bits(5);
+        B200_NOUNROLL for (int i = 0; i < 4; i++) if (av[i] && cabac.bypass(stream)) av[i] = -av[i];
+        ci.sao[c].band_or_class = (uint8_t)cabac.bypass_bits(5, stream);
         B200_NOUNROLL for (int i = 0; i < 4; i++) ci.sao[c].offset[i] = (int8_t)clip3(-128, 127, av[i] * (1 << sc));
       } else {
-        if (c < 2) ci.sao[c].band_or_class = (uint8_t)cabac.bypass_bits(2); else ci.sao[2].band_or_class = ci.sao[1].band_or_class;
+        if (c < 2) ci.sao[c].band_or_class = (uint8_t)cabac.bypass_bits(2, stream); else ci.sao[2].band_or_class = ci.sao[1].band_or_class;
         ci.sao[c].offset[0] = (int8_t)clip3(-128, 127, av[0] << sc); ci.sao[c].offset[1] = (int8_t)clip3(-128, 127, av[1] << sc);
         ci.sao[c].offset[2] = (int8_t)clip3(-128, 127, -(av[2] << sc)); ci.sao[c].offset[3] = (int8_t)clip3(-128, 127, -(av[3] << sc));
       }
@@ -290,15 +277,15 @@ struct Decoder {
     const int sign_hiding = sp->sign_hiding;
     CoefEntry* const coef_out = pb.coefs; uint32_t cn = coef_n; const uint32_t ccap = coef_cap;
     tskip = 0;
-    if (sp->transform_skip && log2n == 2) tskip = cb_.bin(cx[CTX_TSKIP + (c ? 1 : 0)]);
+    if (sp->transform_skip && log2n == 2) tskip = cb_.bin(cx[CTX_TSKIP + (c ? 1 : 0)], stream);
     const int cmax = (log2n << 1) - 1;
     int off, shift;
     if (c == 0) { off = 3 * (log2n - 2) + ((log2n - 1) >> 2); shift = (log2n + 1) >> 2; } else { off = 15; shift = log2n - 2; }
     int lx = 0, ly = 0;
-    B200_NOUNROLL while (lx < cmax && cb_.bin(cx[CTX_LAST_X + off + (lx >> shift)])) lx++;
-    B200_NOUNROLL while (ly < cmax && cb_.bin(cx[CTX_LAST_Y + off + (ly >> shift)])) ly++;
-    if (lx > 3) { const int nb = (lx >> 1) - 1; lx = (1 << nb) * (2 + (lx & 1)) + (int)cb_.bypass_bits(nb); }
-    if (ly > 3) { const int nb = (ly >> 1) - 1; ly = (1 << nb) * (2 + (ly & 1)) + (int)cb_.bypass_bits(nb); }
+    B200_NOUNROLL while (lx < cmax && cb_.bin(cx[CTX_LAST_X + off + (lx >> shift)], stream)) lx++;
+    B200_NOUNROLL while (ly < cmax && cb_.bin(cx[CTX_LAST_Y + off + (ly >> shift)], stream)) ly++;
+    if (lx > 3) { const int nb = (lx >> 1) - 1; lx = (1 << nb) * (2 + (lx & 1)) + (int)cb_.bypass_bits(nb, stream); }
+    if (ly > 3) { const int nb = (ly >> 1) - 1; ly = (1 << nb) * (2 + (ly & 1)) + (int)cb_.bypass_bits(nb, stream); }
     int scan = 0;
     if (log2n == 2 || (log2n == 3 && c == 0)) { if (mode >= 6 && mode <= 14) scan = 2; else if (mode >= 22 && mode <= 30) scan = 1; }
     if (scan == 2) { const int t = lx; lx = ly; ly = t; }
@@ -317,7 +304,7 @@ struct Decoder {
       const int right = (xs + 1 < nsbw) ? (int)((csbf >> (ys * 8 + xs + 1)) & 1) : 0;
       const int below = (ys + 1 < nsbw) ? (int)((csbf >> ((ys + 1) * 8 + xs)) & 1) : 0;
       int infer_dc = 0, coded;
-      if (i < last_sb && i > 0) { coded = cb_.bin(cx[CTX_CSBF + ((right | below) ? 1 : 0) + (c ? 2 : 0)]); infer_dc = 1; } else coded = 1;
+      if (i < last_sb && i > 0) { coded = cb_.bin(cx[CTX_CSBF + ((right | below) ? 1 : 0) + (c ? 2 : 0)], stream); infer_dc = 1; } else coded = 1;
       if (!coded) continue;
       csbf |= 1ull << (ys * 8 + xs);
       const int prev = right | (below << 1);
@@ -338,7 +325,7 @@ struct Decoder {
             else sc = 2;
             if (c == 0) { if (xs || ys) sc += 3; sc += log2n == 3 ? (scan == 0 ? 9 : 15) : 21; } else sc += log2n == 3 ? 9 : 12;
           }
-          if (cb_.bin(cx[CTX_SIG + (c == 0 ? sc : 27 + sc)])) { sig |= 1u << k; infer_dc = 0; }
+          if (cb_.bin(cx[CTX_SIG + (c == 0 ? sc : 27 + sc)], stream)) { sig |= 1u << k; infer_dc = 0; }
         } else sig |= 1u;
       }
       if (!sig) continue;
@@ -350,7 +337,7 @@ struct Decoder {
       int last_sig = -1, first_sig = 16;
       B200_NOUNROLL for (int k = 15; k >= 0; k--) if ((sig >> k) & 1) {
         if (ng1 < 8) {
-          const int g = cb_.bin(cx[CTX_GT1 + ctx_set * 4 + imin(3, g1ctx) + (c ? 16 : 0)]);
+          const int g = cb_.bin(cx[CTX_GT1 + ctx_set * 4 + imin(3, g1ctx) + (c ? 16 : 0)], stream);
           ng1++;
           if (g) { g1 |= 1u << k; g1ctx = 0; if (last_g1 < 0) last_g1 = k; } else if (g1ctx > 0) g1ctx++;
         }
@@ -359,17 +346,17 @@ struct Decoder {
       }
       carry = g1ctx;
       const bool hidden = sign_hiding && (last_sig - first_sig > 3);
-      if (last_g1 >= 0) g2 = cb_.bin(cx[CTX_GT2 + ctx_set + (c ? 4 : 0)]);
+      if (last_g1 >= 0) g2 = cb_.bin(cx[CTX_GT2 + ctx_set + (c ? 4 : 0)], stream);
       int nsign = 0;
       B200_NOUNROLL for (int k = 15; k >= 0; k--) if (((sig >> k) & 1) && (!hidden || k != first_sig)) nsign++;
-      const unsigned signs = cb_.bypass_bits(nsign);
+      const unsigned signs = cb_.bypass_bits(nsign, stream);
       int nsig = 0, sum = 0, rice = 0, sidx = nsign;
       B200_NOUNROLL for (int k = 15; k >= 0; k--) if ((sig >> k) & 1) {
         const int base = 1 + (int)((g1 >> k) & 1) + (k == last_g1 ? g2 : 0);
         int a = base;
         if (base == ((nsig < 8) ? ((k == last_g1) ? 3 : 2) : 1)) {
-          int pre = 0; B200_NOUNROLL while (pre < 32 && cb_.bypass()) pre++;
-          const int rem = pre <= 3 ? (pre << rice) + (int)cb_.bypass_bits(rice) : (((1 << (pre - 3)) + 3 - 1) << rice) + (int)cb_.bypass_bits(pre - 3 + rice);
+          int pre = 0; B200_NOUNROLL while (pre < 32 && cb_.bypass(stream)) pre++;
+          const int rem = pre <= 3 ? (pre << rice) + (int)cb_.bypass_bits(rice, stream) : (((1 << (pre - 3)) + 3 - 1) << rice) + (int)cb_.bypass_bits(pre - 3 + rice, stream);
           a = base + rem;
           if (a > 3 * (1 << rice)) rice = imin(rice + 1, 4);
         }
@@ -409,9 +396,9 @@ struct Decoder {
     const int cbf_c = sp->chroma ? (log2n > 2 ? (cbf_cb | cbf_cr) : (pcb | pcr)) : 0;
     if ((cbf_l || cbf_c) && sp->cu_qp_delta && !is_dqp_coded) {
       int v = 0;
-      B200_NOUNROLL while (v < 5 && cabac.bin(ctx[CTX_QP_DELTA + (v ? 1 : 0)])) v++;
-      if (v == 5) { int k = 0; B200_NOUNROLL while (k < 16 && cabac.bypass()) { v += 1 << k; k++; } v += (int)cabac.bypass_bits(k); }
-      if (v && cabac.bypass()) v = -v;
+      B200_NOUNROLL while (v < 5 && cabac.bin(ctx[CTX_QP_DELTA + (v ? 1 : 0)], stream)) v++;
+      if (v == 5) { int k = 0; B200_NOUNROLL while (k < 16 && cabac.bypass(stream)) { v += 1 << k; k++; } v += (int)cabac.bypass_bits(k, stream); }
+      if (v && cabac.bypass(stream)) v = -v;
       is_dqp_coded = 1; dqp_val = v;
       derive_qpy(cu.x0, cu.y0);
     }
@@ -439,19 +426,19 @@ struct Decoder {
   B200_HDN void transform_tree(const Cu& cu, int x0, int y0, int log2n, int depth, int blk, int pcb, int pcr, int max_depth) {
     if (err) return;
     int split;
-    if (log2n <= sp->log2_max_tb && log2n > sp->log2_min_tb && depth < max_depth && !(cu.nxn && depth == 0)) split = cabac.bin(ctx[CTX_SPLIT_TR + 5 - log2n]);
+    if (log2n <= sp->log2_max_tb && log2n > sp->log2_min_tb && depth < max_depth && !(cu.nxn && depth == 0)) split = cabac.bin(ctx[CTX_SPLIT_TR + 5 - log2n], stream);
     else split = (log2n > sp->log2_max_tb || (cu.nxn && depth == 0)) ? 1 : 0;
     if (split && log2n <= 2) { err = SYN_E_BITSTREAM; return; }
     int cb = 0, cr = 0;
     if (sp->chroma) {
-      if (log2n > 2) { if (depth == 0 || pcb) cb = cabac.bin(ctx[CTX_CBF_CHROMA + depth]); if (depth == 0 || pcr) cr = cabac.bin(ctx[CTX_CBF_CHROMA + depth]); }
+      if (log2n > 2) { if (depth == 0 || pcb) cb = cabac.bin(ctx[CTX_CBF_CHROMA + depth], stream); if (depth == 0 || pcr) cr = cabac.bin(ctx[CTX_CBF_CHROMA + depth], stream); }
       else { cb = pcb; cr = pcr; }
     }
     if (split) {
       const int h = 1 << (log2n - 1);
       B200_NOUNROLL for (int k = 0; k < 4; k++) transform_tree(cu, x0 + (k & 1) * h, y0 + (k >> 1) * h, log2n - 1, depth + 1, k, cb, cr, max_depth);
     } else {
-      const int cl = cabac.bin(ctx[CTX_CBF_LUMA + (depth == 0 ? 1 : 0)]);
+      const int cl = cabac.bin(ctx[CTX_CBF_LUMA + (depth == 0 ? 1 : 0)], stream);
       if (log2n > 2) transform_unit(cu, x0, y0, log2n, blk, cl, cb, cr, 0, 0);
       else transform_unit(cu, x0, y0, log2n, blk, cl, 0, 0, pcb, pcr);
     }
@@ -481,12 +468,12 @@ struct Decoder {
   B200_HDN void coding_unit(int x0, int y0, int log2cb, int depth) {
     Cu cu; cu.x0 = x0; cu.y0 = y0; cu.log2cb = log2cb; cu.nxn = 0; cu.cmode = 0;
     const int n = 1 << log2cb;
-    if (log2cb == sp->log2_min_cb) cu.nxn = !cabac.bin(ctx[CTX_PART_MODE]);
+    if (log2cb == sp->log2_min_cb) cu.nxn = !cabac.bin(ctx[CTX_PART_MODE], stream);
     if (cu.nxn && log2cb == 3 && sp->log2_min_tb > 2) { err = SYN_E_BITSTREAM; return; }
     const int np = cu.nxn ? 4 : 1, pbs = cu.nxn ? n / 2 : n;
     int prev[4], mi[4] = {0, 0, 0, 0}, rem[4] = {0, 0, 0, 0};
-    B200_NOUNROLL for (int i = 0; i < np; i++) prev[i] = cabac.bin(ctx[CTX_PREV_INTRA]);
-    B200_NOUNROLL for (int i = 0; i < np; i++) { if (prev[i]) { mi[i] = cabac.bypass(); if (mi[i]) mi[i] += cabac.bypass(); } else rem[i] = (int)cabac.bypass_bits(5); }
+    B200_NOUNROLL for (int i = 0; i < np; i++) prev[i] = cabac.bin(ctx[CTX_PREV_INTRA], stream);
+    B200_NOUNROLL for (int i = 0; i < np; i++) { if (prev[i]) { mi[i] = cabac.bypass(stream); if (mi[i]) mi[i] += cabac.bypass(stream); } else rem[i] = (int)cabac.bypass_bits(5, stream); }
     B200_NOUNROLL for (int i = 0; i < np; i++) {
       const int px = x0 + (i & 1) * pbs, py = y0 + (i >> 1) * pbs;
       const int m = luma_mode(px, py, prev[i], mi[i], rem[i]);
@@ -494,7 +481,7 @@ struct Decoder {
       B200_NOUNROLL for (int yy = 0; yy < pbs; yy += 4) B200_NOUNROLL for (int xx = 0; xx < pbs; xx += 4) pb.ipm4[((py + yy) >> 2) * sp->w4 + ((px + xx) >> 2)] = (uint8_t)m;
     }
     if (sp->chroma) {
-      int v = 4; if (cabac.bin(ctx[CTX_CHROMA_PRED])) v = (int)cabac.bypass_bits(2);
+      int v = 4; if (cabac.bin(ctx[CTX_CHROMA_PRED], stream)) v = (int)cabac.bypass_bits(2, stream);
       if (v == 4) cu.cmode = cu.lmode[0]; else { cu.cmode = B200_T(kChromaTab)[v]; if (cu.cmode == cu.lmode[0]) cu.cmode = 34; }
     }
     B200_NOUNROLL for (int yy = 0; yy < n; yy += 8) B200_NOUNROLL for (int xx = 0; xx < n; xx += 8) pb.cd8[((y0 + yy) >> 3) * sp->w8 + ((x0 + xx) >> 3)] = (uint8_t)depth;
@@ -513,7 +500,7 @@ struct Decoder {
       int inc = 0;
       if (avail(x0 - 1, y0) && B200_LD_SHARED(pb.cd8 + (y0 >> 3) * sp->w8 + ((x0 - 1) >> 3)) > depth) inc++;
       if (avail(x0, y0 - 1) && B200_LD_SHARED(pb.cd8 + ((y0 - 1) >> 3) * sp->w8 + (x0 >> 3)) > depth) inc++;
-      split = cabac.bin(ctx[CTX_SPLIT_CU + inc]);
+      split = cabac.bin(ctx[CTX_SPLIT_CU + inc], stream);
     } else split = log2cb > sp->log2_min_cb;
     if (sp->cu_qp_delta && log2cb >= sp->qg_log2) {
       is_dqp_coded = 0; dqp_val = 0;
@@ -574,10 +561,11 @@ B200_HD int run_substream(const SeqParams& sp, const PicBuffers& pb, const Subst
     else if (ss.prev < 0) init_contexts(ctx, ss.slice_qp);
     d.first_qg = 1;
   }
-  d.cabac.start(&d.stream, pb.rbsp, pb.rbsp_size, ss.byte_begin);
+  d.stream.d = pb.rbsp; d.stream.size = pb.rbsp_size;
+  d.cabac.start(d.stream, ss.byte_begin);
   B200_NOUNROLL for (uint32_t a = ss.ctb_begin; a < ss.ctb_end; a++) {
     const int rx = (int)(a % (uint32_t)sp.wctb), ry = (int)(a / (uint32_t)sp.wctb);
-    if (ry > 0) sync.wait_row(ry - 1, imin(rx + 2, sp.wctb));     // split_cu_flag context / SAO merge-up read the row above
+    if (ry > 0) sync.wait_row(ry - 1, rx + 1);                   // split_cu_flag context / SAO merge-up read the CTB above (same column)
     if (sp.wpp && rx == 0 && a != ss.ctb_begin) {
       // only reached without WPP sub-stream splitting (never: WPP rows are separate sub-streams); kept for safety
       d.first_qg = 1;
@@ -586,12 +574,12 @@ B200_HD int run_substream(const SeqParams& sp, const PicBuffers& pb, const Subst
     d.decode_ctb((int)a);
     if (d.err) break;
     if (sp.wpp && rx == 1) { uint8_t* st = pb.wpp_ctx + (size_t)ry * CTX_STRIDE; B200_NOUNROLL for (int i = 0; i < CTX_COUNT; i++) st[i] = ctx[i]; }
-    const int end = d.cabac.terminate();                          // end_of_slice_segment_flag
+    const int end = d.cabac.terminate(d.stream);                          // end_of_slice_segment_flag
     const bool last = a + 1 == ss.ctb_end;
     if (end != ((last && ss.last_of_segment) ? 1 : 0)) { d.err = SYN_E_BITSTREAM; break; }
-    if (last && !ss.last_of_segment) { if (!d.cabac.terminate()) { d.err = SYN_E_BITSTREAM; break; } }   // end_of_subset_one_bit
+    if (last && !ss.last_of_segment) { if (!d.cabac.terminate(d.stream)) { d.err = SYN_E_BITSTREAM; break; } }   // end_of_subset_one_bit
     sync.publish_row(ry, rx + 1);
-    if ((uint64_t)d.stream.word * 4 > (uint64_t)pb.rbsp_size + 64) { d.err = SYN_E_BITSTREAM; break; }
+    if (d.cabac.pos > pb.rbsp_size + 64u) { d.err = SYN_E_BITSTREAM; break; }
   }
   // end state for a dependent continuation + dense cursors
   { uint8_t* st = pb.end_state + (size_t)index * CTX_STRIDE; B200_NOUNROLL for (int i = 0; i < CTX_COUNT; i++) st[i] = ctx[i]; st[CTX_COUNT] = (uint8_t)(int8_t)d.last_cu_qpy; }
