@@ -11,6 +11,7 @@
 // used entries are ever touched).  Why on the GPU: the host has 16 usable cores on the target box and CABAC is the
 // end-to-end bottleneck there; the arithmetic decoder is serial per sub-stream but there are thousands of sub-streams.
 #include <cstdint>
+#include <cstdlib>
 // The syntax decoder's lookup tables live in SHARED memory on the device (the dependent table look-ups of every CABAC
 // bin would otherwise go through L1/L2): file-scope __shared__ copies, filled at kernel start, reached through B200_T.
 namespace b200 { namespace syn {
@@ -19,6 +20,11 @@ __shared__ uint8_t s_kTransLps[64];
 __shared__ uint8_t s_kNextState[256];
 __shared__ uint8_t s_kInitI[134];
 __shared__ uint8_t s_kSigMap4[16];
+__shared__ uint8_t s_kScanPos[3][16];
+__shared__ uint8_t s_kScanInv[3][16];
+__shared__ uint8_t s_kSbInv[4][3][64];
+__shared__ uint8_t s_kSigCtx4[3][16];
+__shared__ uint8_t s_kSigCtxN[3][4][16];
 __shared__ uint8_t s_kChromaTab[4];
 __shared__ uint8_t s_kScanX[4][3][64];
 __shared__ uint8_t s_kScanY[4][3][64];
@@ -48,16 +54,22 @@ struct DevSync {
   unsigned* error_flag;
   uint32_t dense_tu, dense_coef, dense_tu_cap, dense_coef_cap;   // unused on the device (fixed slots)
   uint64_t end_bit_position;
-  __device__ void wait_row(int row, int need) {
-    // a CTB takes ~0.5 ms; back off to microseconds so thousands of waiting warps do not flood L2 with polls
-    unsigned spins = 0, ns = 500;
-    while (e_ld_acquire(progress + row) < (unsigned)need) { __nanosleep(ns); if (ns < 4000) ns <<= 1; if (++spins > (1u << 21)) { atomicExch(error_flag, 3u); break; } }
+  // A CTB takes ~0.5 ms: back off to microseconds so thousands of waiting warps do not flood L2 with polls.  Gives up
+  // (error 3) after 20 s of wall time -- only a lost producer can cause that.
+  __device__ static void spin_until(const unsigned* p, unsigned need, unsigned* error_flag) {
+    if (e_ld_acquire(p) >= need) return;
+    unsigned long long t0; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+    unsigned ns = 500;
+    for (;;) {
+      __nanosleep(ns); if (ns < 4000) ns <<= 1;
+      if (e_ld_acquire(p) >= need) return;
+      unsigned long long t1; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+      if (t1 - t0 > 20000000000ull) { atomicExch(error_flag, 3u); return; }
+    }
   }
+  __device__ void wait_row(int row, int need) { spin_until(progress + row, (unsigned)need, error_flag); }
   __device__ void publish_row(int row, int done) { e_st_release(progress + row, (unsigned)done); }
-  __device__ void wait_substream(int idx) {
-    unsigned spins = 0, ns = 500;
-    while (e_ld_acquire(sub_done + idx) == 0u) { __nanosleep(ns); if (ns < 4000) ns <<= 1; if (++spins > (1u << 21)) { atomicExch(error_flag, 3u); break; } }
-  }
+  __device__ void wait_substream(int idx) { spin_until(sub_done + idx, 1u, error_flag); }
   __device__ void finish_substream(int idx, int err) {
     e_st_release(sub_done + idx, 1u);
     if (err) atomicExch(error_flag, (unsigned)err);
@@ -70,6 +82,9 @@ __global__ void __launch_bounds__(EWARPS * 32) hevc_entropy_kernel(const Entropy
   for (int i = threadIdx.x; i < 134; i += blockDim.x) syn::s_kInitI[i] = syn::d_kInitI[i];
   for (int i = threadIdx.x; i < 256; i += blockDim.x) syn::s_kNextState[i] = syn::d_kNextState[i];
   for (int i = threadIdx.x; i < 16; i += blockDim.x) syn::s_kSigMap4[i] = syn::d_kSigMap4[i];
+  for (int i = threadIdx.x; i < 48; i += blockDim.x) { (&syn::s_kScanPos[0][0])[i] = (&syn::d_kScanPos[0][0])[i]; (&syn::s_kScanInv[0][0])[i] = (&syn::d_kScanInv[0][0])[i]; (&syn::s_kSigCtx4[0][0])[i] = (&syn::d_kSigCtx4[0][0])[i]; }
+  for (int i = threadIdx.x; i < 192; i += blockDim.x) (&syn::s_kSigCtxN[0][0][0])[i] = (&syn::d_kSigCtxN[0][0][0])[i];
+  for (int i = threadIdx.x; i < 768; i += blockDim.x) (&syn::s_kSbInv[0][0][0])[i] = (&syn::d_kSbInv[0][0][0])[i];
   for (int i = threadIdx.x; i < 4; i += blockDim.x) syn::s_kChromaTab[i] = syn::d_kChromaTab[i];
   for (int i = threadIdx.x; i < 4 * 3 * 64; i += blockDim.x) { (&syn::s_kScanX[0][0][0])[i] = (&syn::d_kScanX[0][0][0])[i]; (&syn::s_kScanY[0][0][0])[i] = (&syn::d_kScanY[0][0][0])[i]; }
   __syncthreads();
@@ -108,6 +123,7 @@ int launch_entropy(const EntropyBatch& b, cudaStream_t s) {
   int dev = 0, sms = 148; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   int occ = 1; cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, hevc_entropy_kernel, EWARPS * 32, 0);
   if (occ < 1) occ = 1;
+  if (const char* e = getenv("B200_ENTROPY_BLOCKS_PER_SM")) { const int v = atoi(e); if (v >= 1 && v < occ) occ = v; }   // tuning knob
   const int want = (b.nsubs + EWARPS - 1) / EWARPS;
   const int grid = want < sms * occ ? want : sms * occ;
   hevc_entropy_kernel<<<grid, EWARPS * 32, 0, s>>>(b);

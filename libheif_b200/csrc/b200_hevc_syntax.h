@@ -63,8 +63,25 @@ B200_TABLE(uint8_t, kChromaTab, [4], {0, 26, 10, 1})
 B200_TABLE(uint8_t, kScanX, [4][3][64], {{{0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0},{0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0},{0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0}},{{0,0,1,1,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0},{0,1,0,1,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0},{0,0,1,1,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0}},{{0,0,1,0,1,2,0,1,2,3,1,2,3,2,3,3,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0},{0,1,2,3,0,1,2,3,0,1,2,3,0,1,2,3,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0},{0,0,0,0,1,1,1,1,2,2,2,2,3,3,3,3,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0}},{{0,0,1,0,1,2,0,1,2,3,0,1,2,3,4,0,1,2,3,4,5,0,1,2,3,4,5,6,0,1,2,3,4,5,6,7,1,2,3,4,5,6,7,2,3,4,5,6,7,3,4,5,6,7,4,5,6,7,5,6,7,6,7,7},{0,1,2,3,4,5,6,7,0,1,2,3,4,5,6,7,0,1,2,3,4,5,6,7,0,1,2,3,4,5,6,7,0,1,2,3,4,5,6,7,0,1,2,3,4,5,6,7,0,1,2,3,4,5,6,7,0,1,2,3,4,5,6,7},{0,0,0,0,0,0,0,0,1,1,1,1,1,1,1,1,2,2,2,2,2,2,2,2,3,3,3,3,3,3,3,3,4,4,4,4,4,4,4,4,5,5,5,5,5,5,5,5,6,6,6,6,6,6,6,6,7,7,7,7,7,7,7,7}}})
 B200_TABLE(uint8_t, kScanY, [4][3][64], {{{0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0},{0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0},{0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0}},{{0,1,0,1,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0},{0,0,1,1,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0},{0,1,0,1,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0}},{{0,1,0,2,1,0,3,2,1,0,3,2,1,3,2,3,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0},{0,0,0,0,1,1,1,1,2,2,2,2,3,3,3,3,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0},{0,1,2,3,0,1,2,3,0,1,2,3,0,1,2,3,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0}},{{0,1,0,2,1,0,3,2,1,0,4,3,2,1,0,5,4,3,2,1,0,6,5,4,3,2,1,0,7,6,5,4,3,2,1,0,7,6,5,4,3,2,1,7,6,5,4,3,2,7,6,5,4,3,7,6,5,4,7,6,5,7,6,7},{0,0,0,0,0,0,0,0,1,1,1,1,1,1,1,1,2,2,2,2,2,2,2,2,3,3,3,3,3,3,3,3,4,4,4,4,4,4,4,4,5,5,5,5,5,5,5,5,6,6,6,6,6,6,6,6,7,7,7,7,7,7,7,7},{0,1,2,3,4,5,6,7,0,1,2,3,4,5,6,7,0,1,2,3,4,5,6,7,0,1,2,3,4,5,6,7,0,1,2,3,4,5,6,7,0,1,2,3,4,5,6,7,0,1,2,3,4,5,6,7,0,1,2,3,4,5,6,7}}})
 
+// derived from the scans above: 4x4 position (y << 2 | x) of scan index k and its inverse; sub-block scan index of (ys * 8 + xs);
+// sig_coeff_flag context increments (9.3.4.2.5) per scan index: kSigCtx4 for 4x4 blocks, kSigCtxN[scan][prevCsbf] for larger ones
+B200_TABLE(uint8_t, kScanPos, [3][16], {{0,4,1,8,5,2,12,9,6,3,13,10,7,14,11,15},{0,1,2,3,4,5,6,7,8,9,10,11,12,13,14,15},{0,4,8,12,1,5,9,13,2,6,10,14,3,7,11,15}})
+B200_TABLE(uint8_t, kScanInv, [3][16], {{0,2,5,9,1,4,8,12,3,7,11,14,6,10,13,15},{0,1,2,3,4,5,6,7,8,9,10,11,12,13,14,15},{0,4,8,12,1,5,9,13,2,6,10,14,3,7,11,15}})
+B200_TABLE(uint8_t, kSbInv, [4][3][64], {{{0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0},{0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0},{0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0}},{{0,2,0,0,0,0,0,0,1,3,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0},{0,1,0,0,0,0,0,0,2,3,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0},{0,2,0,0,0,0,0,0,1,3,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0}},{{0,2,5,9,0,0,0,0,1,4,8,12,0,0,0,0,3,7,11,14,0,0,0,0,6,10,13,15,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0},{0,1,2,3,0,0,0,0,4,5,6,7,0,0,0,0,8,9,10,11,0,0,0,0,12,13,14,15,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0},{0,4,8,12,0,0,0,0,1,5,9,13,0,0,0,0,2,6,10,14,0,0,0,0,3,7,11,15,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0}},{{0,2,5,9,14,20,27,35,1,4,8,13,19,26,34,42,3,7,12,18,25,33,41,48,6,11,17,24,32,40,47,53,10,16,23,31,39,46,52,57,15,22,30,38,45,51,56,60,21,29,37,44,50,55,59,62,28,36,43,49,54,58,61,63},{0,1,2,3,4,5,6,7,8,9,10,11,12,13,14,15,16,17,18,19,20,21,22,23,24,25,26,27,28,29,30,31,32,33,34,35,36,37,38,39,40,41,42,43,44,45,46,47,48,49,50,51,52,53,54,55,56,57,58,59,60,61,62,63},{0,8,16,24,32,40,48,56,1,9,17,25,33,41,49,57,2,10,18,26,34,42,50,58,3,11,19,27,35,43,51,59,4,12,20,28,36,44,52,60,5,13,21,29,37,45,53,61,6,14,22,30,38,46,54,62,7,15,23,31,39,47,55,63}}})
+B200_TABLE(uint8_t, kSigCtx4, [3][16], {{0,2,1,6,3,4,7,6,4,5,7,8,5,8,8,8},{0,1,4,5,2,3,4,5,6,6,8,8,7,7,8,8},{0,2,6,7,1,3,6,7,4,4,8,8,5,5,8,8}})
+B200_TABLE(uint8_t, kSigCtxN, [3][4][16], {{{2,1,1,1,1,1,0,0,0,0,0,0,0,0,0,0},{2,1,2,0,1,2,0,0,1,2,0,0,1,0,0,0},{2,2,1,2,1,0,2,1,0,0,1,0,0,0,0,0},{2,2,2,2,2,2,2,2,2,2,2,2,2,2,2,2}},{{2,1,1,0,1,1,0,0,1,0,0,0,0,0,0,0},{2,2,2,2,1,1,1,1,0,0,0,0,0,0,0,0},{2,1,0,0,2,1,0,0,2,1,0,0,2,1,0,0},{2,2,2,2,2,2,2,2,2,2,2,2,2,2,2,2}},{{2,1,1,0,1,1,0,0,1,0,0,0,0,0,0,0},{2,1,0,0,2,1,0,0,2,1,0,0,2,1,0,0},{2,2,2,2,1,1,1,1,0,0,0,0,0,0,0,0},{2,2,2,2,2,2,2,2,2,2,2,2,2,2,2,2}}})
+
 B200_HD inline int clip3(int lo, int hi, int v) { return v < lo ? lo : (v > hi ? hi : v); }
 B200_HD inline int imin(int a, int b) { return a < b ? a : b; }
+#ifdef __CUDA_ARCH__
+B200_HD inline int hi_bit(uint32_t v) { return 31 - __clz((int)v); }          // v != 0
+B200_HD inline int lo_bit(uint32_t v) { return __ffs((int)v) - 1; }
+B200_HD inline int pop_count(uint32_t v) { return __popc(v); }
+#else
+B200_HD inline int hi_bit(uint32_t v) { return 31 - __builtin_clz(v); }
+B200_HD inline int lo_bit(uint32_t v) { return __builtin_ctz(v); }
+B200_HD inline int pop_count(uint32_t v) { return __builtin_popcount(v); }
+#endif
 
 // Sequence / picture level parameters the slice data depends on (filled by the host from SPS + PPS).
 struct SeqParams {
@@ -291,83 +308,68 @@ struct Decoder {
     if (scan == 2) { const int t = lx; lx = ly; ly = t; }
     if (lx >= n || ly >= n) { err = SYN_E_BITSTREAM; cabac = cb_; return 0; }
     const int l2sb = log2n - 2;
-    const uint8_t *sbx = B200_T(kScanX)[l2sb][scan], *sby = B200_T(kScanY)[l2sb][scan], *px = B200_T(kScanX)[2][scan], *py = B200_T(kScanY)[2][scan];
-    int last_sb = 0, last_pos = 0;
-    { const int xs = lx >> 2, ys = ly >> 2, xp = lx & 3, yp = ly & 3, nsb = 1 << (2 * l2sb);
-      B200_NOUNROLL for (int i = 0; i < nsb; i++) if (sbx[i] == xs && sby[i] == ys) { last_sb = i; break; }
-      B200_NOUNROLL for (int k = 0; k < 16; k++) if (px[k] == xp && py[k] == yp) { last_pos = k; break; } }
+    const uint8_t *sbx = B200_T(kScanX)[l2sb][scan], *sby = B200_T(kScanY)[l2sb][scan], *spos = B200_T(kScanPos)[scan];
+    const int last_sb = B200_T(kSbInv)[l2sb][scan][((ly >> 2) << 3) + (lx >> 2)];
+    const int last_pos = B200_T(kScanInv)[scan][((ly & 3) << 2) + (lx & 3)];
     uint64_t csbf = 0;                                  // coded_sub_block_flag, bit (ys * 8 + xs)
     int carry = 1, count = 0; bool first_done = false;
     const int nsbw = 1 << l2sb;
+    const int dc_ctx = CTX_SIG + (c ? 27 : 0);
+    const int sig_base = log2n == 2 ? dc_ctx : (c == 0 ? CTX_SIG + (log2n == 3 ? (scan == 0 ? 9 : 15) : 21) : CTX_SIG + 27 + (log2n == 3 ? 9 : 12));
     B200_NOUNROLL for (int i = last_sb; i >= 0; i--) {
       const int xs = sbx[i], ys = sby[i];
       const int right = (xs + 1 < nsbw) ? (int)((csbf >> (ys * 8 + xs + 1)) & 1) : 0;
       const int below = (ys + 1 < nsbw) ? (int)((csbf >> ((ys + 1) * 8 + xs)) & 1) : 0;
-      int infer_dc = 0, coded;
-      if (i < last_sb && i > 0) { coded = cb_.bin(cx[CTX_CSBF + ((right | below) ? 1 : 0) + (c ? 2 : 0)], stream); infer_dc = 1; } else coded = 1;
-      if (!coded) continue;
+      int infer_dc = 0;
+      if (i < last_sb && i > 0) { if (!cb_.bin(cx[CTX_CSBF + ((right | below) ? 1 : 0) + (c ? 2 : 0)], stream)) continue; infer_dc = 1; }
       csbf |= 1ull << (ys * 8 + xs);
-      const int prev = right | (below << 1);
+      // sig_coeff_flag (9.3.4.2.5): context = per-sub-block base + table entry per scan position; DC of the block has its own
+      const uint8_t* tab = log2n == 2 ? B200_T(kSigCtx4)[scan] : B200_T(kSigCtxN)[scan][right | (below << 1)];
+      const int off = sig_base + ((c == 0 && log2n > 2 && (xs | ys)) ? 3 : 0);
       unsigned sig = 0;
-      const int start = i == last_sb ? last_pos - 1 : 15;
-      if (i == last_sb) sig |= 1u << last_pos;
-      B200_NOUNROLL for (int k = start; k >= 0; k--) {
-        if (k > 0 || !infer_dc) {
-          const int xc = (xs << 2) + px[k], yc = (ys << 2) + py[k];
-          int sc;
-          if (log2n == 2) sc = B200_T(kSigMap4)[(yc << 2) + xc];
-          else if (xc + yc == 0) sc = 0;
-          else {
-            const int xp = xc & 3, yp = yc & 3;
-            if (prev == 0) sc = (xp + yp == 0) ? 2 : (xp + yp < 3) ? 1 : 0;
-            else if (prev == 1) sc = yp == 0 ? 2 : (yp == 1 ? 1 : 0);
-            else if (prev == 2) sc = xp == 0 ? 2 : (xp == 1 ? 1 : 0);
-            else sc = 2;
-            if (c == 0) { if (xs || ys) sc += 3; sc += log2n == 3 ? (scan == 0 ? 9 : 15) : 21; } else sc += log2n == 3 ? 9 : 12;
-          }
-          if (cb_.bin(cx[CTX_SIG + (c == 0 ? sc : 27 + sc)], stream)) { sig |= 1u << k; infer_dc = 0; }
-        } else sig |= 1u;
+      int k = 15;
+      if (i == last_sb) { sig = 1u << last_pos; k = last_pos - 1; }
+      B200_NOUNROLL for (; k >= 0; k--) {
+        int ci = off + tab[k];
+        if (k == 0) { if (infer_dc && !sig) { sig = 1u; break; } if (i == 0) ci = dc_ctx; }
+        if (cb_.bin(cx[ci], stream)) sig |= 1u << k;
       }
       if (!sig) continue;
       unsigned g1 = 0;
-      int ng1 = 0, last_g1 = -1, g1ctx = 1, g2 = 0;
+      int last_g1 = -1, g1ctx = 1, g2 = 0;
       int ctx_set = (i == 0 || c > 0) ? 0 : 2;
       if (first_done && carry == 0) ctx_set++;
       first_done = true;
-      int last_sig = -1, first_sig = 16;
-      B200_NOUNROLL for (int k = 15; k >= 0; k--) if ((sig >> k) & 1) {
-        if (ng1 < 8) {
-          const int g = cb_.bin(cx[CTX_GT1 + ctx_set * 4 + imin(3, g1ctx) + (c ? 16 : 0)], stream);
-          ng1++;
-          if (g) { g1 |= 1u << k; g1ctx = 0; if (last_g1 < 0) last_g1 = k; } else if (g1ctx > 0) g1ctx++;
-        }
-        if (last_sig < 0) last_sig = k;
-        first_sig = k;
-      }
+      const int last_sig = hi_bit(sig), first_sig = lo_bit(sig);
+      { unsigned m = sig; const int gbase = CTX_GT1 + ctx_set * 4 + (c ? 16 : 0);
+        B200_NOUNROLL for (int ng1 = 0; m && ng1 < 8; ng1++) {
+          const int kk = hi_bit(m); m ^= 1u << kk;
+          if (cb_.bin(cx[gbase + imin(3, g1ctx)], stream)) { g1 |= 1u << kk; g1ctx = 0; if (last_g1 < 0) last_g1 = kk; } else if (g1ctx > 0) g1ctx++;
+        } }
       carry = g1ctx;
       const bool hidden = sign_hiding && (last_sig - first_sig > 3);
       if (last_g1 >= 0) g2 = cb_.bin(cx[CTX_GT2 + ctx_set + (c ? 4 : 0)], stream);
-      int nsign = 0;
-      B200_NOUNROLL for (int k = 15; k >= 0; k--) if (((sig >> k) & 1) && (!hidden || k != first_sig)) nsign++;
+      const int nsign = pop_count(sig) - (hidden ? 1 : 0);
       const unsigned signs = cb_.bypass_bits(nsign, stream);
       int nsig = 0, sum = 0, rice = 0, sidx = nsign;
-      B200_NOUNROLL for (int k = 15; k >= 0; k--) if ((sig >> k) & 1) {
-        const int base = 1 + (int)((g1 >> k) & 1) + (k == last_g1 ? g2 : 0);
+      B200_NOUNROLL for (unsigned m = sig; m; nsig++) {
+        const int kk = hi_bit(m); m ^= 1u << kk;
+        const int base = 1 + (int)((g1 >> kk) & 1) + (kk == last_g1 ? g2 : 0);
         int a = base;
-        if (base == ((nsig < 8) ? ((k == last_g1) ? 3 : 2) : 1)) {
+        if (base == ((nsig < 8) ? ((kk == last_g1) ? 3 : 2) : 1)) {
           int pre = 0; B200_NOUNROLL while (pre < 32 && cb_.bypass(stream)) pre++;
           const int rem = pre <= 3 ? (pre << rice) + (int)cb_.bypass_bits(rice, stream) : (((1 << (pre - 3)) + 3 - 1) << rice) + (int)cb_.bypass_bits(pre - 3 + rice, stream);
           a = base + rem;
           if (a > 3 * (1 << rice)) rice = imin(rice + 1, 4);
         }
         int neg = 0;
-        if (!hidden || k != first_sig) { sidx--; neg = (int)((signs >> sidx) & 1); }
+        if (!hidden || kk != first_sig) { sidx--; neg = (int)((signs >> sidx) & 1); }
         int v = neg ? -a : a;
-        if (hidden) { sum += a; if (k == first_sig && (sum & 1)) v = -v; }
+        if (hidden) { sum += a; if (kk == first_sig && (sum & 1)) v = -v; }
         if (cn >= ccap) { err = SYN_E_OVERFLOW; cabac = cb_; coef_n = cn; return count; }
-        CoefEntry e; e.pos = (uint16_t)((((ys << 2) + py[k]) << log2n) + (xs << 2) + px[k]); e.level = (int16_t)clip3(-32768, 32767, v);
+        const int p = spos[kk];
+        CoefEntry e; e.pos = (uint16_t)((((ys << 2) + (p >> 2)) << log2n) + (xs << 2) + (p & 3)); e.level = (int16_t)clip3(-32768, 32767, v);
         coef_out[cn++] = e; count++;
-        nsig++;
       }
     }
     cabac = cb_; coef_n = cn;
