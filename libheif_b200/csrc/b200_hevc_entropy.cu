@@ -37,6 +37,7 @@ __shared__ uint8_t s_kScanY[4][3][64];
 namespace b200 {
 
 constexpr int EWARPS = 4;
+constexpr int ELANES_MAX = 4;     // decoders per warp (diverged lanes, independent thread scheduling); experiment knob B200_ENTROPY_LANES
 
 // Polling load: relaxed + gpu scope (served by L2).  ld.acquire would make ptxas emit CCTL.IVALL -- an SM-wide L1 invalidation --
 // on EVERY poll (measured: 43 % of all stall samples of the first version); ordering is obtained instead by reading every
@@ -76,8 +77,9 @@ struct DevSync {
   }
 };
 
-__global__ void __launch_bounds__(EWARPS * 32) hevc_entropy_kernel(const EntropyBatch b) {
-  __shared__ uint8_t s_ctx[EWARPS][syn::CTX_STRIDE];
+__global__ void __launch_bounds__(EWARPS * 32) hevc_entropy_kernel(const EntropyBatch b, const int lanes) {
+  __shared__ uint8_t s_ctx[EWARPS * ELANES_MAX][syn::CTX_STRIDE];
+  __shared__ syn::Decoder s_dec[EWARPS * ELANES_MAX];                    // per-warp decoder state (see run_substream)
   for (int i = threadIdx.x; i < 64; i += blockDim.x) { syn::s_kLps4[i] = syn::d_kLps4[i]; syn::s_kTransLps[i] = syn::d_kTransLps[i]; }
   for (int i = threadIdx.x; i < 134; i += blockDim.x) syn::s_kInitI[i] = syn::d_kInitI[i];
   for (int i = threadIdx.x; i < 256; i += blockDim.x) syn::s_kNextState[i] = syn::d_kNextState[i];
@@ -88,8 +90,9 @@ __global__ void __launch_bounds__(EWARPS * 32) hevc_entropy_kernel(const Entropy
   for (int i = threadIdx.x; i < 4; i += blockDim.x) syn::s_kChromaTab[i] = syn::d_kChromaTab[i];
   for (int i = threadIdx.x; i < 4 * 3 * 64; i += blockDim.x) { (&syn::s_kScanX[0][0][0])[i] = (&syn::d_kScanX[0][0][0])[i]; (&syn::s_kScanY[0][0][0])[i] = (&syn::d_kScanY[0][0][0])[i]; }
   __syncthreads();
-  if ((threadIdx.x & 31) != 0) return;                      // lane 0 of every warp decodes; CABAC is serial per sub-stream
-  uint8_t* ctx = s_ctx[threadIdx.x >> 5];
+  if ((int)(threadIdx.x & 31) >= lanes) return;             // CABAC is serial per sub-stream: `lanes` independent decoders per warp
+  const int slot = (threadIdx.x >> 5) * ELANES_MAX + (threadIdx.x & 31);
+  uint8_t* ctx = s_ctx[slot];
   for (;;) {
     const unsigned t = atomicAdd(b.ticket, 1u);
     if (t >= (unsigned)b.nsubs) break;
@@ -98,7 +101,7 @@ __global__ void __launch_bounds__(EWARPS * 32) hevc_entropy_kernel(const Entropy
     DevSync sync;
     sync.progress = b.progress + ep.progress_base; sync.sub_done = b.sub_done + ep.sub_base; sync.error_flag = b.error_flag;
     sync.dense_tu = sync.dense_coef = sync.dense_tu_cap = sync.dense_coef_cap = 0; sync.end_bit_position = 0;
-    syn::run_substream(ep.sp, ep.pb, b.subs + ep.sub_base, (int)ref.y, ctx, sync);
+    syn::run_substream(s_dec[slot], ep.sp, ep.pb, b.subs + ep.sub_base, (int)ref.y, ctx, sync);
   }
 }
 
@@ -124,9 +127,11 @@ int launch_entropy(const EntropyBatch& b, cudaStream_t s) {
   int occ = 1; cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, hevc_entropy_kernel, EWARPS * 32, 0);
   if (occ < 1) occ = 1;
   if (const char* e = getenv("B200_ENTROPY_BLOCKS_PER_SM")) { const int v = atoi(e); if (v >= 1 && v < occ) occ = v; }   // tuning knob
-  const int want = (b.nsubs + EWARPS - 1) / EWARPS;
+  int lanes = 1;
+  if (const char* e = getenv("B200_ENTROPY_LANES")) { const int v = atoi(e); if (v >= 1 && v <= ELANES_MAX) lanes = v; }
+  const int want = (b.nsubs + EWARPS * lanes - 1) / (EWARPS * lanes);
   const int grid = want < sms * occ ? want : sms * occ;
-  hevc_entropy_kernel<<<grid, EWARPS * 32, 0, s>>>(b);
+  hevc_entropy_kernel<<<grid, EWARPS * 32, 0, s>>>(b, lanes);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return set_error(B200_E_CUDA, "entropy launch: %s", cudaGetErrorString(e));
   return B200_OK;

@@ -211,8 +211,7 @@ __device__ __noinline__ void process_tb(WarpMem& m, const int8_t* __restrict__ m
   if (mode == 1) {
     int s = 0;
     for (int i = lane; i < n; i += 32) s += LEFT(i) + TOP(i);
-#pragma unroll
-    for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    s = __reduce_add_sync(0xffffffffu, s);
     dc = (s + n) >> (log2n + 1);
   }
   const int ang = c_angle[mode], ia = c_inv_angle[mode];
@@ -259,8 +258,7 @@ __device__ __noinline__ void process_tb(WarpMem& m, const int8_t* __restrict__ m
     m.coef[e.pos] = (int16_t)(t < -32768 ? -32768 : (t > 32767 ? 32767 : t));
     maxrow = max(maxrow, e.pos >> log2n); maxcol = max(maxcol, e.pos & (n - 1));
   }
-#pragma unroll
-  for (int o = 16; o; o >>= 1) { maxrow = max(maxrow, __shfl_xor_sync(0xffffffffu, maxrow, o)); maxcol = max(maxcol, __shfl_xor_sync(0xffffffffu, maxcol, o)); }
+  maxrow = __reduce_max_sync(0xffffffffu, maxrow); maxcol = __reduce_max_sync(0xffffffffu, maxcol);
   __syncwarp();
   const int bs2 = 20 - bd;
   if (tskip) {                                          // 8.6.4.2, transform_skip_flag: r = d << 7
@@ -364,11 +362,13 @@ __global__ void __launch_bounds__(WARPS * 32) hevc_recon_kernel(const DeviceBatc
           }
         }
         __syncwarp();
+#pragma unroll 1
         for (int c = 0; c < nch; c++) {
           const int cw = c ? r.W >> 1 : r.W, st = pic->rec_stride[c];
           const int gx0 = (c ? r.x0 >> 1 : r.x0) - 1, gy = (c ? r.y0 >> 1 : r.y0) - 1;
           const int cnt = 1 + 2 * (c ? ctbc : r.ctb);
           uint16_t* dst = c == 0 ? m.top_y : m.top_c[c - 1];
+#pragma unroll 1
           for (int i = lane; i < cnt; i += 32) {
             const int gx = gx0 + i;
             int v = 0;
@@ -397,12 +397,14 @@ __global__ void __launch_bounds__(WARPS * 32) hevc_recon_kernel(const DeviceBatc
         }
       }
       // write the finished CTB to HBM (coalesced rows), keep its last column as the next CTB's left halo
+#pragma unroll 1
       for (int c = 0; c < nch; c++) {
         const int cw = c ? r.W >> 1 : r.W, chh = c ? r.H >> 1 : r.H, st = pic->rec_stride[c];
         const int gx0 = c ? r.x0 >> 1 : r.x0, gy0 = c ? r.y0 >> 1 : r.y0, sz = c ? ctbc : r.ctb, lg = c ? r.log2ctb - 1 : r.log2ctb;
         const uint16_t* tile = c == 0 ? m.tile_y : m.tile_c[c - 1];
         const int ts = c == 0 ? m.ts : m.tsc;
         const int w = min(sz, cw - gx0), h = min(sz, chh - gy0);
+#pragma unroll 2
         for (int i = lane; i < sz * h; i += 32) {
           const int x = i & (sz - 1), y = i >> lg;
           if (x < w) {
@@ -412,6 +414,7 @@ __global__ void __launch_bounds__(WARPS * 32) hevc_recon_kernel(const DeviceBatc
           }
         }
         uint16_t* left = c == 0 ? m.left_y : m.left_c[c - 1];
+#pragma unroll 1
         for (int y = lane; y < sz; y += 32) left[y] = tile[y * ts + sz - 1];
       }
       __syncwarp();                                         // all lanes' stores precede lane 0's release store (cumulativity)

@@ -15,11 +15,13 @@
 #define B200_HDN __host__ __device__ __noinline__
 #define B200_NOUNROLL _Pragma("unroll 1")
 #define B200_HD __host__ __device__
+#define B200_HDI __host__ __device__ __forceinline__
 #define B200_TABLE(type, name, dims, ...) static const type h_##name dims = __VA_ARGS__; static __device__ const type d_##name dims = __VA_ARGS__;
 #else
 #define B200_HDN
 #define B200_NOUNROLL
 #define B200_HD
+#define B200_HDI inline
 #define B200_TABLE(type, name, dims, ...) static const type h_##name dims = __VA_ARGS__;
 #endif
 #if defined(__CUDA_ARCH__) && !defined(B200_T)
@@ -236,10 +238,16 @@ struct Decoder {
 
   // 6.4.1 for a left / above neighbour of the current block: those always precede it in decoding order, so they are
   // available iff they lie inside the picture and in the same slice (HEVC tiles are not supported).
-  B200_HD inline bool avail(int x, int y) const {
+  B200_HDN bool avail(int x, int y) const {
     if (x < 0 || y < 0 || x >= sp->W || y >= sp->H) return false;
     return pb.ctu_slice[(y >> sp->log2ctb) * sp->wctb + (x >> sp->log2ctb)] == (uint16_t)ss->slice_idx;
   }
+
+  // Out-of-line arithmetic-decoder primitives for everything outside residual_coding (which keeps its own register
+  // copy of the decoder): a call instead of ~35 inlined instructions per syntax element keeps the hot code small.
+  B200_HDN int dbin(int ci) { return cabac.bin(ctx[ci], stream); }
+  B200_HDN int dbypass() { return cabac.bypass(stream); }
+  B200_HDN unsigned dbits(int k) { return cabac.bypass_bits(k, stream); }
 
   // -------- SAO (7.3.8.3)
   B200_HDN void parse_sao(int rx, int ry, CtuInfo& ci) {
@@ -247,8 +255,8 @@ struct Decoder {
     B200_NOUNROLL for (int c = 0; c < 3; c++) { ci.sao[c].type = 0; ci.sao[c].band_or_class = 0; B200_NOUNROLL for (int k = 0; k < 4; k++) ci.sao[c].offset[k] = 0; }
     if (!ss->sao_luma && !ss->sao_chroma) return;
     int ml = 0, mu = 0;
-    if (rx > 0 && (uint32_t)(addr - 1) >= ss->slice_addr_rs) ml = cabac.bin(ctx[CTX_SAO_MERGE], stream);
-    if (ry > 0 && !ml && addr - sp->wctb >= (int)ss->slice_addr_rs) mu = cabac.bin(ctx[CTX_SAO_MERGE], stream);
+    if (rx > 0 && (uint32_t)(addr - 1) >= ss->slice_addr_rs) ml = dbin(CTX_SAO_MERGE);
+    if (ry > 0 && !ml && addr - sp->wctb >= (int)ss->slice_addr_rs) mu = dbin(CTX_SAO_MERGE);
     if (ml || mu) {
       const unsigned long long* o = reinterpret_cast<const unsigned long long*>(pb.ctus[ml ? addr - 1 : addr - sp->wctb].sao);   // 3 x 8 bytes
       unsigned long long* dsto = reinterpret_cast<unsigned long long*>(ci.sao);
@@ -257,18 +265,18 @@ struct Decoder {
     }
     B200_NOUNROLL for (int c = 0; c < (sp->chroma ? 3 : 1); c++) {
       if ((c == 0 && !ss->sao_luma) || (c > 0 && !ss->sao_chroma)) continue;
-      if (c < 2) { int t = 0; if (cabac.bin(ctx[CTX_SAO_TYPE], stream)) t = cabac.bypass(stream) ? 2 : 1; ci.sao[c].type = (uint8_t)t; } else ci.sao[2].type = ci.sao[1].type;
+      if (c < 2) { int t = 0; if (dbin(CTX_SAO_TYPE)) t = dbypass() ? 2 : 1; ci.sao[c].type = (uint8_t)t; } else ci.sao[2].type = ci.sao[1].type;
       if (!ci.sao[c].type) continue;
       const int cmax = (1 << (imin(sp->bd, 10) - 5)) - 1;
       int av[4];
-      B200_NOUNROLL for (int i = 0; i < 4; i++) { int v = 0; B200_NOUNROLL while (v < cmax && cabac.bypass(stream)) v++; av[i] = v; }
+      B200_NOUNROLL for (int i = 0; i < 4; i++) { int v = 0; B200_NOUNROLL while (v < cmax && dbypass()) v++; av[i] = v; }
       const int sc = c == 0 ? sp->sao_scale_luma : sp->sao_scale_chroma;
       if (ci.sao[c].type == 1) {
-        B200_NOUNROLL for (int i = 0; i < 4; i++) if (av[i] && cabac.bypass(stream)) av[i] = -av[i];
-        ci.sao[c].band_or_class = (uint8_t)cabac.bypass_bits(5, stream);
+        B200_NOUNROLL for (int i = 0; i < 4; i++) if (av[i] && dbypass()) av[i] = -av[i];
+        ci.sao[c].band_or_class = (uint8_t)dbits(5);
         B200_NOUNROLL for (int i = 0; i < 4; i++) ci.sao[c].offset[i] = (int8_t)clip3(-128, 127, av[i] * (1 << sc));
       } else {
-        if (c < 2) ci.sao[c].band_or_class = (uint8_t)cabac.bypass_bits(2, stream); else ci.sao[2].band_or_class = ci.sao[1].band_or_class;
+        if (c < 2) ci.sao[c].band_or_class = (uint8_t)dbits(2); else ci.sao[2].band_or_class = ci.sao[1].band_or_class;
         ci.sao[c].offset[0] = (int8_t)clip3(-128, 127, av[0] << sc); ci.sao[c].offset[1] = (int8_t)clip3(-128, 127, av[1] << sc);
         ci.sao[c].offset[2] = (int8_t)clip3(-128, 127, -(av[2] << sc)); ci.sao[c].offset[3] = (int8_t)clip3(-128, 127, -(av[3] << sc));
       }
@@ -286,7 +294,7 @@ struct Decoder {
   }
 
   // -------- residual_coding (7.3.8.11): emits sparse (pos, level) entries; returns the number of coefficients
-  B200_HDN int residual(int log2n, int c, int mode, int& tskip) {
+  B200_HDI int residual(int log2n, int c, int mode, int& tskip) {
     const int n = 1 << log2n;
     // Local copies: their addresses never escape, so they live in registers and need no reload after the byte stores
     // into the context array (uint8_t stores may alias any member otherwise).
@@ -299,10 +307,18 @@ struct Decoder {
     int off, shift;
     if (c == 0) { off = 3 * (log2n - 2) + ((log2n - 1) >> 2); shift = (log2n + 1) >> 2; } else { off = 15; shift = log2n - 2; }
     int lx = 0, ly = 0;
-    B200_NOUNROLL while (lx < cmax && cb_.bin(cx[CTX_LAST_X + off + (lx >> shift)], stream)) lx++;
-    B200_NOUNROLL while (ly < cmax && cb_.bin(cx[CTX_LAST_Y + off + (ly >> shift)], stream)) ly++;
-    if (lx > 3) { const int nb = (lx >> 1) - 1; lx = (1 << nb) * (2 + (lx & 1)) + (int)cb_.bypass_bits(nb, stream); }
-    if (ly > 3) { const int nb = (ly >> 1) - 1; ly = (1 << nb) * (2 + (ly & 1)) + (int)cb_.bypass_bits(nb, stream); }
+    // last_sig_coeff_{x,y}_prefix then the two suffixes (7.3.8.11 order); one loop body serves both coordinates
+    B200_NOUNROLL for (int xy = 0; xy < 2; xy++) {
+      const uint8_t* lc = cx + (xy ? CTX_LAST_Y : CTX_LAST_X) + off;
+      int l = 0;
+      B200_NOUNROLL while (l < cmax && cb_.bin(const_cast<uint8_t&>(lc[l >> shift]), stream)) l++;
+      if (xy) ly = l; else lx = l;
+    }
+    B200_NOUNROLL for (int xy = 0; xy < 2; xy++) {
+      int l = xy ? ly : lx;
+      if (l > 3) { const int nb = (l >> 1) - 1; l = (1 << nb) * (2 + (l & 1)) + (int)cb_.bypass_bits(nb, stream); }
+      if (xy) ly = l; else lx = l;
+    }
     int scan = 0;
     if (log2n == 2 || (log2n == 3 && c == 0)) { if (mode >= 6 && mode <= 14) scan = 2; else if (mode >= 22 && mode <= 30) scan = 1; }
     if (scan == 2) { const int t = lx; lx = ly; ly = t; }
@@ -386,21 +402,20 @@ struct Decoder {
       if ((x0 & 7) == 0 && x0 > 0 && (avail(x0 - 1, y0) || (sl.lf_across_slices && x0 - 1 >= 0))) left = 1;
       if ((y0 & 7) == 0 && y0 > 0 && (avail(x0, y0 - 1) || sl.lf_across_slices)) top = 2;
     }
-    B200_NOUNROLL for (int y = 0; y < n8; y++) B200_NOUNROLL for (int x = 0; x < n8; x++) {
-      const int i = (by + y) * sp->w8 + bx + x;
-      pb.qp8[i] = (int8_t)cur_qpy;
-      if (log2n >= 3) pb.edge8[i] = (uint8_t)((x == 0 ? left : 0) | (y == 0 ? top : 0));
-      else pb.edge8[i] |= (uint8_t)(left | top);
-    }
+    // the CTB's flags were cleared in decode_ctb: only the first column / row of 8x8 cells carries an edge.  (QpY of the
+    // cells is written once per coding unit, at its end.)
+    uint8_t* e = pb.edge8 + by * sp->w8 + bx;
+    if (left) B200_NOUNROLL for (int y = 0; y < n8; y++) e[y * sp->w8] |= left;
+    if (top) B200_NOUNROLL for (int x = 0; x < n8; x++) e[x] |= top;
   }
 
-  B200_HDN void transform_unit(const Cu& cu, int x0, int y0, int log2n, int blk, int cbf_l, int cbf_cb, int cbf_cr, int pcb, int pcr) {
+  B200_HDI void transform_unit(const Cu& cu, int x0, int y0, int log2n, int blk, int cbf_l, int cbf_cb, int cbf_cr, int pcb, int pcr) {
     const int cbf_c = sp->chroma ? (log2n > 2 ? (cbf_cb | cbf_cr) : (pcb | pcr)) : 0;
     if ((cbf_l || cbf_c) && sp->cu_qp_delta && !is_dqp_coded) {
       int v = 0;
-      B200_NOUNROLL while (v < 5 && cabac.bin(ctx[CTX_QP_DELTA + (v ? 1 : 0)], stream)) v++;
-      if (v == 5) { int k = 0; B200_NOUNROLL while (k < 16 && cabac.bypass(stream)) { v += 1 << k; k++; } v += (int)cabac.bypass_bits(k, stream); }
-      if (v && cabac.bypass(stream)) v = -v;
+      B200_NOUNROLL while (v < 5 && dbin(CTX_QP_DELTA + (v ? 1 : 0))) v++;
+      if (v == 5) { int k = 0; B200_NOUNROLL while (k < 16 && dbypass()) { v += 1 << k; k++; } v += (int)dbits(k); }
+      if (v && dbypass()) v = -v;
       is_dqp_coded = 1; dqp_val = v;
       derive_qpy(cu.x0, cu.y0);
     }
@@ -408,11 +423,19 @@ struct Decoder {
     const int lmode = cu.lmode[pu];
     const uint32_t coef0 = coef_n;
     int ts_l = 0, ts_cb = 0, ts_cr = 0, nl = 0, ncb = 0, ncr = 0;
-    if (cbf_l) nl = residual(log2n, 0, lmode, ts_l);
     int chroma_here = 0, ccb = 0, ccr = 0;
     if (sp->chroma) {
-      if (log2n > 2) { chroma_here = 1; ccb = cbf_cb; ccr = cbf_cr; if (ccb) ncb = residual(log2n - 1, 1, cu.cmode, ts_cb); if (ccr) ncr = residual(log2n - 1, 2, cu.cmode, ts_cr); }
-      else if (blk == 3) { chroma_here = 1; ccb = pcb; ccr = pcr; if (ccb) ncb = residual(2, 1, cu.cmode, ts_cb); if (ccr) ncr = residual(2, 2, cu.cmode, ts_cr); }
+      if (log2n > 2) { chroma_here = 1; ccb = cbf_cb; ccr = cbf_cr; }
+      else if (blk == 3) { chroma_here = 1; ccb = pcb; ccr = pcr; }      // 4x4 chroma blocks of the parent 8x8 node
+    }
+    // one residual_coding site serves the three components (it is inlined: call frames of a lone lane cost a 128-byte
+    // line of L1 per saved register)
+    B200_NOUNROLL for (int c = 0; c < 3; c++) {
+      const int coded = c == 0 ? cbf_l : (c == 1 ? ccb : ccr);
+      if (!coded) continue;
+      int ts = 0;
+      const int cnt = residual(c == 0 ? log2n : (log2n > 2 ? log2n - 1 : 2), c, c == 0 ? lmode : cu.cmode, ts);
+      if (c == 0) { nl = cnt; ts_l = ts; } else if (c == 1) { ncb = cnt; ts_cb = ts; } else { ncr = cnt; ts_cr = ts; }
     }
     mark_tu(x0, y0, log2n);
     if (tu_n >= tu_cap) { err = SYN_E_OVERFLOW; return; }
@@ -428,21 +451,26 @@ struct Decoder {
   B200_HDN void transform_tree(const Cu& cu, int x0, int y0, int log2n, int depth, int blk, int pcb, int pcr, int max_depth) {
     if (err) return;
     int split;
-    if (log2n <= sp->log2_max_tb && log2n > sp->log2_min_tb && depth < max_depth && !(cu.nxn && depth == 0)) split = cabac.bin(ctx[CTX_SPLIT_TR + 5 - log2n], stream);
+    if (log2n <= sp->log2_max_tb && log2n > sp->log2_min_tb && depth < max_depth && !(cu.nxn && depth == 0)) split = dbin(CTX_SPLIT_TR + 5 - log2n);
     else split = (log2n > sp->log2_max_tb || (cu.nxn && depth == 0)) ? 1 : 0;
     if (split && log2n <= 2) { err = SYN_E_BITSTREAM; return; }
     int cb = 0, cr = 0;
     if (sp->chroma) {
-      if (log2n > 2) { if (depth == 0 || pcb) cb = cabac.bin(ctx[CTX_CBF_CHROMA + depth], stream); if (depth == 0 || pcr) cr = cabac.bin(ctx[CTX_CBF_CHROMA + depth], stream); }
-      else { cb = pcb; cr = pcr; }
+      if (log2n > 2) {
+        B200_NOUNROLL for (int k = 0; k < 2; k++) {
+          int f = 0;
+          if (depth == 0 || (k ? pcr : pcb)) f = dbin(CTX_CBF_CHROMA + depth);
+          if (k) cr = f; else cb = f;
+        }
+      } else { cb = pcb; cr = pcr; }
     }
     if (split) {
       const int h = 1 << (log2n - 1);
       B200_NOUNROLL for (int k = 0; k < 4; k++) transform_tree(cu, x0 + (k & 1) * h, y0 + (k >> 1) * h, log2n - 1, depth + 1, k, cb, cr, max_depth);
     } else {
-      const int cl = cabac.bin(ctx[CTX_CBF_LUMA + (depth == 0 ? 1 : 0)], stream);
-      if (log2n > 2) transform_unit(cu, x0, y0, log2n, blk, cl, cb, cr, 0, 0);
-      else transform_unit(cu, x0, y0, log2n, blk, cl, 0, 0, pcb, pcr);
+      const int cl = dbin(CTX_CBF_LUMA + (depth == 0 ? 1 : 0));
+      const bool big = log2n > 2;
+      transform_unit(cu, x0, y0, log2n, blk, cl, big ? cb : 0, big ? cr : 0, big ? 0 : pcb, big ? 0 : pcr);
     }
   }
 
@@ -467,15 +495,15 @@ struct Decoder {
   }
 
   // -------- 7.3.8.5
-  B200_HDN void coding_unit(int x0, int y0, int log2cb, int depth) {
+  B200_HDI void coding_unit(int x0, int y0, int log2cb, int depth) {
     Cu cu; cu.x0 = x0; cu.y0 = y0; cu.log2cb = log2cb; cu.nxn = 0; cu.cmode = 0;
     const int n = 1 << log2cb;
-    if (log2cb == sp->log2_min_cb) cu.nxn = !cabac.bin(ctx[CTX_PART_MODE], stream);
+    if (log2cb == sp->log2_min_cb) cu.nxn = !dbin(CTX_PART_MODE);
     if (cu.nxn && log2cb == 3 && sp->log2_min_tb > 2) { err = SYN_E_BITSTREAM; return; }
     const int np = cu.nxn ? 4 : 1, pbs = cu.nxn ? n / 2 : n;
     int prev[4], mi[4] = {0, 0, 0, 0}, rem[4] = {0, 0, 0, 0};
-    B200_NOUNROLL for (int i = 0; i < np; i++) prev[i] = cabac.bin(ctx[CTX_PREV_INTRA], stream);
-    B200_NOUNROLL for (int i = 0; i < np; i++) { if (prev[i]) { mi[i] = cabac.bypass(stream); if (mi[i]) mi[i] += cabac.bypass(stream); } else rem[i] = (int)cabac.bypass_bits(5, stream); }
+    B200_NOUNROLL for (int i = 0; i < np; i++) prev[i] = dbin(CTX_PREV_INTRA);
+    B200_NOUNROLL for (int i = 0; i < np; i++) { if (prev[i]) { mi[i] = dbypass(); if (mi[i]) mi[i] += dbypass(); } else rem[i] = (int)dbits(5); }
     B200_NOUNROLL for (int i = 0; i < np; i++) {
       const int px = x0 + (i & 1) * pbs, py = y0 + (i >> 1) * pbs;
       const int m = luma_mode(px, py, prev[i], mi[i], rem[i]);
@@ -483,7 +511,7 @@ struct Decoder {
       B200_NOUNROLL for (int yy = 0; yy < pbs; yy += 4) B200_NOUNROLL for (int xx = 0; xx < pbs; xx += 4) pb.ipm4[((py + yy) >> 2) * sp->w4 + ((px + xx) >> 2)] = (uint8_t)m;
     }
     if (sp->chroma) {
-      int v = 4; if (cabac.bin(ctx[CTX_CHROMA_PRED], stream)) v = (int)cabac.bypass_bits(2, stream);
+      int v = 4; if (dbin(CTX_CHROMA_PRED)) v = (int)dbits(2);
       if (v == 4) cu.cmode = cu.lmode[0]; else { cu.cmode = B200_T(kChromaTab)[v]; if (cu.cmode == cu.lmode[0]) cu.cmode = 34; }
     }
     B200_NOUNROLL for (int yy = 0; yy < n; yy += 8) B200_NOUNROLL for (int xx = 0; xx < n; xx += 8) pb.cd8[((y0 + yy) >> 3) * sp->w8 + ((x0 + xx) >> 3)] = (uint8_t)depth;
@@ -502,7 +530,7 @@ struct Decoder {
       int inc = 0;
       if (avail(x0 - 1, y0) && B200_LD_SHARED(pb.cd8 + (y0 >> 3) * sp->w8 + ((x0 - 1) >> 3)) > depth) inc++;
       if (avail(x0, y0 - 1) && B200_LD_SHARED(pb.cd8 + ((y0 - 1) >> 3) * sp->w8 + (x0 >> 3)) > depth) inc++;
-      split = cabac.bin(ctx[CTX_SPLIT_CU + inc], stream);
+      split = dbin(CTX_SPLIT_CU + inc);
     } else split = log2cb > sp->log2_min_cb;
     if (sp->cu_qp_delta && log2cb >= sp->qg_log2) {
       is_dqp_coded = 0; dqp_val = 0;
@@ -535,9 +563,11 @@ struct Decoder {
 // Decodes one sub-stream.  `Sync` supplies wait_row(row, need) -- block until `need` CTBs of CTB row `row` are done --
 // publish_row(row, done) and wait_substream(index); on the host (sequential order) they are no-ops.
 template <class Sync>
-B200_HD int run_substream(const SeqParams& sp, const PicBuffers& pb, const Substream* all, int index, uint8_t* ctx, Sync& sync) {
+// `d` is caller-provided storage: on the device it lives in SHARED memory -- a lone lane's local memory uses 4 bytes of
+// every 128-byte line, so ~30 resident decoders with their state on the stack overflow L1 (measured: the SM's
+// throughput stopped growing at 8 warps).
+B200_HD int run_substream(Decoder& d, const SeqParams& sp, const PicBuffers& pb, const Substream* all, int index, uint8_t* ctx, Sync& sync) {
   const Substream& ss = all[index];
-  Decoder d;
   d.sp = &sp; d.pb = pb; d.ss = &ss; d.ctx = ctx; d.err = SYN_OK;
   d.is_dqp_coded = 0; d.dqp_val = 0; d.qpy_prev_qg = ss.slice_qp; d.last_cu_qpy = ss.slice_qp; d.first_qg = 1; d.cur_qpy = ss.slice_qp;
   d.tu_n = 0; d.coef_n = 0; d.tu_cap = 0; d.coef_cap = 0;
