@@ -37,7 +37,6 @@ __shared__ uint8_t s_kScanY[4][3][64];
 namespace b200 {
 
 constexpr int EWARPS = 4;
-constexpr int ELANES_MAX = 4;     // decoders per warp (diverged lanes, independent thread scheduling); experiment knob B200_ENTROPY_LANES
 
 // Polling load: relaxed + gpu scope (served by L2).  ld.acquire would make ptxas emit CCTL.IVALL -- an SM-wide L1 invalidation --
 // on EVERY poll (measured: 43 % of all stall samples of the first version); ordering is obtained instead by reading every
@@ -56,7 +55,7 @@ struct DevSync {
   uint32_t dense_tu, dense_coef, dense_tu_cap, dense_coef_cap;   // unused on the device (fixed slots)
   uint64_t end_bit_position;
   // A CTB takes ~0.5 ms: back off to microseconds so thousands of waiting warps do not flood L2 with polls.  Gives up
-  // (error 3) after 20 s of wall time -- only a lost producer can cause that.
+  // (error 3) after 60 s of wall time -- only a lost producer can cause that.
   __device__ static void spin_until(const unsigned* p, unsigned need, unsigned* error_flag) {
     if (e_ld_acquire(p) >= need) return;
     unsigned long long t0; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
@@ -64,8 +63,9 @@ struct DevSync {
     for (;;) {
       __nanosleep(ns); if (ns < 4000) ns <<= 1;
       if (e_ld_acquire(p) >= need) return;
+      if (e_ld_acquire(error_flag)) return;              // a producer failed: do not wait for progress that will never come
       unsigned long long t1; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
-      if (t1 - t0 > 20000000000ull) { atomicExch(error_flag, 3u); return; }
+      if (t1 - t0 > 60000000000ull) { atomicExch(error_flag, 3u); return; }
     }
   }
   __device__ void wait_row(int row, int need) { spin_until(progress + row, (unsigned)need, error_flag); }
@@ -77,9 +77,12 @@ struct DevSync {
   }
 };
 
-__global__ void __launch_bounds__(EWARPS * 32) hevc_entropy_kernel(const EntropyBatch b, const int lanes) {
-  __shared__ uint8_t s_ctx[EWARPS * ELANES_MAX][syn::CTX_STRIDE];
-  __shared__ syn::Decoder s_dec[EWARPS * ELANES_MAX];                    // per-warp decoder state (see run_substream)
+#ifndef B200_ENTROPY_MIN_BLOCKS
+#define B200_ENTROPY_MIN_BLOCKS 1
+#endif
+__global__ void __launch_bounds__(EWARPS * 32, B200_ENTROPY_MIN_BLOCKS) hevc_entropy_kernel(const EntropyBatch b) {
+  __shared__ uint8_t s_ctx[EWARPS][syn::CTX_STRIDE];
+  __shared__ syn::Decoder s_dec[EWARPS];                    // per-warp decoder state (see run_substream)
   for (int i = threadIdx.x; i < 64; i += blockDim.x) { syn::s_kLps4[i] = syn::d_kLps4[i]; syn::s_kTransLps[i] = syn::d_kTransLps[i]; }
   for (int i = threadIdx.x; i < 134; i += blockDim.x) syn::s_kInitI[i] = syn::d_kInitI[i];
   for (int i = threadIdx.x; i < 256; i += blockDim.x) syn::s_kNextState[i] = syn::d_kNextState[i];
@@ -90,8 +93,10 @@ __global__ void __launch_bounds__(EWARPS * 32) hevc_entropy_kernel(const Entropy
   for (int i = threadIdx.x; i < 4; i += blockDim.x) syn::s_kChromaTab[i] = syn::d_kChromaTab[i];
   for (int i = threadIdx.x; i < 4 * 3 * 64; i += blockDim.x) { (&syn::s_kScanX[0][0][0])[i] = (&syn::d_kScanX[0][0][0])[i]; (&syn::s_kScanY[0][0][0])[i] = (&syn::d_kScanY[0][0][0])[i]; }
   __syncthreads();
-  if ((int)(threadIdx.x & 31) >= lanes) return;             // CABAC is serial per sub-stream: `lanes` independent decoders per warp
-  const int slot = (threadIdx.x >> 5) * ELANES_MAX + (threadIdx.x & 31);
+  // Lane 0 of every warp decodes: CABAC is serial per sub-stream.  (Several decoders per warp on diverged lanes were
+  // measured 25-70 % slower: the diverged paths of one warp serialise.)
+  if ((threadIdx.x & 31) != 0) return;
+  const int slot = threadIdx.x >> 5;
   uint8_t* ctx = s_ctx[slot];
   for (;;) {
     const unsigned t = atomicAdd(b.ticket, 1u);
@@ -121,17 +126,13 @@ __global__ void entropy_stats_kernel(const EntropyBatch b, unsigned long long* o
 
 int launch_entropy(const EntropyBatch& b, cudaStream_t s) {
   if (b.nsubs <= 0) return B200_OK;
-  static bool limit_set = false;
-  if (!limit_set) { cudaDeviceSetLimit(cudaLimitStackSize, 8192); limit_set = true; }   // recursion of the quadtree / transform tree
   int dev = 0, sms = 148; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   int occ = 1; cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, hevc_entropy_kernel, EWARPS * 32, 0);
   if (occ < 1) occ = 1;
   if (const char* e = getenv("B200_ENTROPY_BLOCKS_PER_SM")) { const int v = atoi(e); if (v >= 1 && v < occ) occ = v; }   // tuning knob
-  int lanes = 1;
-  if (const char* e = getenv("B200_ENTROPY_LANES")) { const int v = atoi(e); if (v >= 1 && v <= ELANES_MAX) lanes = v; }
-  const int want = (b.nsubs + EWARPS * lanes - 1) / (EWARPS * lanes);
+  const int want = (b.nsubs + EWARPS - 1) / EWARPS;
   const int grid = want < sms * occ ? want : sms * occ;
-  hevc_entropy_kernel<<<grid, EWARPS * 32, 0, s>>>(b, lanes);
+  hevc_entropy_kernel<<<grid, EWARPS * 32, 0, s>>>(b);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return set_error(B200_E_CUDA, "entropy launch: %s", cudaGetErrorString(e));
   return B200_OK;

@@ -448,29 +448,46 @@ struct Decoder {
     pb.tus[tu_n++] = t;
   }
 
-  B200_HDN void transform_tree(const Cu& cu, int x0, int y0, int log2n, int depth, int blk, int pcb, int pcr, int max_depth) {
-    if (err) return;
-    int split;
-    if (log2n <= sp->log2_max_tb && log2n > sp->log2_min_tb && depth < max_depth && !(cu.nxn && depth == 0)) split = dbin(CTX_SPLIT_TR + 5 - log2n);
-    else split = (log2n > sp->log2_max_tb || (cu.nxn && depth == 0)) ? 1 : 0;
-    if (split && log2n <= 2) { err = SYN_E_BITSTREAM; return; }
-    int cb = 0, cr = 0;
-    if (sp->chroma) {
-      if (log2n > 2) {
-        B200_NOUNROLL for (int k = 0; k < 2; k++) {
-          int f = 0;
-          if (depth == 0 || (k ? pcr : pcb)) f = dbin(CTX_CBF_CHROMA + depth);
-          if (k) cr = f; else cb = f;
+  // z-order index -> (x, y): even bits / odd bits compacted (indices < 256)
+  B200_HD static inline int zx(unsigned i) { i &= 0x55u; i = (i | (i >> 1)) & 0x33u; i = (i | (i >> 2)) & 0x0fu; return (int)i; }
+  // depth of the largest quadtree node that STARTS at z-order unit i (levels = depth of a single unit)
+  B200_HD static inline int node_depth(unsigned i, int levels) { const int up = i ? lo_bit(i) >> 1 : levels; return levels - imin(up, levels); }
+
+  // transform_tree (7.3.8.8) without recursion: the tree of one coding unit is walked in z-order over 4x4 units; a node
+  // is entered at the coarsest depth aligned to the current unit, split flags descend, leaves advance.  (Recursion costs
+  // a lone lane one 128-byte line of L1 per saved register and frame level; see run_substream.)
+  B200_HDI void transform_tree(const Cu& cu, int max_depth) {
+    const int levels = cu.log2cb - 2, total = 1 << (2 * levels);
+    unsigned cbm = 0, crm = 0;                          // cbf_cb / cbf_cr of the node on the current path, bit = depth
+    B200_NOUNROLL for (int j = 0; j < total && !err;) {
+      int depth = node_depth((unsigned)j, levels);
+      B200_NOUNROLL for (;;) {
+        const int log2n = cu.log2cb - depth;
+        const int x0 = cu.x0 + (zx((unsigned)j) << 2), y0 = cu.y0 + (zx((unsigned)j >> 1) << 2);
+        const int blk = depth ? (j >> (2 * (levels - depth))) & 3 : 0;
+        const int pcb = depth ? (int)((cbm >> (depth - 1)) & 1) : 0, pcr = depth ? (int)((crm >> (depth - 1)) & 1) : 0;
+        int split;
+        if (log2n <= sp->log2_max_tb && log2n > sp->log2_min_tb && depth < max_depth && !(cu.nxn && depth == 0)) split = dbin(CTX_SPLIT_TR + 5 - log2n);
+        else split = (log2n > sp->log2_max_tb || (cu.nxn && depth == 0)) ? 1 : 0;
+        if (split && log2n <= 2) { err = SYN_E_BITSTREAM; break; }
+        int cb = 0, cr = 0;
+        if (sp->chroma) {
+          if (log2n > 2) {
+            B200_NOUNROLL for (int k = 0; k < 2; k++) {
+              int f = 0;
+              if (depth == 0 || (k ? pcr : pcb)) f = dbin(CTX_CBF_CHROMA + depth);
+              if (k) cr = f; else cb = f;
+            }
+          } else { cb = pcb; cr = pcr; }
         }
-      } else { cb = pcb; cr = pcr; }
-    }
-    if (split) {
-      const int h = 1 << (log2n - 1);
-      B200_NOUNROLL for (int k = 0; k < 4; k++) transform_tree(cu, x0 + (k & 1) * h, y0 + (k >> 1) * h, log2n - 1, depth + 1, k, cb, cr, max_depth);
-    } else {
-      const int cl = dbin(CTX_CBF_LUMA + (depth == 0 ? 1 : 0));
-      const bool big = log2n > 2;
-      transform_unit(cu, x0, y0, log2n, blk, cl, big ? cb : 0, big ? cr : 0, big ? 0 : pcb, big ? 0 : pcr);
+        cbm = (cbm & ~(1u << depth)) | ((unsigned)cb << depth); crm = (crm & ~(1u << depth)) | ((unsigned)cr << depth);
+        if (split) { depth++; continue; }               // the first child starts at the same unit
+        const int cl = dbin(CTX_CBF_LUMA + (depth == 0 ? 1 : 0));
+        const bool big = log2n > 2;
+        transform_unit(cu, x0, y0, log2n, blk, cl, big ? cb : 0, big ? cr : 0, big ? 0 : pcb, big ? 0 : pcr);
+        j += 1 << (2 * (levels - depth));
+        break;
+      }
     }
   }
 
@@ -516,30 +533,38 @@ struct Decoder {
     }
     B200_NOUNROLL for (int yy = 0; yy < n; yy += 8) B200_NOUNROLL for (int xx = 0; xx < n; xx += 8) pb.cd8[((y0 + yy) >> 3) * sp->w8 + ((x0 + xx) >> 3)] = (uint8_t)depth;
     if (!sp->cu_qp_delta) cur_qpy = ss->slice_qp; else derive_qpy(x0, y0);
-    transform_tree(cu, x0, y0, log2cb, 0, 0, 0, 0, sp->max_th_depth_intra + cu.nxn);
+    transform_tree(cu, sp->max_th_depth_intra + cu.nxn);
     B200_NOUNROLL for (int yy = 0; yy < n; yy += 8) B200_NOUNROLL for (int xx = 0; xx < n; xx += 8) pb.qp8[((y0 + yy) >> 3) * sp->w8 + ((x0 + xx) >> 3)] = (int8_t)cur_qpy;
     last_cu_qpy = cur_qpy;
   }
 
   // -------- 7.3.8.4
-  B200_HDN void coding_quadtree(int x0, int y0, int log2cb, int depth) {
-    if (err) return;
-    const int n = 1 << log2cb;
-    int split;
-    if (x0 + n <= sp->W && y0 + n <= sp->H && log2cb > sp->log2_min_cb) {
-      int inc = 0;
-      if (avail(x0 - 1, y0) && B200_LD_SHARED(pb.cd8 + (y0 >> 3) * sp->w8 + ((x0 - 1) >> 3)) > depth) inc++;
-      if (avail(x0, y0 - 1) && B200_LD_SHARED(pb.cd8 + ((y0 - 1) >> 3) * sp->w8 + (x0 >> 3)) > depth) inc++;
-      split = dbin(CTX_SPLIT_CU + inc);
-    } else split = log2cb > sp->log2_min_cb;
-    if (sp->cu_qp_delta && log2cb >= sp->qg_log2) {
-      is_dqp_coded = 0; dqp_val = 0;
-      if (!split || log2cb == sp->qg_log2) { if (first_qg) { qpy_prev_qg = ss->slice_qp; first_qg = 0; } else qpy_prev_qg = last_cu_qpy; }
+  // coding_quadtree (7.3.8.4) of one CTB, iteratively over minimum coding blocks in z-order (same walk as transform_tree)
+  B200_HDI void coding_quadtree(int xc, int yc) {
+    const int log2min = sp->log2_min_cb, levels = sp->log2ctb - log2min, total = 1 << (2 * levels);
+    B200_NOUNROLL for (int i = 0; i < total && !err;) {
+      int depth = node_depth((unsigned)i, levels);
+      B200_NOUNROLL for (;;) {
+        const int log2cb = sp->log2ctb - depth, n = 1 << log2cb;
+        const int x0 = xc + (zx((unsigned)i) << log2min), y0 = yc + (zx((unsigned)i >> 1) << log2min);
+        if (x0 >= sp->W || y0 >= sp->H) { i += 1 << (2 * (levels - depth)); break; }      // node outside the picture: not coded
+        int split;
+        if (x0 + n <= sp->W && y0 + n <= sp->H && log2cb > log2min) {
+          int inc = 0;
+          if (avail(x0 - 1, y0) && B200_LD_SHARED(pb.cd8 + (y0 >> 3) * sp->w8 + ((x0 - 1) >> 3)) > depth) inc++;
+          if (avail(x0, y0 - 1) && B200_LD_SHARED(pb.cd8 + ((y0 - 1) >> 3) * sp->w8 + (x0 >> 3)) > depth) inc++;
+          split = dbin(CTX_SPLIT_CU + inc);
+        } else split = log2cb > log2min;
+        if (sp->cu_qp_delta && log2cb >= sp->qg_log2) {
+          is_dqp_coded = 0; dqp_val = 0;
+          if (!split || log2cb == sp->qg_log2) { if (first_qg) { qpy_prev_qg = ss->slice_qp; first_qg = 0; } else qpy_prev_qg = last_cu_qpy; }
+        }
+        if (split) { depth++; continue; }
+        coding_unit(x0, y0, log2cb, depth);
+        i += 1 << (2 * (levels - depth));
+        break;
+      }
     }
-    if (split) {
-      const int h = n >> 1;
-      B200_NOUNROLL for (int k = 0; k < 4; k++) { const int x1 = x0 + (k & 1) * h, y1 = y0 + (k >> 1) * h; if (x1 < sp->W && y1 < sp->H) coding_quadtree(x1, y1, log2cb - 1, depth + 1); }
-    } else coding_unit(x0, y0, log2cb, depth);
   }
 
   // One coding tree unit (7.3.8.2): SAO syntax + coding quadtree; fills its CtuInfo.
@@ -555,7 +580,7 @@ struct Decoder {
     // 4x4 luma transform units only OR their edge bits: clear this CTB's flags first
     { const int b0x = rx << (sp->log2ctb - 3), b0y = ry << (sp->log2ctb - 3), nb = 1 << (sp->log2ctb - 3);
       B200_NOUNROLL for (int y = 0; y < nb && b0y + y < sp->h8; y++) B200_NOUNROLL for (int x = 0; x < nb && b0x + x < sp->w8; x++) pb.edge8[(b0y + y) * sp->w8 + b0x + x] = 0; }
-    coding_quadtree(rx << sp->log2ctb, ry << sp->log2ctb, sp->log2ctb, 0);
+    coding_quadtree(rx << sp->log2ctb, ry << sp->log2ctb);
     ci.tu_start = t0; ci.tu_count = (uint16_t)(tu_n - t0);
   }
 };
