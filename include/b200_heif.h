@@ -98,6 +98,29 @@ int b200_color_convert_host(const b200_planes* in, const b200_geometry* geom, co
 void b200_ycbcr_to_rgb_coefficients(int matrix_coefficients, int colour_primaries, float out_coeffs[4] /* r_cr,g_cb,g_cr,b_cb */);
 
 /* ------------------------------------------------------------------------------------------------
+ * Overlay compositing and nearest-neighbour plane scaling (a12).  Device -> device.
+ * Replaces: HeifPixelImage::fill_RGB_16bit           libheif/image/pixelimage.cc:1549-1621
+ *           HeifPixelImage::overlay                  libheif/image/pixelimage.cc:1637-1780
+ *           (driven by ImageItem_Overlay::decode_overlay_image, libheif/image-items/overlay.cc:290-393: an 8-bit planar
+ *            RGB 4:4:4 canvas filled with background >> 8, children converted to planar RGB 4:4:4 -- use
+ *            b200_color_convert_device with out_chroma = B200_CHROMA_444 -- and composited in 'iovl' order)
+ *           HeifPixelImage::scale_nearest_neighbor   libheif/image/pixelimage.cc:1783-1972
+ * The overlay reproduces the reference's arithmetic (in*a + out*(255-a)) / 255 and its clipping, including the loop
+ * bounds it uses for negative offsets (fewer rows / columns are drawn than overlap; see oracle/color_oracle.c).
+ * ------------------------------------------------------------------------------------------------ */
+/* planes R,G,B of width x height bytes: every sample = background_rgba[c] >> 8 */
+int b200_overlay_fill_device(void* const planes[3], const size_t strides[3], int width, int height, const uint16_t background_rgba[4], void* stream);
+/* overlay[3] = alpha plane of the child or NULL (opaque copy).  An overlay entirely outside the canvas draws nothing and
+   is not an error (overlay.cc:372-379). */
+int b200_overlay_device(void* const canvas[3], const size_t canvas_strides[3], int canvas_w, int canvas_h, const void* const overlay[4],
+                        const size_t overlay_strides[4], int overlay_w, int overlay_h, int32_t dx, int32_t dy, void* stream);
+/* One plane: out[y][x] = in[y * image_h_in / image_h_out][x * image_w_in / image_w_out] for x < out_w, y < out_h, with the
+   IMAGE sizes in the index arithmetic also for subsampled planes (as the reference does); bytes_per_pixel = interleaved
+   components x bytes per sample (1, 2, 3, 4, 6 or 8).  The caller loops over the planes like pixelimage.cc:1917. */
+int b200_scale_nearest_device(const void* in, size_t in_stride, void* out, size_t out_stride, uint32_t out_w, uint32_t out_h,
+                              uint32_t image_w_in, uint32_t image_h_in, uint32_t image_w_out, uint32_t image_h_out, int bytes_per_pixel, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
  * HEVC intra encoder (host): produces the synthetic inputs of BASELINE configs 2-5 and backs the
  * heif_encoder_plugin (libheif/api/libheif/heif_plugin.h:192-313) exported by this library.
  * Role of: x265 behind libheif/plugins/encoder_x265.cc:752-1051 (encode_image) and :1186-1244

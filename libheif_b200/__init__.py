@@ -11,3 +11,4 @@ from .color import (Geometry, YCbCrImage, convert_colorspace, convert_colorspace
                     CHROMA_INTERLEAVED_RRGGBBAA_LE)
 from .decoder import Decoder, ImageInfo, DecodeStats  # noqa: F401,E402
 from . import hevc_enc  # noqa: F401,E402
+from . import compose  # noqa: F401,E402

@@ -158,3 +158,66 @@ def oracle_postprocess(y, cb, cr, a, chroma, bpp, nclx, ops, out_chroma, bilinea
     if n < 0:
         raise RuntimeError("co_postprocess failed")
     return out[:n].copy(), ow.value, oh.value
+
+
+# ---- a11 / a12: overlay and nearest-neighbour scaling -----------------------------------------------------------------
+def ref_overlay(cw, ch, bkg, children):
+    """UNMODIFIED reference: fill_RGB_16bit + HeifPixelImage::overlay per child. children = [(rgb(3,h,w) u8, alpha(h,w) u8 or None, dx, dy)]."""
+    pl = ref_plugin()
+    n = len(children)
+    packed = []
+    for rgb, al, _, _ in children:
+        parts = [np.ascontiguousarray(rgb, dtype=np.uint8).reshape(-1)]
+        if al is not None:
+            parts.append(np.ascontiguousarray(al, dtype=np.uint8).reshape(-1))
+        packed.append(np.concatenate(parts))
+    ptrs = (C.c_void_p * max(1, n))(*[p.ctypes.data_as(C.c_void_p) for p in packed])
+    arr = lambda vals: (C.c_int * max(1, n))(*vals)
+    out = np.empty(3 * cw * ch, dtype=np.uint8)
+    b = (C.c_uint16 * 4)(*bkg)
+    rc = pl.ref_overlay(cw, ch, b, n, ptrs, arr([c[0].shape[2] for c in children]), arr([c[0].shape[1] for c in children]),
+                        arr([0 if c[1] is None else 1 for c in children]), arr([c[2] for c in children]), arr([c[3] for c in children]),
+                        out.ctypes.data_as(C.c_void_p))
+    if rc != 0:
+        raise RuntimeError(f"ref_overlay rc={rc}")
+    return out.reshape(3, ch, cw)
+
+
+def oracle_overlay(cw, ch, bkg, children):
+    """C restatement (oracle/color_oracle.c: co_fill_rgb16 + co_overlay)."""
+    l = lib()
+    canvas = np.empty(3 * cw * ch, dtype=np.uint8)
+    l.co_fill_rgb16(canvas.ctypes.data_as(C.c_void_p), cw, ch, (C.c_uint16 * 4)(*bkg))
+    for rgb, al, dx, dy in children:
+        parts = [np.ascontiguousarray(rgb, dtype=np.uint8).reshape(-1)]
+        if al is not None:
+            parts.append(np.ascontiguousarray(al, dtype=np.uint8).reshape(-1))
+        ov = np.concatenate(parts)
+        l.co_overlay(canvas.ctypes.data_as(C.c_void_p), cw, ch, ov.ctypes.data_as(C.c_void_p), rgb.shape[2], rgb.shape[1], 0 if al is None else 1,
+                     C.c_int32(dx), C.c_int32(dy))
+    return canvas.reshape(3, ch, cw)
+
+
+def ref_scale_nn(colorspace, chroma, bpp, planes, w, h, ow, oh, has_alpha=False):
+    """UNMODIFIED reference scale_nearest_neighbor. planes: list of 2-D arrays in channel order (+ alpha last). Returns the packed output bytes."""
+    pl = ref_plugin()
+    dt = np.uint8 if bpp <= 8 else np.uint16
+    packed = np.concatenate([np.ascontiguousarray(p, dtype=dt).reshape(-1).view(np.uint8) for p in planes])
+    cap = (ow + 8) * (oh + 8) * 8 * (len(planes) + 1)
+    out = np.empty(cap, dtype=np.uint8)
+    n = pl.ref_scale_nn(colorspace, chroma, bpp, int(has_alpha), w, h, ow, oh, packed.ctypes.data_as(C.c_void_p), out.ctypes.data_as(C.c_void_p), C.c_size_t(cap))
+    if n < 0:
+        raise RuntimeError(f"ref_scale_nn rc={n}")
+    return out[:n].copy()
+
+
+def oracle_scale_plane(plane, out_w, out_h, image_in, image_out, comps=1):
+    """C restatement of one plane of scale_nearest_neighbor (co_scale_nearest_plane). plane: (h, w*comps) u8/u16."""
+    l = lib()
+    p = np.ascontiguousarray(plane)
+    bps = p.dtype.itemsize
+    out = np.empty((out_h, out_w * comps), dtype=p.dtype)
+    l.co_scale_nearest_plane(p.ctypes.data_as(C.c_void_p), C.c_size_t(p.shape[1] * bps), out.ctypes.data_as(C.c_void_p), C.c_size_t(out_w * comps * bps),
+                             C.c_uint32(out_w), C.c_uint32(out_h), C.c_uint32(image_in[0]), C.c_uint32(image_in[1]), C.c_uint32(image_out[0]), C.c_uint32(image_out[1]),
+                             comps, bps)
+    return out

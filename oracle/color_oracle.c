@@ -243,3 +243,58 @@ long co_postprocess(const uint16_t* y, const uint16_t* cb, const uint16_t* cr, c
                     uint8_t* out, int* out_w, int* out_h) {
   return co_postprocess2(y, cb, cr, alpha, w, h, chroma, bpp, cp, mc, full_range, ops, nops, out_chroma, 0, out, out_w, out_h);
 }
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * a11: overlay compositing, restated from HeifPixelImage::fill_RGB_16bit (libheif/image/pixelimage.cc:1549-1621) and
+ * HeifPixelImage::overlay (pixelimage.cc:1637-1780), including the loop bounds of the original: after clipping against
+ * the left / top canvas border the copy loops run `for (y = in_y0; y < in_h - in_y0; ...)` and, on the alpha path,
+ * `for (x = in_x0; x < in_w - in_x0; ...)` with x added to BOTH the source offset in_x0 and the destination offset.
+ * Planes are packed 8-bit, w bytes per row.
+ * ------------------------------------------------------------------------------------------------------------------ */
+void co_fill_rgb16(uint8_t* canvas /* 3 planes */, int cw, int ch, const uint16_t bkg[4]) {
+  for (int c = 0; c < 3; c++) memset(canvas + (size_t)c * cw * ch, (uint8_t)(bkg[c] >> 8), (size_t)cw * ch);
+}
+
+static uint32_t co_negate(int32_t x) { return x == INT32_MIN ? (uint32_t)INT32_MAX + 1u : (uint32_t)(-x); }
+
+void co_overlay(uint8_t* canvas /* R,G,B */, int cw, int ch, const uint8_t* ov /* R,G,B[,A] */, int ow_, int oh_, int has_alpha, int32_t dx, int32_t dy) {
+  const uint8_t* alpha_p = has_alpha ? ov + (size_t)3 * ow_ * oh_ : NULL;
+  for (int c = 0; c < 3; c++) {                      /* the canvas of decode_overlay_image has no alpha plane (overlay.cc:312-322) */
+    const uint8_t* in_p = ov + (size_t)c * ow_ * oh_;
+    uint8_t* out_p = canvas + (size_t)c * cw * ch;
+    uint32_t in_w = (uint32_t)ow_, in_h = (uint32_t)oh_;
+    const uint32_t out_w = (uint32_t)cw, out_h = (uint32_t)ch;
+    const size_t in_stride = (size_t)ow_, out_stride = (size_t)cw, alpha_stride = (size_t)ow_;
+    if (dx > 0 && (uint32_t)dx >= out_w) return;
+    else if (dx < 0 && in_w <= co_negate(dx)) return;
+    if (dy > 0 && (uint32_t)dy >= out_h) return;
+    else if (dy < 0 && in_h <= co_negate(dy)) return;
+    uint32_t in_x0, in_y0, out_x0, out_y0;
+    if (dx + (int64_t)in_w > out_w) in_w = (uint32_t)((int64_t)out_w - dx);
+    if (dy + (int64_t)in_h > out_h) in_h = (uint32_t)((int64_t)out_h - dy);
+    if (dx < 0) { in_x0 = co_negate(dx); out_x0 = 0; in_w = in_w - in_x0; } else { in_x0 = 0; out_x0 = (uint32_t)dx; }
+    if (dy < 0) { in_y0 = co_negate(dy); out_y0 = 0; in_h = in_h - in_y0; } else { in_y0 = 0; out_y0 = (uint32_t)dy; }
+    for (uint32_t y = in_y0; y < in_h; y++) {
+      if (!has_alpha) memcpy(out_p + out_x0 + (out_y0 + y - in_y0) * out_stride, in_p + in_x0 + y * in_stride, in_w);
+      else for (uint32_t x = in_x0; x < in_w; x++) {
+        uint8_t* outptr = &out_p[out_x0 + (out_y0 + y - in_y0) * out_stride + x];
+        const uint8_t in_val = in_p[in_x0 + y * in_stride + x];
+        const uint8_t alpha_val = alpha_p[in_x0 + y * alpha_stride + x];
+        *outptr = (uint8_t)((in_val * alpha_val + *outptr * (255 - alpha_val)) / 255);
+      }
+    }
+  }
+}
+
+/* a12: HeifPixelImage::scale_nearest_neighbor (pixelimage.cc:1783-1972) for ONE plane: the source index is derived from
+ * the IMAGE sizes (m_width / width), also for subsampled chroma planes; `comps` interleaved samples of `bps` bytes. */
+void co_scale_nearest_plane(const uint8_t* in, size_t in_stride, uint8_t* out, size_t out_stride, uint32_t out_w, uint32_t out_h,
+                            uint32_t img_w_in, uint32_t img_h_in, uint32_t img_w_out, uint32_t img_h_out, int comps, int bps) {
+  for (uint32_t y = 0; y < out_h; y++) {
+    const uint32_t iy = (uint32_t)((uint64_t)y * img_h_in / img_h_out);
+    for (uint32_t x = 0; x < out_w; x++) {
+      const uint32_t ix = (uint32_t)((uint64_t)x * img_w_in / img_w_out);
+      memcpy(out + y * out_stride + (size_t)x * comps * bps, in + iy * in_stride + (size_t)ix * comps * bps, (size_t)comps * bps);
+    }
+  }
+}

@@ -190,3 +190,72 @@ extern "C" int ref_postprocess(const void* y, const void* cb, const void* cr, co
   }
   return 0;
 }
+
+// ---- a11 / a12: the reference's own overlay compositing and nearest-neighbour scaler, driven on caller-provided planes.
+// Packed 8-bit planes R,G,B[,A] (row-major, w bytes per row) in, canvas planes R,G,B out.
+extern "C" int ref_overlay(int cw, int ch, const uint16_t bkg[4], int noverlays, const uint8_t* const* ov_data, const int* ov_w, const int* ov_h,
+                           const int* ov_alpha, const int* dx, const int* dy, uint8_t* out /* 3 * cw * ch */) {
+  const heif_security_limits* limits = heif_get_global_security_limits();
+  auto img = std::make_shared<HeifPixelImage>();
+  img->create(cw, ch, heif_colorspace_RGB, heif_chroma_444);
+  for (heif_channel c : {heif_channel_R, heif_channel_G, heif_channel_B}) if (img->add_channel(c, cw, ch, 8, limits)) return -1;
+  if (img->fill_RGB_16bit(bkg[0], bkg[1], bkg[2], bkg[3])) return -2;
+  for (int i = 0; i < noverlays; i++) {
+    auto ov = std::make_shared<HeifPixelImage>();
+    ov->create(ov_w[i], ov_h[i], heif_colorspace_RGB, heif_chroma_444);
+    const heif_channel chans[4] = {heif_channel_R, heif_channel_G, heif_channel_B, heif_channel_Alpha};
+    const int n = ov_alpha[i] ? 4 : 3;
+    for (int k = 0; k < n; k++) {
+      if (ov->add_channel(chans[k], ov_w[i], ov_h[i], 8, limits)) return -3;
+      size_t stride; uint8_t* dst = ov->get_channel_memory(chans[k], &stride);
+      const uint8_t* src = ov_data[i] + (size_t)k * ov_w[i] * ov_h[i];
+      for (int r = 0; r < ov_h[i]; r++) memcpy(dst + r * stride, src + (size_t)r * ov_w[i], (size_t)ov_w[i]);
+    }
+    Error e = img->overlay(ov, dx[i], dy[i]);
+    if (e && !(e.error_code == heif_error_Invalid_input && e.sub_error_code == heif_suberror_Overlay_image_outside_of_canvas)) return -4;
+  }
+  size_t pos = 0;
+  for (heif_channel c : {heif_channel_R, heif_channel_G, heif_channel_B}) {
+    size_t stride; const uint8_t* src = img->get_channel_memory(c, &stride);
+    for (int r = 0; r < ch; r++) { memcpy(out + pos, src + r * stride, (size_t)cw); pos += (size_t)cw; }
+  }
+  return 0;
+}
+
+// planes: colorspace 0 = YCbCr (chroma 1/2/3), 1 = RGB planar 4:4:4, 2 = monochrome, 3 = interleaved (chroma = heif_chroma_interleaved_*);
+// samples uint8 (bpp <= 8) or uint16.  `in` / `out` hold the planes packed one after the other (Y,Cb,Cr | R,G,B | Y | interleaved, then alpha).
+extern "C" int ref_scale_nn(int colorspace, int chroma, int bpp, int has_alpha, int w, int h, int ow, int oh, const uint8_t* in, uint8_t* out, size_t out_capacity) {
+  const heif_security_limits* limits = heif_get_global_security_limits();
+  auto img = std::make_shared<HeifPixelImage>();
+  const heif_colorspace cs = colorspace == 0 ? heif_colorspace_YCbCr : colorspace == 2 ? heif_colorspace_monochrome : heif_colorspace_RGB;
+  img->create(w, h, cs, (heif_chroma)chroma);
+  std::vector<heif_channel> chans;
+  if (colorspace == 0) chans = {heif_channel_Y, heif_channel_Cb, heif_channel_Cr};
+  else if (colorspace == 1) chans = {heif_channel_R, heif_channel_G, heif_channel_B};
+  else if (colorspace == 2) chans = {heif_channel_Y};
+  else chans = {heif_channel_interleaved};
+  if (has_alpha && colorspace != 3) chans.push_back(heif_channel_Alpha);
+  const int bps = bpp > 8 ? 2 : 1;
+  size_t pos = 0;
+  for (heif_channel c : chans) {
+    uint32_t pw = w, ph = h;
+    if (c == heif_channel_Cb || c == heif_channel_Cr) get_subsampled_size(w, h, c, (heif_chroma)chroma, &pw, &ph);
+    if (img->add_channel(c, pw, ph, bpp, limits)) return -1;
+    size_t stride; uint8_t* dst = img->get_channel_memory(c, &stride);
+    const int comps = c == heif_channel_interleaved ? num_interleaved_components_per_plane((heif_chroma)chroma) : 1;
+    const size_t rowb = (size_t)pw * comps * bps;
+    for (uint32_t r = 0; r < ph; r++) { memcpy(dst + r * stride, in + pos, rowb); pos += rowb; }
+  }
+  std::shared_ptr<HeifPixelImage> o;
+  if (img->scale_nearest_neighbor(o, ow, oh, limits)) return -2;
+  pos = 0;
+  for (heif_channel c : chans) {
+    const uint32_t pw = o->get_width(c), ph = o->get_height(c);
+    size_t stride; const uint8_t* src = o->get_channel_memory(c, &stride);
+    const int comps = c == heif_channel_interleaved ? num_interleaved_components_per_plane((heif_chroma)chroma) : 1;
+    const size_t rowb = (size_t)pw * comps * bps;
+    if (pos + rowb * ph > out_capacity) return -3;
+    for (uint32_t r = 0; r < ph; r++) { memcpy(out + pos, src + r * stride, rowb); pos += rowb; }
+  }
+  return (int)(pos > 0x7fffffff ? 0x7fffffff : pos);
+}
