@@ -97,7 +97,7 @@ __global__ void __launch_bounds__(EWARPS * 32, B200_ENTROPY_MIN_BLOCKS) hevc_ent
   // measured 25-70 % slower: the diverged paths of one warp serialise.)
   if ((threadIdx.x & 31) != 0) return;
   const int slot = threadIdx.x >> 5;
-  uint8_t* ctx = s_ctx[slot];
+  const syn::CtxPtr ctx = (syn::CtxPtr)__cvta_generic_to_shared(s_ctx[slot]);
   for (;;) {
     const unsigned t = atomicAdd(b.ticket, 1u);
     if (t >= (unsigned)b.nsubs) break;

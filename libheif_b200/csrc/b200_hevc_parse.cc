@@ -8,6 +8,7 @@
 //                        (b200_hevc_syntax.h), sequentially; the device front-end (b200_hevc_entropy.cu) runs the very
 //                        same code with one warp per sub-stream instead.
 // Input framing is libheif's: [uint32 BE length][NAL]... (libheif/codecs/decoder.cc:275-308).
+#define B200_SYNTAX_HOST_ONLY 1   // this translation unit uses the shared syntax decoder on the host only
 #include "b200_hevc.h"
 #include <algorithm>
 

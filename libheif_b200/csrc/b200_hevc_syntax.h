@@ -9,7 +9,10 @@
 #include <cstring>
 #include "b200_hevc_types.h"
 
-#ifdef __CUDACC__
+#if defined(__CUDA_ARCH__) && !defined(B200_SYNTAX_HOST_ONLY)
+#define B200_SYN_DEVICE 1
+#endif
+#if defined(__CUDACC__) && !defined(B200_SYNTAX_HOST_ONLY)
 // B200_HDN: one out-of-line copy per function on the device.  Full inlining of the syntax tree blew the entropy kernel
 // up to 38k SASS instructions (0.6 MB): the instruction cache, not arithmetic, set the pace of the lone decoding lane.
 #define B200_HDN __host__ __device__ __noinline__
@@ -24,10 +27,10 @@
 #define B200_HDI inline
 #define B200_TABLE(type, name, dims, ...) static const type h_##name dims = __VA_ARGS__;
 #endif
-#if defined(__CUDA_ARCH__) && !defined(B200_T)
+#if defined(B200_SYN_DEVICE) && !defined(B200_T)
 #define B200_T(name) d_##name
 #endif
-#ifdef __CUDA_ARCH__
+#ifdef B200_SYN_DEVICE
 // data written by ANOTHER sub-stream's thread (possibly on another SM): bypass the non-coherent L1
 #define B200_LD_SHARED(p) __ldcg(p)
 #else
@@ -39,6 +42,27 @@
 
 namespace b200 {
 namespace syn {
+
+// Context states and the hot lookup tables live in SHARED memory on the device.  Going through generic pointers costs a
+// 64-bit address, descriptor moves and a slower generic load per access (measured: 72 SASS instructions per
+// sig_coeff_flag); these handles are 32-bit shared-window addresses there and plain pointers on the host.
+#ifdef B200_SYN_DEVICE
+typedef uint32_t CtxPtr;
+typedef uint32_t TabPtr;
+__device__ __forceinline__ uint32_t ctx_ld(CtxPtr p) { uint32_t v; asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(p) : "memory"); return v; }
+__device__ __forceinline__ void ctx_st(CtxPtr p, uint32_t v) { asm volatile("st.shared.u8 [%0], %1;" ::"r"(p), "r"(v) : "memory"); }
+__device__ __forceinline__ uint32_t tab_ld8(TabPtr p, int i) { uint32_t v; asm("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(p + (uint32_t)i)); return v; }
+__device__ __forceinline__ uint32_t tab_ld32(TabPtr p, int i) { uint32_t v; asm("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(p + 4u * (uint32_t)i)); return v; }
+#define B200_TADDR(name) ((::b200::syn::TabPtr)__cvta_generic_to_shared(&B200_T(name)))
+#else
+typedef uint8_t* CtxPtr;
+typedef const uint8_t* TabPtr;
+inline uint32_t ctx_ld(CtxPtr p) { return *p; }
+inline void ctx_st(CtxPtr p, uint32_t v) { *p = (uint8_t)v; }
+inline uint32_t tab_ld8(TabPtr p, int i) { return p[i]; }
+inline uint32_t tab_ld32(TabPtr p, int i) { uint32_t v; memcpy(&v, p + 4 * (size_t)i, 4); return v; }
+#define B200_TADDR(name) (reinterpret_cast<::b200::syn::TabPtr>(&B200_T(name)))
+#endif
 
 enum { CTX_SAO_MERGE = 0, CTX_SAO_TYPE = 1, CTX_SPLIT_CU = 2, CTX_PART_MODE = 5, CTX_PREV_INTRA = 6,
        CTX_CHROMA_PRED = 7, CTX_SPLIT_TR = 8, CTX_CBF_LUMA = 11, CTX_CBF_CHROMA = 13, CTX_QP_DELTA = 18,
@@ -75,7 +99,7 @@ B200_TABLE(uint8_t, kSigCtxN, [3][4][16], {{{2,1,1,1,1,1,0,0,0,0,0,0,0,0,0,0},{2
 
 B200_HD inline int clip3(int lo, int hi, int v) { return v < lo ? lo : (v > hi ? hi : v); }
 B200_HD inline int imin(int a, int b) { return a < b ? a : b; }
-#ifdef __CUDA_ARCH__
+#ifdef B200_SYN_DEVICE
 B200_HD inline int hi_bit(uint32_t v) { return 31 - __clz((int)v); }          // v != 0
 B200_HD inline int lo_bit(uint32_t v) { return __ffs((int)v) - 1; }
 B200_HD inline int pop_count(uint32_t v) { return __popc(v); }
@@ -139,7 +163,7 @@ struct Cabac {
   // big-endian 16 bits at EVEN byte offset p; offsets past the end read the zero padding the buffer ends in (>= 2 bytes, size even)
   B200_HD static inline uint32_t fetch16(const CabacStream& st, uint32_t p) {
     const uint32_t q = p < st.size - 2 ? p : st.size - 2;
-#ifdef __CUDA_ARCH__
+#ifdef B200_SYN_DEVICE
     return __byte_perm((uint32_t)__ldg(reinterpret_cast<const unsigned short*>(st.d + q)), 0, 0x4401);
 #else
     return ((uint32_t)st.d[q] << 8) | st.d[q + 1];
@@ -158,19 +182,20 @@ struct Cabac {
   }
   B200_HD inline uint64_t bit_position() const { return (uint64_t)pos * 8 - (uint32_t)bits; }
   // shift the window left by n (n <= 7), merging the prefetched 16 bits when the look-ahead is exhausted
+  B200_HDN static uint32_t refill16(const CabacStream& st, uint32_t p) { return fetch16(st, p); }   // out of line: keeps the 1-in-12 refill a branch, not predicated code in every bin
   B200_HD inline void shift(int n, const CabacStream& st) {
     val <<= n; bits -= n;
-    if (bits < 0) { val |= next16 << (-bits); bits += 16; pos += 2; next16 = fetch16(st, pos); }
+    if (bits < 0) { val |= next16 << (-bits); bits += 16; pos += 2; next16 = refill16(st, pos); }
   }
-  B200_HD inline int bin(uint8_t& c, const CabacStream& st) {
-    const uint32_t cv = c;
-    const uint32_t rlps = (B200_T(kLps4)[cv >> 1] >> (((range >> 6) & 3) * 8)) & 0xff;
+  B200_HD inline int bin(CtxPtr c, const CabacStream& st) {
+    const uint32_t cv = ctx_ld(c);
+    const uint32_t rlps = (tab_ld32(B200_TADDR(kLps4), (int)(cv >> 1)) >> (((range >> 6) & 3) * 8)) & 0xff;
     const uint32_t rmps = range - rlps;
     const uint32_t lps = (val >> 16) >= rmps ? 1u : 0u;
     val -= lps ? (rmps << 16) : 0u;
     range = lps ? rlps : rmps;
-    c = B200_T(kNextState)[cv | (lps << 7)];
-#ifdef __CUDA_ARCH__
+    ctx_st(c, tab_ld8(B200_TADDR(kNextState), (int)(cv | (lps << 7))));
+#ifdef B200_SYN_DEVICE
     const int n = __clz((int)range) - 23;
 #else
     const int n = __builtin_clz(range) - 23;
@@ -192,7 +217,7 @@ struct Cabac {
       const int t = k > 7 ? 7 : k;                       // window (9 bits) + t <= 16 bits: stays inside bits 31..16 of val
       shift(t, st);
       const uint32_t w = val >> 16;                      // (offset << t) | t fresh bits, < 2^16
-#ifdef __CUDA_ARCH__
+#ifdef B200_SYN_DEVICE
       uint32_t q = (uint32_t)__float2int_rz(__fdividef((float)w, (float)range));   // within 1 of the quotient; fixed up exactly below
       int r = (int)w - (int)(q * range);
       if (r < 0) { q--; r += (int)range; } else if (r >= (int)range) { q++; r -= (int)range; }
@@ -213,13 +238,13 @@ struct Cabac {
   }
 };
 
-B200_HDN inline void init_contexts(uint8_t* ctx, int slice_qp) {          // 9.3.2.2
+B200_HDN inline void init_contexts(CtxPtr ctx, int slice_qp) {          // 9.3.2.2
   const int qp = clip3(0, 51, slice_qp);
   for (int i = 0; i < CTX_COUNT; i++) {
     const int iv = B200_T(kInitI)[i], m = (iv >> 4) * 5 - 45, nn = ((iv & 15) << 3) - 16;
     const int pre = clip3(1, 126, ((m * qp) >> 4) + nn);
     const int mps = pre > 63, st = mps ? pre - 64 : 63 - pre;
-    ctx[i] = (uint8_t)((st << 1) | mps);
+    ctx_st(ctx + i, (uint32_t)((st << 1) | mps));
   }
 }
 
@@ -230,7 +255,7 @@ struct SaoRaw { int8_t type[3], band[3], eo[3]; int8_t off[3][4]; };
 // ---------------------------------------------------------------------------------------------- sub-stream decoder
 struct Decoder {
   const SeqParams* sp; PicBuffers pb; const Substream* ss;
-  Cabac cabac; CabacStream stream; uint8_t* ctx;  // ctx: CTX_COUNT bytes (caller-provided storage)
+  Cabac cabac; CabacStream stream; CtxPtr ctx;    // ctx: CTX_COUNT context states (caller-provided storage)
   int is_dqp_coded, dqp_val, qpy_prev_qg, last_cu_qpy, first_qg, cur_qpy, err;
   uint32_t tu_n, coef_n, tu_cap, coef_cap;        // write cursors / limits of the current CTB (or of the picture when dense)
   int cur_ctb_x, cur_ctb_y;
@@ -245,7 +270,7 @@ struct Decoder {
 
   // Out-of-line arithmetic-decoder primitives for everything outside residual_coding (which keeps its own register
   // copy of the decoder): a call instead of ~35 inlined instructions per syntax element keeps the hot code small.
-  B200_HDN int dbin(int ci) { return cabac.bin(ctx[ci], stream); }
+  B200_HDN int dbin(int ci) { return cabac.bin(ctx + ci, stream); }
   B200_HDN int dbypass() { return cabac.bypass(stream); }
   B200_HDN unsigned dbits(int k) { return cabac.bypass_bits(k, stream); }
 
@@ -298,20 +323,20 @@ struct Decoder {
     const int n = 1 << log2n;
     // Local copies: their addresses never escape, so they live in registers and need no reload after the byte stores
     // into the context array (uint8_t stores may alias any member otherwise).
-    Cabac cb_ = cabac; uint8_t* const cx = ctx;
+    Cabac cb_ = cabac; const CtxPtr cx = ctx;
     const int sign_hiding = sp->sign_hiding;
     CoefEntry* const coef_out = pb.coefs; uint32_t cn = coef_n; const uint32_t ccap = coef_cap;
     tskip = 0;
-    if (sp->transform_skip && log2n == 2) tskip = cb_.bin(cx[CTX_TSKIP + (c ? 1 : 0)], stream);
+    if (sp->transform_skip && log2n == 2) tskip = cb_.bin(cx + (CTX_TSKIP + (c ? 1 : 0)), stream);
     const int cmax = (log2n << 1) - 1;
     int off, shift;
     if (c == 0) { off = 3 * (log2n - 2) + ((log2n - 1) >> 2); shift = (log2n + 1) >> 2; } else { off = 15; shift = log2n - 2; }
     int lx = 0, ly = 0;
     // last_sig_coeff_{x,y}_prefix then the two suffixes (7.3.8.11 order); one loop body serves both coordinates
     B200_NOUNROLL for (int xy = 0; xy < 2; xy++) {
-      const uint8_t* lc = cx + (xy ? CTX_LAST_Y : CTX_LAST_X) + off;
+      const CtxPtr lc = cx + ((xy ? CTX_LAST_Y : CTX_LAST_X) + off);
       int l = 0;
-      B200_NOUNROLL while (l < cmax && cb_.bin(const_cast<uint8_t&>(lc[l >> shift]), stream)) l++;
+      B200_NOUNROLL while (l < cmax && cb_.bin(lc + (l >> shift), stream)) l++;
       if (xy) ly = l; else lx = l;
     }
     B200_NOUNROLL for (int xy = 0; xy < 2; xy++) {
@@ -337,18 +362,18 @@ struct Decoder {
       const int right = (xs + 1 < nsbw) ? (int)((csbf >> (ys * 8 + xs + 1)) & 1) : 0;
       const int below = (ys + 1 < nsbw) ? (int)((csbf >> ((ys + 1) * 8 + xs)) & 1) : 0;
       int infer_dc = 0;
-      if (i < last_sb && i > 0) { if (!cb_.bin(cx[CTX_CSBF + ((right | below) ? 1 : 0) + (c ? 2 : 0)], stream)) continue; infer_dc = 1; }
+      if (i < last_sb && i > 0) { if (!cb_.bin(cx + (CTX_CSBF + ((right | below) ? 1 : 0) + (c ? 2 : 0)), stream)) continue; infer_dc = 1; }
       csbf |= 1ull << (ys * 8 + xs);
       // sig_coeff_flag (9.3.4.2.5): context = per-sub-block base + table entry per scan position; DC of the block has its own
-      const uint8_t* tab = log2n == 2 ? B200_T(kSigCtx4)[scan] : B200_T(kSigCtxN)[scan][right | (below << 1)];
+      const TabPtr tab = log2n == 2 ? B200_TADDR(kSigCtx4) + 16 * scan : B200_TADDR(kSigCtxN) + (64 * scan + 16 * (right | (below << 1)));
       const int off = sig_base + ((c == 0 && log2n > 2 && (xs | ys)) ? 3 : 0);
       unsigned sig = 0;
       int k = 15;
       if (i == last_sb) { sig = 1u << last_pos; k = last_pos - 1; }
       B200_NOUNROLL for (; k >= 0; k--) {
-        int ci = off + tab[k];
+        int ci = off + (int)tab_ld8(tab, k);
         if (k == 0) { if (infer_dc && !sig) { sig = 1u; break; } if (i == 0) ci = dc_ctx; }
-        if (cb_.bin(cx[ci], stream)) sig |= 1u << k;
+        if (cb_.bin(cx + (ci), stream)) sig |= 1u << k;
       }
       if (!sig) continue;
       unsigned g1 = 0;
@@ -360,11 +385,11 @@ struct Decoder {
       { unsigned m = sig; const int gbase = CTX_GT1 + ctx_set * 4 + (c ? 16 : 0);
         B200_NOUNROLL for (int ng1 = 0; m && ng1 < 8; ng1++) {
           const int kk = hi_bit(m); m ^= 1u << kk;
-          if (cb_.bin(cx[gbase + imin(3, g1ctx)], stream)) { g1 |= 1u << kk; g1ctx = 0; if (last_g1 < 0) last_g1 = kk; } else if (g1ctx > 0) g1ctx++;
+          if (cb_.bin(cx + (gbase + imin(3, g1ctx)), stream)) { g1 |= 1u << kk; g1ctx = 0; if (last_g1 < 0) last_g1 = kk; } else if (g1ctx > 0) g1ctx++;
         } }
       carry = g1ctx;
       const bool hidden = sign_hiding && (last_sig - first_sig > 3);
-      if (last_g1 >= 0) g2 = cb_.bin(cx[CTX_GT2 + ctx_set + (c ? 4 : 0)], stream);
+      if (last_g1 >= 0) g2 = cb_.bin(cx + (CTX_GT2 + ctx_set + (c ? 4 : 0)), stream);
       const int nsign = pop_count(sig) - (hidden ? 1 : 0);
       const unsigned signs = cb_.bypass_bits(nsign, stream);
       int nsig = 0, sum = 0, rice = 0, sidx = nsign;
@@ -591,7 +616,7 @@ template <class Sync>
 // `d` is caller-provided storage: on the device it lives in SHARED memory -- a lone lane's local memory uses 4 bytes of
 // every 128-byte line, so ~30 resident decoders with their state on the stack overflow L1 (measured: the SM's
 // throughput stopped growing at 8 warps).
-B200_HD int run_substream(Decoder& d, const SeqParams& sp, const PicBuffers& pb, const Substream* all, int index, uint8_t* ctx, Sync& sync) {
+B200_HD int run_substream(Decoder& d, const SeqParams& sp, const PicBuffers& pb, const Substream* all, int index, CtxPtr ctx, Sync& sync) {
   const Substream& ss = all[index];
   d.sp = &sp; d.pb = pb; d.ss = &ss; d.ctx = ctx; d.err = SYN_OK;
   d.is_dqp_coded = 0; d.dqp_val = 0; d.qpy_prev_qg = ss.slice_qp; d.last_cu_qpy = ss.slice_qp; d.first_qg = 1; d.cur_qpy = ss.slice_qp;
@@ -604,7 +629,7 @@ B200_HD int run_substream(Decoder& d, const SeqParams& sp, const PicBuffers& pb,
   if (ss.prev >= 0) {                                         // dependent slice segment: continue from the previous segment's end state
     sync.wait_substream(ss.prev);
     const uint8_t* st = pb.end_state + (size_t)ss.prev * CTX_STRIDE;
-    B200_NOUNROLL for (int i = 0; i < CTX_COUNT; i++) ctx[i] = B200_LD_SHARED(st + i);
+    B200_NOUNROLL for (int i = 0; i < CTX_COUNT; i++) ctx_st(ctx + i, B200_LD_SHARED(st + i));
     d.last_cu_qpy = (int)(int8_t)B200_LD_SHARED(st + CTX_COUNT); d.first_qg = 0;
   }
   if (ss.init_contexts) init_contexts(ctx, ss.slice_qp);
@@ -614,7 +639,7 @@ B200_HD int run_substream(Decoder& d, const SeqParams& sp, const PicBuffers& pb,
     const int xn = 1 << sp.log2ctb, yn = (ry0 - 1) << sp.log2ctb;
     bool tr = ry0 > 0 && xn < sp.W && pb.ctu_slice[(ry0 - 1) * sp.wctb + 1] == (uint16_t)ss.slice_idx;
     (void)yn;
-    if (tr) { sync.wait_row(ry0 - 1, 2); const uint8_t* st = pb.wpp_ctx + (size_t)(ry0 - 1) * CTX_STRIDE; B200_NOUNROLL for (int i = 0; i < CTX_COUNT; i++) ctx[i] = B200_LD_SHARED(st + i); }
+    if (tr) { sync.wait_row(ry0 - 1, 2); const uint8_t* st = pb.wpp_ctx + (size_t)(ry0 - 1) * CTX_STRIDE; B200_NOUNROLL for (int i = 0; i < CTX_COUNT; i++) ctx_st(ctx + i, B200_LD_SHARED(st + i)); }
     else if (ss.prev < 0) init_contexts(ctx, ss.slice_qp);
     d.first_qg = 1;
   }
@@ -630,7 +655,7 @@ B200_HD int run_substream(Decoder& d, const SeqParams& sp, const PicBuffers& pb,
     if (!sp.wpp && rx == 0 && a != ss.ctb_begin) { /* QG state simply continues */ }
     d.decode_ctb((int)a);
     if (d.err) break;
-    if (sp.wpp && rx == 1) { uint8_t* st = pb.wpp_ctx + (size_t)ry * CTX_STRIDE; B200_NOUNROLL for (int i = 0; i < CTX_COUNT; i++) st[i] = ctx[i]; }
+    if (sp.wpp && rx == 1) { uint8_t* st = pb.wpp_ctx + (size_t)ry * CTX_STRIDE; B200_NOUNROLL for (int i = 0; i < CTX_COUNT; i++) st[i] = (uint8_t)ctx_ld(ctx + i); }
     const int end = d.cabac.terminate(d.stream);                          // end_of_slice_segment_flag
     const bool last = a + 1 == ss.ctb_end;
     if (end != ((last && ss.last_of_segment) ? 1 : 0)) { d.err = SYN_E_BITSTREAM; break; }
@@ -639,7 +664,7 @@ B200_HD int run_substream(Decoder& d, const SeqParams& sp, const PicBuffers& pb,
     if (d.cabac.pos > pb.rbsp_size + 64u) { d.err = SYN_E_BITSTREAM; break; }
   }
   // end state for a dependent continuation + dense cursors
-  { uint8_t* st = pb.end_state + (size_t)index * CTX_STRIDE; B200_NOUNROLL for (int i = 0; i < CTX_COUNT; i++) st[i] = ctx[i]; st[CTX_COUNT] = (uint8_t)(int8_t)d.last_cu_qpy; }
+  { uint8_t* st = pb.end_state + (size_t)index * CTX_STRIDE; B200_NOUNROLL for (int i = 0; i < CTX_COUNT; i++) st[i] = (uint8_t)ctx_ld(ctx + i); st[CTX_COUNT] = (uint8_t)(int8_t)d.last_cu_qpy; }
   if (sp.dense) { sync.dense_tu = d.tu_n; sync.dense_coef = d.coef_n; }
   sync.end_bit_position = d.cabac.bit_position();
   sync.finish_substream(index, d.err);
