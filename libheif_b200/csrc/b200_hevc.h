@@ -42,6 +42,8 @@ struct DeviceBatch {
   const CtuInfo* ctus; const TuCmd* tus; const CoefEntry* coefs; const SliceInfo* slices;
   const int8_t* qp8; const uint8_t* edge8;
   unsigned int* progress;        // one counter per CTB row of every picture, zeroed before launch
+  const unsigned int* entropy_progress;   // K0's counters of the same rows when K0 runs CONCURRENTLY (nullptr: command stream complete)
+  int blocks_per_sm;             // > 0: cap of resident CTAs per SM (co-residency with K0)
   unsigned int* ticket;          // work-distribution counter, zeroed before launch
   unsigned int* error_flag;      // set by a kernel that gave up waiting (zeroed before launch)
   const uint2* row_list;         // (picture, ctb row) in launch order
@@ -56,6 +58,7 @@ struct EntropyBatch {
   const uint2* order;            // (picture, local sub-stream index) in ticket order
   int nsubs;
   unsigned int* ticket; unsigned int* progress; unsigned int* sub_done; unsigned int* error_flag;
+  int blocks_per_sm;             // > 0: cap of resident CTAs per SM (co-residency with K1)
 };
 int launch_entropy(const EntropyBatch& b, cudaStream_t s);
 int launch_entropy_stats(const EntropyBatch& b, unsigned long long* out2, cudaStream_t s);

@@ -91,6 +91,8 @@ struct b200_decoder {
   std::vector<size_t> rec_off; int npics = 0;
   cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};   // 0 start, 1 after H2D, 5 after entropy, 2 after recon, 3 after deblock, 4 after SAO
   cudaStream_t last_stream = nullptr;
+  cudaStream_t side = nullptr;     // K0 runs here, concurrently with K1 on the caller's stream
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   bool have_result = false;
   int debug_stage = 0;
   size_t n_rows = 0, cbytes = 0; bool canvas_fully_covered = true; int max_log2_ctb = 6;
@@ -101,6 +103,9 @@ struct b200_decoder {
     rbsp.release(); subs.release(); sub_order.release(); ctu_slice.release(); epics.release(); ipm4.release(); cd8.release(); wpp_ctx.release();
     end_state.release(); esync.release(); ecount.release();
     for (auto& e : ev) if (e) cudaEventDestroy(e);
+    if (ev_fork) cudaEventDestroy(ev_fork);
+    if (ev_join) cudaEventDestroy(ev_join);
+    if (side) cudaStreamDestroy(side);
   }
 };
 
@@ -111,25 +116,57 @@ static int check_device_error(b200_decoder* d) {
   return B200_OK;
 }
 
-// Device front-end: entropy decoding of every sub-stream of the batch (K0).
-static int run_entropy(b200_decoder* d, cudaStream_t s) {
-  EntropyBatch e{};
-  e.pics = d->epics.d; e.npics = d->npics; e.subs = d->subs.d; e.order = d->sub_order.d; e.nsubs = (int)d->n_subs;
-  e.ticket = d->esync.d; e.progress = d->esync.d + 1; e.sub_done = d->esync.d + 1 + d->n_rows; e.error_flag = d->sync.d + 1;
-  int rc = launch_entropy(e, s);
-  if (rc) return rc;
-  return launch_entropy_stats(e, d->ecount.d, s);
+// K0 (entropy) and K1 (reconstruction) can run CONCURRENTLY: K1 consumes the command stream CTB by CTB as K0 publishes
+// it.  Both kernels are persistent and ticket-driven, so they need not be fully co-resident (whatever part of either
+// grid is resident finishes the work); the caps below only share the SM's registers between them.
+// Measured (profiles/README.md): the overlap hides K1 completely while the batch is critical-path bound -- up to about
+// one wave of sub-streams (32 tiles: 63 vs 85 ms, 64 tiles: 82 vs 94 ms) -- and LOSES once the GPU is throughput bound
+// (128 tiles: 109 vs 101 ms, 256 tiles: 195 vs 126 ms; the two instruction streams evict each other), so it is chosen
+// per batch.  B200_OVERLAP=0/1 forces it.
+static int overlap_blocks(const char* env, int dflt) { if (const char* e = getenv(env)) { const int v = atoi(e); if (v >= 1 && v <= 4) return v; } return dflt; }
+static bool use_overlap(size_t n_subs) {
+  if (const char* e = getenv("B200_OVERLAP")) return atoi(e) != 0;
+  int dev = 0, sms = 148; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  return n_subs <= (size_t)sms * 16;      // one wave of K0: 4 CTAs x 4 warps per SM
 }
 
-// Launches the device half (reconstruction -> deblocking -> SAO/paste) on the command stream currently resident in HBM.
+// Device half: K0 entropy decoding (device front-end only) on the side stream, concurrently K1 reconstruction on `s`
+// consuming the command stream CTB by CTB as K0 publishes it, then deblocking and SAO / paste on `s`.
 static int run_device_pipeline(b200_decoder* d, int n, cudaStream_t s, int* launches_out) {
   int rc;
+  int launches = 0;
+  const bool devfe = d->used_device_front_end;
+  const bool overlap = devfe && use_overlap(d->n_subs);
+  cudaEventRecord(d->ev[1], s);
   DeviceBatch b{};
   b.pics = d->pics.d; b.npics = n; b.ctus = d->ctus.d; b.tus = d->tus.d; b.coefs = d->coefs.d; b.slices = d->slices.d;
   b.qp8 = d->qp8.d; b.edge8 = d->edge8.d; b.ticket = d->sync.d; b.error_flag = d->sync.d + 1; b.progress = d->sync.d + 2; b.row_list = d->rows.d; b.nrows = (int)d->n_rows; b.max_log2_ctb = d->max_log2_ctb;
+  if (devfe) {
+    EntropyBatch e{};
+    e.pics = d->epics.d; e.npics = d->npics; e.subs = d->subs.d; e.order = d->sub_order.d; e.nsubs = (int)d->n_subs;
+    e.ticket = d->esync.d; e.progress = d->esync.d + 1; e.sub_done = d->esync.d + 1 + d->n_rows; e.error_flag = d->sync.d + 1;
+    if (overlap) {
+      if (!d->side) { B200_CUDA_CHECK(cudaStreamCreateWithFlags(&d->side, cudaStreamNonBlocking)); B200_CUDA_CHECK(cudaEventCreate(&d->ev_fork)); B200_CUDA_CHECK(cudaEventCreate(&d->ev_join)); }
+      e.blocks_per_sm = overlap_blocks("B200_OVERLAP_K0_BLOCKS", 3);
+      b.blocks_per_sm = overlap_blocks("B200_OVERLAP_K1_BLOCKS", 2);
+      b.entropy_progress = e.progress;
+      cudaEventRecord(d->ev_fork, s);
+      B200_CUDA_CHECK(cudaStreamWaitEvent(d->side, d->ev_fork, 0));
+      if ((rc = launch_entropy(e, d->side))) return rc;
+      cudaEventRecord(d->ev[5], d->side);
+      if ((rc = launch_entropy_stats(e, d->ecount.d, d->side))) return rc;
+      cudaEventRecord(d->ev_join, d->side);
+    } else {
+      if ((rc = launch_entropy(e, s))) return rc;
+      cudaEventRecord(d->ev[5], s);
+      if ((rc = launch_entropy_stats(e, d->ecount.d, s))) return rc;
+    }
+    launches += 1;
+  } else cudaEventRecord(d->ev[5], s);
   if ((rc = launch_recon(b, s))) return rc;
+  if (devfe && overlap) B200_CUDA_CHECK(cudaStreamWaitEvent(s, d->ev_join, 0));
   cudaEventRecord(d->ev[2], s);
-  int launches = 1;
+  launches += 1;
   if (d->debug_stage != 1) { if ((rc = launch_deblock(b, d->pics.h, s))) return rc; launches += 2; }
   cudaEventRecord(d->ev[3], s);
   if (d->debug_stage == 0) { if ((rc = launch_sao(b, d->pics.h, s))) return rc; launches += 1; }
@@ -310,16 +347,8 @@ int b200_decoder_decode_grid(b200_decoder* d, int cols, int rows, const uint8_t*
   B200_CUDA_CHECK(cudaMemsetAsync(d->sync.d, 0, (n_rows + 2) * sizeof(unsigned), s));
   if (!canvas_fully_covered) B200_CUDA_CHECK(cudaMemsetAsync(d->canvas.d, 0, cbytes, s));     // uncovered canvas stays zero (calloc in the reference)
   d->n_rows = n_rows; d->cbytes = cbytes; d->canvas_fully_covered = canvas_fully_covered; d->npics = n; d->n_subs = n_subs; d->used_device_front_end = devfe;
-  cudaEventRecord(d->ev[1], s);
   int launches = 0;
-  if (devfe) {
-    if ((rc = run_entropy(d, s))) return rc;
-    launches += 1;
-  }
-  cudaEventRecord(d->ev[5], s);
-  int l2 = 0;
-  if ((rc = run_device_pipeline(d, n, s, &l2))) return rc;
-  launches += l2;
+  if ((rc = run_device_pipeline(d, n, s, &launches))) return rc;
   d->last_stream = s; d->have_result = true;
   b200_image_info& inf = d->info;
   inf.width = cw; inf.height = chh; inf.tile_width = tw; inf.tile_height = th; inf.chroma = chroma ? B200_CHROMA_420 : B200_CHROMA_MONO; inf.bit_depth = bd;
@@ -348,12 +377,8 @@ int b200_decoder_rerun_device(b200_decoder* d, void* stream_) {
     B200_CUDA_CHECK(cudaMemsetAsync(d->esync.d, 0, (1 + d->n_rows + d->n_subs) * sizeof(unsigned), s));
     B200_CUDA_CHECK(cudaMemsetAsync(d->ecount.d, 0, 2 * sizeof(unsigned long long), s));
   }
-  cudaEventRecord(d->ev[1], s);
-  int rc;
-  if (d->used_device_front_end && (rc = run_entropy(d, s))) return rc;
-  cudaEventRecord(d->ev[5], s);
   int launches = 0;
-  rc = run_device_pipeline(d, d->npics, s, &launches);
+  int rc = run_device_pipeline(d, d->npics, s, &launches);
   d->last_stream = s;
   return rc;
 }
@@ -364,6 +389,7 @@ int b200_decoder_get_stats(b200_decoder* d, b200_decode_stats* out) {
   float a = 0, en = 0, b = 0, c = 0, e = 0;
   cudaEventElapsedTime(&a, d->ev[0], d->ev[1]); cudaEventElapsedTime(&en, d->ev[1], d->ev[5]); cudaEventElapsedTime(&b, d->ev[5], d->ev[2]);
   cudaEventElapsedTime(&c, d->ev[2], d->ev[3]); cudaEventElapsedTime(&e, d->ev[3], d->ev[4]);
+  if (b < 0) { en += b; b = 0; }   // K0 and K1 overlap: recon_ms is the part of K1 that runs after K0 has finished
   d->stats.h2d_ms = a; d->stats.entropy_ms = en; d->stats.recon_ms = b; d->stats.deblock_ms = c; d->stats.sao_ms = e; d->stats.gpu_ms = en + b + c + e;
   d->stats.front_end = d->used_device_front_end ? 1 : 0;
   if (d->used_device_front_end) {

@@ -108,6 +108,17 @@ __device__ __forceinline__ bool available(const RowCtx& r, int xn, int yn, int x
 }
 
 // sample of component c at tile-relative position (tx, ty); tx in [-1, 2*ctb), ty in [-1, ctb)
+// Command-stream reads: L1-bypassing (ld.global.cg).  With K0 running concurrently a neighbouring, not yet written
+// entry may share a cache line with one read earlier; L1 is not coherent, L2 is.
+__device__ __forceinline__ TuCmd ld_tu(const TuCmd* p) { const uint4 v = __ldcg(reinterpret_cast<const uint4*>(p)); return TuCmd{v.x, v.y, v.z, v.w}; }
+__device__ __forceinline__ CoefEntry ld_coef(const CoefEntry* p) { const unsigned v = __ldcg(reinterpret_cast<const unsigned*>(p)); CoefEntry e; e.pos = (uint16_t)(v & 0xffff); e.level = (int16_t)(v >> 16); return e; }
+__device__ __forceinline__ CtuInfo ld_ctu(const CtuInfo* p) {
+  CtuInfo c; const uint2* s = reinterpret_cast<const uint2*>(p); uint2* d = reinterpret_cast<uint2*>(&c);
+#pragma unroll
+  for (int i = 0; i < (int)(sizeof(CtuInfo) / 8); i++) d[i] = __ldcg(s + i);
+  return c;
+}
+
 __device__ __forceinline__ int tile_sample(const WarpMem& m, int c, int tx, int ty) {
   if (c == 0) { if (ty < 0) return m.top_y[tx + 1]; if (tx < 0) return m.left_y[ty]; return m.tile_y[ty * m.ts + tx]; }
   if (ty < 0) return m.top_c[c - 1][tx + 1];
@@ -253,7 +264,7 @@ __device__ __noinline__ void process_tb(WarpMem& m, const int8_t* __restrict__ m
   const long long scale = (long long)(c_level_scale[qp % 6] << (qp / 6)) * 16;
   int maxrow = 0, maxcol = 0;
   for (int i = lane; i < ncoef; i += 32) {
-    const CoefEntry e = ce[i];
+    const CoefEntry e = ld_coef(&ce[i]);
     const long long t = ((long long)e.level * scale + (1LL << (bd_shift - 1))) >> bd_shift;
     m.coef[e.pos] = (int16_t)(t < -32768 ? -32768 : (t > 32767 ? 32767 : t));
     maxrow = max(maxrow, e.pos >> log2n); maxcol = max(maxcol, e.pos & (n - 1));
@@ -336,31 +347,47 @@ __global__ void __launch_bounds__(WARPS * 32) hevc_recon_kernel(const DeviceBatc
     const TuCmd* tus = b.tus + pic->tu_base;
     const CoefEntry* coefs = b.coefs + pic->coef_base;
     unsigned* prog = b.progress + pic->progress_base;
+    const unsigned* eprog = b.entropy_progress ? b.entropy_progress + pic->progress_base : nullptr;
     const bool b8 = r.bd == 8;
     const int ctbc = r.ctb >> 1;
     const int nch = r.chroma ? 3 : 1;
 
     for (r.rx = 0; r.rx < r.wctb; r.rx++) {
       r.x0 = r.rx << r.log2ctb;
-      const CtuInfo ci = r.ctus[r.ry * r.wctb + r.rx];
-      r.cur_slice = ci.slice_idx;
-      r.nb_slice[0] = r.rx > 0 ? r.ctus[r.ry * r.wctb + r.rx - 1].slice_idx : -1;
-      r.nb_slice[1] = (r.rx > 0 && r.ry > 0) ? r.ctus[(r.ry - 1) * r.wctb + r.rx - 1].slice_idx : -1;
-      r.nb_slice[2] = r.ry > 0 ? r.ctus[(r.ry - 1) * r.wctb + r.rx].slice_idx : -1;
-      r.nb_slice[3] = (r.ry > 0 && r.rx + 1 < r.wctb) ? r.ctus[(r.ry - 1) * r.wctb + r.rx + 1].slice_idx : -1;
-      TuCmd next_cmd = ci.tu_count ? tus[ci.tu_start] : TuCmd{0, 0, 0, 0};
-      if (r.ry > 0) {
-        // wait for the above-right CTB (wavefront, lag 2), then fetch the halo row above from HBM/L2
-        const unsigned need = (unsigned)min(r.rx + 2, r.wctb);
-        if (lane == 0) {
-          // relaxed polling load (no L1 invalidation); the halo is read with __ldcg below.  A CTB takes ~0.2 ms: back off
-          // to microseconds so waiting rows do not flood L2 with polls.
-          unsigned spins = 0, ns = 250;
+      // (1) with K0 running concurrently: this CTB's commands must have been published; (2) wavefront: the above-right
+      // CTB must be reconstructed (lag 2).  Relaxed polling loads (no L1 invalidation) with microsecond back-off (a CTB
+      // takes ~0.2 ms): waiting rows must not flood L2 with polls.  Everything produced by another SM during this
+      // kernel -- commands and the halo row -- is then read with L1-bypassing loads.
+      int abort = 0;
+      if (lane == 0) {
+        unsigned spins = 0, ns = 250;
+        if (eprog) while (ld_acquire(&eprog[r.ry]) < (unsigned)(r.rx + 1)) {
+          __nanosleep(ns); if (ns < 2000) ns <<= 1;
+          if (ld_acquire(b.error_flag)) break;                                     // K0 failed (corrupt stream): its progress will never come
+          if (++spins > (1u << 23)) { atomicExch(b.error_flag, 1u); break; }       // ~16 s; turns a would-be hang into an error
+        }
+        if (r.ry > 0) {
+          const unsigned need = (unsigned)min(r.rx + 2, r.wctb);
+          spins = 0; ns = 250;
           while (ld_acquire(&prog[r.ry - 1]) < need) {
             __nanosleep(ns); if (ns < 2000) ns <<= 1;
-            if (++spins > (1u << 23)) { atomicExch(b.error_flag, 1u); break; }     // ~16 s; never observed; turns a would-be hang into an error
+            if (ld_acquire(b.error_flag)) break;
+            if (++spins > (1u << 23)) { atomicExch(b.error_flag, 1u); break; }
           }
         }
+        abort = ld_acquire(b.error_flag) != 0u;
+      }
+      abort = __shfl_sync(0xffffffffu, abort, 0);
+      if (abort) return;                                     // the batch is reported as failed; nothing it produced is used
+      const CtuInfo ci = ld_ctu(&r.ctus[r.ry * r.wctb + r.rx]);
+      r.cur_slice = ci.slice_idx;
+      r.nb_slice[0] = r.rx > 0 ? (int)__ldcg(&r.ctus[r.ry * r.wctb + r.rx - 1].slice_idx) : -1;
+      r.nb_slice[1] = (r.rx > 0 && r.ry > 0) ? (int)__ldcg(&r.ctus[(r.ry - 1) * r.wctb + r.rx - 1].slice_idx) : -1;
+      r.nb_slice[2] = r.ry > 0 ? (int)__ldcg(&r.ctus[(r.ry - 1) * r.wctb + r.rx].slice_idx) : -1;
+      r.nb_slice[3] = (r.ry > 0 && r.rx + 1 < r.wctb) ? (int)__ldcg(&r.ctus[(r.ry - 1) * r.wctb + r.rx + 1].slice_idx) : -1;
+      TuCmd next_cmd = ci.tu_count ? ld_tu(&tus[ci.tu_start]) : TuCmd{0, 0, 0, 0};
+      if (r.ry > 0) {
+        // fetch the halo row above from HBM/L2
         __syncwarp();
 #pragma unroll 1
         for (int c = 0; c < nch; c++) {
@@ -382,7 +409,7 @@ __global__ void __launch_bounds__(WARPS * 32) hevc_recon_kernel(const DeviceBatc
       const SliceInfo sl = r.slices[ci.slice_idx];
       for (unsigned ti = 0; ti < ci.tu_count; ti++) {
         const TuCmd cmd = next_cmd;
-        if (ti + 1 < ci.tu_count) next_cmd = tus[ci.tu_start + ti + 1];      // prefetch: hides one dependent HBM/L2 round trip per TU
+        if (ti + 1 < ci.tu_count) next_cmd = ld_tu(&tus[ci.tu_start + ti + 1]);      // prefetch: hides one dependent HBM/L2 round trip per TU
         const int x4 = cmd.w0 & 0xfff, y4 = (cmd.w0 >> 12) & 0xfff, log2n = 2 + ((cmd.w0 >> 24) & 3);
         const int lmode = cmd.w1 & 63, cmode = (cmd.w1 >> 6) & 63, qpy = (int)((cmd.w1 >> 12) & 0xff) - 64;
         const int nl = cmd.w3 & 0x7ff, ncb = (cmd.w3 >> 11) & 0x3ff, ncr = (cmd.w3 >> 21) & 0x3ff;
@@ -433,6 +460,7 @@ int launch_recon(const DeviceBatch& b, cudaStream_t s) {
   int occ = 1;
   cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, hevc_recon_kernel, WARPS * 32, smem);
   if (occ < 1) occ = 1;
+  if (b.blocks_per_sm > 0 && b.blocks_per_sm < occ) occ = b.blocks_per_sm;
   const int want = (b.nrows + WARPS - 1) / WARPS;
   const int grid = want < sms * occ ? want : sms * occ;
   hevc_recon_kernel<<<grid, WARPS * 32, smem, s>>>(b);
