@@ -259,14 +259,16 @@ struct Decoder {
   int is_dqp_coded, dqp_val, qpy_prev_qg, last_cu_qpy, first_qg, cur_qpy, err;
   uint32_t tu_n, coef_n, tu_cap, coef_cap;        // write cursors / limits of the current CTB (or of the picture when dense)
   int cur_ctb_x, cur_ctb_y;
+  int ctb_x0, ctb_y0, left_ok, up_ok;            // current CTB: origin, availability of the CTB to the left / above (same slice)
   struct Cu { int x0, y0, log2cb, nxn, lmode[4], cmode; };
 
-  // 6.4.1 for a left / above neighbour of the current block: those always precede it in decoding order, so they are
-  // available iff they lie inside the picture and in the same slice (HEVC tiles are not supported).
-  B200_HDN bool avail(int x, int y) const {
-    if (x < 0 || y < 0 || x >= sp->W || y >= sp->H) return false;
-    return pb.ctu_slice[(y >> sp->log2ctb) * sp->wctb + (x >> sp->log2ctb)] == (uint16_t)ss->slice_idx;
-  }
+  // 6.4.1 for the LEFT (x - 1, y) or ABOVE (x, y - 1) neighbour of a position inside the current CTB -- the only queries
+  // the intra syntax makes.  Such a neighbour precedes the block in decoding order, so it is available iff it lies in the
+  // picture and in the same slice (HEVC tiles are not supported): always inside the current CTB, else decided once per CTB.
+  B200_HD inline bool avail(int x, int y) const { return x >= ctb_x0 ? (y >= ctb_y0 ? true : up_ok != 0) : left_ok != 0; }
+  // Map cells of this CTB row were written by this very thread (plain load, L1); cells of the row above by another
+  // sub-stream's thread, possibly on another SM (L1-bypassing load).
+  B200_HD inline int ld_cell(const uint8_t* p, int y) const { return y >= ctb_y0 ? (int)*p : (int)B200_LD_SHARED(p); }
 
   // Out-of-line arithmetic-decoder primitives for everything outside residual_coding (which keeps its own register
   // copy of the decoder): a call instead of ~35 inlined instructions per syntax element keeps the hot code small.
@@ -312,8 +314,8 @@ struct Decoder {
   B200_HDN void derive_qpy(int xcb, int ycb) {
     const int mask = (1 << sp->qg_log2) - 1, xqg = xcb & ~mask, yqg = ycb & ~mask, cm = ~((1 << sp->log2ctb) - 1);
     int qa = qpy_prev_qg, qb = qpy_prev_qg;
-    if (avail(xqg - 1, yqg) && ((xqg - 1) & cm) == (xqg & cm)) qa = B200_LD_SHARED(pb.qp8 + (yqg >> 3) * sp->w8 + ((xqg - 1) >> 3));
-    if (avail(xqg, yqg - 1) && ((yqg - 1) & cm) == (yqg & cm)) qb = B200_LD_SHARED(pb.qp8 + ((yqg - 1) >> 3) * sp->w8 + (xqg >> 3));
+    if (avail(xqg - 1, yqg) && ((xqg - 1) & cm) == (xqg & cm)) qa = pb.qp8[(yqg >> 3) * sp->w8 + ((xqg - 1) >> 3)];   // same CTB: own data
+    if (avail(xqg, yqg - 1) && ((yqg - 1) & cm) == (yqg & cm)) qb = pb.qp8[((yqg - 1) >> 3) * sp->w8 + (xqg >> 3)];
     const int pred = (qa + qb + 1) >> 1, qbd = 6 * (sp->bd - 8);
     cur_qpy = ((pred + dqp_val + 52 + 2 * qbd) % (52 + qbd)) - qbd;
   }
@@ -519,8 +521,8 @@ struct Decoder {
   // -------- 8.4.2
   B200_HDN int luma_mode(int x, int y, int prev, int mpm_idx, int rem) const {
     int ca = 1, cb = 1;
-    if (avail(x - 1, y)) ca = B200_LD_SHARED(pb.ipm4 + (y >> 2) * sp->w4 + ((x - 1) >> 2));
-    if (avail(x, y - 1) && (y - 1) >= ((y >> sp->log2ctb) << sp->log2ctb)) cb = B200_LD_SHARED(pb.ipm4 + ((y - 1) >> 2) * sp->w4 + (x >> 2));
+    if (avail(x - 1, y)) ca = pb.ipm4[(y >> 2) * sp->w4 + ((x - 1) >> 2)];               // this CTB row: own data
+    if (avail(x, y - 1) && (y - 1) >= ((y >> sp->log2ctb) << sp->log2ctb)) cb = pb.ipm4[((y - 1) >> 2) * sp->w4 + (x >> 2)];
     int c0, c1, c2;
     if (ca == cb) { if (ca < 2) { c0 = 0; c1 = 1; c2 = 26; } else { c0 = ca; c1 = 2 + ((ca + 29) % 32); c2 = 2 + ((ca - 2 + 1) % 32); } }
     else { c0 = ca; c1 = cb; if (ca != 0 && cb != 0) c2 = 0; else if (ca != 1 && cb != 1) c2 = 1; else c2 = 26; }
@@ -576,8 +578,8 @@ struct Decoder {
         int split;
         if (x0 + n <= sp->W && y0 + n <= sp->H && log2cb > log2min) {
           int inc = 0;
-          if (avail(x0 - 1, y0) && B200_LD_SHARED(pb.cd8 + (y0 >> 3) * sp->w8 + ((x0 - 1) >> 3)) > depth) inc++;
-          if (avail(x0, y0 - 1) && B200_LD_SHARED(pb.cd8 + ((y0 - 1) >> 3) * sp->w8 + (x0 >> 3)) > depth) inc++;
+          if (avail(x0 - 1, y0) && (int)pb.cd8[(y0 >> 3) * sp->w8 + ((x0 - 1) >> 3)] > depth) inc++;
+          if (avail(x0, y0 - 1) && ld_cell(pb.cd8 + ((y0 - 1) >> 3) * sp->w8 + (x0 >> 3), y0 - 1) > depth) inc++;
           split = dbin(CTX_SPLIT_CU + inc);
         } else split = log2cb > log2min;
         if (sp->cu_qp_delta && log2cb >= sp->qg_log2) {
@@ -596,6 +598,9 @@ struct Decoder {
   B200_HDN void decode_ctb(int addr) {
     const int rx = addr % sp->wctb, ry = addr / sp->wctb;
     cur_ctb_x = rx; cur_ctb_y = ry;
+    ctb_x0 = rx << sp->log2ctb; ctb_y0 = ry << sp->log2ctb;
+    left_ok = rx > 0 && pb.ctu_slice[addr - 1] == (uint16_t)ss->slice_idx;
+    up_ok = ry > 0 && pb.ctu_slice[addr - sp->wctb] == (uint16_t)ss->slice_idx;
     CtuInfo& ci = pb.ctus[addr];
     ci.slice_idx = (uint16_t)ss->slice_idx;
     if (!sp->dense) { tu_n = (uint32_t)addr * (uint32_t)sp->tu_slots; tu_cap = tu_n + (uint32_t)sp->tu_slots; coef_n = (uint32_t)addr * (uint32_t)sp->coef_slots; coef_cap = coef_n + (uint32_t)sp->coef_slots; }
