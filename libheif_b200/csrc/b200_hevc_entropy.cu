@@ -59,10 +59,11 @@ struct DevSync {
   __device__ static void spin_until(const unsigned* p, unsigned need, unsigned* error_flag) {
     if (e_ld_acquire(p) >= need) return;
     unsigned long long t0; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
-    unsigned ns = 500;
+    unsigned ns = 500, spins = 0;
     for (;;) {
       __nanosleep(ns); if (ns < 4000) ns <<= 1;
       if (e_ld_acquire(p) >= need) return;
+      if ((++spins & 31u) != 0) continue;
       if (e_ld_acquire(error_flag)) return;              // a producer failed: do not wait for progress that will never come
       unsigned long long t1; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
       if (t1 - t0 > 60000000000ull) { atomicExch(error_flag, 3u); return; }

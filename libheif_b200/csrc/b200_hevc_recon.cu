@@ -108,14 +108,16 @@ __device__ __forceinline__ bool available(const RowCtx& r, int xn, int yn, int x
 }
 
 // sample of component c at tile-relative position (tx, ty); tx in [-1, 2*ctb), ty in [-1, ctb)
-// Command-stream reads: L1-bypassing (ld.global.cg).  With K0 running concurrently a neighbouring, not yet written
-// entry may share a cache line with one read earlier; L1 is not coherent, L2 is.
-__device__ __forceinline__ TuCmd ld_tu(const TuCmd* p) { const uint4 v = __ldcg(reinterpret_cast<const uint4*>(p)); return TuCmd{v.x, v.y, v.z, v.w}; }
-__device__ __forceinline__ CoefEntry ld_coef(const CoefEntry* p) { const unsigned v = __ldcg(reinterpret_cast<const unsigned*>(p)); CoefEntry e; e.pos = (uint16_t)(v & 0xffff); e.level = (int16_t)(v >> 16); return e; }
-__device__ __forceinline__ CtuInfo ld_ctu(const CtuInfo* p) {
+// Command-stream reads.  LIVE = K0 is running concurrently: a neighbouring, not yet written entry may share a cache
+// line with one read earlier and L1 is not coherent, so everything goes to L2 (ld.global.cg).  Otherwise the command
+// stream is complete and plain loads let consecutive entries hit the L1 line the first one brought in.
+template <bool LIVE, class T> __device__ __forceinline__ T ld_cmd(const T* p) { return LIVE ? __ldcg(p) : *p; }
+template <bool LIVE> __device__ __forceinline__ TuCmd ld_tu(const TuCmd* p) { const uint4 v = ld_cmd<LIVE>(reinterpret_cast<const uint4*>(p)); return TuCmd{v.x, v.y, v.z, v.w}; }
+template <bool LIVE> __device__ __forceinline__ CoefEntry ld_coef(const CoefEntry* p) { const unsigned v = ld_cmd<LIVE>(reinterpret_cast<const unsigned*>(p)); CoefEntry e; e.pos = (uint16_t)(v & 0xffff); e.level = (int16_t)(v >> 16); return e; }
+template <bool LIVE> __device__ __forceinline__ CtuInfo ld_ctu(const CtuInfo* p) {
   CtuInfo c; const uint2* s = reinterpret_cast<const uint2*>(p); uint2* d = reinterpret_cast<uint2*>(&c);
 #pragma unroll
-  for (int i = 0; i < (int)(sizeof(CtuInfo) / 8); i++) d[i] = __ldcg(s + i);
+  for (int i = 0; i < (int)(sizeof(CtuInfo) / 8); i++) d[i] = ld_cmd<LIVE>(s + i);
   return c;
 }
 
@@ -128,6 +130,7 @@ __device__ __forceinline__ int tile_sample(const WarpMem& m, int c, int tx, int 
 
 // One transform block: 8.4.4.2 prediction into the tile, then (if coded) 8.6.3 scaling + 8.6.4 inverse transform
 // + 8.6.6 reconstruction.  (bx, by): position inside the tile in samples of component c.
+template <bool LIVE>
 __device__ __noinline__ void process_tb(WarpMem& m, const int8_t* __restrict__ mat, const RowCtx& r, int c, int bx, int by, int log2n, int mode,
                            const CoefEntry* __restrict__ ce, int ncoef, int qp, int tskip, int lane) {
   const int n = 1 << log2n, sh = c ? 1 : 0, bd = r.bd;
@@ -264,7 +267,7 @@ __device__ __noinline__ void process_tb(WarpMem& m, const int8_t* __restrict__ m
   const long long scale = (long long)(c_level_scale[qp % 6] << (qp / 6)) * 16;
   int maxrow = 0, maxcol = 0;
   for (int i = lane; i < ncoef; i += 32) {
-    const CoefEntry e = ld_coef(&ce[i]);
+    const CoefEntry e = ld_coef<LIVE>(&ce[i]);
     const long long t = ((long long)e.level * scale + (1LL << (bd_shift - 1))) >> bd_shift;
     m.coef[e.pos] = (int16_t)(t < -32768 ? -32768 : (t > 32767 ? 32767 : t));
     maxrow = max(maxrow, e.pos >> log2n); maxcol = max(maxcol, e.pos & (n - 1));
@@ -316,7 +319,8 @@ __device__ __forceinline__ int chroma_qp(int qpy, int off, int bd) {       // 8.
   return qpc + qbd;
 }
 
-__global__ void __launch_bounds__(WARPS * 32) hevc_recon_kernel(const DeviceBatch b) {
+template <bool LIVE>
+__global__ void __launch_bounds__(WARPS * 32, 5) hevc_recon_kernel(const DeviceBatch b) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   int8_t* mat = reinterpret_cast<int8_t*>(smem_raw);                       // 32x32 DCT matrix, shared by the CTA
   for (int i = threadIdx.x; i < 1024; i += blockDim.x) {
@@ -363,29 +367,29 @@ __global__ void __launch_bounds__(WARPS * 32) hevc_recon_kernel(const DeviceBatc
         unsigned spins = 0, ns = 250;
         if (eprog) while (ld_acquire(&eprog[r.ry]) < (unsigned)(r.rx + 1)) {
           __nanosleep(ns); if (ns < 2000) ns <<= 1;
-          if (ld_acquire(b.error_flag)) break;                                     // K0 failed (corrupt stream): its progress will never come
-          if (++spins > (1u << 23)) { atomicExch(b.error_flag, 1u); break; }       // ~16 s; turns a would-be hang into an error
+          if ((++spins & 31u) == 0 && ld_acquire(b.error_flag)) break;            // K0 failed (corrupt stream): its progress will never come
+          if (spins > (1u << 23)) { atomicExch(b.error_flag, 1u); break; }       // ~16 s; turns a would-be hang into an error
         }
         if (r.ry > 0) {
           const unsigned need = (unsigned)min(r.rx + 2, r.wctb);
           spins = 0; ns = 250;
           while (ld_acquire(&prog[r.ry - 1]) < need) {
             __nanosleep(ns); if (ns < 2000) ns <<= 1;
-            if (ld_acquire(b.error_flag)) break;
-            if (++spins > (1u << 23)) { atomicExch(b.error_flag, 1u); break; }
+            if ((++spins & 31u) == 0 && ld_acquire(b.error_flag)) break;
+            if (spins > (1u << 23)) { atomicExch(b.error_flag, 1u); break; }
           }
         }
         abort = ld_acquire(b.error_flag) != 0u;
       }
       abort = __shfl_sync(0xffffffffu, abort, 0);
       if (abort) return;                                     // the batch is reported as failed; nothing it produced is used
-      const CtuInfo ci = ld_ctu(&r.ctus[r.ry * r.wctb + r.rx]);
+      const CtuInfo ci = ld_ctu<LIVE>(&r.ctus[r.ry * r.wctb + r.rx]);
       r.cur_slice = ci.slice_idx;
-      r.nb_slice[0] = r.rx > 0 ? (int)__ldcg(&r.ctus[r.ry * r.wctb + r.rx - 1].slice_idx) : -1;
-      r.nb_slice[1] = (r.rx > 0 && r.ry > 0) ? (int)__ldcg(&r.ctus[(r.ry - 1) * r.wctb + r.rx - 1].slice_idx) : -1;
-      r.nb_slice[2] = r.ry > 0 ? (int)__ldcg(&r.ctus[(r.ry - 1) * r.wctb + r.rx].slice_idx) : -1;
-      r.nb_slice[3] = (r.ry > 0 && r.rx + 1 < r.wctb) ? (int)__ldcg(&r.ctus[(r.ry - 1) * r.wctb + r.rx + 1].slice_idx) : -1;
-      TuCmd next_cmd = ci.tu_count ? ld_tu(&tus[ci.tu_start]) : TuCmd{0, 0, 0, 0};
+      r.nb_slice[0] = r.rx > 0 ? (int)ld_cmd<LIVE>(&r.ctus[r.ry * r.wctb + r.rx - 1].slice_idx) : -1;
+      r.nb_slice[1] = (r.rx > 0 && r.ry > 0) ? (int)ld_cmd<LIVE>(&r.ctus[(r.ry - 1) * r.wctb + r.rx - 1].slice_idx) : -1;
+      r.nb_slice[2] = r.ry > 0 ? (int)ld_cmd<LIVE>(&r.ctus[(r.ry - 1) * r.wctb + r.rx].slice_idx) : -1;
+      r.nb_slice[3] = (r.ry > 0 && r.rx + 1 < r.wctb) ? (int)ld_cmd<LIVE>(&r.ctus[(r.ry - 1) * r.wctb + r.rx + 1].slice_idx) : -1;
+      TuCmd next_cmd = ci.tu_count ? ld_tu<LIVE>(&tus[ci.tu_start]) : TuCmd{0, 0, 0, 0};
       if (r.ry > 0) {
         // fetch the halo row above from HBM/L2
         __syncwarp();
@@ -409,18 +413,18 @@ __global__ void __launch_bounds__(WARPS * 32) hevc_recon_kernel(const DeviceBatc
       const SliceInfo sl = r.slices[ci.slice_idx];
       for (unsigned ti = 0; ti < ci.tu_count; ti++) {
         const TuCmd cmd = next_cmd;
-        if (ti + 1 < ci.tu_count) next_cmd = ld_tu(&tus[ci.tu_start + ti + 1]);      // prefetch: hides one dependent HBM/L2 round trip per TU
+        if (ti + 1 < ci.tu_count) next_cmd = ld_tu<LIVE>(&tus[ci.tu_start + ti + 1]);      // prefetch: hides one dependent HBM/L2 round trip per TU
         const int x4 = cmd.w0 & 0xfff, y4 = (cmd.w0 >> 12) & 0xfff, log2n = 2 + ((cmd.w0 >> 24) & 3);
         const int lmode = cmd.w1 & 63, cmode = (cmd.w1 >> 6) & 63, qpy = (int)((cmd.w1 >> 12) & 0xff) - 64;
         const int nl = cmd.w3 & 0x7ff, ncb = (cmd.w3 >> 11) & 0x3ff, ncr = (cmd.w3 >> 21) & 0x3ff;
         const CoefEntry* ce = coefs + cmd.w2;
         const int bx = (x4 << 2) - r.x0, by = (y4 << 2) - r.y0;
-        process_tb(m, mat, r, 0, bx, by, log2n, lmode, ce, ((cmd.w0 >> 26) & 1) ? nl : 0, qpy + 6 * (r.bd - 8), (cmd.w0 >> 30) & 1, lane);
+        process_tb<LIVE>(m, mat, r, 0, bx, by, log2n, lmode, ce, ((cmd.w0 >> 26) & 1) ? nl : 0, qpy + 6 * (r.bd - 8), (cmd.w0 >> 30) & 1, lane);
         if ((cmd.w0 >> 29) & 1) {
           int cbx, cby, clog;
           if (log2n > 2) { cbx = bx >> 1; cby = by >> 1; clog = log2n - 1; } else { cbx = (bx - 4) >> 1; cby = (by - 4) >> 1; clog = 2; }
-          process_tb(m, mat, r, 1, cbx, cby, clog, cmode, ce + nl, ((cmd.w0 >> 27) & 1) ? ncb : 0, chroma_qp(qpy, sl.cb_qp_offset, r.bd), (cmd.w0 >> 31) & 1, lane);
-          process_tb(m, mat, r, 2, cbx, cby, clog, cmode, ce + nl + ncb, ((cmd.w0 >> 28) & 1) ? ncr : 0, chroma_qp(qpy, sl.cr_qp_offset, r.bd), (cmd.w1 >> 20) & 1, lane);
+          process_tb<LIVE>(m, mat, r, 1, cbx, cby, clog, cmode, ce + nl, ((cmd.w0 >> 27) & 1) ? ncb : 0, chroma_qp(qpy, sl.cb_qp_offset, r.bd), (cmd.w0 >> 31) & 1, lane);
+          process_tb<LIVE>(m, mat, r, 2, cbx, cby, clog, cmode, ce + nl + ncb, ((cmd.w0 >> 28) & 1) ? ncr : 0, chroma_qp(qpy, sl.cr_qp_offset, r.bd), (cmd.w1 >> 20) & 1, lane);
         }
       }
       // write the finished CTB to HBM (coalesced rows), keep its last column as the next CTB's left halo
@@ -453,17 +457,19 @@ __global__ void __launch_bounds__(WARPS * 32) hevc_recon_kernel(const DeviceBatc
 int launch_recon(const DeviceBatch& b, cudaStream_t s) {
   if (b.nrows <= 0) return B200_OK;
   const size_t smem = MAT_BYTES + warp_mem_bytes(b.max_log2_ctb) * WARPS;
-  B200_CUDA_CHECK(cudaFuncSetAttribute(hevc_recon_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(MAT_BYTES + warp_mem_bytes(6) * WARPS)));
+  const bool live = b.entropy_progress != nullptr;
+  auto kern = live ? hevc_recon_kernel<true> : hevc_recon_kernel<false>;
+  B200_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(MAT_BYTES + warp_mem_bytes(6) * WARPS)));
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   int occ = 1;
-  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, hevc_recon_kernel, WARPS * 32, smem);
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, WARPS * 32, smem);
   if (occ < 1) occ = 1;
   if (b.blocks_per_sm > 0 && b.blocks_per_sm < occ) occ = b.blocks_per_sm;
   const int want = (b.nrows + WARPS - 1) / WARPS;
   const int grid = want < sms * occ ? want : sms * occ;
-  hevc_recon_kernel<<<grid, WARPS * 32, smem, s>>>(b);
+  kern<<<grid, WARPS * 32, smem, s>>>(b);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return set_error(B200_E_CUDA, "recon launch: %s", cudaGetErrorString(e));
   return B200_OK;

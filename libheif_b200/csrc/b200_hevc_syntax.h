@@ -160,6 +160,7 @@ struct CabacStream { const uint8_t* d; uint32_t size; };
 struct Cabac {
   uint32_t val, range; int bits;                      // bits: valid look-ahead bits in the low half of val
   uint32_t pos, next16;                               // byte offset of the 16 bits that follow next16's
+  TabPtr lps_tab, next_tab;                           // rangeTabLps / state-transition tables (their shared-window addresses are not free to form on the device)
   // big-endian 16 bits at EVEN byte offset p; offsets past the end read the zero padding the buffer ends in (>= 2 bytes, size even)
   B200_HD static inline uint32_t fetch16(const CabacStream& st, uint32_t p) {
     const uint32_t q = p < st.size - 2 ? p : st.size - 2;
@@ -179,6 +180,7 @@ struct Cabac {
       val = fetch16(st, start_byte) << 9; bits = 7; pos = start_byte + 2;
     }
     range = 510; next16 = fetch16(st, pos);
+    lps_tab = B200_TADDR(kLps4); next_tab = B200_TADDR(kNextState);
   }
   B200_HD inline uint64_t bit_position() const { return (uint64_t)pos * 8 - (uint32_t)bits; }
   // shift the window left by n (n <= 7), merging the prefetched 16 bits when the look-ahead is exhausted
@@ -189,12 +191,12 @@ struct Cabac {
   }
   B200_HD inline int bin(CtxPtr c, const CabacStream& st) {
     const uint32_t cv = ctx_ld(c);
-    const uint32_t rlps = (tab_ld32(B200_TADDR(kLps4), (int)(cv >> 1)) >> (((range >> 6) & 3) * 8)) & 0xff;
+    const uint32_t rlps = (tab_ld32(lps_tab, (int)(cv >> 1)) >> (((range >> 6) & 3) * 8)) & 0xff;
     const uint32_t rmps = range - rlps;
     const uint32_t lps = (val >> 16) >= rmps ? 1u : 0u;
     val -= lps ? (rmps << 16) : 0u;
     range = lps ? rlps : rmps;
-    ctx_st(c, tab_ld8(B200_TADDR(kNextState), (int)(cv | (lps << 7))));
+    ctx_st(c, tab_ld8(next_tab, (int)(cv | (lps << 7))));
 #ifdef B200_SYN_DEVICE
     const int n = __clz((int)range) - 23;
 #else
