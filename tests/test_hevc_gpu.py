@@ -106,3 +106,22 @@ def test_unsupported_and_corrupt_streams_fail_cleanly(dec):
         dec.decode_image(synth_stream("ctb64"), max_image_size_pixels=1000)   # security limit (decoder_libde265.cc:189-198)
     i = dec.decode_image(synth_stream("ctb32"))            # decoder still usable afterwards
     assert i.width == 128
+
+
+@pytest.mark.parametrize("overlap", ["0", "1"])
+def test_entropy_and_reconstruction_sequential_and_concurrent(cuda, overlap, monkeypatch):
+    """K0 (CABAC) and K1 (reconstruction) run back to back for large batches and concurrently -- K1 consuming the command
+    stream CTB by CTB while K0 produces it -- for small ones; both orders must give the oracle's planes."""
+    monkeypatch.setenv("B200_OVERLAP", overlap)
+    d = lb.Decoder(host_threads=4)
+    try:
+        names = ["ctb32_wpp_deep", "slices_wpp", "main12_wpp", "dependent_slices", "tile_1024_like"]
+        for name in names:
+            au = synth_stream(name)
+            want, _ = ob.restatement_decode(au)
+            d.decode_grid([au], 1, 1)
+            got = d.planes_host()
+            for c in range(len(want)):
+                assert np.array_equal(got[c], want[c]), f"{name} plane {c} overlap={overlap}"
+    finally:
+        d.close()
