@@ -18,6 +18,7 @@ namespace b200 { namespace syn {
 __shared__ uint32_t s_kLps4[64];
 __shared__ uint8_t s_kTransLps[64];
 __shared__ uint8_t s_kNextState[256];
+__shared__ unsigned long long s_kState[128];
 __shared__ uint8_t s_kInitI[134];
 __shared__ uint8_t s_kSigMap4[16];
 __shared__ uint8_t s_kScanPos[3][16];
@@ -87,6 +88,7 @@ __global__ void __launch_bounds__(EWARPS * 32, B200_ENTROPY_MIN_BLOCKS) hevc_ent
   for (int i = threadIdx.x; i < 64; i += blockDim.x) { syn::s_kLps4[i] = syn::d_kLps4[i]; syn::s_kTransLps[i] = syn::d_kTransLps[i]; }
   for (int i = threadIdx.x; i < 134; i += blockDim.x) syn::s_kInitI[i] = syn::d_kInitI[i];
   for (int i = threadIdx.x; i < 256; i += blockDim.x) syn::s_kNextState[i] = syn::d_kNextState[i];
+  for (int i = threadIdx.x; i < 128; i += blockDim.x) syn::s_kState[i] = syn::d_kState[i];
   for (int i = threadIdx.x; i < 16; i += blockDim.x) syn::s_kSigMap4[i] = syn::d_kSigMap4[i];
   for (int i = threadIdx.x; i < 48; i += blockDim.x) { (&syn::s_kScanPos[0][0])[i] = (&syn::d_kScanPos[0][0])[i]; (&syn::s_kScanInv[0][0])[i] = (&syn::d_kScanInv[0][0])[i]; (&syn::s_kSigCtx4[0][0])[i] = (&syn::d_kSigCtx4[0][0])[i]; }
   for (int i = threadIdx.x; i < 192; i += blockDim.x) (&syn::s_kSigCtxN[0][0][0])[i] = (&syn::d_kSigCtxN[0][0][0])[i];

@@ -52,6 +52,7 @@ typedef uint32_t TabPtr;
 __device__ __forceinline__ uint32_t ctx_ld(CtxPtr p) { uint32_t v; asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(p) : "memory"); return v; }
 __device__ __forceinline__ void ctx_st(CtxPtr p, uint32_t v) { asm volatile("st.shared.u8 [%0], %1;" ::"r"(p), "r"(v) : "memory"); }
 __device__ __forceinline__ uint32_t tab_ld8(TabPtr p, int i) { uint32_t v; asm("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(p + (uint32_t)i)); return v; }
+__device__ __forceinline__ uint2 tab_ld64(TabPtr p, int i) { uint2 v; asm("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(p + 8u * (uint32_t)i)); return v; }
 __device__ __forceinline__ uint32_t tab_ld32(TabPtr p, int i) { uint32_t v; asm("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(p + 4u * (uint32_t)i)); return v; }
 #define B200_TADDR(name) ((::b200::syn::TabPtr)__cvta_generic_to_shared(&B200_T(name)))
 #else
@@ -61,6 +62,8 @@ inline uint32_t ctx_ld(CtxPtr p) { return *p; }
 inline void ctx_st(CtxPtr p, uint32_t v) { *p = (uint8_t)v; }
 inline uint32_t tab_ld8(TabPtr p, int i) { return p[i]; }
 inline uint32_t tab_ld32(TabPtr p, int i) { uint32_t v; memcpy(&v, p + 4 * (size_t)i, 4); return v; }
+struct U2 { uint32_t x, y; };
+inline U2 tab_ld64(TabPtr p, int i) { uint64_t v; memcpy(&v, p + 8 * (size_t)i, 8); return U2{(uint32_t)v, (uint32_t)(v >> 32)}; }
 #define B200_TADDR(name) (reinterpret_cast<::b200::syn::TabPtr>(&B200_T(name)))
 #endif
 
@@ -151,6 +154,10 @@ struct PicBuffers {              // per-picture arrays (host memory on the host 
 // the host front-end cross-checks against the entry points of every WPP stream it parses.
 B200_TABLE(uint8_t, kNextState, [256], {2,3,4,5,6,7,8,9,10,11,12,13,14,15,16,17,18,19,20,21,22,23,24,25,26,27,28,29,30,31,32,33,34,35,36,37,38,39,40,41,42,43,44,45,46,47,48,49,50,51,52,53,54,55,56,57,58,59,60,61,62,63,64,65,66,67,68,69,70,71,72,73,74,75,76,77,78,79,80,81,82,83,84,85,86,87,88,89,90,91,92,93,94,95,96,97,98,99,100,101,102,103,104,105,106,107,108,109,110,111,112,113,114,115,116,117,118,119,120,121,122,123,124,125,124,125,126,127,1,0,0,1,2,3,4,5,4,5,8,9,8,9,10,11,12,13,14,15,16,17,18,19,18,19,22,23,22,23,24,25,26,27,26,27,30,31,30,31,32,33,32,33,36,37,36,37,38,39,38,39,42,43,42,43,44,45,44,45,46,47,48,49,48,49,50,51,52,53,52,53,54,55,54,55,56,57,58,59,58,59,60,61,60,61,60,61,62,63,64,65,64,65,66,67,66,67,66,67,68,69,68,69,70,71,70,71,70,71,72,73,72,73,72,73,74,75,74,75,74,75,76,77,76,77,126,127})   // [ctx byte | lps << 7] -> next ctx byte ((pStateIdx << 1) | valMps)
 
+// Both tables fused, one 64-bit entry per context byte (pStateIdx << 1 | valMps): bits 0-31 rangeTabLps[0..3], 32-39 next
+// context byte after an MPS, 40-47 after an LPS -- one shared-memory load per bin instead of two dependent ones.
+B200_TABLE(uint64_t, kState, [128], {0x0102f0d0b080ull,0x0003f0d0b080ull,0x0004e3c5a780ull,0x0105e3c5a780ull,0x0206d8bb9e80ull,0x0307d8bb9e80ull,0x0408cdb2967bull,0x0509cdb2967bull,0x040ac3a98e74ull,0x050bc3a98e74ull,0x080cb9a0876full,0x090db9a0876full,0x080eaf988069ull,0x090faf988069ull,0x0a10a6907a64ull,0x0b11a6907a64ull,0x0c129e89745full,0x0d139e89745full,0x0e1496826e5aull,0x0f1596826e5aull,0x10168e7b6855ull,0x11178e7b6855ull,0x121887756351ull,0x131987756351ull,0x121a806f5e4dull,0x131b806f5e4dull,0x161c7a695949ull,0x171d7a695949ull,0x161e74645545ull,0x171f74645545ull,0x18206e5f5042ull,0x19216e5f5042ull,0x1a22685a4c3eull,0x1b23685a4c3eull,0x1a246356483bull,0x1b256356483bull,0x1e265e514538ull,0x1f275e514538ull,0x1e28594d4135ull,0x1f29594d4135ull,0x202a55493e33ull,0x212b55493e33ull,0x202c50453b30ull,0x212d50453b30ull,0x242e4c42382eull,0x252f4c42382eull,0x2430483f352bull,0x2531483f352bull,0x2632453b3229ull,0x2733453b3229ull,0x263441383027ull,0x273541383027ull,0x2a363e362d25ull,0x2b373e362d25ull,0x2a383b332b23ull,0x2b393b332b23ull,0x2c3a38302921ull,0x2d3b38302921ull,0x2c3c352e2720ull,0x2d3d352e2720ull,0x2e3e322b251eull,0x2f3f322b251eull,0x30403029231dull,0x31413029231dull,0x30422d27211bull,0x31432d27211bull,0x32442b251f1aull,0x33452b251f1aull,0x344629231e18ull,0x354729231e18ull,0x344827211c17ull,0x354927211c17ull,0x364a25201b16ull,0x374b25201b16ull,0x364c231e1a15ull,0x374d231e1a15ull,0x384e211d1814ull,0x394f211d1814ull,0x3a501f1b1713ull,0x3b511f1b1713ull,0x3a521e1a1612ull,0x3b531e1a1612ull,0x3c541c191511ull,0x3d551c191511ull,0x3c561b171410ull,0x3d571b171410ull,0x3c581916130full,0x3d591916130full,0x3e5a1815120eull,0x3f5b1815120eull,0x405c1714110eull,0x415d1714110eull,0x405e1613100dull,0x415f1613100dull,0x426015120f0cull,0x436115120f0cull,0x426214110e0cull,0x436314110e0cull,0x426413100e0bull,0x436513100e0bull,0x4466120f0d0bull,0x4567120f0d0bull,0x4468110f0c0aull,0x4569110f0c0aull,0x466a100e0c0aull,0x476b100e0c0aull,0x466c0f0d0b09ull,0x476d0f0d0b09ull,0x466e0e0c0b09ull,0x476f0e0c0b09ull,0x48700e0c0a08ull,0x49710e0c0a08ull,0x48720d0b0908ull,0x49730d0b0908ull,0x48740c0b0907ull,0x49750c0b0907ull,0x4a760c0a0907ull,0x4b770c0a0907ull,0x4a780b0a0807ull,0x4b790b0a0807ull,0x4a7a0b090806ull,0x4b7b0b090806ull,0x4c7c0a090706ull,0x4d7d0a090706ull,0x4c7c09080706ull,0x4d7d09080706ull,0x7e7e02020202ull,0x7f7f02020202ull})
+
 // The sub-stream's bytes (cold: touched once per 16 consumed bits).
 struct CabacStream { const uint8_t* d; uint32_t size; };
 
@@ -160,7 +167,7 @@ struct CabacStream { const uint8_t* d; uint32_t size; };
 struct Cabac {
   uint32_t val, range; int bits;                      // bits: valid look-ahead bits in the low half of val
   uint32_t pos, next16;                               // byte offset of the 16 bits that follow next16's
-  TabPtr lps_tab, next_tab;                           // rangeTabLps / state-transition tables (their shared-window addresses are not free to form on the device)
+  TabPtr state_tab;                                   // kState (its shared-window address is not free to form on the device)
   // big-endian 16 bits at EVEN byte offset p; offsets past the end read the zero padding the buffer ends in (>= 2 bytes, size even)
   B200_HD static inline uint32_t fetch16(const CabacStream& st, uint32_t p) {
     const uint32_t q = p < st.size - 2 ? p : st.size - 2;
@@ -180,7 +187,7 @@ struct Cabac {
       val = fetch16(st, start_byte) << 9; bits = 7; pos = start_byte + 2;
     }
     range = 510; next16 = fetch16(st, pos);
-    lps_tab = B200_TADDR(kLps4); next_tab = B200_TADDR(kNextState);
+    state_tab = B200_TADDR(kState);
   }
   B200_HD inline uint64_t bit_position() const { return (uint64_t)pos * 8 - (uint32_t)bits; }
   // shift the window left by n (n <= 7), merging the prefetched 16 bits when the look-ahead is exhausted
@@ -191,12 +198,17 @@ struct Cabac {
   }
   B200_HD inline int bin(CtxPtr c, const CabacStream& st) {
     const uint32_t cv = ctx_ld(c);
-    const uint32_t rlps = (tab_ld32(lps_tab, (int)(cv >> 1)) >> (((range >> 6) & 3) * 8)) & 0xff;
+    const auto e = tab_ld64(state_tab, (int)cv);
+#ifdef B200_SYN_DEVICE
+    const uint32_t rlps = __byte_perm(0u, e.x, range >> 6);          // range in [256, 510]: selector 4..7 = byte (range >> 6) & 3 of e.x
+#else
+    const uint32_t rlps = (e.x >> (((range >> 6) & 3) * 8)) & 0xff;
+#endif
     const uint32_t rmps = range - rlps;
     const uint32_t lps = (val >> 16) >= rmps ? 1u : 0u;
     val -= lps ? (rmps << 16) : 0u;
     range = lps ? rlps : rmps;
-    ctx_st(c, tab_ld8(next_tab, (int)(cv | (lps << 7))));
+    ctx_st(c, lps ? e.y >> 8 : e.y);                                  // the store keeps the low byte
 #ifdef B200_SYN_DEVICE
     const int n = __clz((int)range) - 23;
 #else
@@ -204,7 +216,7 @@ struct Cabac {
 #endif
     range <<= n;
     shift(n, st);
-    return (int)((cv & 1) ^ lps);
+    return (int)((cv ^ lps) & 1u);
   }
   B200_HD inline int bypass(const CabacStream& st) {
     shift(1, st);
@@ -371,13 +383,14 @@ struct Decoder {
       // sig_coeff_flag (9.3.4.2.5): context = per-sub-block base + table entry per scan position; DC of the block has its own
       const TabPtr tab = log2n == 2 ? B200_TADDR(kSigCtx4) + 16 * scan : B200_TADDR(kSigCtxN) + (64 * scan + 16 * (right | (below << 1)));
       const int off = sig_base + ((c == 0 && log2n > 2 && (xs | ys)) ? 3 : 0);
+      // flags are shifted in from the right: after the last position (k = 0) bit k of `sig` is the flag of scan position k
       unsigned sig = 0;
       int k = 15;
-      if (i == last_sb) { sig = 1u << last_pos; k = last_pos - 1; }
+      if (i == last_sb) { sig = 1u; k = last_pos - 1; }
       B200_NOUNROLL for (; k >= 0; k--) {
         int ci = off + (int)tab_ld8(tab, k);
         if (k == 0) { if (infer_dc && !sig) { sig = 1u; break; } if (i == 0) ci = dc_ctx; }
-        if (cb_.bin(cx + (ci), stream)) sig |= 1u << k;
+        sig = (sig << 1) | (unsigned)cb_.bin(cx + (ci), stream);
       }
       if (!sig) continue;
       unsigned g1 = 0;
