@@ -124,6 +124,25 @@ static int check_device_error(b200_decoder* d) {
 // (128 tiles: 109 vs 101 ms, 256 tiles: 195 vs 126 ms; the two instruction streams evict each other), so it is chosen
 // per batch.  B200_OVERLAP=0/1 forces it.
 static int overlap_blocks(const char* env, int dflt) { if (const char* e = getenv(env)) { const int v = atoi(e); if (v >= 1 && v <= 4) return v; } return dflt; }
+// At most ONE overlapped K0/K1 pair is in flight per process: libheif drives many decoder instances from its own threads,
+// and the spinning K1 grids of many instances must never be able to keep all their K0 grids off the GPU.  A batch that
+// finds the slot taken simply runs its kernels back to back.
+// (Successive batches of the SAME decoder are ordered by its stream and may all overlap.)
+static std::mutex g_overlap_mutex;
+static const void* g_overlap_owner = nullptr;
+static int g_overlap_count = 0;
+static bool overlap_acquire(const void* who) {
+  std::lock_guard<std::mutex> lk(g_overlap_mutex);
+  if (g_overlap_owner && g_overlap_owner != who) return false;
+  g_overlap_owner = who; g_overlap_count++;
+  return true;
+}
+static void overlap_release() {
+  std::lock_guard<std::mutex> lk(g_overlap_mutex);
+  if (g_overlap_count > 0 && --g_overlap_count == 0) g_overlap_owner = nullptr;
+}
+static void CUDART_CB overlap_done(void*) { overlap_release(); }
+
 static bool use_overlap(size_t n_subs) {
   if (const char* e = getenv("B200_OVERLAP")) return atoi(e) != 0;
   int dev = 0, sms = 148; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
@@ -136,7 +155,9 @@ static int run_device_pipeline(b200_decoder* d, int n, cudaStream_t s, int* laun
   int rc;
   int launches = 0;
   const bool devfe = d->used_device_front_end;
-  const bool overlap = devfe && use_overlap(d->n_subs);
+  bool overlap = devfe && use_overlap(d->n_subs);
+  if (overlap) overlap = overlap_acquire(d);
+  struct Release { bool armed; ~Release() { if (armed) overlap_release(); } } release{overlap};   // error paths
   cudaEventRecord(d->ev[1], s);
   DeviceBatch b{};
   b.pics = d->pics.d; b.npics = n; b.ctus = d->ctus.d; b.tus = d->tus.d; b.coefs = d->coefs.d; b.slices = d->slices.d;
@@ -164,7 +185,11 @@ static int run_device_pipeline(b200_decoder* d, int n, cudaStream_t s, int* laun
     launches += 1;
   } else cudaEventRecord(d->ev[5], s);
   if ((rc = launch_recon(b, s))) return rc;
-  if (devfe && overlap) B200_CUDA_CHECK(cudaStreamWaitEvent(s, d->ev_join, 0));
+  if (devfe && overlap) {
+    B200_CUDA_CHECK(cudaStreamWaitEvent(s, d->ev_join, 0));
+    B200_CUDA_CHECK(cudaLaunchHostFunc(s, overlap_done, nullptr));   // the slot is free once K0 and K1 have both finished
+    release.armed = false;
+  }
   cudaEventRecord(d->ev[2], s);
   launches += 1;
   if (d->debug_stage != 1) { if ((rc = launch_deblock(b, d->pics.h, s))) return rc; launches += 2; }

@@ -62,7 +62,7 @@ struct DevSync {
     unsigned long long t0; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
     unsigned ns = 500, spins = 0;
     for (;;) {
-      __nanosleep(ns); if (ns < 4000) ns <<= 1;
+      __nanosleep(ns); if (ns < 16000) ns <<= 1;
       if (e_ld_acquire(p) >= need) return;
       if ((++spins & 31u) != 0) continue;
       if (e_ld_acquire(error_flag)) return;              // a producer failed: do not wait for progress that will never come

@@ -366,15 +366,15 @@ __global__ void __launch_bounds__(WARPS * 32, 5) hevc_recon_kernel(const DeviceB
       if (lane == 0) {
         unsigned spins = 0, ns = 250;
         if (eprog) while (ld_acquire(&eprog[r.ry]) < (unsigned)(r.rx + 1)) {
-          __nanosleep(ns); if (ns < 2000) ns <<= 1;
+          __nanosleep(ns); if (ns < 8000) ns <<= 1;
           if ((++spins & 31u) == 0 && ld_acquire(b.error_flag)) break;            // K0 failed (corrupt stream): its progress will never come
-          if (spins > (1u << 23)) { atomicExch(b.error_flag, 1u); break; }       // ~16 s; turns a would-be hang into an error
+          if (spins > (1u << 23)) { atomicExch(b.error_flag, 1u); break; }       // ~1 min; turns a would-be hang into an error
         }
         if (r.ry > 0) {
           const unsigned need = (unsigned)min(r.rx + 2, r.wctb);
           spins = 0; ns = 250;
           while (ld_acquire(&prog[r.ry - 1]) < need) {
-            __nanosleep(ns); if (ns < 2000) ns <<= 1;
+            __nanosleep(ns); if (ns < 8000) ns <<= 1;
             if ((++spins & 31u) == 0 && ld_acquire(b.error_flag)) break;
             if (spins > (1u << 23)) { atomicExch(b.error_flag, 1u); break; }
           }
