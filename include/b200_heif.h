@@ -183,7 +183,8 @@ typedef struct b200_decode_stats {
   double entropy_ms, recon_ms, deblock_ms, sao_ms;      /* per-kernel device times of the last call (entropy_ms: device front-end only) */
   uint64_t bitstream_bytes, command_bytes, coefficient_entries, transform_units, ctus, h2d_bytes, pixels;
   int kernel_launches;
-  int front_end;                                        /* 1 = CABAC decoded on the GPU, 0 = on the host cores */
+  int front_end;                                        /* 0 = CABAC decoded on the host cores, 1 = on the GPU, 2 = on the GPU with the
+                                                           reconstruction kernel running concurrently (entropy_ms then covers both) */
 } b200_decode_stats;
 
 /* host_threads: CABAC parser threads (0 = number of online cores).  The CUDA device is the current one. */

@@ -92,6 +92,7 @@ struct b200_decoder {
   cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};   // 0 start, 1 after H2D, 5 after entropy, 2 after recon, 3 after deblock, 4 after SAO
   cudaStream_t last_stream = nullptr;
   cudaStream_t side = nullptr;     // K0 runs here, concurrently with K1 on the caller's stream
+  bool last_overlapped = false;
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   bool have_result = false;
   int debug_stage = 0;
@@ -158,6 +159,7 @@ static int run_device_pipeline(b200_decoder* d, int n, cudaStream_t s, int* laun
   bool overlap = devfe && use_overlap(d->n_subs);
   if (overlap) overlap = overlap_acquire(d);
   struct Release { bool armed; ~Release() { if (armed) overlap_release(); } } release{overlap};   // error paths
+  d->last_overlapped = overlap;
   cudaEventRecord(d->ev[1], s);
   DeviceBatch b{};
   b.pics = d->pics.d; b.npics = n; b.ctus = d->ctus.d; b.tus = d->tus.d; b.coefs = d->coefs.d; b.slices = d->slices.d;
@@ -416,7 +418,7 @@ int b200_decoder_get_stats(b200_decoder* d, b200_decode_stats* out) {
   cudaEventElapsedTime(&c, d->ev[2], d->ev[3]); cudaEventElapsedTime(&e, d->ev[3], d->ev[4]);
   if (b < 0) { en += b; b = 0; }   // K0 and K1 overlap: recon_ms is the part of K1 that runs after K0 has finished
   d->stats.h2d_ms = a; d->stats.entropy_ms = en; d->stats.recon_ms = b; d->stats.deblock_ms = c; d->stats.sao_ms = e; d->stats.gpu_ms = en + b + c + e;
-  d->stats.front_end = d->used_device_front_end ? 1 : 0;
+  d->stats.front_end = d->used_device_front_end ? (d->last_overlapped ? 2 : 1) : 0;
   if (d->used_device_front_end) {
     B200_CUDA_CHECK(cudaMemcpy(d->ecount.h, d->ecount.d, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
     d->stats.transform_units = d->ecount.h[0]; d->stats.coefficient_entries = d->ecount.h[1];
