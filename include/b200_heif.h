@@ -67,9 +67,18 @@ typedef struct b200_planes {
 typedef struct b200_geometry {
   int m[6];          /* src_x = m[0]*u + m[1]*v + m[2] ;  src_y = m[3]*u + m[4]*v + m[5] */
   int out_w, out_h;  /* size of the transformed picture */
+  /* The reference converts a subsampled picture to 4:4:4 before a transform its plane-wise code cannot express -- 4:2:0:
+     rotate 90 with odd width, 180 with an odd side, 270 with odd height; any mirror with an odd side; crop with odd left
+     or top (pixelimage.cc:1187-1215, 1370-1396, 1458-1481).  The composition functions record that point: transforms
+     before it are kept in `pre` (applied to the subsampled planes), then chroma is upsampled bilinearly
+     (Op_YCbCr420_bilinear_to_YCbCr444, what convert_colorspace picks there), then `m` applies to the 4:4:4 picture. */
+  int chroma;        /* chroma format the chain started from (B200_CHROMA_*); decides the rules above */
+  int detour;        /* 1: the 4:4:4 conversion point was reached */
+  int pre[6]; int pre_w, pre_h;
 } b200_geometry;
 
-void b200_geometry_identity(int width, int height, b200_geometry* g);
+void b200_geometry_identity(int width, int height, b200_geometry* g);               /* = b200_geometry_init(width, height, B200_CHROMA_420, g) */
+void b200_geometry_init(int width, int height, int chroma, b200_geometry* g);
 int b200_geometry_rotate_ccw(b200_geometry* g, int degrees /*0,90,180,270*/);   /* HeifPixelImage::rotate_ccw, pixelimage.cc:1175-1333 */
 int b200_geometry_mirror(b200_geometry* g, int direction /*heif_transform_mirror_direction: 0 = vertical (top<->bottom), 1 = horizontal (left<->right)*/); /* pixelimage.cc:1336-1424 */
 int b200_geometry_crop(b200_geometry* g, int left, int right, int top, int bottom); /* HeifPixelImage::crop, inclusive right/bottom, pixelimage.cc:1433-1546 */

@@ -18,7 +18,8 @@ class Planes(C.Structure):
 
 
 class Geometry(C.Structure):
-    _fields_ = [("m", C.c_int * 6), ("out_w", C.c_int), ("out_h", C.c_int)]
+    _fields_ = [("m", C.c_int * 6), ("out_w", C.c_int), ("out_h", C.c_int), ("chroma", C.c_int), ("detour", C.c_int),
+                ("pre", C.c_int * 6), ("pre_w", C.c_int), ("pre_h", C.c_int)]
 
 
 class ColorOptions(C.Structure):
@@ -44,6 +45,8 @@ def lib():
         _lib.b200_last_error.restype = C.c_char_p
         _lib.b200_geometry_identity.argtypes = [C.c_int, C.c_int, C.POINTER(Geometry)]
         _lib.b200_geometry_identity.restype = None
+        _lib.b200_geometry_init.argtypes = [C.c_int, C.c_int, C.c_int, C.POINTER(Geometry)]
+        _lib.b200_geometry_init.restype = None
         _lib.b200_geometry_rotate_ccw.argtypes = [C.POINTER(Geometry), C.c_int]
         _lib.b200_geometry_mirror.argtypes = [C.POINTER(Geometry), C.c_int]
         _lib.b200_geometry_crop.argtypes = [C.POINTER(Geometry)] + [C.c_int] * 4

@@ -24,9 +24,10 @@ _BYTES_PER_PIXEL = {10: 3, 11: 4, 12: 6, 13: 8, 14: 6, 15: 8}
 class Geometry:
     """Chain of irot / imir / clap transforms, composed in the order libheif applies them."""
 
-    def __init__(self, width: int, height: int):
+    def __init__(self, width: int, height: int, chroma: int = 1):
+        """chroma: B200_CHROMA_* of the picture the chain applies to (decides where the reference converts to 4:4:4 first)."""
         self.g = _lib.Geometry()
-        _lib.lib().b200_geometry_identity(width, height, C.byref(self.g))
+        _lib.lib().b200_geometry_init(width, height, chroma, C.byref(self.g))
 
     def rotate_ccw(self, degrees: int) -> "Geometry":
         _lib.check(_lib.lib().b200_geometry_rotate_ccw(C.byref(self.g), degrees))

@@ -18,9 +18,13 @@ int b200_version(void) { return 100; }
 
 void b200_ycbcr_to_rgb_coefficients(int mc, int cp, float out[4]) { ycbcr_to_rgb_coefficients(mc, cp, out); }
 
-void b200_geometry_identity(int w, int h, b200_geometry* g) {
+void b200_geometry_init(int w, int h, int chroma, b200_geometry* g) {
   g->m[0] = 1; g->m[1] = 0; g->m[2] = 0; g->m[3] = 0; g->m[4] = 1; g->m[5] = 0; g->out_w = w; g->out_h = h;
+  g->chroma = chroma; g->detour = 0;
+  for (int i = 0; i < 6; i++) g->pre[i] = g->m[i];
+  g->pre_w = w; g->pre_h = h;
 }
+void b200_geometry_identity(int w, int h, b200_geometry* g) { b200_geometry_init(w, h, B200_CHROMA_420, g); }
 
 // new(u,v) -> old(u',v') = T(u,v), then old mapping applied: m' = m o T
 static void compose(b200_geometry* g, const int t[6], int nw, int nh) {
@@ -31,25 +35,44 @@ static void compose(b200_geometry* g, const int t[6], int nw, int nh) {
   g->out_w = nw; g->out_h = nh;
 }
 
+// The reference's "need_conversion" tests (pixelimage.cc:1187-1215 rotate, 1370-1381 mirror, 1458-1467 crop), on the picture
+// as it is at this point of the chain.  Once taken, the picture is 4:4:4 and no further test applies.
+static void detour_if(b200_geometry* g, bool need) {
+  if (!need || g->detour) return;
+  for (int i = 0; i < 6; i++) g->pre[i] = g->m[i];
+  g->pre_w = g->out_w; g->pre_h = g->out_h;
+  g->m[0] = 1; g->m[1] = 0; g->m[2] = 0; g->m[3] = 0; g->m[4] = 1; g->m[5] = 0;
+  g->detour = 1;
+}
+
 int b200_geometry_rotate_ccw(b200_geometry* g, int degrees) {
   const int w = g->out_w, h = g->out_h;
   if (degrees == 0) return B200_OK;
-  if (degrees == 90) { const int t[6] = {0, -1, w - 1, 1, 0, 0}; compose(g, t, h, w); return B200_OK; }        // out[y][x] = in[x][w-1-y]
-  if (degrees == 180) { const int t[6] = {-1, 0, w - 1, 0, -1, h - 1}; compose(g, t, w, h); return B200_OK; }
-  if (degrees == 270) { const int t[6] = {0, 1, 0, -1, 0, h - 1}; compose(g, t, h, w); return B200_OK; }       // out[y][x] = in[h-1-x][y]
-  return set_error(B200_E_INVALID, "rotation %d", degrees);
+  if (degrees != 90 && degrees != 180 && degrees != 270) return set_error(B200_E_INVALID, "rotation %d", degrees);
+  const bool ow = w & 1, oh = h & 1;
+  if (g->chroma == B200_CHROMA_422) detour_if(g, degrees == 90 || degrees == 270 || (degrees == 180 && oh));
+  else if (g->chroma == B200_CHROMA_420) detour_if(g, (degrees == 90 && ow) || (degrees == 180 && (ow || oh)) || (degrees == 270 && oh));
+  if (degrees == 90) { const int t[6] = {0, -1, w - 1, 1, 0, 0}; compose(g, t, h, w); }        // out[y][x] = in[x][w-1-y]
+  else if (degrees == 180) { const int t[6] = {-1, 0, w - 1, 0, -1, h - 1}; compose(g, t, w, h); }
+  else { const int t[6] = {0, 1, 0, -1, 0, h - 1}; compose(g, t, h, w); }                       // out[y][x] = in[h-1-x][y]
+  return B200_OK;
 }
 
 int b200_geometry_mirror(b200_geometry* g, int direction) {
   const int w = g->out_w, h = g->out_h;
-  if (direction == 1) { const int t[6] = {-1, 0, w - 1, 0, 1, 0}; compose(g, t, w, h); return B200_OK; }
-  if (direction == 0) { const int t[6] = {1, 0, 0, 0, -1, h - 1}; compose(g, t, w, h); return B200_OK; }
-  return set_error(B200_E_INVALID, "mirror direction %d", direction);
+  if (direction != 0 && direction != 1) return set_error(B200_E_INVALID, "mirror direction %d", direction);
+  if (g->chroma == B200_CHROMA_422) detour_if(g, direction == 1 && (w & 1));
+  else if (g->chroma == B200_CHROMA_420) detour_if(g, (w & 1) || (h & 1));
+  if (direction == 1) { const int t[6] = {-1, 0, w - 1, 0, 1, 0}; compose(g, t, w, h); }
+  else { const int t[6] = {1, 0, 0, 0, -1, h - 1}; compose(g, t, w, h); }
+  return B200_OK;
 }
 
 int b200_geometry_crop(b200_geometry* g, int left, int right, int top, int bottom) {
   if (left < 0 || top < 0 || right >= g->out_w || bottom >= g->out_h || right < left || bottom < top)
     return set_error(B200_E_INVALID, "crop window outside image");
+  if (g->chroma == B200_CHROMA_422) detour_if(g, left & 1);
+  else if (g->chroma == B200_CHROMA_420) detour_if(g, (left & 1) || (top & 1));
   const int t[6] = {1, 0, left, 0, 1, top};
   compose(g, t, right - left + 1, bottom - top + 1);
   return B200_OK;

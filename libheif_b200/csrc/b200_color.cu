@@ -371,6 +371,62 @@ void ycbcr_to_rgb_coefficients(int matrix, int primaries, float out[4]) {
   } else { out[0] = 1.402f; out[1] = -0.344136f; out[2] = -0.714136f; out[3] = 1.772f; }
 }
 
+// Plane-wise geometry (rotate / mirror / crop on a 4:2:0 picture as the reference's ComponentStorage code does it) for
+// the transforms that precede the 4:4:4 conversion point: luma-resolution planes follow the affine map, chroma planes
+// follow it at half resolution (those transforms keep the 2x2 chroma grid aligned, otherwise the conversion point would
+// have been earlier).
+template <typename T>
+__global__ void plane_geometry_kernel(const T* __restrict__ in, long long in_stride, T* __restrict__ out, long long out_stride, int out_w, int out_h,
+                                      int m0, int m1, int m2, int m3, int m4, int m5, int shift) {
+  const int u = blockIdx.x * blockDim.x + threadIdx.x, v = blockIdx.y;
+  if (u >= out_w || v >= out_h) return;
+  const int sx = (m0 * (u << shift) + m1 * (v << shift) + m2) >> shift, sy = (m3 * (u << shift) + m4 * (v << shift) + m5) >> shift;
+  out[(long long)v * out_stride + u] = in[(long long)sy * in_stride + sx];
+}
+
+int launch_color(const b200_planes* in, const b200_geometry* g, const b200_color_options* opt, void* out, void* out_g,
+                 void* out_b, size_t out_stride, cudaStream_t stream, int* pipeline);
+
+// 4:2:0 picture -> (plane-wise geometry `pre`) -> Op_YCbCr420_bilinear_to_YCbCr444 -> the rest of the chain and the colour
+// conversion from 4:4:4.  Serves the reference's 4:4:4 conversion point and bilinear upsampling after geometry.
+static int convert_via_444(const b200_planes* in, const b200_geometry* g, const b200_color_options* opt, void* out, void* out_g, void* out_b,
+                           size_t out_stride, cudaStream_t stream, int* pipeline) {
+  const int bps = in->bit_depth > 8 ? 2 : 1;
+  const int pw = g->pre_w, ph = g->pre_h, pcw = (pw + 1) / 2, pch = (ph + 1) / 2;
+  const bool pre_identity = g->pre[0] == 1 && g->pre[1] == 0 && g->pre[2] == 0 && g->pre[3] == 0 && g->pre[4] == 1 && g->pre[5] == 0 && pw == in->width && ph == in->height;
+  const size_t pitch = (((size_t)pw * bps) + 255) & ~(size_t)255, cpitch = (((size_t)pcw * bps) + 255) & ~(size_t)255;
+  const size_t n_full = pitch * ph, n_c = cpitch * pch;
+  char* tmp = nullptr;
+  B200_CUDA_CHECK(cudaMallocAsync(&tmp, 4 * n_full + 2 * n_c, stream));    // Y', A', Cb444, Cr444, Cb', Cr'
+  char *ty = tmp, *ta = tmp + n_full, *u_cb = tmp + 2 * n_full, *u_cr = tmp + 3 * n_full, *tcb = tmp + 4 * n_full, *tcr = tmp + 4 * n_full + n_c;
+  b200_planes p = *in;
+  if (!pre_identity) {
+    const int* q = g->pre;
+    auto run = [&](const void* src, size_t sstride, void* dst, size_t dstride, int w, int h, int shift) {
+      dim3 grid((w + 255) / 256, h);
+      if (bps == 1) plane_geometry_kernel<uint8_t><<<grid, 256, 0, stream>>>((const uint8_t*)src, (long long)sstride, (uint8_t*)dst, (long long)dstride, w, h, q[0], q[1], q[2], q[3], q[4], q[5], shift);
+      else plane_geometry_kernel<uint16_t><<<grid, 256, 0, stream>>>((const uint16_t*)src, (long long)sstride / 2, (uint16_t*)dst, (long long)dstride / 2, w, h, q[0], q[1], q[2], q[3], q[4], q[5], shift);
+    };
+    run(in->y, in->y_stride, ty, pitch, pw, ph, 0);
+    run(in->cb, in->c_stride, tcb, cpitch, pcw, pch, 1);
+    run(in->cr, in->c_stride, tcr, cpitch, pcw, pch, 1);
+    if (in->alpha) run(in->alpha, in->alpha_stride, ta, pitch, pw, ph, 0);
+    p.y = ty; p.y_stride = pitch; p.cb = tcb; p.cr = tcr; p.c_stride = cpitch;
+    if (in->alpha) { p.alpha = ta; p.alpha_stride = pitch; }
+    p.width = pw; p.height = ph;
+  }
+  dim3 grid((pw + 255) / 256, ph);
+  if (bps == 1) bilinear_420_to_444_kernel<uint8_t><<<grid, 256, 0, stream>>>((const uint8_t*)p.cb, (const uint8_t*)p.cr, (long long)p.c_stride, (uint8_t*)u_cb, (uint8_t*)u_cr, (long long)pitch, pw, ph);
+  else bilinear_420_to_444_kernel<uint16_t><<<grid, 256, 0, stream>>>((const uint16_t*)p.cb, (const uint16_t*)p.cr, (long long)p.c_stride / 2, (uint16_t*)u_cb, (uint16_t*)u_cr, (long long)pitch / 2, pw, ph);
+  p.cb = u_cb; p.cr = u_cr; p.c_stride = pitch; p.chroma = B200_CHROMA_444;
+  b200_geometry rest = *g; rest.detour = 0; rest.chroma = B200_CHROMA_444;
+  b200_color_options o2 = *opt; o2.chroma_upsampling = 0;
+  int rc = launch_color(&p, &rest, &o2, out, out_g, out_b, out_stride, stream, pipeline);
+  if (pipeline) *pipeline |= B200_PIPE_BILINEAR;
+  cudaFreeAsync(tmp, stream);
+  return rc;
+}
+
 // Mirror of the reference planner's choice for the supported states (colorconversion.cc:279-435; the
 // measured pipelines are tabulated in SURVEY.md Appendix A and re-checked by tests/test_color_parity.py).
 int launch_color(const b200_planes* in, const b200_geometry* g, const b200_color_options* opt, void* out, void* out_g,
@@ -385,11 +441,36 @@ int launch_color(const b200_planes* in, const b200_geometry* g, const b200_color
   if (in->chroma != B200_CHROMA_MONO && (mc == 0 || mc == 8 || mc == 11 || mc == 14 || mc == 16))
     return set_error(B200_E_UNSUPPORTED, "matrix_coefficients %d has no linear YCbCr->RGB path here", mc);
   if (interleaved16 && in->bit_depth == 8) return set_error(B200_E_UNSUPPORTED, "8-bit input to RRGGBB output");
+  const bool subsampled = in->chroma == B200_CHROMA_420 || in->chroma == B200_CHROMA_422;
+  if (g->detour && !subsampled) {
+    // the chain was composed with the rules of a subsampled format but the picture is not subsampled: one affine map
+    b200_geometry t = *g; t.detour = 0;
+    t.m[0] = g->pre[0] * g->m[0] + g->pre[1] * g->m[3]; t.m[1] = g->pre[0] * g->m[1] + g->pre[1] * g->m[4]; t.m[2] = g->pre[0] * g->m[2] + g->pre[1] * g->m[5] + g->pre[2];
+    t.m[3] = g->pre[3] * g->m[0] + g->pre[4] * g->m[3]; t.m[4] = g->pre[3] * g->m[1] + g->pre[4] * g->m[4]; t.m[5] = g->pre[3] * g->m[2] + g->pre[4] * g->m[5] + g->pre[5];
+    return launch_color(in, &t, opt, out, out_g, out_b, out_stride, stream, pipeline);
+  }
+  const bool geom_identity = g->m[0] == 1 && g->m[1] == 0 && g->m[2] == 0 && g->m[3] == 0 && g->m[4] == 1 && g->m[5] == 0 && g->out_w == in->width && g->out_h == in->height && !g->detour;
+  if (subsampled && !geom_identity && g->chroma != in->chroma)
+    return set_error(B200_E_INVALID, "geometry was composed for chroma format %d, the picture has %d (b200_geometry_init)", g->chroma, in->chroma);
+  if (g->detour) {
+    // 4:4:4 conversion point of the reference (see b200_geometry)
+    if (in->chroma != B200_CHROMA_420) return set_error(B200_E_UNSUPPORTED, "4:2:2 picture needs the 4:4:4 detour of the reference (Op_YCbCr422_bilinear_to_YCbCr444)");
+    if (!in->full_range) return set_error(B200_E_UNSUPPORTED, "limited-range 4:2:0 picture with an odd-origin crop / odd-size rotate or mirror: the reference range-converts it through RGB");
+    return convert_via_444(in, g, opt, out, out_g, out_b, out_stride, stream, pipeline);
+  }
   if (opt->chroma_upsampling == 1 && in->chroma == B200_CHROMA_420) {
     // heif_color_conversion_options.only_use_preferred_chroma_algorithm with bilinear upsampling: the reference runs
     // Op_YCbCr420_bilinear_to_YCbCr444 first and converts from 4:4:4 with the generic float op.
     const bool identity = g->m[0] == 1 && g->m[1] == 0 && g->m[2] == 0 && g->m[3] == 0 && g->m[4] == 1 && g->m[5] == 0 && g->out_w == in->width && g->out_h == in->height;
-    if (!identity) return set_error(B200_E_UNSUPPORTED, "bilinear chroma upsampling combined with rotate/mirror/crop");
+    if (!identity) {
+      // geometry happens on the planes BEFORE the colour conversion in the reference, so the bilinear op sees the
+      // transformed 4:2:0 picture: all of the chain is `pre`, nothing is left after the upsampling
+      b200_geometry t = *g; t.detour = 1;
+      for (int i = 0; i < 6; i++) t.pre[i] = g->m[i];
+      t.pre_w = g->out_w; t.pre_h = g->out_h;
+      t.m[0] = 1; t.m[1] = 0; t.m[2] = 0; t.m[3] = 0; t.m[4] = 1; t.m[5] = 0;
+      return convert_via_444(in, &t, opt, out, out_g, out_b, out_stride, stream, pipeline);
+    }
     const int bps = in->bit_depth > 8 ? 2 : 1;
     const size_t pitch = (((size_t)in->width * bps) + 255) & ~(size_t)255;
     char* tmp = nullptr;

@@ -46,10 +46,36 @@ static void plane_mirror(uint16_t* d, int w, int h, int direction) {           /
   else { for (int y = 0; y < h / 2; y++) for (int x = 0; x < w; x++) { uint16_t t = d[y * w + x]; d[y * w + x] = d[(h - 1 - y) * w + x]; d[(h - 1 - y) * w + x] = t; } }
 }
 
-static void co_geometry(co_image* im, const int* ops, int nops) {
+void co_bilinear_420_to_444(const uint16_t* in, int w, int h, uint16_t* out);
+
+/* rotate_ccw / mirror_inplace / crop on subsampled images the plane-wise code cannot handle first convert to 4:4:4
+ * (pixelimage.cc:1187-1215, 1370-1396, 1458-1481): convert_colorspace(YCbCr, 4:4:4, nclx_profile() /+ undefined, but
+ * full_range_flag = true +/, bpp, default options) = Op_YCbCr420_bilinear_to_YCbCr444 for a full-range 4:2:0 image.  A
+ * limited-range image would additionally be range-converted through RGB (the default target profile is full range) and a
+ * 4:2:2 one needs Op_YCbCr422_bilinear_to_YCbCr444: neither is restated -> -1. */
+static int co_detour_needed(const co_image* im, const int* o) {
+  const int ow = im->w & 1, oh = im->h & 1;
+  if (im->chroma == 2) {
+    if (o[0] == 1) return (o[1] == 90 || o[1] == 270) || (o[1] == 180 && oh);
+    if (o[0] == 2) return o[1] == 1 && ow;
+    if (o[0] == 3) return o[1] & 1;
+  } else if (im->chroma == 1) {
+    if (o[0] == 1) return (o[1] == 90 && ow) || (o[1] == 180 && (ow || oh)) || (o[1] == 270 && oh);
+    if (o[0] == 2) return ow || oh;
+    if (o[0] == 3) return (o[1] & 1) || (o[3] & 1);
+  }
+  return 0;
+}
+
+static int co_geometry(co_image* im, const int* ops, int nops, int full_range) {
   for (int i = 0; i < nops; i++) {
     const int* o = ops + 5 * i;
     int np = im->chroma ? 3 : 1;
+    if (co_detour_needed(im, o)) {
+      if (im->chroma != 1 || !full_range) return -1;
+      for (int c = 1; c <= 2; c++) { uint16_t* up = (uint16_t*)malloc((size_t)im->w * im->h * 2 + 2); co_bilinear_420_to_444(im->p[c], im->w, im->h, up); free(im->p[c]); im->p[c] = up; }
+      im->chroma = 3; im->cw = im->w; im->ch = im->h;
+    }
     if (o[0] == 1 && o[1] != 0) {
       for (int c = 0; c < 4; c++) {
         if (!im->p[c]) continue;
@@ -76,6 +102,7 @@ static void co_geometry(co_image* im, const int* ops, int nops) {
       im->w = nw; im->h = nh; im->cw = ncw; im->ch = nch;
     }
   }
+  return 0;
 }
 
 /* nclx.cc:84-173 */
@@ -172,8 +199,9 @@ long co_postprocess2(const uint16_t* y, const uint16_t* cb, const uint16_t* cr, 
     size_t n = (size_t)((c == 1 || c == 2) ? im.cw * im.ch : w * h);
     im.p[c] = (uint16_t*)malloc(n * 2 + 2); memcpy(im.p[c], src[c], n * 2);
   }
-  co_geometry(&im, ops, nops);
+  if (co_geometry(&im, ops, nops, full_range)) { co_free(&im); return -2; }
   w = im.w; h = im.h;
+  if (im.chroma != chroma) { chroma = im.chroma; sh = (chroma == 1 || chroma == 2) ? 1 : 0; sv = chroma == 1 ? 1 : 0; }   /* 4:4:4 detour taken */
   if (bilinear && im.chroma == 1) {          /* only_use_preferred_chroma_algorithm: Op_YCbCr420_bilinear_to_YCbCr444 first, then the generic float op */
     for (int c = 1; c <= 2; c++) { uint16_t* up = (uint16_t*)malloc((size_t)w * h * 2 + 2); co_bilinear_420_to_444(im.p[c], w, h, up); free(im.p[c]); im.p[c] = up; }
     im.chroma = 3; im.cw = w; im.ch = h; chroma = 3; sh = 0; sv = 0;

@@ -29,8 +29,8 @@ def _img(y, cb, cr, a, chroma, bpp, nclx, dev=None):
                          transfer_characteristics=tc, matrix_coefficients=mc, full_range=bool(fr))
 
 
-def _geom(w, h, ops):
-    g = lb.Geometry(w, h)
+def _geom(w, h, ops, chroma=1):
+    g = lb.Geometry(w, h, chroma)
     for o in ops:
         if o[0] == 1:
             g.rotate_ccw(o[1])
@@ -63,9 +63,9 @@ def test_geometry_fused(cuda, ops, fmt, size):
     chroma, bpp, nclx, outc = fmt
     w, h = size
     y, cb, cr, _ = random_ycbcr(1234, w, h, chroma, bpp)
-    # crops with an odd origin on 4:2:0 go through a 4:4:4 detour in the reference: not part of this parity set
+    # (even sizes and crop origins: no 4:4:4 conversion point of the reference in these chains; see test_444_detour)
     want, ow, oh = oracle_postprocess(y, cb, cr, None, chroma, bpp, nclx, ops, outc)
-    got = lb.convert_colorspace(_img(y, cb, cr, None, chroma, bpp, nclx, cuda), outc, _geom(w, h, ops))
+    got = lb.convert_colorspace(_img(y, cb, cr, None, chroma, bpp, nclx, cuda), outc, _geom(w, h, ops, chroma))
     assert np.array_equal(_as_bytes(got), want)
 
 
@@ -120,3 +120,33 @@ def test_bilinear_chroma_upsampling(cuda, case, size):
     want, ow, oh = oracle_postprocess(y, cb, cr, None, chroma, bpp, nclx, [], outc, bilinear=1)
     got = lb.convert_colorspace(_img(y, cb, cr, None, chroma, bpp, nclx, cuda), outc, bilinear=True)
     assert np.array_equal(_as_bytes(got), want)
+
+
+from test_color_oracle import DETOUR  # noqa: E402
+
+
+@pytest.mark.parametrize("case", DETOUR)
+@pytest.mark.parametrize("fmt", [(8, (1, 13, 6, 1), 10, False), (8, (1, 13, 6, 1), 11, True), (10, (9, 16, 9, 1), 14, False)])
+def test_444_detour(cuda, case, fmt):
+    """4:2:0 pictures whose transform chain makes the reference convert to 4:4:4 first (odd crop origin, odd sizes under
+    rotate / mirror): plane-wise pre-pass + bilinear upsampling + the rest of the chain, against the restatement."""
+    w, h, ops = case
+    bpp, nclx, outc, alpha = fmt
+    y, cb, cr, a = random_ycbcr(77, w, h, 1, bpp, alpha=alpha)
+    want, ow, oh = oracle_postprocess(y, cb, cr, a, 1, bpp, nclx, ops, outc)
+    out = lb.convert_colorspace(_img(y, cb, cr, a, 1, bpp, nclx, cuda), outc, _geom(w, h, ops, 1))
+    assert np.array_equal(_as_bytes(out), want)
+
+
+def test_444_detour_limited_range_is_refused(cuda):
+    y, cb, cr, _ = random_ycbcr(5, 34, 18, 1, 8)
+    with pytest.raises(lb.B200Error):
+        lb.convert_colorspace(_img(y, cb, cr, None, 1, 8, (1, 13, 6, 0), cuda), 10, _geom(34, 18, [(3, 3, 30, 1, 16)], 1))
+
+
+@pytest.mark.parametrize("ops", GEOM[:6])
+def test_bilinear_after_geometry(cuda, ops):
+    y, cb, cr, _ = random_ycbcr(99, 32, 24, 1, 8)
+    want, ow, oh = oracle_postprocess(y, cb, cr, None, 1, 8, (1, 13, 6, 0), ops, 10, bilinear=1)
+    out = lb.convert_colorspace(_img(y, cb, cr, None, 1, 8, (1, 13, 6, 0), cuda), 10, _geom(32, 24, ops, 1), bilinear=True)
+    assert np.array_equal(_as_bytes(out), want)

@@ -87,3 +87,40 @@ def test_bilinear_pipeline_matches_reference(case, size):
     got, ow, oh = oracle_postprocess(y, cb, cr, None, chroma, bpp, nclx, [], outc, bilinear=1)
     assert (ow, oh) == (rw, rh)
     assert np.array_equal(ref, got), f"first diff at {np.argwhere(ref != got)[:4].ravel()}"
+
+
+# 4:4:4 conversion point of the reference (pixelimage.cc:1187-1215, 1370-1396, 1458-1481): 4:2:0 pictures with an odd
+# crop origin / odd sizes under rotate or mirror are first converted to 4:4:4 (bilinear), full-range pictures only here.
+DETOUR = [
+    (34, 18, [(3, 3, 30, 1, 16)]),                                # crop with odd left and top
+    (34, 18, [(3, 2, 30, 1, 16)]),                                # odd top only
+    (33, 18, [(1, 90)]), (34, 17, [(1, 270)]), (33, 17, [(1, 180)]),
+    (33, 18, [(2, 1)]), (34, 17, [(2, 0)]),
+    (64, 48, [(3, 2, 61, 2, 45), (3, 1, 50, 0, 40)]),             # even crop, then odd crop of the result
+    (64, 48, [(1, 90), (3, 2, 40, 3, 50), (2, 0), (1, 180)]),     # rotate, odd crop, then more transforms on the 4:4:4 picture
+    (63, 47, [(1, 180), (3, 5, 40, 3, 30)]),
+]
+
+
+@needs_ref
+@pytest.mark.parametrize("case", DETOUR)
+@pytest.mark.parametrize("fmt", [(8, (1, 13, 6, 1), 10, False), (8, (1, 13, 6, 1), 11, True), (10, (9, 16, 9, 1), 14, False), (12, (1, 13, 1, 1), 10, False)])
+def test_444_detour_matches_reference(case, fmt):
+    w, h, ops = case
+    bpp, nclx, outc, alpha = fmt
+    y, cb, cr, a = random_ycbcr(77, w, h, 1, bpp, alpha=alpha)
+    ref, rw, rh, _ = ref_postprocess(y, cb, cr, a, 1, bpp, nclx, ops, outc)
+    got, ow, oh = oracle_postprocess(y, cb, cr, a, 1, bpp, nclx, ops, outc)
+    assert (ow, oh) == (rw, rh)
+    assert np.array_equal(ref, got)
+
+
+@needs_ref
+@pytest.mark.parametrize("ops", GEOM[:6])
+def test_bilinear_after_geometry_matches_reference(ops):
+    """only_use_preferred_chroma_algorithm + bilinear: the upsampling op sees the picture AFTER rotate / mirror / crop."""
+    y, cb, cr, _ = random_ycbcr(99, 32, 24, 1, 8)
+    ref, rw, rh, _ = ref_postprocess(y, cb, cr, None, 1, 8, (1, 13, 6, 0), ops, 10, only_preferred=1, upsampling=2)
+    got, ow, oh = oracle_postprocess(y, cb, cr, None, 1, 8, (1, 13, 6, 0), ops, 10, bilinear=1)
+    assert (ow, oh) == (rw, rh)
+    assert np.array_equal(ref, got)
