@@ -167,7 +167,8 @@ int b200_hevc_encode_intra(const b200_hevc_enc_params* p, const void* y, const v
 void b200_free(void* p);
 
 /* ------------------------------------------------------------------------------------------------
- * HEVC intra decoder: host CABAC front-end + sm_100a reconstruction / deblocking / SAO kernels.
+ * HEVC intra decoder: header parsing on the host; CABAC + slice-data syntax, reconstruction, deblocking and SAO as
+ * sm_100a kernels (CABAC can be moved to host threads with b200_decoder_set_front_end).
  * Replaces: the libde265 calls of libheif/plugins/decoder_libde265.cc -- de265_new_decoder :181,
  *   de265_push_NAL :360, de265_decode :402, de265_get_next_picture :410, de265_get_image_plane :137,
  *   de265_get_image_{colour_primaries,transfer_characteristics,matrix_coefficients,full_range_flag} :428-446,

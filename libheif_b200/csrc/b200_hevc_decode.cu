@@ -1,5 +1,6 @@
-// b200_hevc_decode.cu -- decoder object behind the C ABI: parallel host CABAC front-end, staging into pinned
-// memory, one H2D per array, then the reconstruction / deblocking / SAO kernels for the whole batch of tiles.
+// b200_hevc_decode.cu -- decoder object behind the C ABI: header parsing on host threads (one tile per task), staging
+// into pinned memory, one H2D per array, then the entropy (K0) / reconstruction (K1) / deblocking / SAO kernels for the
+// whole batch of tiles.  With the host front-end the same threads also run the CABAC syntax decoder.
 //
 // Mirrors the call order libheif uses on a decoder plugin instance (new_decoder2 -> push_data2 -> flush_data ->
 // decode_next_image2 -> free_decoder, libheif/codecs/decoder.cc:388-405,441-446,458-460,487-493), but for N

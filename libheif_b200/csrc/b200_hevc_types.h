@@ -1,10 +1,12 @@
-// b200_hevc_types.h -- command stream between the host HEVC front-end (b200_hevc_parse.cc) and the sm_100a
-// reconstruction kernels (b200_hevc_recon.cu, b200_hevc_filters.cu).  Plain PODs, identical on host and device.
+// b200_hevc_types.h -- command stream between the entropy stage (K0 on the GPU, b200_hevc_entropy.cu; or the same
+// syntax decoder on the host, b200_hevc_parse.cc) and the sm_100a reconstruction kernels (b200_hevc_recon.cu,
+// b200_hevc_filters.cu).  Plain PODs, identical on host and device.
 //
-// Division of labour (BASELINE.json north_star): everything that is serial per sub-stream -- NAL / parameter-set /
-// slice-header parsing, CABAC, the coding quadtree syntax, intra-mode (MPM) and QP derivation -- runs on the host;
-// everything per-sample -- scaling, inverse DCT/DST, intra prediction, reconstruction, deblocking, SAO,
-// conformance crop + paste -- runs on the GPU from this stream.
+// Division of labour: NAL / parameter-set / slice-header parsing runs on the host (microseconds per tile); everything
+// that is serial per CABAC sub-stream -- the arithmetic decoder, the coding quadtree syntax, intra-mode (MPM) and QP
+// derivation -- produces this stream (BASELINE.json's north_star put it on the host; the GPU box has 16 usable cores, so
+// it is on the GPU, one warp per sub-stream: SURVEY 8(f) N1); everything per-sample -- scaling, inverse DCT/DST, intra
+// prediction, reconstruction, deblocking, SAO, conformance crop + paste -- consumes it.
 #pragma once
 #include <cstdint>
 

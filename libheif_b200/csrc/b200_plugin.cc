@@ -110,7 +110,7 @@ void release_decoder(b200_decoder* d) { std::lock_guard<std::mutex> l(g_pool_mu)
 
 struct DecInstance { std::vector<uint8_t> data; std::deque<uintptr_t> user; int strict = 0; const b200h_security_limits* limits = nullptr; };
 
-const char* dec_name() { return "b200 HEVC intra decoder (sm_100a CUDA kernels, host CABAC)"; }
+const char* dec_name() { return "b200 HEVC intra decoder (sm_100a CUDA kernels)"; }
 void dec_init() {}
 void dec_deinit() { std::lock_guard<std::mutex> l(g_pool_mu); for (auto& e : g_pool) b200_decoder_destroy(e.dec); g_pool.clear(); }
 int dec_supports(int format) { return format == B200H_COMPRESSION_HEVC ? 200 : 0; }          // libde265 reports 100, ffmpeg 90
