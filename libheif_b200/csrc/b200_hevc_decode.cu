@@ -27,7 +27,6 @@ class Pool {
  public:
   explicit Pool(int n) : stop_(false), gen_(0), next_(0), total_(0), pending_(0) { for (int i = 0; i < n; i++) th_.emplace_back([this] { run(); }); }
   ~Pool() { { std::lock_guard<std::mutex> l(mu_); stop_ = true; } cv_.notify_all(); for (auto& t : th_) t.join(); }
-  int size() const { return (int)th_.size(); }
   void parallel_for(int n, const std::function<void(int)>& fn) {
     if (n <= 0) return;
     if (th_.empty() || n == 1) { for (int i = 0; i < n; i++) fn(i); return; }
