@@ -261,11 +261,13 @@ __device__ __noinline__ void process_tb(WarpMem& m, const int8_t* __restrict__ m
   __syncwarp();
   if (ncoef == 0) return;
   // ---- scaling (8.6.3, flat scaling list m = 16)
+#pragma unroll 1
   for (int i = lane; i < n * n / 2; i += 32) reinterpret_cast<uint32_t*>(m.coef)[i] = 0;
   __syncwarp();
   const int bd_shift = bd + log2n - 5;
   const long long scale = (long long)(c_level_scale[qp % 6] << (qp / 6)) * 16;
   int maxrow = 0, maxcol = 0;
+#pragma unroll 1
   for (int i = lane; i < ncoef; i += 32) {
     const CoefEntry e = ld_coef<LIVE>(&ce[i]);
     const long long t = ((long long)e.level * scale + (1LL << (bd_shift - 1))) >> bd_shift;
@@ -276,6 +278,7 @@ __device__ __noinline__ void process_tb(WarpMem& m, const int8_t* __restrict__ m
   __syncwarp();
   const int bs2 = 20 - bd;
   if (tskip) {                                          // 8.6.4.2, transform_skip_flag: r = d << 7
+#pragma unroll 1
     for (int p = lane; p < n * n; p += 32) {
       const int x = p & (n - 1), y = p >> log2n;
       const int res = (((int)m.coef[p] << 7) + (1 << (bs2 - 1))) >> bs2;
@@ -291,6 +294,7 @@ __device__ __noinline__ void process_tb(WarpMem& m, const int8_t* __restrict__ m
   const int8_t* mrow = dst ? mat + 1024 : mat;
   const int mstride = dst ? 4 : (32 << (5 - log2n));
   // first stage (columns): tmp[x][y] = clip16((sum_k coef[k][x] * M[k][y] + 64) >> 7), only columns that hold coefficients
+#pragma unroll 1
   for (int i = lane; i < n * (maxcol + 1); i += 32) {
     const int y = i & (n - 1), x = i >> log2n;
     int e = 0;
@@ -300,6 +304,7 @@ __device__ __noinline__ void process_tb(WarpMem& m, const int8_t* __restrict__ m
   }
   __syncwarp();
   // second stage (rows) + reconstruction (8.6.6)
+#pragma unroll 1
   for (int p = lane; p < n * n; p += 32) {
     const int x = p & (n - 1), y = p >> log2n;
     int e = 0;
