@@ -17,6 +17,9 @@
 
 namespace b200 {
 
+#ifndef B200_RECON_MIN_BLOCKS
+#define B200_RECON_MIN_BLOCKS 5                // register cap: 65536 / (5 * 128) = 102 -> 96 registers per thread
+#endif
 constexpr int WARPS = 4;                       // warps (= CTB rows in flight) per CTA
 constexpr int MAT_BYTES = 1024 + 16;           // 32x32 DCT matrix + 4x4 DST matrix, shared by the CTA
 
@@ -325,7 +328,7 @@ __device__ __forceinline__ int chroma_qp(int qpy, int off, int bd) {       // 8.
 }
 
 template <bool LIVE>
-__global__ void __launch_bounds__(WARPS * 32, 5) hevc_recon_kernel(const DeviceBatch b) {
+__global__ void __launch_bounds__(WARPS * 32, B200_RECON_MIN_BLOCKS) hevc_recon_kernel(const DeviceBatch b) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   int8_t* mat = reinterpret_cast<int8_t*>(smem_raw);                       // 32x32 DCT matrix, shared by the CTA
   for (int i = threadIdx.x; i < 1024; i += blockDim.x) {
@@ -340,6 +343,15 @@ __global__ void __launch_bounds__(WARPS * 32, 5) hevc_recon_kernel(const DeviceB
   const int lane = threadIdx.x & 31;
   WarpMem m;
   warp_mem_init(m, smem_raw + MAT_BYTES + (threadIdx.x >> 5) * warp_mem_bytes(b.max_log2_ctb), b.max_log2_ctb);
+  // process_tb is out of line and takes the warp's descriptors by reference: they live in SHARED memory (as locals they
+  // would sit in local memory, one 128-byte line of L1 per word and warp; measured: 35 % of all stall cycles were loads
+  // of exactly these fields).  The kernel body keeps its own register copies.
+  __shared__ WarpMem s_wm[WARPS];
+  __shared__ RowCtx s_row[WARPS];
+  WarpMem& wm = s_wm[threadIdx.x >> 5];
+  RowCtx& rs = s_row[threadIdx.x >> 5];
+  if (lane == 0) wm = m;
+  __syncwarp();
 
   for (;;) {
     unsigned t = 0;
@@ -395,6 +407,8 @@ __global__ void __launch_bounds__(WARPS * 32, 5) hevc_recon_kernel(const DeviceB
       r.nb_slice[2] = r.ry > 0 ? (int)ld_cmd<LIVE>(&r.ctus[(r.ry - 1) * r.wctb + r.rx].slice_idx) : -1;
       r.nb_slice[3] = (r.ry > 0 && r.rx + 1 < r.wctb) ? (int)ld_cmd<LIVE>(&r.ctus[(r.ry - 1) * r.wctb + r.rx + 1].slice_idx) : -1;
       TuCmd next_cmd = ci.tu_count ? ld_tu<LIVE>(&tus[ci.tu_start]) : TuCmd{0, 0, 0, 0};
+      if (lane == 0) rs = r;                                 // the shared copy process_tb reads (synchronised by the __syncwarp below / in process_tb)
+      __syncwarp();
       if (r.ry > 0) {
         // fetch the halo row above from HBM/L2
         __syncwarp();
@@ -424,12 +438,12 @@ __global__ void __launch_bounds__(WARPS * 32, 5) hevc_recon_kernel(const DeviceB
         const int nl = cmd.w3 & 0x7ff, ncb = (cmd.w3 >> 11) & 0x3ff, ncr = (cmd.w3 >> 21) & 0x3ff;
         const CoefEntry* ce = coefs + cmd.w2;
         const int bx = (x4 << 2) - r.x0, by = (y4 << 2) - r.y0;
-        process_tb<LIVE>(m, mat, r, 0, bx, by, log2n, lmode, ce, ((cmd.w0 >> 26) & 1) ? nl : 0, qpy + 6 * (r.bd - 8), (cmd.w0 >> 30) & 1, lane);
+        process_tb<LIVE>(wm, mat, rs, 0, bx, by, log2n, lmode, ce, ((cmd.w0 >> 26) & 1) ? nl : 0, qpy + 6 * (r.bd - 8), (cmd.w0 >> 30) & 1, lane);
         if ((cmd.w0 >> 29) & 1) {
           int cbx, cby, clog;
           if (log2n > 2) { cbx = bx >> 1; cby = by >> 1; clog = log2n - 1; } else { cbx = (bx - 4) >> 1; cby = (by - 4) >> 1; clog = 2; }
-          process_tb<LIVE>(m, mat, r, 1, cbx, cby, clog, cmode, ce + nl, ((cmd.w0 >> 27) & 1) ? ncb : 0, chroma_qp(qpy, sl.cb_qp_offset, r.bd), (cmd.w0 >> 31) & 1, lane);
-          process_tb<LIVE>(m, mat, r, 2, cbx, cby, clog, cmode, ce + nl + ncb, ((cmd.w0 >> 28) & 1) ? ncr : 0, chroma_qp(qpy, sl.cr_qp_offset, r.bd), (cmd.w1 >> 20) & 1, lane);
+          process_tb<LIVE>(wm, mat, rs, 1, cbx, cby, clog, cmode, ce + nl, ((cmd.w0 >> 27) & 1) ? ncb : 0, chroma_qp(qpy, sl.cb_qp_offset, r.bd), (cmd.w0 >> 31) & 1, lane);
+          process_tb<LIVE>(wm, mat, rs, 2, cbx, cby, clog, cmode, ce + nl + ncb, ((cmd.w0 >> 28) & 1) ? ncr : 0, chroma_qp(qpy, sl.cr_qp_offset, r.bd), (cmd.w1 >> 20) & 1, lane);
         }
       }
       // write the finished CTB to HBM (coalesced rows), keep its last column as the next CTB's left halo
