@@ -212,7 +212,12 @@ long co_postprocess2(const uint16_t* y, const uint16_t* cb, const uint16_t* cr, 
   /* >8-bit full-range 4:2:0 to an 8-bit interleaved target: the reference planner runs Op_to_sdr_planes on the
      YCbCr planes FIRST and then the integer op (observed with ref_postprocess); every other >8-bit case
      converts in float at full depth and shifts afterwards. */
-  const int pre_shift = (chroma == 1 && bpp > 8 && full_range && interleaved8) ? bpp - 8 : 0;
+  /* matrix_coefficients 0 (GBR), 8 (YCgCo), 16 (YCgCo-Re): special branches of the GENERIC op only (yuv2rgb.cc:225-262).
+     The dedicated 4:2:0 ops have no such branch: 0 and 8 are excluded from them (so the generic op always runs), 16 is
+     not -- there they convert with the default coefficients as if the matrix were unspecified (observed with ref_postprocess). */
+  const int special_matrix = (mc == 0 || mc == 8 || mc == 16) && chroma != 0;
+  const int dedicated_ok = !(mc == 0 || mc == 8);                 /* Op_YCbCr420_to_RGB24/32, Op_YCbCr420_to_RRGGBBaa */
+  const int pre_shift = (chroma == 1 && bpp > 8 && full_range && interleaved8 && dedicated_ok) ? bpp - 8 : 0;
   if (pre_shift) {
     for (int c = 0; c < 4; c++) if (im.p[c]) {
       size_t n = (size_t)((c == 1 || c == 2) ? im.cw * im.ch : im.w * im.h);
@@ -220,7 +225,9 @@ long co_postprocess2(const uint16_t* y, const uint16_t* cb, const uint16_t* cr, 
     }
     bpp = 8;
   }
-  const int int_mode = chroma == 1 && bpp == 8 && full_range && interleaved8;     /* yuv2rgb.cc:300-340 */
+  const int int_mode = chroma == 1 && bpp == 8 && full_range && interleaved8 && dedicated_ok;     /* yuv2rgb.cc:300-340 */
+  const int rrggbb_direct = chroma == 1 && bpp > 8 && (out_chroma >= 12 && out_chroma <= 15) && dedicated_ok;   /* Op_YCbCr420_to_RRGGBBaa */
+  const int special = special_matrix && !int_mode && !rrggbb_direct;
   const int ci[4] = {(int)lroundf(256 * cf[0]), (int)lroundf(256 * cf[1]), (int)lroundf(256 * cf[2]), (int)lroundf(256 * cf[3])};
   const int half = 1 << (bpp - 1), maxv = (1 << bpp) - 1;
   const float lro = (float)(16 << (bpp - 8));
@@ -235,7 +242,21 @@ long co_postprocess2(const uint16_t* y, const uint16_t* cb, const uint16_t* cr, 
     if (!chroma) r = g = b = Y;
     else {
       int Cb = im.p[1][(yy >> sv) * im.cw + (xx >> sh)], Cr = im.p[2][(yy >> sv) * im.cw + (xx >> sh)];
-      if (int_mode) {
+      if (special) {
+        if (mc == 0) {
+          if (full_range) { r = Cr; g = Y; b = Cb; }
+          else { r = clip_f_u16(((float)Cr - lro) * 1.1429f, maxv); g = clip_f_u16(((float)Y - lro) * 1.1689f, maxv); b = clip_f_u16(((float)Cb - lro) * 1.1429f, maxv); }
+        } else if (mc == 8) {                     /* clip_int_u8 also for > 8 bit: reference quirk (yuv2rgb.cc:240-242) */
+          int cbv = Cb - half, crv = Cr - half;
+          r = clip_int_u8(Y - cbv + crv); g = clip_int_u8(Y + cbv); b = clip_int_u8(Y - cbv - crv);
+        } else {                                  /* 16: YCgCo-Re, int16 arithmetic, x4 */
+          int16_t yy = (int16_t)Y, cbv = (int16_t)((int16_t)Cb - (int16_t)half), crv = (int16_t)((int16_t)Cr - (int16_t)half);
+          int16_t t = (int16_t)(yy - (cbv >> 1)), gg = (int16_t)(t + cbv), bb = (int16_t)(t - (crv >> 1)), rr = (int16_t)(bb + crv);
+          int rv = rr * 4, gv = gg * 4, bv = bb * 4;
+          r = rv < 0 ? 0 : (rv > maxv ? maxv : rv); g = gv < 0 ? 0 : (gv > maxv ? maxv : gv); b = bv < 0 ? 0 : (bv > maxv ? maxv : bv);
+        }
+        r >>= sdr_shift; g >>= sdr_shift; b >>= sdr_shift;
+      } else if (int_mode) {
         int cbv = Cb - 128, crv = Cr - 128;
         r = clip_int_u8(Y + ((ci[0] * crv + 128) >> 8));
         g = clip_int_u8(Y + ((ci[1] * cbv + ci[2] * crv + 128) >> 8));

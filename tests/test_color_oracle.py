@@ -124,3 +124,18 @@ def test_bilinear_after_geometry_matches_reference(ops):
     got, ow, oh = oracle_postprocess(y, cb, cr, None, 1, 8, (1, 13, 6, 0), ops, 10, bilinear=1)
     assert (ow, oh) == (rw, rh)
     assert np.array_equal(ref, got)
+
+
+# matrix_coefficients 0 (GBR), 8 (YCgCo), 16 (YCgCo-Re): special branches of the generic op; the dedicated 4:2:0 ops ignore
+# them (16) or are not selected (0, 8).  Restated in the oracle for round 2; the CUDA path still refuses these matrices.
+@needs_ref
+@pytest.mark.parametrize("mc", [0, 8, 16])
+@pytest.mark.parametrize("chroma", [1, 2, 3])
+@pytest.mark.parametrize("bpp,outc", [(8, 10), (8, 11), (8, 3), (10, 10), (10, 14), (10, 3), (12, 15)])
+@pytest.mark.parametrize("full", [0, 1])
+def test_special_matrices_match_reference(mc, chroma, bpp, outc, full):
+    y, cb, cr, a = random_ycbcr(4242 + mc, 34, 18, chroma, bpp, alpha=outc in (11, 15))
+    ref, rw, rh, _ = ref_postprocess(y, cb, cr, a, chroma, bpp, (1, 13, mc, full), [], outc)
+    got, ow, oh = oracle_postprocess(y, cb, cr, a, chroma, bpp, (1, 13, mc, full), [], outc)
+    assert (ow, oh) == (rw, rh)
+    assert np.array_equal(ref, got)
