@@ -67,14 +67,46 @@ static int co_detour_needed(const co_image* im, const int* o) {
   return 0;
 }
 
-static int co_geometry(co_image* im, const int* ops, int nops, int full_range) {
+static int clip_f_u16(float fx, int maxi);
+static void co_kr_kb(int matrix, int primaries, float* pKr, float* pKb);
+void co_coefficients(int matrix, int primaries, float out[4]);
+static int co_geometry(co_image* im, const int* ops, int nops, int* full_range, int bpp, int cp, int mc) {
   for (int i = 0; i < nops; i++) {
     const int* o = ops + 5 * i;
     int np = im->chroma ? 3 : 1;
     if (co_detour_needed(im, o)) {
-      if (im->chroma != 1 || !full_range) return -1;
+      if (im->chroma != 1) return -1;
       for (int c = 1; c <= 2; c++) { uint16_t* up = (uint16_t*)malloc((size_t)im->w * im->h * 2 + 2); co_bilinear_420_to_444(im->p[c], im->w, im->h, up); free(im->p[c]); im->p[c] = up; }
       im->chroma = 3; im->cw = im->w; im->ch = im->h;
+      if (!*full_range) {
+        /* The target profile of the detour is nclx_profile() with full_range_flag = true, so a limited-range picture is
+           also range-converted; the path the planner finds goes through RGB after the upsampling: Op_YCbCr_to_RGB<T>
+           (generic float op on the 4:4:4 picture, yuv2rgb.cc:263-279) then Op_RGB_to_YCbCr<T> to full-range 4:4:4 with
+           the same matrix (rgb2yuv.cc:226-300, coefficients nclx.cc:177-200). */
+        if (mc == 0 || mc == 8 || mc == 11 || mc == 14 || mc == 16) return -1;
+        const int half = 1 << (bpp - 1), maxv = (1 << bpp) - 1; const float lro = (float)(16 << (bpp - 8));
+        float cf[4]; co_coefficients(mc, cp, cf);
+        float Kr, Kb; co_kr_kb(mc, cp, &Kr, &Kb);
+        float c[3][3];
+        if (Kb != 0 || Kr != 0) {
+          c[0][0] = Kr; c[0][1] = 1 - Kr - Kb; c[0][2] = Kb;
+          c[1][0] = -Kr / (1 - Kb) / 2; c[1][1] = -(1 - Kr - Kb) / (1 - Kb) / 2; c[1][2] = 0.5f;
+          c[2][0] = 0.5f; c[2][1] = -(1 - Kr - Kb) / (1 - Kr) / 2; c[2][2] = -Kb / (1 - Kr) / 2;
+        } else {
+          c[0][0] = 0.299f; c[0][1] = 0.587f; c[0][2] = 0.114f; c[1][0] = -0.168735f; c[1][1] = -0.331264f; c[1][2] = 0.5f;
+          c[2][0] = 0.5f; c[2][1] = -0.418688f; c[2][2] = -0.081312f;
+        }
+        for (size_t i = 0; i < (size_t)im->w * im->h; i++) {
+          float yv = (float)im->p[0][i], cbv = (float)(im->p[1][i] - half), crv = (float)(im->p[2][i] - half);
+          yv = (yv - lro) * 1.1689f; cbv = cbv * 1.1429f; crv = crv * 1.1429f;
+          const float r = (float)clip_f_u16(yv + cf[0] * crv, maxv), g = (float)clip_f_u16(yv + cf[1] * cbv + cf[2] * crv, maxv), b = (float)clip_f_u16(yv + cf[3] * cbv, maxv);
+          im->p[0][i] = (uint16_t)clip_f_u16(r * c[0][0] + g * c[0][1] + b * c[0][2], maxv);
+          im->p[1][i] = (uint16_t)clip_f_u16((r * c[1][0] + g * c[1][1] + b * c[1][2]) + half, maxv);
+          im->p[2][i] = (uint16_t)clip_f_u16((r * c[2][0] + g * c[2][1] + b * c[2][2]) + half, maxv);
+        }
+        *full_range = 1;
+      }
+
     }
     if (o[0] == 1 && o[1] != 0) {
       for (int c = 0; c < 4; c++) {
@@ -105,8 +137,8 @@ static int co_geometry(co_image* im, const int* ops, int nops, int full_range) {
   return 0;
 }
 
-/* nclx.cc:84-173 */
-void co_coefficients(int matrix, int primaries, float out[4]) {
+/* nclx.cc:84-140 (get_Kr_Kb) */
+static void co_kr_kb(int matrix, int primaries, float* pKr, float* pKb) {
   float Kr = 0.0f, Kb = 0.0f;
   if (matrix == 12 || matrix == 13) {
     float gx, gy, bx, by, rx, ry, wx, wy; int ok = 1;
@@ -138,6 +170,12 @@ void co_coefficients(int matrix, int primaries, float out[4]) {
     case 9: case 10: Kr = 0.2627f; Kb = 0.0593f; break;
     default: break;
   }
+  *pKr = Kr; *pKb = Kb;
+}
+
+/* nclx.cc:143-173 */
+void co_coefficients(int matrix, int primaries, float out[4]) {
+  float Kr, Kb; co_kr_kb(matrix, primaries, &Kr, &Kb);
   if (Kb != 0 || Kr != 0) {
     out[0] = 2 * (-Kr + 1); out[1] = 2 * Kb * (-Kb + 1) / (Kb + Kr - 1);
     out[2] = 2 * Kr * (-Kr + 1) / (Kb + Kr - 1); out[3] = 2 * (-Kb + 1);
@@ -199,7 +237,7 @@ long co_postprocess2(const uint16_t* y, const uint16_t* cb, const uint16_t* cr, 
     size_t n = (size_t)((c == 1 || c == 2) ? im.cw * im.ch : w * h);
     im.p[c] = (uint16_t*)malloc(n * 2 + 2); memcpy(im.p[c], src[c], n * 2);
   }
-  if (co_geometry(&im, ops, nops, full_range)) { co_free(&im); return -2; }
+  if (co_geometry(&im, ops, nops, &full_range, bpp, cp, mc)) { co_free(&im); return -2; }
   w = im.w; h = im.h;
   if (im.chroma != chroma) { chroma = im.chroma; sh = (chroma == 1 || chroma == 2) ? 1 : 0; sv = chroma == 1 ? 1 : 0; }   /* 4:4:4 detour taken */
   if (bilinear && im.chroma == 1) {          /* only_use_preferred_chroma_algorithm: Op_YCbCr420_bilinear_to_YCbCr444 first, then the generic float op */

@@ -90,7 +90,8 @@ def test_bilinear_pipeline_matches_reference(case, size):
 
 
 # 4:4:4 conversion point of the reference (pixelimage.cc:1187-1215, 1370-1396, 1458-1481): 4:2:0 pictures with an odd
-# crop origin / odd sizes under rotate or mirror are first converted to 4:4:4 (bilinear), full-range pictures only here.
+# crop origin / odd sizes under rotate or mirror are first converted to 4:4:4 (bilinear; limited-range pictures are also
+# range-converted through RGB because the conversion's target profile is full range).
 DETOUR = [
     (34, 18, [(3, 3, 30, 1, 16)]),                                # crop with odd left and top
     (34, 18, [(3, 2, 30, 1, 16)]),                                # odd top only
@@ -104,7 +105,9 @@ DETOUR = [
 
 @needs_ref
 @pytest.mark.parametrize("case", DETOUR)
-@pytest.mark.parametrize("fmt", [(8, (1, 13, 6, 1), 10, False), (8, (1, 13, 6, 1), 11, True), (10, (9, 16, 9, 1), 14, False), (12, (1, 13, 1, 1), 10, False)])
+@pytest.mark.parametrize("fmt", [(8, (1, 13, 6, 1), 10, False), (8, (1, 13, 6, 1), 11, True), (10, (9, 16, 9, 1), 14, False), (12, (1, 13, 1, 1), 10, False),
+                                 # limited range: the conversion point also range-converts, through RGB (restated in the oracle; the CUDA path refuses these)
+                                 (8, (1, 13, 6, 0), 10, False), (8, (2, 2, 2, 0), 11, True), (10, (9, 16, 9, 0), 14, False), (12, (1, 13, 1, 0), 3, False)])
 def test_444_detour_matches_reference(case, fmt):
     w, h, ops = case
     bpp, nclx, outc, alpha = fmt
