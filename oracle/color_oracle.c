@@ -48,11 +48,24 @@ static void plane_mirror(uint16_t* d, int w, int h, int direction) {           /
 
 void co_bilinear_420_to_444(const uint16_t* in, int w, int h, uint16_t* out);
 
+/* Op_YCbCr422_bilinear_to_YCbCr444<T> (chroma_sampling.cc:784-905) for one chroma plane: in (w+1)/2 x h, out w x h. */
+void co_bilinear_422_to_444(const uint16_t* in, int w, int h, uint16_t* out) {
+  const int cw = (w + 1) / 2;
+  for (int y = 0; y < h; y++) out[(size_t)y * w] = in[(size_t)y * cw];                                   /* left border */
+  if (w % 2 == 0) for (int y = 0; y < h; y++) out[(size_t)y * w + w - 1] = in[(size_t)y * cw + w / 2 - 1];  /* right border */
+  for (int y = 0; y < h; y++) for (int x = 1; x < w - 1; x += 2) {
+    const int cx = x / 2;
+    const unsigned c00 = in[(size_t)y * cw + cx], c01 = in[(size_t)y * cw + cx + 1];
+    out[(size_t)y * w + x] = (uint16_t)((c00 * 3 + c01 + 2) / 4);
+    out[(size_t)y * w + x + 1] = (uint16_t)((c00 + c01 * 3 + 2) / 4);
+  }
+}
+
 /* rotate_ccw / mirror_inplace / crop on subsampled images the plane-wise code cannot handle first convert to 4:4:4
  * (pixelimage.cc:1187-1215, 1370-1396, 1458-1481): convert_colorspace(YCbCr, 4:4:4, nclx_profile() /+ undefined, but
  * full_range_flag = true +/, bpp, default options) = Op_YCbCr420_bilinear_to_YCbCr444 for a full-range 4:2:0 image.  A
- * limited-range image would additionally be range-converted through RGB (the default target profile is full range) and a
- * 4:2:2 one needs Op_YCbCr422_bilinear_to_YCbCr444: neither is restated -> -1. */
+ * limited-range image is additionally range-converted through RGB (the default target profile is full range); a 4:2:2
+ * image takes Op_YCbCr422_bilinear_to_YCbCr444. */
 static int co_detour_needed(const co_image* im, const int* o) {
   const int ow = im->w & 1, oh = im->h & 1;
   if (im->chroma == 2) {
@@ -75,8 +88,11 @@ static int co_geometry(co_image* im, const int* ops, int nops, int* full_range, 
     const int* o = ops + 5 * i;
     int np = im->chroma ? 3 : 1;
     if (co_detour_needed(im, o)) {
-      if (im->chroma != 1) return -1;
-      for (int c = 1; c <= 2; c++) { uint16_t* up = (uint16_t*)malloc((size_t)im->w * im->h * 2 + 2); co_bilinear_420_to_444(im->p[c], im->w, im->h, up); free(im->p[c]); im->p[c] = up; }
+      for (int c = 1; c <= 2; c++) {
+        uint16_t* up = (uint16_t*)malloc((size_t)im->w * im->h * 2 + 2);
+        if (im->chroma == 1) co_bilinear_420_to_444(im->p[c], im->w, im->h, up); else co_bilinear_422_to_444(im->p[c], im->w, im->h, up);
+        free(im->p[c]); im->p[c] = up;
+      }
       im->chroma = 3; im->cw = im->w; im->ch = im->h;
       if (!*full_range) {
         /* The target profile of the detour is nclx_profile() with full_range_flag = true, so a limited-range picture is

@@ -142,3 +142,24 @@ def test_special_matrices_match_reference(mc, chroma, bpp, outc, full):
     got, ow, oh = oracle_postprocess(y, cb, cr, a, chroma, bpp, (1, 13, mc, full), [], outc)
     assert (ow, oh) == (rw, rh)
     assert np.array_equal(ref, got)
+
+
+# 4:2:2 pictures: rotate 90 / 270 always, 180 with odd height, horizontal mirror with odd width and crop with odd left
+# convert to 4:4:4 first (Op_YCbCr422_bilinear_to_YCbCr444).  Restated for round 2; the CUDA path refuses these chains.
+DETOUR_422 = [
+    (34, 18, [(1, 90)]), (33, 18, [(1, 270)]), (34, 17, [(1, 180)]), (34, 18, [(1, 180)]),
+    (33, 17, [(2, 1)]), (34, 17, [(2, 0)]), (64, 48, [(3, 3, 61, 1, 45), (1, 90)]), (64, 48, [(3, 2, 61, 1, 45)]),
+]
+
+
+@needs_ref
+@pytest.mark.parametrize("case", DETOUR_422)
+@pytest.mark.parametrize("fmt", [(8, (1, 13, 6, 1), 10, False), (8, (1, 13, 6, 0), 11, True), (10, (9, 16, 9, 0), 14, False), (12, (1, 13, 1, 1), 3, False)])
+def test_444_detour_422_matches_reference(case, fmt):
+    w, h, ops = case
+    bpp, nclx, outc, alpha = fmt
+    y, cb, cr, a = random_ycbcr(78, w, h, 2, bpp, alpha=alpha)
+    ref, rw, rh, _ = ref_postprocess(y, cb, cr, a, 2, bpp, nclx, ops, outc)
+    got, ow, oh = oracle_postprocess(y, cb, cr, a, 2, bpp, nclx, ops, outc)
+    assert (ow, oh) == (rw, rh)
+    assert np.array_equal(ref, got)
