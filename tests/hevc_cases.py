@@ -47,12 +47,25 @@ SYNTH = [
     ("tile_1024_like", 512, 512, 8, True, dict(log2_ctb_size=5, qp=27, wpp=1)),
 ]
 
+# More feature combinations, used by the CPU tests only (FFmpeg pin of the restatement, host front-end vs restatement):
+# they widen the pin of the oracle and of the syntax decoder the GPU kernel shares with the host front-end.
+SYNTH_CPU_EXTRA = [
+    ("x_main10_slices_wpp_tskip", 264, 136, 10, True, dict(log2_ctb_size=5, slice_ctb_rows=2, wpp=1, transform_skip=1, mode_decision=0)),
+    ("x_ctb64_dependent_wpp", 320, 256, 8, True, dict(log2_ctb_size=6, slice_ctb_rows=2, dependent_slice_segments=1, wpp=1)),
+    ("x_mono12_ctb64", 200, 136, 12, False, dict(log2_ctb_size=6, qp=20, dqp_range=8)),
+    ("x_ctb16_deep_qp14", 136, 72, 8, True, dict(log2_ctb_size=4, qp=14, max_transform_hierarchy_depth_intra=2, dqp_range=5, diff_cu_qp_delta_depth=1, sao=0)),
+    ("x_main12_highqp_nolf", 160, 96, 12, True, dict(log2_ctb_size=5, qp=45, deblocking_disabled=1, sign_data_hiding=0)),
+    ("x_odd_8bit_wpp_random", 74, 58, 8, True, dict(log2_ctb_size=5, wpp=1, mode_decision=0, max_transform_hierarchy_depth_intra=3, cb_qp_offset=-5, cr_qp_offset=7)),
+    ("x_main10_ctb64_qg8", 256, 128, 10, True, dict(log2_ctb_size=6, diff_cu_qp_delta_depth=3, dqp_range=12, qp=30)),
+    ("x_slices_every_row_nolf_across", 192, 160, 8, True, dict(log2_ctb_size=5, slice_ctb_rows=1, loop_filter_across_slices=0, slice_loop_filter_across_slices=0)),
+]
+
 _cache = {}
 
 
 def synth_stream(name):
     if name not in _cache:
-        for (nm, w, h, bd, chroma, opts) in SYNTH:
+        for (nm, w, h, bd, chroma, opts) in SYNTH + SYNTH_CPU_EXTRA:
             if nm == name:
                 y, cb, cr = hevc_enc.synthetic_image(0xB200 + w + h, w, h, bd, chroma)
                 _cache[name] = hevc_enc.encode_intra(y, cb, cr, bit_depth=bd, **opts)
@@ -61,3 +74,7 @@ def synth_stream(name):
 
 def all_streams():
     return fixture_streams() + [(s[0], synth_stream(s[0])) for s in SYNTH]
+
+
+def cpu_extra_streams():
+    return [(s[0], synth_stream(s[0])) for s in SYNTH_CPU_EXTRA]

@@ -6,7 +6,7 @@ import hashlib
 import numpy as np
 import pytest
 
-from hevc_cases import all_streams
+from hevc_cases import all_streams, cpu_extra_streams
 from oracle import bindings as ob
 
 have_ffmpeg = ob.avcodec_dir() is not None
@@ -19,7 +19,7 @@ FFMPEG_CTB16_CHROMA_SAO = {"ctb16_basic"}
 
 
 @pytest.mark.skipif(not have_ffmpeg, reason="FFmpeg (cv2 wheel) not present")
-@pytest.mark.parametrize("name,au", all_streams(), ids=[s[0] for s in all_streams()])
+@pytest.mark.parametrize("name,au", all_streams() + cpu_extra_streams(), ids=[s[0] for s in all_streams() + cpu_extra_streams()])
 def test_restatement_matches_ffmpeg(name, au):
     ff, bd, ch = ob.ffmpeg_decode(au)
     rs, info = ob.restatement_decode(au)

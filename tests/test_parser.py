@@ -7,7 +7,7 @@ import ctypes as C
 import numpy as np
 import pytest
 
-from hevc_cases import all_streams
+from hevc_cases import all_streams, cpu_extra_streams
 from libheif_b200 import _lib
 from oracle import bindings as ob
 
@@ -37,7 +37,7 @@ def oracle_digest(au):
                 lm=lm[:w * h // 16].copy(), cm=cm[:w * h // 16].copy())
 
 
-@pytest.mark.parametrize("name,au", all_streams(), ids=[s[0] for s in all_streams()])
+@pytest.mark.parametrize("name,au", all_streams() + cpu_extra_streams(), ids=[s[0] for s in all_streams() + cpu_extra_streams()])
 def test_front_end_matches_restatement(name, au):
     p, o = product_digest(au), oracle_digest(au)
     assert (p["w"], p["h"]) == (o["w"], o["h"])
