@@ -19,7 +19,8 @@ struct BitRd {
   const uint8_t* d; size_t n; size_t pos;
   unsigned bit() { unsigned v = (pos >> 3) < n ? (d[pos >> 3] >> (7 - (pos & 7))) & 1 : 0; pos++; return v; }
   unsigned bits(int k) { unsigned v = 0; while (k-- > 0) v = (v << 1) | bit(); return v; }
-  unsigned ue() { int z = 0; while (bit() == 0 && z < 32) z++; return z ? ((1u << z) - 1 + bits(z)) : 0; }
+  // ue(v), 9.2: more than 31 leading zero bits cannot be a valid code; saturate (callers range-check the value)
+  unsigned ue() { int z = 0; while (bit() == 0 && z < 32) z++; if (z >= 32) return 0xffffffffu; return z ? ((1u << z) - 1 + bits(z)) : 0; }
   int se() { unsigned k = ue(); return (k & 1) ? (int)((k + 1) >> 1) : -(int)(k >> 1); }
 };
 
@@ -191,7 +192,9 @@ class HeaderParser {
         if (p.transform_skip && b.ue() != 0) return set_error(B200_E_UNSUPPORTED, "transform skip larger than 4x4");
         if (b.bit()) return set_error(B200_E_UNSUPPORTED, "cross-component prediction");
         if (b.bit()) return set_error(B200_E_UNSUPPORTED, "chroma QP offset lists");
-        p.log2_sao_scale_luma = b.ue(); p.log2_sao_scale_chroma = b.ue();
+        const unsigned sl = b.ue(), sc = b.ue();               // log2_sao_offset_scale_*: 0 .. max(0, BitDepth - 10) (7.4.3.3.2)
+        if (sl > 6 || sc > 6) return set_error(B200_E_BITSTREAM, "log2_sao_offset_scale out of range");
+        p.log2_sao_scale_luma = (int)sl; p.log2_sao_scale_chroma = (int)sc;
       }
     }
     p.valid = true; pps_tab[id] = p;
@@ -243,6 +246,8 @@ class HeaderParser {
       S = s; PP = p; int rc = start_picture(); if (rc) return rc;
       fill_seq_params();
       if (P.sp.qg_log2 < 3) return set_error(B200_E_BITSTREAM, "diff_cu_qp_delta_depth");
+      { const int mx = P.sp.bd > 10 ? P.sp.bd - 10 : 0;
+        if (P.sp.sao_scale_luma > mx || P.sp.sao_scale_chroma > mx) return set_error(B200_E_BITSTREAM, "log2_sao_offset_scale exceeds BitDepth - 10"); }
     } else if (!started) return set_error(B200_E_BITSTREAM, "slice segment before the first one of the picture");
     else if (p != PP) return set_error(B200_E_UNSUPPORTED, "slice segments of one picture use different PPS");
     P.desc.pps_cb_qp_offset = p->cb_qp_offset; P.desc.pps_cr_qp_offset = p->cr_qp_offset;
