@@ -2,6 +2,7 @@
 (FFmpeg libavcodec, oracle/ffhevc.c) for the reference's fixtures and for every synthetic stream; plus the golden md5s
 of SURVEY.md Appendix C for the reference fixtures (planes of examples/example.heic)."""
 import hashlib
+import os
 
 import numpy as np
 import pytest
@@ -35,3 +36,15 @@ def test_example_heic_golden_md5():
     rs, _ = ob.restatement_decode(au)
     md5 = [hashlib.md5(p.astype(np.uint8).tobytes()).hexdigest() for p in rs]
     assert md5 == ["5a0423057f3fede64a297243982465c7", "8a2344a26a2347f045842be7f731085c", "29ad6bcbe5dd90a536d0abe36777a1b5"]
+
+
+@pytest.mark.skipif(not (os.path.exists("/root/reference/examples/example.heic") and ob.ref_plugin() is not None and have_ffmpeg),
+                    reason="reference tree / oracle/_ref not present")
+def test_golden_streams_are_what_the_reference_pushes_into_a_decoder_plugin():
+    """tests/golden/streams/*.au regenerate byte-for-byte from the reference's fixture files through the unmodified
+    reference libheif (tests/golden/make_streams.py --check)."""
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "tests", "golden", "make_streams.py"), "--check"], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:]
