@@ -17,6 +17,9 @@ namespace {
 
 struct BitRd {
   const uint8_t* d; size_t n; size_t pos;
+  // reads past the end return zeros; overrun() reports them, and every bitstream-controlled loop below is bounded by
+  // the specification's range for its count, so a short NAL can neither hang nor over-read
+  bool overrun() const { return pos > 8 * n; }
   unsigned bit() { unsigned v = (pos >> 3) < n ? (d[pos >> 3] >> (7 - (pos & 7))) & 1 : 0; pos++; return v; }
   unsigned bits(int k) { unsigned v = 0; while (k-- > 0) v = (v << 1) | bit(); return v; }
   // ue(v), 9.2: more than 31 leading zero bits cannot be a valid code; saturate (callers range-check the value)
@@ -100,50 +103,77 @@ class HeaderParser {
     if (msl > 0) for (int i = msl; i < 8; i++) b.bits(2);
     for (int i = 0; i < msl; i++) { if (pp[i]) { b.bits(32); b.bits(32); b.bits(24); } if (lp[i]) b.bits(8); }
   }
-  static void st_rps(BitRd& b, Sps& s, int idx, int num) {
+  // 7.3.7 st_ref_pic_set; false = malformed (delta_idx_minus1 > idx - 1, or more than 16 pictures: sps_max_dec_pic_buffering <= 16)
+  static bool st_rps(BitRd& b, Sps& s, int idx, int num) {
     int inter = idx ? b.bit() : 0;
     if (inter) {
-      int di = 1; if (idx == num) di = b.ue() + 1;
+      unsigned di = 1; if (idx == num) { const unsigned v = b.ue(); if (v >= (unsigned)idx) return false; di = v + 1; }
       b.bit(); b.ue();
-      int ref = std::max(0, idx - di), cnt = 0;
+      const int ref = idx - (int)di;                   // 0 <= ref < idx <= 64
+      int cnt = 0;
       for (int j = 0; j <= s.st_num_delta[ref]; j++) { int used = b.bit(), ud = 1; if (!used) ud = b.bit(); if (used || ud) cnt++; }
+      if (cnt > 16) return false;
       s.st_num_delta[idx] = cnt;
-    } else { int nn = b.ue(), np = b.ue(); for (int i = 0; i < nn + np; i++) { b.ue(); b.bit(); } s.st_num_delta[idx] = nn + np; }
+    } else {
+      const unsigned nn = b.ue(), np = b.ue();
+      if (nn > 16 || np > 16 || nn + np > 16) return false;
+      for (unsigned i = 0; i < nn + np; i++) { b.ue(); b.bit(); }
+      s.st_num_delta[idx] = (int)(nn + np);
+    }
+    return !b.overrun();
   }
-  static void skip_hrd(BitRd& b, int msl) {
+  static bool skip_hrd(BitRd& b, int msl) {
     int nal = b.bit(), vcl = b.bit(), sub = 0;
     if (nal || vcl) { sub = b.bit(); if (sub) { b.bits(8); b.bits(5); b.bit(); b.bits(5); } b.bits(4); b.bits(4); if (sub) b.bits(4); b.bits(5); b.bits(5); b.bits(5); }
     for (int i = 0; i <= msl; i++) {
       int gen = b.bit(), within = 1, low = 0, cnt = 0;
       if (!gen) within = b.bit();
       if (within) b.ue(); else low = b.bit();
-      if (!low) cnt = b.ue();
+      if (!low) { const unsigned v = b.ue(); if (v > 31) return false; cnt = (int)v; }          // cpb_cnt_minus1: 0..31 (E.3.2)
       for (int k = 0; k < nal + vcl; k++) for (int c = 0; c <= cnt; c++) { b.ue(); b.ue(); if (sub) { b.ue(); b.ue(); } b.bit(); }
+      if (b.overrun()) return false;
     }
+    return true;
   }
   int parse_sps(const uint8_t* r, size_t n) {                                  // 7.3.2.2
     BitRd b{r, n, 16}; Sps s;
     b.bits(4); int msl = b.bits(3); b.bit();
     skip_ptl(b, msl);
     unsigned id = b.ue(); if (id > 15) return set_error(B200_E_BITSTREAM, "sps id");
-    s.chroma_format_idc = b.ue();
+    // every ue(v) is range-checked BEFORE it is used in arithmetic (a saturated code is 0xffffffff): 7.4.3.2.1 ranges
+    { const unsigned v = b.ue(); if (v > 3) return set_error(B200_E_BITSTREAM, "chroma_format_idc"); s.chroma_format_idc = (int)v; }
     if (s.chroma_format_idc == 3) b.bit();
-    s.width = b.ue(); s.height = b.ue();
-    if (b.bit()) { s.conf_l = b.ue(); s.conf_r = b.ue(); s.conf_t = b.ue(); s.conf_b = b.ue(); }
-    s.bit_depth = 8 + b.ue(); int bdc = 8 + b.ue();
-    s.log2_max_poc_lsb = 4 + b.ue();
+    { const unsigned w = b.ue(), h = b.ue(); if (w == 0 || h == 0 || w > 16384 || h > 16384) return set_error(B200_E_BITSTREAM, "picture size %ux%u", w, h); s.width = (int)w; s.height = (int)h; }
+    if (b.bit()) {
+      const unsigned cl = b.ue(), cr = b.ue(), ct = b.ue(), cbm = b.ue();
+      const uint64_t sub = s.chroma_format_idc == 1 || s.chroma_format_idc == 2 ? 2 : 1, subh = s.chroma_format_idc == 1 ? 2 : 1;
+      if (sub * ((uint64_t)cl + cr) >= (uint64_t)s.width || subh * ((uint64_t)ct + cbm) >= (uint64_t)s.height) return set_error(B200_E_BITSTREAM, "conformance window larger than the picture");
+      s.conf_l = (int)cl; s.conf_r = (int)cr; s.conf_t = (int)ct; s.conf_b = (int)cbm;
+    }
+    int bdc;
+    { const unsigned bl = b.ue(), bc = b.ue(); if (bl > 8 || bc > 8) return set_error(B200_E_BITSTREAM, "bit depth"); s.bit_depth = 8 + (int)bl; bdc = 8 + (int)bc; }
+    { const unsigned v = b.ue(); if (v > 12) return set_error(B200_E_BITSTREAM, "log2_max_pic_order_cnt_lsb"); s.log2_max_poc_lsb = 4 + (int)v; }
     int sub = b.bit();
     for (int i = sub ? 0 : msl; i <= msl; i++) { b.ue(); b.ue(); b.ue(); }
-    s.log2_min_cb = 3 + b.ue(); s.log2_ctb = s.log2_min_cb + b.ue();
-    s.log2_min_tb = 2 + b.ue(); s.log2_max_tb = s.log2_min_tb + b.ue();
-    b.ue(); s.max_th_depth_intra = b.ue();
+    {
+      const unsigned a = b.ue(), d1 = b.ue(), t = b.ue(), d2 = b.ue();
+      if (a > 3 || d1 > 3 || a + d1 > 3 || 3 + a + d1 < 4) return set_error(B200_E_BITSTREAM, "coding block size configuration");       // MinCb 8..64, CTB 16..64
+      s.log2_min_cb = 3 + (int)a; s.log2_ctb = s.log2_min_cb + (int)d1;
+      if (t > 3 || 2 + (int)t >= s.log2_min_cb) return set_error(B200_E_BITSTREAM, "log2_min_luma_transform_block_size");                 // MinTb < MinCb
+      s.log2_min_tb = 2 + (int)t;
+      if (d2 > 3 || s.log2_min_tb + (int)d2 > std::min(5, s.log2_ctb)) return set_error(B200_E_BITSTREAM, "log2_diff_max_min_luma_transform_block_size");
+      s.log2_max_tb = s.log2_min_tb + (int)d2;
+    }
+    { const unsigned inter = b.ue(), intra = b.ue(); const unsigned mx = (unsigned)(s.log2_ctb - s.log2_min_tb);
+      if (inter > mx || intra > mx) return set_error(B200_E_BITSTREAM, "max_transform_hierarchy_depth");
+      s.max_th_depth_intra = (int)intra; }
     if (b.bit()) return set_error(B200_E_UNSUPPORTED, "scaling lists are not supported");
     b.bit(); s.sao = b.bit();
     if (b.bit()) return set_error(B200_E_UNSUPPORTED, "PCM is not supported");
-    s.num_st_rps = b.ue(); if (s.num_st_rps > 64) return set_error(B200_E_BITSTREAM, "num_short_term_ref_pic_sets");
-    for (int i = 0; i < s.num_st_rps; i++) st_rps(b, s, i, s.num_st_rps);
+    { const unsigned v = b.ue(); if (v > 64) return set_error(B200_E_BITSTREAM, "num_short_term_ref_pic_sets"); s.num_st_rps = (int)v; }
+    for (int i = 0; i < s.num_st_rps; i++) if (!st_rps(b, s, i, s.num_st_rps)) return set_error(B200_E_BITSTREAM, "short-term reference picture set %d", i);
     s.long_term = b.bit();
-    if (s.long_term) { s.num_lt_sps = b.ue(); for (int i = 0; i < s.num_lt_sps; i++) { b.bits(s.log2_max_poc_lsb); b.bit(); } }
+    if (s.long_term) { const unsigned v = b.ue(); if (v > 32) return set_error(B200_E_BITSTREAM, "num_long_term_ref_pics_sps"); s.num_lt_sps = (int)v; for (int i = 0; i < s.num_lt_sps; i++) { b.bits(s.log2_max_poc_lsb); b.bit(); } }
     s.temporal_mvp = b.bit(); s.strong_intra = b.bit();
     if (b.bit()) {   // VUI (E.2.1)
       if (b.bit()) { if (b.bits(8) == 255) { b.bits(16); b.bits(16); } }
@@ -153,7 +183,7 @@ class HeaderParser {
       if (b.bit()) { b.ue(); b.ue(); }
       b.bit(); b.bit(); b.bit();
       if (b.bit()) { b.ue(); b.ue(); b.ue(); b.ue(); }
-      if (b.bit()) { b.bits(32); b.bits(32); if (b.bit()) b.ue(); if (b.bit()) skip_hrd(b, msl); }
+      if (b.bit()) { b.bits(32); b.bits(32); if (b.bit()) b.ue(); if (b.bit() && !skip_hrd(b, msl)) return set_error(B200_E_BITSTREAM, "hrd_parameters"); }
       if (b.bit()) { b.bits(3); b.ue(); b.ue(); b.ue(); b.ue(); b.ue(); }
     }
     if (b.bit()) {   // sps_extension
@@ -162,6 +192,7 @@ class HeaderParser {
     }
     if (s.chroma_format_idc > 1) return set_error(B200_E_UNSUPPORTED, "chroma_format_idc %d (only 4:2:0 and 4:0:0)", s.chroma_format_idc);
     if (s.bit_depth != bdc || s.bit_depth > 12) return set_error(B200_E_UNSUPPORTED, "bit depth luma %d chroma %d", s.bit_depth, bdc);
+    if (b.overrun()) return set_error(B200_E_BITSTREAM, "sequence parameter set is truncated");
     if (s.log2_ctb > 6 || s.log2_ctb < 4 || s.log2_max_tb > 5 || s.log2_min_cb > s.log2_ctb || s.log2_max_tb > s.log2_ctb) return set_error(B200_E_BITSTREAM, "block size configuration");
     if (s.width <= 0 || s.height <= 0 || s.width > 16384 || s.height > 16384 || (s.width & ((1 << s.log2_min_cb) - 1)) || (s.height & ((1 << s.log2_min_cb) - 1)))
       return set_error(B200_E_BITSTREAM, "picture size %dx%d", s.width, s.height);
@@ -171,19 +202,21 @@ class HeaderParser {
   int parse_pps(const uint8_t* r, size_t n) {                                  // 7.3.2.3
     BitRd b{r, n, 16}; Pps p;
     unsigned id = b.ue(); if (id > 63) return set_error(B200_E_BITSTREAM, "pps id");
-    p.sps_id = b.ue(); if (p.sps_id > 15) return set_error(B200_E_BITSTREAM, "pps sps id");
+    { const unsigned v = b.ue(); if (v > 15) return set_error(B200_E_BITSTREAM, "pps sps id"); p.sps_id = (int)v; }
     p.dependent_slices = b.bit(); p.output_flag_present = b.bit(); p.num_extra_bits = b.bits(3);
     p.sign_hiding = b.bit(); b.bit(); b.ue(); b.ue();
-    p.init_qp = 26 + b.se(); b.bit();
+    { const int v = b.se(); if (v < -26 - 24 || v > 25) return set_error(B200_E_BITSTREAM, "init_qp_minus26"); p.init_qp = 26 + v; }      // -(26 + QpBdOffset) .. 25; re-checked against the SPS bit depth per slice
+    b.bit();
     p.transform_skip = b.bit(); p.cu_qp_delta = b.bit();
-    if (p.cu_qp_delta) p.diff_cu_qp_delta_depth = b.ue();
+    if (p.cu_qp_delta) { const unsigned v = b.ue(); if (v > 3) return set_error(B200_E_BITSTREAM, "diff_cu_qp_delta_depth"); p.diff_cu_qp_delta_depth = (int)v; }
     p.cb_qp_offset = b.se(); p.cr_qp_offset = b.se(); p.slice_chroma_qp_offsets = b.bit();
+    if (p.cb_qp_offset < -12 || p.cb_qp_offset > 12 || p.cr_qp_offset < -12 || p.cr_qp_offset > 12) return set_error(B200_E_BITSTREAM, "pps chroma qp offset");
     b.bit(); b.bit();
     if (b.bit()) return set_error(B200_E_UNSUPPORTED, "transquant bypass is not supported");
     if (b.bit()) return set_error(B200_E_UNSUPPORTED, "HEVC tiles are not supported");
     p.wpp = b.bit();
     p.lf_across_slices = b.bit();
-    if (b.bit()) { p.deblock_override_enabled = b.bit(); p.deblock_disabled = b.bit(); if (!p.deblock_disabled) { p.beta_offset = 2 * b.se(); p.tc_offset = 2 * b.se(); } }
+    if (b.bit()) { p.deblock_override_enabled = b.bit(); p.deblock_disabled = b.bit(); if (!p.deblock_disabled) { const int be = b.se(), tc = b.se(); if (be < -6 || be > 6 || tc < -6 || tc > 6) return set_error(B200_E_BITSTREAM, "pps deblocking offsets"); p.beta_offset = 2 * be; p.tc_offset = 2 * tc; } }
     if (b.bit()) return set_error(B200_E_UNSUPPORTED, "scaling lists are not supported");
     b.bit(); b.ue(); p.slice_ext_present = b.bit();
     if (b.bit()) {
@@ -197,6 +230,7 @@ class HeaderParser {
         p.log2_sao_scale_luma = (int)sl; p.log2_sao_scale_chroma = (int)sc;
       }
     }
+    if (b.overrun()) return set_error(B200_E_BITSTREAM, "picture parameter set is truncated");
     p.valid = true; pps_tab[id] = p;
     return B200_OK;
   }
@@ -262,12 +296,13 @@ class HeaderParser {
       if (p->output_flag_present) b.bit();
       if (nal_type != 19 && nal_type != 20) {
         b.bits(S->log2_max_poc_lsb);
-        if (!b.bit()) { Sps tmp = *S; st_rps(b, tmp, S->num_st_rps, S->num_st_rps); }
+        if (!b.bit()) { Sps tmp = *S; if (!st_rps(b, tmp, S->num_st_rps, S->num_st_rps)) return set_error(B200_E_BITSTREAM, "slice short-term reference picture set"); }
         else if (S->num_st_rps > 1) b.bits(ceil_log2((unsigned)S->num_st_rps));
         if (S->long_term) {
-          int nsps = 0; if (S->num_lt_sps > 0) nsps = b.ue();
-          int npics = b.ue();
-          for (int i = 0; i < nsps + npics; i++) {
+          unsigned nsps = 0; if (S->num_lt_sps > 0) nsps = b.ue();
+          const unsigned npics = b.ue();
+          if (nsps > 32 || npics > 32) return set_error(B200_E_BITSTREAM, "long-term reference picture count");
+          for (unsigned i = 0; i < nsps + npics; i++) {
             if (i < nsps) { if (S->num_lt_sps > 1) b.bits(ceil_log2((unsigned)S->num_lt_sps)); } else { b.bits(S->log2_max_poc_lsb); b.bit(); }
             if (b.bit()) b.ue();
           }
@@ -276,12 +311,14 @@ class HeaderParser {
       }
       sao_luma = sao_chroma = 0;
       if (S->sao) { sao_luma = b.bit(); if (P.desc.chroma) sao_chroma = b.bit(); }
-      slice_qp = p->init_qp + b.se();
+      { const int dq = b.se(), qbd = 6 * (S->bit_depth - 8);
+        if (dq < -128 || dq > 128 || p->init_qp + dq < -qbd || p->init_qp + dq > 51) return set_error(B200_E_BITSTREAM, "SliceQpY %d outside [%d, 51]", p->init_qp + dq, -qbd);   // 7.4.7.1
+        slice_qp = p->init_qp + dq; }
       int cb_off = 0, cr_off = 0;
-      if (p->slice_chroma_qp_offsets) { cb_off = b.se(); cr_off = b.se(); }
+      if (p->slice_chroma_qp_offsets) { cb_off = b.se(); cr_off = b.se(); if (cb_off < -12 || cb_off > 12 || cr_off < -12 || cr_off > 12) return set_error(B200_E_BITSTREAM, "slice chroma qp offset"); }
       int dis = p->deblock_disabled, beta = p->beta_offset, tc = p->tc_offset, ovr = 0;
       if (p->deblock_override_enabled) ovr = b.bit();
-      if (ovr) { dis = b.bit(); if (!dis) { beta = 2 * b.se(); tc = 2 * b.se(); } }
+      if (ovr) { dis = b.bit(); if (!dis) { const int be = b.se(), t2 = b.se(); if (be < -6 || be > 6 || t2 < -6 || t2 > 6) return set_error(B200_E_BITSTREAM, "slice deblocking offsets"); beta = 2 * be; tc = 2 * t2; } }
       int across = p->lf_across_slices;
       if (p->lf_across_slices && (sao_luma || sao_chroma || !dis)) across = b.bit();
       if (P.slices.size() >= 65000) return set_error(B200_E_UNSUPPORTED, "too many slices");
@@ -292,9 +329,10 @@ class HeaderParser {
       slice_idx = (int)P.slices.size() - 1; slice_addr_rs = seg_addr;
     } else if (slice_idx < 0) return set_error(B200_E_BITSTREAM, "dependent slice segment without a slice");
     std::vector<uint32_t> entry;
-    if (p->wpp) { int ne = b.ue(); if (ne > total) return set_error(B200_E_BITSTREAM, "num_entry_point_offsets"); if (ne > 0) { int len = b.ue() + 1; if (len > 32) return set_error(B200_E_BITSTREAM, "offset_len_minus1"); for (int i = 0; i < ne; i++) entry.push_back(b.bits(len) + 1); } }
-    if (p->slice_ext_present) { int len = b.ue(); for (int i = 0; i < len; i++) b.bits(8); }
+    if (p->wpp) { const unsigned ne = b.ue(); if (ne > (unsigned)total) return set_error(B200_E_BITSTREAM, "num_entry_point_offsets"); if (ne > 0) { const unsigned lm1 = b.ue(); if (lm1 > 31) return set_error(B200_E_BITSTREAM, "offset_len_minus1"); const int len = (int)lm1 + 1; for (unsigned i = 0; i < ne; i++) { const uint64_t v = (uint64_t)b.bits(len) + 1; if (v > n) return set_error(B200_E_BITSTREAM, "entry point offset beyond the NAL"); entry.push_back((uint32_t)v); } } }
+    if (p->slice_ext_present) { const unsigned len = b.ue(); if (len > 256) return set_error(B200_E_BITSTREAM, "slice_segment_header_extension_length"); for (unsigned i = 0; i < len; i++) b.bits(8); }
     b.bit(); b.pos = (b.pos + 7) & ~(size_t)7;
+    if (b.overrun()) return set_error(B200_E_BITSTREAM, "slice segment header is truncated");
     const size_t hdr_rbsp = b.pos >> 3;
     if (hdr_rbsp > n) return set_error(B200_E_BITSTREAM, "slice header runs past the NAL");
     // ---- append the segment's data to the picture's RBSP buffer (4-byte aligned start)

@@ -458,6 +458,7 @@ struct Decoder {
       B200_NOUNROLL while (v < 5 && dbin(CTX_QP_DELTA + (v ? 1 : 0))) v++;
       if (v == 5) { int k = 0; B200_NOUNROLL while (k < 16 && dbypass()) { v += 1 << k; k++; } v += (int)dbits(k); }
       if (v && dbypass()) v = -v;
+      { const int half = 3 * (sp->bd - 8); if (v < -(26 + half) || v > 25 + half) { err = SYN_E_BITSTREAM; return; } }   // CuQpDeltaVal range (7.4.9.10)
       is_dqp_coded = 1; dqp_val = v;
       derive_qpy(cu.x0, cu.y0);
     }
