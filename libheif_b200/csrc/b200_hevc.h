@@ -41,13 +41,14 @@ struct DeviceBatch {
   const PicDesc* pics; int npics;
   const CtuInfo* ctus; const TuCmd* tus; const CoefEntry* coefs; const SliceInfo* slices;
   const int8_t* qp8; const uint8_t* edge8;
-  unsigned int* progress;        // one counter per CTB row of every picture, zeroed before launch
+  unsigned int* progress;        // two counters (luma, chroma) per CTB row of every picture, zeroed before launch
   const unsigned int* entropy_progress;   // K0's counters of the same rows when K0 runs CONCURRENTLY (nullptr: command stream complete)
   int blocks_per_sm;             // > 0: cap of resident CTAs per SM (co-residency with K0)
   unsigned int* ticket;          // work-distribution counter, zeroed before launch
   unsigned int* error_flag;      // set by a kernel that gave up waiting (zeroed before launch)
-  const uint2* row_list;         // (picture, ctb row) in launch order
-  int nrows;
+  const uint2* row_list;         // (picture, ctb row | component group << 31) in launch order
+  int nrows;                     // work items: CTB rows x component groups (luma; Cb + Cr)
+  int wide_samples;              // 1: planes hold uint16 samples (bit depth > 8)
   int max_log2_ctb;              // largest CTB size of the batch (sizes the per-warp shared memory)
 };
 // Device front-end (b200_hevc_entropy.cu)

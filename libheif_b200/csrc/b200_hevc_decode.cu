@@ -96,7 +96,7 @@ struct b200_decoder {
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   bool have_result = false;
   int debug_stage = 0;
-  size_t n_rows = 0, cbytes = 0; bool canvas_fully_covered = true; int max_log2_ctb = 6;
+  size_t n_rows = 0, n_items = 0, cbytes = 0; bool canvas_fully_covered = true; int max_log2_ctb = 6, info_bps = 1;
   ~b200_decoder() {
     delete pool;
     pics.release(); ctus.release(); tus.release(); coefs.release(); slices.release(); qp8.release(); edge8.release(); rows.release();
@@ -163,7 +163,7 @@ static int run_device_pipeline(b200_decoder* d, int n, cudaStream_t s, int* laun
   cudaEventRecord(d->ev[1], s);
   DeviceBatch b{};
   b.pics = d->pics.d; b.npics = n; b.ctus = d->ctus.d; b.tus = d->tus.d; b.coefs = d->coefs.d; b.slices = d->slices.d;
-  b.qp8 = d->qp8.d; b.edge8 = d->edge8.d; b.ticket = d->sync.d; b.error_flag = d->sync.d + 1; b.progress = d->sync.d + 2; b.row_list = d->rows.d; b.nrows = (int)d->n_rows; b.max_log2_ctb = d->max_log2_ctb;
+  b.qp8 = d->qp8.d; b.edge8 = d->edge8.d; b.ticket = d->sync.d; b.error_flag = d->sync.d + 1; b.progress = d->sync.d + 2; b.row_list = d->rows.d; b.nrows = (int)d->n_items; b.max_log2_ctb = d->max_log2_ctb; b.wide_samples = d->info_bps == 2;
   if (devfe) {
     EntropyBatch e{};
     e.pics = d->epics.d; e.npics = d->npics; e.subs = d->subs.d; e.order = d->sub_order.d; e.nsubs = (int)d->n_subs;
@@ -277,8 +277,8 @@ int b200_decoder_decode_grid(b200_decoder* d, int cols, int rows, const uint8_t*
   if (n_tu > 0xffffffffull) return set_error(B200_E_UNSUPPORTED, "batch too large");
   int rc;
   if ((rc = d->pics.reserve((size_t)n)) || (rc = d->ctus.reserve(n_ctu, !devfe)) || (rc = d->tus.reserve(n_tu, !devfe)) || (rc = d->coefs.reserve(n_coef + 1, !devfe)) ||
-      (rc = d->slices.reserve(n_slice)) || (rc = d->qp8.reserve(n_map, !devfe)) || (rc = d->edge8.reserve(n_map, !devfe)) || (rc = d->rows.reserve(n_rows)) ||
-      (rc = d->sync.reserve(n_rows + 2, false)) || (rc = d->rec.reserve(rec_bytes, false)))
+      (rc = d->slices.reserve(n_slice)) || (rc = d->qp8.reserve(n_map, !devfe)) || (rc = d->edge8.reserve(n_map, !devfe)) || (rc = d->rows.reserve(2 * n_rows)) ||
+      (rc = d->sync.reserve(2 * n_rows + 2, false)) || (rc = d->rec.reserve(rec_bytes, false)))
     return rc;
   if (devfe && ((rc = d->rbsp.reserve(n_rbsp + 16)) || (rc = d->subs.reserve(n_subs)) || (rc = d->sub_order.reserve(n_subs)) || (rc = d->ctu_slice.reserve(n_ctu)) ||
                 (rc = d->epics.reserve((size_t)n)) || (rc = d->ipm4.reserve(n_map4, false)) || (rc = d->cd8.reserve(n_map, false)) ||
@@ -314,7 +314,11 @@ int b200_decoder_decode_grid(b200_decoder* d, int cols, int rows, const uint8_t*
   // wavefront instead of idling behind one tile's 2-CTB stagger.
   { size_t row_cursor = 0; int max_h = 0; d->max_log2_ctb = 4;
     for (int i = 0; i < n; i++) { max_h = std::max(max_h, d->parsed[(size_t)i].desc.hctb); d->max_log2_ctb = std::max(d->max_log2_ctb, d->parsed[(size_t)i].desc.log2_ctb); }
-    for (int r = 0; r < max_h; r++) for (int i = 0; i < n; i++) if (r < d->parsed[(size_t)i].desc.hctb) d->rows.h[row_cursor++] = make_uint2((unsigned)i, (unsigned)r); }
+    for (int r = 0; r < max_h; r++) for (int i = 0; i < n; i++) if (r < d->parsed[(size_t)i].desc.hctb) {
+      d->rows.h[row_cursor++] = make_uint2((unsigned)i, (unsigned)r);                                        // luma
+      if (chroma) d->rows.h[row_cursor++] = make_uint2((unsigned)i, (unsigned)r | 0x80000000u);              // Cb + Cr
+    }
+    d->n_items = row_cursor; d->info_bps = bps; }
   if (devfe) {
     // sub-stream ticket order: k-th sub-stream of every picture, k = 0, 1, ... (same argument as for the rows)
     size_t cur = 0, maxs = 0;
@@ -352,8 +356,8 @@ int b200_decoder_decode_grid(b200_decoder* d, int cols, int rows, const uint8_t*
   cudaEventRecord(d->ev[0], s);
   B200_CUDA_CHECK(cudaMemcpyAsync(d->pics.d, d->pics.h, (size_t)n * sizeof(PicDesc), cudaMemcpyHostToDevice, s));
   B200_CUDA_CHECK(cudaMemcpyAsync(d->slices.d, d->slices.h, n_slice * sizeof(SliceInfo), cudaMemcpyHostToDevice, s));
-  B200_CUDA_CHECK(cudaMemcpyAsync(d->rows.d, d->rows.h, n_rows * sizeof(uint2), cudaMemcpyHostToDevice, s));
-  size_t h2d = (size_t)n * sizeof(PicDesc) + n_slice * sizeof(SliceInfo) + n_rows * sizeof(uint2);
+  B200_CUDA_CHECK(cudaMemcpyAsync(d->rows.d, d->rows.h, d->n_items * sizeof(uint2), cudaMemcpyHostToDevice, s));
+  size_t h2d = (size_t)n * sizeof(PicDesc) + n_slice * sizeof(SliceInfo) + d->n_items * sizeof(uint2);
   if (!devfe) {
     B200_CUDA_CHECK(cudaMemcpyAsync(d->ctus.d, d->ctus.h, n_ctu * sizeof(CtuInfo), cudaMemcpyHostToDevice, s));
     B200_CUDA_CHECK(cudaMemcpyAsync(d->tus.d, d->tus.h, n_tu * sizeof(TuCmd), cudaMemcpyHostToDevice, s));
@@ -371,7 +375,7 @@ int b200_decoder_decode_grid(b200_decoder* d, int cols, int rows, const uint8_t*
     B200_CUDA_CHECK(cudaMemsetAsync(d->ecount.d, 0, 2 * sizeof(unsigned long long), s));
     h2d += n_rbsp + n_subs * (sizeof(syn::Substream) + sizeof(uint2)) + n_ctu * sizeof(uint16_t) + (size_t)n * sizeof(EntropyPic);
   }
-  B200_CUDA_CHECK(cudaMemsetAsync(d->sync.d, 0, (n_rows + 2) * sizeof(unsigned), s));
+  B200_CUDA_CHECK(cudaMemsetAsync(d->sync.d, 0, (2 * n_rows + 2) * sizeof(unsigned), s));
   if (!canvas_fully_covered) B200_CUDA_CHECK(cudaMemsetAsync(d->canvas.d, 0, cbytes, s));     // uncovered canvas stays zero (calloc in the reference)
   d->n_rows = n_rows; d->cbytes = cbytes; d->canvas_fully_covered = canvas_fully_covered; d->npics = n; d->n_subs = n_subs; d->used_device_front_end = devfe;
   int launches = 0;
@@ -399,7 +403,7 @@ int b200_decoder_decode_grid(b200_decoder* d, int cols, int rows, const uint8_t*
 int b200_decoder_rerun_device(b200_decoder* d, void* stream_) {
   if (!d || !d->have_result) return set_error(B200_E_INVALID, "no decode result");
   cudaStream_t s = (cudaStream_t)stream_;
-  B200_CUDA_CHECK(cudaMemsetAsync(d->sync.d, 0, (d->n_rows + 2) * sizeof(unsigned), s));
+  B200_CUDA_CHECK(cudaMemsetAsync(d->sync.d, 0, (2 * d->n_rows + 2) * sizeof(unsigned), s));
   if (d->used_device_front_end) {
     B200_CUDA_CHECK(cudaMemsetAsync(d->esync.d, 0, (1 + d->n_rows + d->n_subs) * sizeof(unsigned), s));
     B200_CUDA_CHECK(cudaMemsetAsync(d->ecount.d, 0, 2 * sizeof(unsigned long long), s));

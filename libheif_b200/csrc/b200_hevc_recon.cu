@@ -3,67 +3,53 @@
 // Does the per-sample half of what libde265 does inside de265_decode() (reached from
 // libheif/plugins/decoder_libde265.cc:386-457): H.265 8.6.2-8.6.4 (scaling, transforms), 8.4.4.2 (intra sample
 // prediction incl. reference substitution and smoothing), 8.6.6 (reconstruction), driven by the command stream
-// of the host front-end (b200_hevc_types.h).
+// of the entropy stage (b200_hevc_types.h).
 //
-// Mapping: ONE WARP OWNS ONE CTB ROW of one picture and walks its CTBs left to right (the only order the
-// left-neighbour dependency allows); rows of a picture advance as a wavefront with a lag of two CTBs
-// (above-right dependency), published through a per-row progress counter (release/acquire in global memory).
-// Pictures of a batch (grid tiles) are independent, so a batch exposes (#pictures x CTB rows) warps of work; a
-// global ticket hands rows out in picture-major order, which makes the spin-wait deadlock-free without requiring
-// co-residency.  The CTB being reconstructed lives in shared memory together with its halo (row above incl.
-// above-right, column to the left), all neighbour reads of the intra predictor hit shared memory; the finished
-// CTB is written to HBM once, coalesced.  Integer work: no tensor cores.
+// Work item = (picture, CTB row, component group): luma, or the Cb + Cr pair.  Chroma prediction never reads luma, so the
+// two groups are independent wavefronts; Cb and Cr share position, size, mode and availability, so one warp does both at
+// once on its two half-warps.  ONE WARP walks the CTBs of its row left to right; rows advance as a wavefront with a lag
+// of two CTBs (above-right dependency) through per-(row, group) progress counters.  A global ticket hands items out in
+// "row k of every picture" order, so a dependency always holds a smaller ticket (no co-residency requirement).
+//
+// Per CTB the warp works in two phases:
+//   A. residual phase, lane-parallel over the CTB's transform units (no dependency between them): every lane decodes
+//      one TuCmd, derives the neighbour availability of its block (6.4.1, z-scan order) into a packed descriptor, and
+//      -- 4x4 blocks being 80 % of all blocks of a typical intra picture -- dequantises and inverse-transforms its own
+//      4x4 block entirely in registers (32 blocks per pass).  Larger blocks (8..32) are done by the whole warp, one at a
+//      time, with zero-row/column skipping.  Residuals land in shared memory, block-contiguous in z-order.
+//   B. prediction phase, block after block (the intra dependency chain): one gather of the 4n+1 neighbours with the
+//      substitution process (8.4.4.2.2) folded into the index computation, optional smoothing, prediction, residual
+//      add, store into the CTB tile in shared memory.  ~100 warp instructions per block instead of ~900.
+// The finished CTB leaves shared memory with one cp.async.bulk (TMA) row copy per lane; the halo (row above incl.
+// above-right, column to the left) is kept in shared memory next to the tile.  Integer work: no tensor cores.
 #include "b200_hevc.h"
 
 namespace b200 {
 
 #ifndef B200_RECON_MIN_BLOCKS
-#define B200_RECON_MIN_BLOCKS 5                // register cap: 65536 / (5 * 128) = 102 -> 96 registers per thread
+#define B200_RECON_MIN_BLOCKS 5
 #endif
-constexpr int WARPS = 4;                       // warps (= CTB rows in flight) per CTA
-constexpr int MAT_BYTES = 1024 + 16;           // 32x32 DCT matrix + 4x4 DST matrix, shared by the CTA
+constexpr int WARPS = 4;                       // warps (= work items in flight) per CTA
+constexpr int PAD = 16;                        // samples left of the tile / halo row: column PAD - 1 is the left halo
+constexpr int MAT_BYTES = 1024 + 32;           // 32x32 DCT matrix (+ padding), shared by the CTA
+constexpr int REF_STRIDE = 136;                // int16 entries per neighbour array (4 * 32 + 1 rounded up)
 
-// Per-warp shared-memory working set; sized at launch from the largest CTB of the batch so that small CTBs buy
-// occupancy (CTB 64: 17.7 KB per warp, CTB 32: 7.6 KB, CTB 16: 2.5 KB).
-struct WarpMem {
-  uint16_t* tile_y; uint16_t* tile_c[2];       // current CTB, stride ts / tsc
-  int16_t* coef;                               // scaled coefficients [k][x]
-  int16_t* tmp;                                // first-stage output, transposed: [x][y]
-  uint16_t* top_y; uint16_t* left_y;           // halo: top_y[0] = above-left corner, top_y[1 + x], x < 2 * ctb
-  uint16_t* top_c[2]; uint16_t* left_c[2];
-  int16_t* ref_r; int16_t* ref_a; int16_t* ref_b;   // neighbour array (index 0 = bottom of left column): available samples only / substituted / filtered
-  unsigned* avm;                               // availability bit mask of the neighbour array, 32 entries per word
-  int ts, tsc;
-};
-__host__ __device__ inline size_t warp_mem_bytes(int log2ctb) {
+struct WarpLayout { int tile, top, res, tmp, desc, total; };     // byte offsets inside the warp's shared-memory slice
+__host__ __device__ inline WarpLayout warp_layout(int log2ctb, int bps) {
   const int ctb = 1 << log2ctb, tb = ctb < 32 ? ctb : 32;
-  size_t n = (size_t)ctb * ctb + 2 * (size_t)(ctb / 2) * (ctb / 2)      // tiles
-           + 2 * (size_t)tb * tb                                         // coef + tmp
-           + (1 + 2 * ctb + 3) + ctb + 2 * (1 + ctb + 3) + 2 * (ctb / 2) // halos
-           + 3 * 136 + 16;                                               // ref_r, ref_a, ref_b, avm
-  return (n * 2 + 15) & ~(size_t)15;
-}
-__device__ inline void warp_mem_init(WarpMem& m, unsigned char* base, int log2ctb) {
-  const int ctb = 1 << log2ctb, tb = ctb < 32 ? ctb : 32, cc = ctb / 2;
-  uint16_t* p = reinterpret_cast<uint16_t*>(base);
-  m.ts = ctb; m.tsc = cc;
-  m.tile_y = p; p += ctb * ctb;
-  m.tile_c[0] = p; p += cc * cc; m.tile_c[1] = p; p += cc * cc;
-  m.coef = reinterpret_cast<int16_t*>(p); p += tb * tb;
-  m.tmp = reinterpret_cast<int16_t*>(p); p += tb * tb;
-  m.top_y = p; p += 1 + 2 * ctb + 3;
-  m.left_y = p; p += ctb;
-  m.top_c[0] = p; p += 1 + ctb + 3; m.top_c[1] = p; p += 1 + ctb + 3;
-  m.left_c[0] = p; p += cc; m.left_c[1] = p; p += cc;
-  m.ref_r = reinterpret_cast<int16_t*>(p); p += 136;
-  m.ref_a = reinterpret_cast<int16_t*>(p); p += 136;
-  m.ref_b = reinterpret_cast<int16_t*>(p); p += 136;
-  m.avm = reinterpret_cast<unsigned*>(p);
+  WarpLayout L; int o = 0;
+  L.tile = o; o += ctb * (ctb + PAD) * bps;                      // luma tile; the Cb + Cr tiles of a chroma item fit inside
+  L.top = o; o += (2 * PAD + 2 * ctb + 32) * bps;                // halo row(s)
+  o = (o + 15) & ~15;
+  L.res = o; o += ctb * ctb * 2;                                 // residuals, int16, z-order block-contiguous
+  L.tmp = o; o += (tb * tb * 2 > 1024 ? tb * tb * 2 : 1024);     // first-stage output / 4x4 scratch / neighbour arrays
+  L.desc = o; o += (ctb / 4) * (ctb / 4) * 8;                    // one descriptor per transform block of the CTB
+  L.total = (o + 15) & ~15;
+  return L;
 }
 
 __constant__ int8_t c_dct[32] = {64, 90, 90, 90, 89, 88, 87, 85, 83, 82, 80, 78, 75, 73, 70, 67,
                                  64, 61, 57, 54, 50, 46, 43, 38, 36, 31, 25, 22, 18, 13, 9, 4};
-__constant__ int8_t c_dst[16] = {29, 55, 74, 84, 74, 74, 0, -74, 84, -29, -74, 55, 55, -84, 74, -29};
 __constant__ int8_t c_angle[35] = {0, 0, 32, 26, 21, 17, 13, 9, 5, 2, 0, -2, -5, -9, -13, -17, -21, -26, -32,
                                    -26, -21, -17, -13, -9, -5, -2, 0, 2, 5, 9, 13, 17, 21, 26, 32};
 __constant__ int16_t c_inv_angle[35] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, -4096, -1638, -910, -630, -482, -390, -315, -256,
@@ -83,34 +69,12 @@ __device__ __forceinline__ unsigned ld_acquire(const unsigned* p) {
 __device__ __forceinline__ void st_release(unsigned* p, unsigned v) {
   asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
-
-struct RowCtx {             // warp-uniform state of the CTB row being decoded
-  const PicDesc* pic; const CtuInfo* ctus; const SliceInfo* slices;
-  int W, H, log2ctb, ctb, wctb, bd, chroma, strong;
-  int rx, ry, x0, y0;       // current CTB
-  int cur_slice;
-  int nb_slice[4];          // slice of the left, above-left, above, above-right CTB (-1: outside / not decoded)
-};
-
-// Availability of the luma location (xn, yn) for a block whose first luma sample is (xc, yc) -- H.265 6.4.1 restated
-// for the wavefront schedule: previous CTB rows up to the above-right CTB and the left CTB are complete.
-__device__ __forceinline__ bool available(const RowCtx& r, int xn, int yn, int xc, int yc) {
-  if (xn < 0 || yn < 0 || xn >= r.W || yn >= r.H) return false;
-  const int ncx = xn >> r.log2ctb, ncy = yn >> r.log2ctb;
-  if (ncy > r.ry) return false;
-  if (ncy == r.ry) {
-    if (ncx > r.rx) return false;
-    if (ncx == r.rx) {
-      const unsigned m = r.ctb - 1;
-      return morton4((xn & m) >> 2, (yn & m) >> 2) < morton4((xc & m) >> 2, (yc & m) >> 2);
-    }
-  }
-  // neighbouring CTB: only left, above-left, above and above-right can be referenced (extent <= 2 * nTbS <= CTB size)
-  const int k = ncy == r.ry ? 0 : 1 + (ncx - r.rx + 1);
-  return r.nb_slice[k] == r.cur_slice;
+// TMA (bulk asynchronous copy) of one finished tile row: shared -> global.  Source and destination 16-byte aligned, size a
+// multiple of 16.
+__device__ __forceinline__ void bulk_store(void* g, const void* s, unsigned bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(g), "r"((unsigned)__cvta_generic_to_shared(s)), "r"(bytes) : "memory");
 }
 
-// sample of component c at tile-relative position (tx, ty); tx in [-1, 2*ctb), ty in [-1, ctb)
 // Command-stream reads.  LIVE = K0 is running concurrently: a neighbouring, not yet written entry may share a cache
 // line with one read earlier and L1 is not coherent, so everything goes to L2 (ld.global.cg).  Otherwise the command
 // stream is complete and plain loads let consecutive entries hit the L1 line the first one brought in.
@@ -124,119 +88,232 @@ template <bool LIVE> __device__ __forceinline__ CtuInfo ld_ctu(const CtuInfo* p)
   return c;
 }
 
-__device__ __forceinline__ int tile_sample(const WarpMem& m, int c, int tx, int ty) {
-  if (c == 0) { if (ty < 0) return m.top_y[tx + 1]; if (tx < 0) return m.left_y[ty]; return m.tile_y[ty * m.ts + tx]; }
-  if (ty < 0) return m.top_c[c - 1][tx + 1];
-  if (tx < 0) return m.left_c[c - 1][ty];
-  return m.tile_c[c - 1][ty * m.tsc + tx];
+__device__ __forceinline__ int chroma_qp(int qpy, int off, int bd) {       // 8.6.1, ChromaArrayType == 1
+  const int qbd = 6 * (bd - 8);
+  const int qpi = clip3i(-qbd, 57, qpy + off);
+  const int qpc = qpi < 30 ? qpi : (qpi >= 43 ? qpi - 6 : c_qpc[qpi - 30]);
+  return qpc + qbd;
 }
 
-// One transform block: 8.4.4.2 prediction into the tile, then (if coded) 8.6.3 scaling + 8.6.4 inverse transform
-// + 8.6.6 reconstruction.  (bx, by): position inside the tile in samples of component c.
-template <bool LIVE>
-__device__ __noinline__ void process_tb(WarpMem& m, const int8_t* __restrict__ mat, const RowCtx& r, int c, int bx, int by, int log2n, int mode,
-                           const CoefEntry* __restrict__ ce, int ncoef, int qp, int tskip, int lane) {
-  const int n = 1 << log2n, sh = c ? 1 : 0, bd = r.bd;
-  const int cx0 = c ? r.x0 >> 1 : r.x0, cy0 = c ? r.y0 >> 1 : r.y0;      // tile origin in component samples
-  const int xl = (cx0 + bx) << sh, yl = (cy0 + by) << sh;                 // luma location of the block
-  // ---- neighbour array with availability, then substitution (8.4.4.2.2)
-  // The left / below-left / corner / above / above-right neighbour regions each lie inside ONE aligned block of the
-  // current block's size, so z-scan availability (6.4.1) is decided per region (5 tests per block, done by lanes 0..4)
-  // and per sample only the picture bounds remain.
-  unsigned regions;
-  {
-    const int nl = n << sh;
-    bool f = false;
-    if (lane < 5) {
-      const int xn = lane == 4 ? xl + nl : (lane == 3 ? xl : xl - 1);
-      const int yn = lane == 0 ? yl : (lane == 1 ? yl + nl : yl - 1);      // 0: left, 1: below-left, 2: corner, 3: above, 4: above-right
-      f = available(r, xn, yn, xl, yl);
-    }
-    regions = __ballot_sync(0xffffffffu, f);
+// 8.6.3 scaling with the flat scaling list (m = 16): TransCoeffLevel -> d, clipped to 16 bits
+__device__ __forceinline__ int dequant(int level, int qp, int bd_shift) {
+  const long long scale = (long long)(c_level_scale[qp % 6] << (qp / 6)) * 16;
+  const long long t = ((long long)level * scale + (1LL << (bd_shift - 1))) >> bd_shift;
+  return (int)(t < -32768 ? -32768 : (t > 32767 ? 32767 : t));
+}
+
+// Descriptor of one transform block, built in phase A, consumed in phase B (uint2):
+//  x: bx/4 [0:4) by/4 [4:8) log2n-2 [8:10) mode [10:16) coded [16] (Cr: [17]) availL [18] availCorner [19] availTop [20]
+//     available below-left samples / 4 [21:25)  available above-right samples / 4 [25:29)
+//  y: offset of the block's residuals inside the component's residual area (samples)
+__device__ __forceinline__ unsigned make_desc(int bx, int by, int lg, int mode, int coded0, int coded1, int cs, int cx0, int cy0, int cw, int ch,
+                                              bool nbL, bool nbAL, bool nbA, bool nbAR) {
+  const int n = 1 << lg;
+  const bool fL = bx > 0 || nbL, fT = by > 0 || nbA;
+  const bool fC = (bx > 0 && by > 0) ? true : (bx > 0 ? nbA : (by > 0 ? nbL : nbAL));
+  const unsigned me = morton4((unsigned)bx >> 2, (unsigned)by >> 2);
+  bool tr = false, bl = false;
+  if (cx0 + bx + n < cw) {
+    if (by > 0) { if (bx + n < cs) tr = morton4((unsigned)(bx + n) >> 2, (unsigned)(by - 1) >> 2) < me; }
+    else tr = (bx + n < cs) ? nbA : nbAR;
   }
-  const int wc = c ? r.W >> 1 : r.W, hc = c ? r.H >> 1 : r.H;
-  const int nk = (4 * n + 32) >> 5;                 // 32-entry chunks that hold the 4n+1 neighbours
-  // Loops over the chunks stay rolled: this function is the instruction-cache footprint of the kernel (measured: 60 % of
-  // all stall cycles were instruction fetch when the three chunk loops were unrolled five-fold).
+  if (cy0 + by + n < ch && by + n < cs) {
+    if (bx > 0) bl = morton4((unsigned)(bx - 1) >> 2, (unsigned)(by + n) >> 2) < me; else bl = nbL;
+  }
+  const int trc = tr ? min(n, cw - (cx0 + bx + n)) : 0, blc = bl ? min(n, ch - (cy0 + by + n)) : 0;
+  return (unsigned)(bx >> 2) | ((unsigned)(by >> 2) << 4) | ((unsigned)(lg - 2) << 8) | ((unsigned)mode << 10) | ((unsigned)coded0 << 16) | ((unsigned)coded1 << 17) |
+         ((unsigned)fL << 18) | ((unsigned)fC << 19) | ((unsigned)fT << 20) | ((unsigned)(blc >> 2) << 21) | ((unsigned)(trc >> 2) << 25);
+}
+
+// ---- phase A, 4x4 blocks: the calling lane owns the block.  scr: the warp's [16][32] int16 scratch (column = lane).
+template <bool LIVE>
+__device__ __forceinline__ void residual4_lane(int16_t* scr, int lane, const CoefEntry* __restrict__ ce, int nnz, int qp, int bd, bool dst, bool tskip, int16_t* out) {
+  int16_t* my = scr + lane;
+#pragma unroll
+  for (int p = 0; p < 16; p++) my[p * 32] = 0;
+  const int bd_shift = bd - 3;                        // bd + log2(4) - 5
 #pragma unroll 1
-  for (int k = 0; k < nk; k++) {
-    const int i = lane + 32 * k;
-    bool av = false; int v = 0;
-    if (i <= 4 * n) {
-      int px, py;
-      if (i < 2 * n) { const int y = 2 * n - 1 - i; px = bx - 1; py = by + y; av = ((regions >> (y < n ? 0 : 1)) & 1) && (cy0 + py < hc); }
-      else if (i == 2 * n) { px = bx - 1; py = by - 1; av = (regions >> 2) & 1; }
-      else { const int x = i - 2 * n - 1; px = bx + x; py = by - 1; av = ((regions >> (x < n ? 3 : 4)) & 1) && (cx0 + px < wc); }
-      if (av) v = tile_sample(m, c, px, py);
+  for (int i = 0; i < nnz; i++) {
+    const CoefEntry e = ld_coef<LIVE>(&ce[i]);
+    my[(e.pos & 15) * 32] = (int16_t)dequant(e.level, qp, bd_shift);
+  }
+  int c[16];
+#pragma unroll
+  for (int p = 0; p < 16; p++) c[p] = my[p * 32];
+  const int bs2 = 20 - bd, rnd = 1 << (bs2 - 1);
+  unsigned* o32 = reinterpret_cast<unsigned*>(out);
+  if (tskip) {                                        // 8.6.4.2, transform_skip_flag: r = d << 7
+#pragma unroll
+    for (int p = 0; p < 16; p += 2) {
+      const int r0 = ((c[p] << 7) + rnd) >> bs2, r1 = ((c[p + 1] << 7) + rnd) >> bs2;
+      o32[p >> 1] = (unsigned)(r0 & 0xffff) | ((unsigned)r1 << 16);
     }
-    const unsigned bal = __ballot_sync(0xffffffffu, av);
-    if (av) m.ref_r[i] = (int16_t)v;
-    if (lane == 0) m.avm[k] = bal;
+    return;
+  }
+  // coefficient c[k * 4 + x] (k: vertical frequency).  First stage (columns): t[x][y] = clip16((sum_k c[k][x] * M[k][y] + 64) >> 7)
+  int t[16];
+#pragma unroll
+  for (int x = 0; x < 4; x++) {
+    const int c0 = c[x], c1 = c[4 + x], c2 = c[8 + x], c3 = c[12 + x];
+    int e0, e1, e2, e3;
+    if (dst) {                                        // DST-VII (8.6.4.2): M = {29 55 74 84; 74 74 0 -74; 84 -29 -74 55; 55 -84 74 -29}
+      e0 = 29 * c0 + 74 * c1 + 84 * c2 + 55 * c3; e1 = 55 * c0 + 74 * c1 - 29 * c2 - 84 * c3;
+      e2 = 74 * c0 - 74 * c2 + 74 * c3;           e3 = 84 * c0 - 74 * c1 + 55 * c2 - 29 * c3;
+    } else {                                          // DCT-II: M = {64 64 64 64; 83 36 -36 -83; 64 -64 -64 64; 36 -83 83 -36}
+      const int a = 64 * (c0 + c2), b = 64 * (c0 - c2), o0 = 83 * c1 + 36 * c3, o1 = 36 * c1 - 83 * c3;
+      e0 = a + o0; e1 = b + o1; e2 = b - o1; e3 = a - o0;
+    }
+    t[x * 4 + 0] = clip3i(-32768, 32767, (e0 + 64) >> 7); t[x * 4 + 1] = clip3i(-32768, 32767, (e1 + 64) >> 7);
+    t[x * 4 + 2] = clip3i(-32768, 32767, (e2 + 64) >> 7); t[x * 4 + 3] = clip3i(-32768, 32767, (e3 + 64) >> 7);
+  }
+  // second stage (rows): r[y][x] = (sum_k t[k][y] * M[k][x] + rnd) >> bs2
+#pragma unroll
+  for (int y = 0; y < 4; y++) {
+    const int c0 = t[y], c1 = t[4 + y], c2 = t[8 + y], c3 = t[12 + y];
+    int e0, e1, e2, e3;
+    if (dst) {
+      e0 = 29 * c0 + 74 * c1 + 84 * c2 + 55 * c3; e1 = 55 * c0 + 74 * c1 - 29 * c2 - 84 * c3;
+      e2 = 74 * c0 - 74 * c2 + 74 * c3;           e3 = 84 * c0 - 74 * c1 + 55 * c2 - 29 * c3;
+    } else {
+      const int a = 64 * (c0 + c2), b = 64 * (c0 - c2), o0 = 83 * c1 + 36 * c3, o1 = 36 * c1 - 83 * c3;
+      e0 = a + o0; e1 = b + o1; e2 = b - o1; e3 = a - o0;
+    }
+    const int r0 = (e0 + rnd) >> bs2, r1 = (e1 + rnd) >> bs2, r2 = (e2 + rnd) >> bs2, r3 = (e3 + rnd) >> bs2;
+    o32[y * 2] = (unsigned)(r0 & 0xffff) | ((unsigned)r1 << 16);
+    o32[y * 2 + 1] = (unsigned)(r2 & 0xffff) | ((unsigned)r3 << 16);
+  }
+}
+
+// ---- phase A, 8x8 .. 32x32 blocks: the whole warp, in place in the block's residual slot (coefficients -> residuals).
+template <bool LIVE>
+__device__ __noinline__ void residual_big(int16_t* rs, int16_t* tmp, const int8_t* __restrict__ mat, const CoefEntry* __restrict__ ce, int nnz, int lg, int qp, int bd, int lane) {
+  const int n = 1 << lg;
+  unsigned* z = reinterpret_cast<unsigned*>(rs);
+#pragma unroll 1
+  for (int i = lane; i < n * n / 2; i += 32) z[i] = 0;
+  __syncwarp();
+  const int bd_shift = bd + lg - 5;
+  int maxrow = 0, maxcol = 0;
+#pragma unroll 1
+  for (int i = lane; i < nnz; i += 32) {
+    const CoefEntry e = ld_coef<LIVE>(&ce[i]);
+    const int pos = e.pos & (n * n - 1);
+    rs[pos] = (int16_t)dequant(e.level, qp, bd_shift);
+    maxrow = max(maxrow, pos >> lg); maxcol = max(maxcol, pos & (n - 1));
+  }
+  maxrow = __reduce_max_sync(0xffffffffu, maxrow); maxcol = __reduce_max_sync(0xffffffffu, maxcol);
+  __syncwarp();
+  const int mstride = 32 << (5 - lg);                 // row k of the n-point DCT = row k << (5 - log2n) of the 32-point one
+  // first stage (columns): tmp[x][y] = clip16((sum_k coef[k][x] * M[k][y] + 64) >> 7), only columns that hold coefficients
+#pragma unroll 1
+  for (int i = lane; i < n * (maxcol + 1); i += 32) {
+    const int y = i & (n - 1), x = i >> lg;
+    int e = 0;
+#pragma unroll 2
+    for (int k = 0; k <= maxrow; k++) e += (int)rs[k * n + x] * (int)mat[k * mstride + y];
+    tmp[x * n + y] = (int16_t)clip3i(-32768, 32767, (e + 64) >> 7);
   }
   __syncwarp();
-  {
-    int first = -1;
+  // second stage (rows): residual r[y][x]
+  const int bs2 = 20 - bd, rnd = 1 << (bs2 - 1);
 #pragma unroll 1
-    for (int k = nk - 1; k >= 0; k--) { const unsigned bal = m.avm[k]; if (bal) first = 32 * k + __ffs(bal) - 1; }
-    const int fill = first < 0 ? (1 << (bd - 1)) : (int)m.ref_r[first];
-    int carry = -1;                                   // highest available index in earlier chunks
-#pragma unroll 1
-    for (int k = 0; k < nk; k++) {
-      const int i = lane + 32 * k;
-      const unsigned bal = m.avm[k];
-      const unsigned le = bal & (0xffffffffu >> (31 - lane));
-      const int j = le ? 32 * k + 31 - __clz(le) : carry;
-      if (i <= 4 * n) m.ref_a[i] = (int16_t)(j < 0 ? fill : (int)m.ref_r[j]);      // j == i when the sample itself is available
-      if (bal) carry = 32 * k + 31 - __clz(bal);
-    }
-    __syncwarp();
+  for (int p = lane; p < n * n; p += 32) {
+    const int x = p & (n - 1), y = p >> lg;
+    int e = 0;
+#pragma unroll 2
+    for (int k = 0; k <= maxcol; k++) e += (int)tmp[k * n + y] * (int)mat[k * mstride + x];
+    rs[p] = (int16_t)((e + rnd) >> bs2);
   }
+  __syncwarp();
+}
+
+// ---- phase B: one transform block (of one component, or of Cb and Cr on the two half-warps).
+//  tl: the lane's component tile (row stride S, sample (x, y) at tl[y * S + PAD + x]), tp: its halo row (sample x at
+//  tp[PAD + x]), rs: its residual area, rf: its neighbour array(s), l / lpc: lane index inside / lanes per component,
+//  gmask: the lanes working on this component.
+template <typename P>
+__device__ __forceinline__ void predict_tb(const uint2 d, P* tl, const P* tp, const int16_t* rs, int16_t* rf, int S, int l, int lpc, unsigned gmask, int cidx, bool luma, int bd, int strong_en) {
+  const int bx = (int)(d.x & 15) << 2, by = (int)((d.x >> 4) & 15) << 2, lg = 2 + (int)((d.x >> 8) & 3), mode = (int)((d.x >> 10) & 63);
+  const int n = 1 << lg, n2 = 2 * n, n4 = 4 * n;
+  const bool coded = (d.x >> (16 + cidx)) & 1;
+  const bool fL = (d.x >> 18) & 1, fC = (d.x >> 19) & 1, fT = (d.x >> 20) & 1;
+  const int blc = (int)((d.x >> 21) & 15) << 2, trc = (int)((d.x >> 25) & 15) << 2;
+  // ---- neighbour array rf[0 .. 4n]: index 0 = bottom of the below-left column ... 2n = corner ... 4n = end of above-right.
+  // Substitution (8.4.4.2.2) = every unavailable index reads the nearest available index below it, or the first available
+  // one; the available indices form up to five intervals known per block, so the source index is a handful of min / compare.
+  const int first = blc ? n - blc : (fL ? n : (fC ? n2 : (fT ? n2 + 1 : (trc ? 3 * n + 1 : -1))));
+  const P* colL = tl + by * S + PAD + bx - 1;                          // left column: sample y at colL[y * S]
+  const P* rowA = (by > 0 ? tl + (by - 1) * S : tp) + PAD + bx;        // row above: sample x at rowA[x] (x = -1: corner)
+  int dcs = 0;
+  const bool small = n4 < lpc;                                         // 4x4 on a full warp: the corner rides in the same pass
+  const int jn = small ? n4 + 1 : n4;
+#pragma unroll 1
+  for (int j = l; j < jn; j += lpc) {
+    const int i = j == n4 ? n2 : (j < n2 ? j : j + 1);
+    int v = 1 << (bd - 1);
+    if (first >= 0) {
+      int s = first;
+      if (blc && i >= n - blc) s = min(i, n - 1);
+      if (fL && i >= n) s = min(i, n2 - 1);
+      if (fC && i >= n2) s = n2;
+      if (fT && i > n2) s = min(i, 3 * n);
+      if (trc && i > 3 * n) s = min(i, 3 * n + trc);
+      v = s < n2 ? (int)colL[(n2 - 1 - s) * S] : (int)rowA[s - n2 - 1];
+    }
+    rf[i] = (int16_t)v;
+    if ((i >= n && i < n2) || (i > n2 && i <= 3 * n)) dcs += v;
+  }
+  if (!small && l == 0) {                                               // corner (index 2n) for blocks that fill every lane
+    int v = 1 << (bd - 1);
+    if (first >= 0) {
+      int s = first;
+      if (blc) s = n - 1;
+      if (fL) s = n2 - 1;
+      if (fC) s = n2;
+      v = s < n2 ? (int)colL[(n2 - 1 - s) * S] : (int)rowA[s - n2 - 1];
+    }
+    rf[n2] = (int16_t)v;
+  }
+  __syncwarp();
   // ---- smoothing of the neighbours (8.4.4.2.3): luma only in 4:2:0
-  const int16_t* ref = m.ref_a;
-  if (c == 0 && mode != 1 && n != 4) {
+  const int16_t* ref = rf;
+  if (luma && mode != 1 && n != 4) {
     const int dist = min(abs(mode - 26), abs(mode - 10));
     const int thr = n == 8 ? 7 : (n == 16 ? 1 : 0);
     if (dist > thr) {
-      const int corner = m.ref_a[2 * n], bl = m.ref_a[0], tr = m.ref_a[4 * n];
-      const bool strong = r.strong && n == 32 && abs(corner + tr - 2 * m.ref_a[3 * n]) < (1 << (bd - 5)) &&
-                          abs(corner + bl - 2 * m.ref_a[n]) < (1 << (bd - 5));
+      const int corner = rf[n2], bl = rf[0], tr = rf[n4];
+      const bool strong = strong_en && n == 32 && abs(corner + tr - 2 * rf[3 * n]) < (1 << (bd - 5)) && abs(corner + bl - 2 * rf[n]) < (1 << (bd - 5));
+      int16_t* rb = rf + REF_STRIDE;
 #pragma unroll 1
-      for (int k = 0; k < nk; k++) {
-        const int i = lane + 32 * k;
-        if (i <= 4 * n) {
-          int v;
-          if (i == 0 || i == 4 * n) v = m.ref_a[i];
-          else if (strong) {
-            if (i == 2 * n) v = corner;
-            else if (i < 2 * n) { const int y = 2 * n - 1 - i; v = ((63 - y) * corner + (y + 1) * bl + 32) >> 6; }
-            else { const int x = i - 2 * n - 1; v = ((63 - x) * corner + (x + 1) * tr + 32) >> 6; }
-          } else v = (m.ref_a[i - 1] + 2 * m.ref_a[i] + m.ref_a[i + 1] + 2) >> 2;
-          m.ref_b[i] = (int16_t)v;
-        }
+      for (int i = l; i <= n4; i += lpc) {
+        int v;
+        if (i == 0 || i == n4) v = rf[i];
+        else if (strong) {
+          if (i == n2) v = corner;
+          else if (i < n2) { const int y = n2 - 1 - i; v = ((63 - y) * corner + (y + 1) * bl + 32) >> 6; }
+          else { const int x = i - n2 - 1; v = ((63 - x) * corner + (x + 1) * tr + 32) >> 6; }
+        } else v = (rf[i - 1] + 2 * rf[i] + rf[i + 1] + 2) >> 2;
+        rb[i] = (int16_t)v;
       }
       __syncwarp();
-      ref = m.ref_b;
+      ref = rb;
     }
   }
-  // ---- prediction (8.4.4.2.4 - 8.4.4.2.6) written straight into the tile
-  uint16_t* tile = c == 0 ? m.tile_y : m.tile_c[c - 1];
-  const int ts = c == 0 ? m.ts : m.tsc;
+  // ---- prediction (8.4.4.2.4 - 8.4.4.2.6) + residual (8.6.6), written straight into the tile
   const int maxv = (1 << bd) - 1;
-#define LEFT(y) ((int)ref[2 * n - 1 - (y)])
-#define TOP(x) ((int)ref[2 * n + 1 + (x)])
+#define LEFT(y) ((int)ref[n2 - 1 - (y)])
+#define TOP(x) ((int)ref[n2 + 1 + (x)])
   int dc = 0;
-  if (mode == 1) {
-    int s = 0;
-    for (int i = lane; i < n; i += 32) s += LEFT(i) + TOP(i);
-    s = __reduce_add_sync(0xffffffffu, s);
-    dc = (s + n) >> (log2n + 1);
-  }
+  if (mode == 1) dc = (__reduce_add_sync(gmask, dcs) + n) >> (lg + 1);
   const int ang = c_angle[mode], ia = c_inv_angle[mode];
-  const bool edge = c == 0 && n < 32;
-  for (int p = lane; p < n * n; p += 32) {
-    const int x = p & (n - 1), y = p >> log2n;
+  const bool edge = luma && n < 32;
+  const int16_t* rsb = rs + d.y;
+  P* out = tl + by * S + PAD + bx;
+#pragma unroll 1
+  for (int e = l; e < n * n; e += lpc) {
+    const int x = e & (n - 1), y = e >> lg;
     int v;
-    if (mode == 0) v = ((n - 1 - x) * LEFT(y) + (x + 1) * TOP(n) + (n - 1 - y) * TOP(x) + (y + 1) * LEFT(n) + n) >> (log2n + 1);
+    if (mode == 0) v = ((n - 1 - x) * LEFT(y) + (x + 1) * TOP(n) + (n - 1 - y) * TOP(x) + (y + 1) * LEFT(n) + n) >> (lg + 1);
     else if (mode == 1) {
       v = dc;
       if (edge) {
@@ -257,77 +334,15 @@ __device__ __noinline__ void process_tb(WarpMem& m, const int8_t* __restrict__ m
       if (f) { const int b = k1 >= 0 ? LEFT(k1 - 1) : TOP(-1 + ((k1 * ia + 128) >> 8)); v = ((32 - f) * a + f * b + 16) >> 5; } else v = a;
       if (mode == 10 && edge && y == 0) v = clip3i(0, maxv, LEFT(0) + ((TOP(x) - TOP(-1)) >> 1));
     }
-    tile[(by + y) * ts + bx + x] = (uint16_t)v;
+    if (coded) v = clip3i(0, maxv, v + (int)rsb[e]);
+    out[y * S + x] = (P)v;
   }
 #undef LEFT
 #undef TOP
   __syncwarp();
-  if (ncoef == 0) return;
-  // ---- scaling (8.6.3, flat scaling list m = 16)
-#pragma unroll 1
-  for (int i = lane; i < n * n / 2; i += 32) reinterpret_cast<uint32_t*>(m.coef)[i] = 0;
-  __syncwarp();
-  const int bd_shift = bd + log2n - 5;
-  const long long scale = (long long)(c_level_scale[qp % 6] << (qp / 6)) * 16;
-  int maxrow = 0, maxcol = 0;
-#pragma unroll 1
-  for (int i = lane; i < ncoef; i += 32) {
-    const CoefEntry e = ld_coef<LIVE>(&ce[i]);
-    const long long t = ((long long)e.level * scale + (1LL << (bd_shift - 1))) >> bd_shift;
-    m.coef[e.pos] = (int16_t)(t < -32768 ? -32768 : (t > 32767 ? 32767 : t));
-    maxrow = max(maxrow, e.pos >> log2n); maxcol = max(maxcol, e.pos & (n - 1));
-  }
-  maxrow = __reduce_max_sync(0xffffffffu, maxrow); maxcol = __reduce_max_sync(0xffffffffu, maxcol);
-  __syncwarp();
-  const int bs2 = 20 - bd;
-  if (tskip) {                                          // 8.6.4.2, transform_skip_flag: r = d << 7
-#pragma unroll 1
-    for (int p = lane; p < n * n; p += 32) {
-      const int x = p & (n - 1), y = p >> log2n;
-      const int res = (((int)m.coef[p] << 7) + (1 << (bs2 - 1))) >> bs2;
-      uint16_t* q = &tile[(by + y) * ts + bx + x];
-      *q = (uint16_t)clip3i(0, maxv, (int)*q + res);
-    }
-    __syncwarp();
-    return;
-  }
-  // matrix rows: DST-VII 4x4 for intra luma 4x4 (appended to the DCT matrix in shared memory), else row k of the
-  // n-point DCT = row k << (5 - log2n) of the 32-point one
-  const bool dst = c == 0 && log2n == 2;
-  const int8_t* mrow = dst ? mat + 1024 : mat;
-  const int mstride = dst ? 4 : (32 << (5 - log2n));
-  // first stage (columns): tmp[x][y] = clip16((sum_k coef[k][x] * M[k][y] + 64) >> 7), only columns that hold coefficients
-#pragma unroll 1
-  for (int i = lane; i < n * (maxcol + 1); i += 32) {
-    const int y = i & (n - 1), x = i >> log2n;
-    int e = 0;
-#pragma unroll 2
-    for (int k = 0; k <= maxrow; k++) e += (int)m.coef[k * n + x] * (int)mrow[k * mstride + y];
-    m.tmp[x * n + y] = (int16_t)clip3i(-32768, 32767, (e + 64) >> 7);
-  }
-  __syncwarp();
-  // second stage (rows) + reconstruction (8.6.6)
-#pragma unroll 1
-  for (int p = lane; p < n * n; p += 32) {
-    const int x = p & (n - 1), y = p >> log2n;
-    int e = 0;
-#pragma unroll 2
-    for (int k = 0; k <= maxcol; k++) e += (int)m.tmp[k * n + y] * (int)mrow[k * mstride + x];
-    const int res = (e + (1 << (bs2 - 1))) >> bs2;
-    uint16_t* q = &tile[(by + y) * ts + bx + x];
-    *q = (uint16_t)clip3i(0, maxv, (int)*q + res);
-  }
-  __syncwarp();
 }
 
-__device__ __forceinline__ int chroma_qp(int qpy, int off, int bd) {       // 8.6.1, ChromaArrayType == 1
-  const int qbd = 6 * (bd - 8);
-  const int qpi = clip3i(-qbd, 57, qpy + off);
-  const int qpc = qpi < 30 ? qpi : (qpi >= 43 ? qpi - 6 : c_qpc[qpi - 30]);
-  return qpc + qbd;
-}
-
-template <bool LIVE>
+template <typename P, bool LIVE>
 __global__ void __launch_bounds__(WARPS * 32, B200_RECON_MIN_BLOCKS) hevc_recon_kernel(const DeviceBatch b) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   int8_t* mat = reinterpret_cast<int8_t*>(smem_raw);                       // 32x32 DCT matrix, shared by the CTA
@@ -338,20 +353,16 @@ __global__ void __launch_bounds__(WARPS * 32, B200_RECON_MIN_BLOCKS) hevc_recon_
     else { int j = (k * (2 * x + 1)) & 127, sgn = 1; if (j > 64) j = 128 - j; if (j > 32) { j = 64 - j; sgn = -1; } v = sgn * c_dct[j]; }
     mat[i] = (int8_t)v;
   }
-  if (threadIdx.x < 16) mat[1024 + threadIdx.x] = c_dst[threadIdx.x];
   __syncthreads();
   const int lane = threadIdx.x & 31;
-  WarpMem m;
-  warp_mem_init(m, smem_raw + MAT_BYTES + (threadIdx.x >> 5) * warp_mem_bytes(b.max_log2_ctb), b.max_log2_ctb);
-  // process_tb is out of line and takes the warp's descriptors by reference: they live in SHARED memory (as locals they
-  // would sit in local memory, one 128-byte line of L1 per word and warp; measured: 35 % of all stall cycles were loads
-  // of exactly these fields).  The kernel body keeps its own register copies.
-  __shared__ WarpMem s_wm[WARPS];
-  __shared__ RowCtx s_row[WARPS];
-  WarpMem& wm = s_wm[threadIdx.x >> 5];
-  RowCtx& rs = s_row[threadIdx.x >> 5];
-  if (lane == 0) wm = m;
-  __syncwarp();
+  const WarpLayout L = warp_layout(b.max_log2_ctb, (int)sizeof(P));
+  unsigned char* wb = smem_raw + MAT_BYTES + (threadIdx.x >> 5) * L.total;
+  P* const tile0 = reinterpret_cast<P*>(wb + L.tile);
+  P* const top0 = reinterpret_cast<P*>(wb + L.top);
+  int16_t* const res0 = reinterpret_cast<int16_t*>(wb + L.res);
+  int16_t* const tmp = reinterpret_cast<int16_t*>(wb + L.tmp);
+  uint2* const desc = reinterpret_cast<uint2*>(wb + L.desc);
+  const unsigned lt_mask = (1u << lane) - 1u;
 
   for (;;) {
     unsigned t = 0;
@@ -360,125 +371,179 @@ __global__ void __launch_bounds__(WARPS * 32, B200_RECON_MIN_BLOCKS) hevc_recon_
     if (t >= (unsigned)b.nrows) break;
     const uint2 pr = b.row_list[t];
     const PicDesc* pic = &b.pics[pr.x];
-    RowCtx r;
-    r.pic = pic; r.ctus = b.ctus + pic->ctu_base; r.slices = b.slices + pic->slice_base;
-    r.W = pic->width; r.H = pic->height; r.log2ctb = pic->log2_ctb; r.ctb = 1 << r.log2ctb; r.wctb = pic->wctb;
-    r.bd = pic->bit_depth; r.chroma = pic->chroma; r.strong = pic->strong_intra;
-    r.ry = (int)pr.y; r.y0 = r.ry << r.log2ctb;
+    const int g = (int)(pr.y >> 31), ry = (int)(pr.y & 0x7fffffffu);        // g = 0: luma, 1: Cb + Cr
+    const CtuInfo* ctus = b.ctus + pic->ctu_base;
+    const SliceInfo* slices = b.slices + pic->slice_base;
+    const int log2ctb = pic->log2_ctb, wctb = pic->wctb, bd = pic->bit_depth, strong_en = pic->strong_intra;
+    const int cs = (1 << log2ctb) >> g, S = cs + PAD;                        // component CTB size, tile row stride
+    const int cw = pic->width >> g, ch = pic->height >> g;
+    const int y0 = ry << log2ctb, cy0 = y0 >> g;
     const TuCmd* tus = b.tus + pic->tu_base;
     const CoefEntry* coefs = b.coefs + pic->coef_base;
-    unsigned* prog = b.progress + pic->progress_base;
+    unsigned* prog = b.progress + 2 * pic->progress_base + g;               // counter of (row r, group g) at prog[2 * r]
     const unsigned* eprog = b.entropy_progress ? b.entropy_progress + pic->progress_base : nullptr;
-    const bool b8 = r.bd == 8;
-    const int ctbc = r.ctb >> 1;
-    const int nch = r.chroma ? 3 : 1;
+    // lane roles in phase B
+    const int lpc = g ? 16 : 32, l = lane & (lpc - 1), cidx = g ? lane >> 4 : 0;
+    const unsigned gmask = g ? (0xffffu << (16 * cidx)) : 0xffffffffu;
+    P* const tl = tile0 + cidx * (cs * S);
+    P* const tp = top0 + cidx * (PAD + 2 * cs + 16);
+    int16_t* const rs = res0 + cidx * (cs * cs);
+    int16_t* const rf = tmp + cidx * REF_STRIDE;
+    P* const recp = static_cast<P*>(pic->rec[g + cidx]);
+    const int rst = pic->rec_stride[g + cidx];
 
-    for (r.rx = 0; r.rx < r.wctb; r.rx++) {
-      r.x0 = r.rx << r.log2ctb;
-      // (1) with K0 running concurrently: this CTB's commands must have been published; (2) wavefront: the above-right
-      // CTB must be reconstructed (lag 2).  Relaxed polling loads (no L1 invalidation) with microsecond back-off (a CTB
-      // takes ~0.2 ms): waiting rows must not flood L2 with polls.  Everything produced by another SM during this
-      // kernel -- commands and the halo row -- is then read with L1-bypassing loads.
-      int abort = 0;
-      if (lane == 0) {
-        unsigned spins = 0, ns = 250;
-        if (eprog) while (ld_acquire(&eprog[r.ry]) < (unsigned)(r.rx + 1)) {
-          __nanosleep(ns); if (ns < 8000) ns <<= 1;
-          if ((++spins & 31u) == 0 && ld_acquire(b.error_flag)) break;            // K0 failed (corrupt stream): its progress will never come
-          if (spins > (1u << 23)) { atomicExch(b.error_flag, 1u); break; }       // ~1 min; turns a would-be hang into an error
+    for (int rx = 0; rx < wctb; rx++) {
+      const int x0 = rx << log2ctb, cx0 = x0 >> g;
+      // (1) with K0 running concurrently: this CTB's commands must have been published.  Relaxed polling loads (no L1
+      // invalidation) with microsecond back-off: waiting rows must not flood L2 with polls.
+      if (eprog) {
+        int abort = 0;
+        if (lane == 0) {
+          unsigned spins = 0, ns = 250;
+          while (ld_acquire(&eprog[ry]) < (unsigned)(rx + 1)) {
+            __nanosleep(ns); if (ns < 8000) ns <<= 1;
+            if ((++spins & 31u) == 0 && ld_acquire(b.error_flag)) break;            // K0 failed (corrupt stream): its progress will never come
+            if (spins > (1u << 23)) { atomicExch(b.error_flag, 1u); break; }       // ~1 min; turns a would-be hang into an error
+          }
+          abort = ld_acquire(b.error_flag) != 0u;
         }
-        if (r.ry > 0) {
-          const unsigned need = (unsigned)min(r.rx + 2, r.wctb);
-          spins = 0; ns = 250;
-          while (ld_acquire(&prog[r.ry - 1]) < need) {
+        if (__shfl_sync(0xffffffffu, abort, 0)) return;
+      }
+      const int addr = ry * wctb + rx;
+      const CtuInfo ci = ld_ctu<LIVE>(&ctus[addr]);
+      const int cur = ci.slice_idx;
+      const bool nbL = rx > 0 && (int)ld_cmd<LIVE>(&ctus[addr - 1].slice_idx) == cur;
+      const bool nbAL = rx > 0 && ry > 0 && (int)ld_cmd<LIVE>(&ctus[addr - wctb - 1].slice_idx) == cur;
+      const bool nbA = ry > 0 && (int)ld_cmd<LIVE>(&ctus[addr - wctb].slice_idx) == cur;
+      const bool nbAR = ry > 0 && rx + 1 < wctb && (int)ld_cmd<LIVE>(&ctus[addr - wctb + 1].slice_idx) == cur;
+      const SliceInfo sl = slices[cur];
+      // ---- phase A: descriptors + residuals, lane-parallel over the CTB's transform units
+      int ntb = 0;
+#pragma unroll 1
+      for (unsigned base = 0; base < ci.tu_count; base += 32) {
+        const bool valid = base + lane < ci.tu_count;
+        TuCmd cmd{0, 0, 0, 0};
+        if (valid) cmd = ld_tu<LIVE>(&tus[ci.tu_start + base + lane]);
+        const int log2n = 2 + (int)((cmd.w0 >> 24) & 3);
+        const int lx = (int)((cmd.w0 & 0xfff) << 2) - x0, ly = (int)(((cmd.w0 >> 12) & 0xfff) << 2) - y0;   // luma position inside the CTB
+        const int qpy = (int)((cmd.w1 >> 12) & 0xff) - 64;
+        const int nl = (int)(cmd.w3 & 0x7ff), ncb = (int)((cmd.w3 >> 11) & 0x3ff), ncr = (int)((cmd.w3 >> 21) & 0x3ff);
+        const CoefEntry* ce = coefs + cmd.w2;
+        bool has; int bx, by, lg, mode, coded0, coded1, qp0, qp1 = 0, ts0, ts1 = 0, n0, n1 = 0; const CoefEntry* ce1 = ce;
+        if (g == 0) {
+          has = valid; bx = lx; by = ly; lg = log2n; mode = (int)(cmd.w1 & 63); coded0 = (int)((cmd.w0 >> 26) & 1); coded1 = 0;
+          qp0 = qpy + 6 * (bd - 8); ts0 = (int)((cmd.w0 >> 30) & 1); n0 = nl;
+        } else {
+          has = valid && ((cmd.w0 >> 29) & 1);
+          if (log2n > 2) { bx = lx >> 1; by = ly >> 1; lg = log2n - 1; } else { bx = (lx - 4) >> 1; by = (ly - 4) >> 1; lg = 2; }
+          mode = (int)((cmd.w1 >> 6) & 63); coded0 = (int)((cmd.w0 >> 27) & 1); coded1 = (int)((cmd.w0 >> 28) & 1);
+          qp0 = chroma_qp(qpy, sl.cb_qp_offset, bd); qp1 = chroma_qp(qpy, sl.cr_qp_offset, bd);
+          ts0 = (int)((cmd.w0 >> 31) & 1); ts1 = (int)((cmd.w1 >> 20) & 1);
+          ce = ce + nl; n0 = ncb; ce1 = ce + ncb; n1 = ncr;
+        }
+        if (!has) { coded0 = coded1 = 0; bx = by = 0; lg = 2; }
+        coded0 = coded0 && n0 > 0; coded1 = coded1 && n1 > 0;
+        const unsigned hb = __ballot_sync(0xffffffffu, has);
+        const int idx = ntb + __popc(hb & lt_mask);
+        const unsigned roff = morton4((unsigned)bx >> 2, (unsigned)by >> 2) * 16;
+        if (has) desc[idx] = make_uint2(make_desc(bx, by, lg, mode, coded0, coded1, cs, cx0, cy0, cw, ch, nbL, nbAL, nbA, nbAR), roff);
+        ntb += __popc(hb);
+        // 4x4 blocks: one lane each, in registers
+        if (lg == 2) {
+#pragma unroll 1
+          for (int c2 = 0; c2 < 2; c2++)
+            if (c2 ? coded1 : coded0)
+              residual4_lane<LIVE>(tmp, lane, c2 ? ce1 : ce, c2 ? n1 : n0, c2 ? qp1 : qp0, bd, g == 0, c2 ? ts1 : ts0, res0 + (c2 ? cs * cs : 0) + roff);
+        }
+        __syncwarp();
+        // larger blocks: the whole warp, one block at a time
+        unsigned big0 = __ballot_sync(0xffffffffu, lg > 2 && coded0), big1 = __ballot_sync(0xffffffffu, lg > 2 && coded1);
+#pragma unroll 1
+        for (int c2 = 0; c2 < 2; c2++) {
+          unsigned m = c2 ? big1 : big0;
+          while (m) {
+            const int src = __ffs(m) - 1; m &= m - 1;
+            const unsigned long long cp = __shfl_sync(0xffffffffu, (unsigned long long)(c2 ? ce1 : ce), src);
+            const int nn = __shfl_sync(0xffffffffu, c2 ? n1 : n0, src), lgg = __shfl_sync(0xffffffffu, lg, src), qq = __shfl_sync(0xffffffffu, c2 ? qp1 : qp0, src);
+            const unsigned ro = __shfl_sync(0xffffffffu, roff, src);
+            residual_big<LIVE>(res0 + (c2 ? cs * cs : 0) + ro, tmp, mat, reinterpret_cast<const CoefEntry*>(cp), nn, lgg, qq, bd, lane);
+          }
+        }
+      }
+      __syncwarp();
+      // (2) wavefront: the above-right CTB of this component group must be reconstructed (lag 2)
+      if (ry > 0) {
+        int abort = 0;
+        if (lane == 0) {
+          const unsigned need = (unsigned)min(rx + 2, wctb);
+          unsigned spins = 0, ns = 250;
+          while (ld_acquire(&prog[2 * (ry - 1)]) < need) {
             __nanosleep(ns); if (ns < 8000) ns <<= 1;
             if ((++spins & 31u) == 0 && ld_acquire(b.error_flag)) break;
             if (spins > (1u << 23)) { atomicExch(b.error_flag, 1u); break; }
           }
+          abort = ld_acquire(b.error_flag) != 0u;
         }
-        abort = ld_acquire(b.error_flag) != 0u;
+        if (__shfl_sync(0xffffffffu, abort, 0)) return;                      // the batch is reported as failed; nothing it produced is used
+        // halo row above (corner .. above-right) from HBM/L2: written by another SM during this kernel -> L1-bypassing loads
+        const int cnt = 1 + 2 * cs;
+        const P* grow = recp + (size_t)(cy0 - 1) * rst;
+#pragma unroll 1
+        for (int i = l; i < cnt; i += lpc) {
+          const int gx = cx0 - 1 + i;
+          int v = 0;
+          if (gx >= 0 && gx < cw) v = (int)__ldcg(grow + gx);
+          tp[PAD - 1 + i] = (P)v;
+        }
       }
-      abort = __shfl_sync(0xffffffffu, abort, 0);
-      if (abort) return;                                     // the batch is reported as failed; nothing it produced is used
-      const CtuInfo ci = ld_ctu<LIVE>(&r.ctus[r.ry * r.wctb + r.rx]);
-      r.cur_slice = ci.slice_idx;
-      r.nb_slice[0] = r.rx > 0 ? (int)ld_cmd<LIVE>(&r.ctus[r.ry * r.wctb + r.rx - 1].slice_idx) : -1;
-      r.nb_slice[1] = (r.rx > 0 && r.ry > 0) ? (int)ld_cmd<LIVE>(&r.ctus[(r.ry - 1) * r.wctb + r.rx - 1].slice_idx) : -1;
-      r.nb_slice[2] = r.ry > 0 ? (int)ld_cmd<LIVE>(&r.ctus[(r.ry - 1) * r.wctb + r.rx].slice_idx) : -1;
-      r.nb_slice[3] = (r.ry > 0 && r.rx + 1 < r.wctb) ? (int)ld_cmd<LIVE>(&r.ctus[(r.ry - 1) * r.wctb + r.rx + 1].slice_idx) : -1;
-      TuCmd next_cmd = ci.tu_count ? ld_tu<LIVE>(&tus[ci.tu_start]) : TuCmd{0, 0, 0, 0};
-      if (lane == 0) rs = r;                                 // the shared copy process_tb reads (synchronised by the __syncwarp below / in process_tb)
       __syncwarp();
-      if (r.ry > 0) {
-        // fetch the halo row above from HBM/L2
-        __syncwarp();
+      // ---- phase B: prediction + reconstruction, block after block
 #pragma unroll 1
-        for (int c = 0; c < nch; c++) {
-          const int cw = c ? r.W >> 1 : r.W, st = pic->rec_stride[c];
-          const int gx0 = (c ? r.x0 >> 1 : r.x0) - 1, gy = (c ? r.y0 >> 1 : r.y0) - 1;
-          const int cnt = 1 + 2 * (c ? ctbc : r.ctb);
-          uint16_t* dst = c == 0 ? m.top_y : m.top_c[c - 1];
+      for (int k = 0; k < ntb; k++) predict_tb<P>(desc[k], tl, tp, rs, rf, S, l, lpc, gmask, cidx, g == 0, bd, strong_en);
+      // ---- the finished CTB goes to HBM; its last column becomes the next CTB's left halo
+      {
+        const int w = min(cs, cw - cx0), h = min(cs, ch - cy0);
+        const unsigned rowb = (unsigned)(w * (int)sizeof(P));
+        P* gdst = recp + (size_t)cy0 * rst + cx0;
+        if ((rowb & 15u) == 0) {
+          // TMA: one bulk row copy per lane (generic-proxy writes of the tile made visible to the async proxy first)
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+          __syncwarp();
 #pragma unroll 1
-          for (int i = lane; i < cnt; i += 32) {
-            const int gx = gx0 + i;
-            int v = 0;
-            if (gx >= 0 && gx < cw) v = b8 ? (int)__ldcg(static_cast<const uint8_t*>(pic->rec[c]) + (size_t)gy * st + gx)
-                                           : (int)__ldcg(static_cast<const uint16_t*>(pic->rec[c]) + (size_t)gy * st + gx);
-            dst[i] = (uint16_t)v;
+          for (int y = l; y < h; y += lpc) bulk_store(gdst + (size_t)y * rst, tl + y * S + PAD, rowb);
+          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        } else {
+          const int wq = (int)(rowb >> 2);                                     // 4-byte words per row (widths are multiples of 4 samples)
+#pragma unroll 1
+          for (int i = l; i < h * wq; i += lpc) {
+            const int y = i / wq, q = i - y * wq;
+            reinterpret_cast<unsigned*>(gdst + (size_t)y * rst)[q] = reinterpret_cast<const unsigned*>(tl + y * S + PAD)[q];
           }
         }
+        // last column -> left halo of the next CTB (read before, written after the rows have left the tile)
+        P keep0 = 0, keep1 = 0;
+        if (l < cs) keep0 = tl[l * S + PAD + cs - 1];
+        if (l + lpc < cs) keep1 = tl[(l + lpc) * S + PAD + cs - 1];
+        if ((rowb & 15u) == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");     // rows are in global memory; the tile may be overwritten
         __syncwarp();
+        if (l < cs) tl[l * S + PAD - 1] = keep0;
+        if (l + lpc < cs) tl[(l + lpc) * S + PAD - 1] = keep1;
+        __threadfence();
+        __syncwarp();                                         // all lanes' stores precede lane 0's release store (cumulativity)
+        if (lane == 0) st_release(&prog[2 * ry], (unsigned)(rx + 1));
       }
-      const SliceInfo sl = r.slices[ci.slice_idx];
-      for (unsigned ti = 0; ti < ci.tu_count; ti++) {
-        const TuCmd cmd = next_cmd;
-        if (ti + 1 < ci.tu_count) next_cmd = ld_tu<LIVE>(&tus[ci.tu_start + ti + 1]);      // prefetch: hides one dependent HBM/L2 round trip per TU
-        const int x4 = cmd.w0 & 0xfff, y4 = (cmd.w0 >> 12) & 0xfff, log2n = 2 + ((cmd.w0 >> 24) & 3);
-        const int lmode = cmd.w1 & 63, cmode = (cmd.w1 >> 6) & 63, qpy = (int)((cmd.w1 >> 12) & 0xff) - 64;
-        const int nl = cmd.w3 & 0x7ff, ncb = (cmd.w3 >> 11) & 0x3ff, ncr = (cmd.w3 >> 21) & 0x3ff;
-        const CoefEntry* ce = coefs + cmd.w2;
-        const int bx = (x4 << 2) - r.x0, by = (y4 << 2) - r.y0;
-        process_tb<LIVE>(wm, mat, rs, 0, bx, by, log2n, lmode, ce, ((cmd.w0 >> 26) & 1) ? nl : 0, qpy + 6 * (r.bd - 8), (cmd.w0 >> 30) & 1, lane);
-        if ((cmd.w0 >> 29) & 1) {
-          int cbx, cby, clog;
-          if (log2n > 2) { cbx = bx >> 1; cby = by >> 1; clog = log2n - 1; } else { cbx = (bx - 4) >> 1; cby = (by - 4) >> 1; clog = 2; }
-          process_tb<LIVE>(wm, mat, rs, 1, cbx, cby, clog, cmode, ce + nl, ((cmd.w0 >> 27) & 1) ? ncb : 0, chroma_qp(qpy, sl.cb_qp_offset, r.bd), (cmd.w0 >> 31) & 1, lane);
-          process_tb<LIVE>(wm, mat, rs, 2, cbx, cby, clog, cmode, ce + nl + ncb, ((cmd.w0 >> 28) & 1) ? ncr : 0, chroma_qp(qpy, sl.cr_qp_offset, r.bd), (cmd.w1 >> 20) & 1, lane);
-        }
-      }
-      // write the finished CTB to HBM (coalesced rows), keep its last column as the next CTB's left halo
-#pragma unroll 1
-      for (int c = 0; c < nch; c++) {
-        const int cw = c ? r.W >> 1 : r.W, chh = c ? r.H >> 1 : r.H, st = pic->rec_stride[c];
-        const int gx0 = c ? r.x0 >> 1 : r.x0, gy0 = c ? r.y0 >> 1 : r.y0, sz = c ? ctbc : r.ctb, lg = c ? r.log2ctb - 1 : r.log2ctb;
-        const uint16_t* tile = c == 0 ? m.tile_y : m.tile_c[c - 1];
-        const int ts = c == 0 ? m.ts : m.tsc;
-        const int w = min(sz, cw - gx0), h = min(sz, chh - gy0);
-#pragma unroll 2
-        for (int i = lane; i < sz * h; i += 32) {
-          const int x = i & (sz - 1), y = i >> lg;
-          if (x < w) {
-            const uint16_t v = tile[y * ts + x];
-            if (b8) static_cast<uint8_t*>(pic->rec[c])[(size_t)(gy0 + y) * st + gx0 + x] = (uint8_t)v;
-            else static_cast<uint16_t*>(pic->rec[c])[(size_t)(gy0 + y) * st + gx0 + x] = v;
-          }
-        }
-        uint16_t* left = c == 0 ? m.left_y : m.left_c[c - 1];
-#pragma unroll 1
-        for (int y = lane; y < sz; y += 32) left[y] = tile[y * ts + sz - 1];
-      }
-      __syncwarp();                                         // all lanes' stores precede lane 0's release store (cumulativity)
-      if (lane == 0) st_release(&prog[r.ry], (unsigned)(r.rx + 1));
     }
   }
 }
 
 int launch_recon(const DeviceBatch& b, cudaStream_t s) {
   if (b.nrows <= 0) return B200_OK;
-  const size_t smem = MAT_BYTES + warp_mem_bytes(b.max_log2_ctb) * WARPS;
   const bool live = b.entropy_progress != nullptr;
-  auto kern = live ? hevc_recon_kernel<true> : hevc_recon_kernel<false>;
-  B200_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(MAT_BYTES + warp_mem_bytes(6) * WARPS)));
+  const int bps = b.wide_samples ? 2 : 1;
+  const size_t smem = MAT_BYTES + (size_t)warp_layout(b.max_log2_ctb, bps).total * WARPS;
+  const void* kern = bps == 2 ? (live ? (const void*)hevc_recon_kernel<uint16_t, true> : (const void*)hevc_recon_kernel<uint16_t, false>)
+                              : (live ? (const void*)hevc_recon_kernel<uint8_t, true> : (const void*)hevc_recon_kernel<uint8_t, false>);
+  B200_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(MAT_BYTES + (size_t)warp_layout(6, 2).total * WARPS)));
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
@@ -488,8 +553,8 @@ int launch_recon(const DeviceBatch& b, cudaStream_t s) {
   if (b.blocks_per_sm > 0 && b.blocks_per_sm < occ) occ = b.blocks_per_sm;
   const int want = (b.nrows + WARPS - 1) / WARPS;
   const int grid = want < sms * occ ? want : sms * occ;
-  kern<<<grid, WARPS * 32, smem, s>>>(b);
-  cudaError_t e = cudaGetLastError();
+  void* args[] = {const_cast<DeviceBatch*>(&b)};
+  cudaError_t e = cudaLaunchKernel(kern, dim3((unsigned)grid), dim3(WARPS * 32), args, smem, s);
   if (e != cudaSuccess) return set_error(B200_E_CUDA, "recon launch: %s", cudaGetErrorString(e));
   return B200_OK;
 }
