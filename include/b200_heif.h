@@ -229,6 +229,15 @@ int b200_decode_grid_to_rgb_host(b200_decoder* dec, int cols, int rows, const ui
                                  uint64_t max_image_size_pixels, int canvas_w, int canvas_h, const b200_geometry* geom /* NULL = identity */,
                                  const b200_color_options* opt, void* out, size_t out_stride, b200_image_info* info);
 
+/* Page-locked host memory: outputs of b200_decode_grid_to_rgb_host / b200_decoder_read_planes placed here are written by
+   DMA directly (no bounce copy).  b200_host_register page-locks memory the caller owns (e.g. the planes of a heif_image,
+   or a shared-memory mapping several ranks write their row bands into).  Counterpart in the reference: none (its planes
+   are plain calloc memory, libheif/image/pixelimage.cc:409-442). */
+int b200_host_alloc(size_t bytes, void** out);
+void b200_host_free(void* p);
+int b200_host_register(void* p, size_t bytes);
+int b200_host_unregister(void* p);
+
 #ifdef __cplusplus
 }
 #endif

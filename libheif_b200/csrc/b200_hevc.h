@@ -56,9 +56,11 @@ struct EntropyPic { syn::SeqParams sp; syn::PicBuffers pb; uint32_t progress_bas
 struct EntropyBatch {
   const EntropyPic* pics; int npics;
   const syn::Substream* subs;    // batch-wide, grouped per picture (EntropyPic::sub_base)
-  const uint2* order;            // (picture, local sub-stream index) in ticket order
   int nsubs;
-  unsigned int* ticket; unsigned int* progress; unsigned int* sub_done; unsigned int* error_flag;
+  // ready queue: queue[0 .. nsubs) holds (batch-wide sub-stream index + 1), 0 = not yet pushed; qhead / qtail are the pop and
+  // push cursors; deps[i] counts the events sub-stream i still waits for (wake_* links in syn::Substream are batch-wide)
+  unsigned int* queue; unsigned int* qhead; unsigned int* qtail; unsigned int* deps;
+  unsigned int* progress; unsigned int* sub_done; unsigned int* error_flag;
   int blocks_per_sm;             // > 0: cap of resident CTAs per SM (co-residency with K1)
 };
 int launch_entropy(const EntropyBatch& b, cudaStream_t s);

@@ -79,9 +79,10 @@ struct b200_decoder {
   std::vector<int> parse_rc; std::vector<std::string> parse_msg;
   DevBuf<PicDesc> pics; DevBuf<CtuInfo> ctus; DevBuf<TuCmd> tus; DevBuf<CoefEntry> coefs; DevBuf<SliceInfo> slices;
   DevBuf<int8_t> qp8; DevBuf<uint8_t> edge8; DevBuf<uint2> rows; DevBuf<unsigned> sync;   // sync: [0] ticket, [1] error flag, [2..] progress
-  DevBuf<uint8_t> rec; DevBuf<uint8_t> canvas;
+  DevBuf<uint8_t> rec; DevBuf<uint8_t> canvas; DevBuf<uint8_t> rgb; DevBuf<uint8_t> bounce;   // rgb / bounce: fused host entry point
+  cudaStream_t own = nullptr; cudaEvent_t ev_band[2] = {nullptr, nullptr};
   // device front-end (entropy decoding on the GPU)
-  DevBuf<uint8_t> rbsp; DevBuf<syn::Substream> subs; DevBuf<uint2> sub_order; DevBuf<uint16_t> ctu_slice; DevBuf<EntropyPic> epics;
+  DevBuf<uint8_t> rbsp; DevBuf<syn::Substream> subs; DevBuf<unsigned> equeue; DevBuf<uint16_t> ctu_slice; DevBuf<EntropyPic> epics;
   DevBuf<uint8_t> ipm4, cd8, wpp_ctx, end_state; DevBuf<unsigned> esync; DevBuf<unsigned long long> ecount;
   int front_end = 1;               // 1 = CABAC on the GPU (default), 0 = CABAC on the host cores
   bool used_device_front_end = false; size_t n_subs = 0;
@@ -100,8 +101,10 @@ struct b200_decoder {
   ~b200_decoder() {
     delete pool;
     pics.release(); ctus.release(); tus.release(); coefs.release(); slices.release(); qp8.release(); edge8.release(); rows.release();
-    sync.release(); rec.release(); canvas.release();
-    rbsp.release(); subs.release(); sub_order.release(); ctu_slice.release(); epics.release(); ipm4.release(); cd8.release(); wpp_ctx.release();
+    sync.release(); rec.release(); canvas.release(); rgb.release(); bounce.release();
+    if (own) cudaStreamDestroy(own);
+    for (auto& e : ev_band) if (e) cudaEventDestroy(e);
+    rbsp.release(); subs.release(); equeue.release(); ctu_slice.release(); epics.release(); ipm4.release(); cd8.release(); wpp_ctx.release();
     end_state.release(); esync.release(); ecount.release();
     for (auto& e : ev) if (e) cudaEventDestroy(e);
     if (ev_fork) cudaEventDestroy(ev_fork);
@@ -166,8 +169,9 @@ static int run_device_pipeline(b200_decoder* d, int n, cudaStream_t s, int* laun
   b.qp8 = d->qp8.d; b.edge8 = d->edge8.d; b.ticket = d->sync.d; b.error_flag = d->sync.d + 1; b.progress = d->sync.d + 2; b.row_list = d->rows.d; b.nrows = (int)d->n_items; b.max_log2_ctb = d->max_log2_ctb; b.wide_samples = d->info_bps == 2;
   if (devfe) {
     EntropyBatch e{};
-    e.pics = d->epics.d; e.npics = d->npics; e.subs = d->subs.d; e.order = d->sub_order.d; e.nsubs = (int)d->n_subs;
-    e.ticket = d->esync.d; e.progress = d->esync.d + 1; e.sub_done = d->esync.d + 1 + d->n_rows; e.error_flag = d->sync.d + 1;
+    e.pics = d->epics.d; e.npics = d->npics; e.subs = d->subs.d; e.nsubs = (int)d->n_subs;
+    e.qhead = d->equeue.d; e.qtail = d->equeue.d + 1; e.queue = d->equeue.d + 2; e.deps = d->equeue.d + 2 + d->n_subs;
+    e.progress = d->esync.d + 1; e.sub_done = d->esync.d + 1 + d->n_rows; e.error_flag = d->sync.d + 1;
     if (overlap) {
       if (!d->side) { B200_CUDA_CHECK(cudaStreamCreateWithFlags(&d->side, cudaStreamNonBlocking)); B200_CUDA_CHECK(cudaEventCreate(&d->ev_fork)); B200_CUDA_CHECK(cudaEventCreate(&d->ev_join)); }
       e.blocks_per_sm = overlap_blocks("B200_OVERLAP_K0_BLOCKS", 3);
@@ -280,7 +284,7 @@ int b200_decoder_decode_grid(b200_decoder* d, int cols, int rows, const uint8_t*
       (rc = d->slices.reserve(n_slice)) || (rc = d->qp8.reserve(n_map, !devfe)) || (rc = d->edge8.reserve(n_map, !devfe)) || (rc = d->rows.reserve(2 * n_rows)) ||
       (rc = d->sync.reserve(2 * n_rows + 2, false)) || (rc = d->rec.reserve(rec_bytes, false)))
     return rc;
-  if (devfe && ((rc = d->rbsp.reserve(n_rbsp + 16)) || (rc = d->subs.reserve(n_subs)) || (rc = d->sub_order.reserve(n_subs)) || (rc = d->ctu_slice.reserve(n_ctu)) ||
+  if (devfe && ((rc = d->rbsp.reserve(n_rbsp + 16)) || (rc = d->subs.reserve(n_subs)) || (rc = d->equeue.reserve(2 + 2 * n_subs)) || (rc = d->ctu_slice.reserve(n_ctu)) ||
                 (rc = d->epics.reserve((size_t)n)) || (rc = d->ipm4.reserve(n_map4, false)) || (rc = d->cd8.reserve(n_map, false)) ||
                 (rc = d->wpp_ctx.reserve(n_rows * syn::CTX_STRIDE, false)) || (rc = d->end_state.reserve(n_subs * syn::CTX_STRIDE + 16, false)) ||
                 (rc = d->esync.reserve(1 + n_rows + n_subs, false)) || (rc = d->ecount.reserve(2, true))))
@@ -319,12 +323,6 @@ int b200_decoder_decode_grid(b200_decoder* d, int cols, int rows, const uint8_t*
       if (chroma) d->rows.h[row_cursor++] = make_uint2((unsigned)i, (unsigned)r | 0x80000000u);              // Cb + Cr
     }
     d->n_items = row_cursor; d->info_bps = bps; }
-  if (devfe) {
-    // sub-stream ticket order: k-th sub-stream of every picture, k = 0, 1, ... (same argument as for the rows)
-    size_t cur = 0, maxs = 0;
-    for (int i = 0; i < n; i++) maxs = std::max(maxs, d->parsed[(size_t)i].hdr.subs.size());
-    for (size_t k = 0; k < maxs; k++) for (int i = 0; i < n; i++) if (k < d->parsed[(size_t)i].hdr.subs.size()) d->sub_order.h[cur++] = make_uint2((unsigned)i, (unsigned)k);
-  }
   d->pool->parallel_for(n, [&](int i) {
     const ParsedPicture& pp = d->parsed[(size_t)i]; const PicDesc& p = pp.desc;
     if (!devfe) {
@@ -339,7 +337,21 @@ int b200_decoder_decode_grid(b200_decoder* d, int cols, int rows, const uint8_t*
       memcpy(d->slices.h + p.slice_base, H.slices.data(), H.slices.size() * sizeof(SliceInfo));
       memcpy(d->rbsp.h + rbsp_off[(size_t)i], H.rbsp.data(), H.rbsp.size());
       memcpy(d->ctu_slice.h + p.ctu_base, H.ctu_slice.data(), H.ctu_slice.size() * sizeof(uint16_t));
-      for (size_t k = 0; k < H.subs.size(); k++) { syn::Substream ss = H.subs[k]; ss.pic = (uint32_t)i; d->subs.h[sub_off[(size_t)i] + k] = ss; }
+      // Ready-queue links (batch-wide indices): which sub-stream each one releases, and how many events each waits for before
+      // its first bin -- the conditions of run_substream (b200_hevc_syntax.h): the contexts stored after the 2nd CTB of the
+      // row above (WPP, 9.3.2.2) and the end state of the slice segment it continues.
+      const size_t so = sub_off[(size_t)i];
+      for (size_t k = 0; k < H.subs.size(); k++) { syn::Substream ss = H.subs[k]; ss.pic = (uint32_t)i; ss.wake_ctb2 = ss.wake_end = -1; ss.deps = 0; d->subs.h[so + k] = ss; }
+      for (size_t k = 0; k < H.subs.size(); k++) {
+        syn::Substream& ss = d->subs.h[so + k];
+        if (ss.prev >= 0) { ss.deps++; d->subs.h[so + (size_t)ss.prev].wake_end = (int32_t)(so + k); }
+        const int wctb = H.desc.wctb, rx0 = (int)(ss.ctb_begin % (uint32_t)wctb), ry0 = (int)(ss.ctb_begin / (uint32_t)wctb);
+        if (H.sp.wpp && rx0 == 0 && (!ss.init_contexts || ss.prev >= 0) && ss.ctb_begin != ss.slice_addr_rs && ry0 > 0 && (1 << H.desc.log2_ctb) < H.desc.width &&
+            H.ctu_slice[(size_t)(ry0 - 1) * wctb + 1] == (uint16_t)ss.slice_idx) {
+          const uint32_t a = (uint32_t)(ry0 - 1) * (uint32_t)wctb + 1;
+          for (size_t j = 0; j < H.subs.size(); j++) if (H.subs[j].ctb_begin <= a && a < H.subs[j].ctb_end) { ss.deps++; d->subs.h[so + j].wake_ctb2 = (int32_t)(so + k); break; }
+        }
+      }
       EntropyPic ep{};
       ep.sp = H.sp; ep.sp.dense = 0;
       ep.pb.rbsp = d->rbsp.d + rbsp_off[(size_t)i]; ep.pb.rbsp_size = (uint32_t)H.rbsp.size();
@@ -351,6 +363,16 @@ int b200_decoder_decode_grid(b200_decoder* d, int cols, int rows, const uint8_t*
       d->epics.h[i] = ep;
     }
   });
+  if (devfe) {
+    // ready queue image: cursors, the sub-streams without prerequisites in "k-th sub-stream of every picture" order (so
+    // that whatever a popped sub-stream polls for was popped before it), empty slots, the dependency counters
+    unsigned* q = d->equeue.h; size_t cur = 0, maxs = 0;
+    for (int i = 0; i < n; i++) maxs = std::max(maxs, d->parsed[(size_t)i].hdr.subs.size());
+    for (size_t k = 0; k < maxs; k++) for (int i = 0; i < n; i++) if (k < d->parsed[(size_t)i].hdr.subs.size() && d->subs.h[sub_off[(size_t)i] + k].deps == 0) q[2 + cur++] = (unsigned)(sub_off[(size_t)i] + k) + 1u;
+    q[0] = 0; q[1] = (unsigned)cur;
+    for (size_t k = cur; k < n_subs; k++) q[2 + k] = 0;
+    for (size_t k = 0; k < n_subs; k++) q[2 + n_subs + k] = d->subs.h[k].deps;
+  }
   const double t2 = now_ms();
   // ---- 4. H2D + kernels
   cudaEventRecord(d->ev[0], s);
@@ -368,12 +390,12 @@ int b200_decoder_decode_grid(b200_decoder* d, int cols, int rows, const uint8_t*
   } else {
     B200_CUDA_CHECK(cudaMemcpyAsync(d->rbsp.d, d->rbsp.h, n_rbsp, cudaMemcpyHostToDevice, s));
     B200_CUDA_CHECK(cudaMemcpyAsync(d->subs.d, d->subs.h, n_subs * sizeof(syn::Substream), cudaMemcpyHostToDevice, s));
-    B200_CUDA_CHECK(cudaMemcpyAsync(d->sub_order.d, d->sub_order.h, n_subs * sizeof(uint2), cudaMemcpyHostToDevice, s));
+    B200_CUDA_CHECK(cudaMemcpyAsync(d->equeue.d, d->equeue.h, (2 + 2 * n_subs) * sizeof(unsigned), cudaMemcpyHostToDevice, s));
     B200_CUDA_CHECK(cudaMemcpyAsync(d->ctu_slice.d, d->ctu_slice.h, n_ctu * sizeof(uint16_t), cudaMemcpyHostToDevice, s));
     B200_CUDA_CHECK(cudaMemcpyAsync(d->epics.d, d->epics.h, (size_t)n * sizeof(EntropyPic), cudaMemcpyHostToDevice, s));
     B200_CUDA_CHECK(cudaMemsetAsync(d->esync.d, 0, (1 + n_rows + n_subs) * sizeof(unsigned), s));
     B200_CUDA_CHECK(cudaMemsetAsync(d->ecount.d, 0, 2 * sizeof(unsigned long long), s));
-    h2d += n_rbsp + n_subs * (sizeof(syn::Substream) + sizeof(uint2)) + n_ctu * sizeof(uint16_t) + (size_t)n * sizeof(EntropyPic);
+    h2d += n_rbsp + n_subs * (sizeof(syn::Substream) + 2 * sizeof(unsigned)) + n_ctu * sizeof(uint16_t) + (size_t)n * sizeof(EntropyPic);
   }
   B200_CUDA_CHECK(cudaMemsetAsync(d->sync.d, 0, (2 * n_rows + 2) * sizeof(unsigned), s));
   if (!canvas_fully_covered) B200_CUDA_CHECK(cudaMemsetAsync(d->canvas.d, 0, cbytes, s));     // uncovered canvas stays zero (calloc in the reference)
@@ -407,6 +429,7 @@ int b200_decoder_rerun_device(b200_decoder* d, void* stream_) {
   if (d->used_device_front_end) {
     B200_CUDA_CHECK(cudaMemsetAsync(d->esync.d, 0, (1 + d->n_rows + d->n_subs) * sizeof(unsigned), s));
     B200_CUDA_CHECK(cudaMemsetAsync(d->ecount.d, 0, 2 * sizeof(unsigned long long), s));
+    B200_CUDA_CHECK(cudaMemcpyAsync(d->equeue.d, d->equeue.h, (2 + 2 * d->n_subs) * sizeof(unsigned), cudaMemcpyHostToDevice, s));
   }
   int launches = 0;
   int rc = run_device_pipeline(d, d->npics, s, &launches);
@@ -476,8 +499,10 @@ int b200_decode_grid_to_rgb_host(b200_decoder* d, int cols, int rows, const uint
                                  uint64_t max_pixels, int canvas_w, int canvas_h, const b200_geometry* geom,
                                  const b200_color_options* opt, void* out, size_t out_stride, b200_image_info* info) {
   if (!d || !opt || !out) return set_error(B200_E_INVALID, "null argument");
+  if (!d->own) B200_CUDA_CHECK(cudaStreamCreateWithFlags(&d->own, cudaStreamNonBlocking));
+  cudaStream_t s = d->own;
   b200_image_info inf;
-  int rc = b200_decoder_decode_grid(d, cols, rows, au, au_size, max_pixels, canvas_w, canvas_h, &inf, nullptr);
+  int rc = b200_decoder_decode_grid(d, cols, rows, au, au_size, max_pixels, canvas_w, canvas_h, &inf, s);
   if (rc) return rc;
   if (info) *info = inf;
   b200_planes pl; if ((rc = b200_decoder_get_planes(d, &pl))) return rc;
@@ -490,12 +515,59 @@ int b200_decode_grid_to_rgb_host(b200_decoder* d, int cols, int rows, const uint
     default: return set_error(B200_E_UNSUPPORTED, "b200_decode_grid_to_rgb_host needs an interleaved target");
   }
   const size_t rowb = (size_t)g.out_w * bpp, pitch = (rowb + 255) & ~(size_t)255;
-  static thread_local DevBuf<uint8_t> rgb;
-  if ((rc = rgb.reserve(pitch * g.out_h, false))) return rc;
-  if ((rc = b200_color_convert_device(&pl, &g, opt, rgb.d, nullptr, nullptr, pitch, nullptr, nullptr))) return rc;
-  B200_CUDA_CHECK(cudaMemcpy2D(out, out_stride, rgb.d, pitch, rowb, g.out_h, cudaMemcpyDeviceToHost));
+  if ((rc = d->rgb.reserve(pitch * g.out_h, false))) return rc;
+  if ((rc = b200_color_convert_device(&pl, &g, opt, d->rgb.d, nullptr, nullptr, pitch, s, nullptr))) return rc;
+  // D2H: straight into the caller's buffer when it is page-locked (b200_host_alloc, cudaHostAlloc, cudaHostRegister);
+  // pageable memory goes through a page-locked bounce buffer in row bands, the copy of band i overlapping the memcpy of
+  // band i - 1 on the decoder's host threads
+  cudaPointerAttributes pa{};
+  const bool pinned = cudaPointerGetAttributes(&pa, out) == cudaSuccess && (pa.type == cudaMemoryTypeHost || pa.type == cudaMemoryTypeManaged);
+  cudaGetLastError();
+  if (pinned) {
+    B200_CUDA_CHECK(cudaMemcpy2DAsync(out, out_stride, d->rgb.d, pitch, rowb, (size_t)g.out_h, cudaMemcpyDeviceToHost, s));
+    B200_CUDA_CHECK(cudaStreamSynchronize(s));
+  } else {
+    const size_t band_rows = std::max<size_t>(1, (size_t)(32u << 20) / rowb);
+    const int nb = (int)(((size_t)g.out_h + band_rows - 1) / band_rows);
+    if ((rc = d->bounce.reserve(2 * band_rows * rowb, true))) return rc;
+    for (auto& e : d->ev_band) if (!e) B200_CUDA_CHECK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    for (int k = 0; k <= nb; k++) {
+      if (k < nb) {
+        const size_t y0 = (size_t)k * band_rows, h = std::min(band_rows, (size_t)g.out_h - y0);
+        B200_CUDA_CHECK(cudaMemcpy2DAsync(d->bounce.h + (size_t)(k & 1) * band_rows * rowb, rowb, d->rgb.d + y0 * pitch, pitch, rowb, h, cudaMemcpyDeviceToHost, s));
+        B200_CUDA_CHECK(cudaEventRecord(d->ev_band[k & 1], s));
+      }
+      if (k > 0) {
+        const int j = k - 1;
+        const size_t y0 = (size_t)j * band_rows, h = std::min(band_rows, (size_t)g.out_h - y0);
+        B200_CUDA_CHECK(cudaEventSynchronize(d->ev_band[j & 1]));
+        const uint8_t* src = d->bounce.h + (size_t)(j & 1) * band_rows * rowb;
+        const int parts = 8;
+        d->pool->parallel_for(parts, [&](int t) {
+          const size_t r0 = h * (size_t)t / parts, r1 = h * (size_t)(t + 1) / parts;
+          for (size_t y = r0; y < r1; y++) memcpy(static_cast<uint8_t*>(out) + (y0 + y) * out_stride, src + y * rowb, rowb);
+        });
+      }
+    }
+    B200_CUDA_CHECK(cudaStreamSynchronize(s));
+  }
   return check_device_error(d);
 }
+
+// Page-locked host memory for the outputs of b200_decode_grid_to_rgb_host / b200_decoder_read_planes (DMA target).
+int b200_host_alloc(size_t bytes, void** out) {
+  if (!out) return set_error(B200_E_INVALID, "null argument");
+  B200_CUDA_CHECK(cudaHostAlloc(out, bytes, cudaHostAllocDefault));
+  return B200_OK;
+}
+void b200_host_free(void* p) { if (p) cudaFreeHost(p); }
+// Page-lock memory the caller already owns (e.g. a shared-memory mapping several processes write their bands into).
+int b200_host_register(void* p, size_t bytes) {
+  if (!p) return set_error(B200_E_INVALID, "null argument");
+  B200_CUDA_CHECK(cudaHostRegister(p, bytes, cudaHostRegisterPortable));
+  return B200_OK;
+}
+int b200_host_unregister(void* p) { if (p) B200_CUDA_CHECK(cudaHostUnregister(p)); return B200_OK; }
 
 }  // extern "C"
 

@@ -5,8 +5,11 @@
 // b200_hevc_syntax.h, the same source the host front-end uses).  With entropy_coding_sync every CTB row is its own
 // sub-stream, located by the slice header's entry points, so a 16384x16384 grid of 1024x1024 tiles exposes 8192
 // independent-ish streams: rows of one picture advance as a wavefront (context hand-over after the 2nd CTB of the row
-// above, 9.3.2.2), pictures are independent.  Sub-streams are handed out by a global ticket in "k-th sub-stream of every
-// picture" order, so a dependency always holds a smaller ticket (no deadlock, no co-residency requirement).
+// above, 9.3.2.2), pictures are independent.  Sub-streams are handed out through a READY QUEUE: a sub-stream enters it when
+// the events it has to wait for before its first bin have happened (context hand-over stored by the row above; end of the
+// slice segment it continues) -- the warp that causes the last such event pushes it.  A resident warp therefore never sits
+// on a sub-stream that cannot start (18 % of all warp time with static tickets), and whatever is popped only ever waits for
+// sub-streams popped before it (no deadlock, no co-residency requirement).
 // Output: the command stream of b200_hevc_types.h, written into fixed per-CTB slots in HBM (worst-case sized; only the
 // used entries are ever touched).  Why on the GPU: the host has 16 usable cores on the target box and CABAC is the
 // end-to-end bottleneck there; the arithmetic decoder is serial per sub-stream but there are thousands of sub-streams.
@@ -53,21 +56,20 @@ struct DevSync {
   unsigned* progress;      // per CTB row of this picture
   unsigned* sub_done;      // per sub-stream of this picture
   unsigned* error_flag;
+  unsigned* queue; unsigned* qtail; unsigned* deps;               // batch-wide ready queue (see the kernel)
   uint32_t dense_tu, dense_coef, dense_tu_cap, dense_coef_cap;   // unused on the device (fixed slots)
   uint64_t end_bit_position;
-  // A CTB takes ~0.5 ms: back off to microseconds so thousands of waiting warps do not flood L2 with polls.  Gives up
-  // (error 3) after 60 s of wall time -- only a lost producer can cause that.
+  // Waits inside a sub-stream are short (the row above runs two CTBs ahead): poll with a sub-microsecond back-off.  Gives
+  // up (error 3) after ~60 s -- only a lost producer can cause that.
   __device__ static void spin_until(const unsigned* p, unsigned need, unsigned* error_flag) {
     if (e_ld_acquire(p) >= need) return;
-    unsigned long long t0; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
-    unsigned ns = 500, spins = 0;
+    unsigned ns = 200, spins = 0;
     for (;;) {
-      __nanosleep(ns); if (ns < 16000) ns <<= 1;
+      __nanosleep(ns); if (ns < 8000) ns <<= 1;
       if (e_ld_acquire(p) >= need) return;
-      if ((++spins & 31u) != 0) continue;
+      if ((++spins & 63u) != 0) continue;
       if (e_ld_acquire(error_flag)) return;              // a producer failed: do not wait for progress that will never come
-      unsigned long long t1; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
-      if (t1 - t0 > 60000000000ull) { atomicExch(error_flag, 3u); return; }
+      if (spins > (1u << 23)) { atomicExch(error_flag, 3u); return; }
     }
   }
   __device__ void wait_row(int row, int need) { spin_until(progress + row, (unsigned)need, error_flag); }
@@ -77,13 +79,19 @@ struct DevSync {
     e_st_release(sub_done + idx, 1u);
     if (err) atomicExch(error_flag, (unsigned)err);
   }
+  // One of the events sub-stream `target` (batch-wide index) waits for has happened; the last one makes it ready.
+  __device__ void notify(int target) {
+    if (target < 0) return;
+    __threadfence();                                     // what the target will read (contexts, end state) is published first
+    if (atomicSub(deps + target, 1u) == 1u) { const unsigned s = atomicAdd(qtail, 1u); e_st_release(queue + s, (unsigned)target + 1u); }
+  }
 };
 
 #ifndef B200_ENTROPY_MIN_BLOCKS
 #define B200_ENTROPY_MIN_BLOCKS 1
 #endif
 __global__ void __launch_bounds__(EWARPS * 32, B200_ENTROPY_MIN_BLOCKS) hevc_entropy_kernel(const EntropyBatch b) {
-  __shared__ uint8_t s_ctx[EWARPS][syn::CTX_STRIDE];
+  __shared__ __align__(8) syn::U2 s_ctx[EWARPS][syn::CTX_COUNT];   // context variables: one state-table entry each
   __shared__ syn::Decoder s_dec[EWARPS];                    // per-warp decoder state (see run_substream)
   for (int i = threadIdx.x; i < 64; i += blockDim.x) { syn::s_kLps4[i] = syn::d_kLps4[i]; syn::s_kTransLps[i] = syn::d_kTransLps[i]; }
   for (int i = threadIdx.x; i < 134; i += blockDim.x) syn::s_kInitI[i] = syn::d_kInitI[i];
@@ -99,17 +107,30 @@ __global__ void __launch_bounds__(EWARPS * 32, B200_ENTROPY_MIN_BLOCKS) hevc_ent
   // Lane 0 of every warp decodes: CABAC is serial per sub-stream.  (Several decoders per warp on diverged lanes were
   // measured 25-70 % slower: the diverged paths of one warp serialise.)
   if ((threadIdx.x & 31) != 0) return;
-  const int slot = threadIdx.x >> 5;
-  const syn::CtxPtr ctx = (syn::CtxPtr)__cvta_generic_to_shared(s_ctx[slot]);
+  const int slot_w = threadIdx.x >> 5;
+  const syn::CtxPtr ctx = (syn::CtxPtr)__cvta_generic_to_shared(s_ctx[slot_w]);
   for (;;) {
-    const unsigned t = atomicAdd(b.ticket, 1u);
-    if (t >= (unsigned)b.nsubs) break;
-    const uint2 ref = b.order[t];                            // (picture, local sub-stream index)
-    const EntropyPic& ep = b.pics[ref.x];
+    const unsigned slot = atomicAdd(b.qhead, 1u);
+    if (slot >= (unsigned)b.nsubs) break;
+    // the slot is filled when the sub-stream becomes ready (already, for those without prerequisites)
+    unsigned item = e_ld_acquire(b.queue + slot);
+    if (!item) {
+      unsigned ns = 500, spins = 0;
+      for (;;) {
+        __nanosleep(ns); if (ns < 16000) ns <<= 1;
+        if ((item = e_ld_acquire(b.queue + slot)) != 0u) break;
+        if ((++spins & 31u) != 0) continue;
+        if (e_ld_acquire(b.error_flag)) return;          // a producer failed: its dependants never become ready
+        if (spins > (1u << 22)) { atomicExch(b.error_flag, 3u); return; }
+      }
+    }
+    const syn::Substream& gs = b.subs[item - 1u];
+    const EntropyPic& ep = b.pics[gs.pic];
     DevSync sync;
     sync.progress = b.progress + ep.progress_base; sync.sub_done = b.sub_done + ep.sub_base; sync.error_flag = b.error_flag;
+    sync.queue = b.queue; sync.qtail = b.qtail; sync.deps = b.deps;
     sync.dense_tu = sync.dense_coef = sync.dense_tu_cap = sync.dense_coef_cap = 0; sync.end_bit_position = 0;
-    syn::run_substream(s_dec[slot], ep.sp, ep.pb, b.subs + ep.sub_base, (int)ref.y, ctx, sync);
+    syn::run_substream(s_dec[slot_w], ep.sp, ep.pb, b.subs + ep.sub_base, (int)(item - 1u - ep.sub_base), ctx, sync);
   }
 }
 

@@ -353,6 +353,7 @@ class HeaderParser {
       ss.slice_addr_rs = (uint32_t)slice_addr_rs; ss.slice_idx = slice_idx; ss.slice_qp = slice_qp; ss.sao_luma = (uint8_t)sao_luma; ss.sao_chroma = (uint8_t)sao_chroma;
       ss.init_contexts = (uint8_t)(first_sub && !dependent); ss.last_of_segment = 0;
       ss.prev = (first_sub && dependent) ? last_seg_sub : -1;
+      ss.wake_ctb2 = ss.wake_end = -1; ss.deps = 0;
       P.subs.push_back(ss); sg.nsubs++;
     };
     if (p->wpp) {
@@ -422,6 +423,7 @@ struct HostSync {      // sequential execution: every dependency is already sati
   B200_HD void publish_row(int, int) {}
   B200_HD void wait_substream(int) {}
   B200_HD void finish_substream(int, int e) { if (e && !err) err = e; }
+  B200_HD void notify(int) {}
 };
 
 }  // namespace
@@ -457,7 +459,7 @@ int parse_access_unit(const uint8_t* data, size_t size, const ParseLimits& limit
   pb.wpp_ctx = out.wpp_ctx.data(); pb.end_state = out.end_state.data();
   for (size_t a = 0; a < nctb; a++) out.ctus[a].slice_idx = H.ctu_slice[a];
   HostSync sync; sync.dense_tu_cap = (uint32_t)tu_cap; sync.dense_coef_cap = (uint32_t)coef_cap;
-  uint8_t ctx[syn::CTX_STRIDE];
+  syn::U2 ctx[syn::CTX_COUNT];
   for (size_t i = 0; i < H.subs.size(); i++) {
     syn::Decoder dec;
     int e = syn::run_substream(dec, sp, pb, H.subs.data(), (int)i, ctx, sync);

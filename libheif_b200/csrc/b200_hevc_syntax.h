@@ -49,20 +49,25 @@ namespace syn {
 #ifdef B200_SYN_DEVICE
 typedef uint32_t CtxPtr;
 typedef uint32_t TabPtr;
-__device__ __forceinline__ uint32_t ctx_ld(CtxPtr p) { uint32_t v; asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(p) : "memory"); return v; }
-__device__ __forceinline__ void ctx_st(CtxPtr p, uint32_t v) { asm volatile("st.shared.u8 [%0], %1;" ::"r"(p), "r"(v) : "memory"); }
+struct U2 { uint32_t x, y; };
+// No "memory" clobbers: the context array is only ever touched through these handles, and asm volatile statements keep
+// their program order among themselves (loads of one context never pass stores to it).
+__device__ __forceinline__ U2 ctx_ld(CtxPtr p) { U2 v; asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(p)); return v; }
+__device__ __forceinline__ void ctx_st(CtxPtr p, U2 v) { asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(p), "r"(v.x), "r"(v.y)); }
+__device__ __forceinline__ CtxPtr ctx_at(CtxPtr base, int i) { return base + 8u * (uint32_t)i; }
 __device__ __forceinline__ uint32_t tab_ld8(TabPtr p, int i) { uint32_t v; asm("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(p + (uint32_t)i)); return v; }
-__device__ __forceinline__ uint2 tab_ld64(TabPtr p, int i) { uint2 v; asm("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(p + 8u * (uint32_t)i)); return v; }
+__device__ __forceinline__ U2 tab_ld64(TabPtr p, int i) { U2 v; asm("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(p + 8u * (uint32_t)i)); return v; }
 __device__ __forceinline__ uint32_t tab_ld32(TabPtr p, int i) { uint32_t v; asm("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(p + 4u * (uint32_t)i)); return v; }
 #define B200_TADDR(name) ((::b200::syn::TabPtr)__cvta_generic_to_shared(&B200_T(name)))
 #else
-typedef uint8_t* CtxPtr;
+struct U2 { uint32_t x, y; };
+typedef U2* CtxPtr;
 typedef const uint8_t* TabPtr;
-inline uint32_t ctx_ld(CtxPtr p) { return *p; }
-inline void ctx_st(CtxPtr p, uint32_t v) { *p = (uint8_t)v; }
+inline U2 ctx_ld(CtxPtr p) { return *p; }
+inline void ctx_st(CtxPtr p, U2 v) { *p = v; }
+inline CtxPtr ctx_at(CtxPtr base, int i) { return base + i; }
 inline uint32_t tab_ld8(TabPtr p, int i) { return p[i]; }
 inline uint32_t tab_ld32(TabPtr p, int i) { uint32_t v; memcpy(&v, p + 4 * (size_t)i, 4); return v; }
-struct U2 { uint32_t x, y; };
 inline U2 tab_ld64(TabPtr p, int i) { uint64_t v; memcpy(&v, p + 8 * (size_t)i, 8); return U2{(uint32_t)v, (uint32_t)(v >> 32)}; }
 #define B200_TADDR(name) (reinterpret_cast<::b200::syn::TabPtr>(&B200_T(name)))
 #endif
@@ -133,6 +138,10 @@ struct Substream {
   uint8_t init_contexts;         // 1: first sub-stream of an independent slice segment
   uint8_t last_of_segment;       // 1: end_of_slice_segment_flag must be 1 at ctb_end - 1
   int32_t prev;                  // sub-stream whose end state this one continues (dependent slice segment), else -1
+  // Ready-queue scheduling of the device front-end (filled by the decoder object, batch-wide sub-stream indices, -1 = none):
+  int32_t wake_ctb2;             // sub-stream that becomes startable once this one has stored the contexts after its 2nd CTB of a row (9.3.2.2)
+  int32_t wake_end;              // sub-stream that continues this one's end state (dependent slice segment)
+  uint32_t deps;                 // number of such events this sub-stream waits for before it may start
 };
 
 struct PicBuffers {              // per-picture arrays (host memory on the host path, HBM on the device path)
@@ -155,8 +164,9 @@ struct PicBuffers {              // per-picture arrays (host memory on the host 
 B200_TABLE(uint8_t, kNextState, [256], {2,3,4,5,6,7,8,9,10,11,12,13,14,15,16,17,18,19,20,21,22,23,24,25,26,27,28,29,30,31,32,33,34,35,36,37,38,39,40,41,42,43,44,45,46,47,48,49,50,51,52,53,54,55,56,57,58,59,60,61,62,63,64,65,66,67,68,69,70,71,72,73,74,75,76,77,78,79,80,81,82,83,84,85,86,87,88,89,90,91,92,93,94,95,96,97,98,99,100,101,102,103,104,105,106,107,108,109,110,111,112,113,114,115,116,117,118,119,120,121,122,123,124,125,124,125,126,127,1,0,0,1,2,3,4,5,4,5,8,9,8,9,10,11,12,13,14,15,16,17,18,19,18,19,22,23,22,23,24,25,26,27,26,27,30,31,30,31,32,33,32,33,36,37,36,37,38,39,38,39,42,43,42,43,44,45,44,45,46,47,48,49,48,49,50,51,52,53,52,53,54,55,54,55,56,57,58,59,58,59,60,61,60,61,60,61,62,63,64,65,64,65,66,67,66,67,66,67,68,69,68,69,70,71,70,71,70,71,72,73,72,73,72,73,74,75,74,75,74,75,76,77,76,77,126,127})   // [ctx byte | lps << 7] -> next ctx byte ((pStateIdx << 1) | valMps)
 
 // Both tables fused, one 64-bit entry per context byte (pStateIdx << 1 | valMps): bits 0-31 rangeTabLps[0..3], 32-39 next
-// context byte after an MPS, 40-47 after an LPS -- one shared-memory load per bin instead of two dependent ones.
-B200_TABLE(uint64_t, kState, [128], {0x0102f0d0b080ull,0x0003f0d0b080ull,0x0004e3c5a780ull,0x0105e3c5a780ull,0x0206d8bb9e80ull,0x0307d8bb9e80ull,0x0408cdb2967bull,0x0509cdb2967bull,0x040ac3a98e74ull,0x050bc3a98e74ull,0x080cb9a0876full,0x090db9a0876full,0x080eaf988069ull,0x090faf988069ull,0x0a10a6907a64ull,0x0b11a6907a64ull,0x0c129e89745full,0x0d139e89745full,0x0e1496826e5aull,0x0f1596826e5aull,0x10168e7b6855ull,0x11178e7b6855ull,0x121887756351ull,0x131987756351ull,0x121a806f5e4dull,0x131b806f5e4dull,0x161c7a695949ull,0x171d7a695949ull,0x161e74645545ull,0x171f74645545ull,0x18206e5f5042ull,0x19216e5f5042ull,0x1a22685a4c3eull,0x1b23685a4c3eull,0x1a246356483bull,0x1b256356483bull,0x1e265e514538ull,0x1f275e514538ull,0x1e28594d4135ull,0x1f29594d4135ull,0x202a55493e33ull,0x212b55493e33ull,0x202c50453b30ull,0x212d50453b30ull,0x242e4c42382eull,0x252f4c42382eull,0x2430483f352bull,0x2531483f352bull,0x2632453b3229ull,0x2733453b3229ull,0x263441383027ull,0x273541383027ull,0x2a363e362d25ull,0x2b373e362d25ull,0x2a383b332b23ull,0x2b393b332b23ull,0x2c3a38302921ull,0x2d3b38302921ull,0x2c3c352e2720ull,0x2d3d352e2720ull,0x2e3e322b251eull,0x2f3f322b251eull,0x30403029231dull,0x31413029231dull,0x30422d27211bull,0x31432d27211bull,0x32442b251f1aull,0x33452b251f1aull,0x344629231e18ull,0x354729231e18ull,0x344827211c17ull,0x354927211c17ull,0x364a25201b16ull,0x374b25201b16ull,0x364c231e1a15ull,0x374d231e1a15ull,0x384e211d1814ull,0x394f211d1814ull,0x3a501f1b1713ull,0x3b511f1b1713ull,0x3a521e1a1612ull,0x3b531e1a1612ull,0x3c541c191511ull,0x3d551c191511ull,0x3c561b171410ull,0x3d571b171410ull,0x3c581916130full,0x3d591916130full,0x3e5a1815120eull,0x3f5b1815120eull,0x405c1714110eull,0x415d1714110eull,0x405e1613100dull,0x415f1613100dull,0x426015120f0cull,0x436115120f0cull,0x426214110e0cull,0x436314110e0cull,0x426413100e0bull,0x436513100e0bull,0x4466120f0d0bull,0x4567120f0d0bull,0x4468110f0c0aull,0x4569110f0c0aull,0x466a100e0c0aull,0x476b100e0c0aull,0x466c0f0d0b09ull,0x476d0f0d0b09ull,0x466e0e0c0b09ull,0x476f0e0c0b09ull,0x48700e0c0a08ull,0x49710e0c0a08ull,0x48720d0b0908ull,0x49730d0b0908ull,0x48740c0b0907ull,0x49750c0b0907ull,0x4a760c0a0907ull,0x4b770c0a0907ull,0x4a780b0a0807ull,0x4b790b0a0807ull,0x4a7a0b090806ull,0x4b7b0b090806ull,0x4c7c0a090706ull,0x4d7d0a090706ull,0x4c7c09080706ull,0x4d7d09080706ull,0x7e7e02020202ull,0x7f7f02020202ull})
+// context byte after an MPS, 40-47 after an LPS, 56-62 the context byte itself.  A context variable HOLDS its entry (8 bytes),
+// so a bin costs one shared-memory load on the dependency chain; the entry of the next state is fetched off the chain.
+B200_TABLE(uint64_t, kState, [128], {0x00000102f0d0b080ull,0x01000003f0d0b080ull,0x02000004e3c5a780ull,0x03000105e3c5a780ull,0x04000206d8bb9e80ull,0x05000307d8bb9e80ull,0x06000408cdb2967bull,0x07000509cdb2967bull,0x0800040ac3a98e74ull,0x0900050bc3a98e74ull,0x0a00080cb9a0876full,0x0b00090db9a0876full,0x0c00080eaf988069ull,0x0d00090faf988069ull,0x0e000a10a6907a64ull,0x0f000b11a6907a64ull,0x10000c129e89745full,0x11000d139e89745full,0x12000e1496826e5aull,0x13000f1596826e5aull,0x140010168e7b6855ull,0x150011178e7b6855ull,0x1600121887756351ull,0x1700131987756351ull,0x1800121a806f5e4dull,0x1900131b806f5e4dull,0x1a00161c7a695949ull,0x1b00171d7a695949ull,0x1c00161e74645545ull,0x1d00171f74645545ull,0x1e0018206e5f5042ull,0x1f0019216e5f5042ull,0x20001a22685a4c3eull,0x21001b23685a4c3eull,0x22001a246356483bull,0x23001b256356483bull,0x24001e265e514538ull,0x25001f275e514538ull,0x26001e28594d4135ull,0x27001f29594d4135ull,0x2800202a55493e33ull,0x2900212b55493e33ull,0x2a00202c50453b30ull,0x2b00212d50453b30ull,0x2c00242e4c42382eull,0x2d00252f4c42382eull,0x2e002430483f352bull,0x2f002531483f352bull,0x30002632453b3229ull,0x31002733453b3229ull,0x3200263441383027ull,0x3300273541383027ull,0x34002a363e362d25ull,0x35002b373e362d25ull,0x36002a383b332b23ull,0x37002b393b332b23ull,0x38002c3a38302921ull,0x39002d3b38302921ull,0x3a002c3c352e2720ull,0x3b002d3d352e2720ull,0x3c002e3e322b251eull,0x3d002f3f322b251eull,0x3e0030403029231dull,0x3f0031413029231dull,0x400030422d27211bull,0x410031432d27211bull,0x420032442b251f1aull,0x430033452b251f1aull,0x4400344629231e18ull,0x4500354729231e18ull,0x4600344827211c17ull,0x4700354927211c17ull,0x4800364a25201b16ull,0x4900374b25201b16ull,0x4a00364c231e1a15ull,0x4b00374d231e1a15ull,0x4c00384e211d1814ull,0x4d00394f211d1814ull,0x4e003a501f1b1713ull,0x4f003b511f1b1713ull,0x50003a521e1a1612ull,0x51003b531e1a1612ull,0x52003c541c191511ull,0x53003d551c191511ull,0x54003c561b171410ull,0x55003d571b171410ull,0x56003c581916130full,0x57003d591916130full,0x58003e5a1815120eull,0x59003f5b1815120eull,0x5a00405c1714110eull,0x5b00415d1714110eull,0x5c00405e1613100dull,0x5d00415f1613100dull,0x5e00426015120f0cull,0x5f00436115120f0cull,0x6000426214110e0cull,0x6100436314110e0cull,0x6200426413100e0bull,0x6300436513100e0bull,0x64004466120f0d0bull,0x65004567120f0d0bull,0x66004468110f0c0aull,0x67004569110f0c0aull,0x6800466a100e0c0aull,0x6900476b100e0c0aull,0x6a00466c0f0d0b09ull,0x6b00476d0f0d0b09ull,0x6c00466e0e0c0b09ull,0x6d00476f0e0c0b09ull,0x6e0048700e0c0a08ull,0x6f0049710e0c0a08ull,0x700048720d0b0908ull,0x710049730d0b0908ull,0x720048740c0b0907ull,0x730049750c0b0907ull,0x74004a760c0a0907ull,0x75004b770c0a0907ull,0x76004a780b0a0807ull,0x77004b790b0a0807ull,0x78004a7a0b090806ull,0x79004b7b0b090806ull,0x7a004c7c0a090706ull,0x7b004d7d0a090706ull,0x7c004c7c09080706ull,0x7d004d7d09080706ull,0x7e007e7e02020202ull,0x7f007f7f02020202ull})
 
 // The sub-stream's bytes (cold: touched once per 16 consumed bits).
 struct CabacStream { const uint8_t* d; uint32_t size; };
@@ -191,24 +201,25 @@ struct Cabac {
   }
   B200_HD inline uint64_t bit_position() const { return (uint64_t)pos * 8 - (uint32_t)bits; }
   // shift the window left by n (n <= 7), merging the prefetched 16 bits when the look-ahead is exhausted
-  B200_HDN static uint32_t refill16(const CabacStream& st, uint32_t p) { return fetch16(st, p); }   // out of line: keeps the 1-in-12 refill a branch, not predicated code in every bin
+  // (inline: a call here costs a convergence barrier and argument set-up at every one of the ~15 sites it is inlined into)
   B200_HD inline void shift(int n, const CabacStream& st) {
     val <<= n; bits -= n;
-    if (bits < 0) { val |= next16 << (-bits); bits += 16; pos += 2; next16 = refill16(st, pos); }
+    if (bits < 0) { val |= next16 << (-bits); bits += 16; pos += 2; next16 = fetch16(st, pos); }
   }
-  B200_HD inline int bin(CtxPtr c, const CabacStream& st) {
-    const uint32_t cv = ctx_ld(c);
-    const auto e = tab_ld64(state_tab, (int)cv);
+  // One context-coded bin with the context's entry `e` already in registers; `ne` returns the entry written back (the
+  // caller forwards it when the next bin uses the same context and was fetched before this store).
+  B200_HD inline int bin_e(const U2 e, CtxPtr c, const CabacStream& st, U2& ne) {
 #ifdef B200_SYN_DEVICE
-    const uint32_t rlps = __byte_perm(0u, e.x, range >> 6);          // range in [256, 510]: selector 4..7 = byte (range >> 6) & 3 of e.x
+    uint32_t rlps; asm("prmt.b32 %0, 0, %1, %2;" : "=r"(rlps) : "r"(e.x), "r"(range >> 6));   // range in [256, 510]: selector 4..7 = byte (range >> 6) & 3 of e.x
 #else
     const uint32_t rlps = (e.x >> (((range >> 6) & 3) * 8)) & 0xff;
 #endif
-    const uint32_t rmps = range - rlps;
-    const uint32_t lps = (val >> 16) >= rmps ? 1u : 0u;
-    val -= lps ? (rmps << 16) : 0u;
+    const uint32_t rmps = range - rlps, t = rmps << 16;
+    const bool lps = val >= t;
+    if (lps) val -= t;
     range = lps ? rlps : rmps;
-    ctx_st(c, lps ? e.y >> 8 : e.y);                                  // the store keeps the low byte
+    ne = tab_ld64(state_tab, (int)((lps ? e.y >> 8 : e.y) & 0xffu));
+    ctx_st(c, ne);
 #ifdef B200_SYN_DEVICE
     const int n = __clz((int)range) - 23;
 #else
@@ -216,8 +227,9 @@ struct Cabac {
 #endif
     range <<= n;
     shift(n, st);
-    return (int)((cv ^ lps) & 1u);
+    return (int)(((e.y >> 24) ^ (lps ? 1u : 0u)) & 1u);
   }
+  B200_HD inline int bin(CtxPtr c, const CabacStream& st) { U2 ne; return bin_e(ctx_ld(c), c, st, ne); }
   B200_HD inline int bypass(const CabacStream& st) {
     shift(1, st);
     const uint32_t one = (val >> 16) >= range ? 1u : 0u;
@@ -258,7 +270,7 @@ B200_HDN inline void init_contexts(CtxPtr ctx, int slice_qp) {          // 9.3.2
     const int iv = B200_T(kInitI)[i], m = (iv >> 4) * 5 - 45, nn = ((iv & 15) << 3) - 16;
     const int pre = clip3(1, 126, ((m * qp) >> 4) + nn);
     const int mps = pre > 63, st = mps ? pre - 64 : 63 - pre;
-    ctx_st(ctx + i, (uint32_t)((st << 1) | mps));
+    ctx_st(ctx_at(ctx, i), tab_ld64(B200_TADDR(kState), (st << 1) | mps));
   }
 }
 
@@ -286,7 +298,7 @@ struct Decoder {
 
   // Out-of-line arithmetic-decoder primitives for everything outside residual_coding (which keeps its own register
   // copy of the decoder): a call instead of ~35 inlined instructions per syntax element keeps the hot code small.
-  B200_HDN int dbin(int ci) { return cabac.bin(ctx + ci, stream); }
+  B200_HDN int dbin(int ci) { return cabac.bin(ctx_at(ctx, ci), stream); }
   B200_HDN int dbypass() { return cabac.bypass(stream); }
   B200_HDN unsigned dbits(int k) { return cabac.bypass_bits(k, stream); }
 
@@ -335,24 +347,33 @@ struct Decoder {
   }
 
   // -------- residual_coding (7.3.8.11): emits sparse (pos, level) entries; returns the number of coefficients
-  B200_HDI int residual(int log2n, int c, int mode, int& tskip) {
+  B200_HDN int residual(int log2n, int c, int mode, int& tskip) {
     const int n = 1 << log2n;
-    // Local copies: their addresses never escape, so they live in registers and need no reload after the byte stores
-    // into the context array (uint8_t stores may alias any member otherwise).
+    // Local copies: their addresses never escape, so they live in registers.
     Cabac cb_ = cabac; const CtxPtr cx = ctx;
     const int sign_hiding = sp->sign_hiding;
     CoefEntry* const coef_out = pb.coefs; uint32_t cn = coef_n; const uint32_t ccap = coef_cap;
     tskip = 0;
-    if (sp->transform_skip && log2n == 2) tskip = cb_.bin(cx + (CTX_TSKIP + (c ? 1 : 0)), stream);
+    if (sp->transform_skip && log2n == 2) tskip = cb_.bin(ctx_at(cx, CTX_TSKIP + (c ? 1 : 0)), stream);
     const int cmax = (log2n << 1) - 1;
     int off, shift;
     if (c == 0) { off = 3 * (log2n - 2) + ((log2n - 1) >> 2); shift = (log2n + 1) >> 2; } else { off = 15; shift = log2n - 2; }
     int lx = 0, ly = 0;
-    // last_sig_coeff_{x,y}_prefix then the two suffixes (7.3.8.11 order); one loop body serves both coordinates
+    // last_sig_coeff_{x,y}_prefix then the two suffixes (7.3.8.11 order); one loop body serves both coordinates.  The entry
+    // of the context the NEXT bin would use is fetched before the current bin is decoded (it is needed only if that bin is
+    // 1); when it is the same context, the freshly written entry is forwarded in registers.
     B200_NOUNROLL for (int xy = 0; xy < 2; xy++) {
-      const CtxPtr lc = cx + ((xy ? CTX_LAST_Y : CTX_LAST_X) + off);
+      const CtxPtr lc = ctx_at(cx, (xy ? CTX_LAST_Y : CTX_LAST_X) + off);
       int l = 0;
-      B200_NOUNROLL while (l < cmax && cb_.bin(lc + (l >> shift), stream)) l++;
+      CtxPtr a_cur = lc; U2 e_cur = ctx_ld(a_cur);
+      B200_NOUNROLL while (l < cmax) {
+        const CtxPtr a_next = ctx_at(lc, (l + 1) >> shift);
+        U2 e_next = ctx_ld(a_next), ne;
+        const int b = cb_.bin_e(e_cur, a_cur, stream, ne);
+        if (!b) break;
+        if (a_next == a_cur) e_next = ne;
+        a_cur = a_next; e_cur = e_next; l++;
+      }
       if (xy) ly = l; else lx = l;
     }
     B200_NOUNROLL for (int xy = 0; xy < 2; xy++) {
@@ -378,35 +399,47 @@ struct Decoder {
       const int right = (xs + 1 < nsbw) ? (int)((csbf >> (ys * 8 + xs + 1)) & 1) : 0;
       const int below = (ys + 1 < nsbw) ? (int)((csbf >> ((ys + 1) * 8 + xs)) & 1) : 0;
       int infer_dc = 0;
-      if (i < last_sb && i > 0) { if (!cb_.bin(cx + (CTX_CSBF + ((right | below) ? 1 : 0) + (c ? 2 : 0)), stream)) continue; infer_dc = 1; }
+      if (i < last_sb && i > 0) { if (!cb_.bin(ctx_at(cx, CTX_CSBF + ((right | below) ? 1 : 0) + (c ? 2 : 0)), stream)) continue; infer_dc = 1; }
       csbf |= 1ull << (ys * 8 + xs);
       // sig_coeff_flag (9.3.4.2.5): context = per-sub-block base + table entry per scan position; DC of the block has its own
       const TabPtr tab = log2n == 2 ? B200_TADDR(kSigCtx4) + 16 * scan : B200_TADDR(kSigCtxN) + (64 * scan + 16 * (right | (below << 1)));
-      const int off = sig_base + ((c == 0 && log2n > 2 && (xs | ys)) ? 3 : 0);
+      const CtxPtr cbase = ctx_at(cx, sig_base + ((c == 0 && log2n > 2 && (xs | ys)) ? 3 : 0));
       // flags are shifted in from the right: after the last position (k = 0) bit k of `sig` is the flag of scan position k
       unsigned sig = 0;
       int k = 15;
       if (i == last_sb) { sig = 1u; k = last_pos - 1; }
-      B200_NOUNROLL for (; k >= 0; k--) {
-        int ci = off + (int)tab_ld8(tab, k);
-        if (k == 0) { if (infer_dc && !sig) { sig = 1u; break; } if (i == 0) ci = dc_ctx; }
-        sig = (sig << 1) | (unsigned)cb_.bin(cx + (ci), stream);
+      if (k >= 0) {
+        // software pipeline: the entry of position k - 1 is in flight while position k is decoded (the contexts depend on the
+        // position only, 9.3.4.2.5); same context twice in a row -> forward the new entry in registers
+        const CtxPtr a0 = i == 0 ? ctx_at(cx, dc_ctx) : ctx_at(cbase, (int)tab_ld8(tab, 0));
+        CtxPtr a_cur = k > 0 ? ctx_at(cbase, (int)tab_ld8(tab, k)) : a0;
+        U2 e_cur = ctx_ld(a_cur);
+        B200_NOUNROLL for (; k > 0; k--) {
+          const CtxPtr a_next = k > 1 ? ctx_at(cbase, (int)tab_ld8(tab, k - 1)) : a0;
+          U2 e_next = ctx_ld(a_next), ne;
+          sig = (sig << 1) | (unsigned)cb_.bin_e(e_cur, a_cur, stream, ne);
+          if (a_next == a_cur) e_next = ne;
+          a_cur = a_next; e_cur = e_next;
+        }
+        if (infer_dc && !sig) sig = 1u;
+        else { U2 ne; sig = (sig << 1) | (unsigned)cb_.bin_e(e_cur, a_cur, stream, ne); }
       }
       if (!sig) continue;
       unsigned g1 = 0;
-      int last_g1 = -1, g1ctx = 1, g2 = 0;
+      int g1ctx = 1, g2 = 0;
       int ctx_set = (i == 0 || c > 0) ? 0 : 2;
       if (first_done && carry == 0) ctx_set++;
       first_done = true;
       const int last_sig = hi_bit(sig), first_sig = lo_bit(sig);
-      { unsigned m = sig; const int gbase = CTX_GT1 + ctx_set * 4 + (c ? 16 : 0);
+      { unsigned m = sig; const CtxPtr gbase = ctx_at(cx, CTX_GT1 + ctx_set * 4 + (c ? 16 : 0));
         B200_NOUNROLL for (int ng1 = 0; m && ng1 < 8; ng1++) {
           const int kk = hi_bit(m); m ^= 1u << kk;
-          if (cb_.bin(cx + (gbase + imin(3, g1ctx)), stream)) { g1 |= 1u << kk; g1ctx = 0; if (last_g1 < 0) last_g1 = kk; } else if (g1ctx > 0) g1ctx++;
+          if (cb_.bin(ctx_at(gbase, imin(3, g1ctx)), stream)) { g1 |= 1u << kk; g1ctx = 0; } else if (g1ctx > 0) g1ctx++;
         } }
       carry = g1ctx;
+      const int last_g1 = g1 ? hi_bit(g1) : -1;           // the first coefficient (in decoding order) with a greater1 flag of 1
       const bool hidden = sign_hiding && (last_sig - first_sig > 3);
-      if (last_g1 >= 0) g2 = cb_.bin(cx + (CTX_GT2 + ctx_set + (c ? 4 : 0)), stream);
+      if (last_g1 >= 0) g2 = cb_.bin(ctx_at(cx, CTX_GT2 + ctx_set + (c ? 4 : 0)), stream);
       const int nsign = pop_count(sig) - (hidden ? 1 : 0);
       const unsigned signs = cb_.bypass_bits(nsign, stream);
       int nsig = 0, sum = 0, rice = 0, sidx = nsign;
@@ -416,7 +449,7 @@ struct Decoder {
         int a = base;
         if (base == ((nsig < 8) ? ((kk == last_g1) ? 3 : 2) : 1)) {
           int pre = 0; B200_NOUNROLL while (pre < 32 && cb_.bypass(stream)) pre++;
-          const int rem = pre <= 3 ? (pre << rice) + (int)cb_.bypass_bits(rice, stream) : (((1 << (pre - 3)) + 3 - 1) << rice) + (int)cb_.bypass_bits(pre - 3 + rice, stream);
+          const int rem = (pre <= 3 ? (pre << rice) : (((1 << (pre - 3)) + 3 - 1) << rice)) + (int)cb_.bypass_bits(pre <= 3 ? rice : pre - 3 + rice, stream);
           a = base + rem;
           if (a > 3 * (1 << rice)) rice = imin(rice + 1, 4);
         }
@@ -650,7 +683,7 @@ B200_HD int run_substream(Decoder& d, const SeqParams& sp, const PicBuffers& pb,
   if (ss.prev >= 0) {                                         // dependent slice segment: continue from the previous segment's end state
     sync.wait_substream(ss.prev);
     const uint8_t* st = pb.end_state + (size_t)ss.prev * CTX_STRIDE;
-    B200_NOUNROLL for (int i = 0; i < CTX_COUNT; i++) ctx_st(ctx + i, B200_LD_SHARED(st + i));
+    B200_NOUNROLL for (int i = 0; i < CTX_COUNT; i++) ctx_st(ctx_at(ctx, i), tab_ld64(B200_TADDR(kState), (int)B200_LD_SHARED(st + i) & 127));
     d.last_cu_qpy = (int)(int8_t)B200_LD_SHARED(st + CTX_COUNT); d.first_qg = 0;
   }
   if (ss.init_contexts) init_contexts(ctx, ss.slice_qp);
@@ -660,7 +693,7 @@ B200_HD int run_substream(Decoder& d, const SeqParams& sp, const PicBuffers& pb,
     const int xn = 1 << sp.log2ctb, yn = (ry0 - 1) << sp.log2ctb;
     bool tr = ry0 > 0 && xn < sp.W && pb.ctu_slice[(ry0 - 1) * sp.wctb + 1] == (uint16_t)ss.slice_idx;
     (void)yn;
-    if (tr) { sync.wait_row(ry0 - 1, 2); const uint8_t* st = pb.wpp_ctx + (size_t)(ry0 - 1) * CTX_STRIDE; B200_NOUNROLL for (int i = 0; i < CTX_COUNT; i++) ctx_st(ctx + i, B200_LD_SHARED(st + i)); }
+    if (tr) { sync.wait_row(ry0 - 1, 2); const uint8_t* st = pb.wpp_ctx + (size_t)(ry0 - 1) * CTX_STRIDE; B200_NOUNROLL for (int i = 0; i < CTX_COUNT; i++) ctx_st(ctx_at(ctx, i), tab_ld64(B200_TADDR(kState), (int)B200_LD_SHARED(st + i) & 127)); }
     else if (ss.prev < 0) init_contexts(ctx, ss.slice_qp);
     d.first_qg = 1;
   }
@@ -676,19 +709,21 @@ B200_HD int run_substream(Decoder& d, const SeqParams& sp, const PicBuffers& pb,
     if (!sp.wpp && rx == 0 && a != ss.ctb_begin) { /* QG state simply continues */ }
     d.decode_ctb((int)a);
     if (d.err) break;
-    if (sp.wpp && rx == 1) { uint8_t* st = pb.wpp_ctx + (size_t)ry * CTX_STRIDE; B200_NOUNROLL for (int i = 0; i < CTX_COUNT; i++) st[i] = (uint8_t)ctx_ld(ctx + i); }
+    if (sp.wpp && rx == 1) { uint8_t* st = pb.wpp_ctx + (size_t)ry * CTX_STRIDE; B200_NOUNROLL for (int i = 0; i < CTX_COUNT; i++) st[i] = (uint8_t)(ctx_ld(ctx_at(ctx, i)).y >> 24); }
     const int end = d.cabac.terminate(d.stream);                          // end_of_slice_segment_flag
     const bool last = a + 1 == ss.ctb_end;
     if (end != ((last && ss.last_of_segment) ? 1 : 0)) { d.err = SYN_E_BITSTREAM; break; }
     if (last && !ss.last_of_segment) { if (!d.cabac.terminate(d.stream)) { d.err = SYN_E_BITSTREAM; break; } }   // end_of_subset_one_bit
     sync.publish_row(ry, rx + 1);
+    if (sp.wpp && rx == 1) sync.notify(ss.wake_ctb2);           // the row below may start (its context hand-over is stored)
     if (d.cabac.pos > pb.rbsp_size + 64u) { d.err = SYN_E_BITSTREAM; break; }
   }
   // end state for a dependent continuation + dense cursors
-  { uint8_t* st = pb.end_state + (size_t)index * CTX_STRIDE; B200_NOUNROLL for (int i = 0; i < CTX_COUNT; i++) st[i] = (uint8_t)ctx_ld(ctx + i); st[CTX_COUNT] = (uint8_t)(int8_t)d.last_cu_qpy; }
+  { uint8_t* st = pb.end_state + (size_t)index * CTX_STRIDE; B200_NOUNROLL for (int i = 0; i < CTX_COUNT; i++) st[i] = (uint8_t)(ctx_ld(ctx_at(ctx, i)).y >> 24); st[CTX_COUNT] = (uint8_t)(int8_t)d.last_cu_qpy; }
   if (sp.dense) { sync.dense_tu = d.tu_n; sync.dense_coef = d.coef_n; }
   sync.end_bit_position = d.cabac.bit_position();
   sync.finish_substream(index, d.err);
+  if (!d.err) sync.notify(ss.wake_end);
   return d.err;
 }
 

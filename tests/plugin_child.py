@@ -46,6 +46,20 @@ cpu_grid = rh.decode_file(os.path.join(tmp, "grid.heic"), decoder_id="b200-oracl
 res["grid_shape"] = list(cpu_grid.shape)
 res["grid_md5_cpu"] = hashlib.md5(cpu_grid.tobytes()).hexdigest()
 res["single_md5_cpu"] = hashlib.md5(cpu_single.tobytes()).hexdigest()
+# oracle/heic_writer.py: the same tiles wrapped by our own ISOBMFF writer must decode to the same picture as the file the
+# reference's writer produced (same encoder parameters -> byte-identical access units)
+from oracle import heic_writer as hw  # noqa: E402
+from libheif_b200 import hevc_enc  # noqa: E402
+aus = []
+for k in range(6):
+    ty, tcb, tcr = synthetic_image(100 + k, 128, 128, 8, True)
+    aus.append(hevc_enc.encode_intra(ty, tcb, tcr, bit_depth=8, log2_ctb_size=5, qp=51 - (60 * 45 + 50) // 100, wpp=1, seed=0xB200, vui_present=1,
+                                     colour_description_present=1, colour_primaries=1, transfer_characteristics=13, matrix_coefficients=6, full_range=1))
+hw.write_heic(os.path.join(tmp, "grid_own.heic"), aus, cols=3, rows=2)
+own = rh.decode_file(os.path.join(tmp, "grid_own.heic"), decoder_id="b200-oracle", threads=4)
+res["grid_md5_own_writer"] = hashlib.md5(own.tobytes()).hexdigest()
+hw.write_heic(os.path.join(tmp, "single_own.heic"), aus[:1])
+res["single_own_shape"] = list(rh.decode_file(os.path.join(tmp, "single_own.heic"), decoder_id="b200-oracle").shape)
 if mode == "roundtrip-gpu":
     rh.check(h.heif_register_decoder_plugin(b200.b200_get_decoder_plugin()), "register decoder plugin")
     for name in ("single", "grid"):

@@ -50,6 +50,9 @@ def test_encoder_plugin_through_reference_libheif():
     assert res["single_shape"] == [136, 600]
     assert res["grid_shape"] == [256, 1152]
     assert res["single_psnr_luma_vs_green"] > 18      # G is only a proxy for Y: this guards against gross corruption
+    # oracle/heic_writer.py (used by the reference arm of bench.py) produces files the reference reads identically
+    assert res["grid_md5_own_writer"] == res["grid_md5_cpu"]
+    assert res["single_own_shape"] == [128, 384]
 
 
 @pytest.mark.gpu
