@@ -224,6 +224,10 @@ int b200_decoder_get_stats(b200_decoder* dec, b200_decode_stats* out);
 /* Re-launch the device kernels on the command stream already resident in HBM (no host parse, no H2D). */
 int b200_decoder_rerun_device(b200_decoder* dec, void* stream);
 
+/* Host only, no CUDA: what de265_get_image_width / _height / de265_get_bits_per_pixel / de265_get_chroma_format and the colour
+   getters (decoder_libde265.cc:102-137, 428-446) would report for this access unit, from its parameter sets alone. */
+int b200_probe_access_unit(const uint8_t* au, size_t au_size, uint64_t max_image_size_pixels, b200_image_info* info);
+
 /* Fused convenience: decode grid -> geometry -> colour conversion -> interleaved RGB in HOST memory. */
 int b200_decode_grid_to_rgb_host(b200_decoder* dec, int cols, int rows, const uint8_t* const* au, const size_t* au_size,
                                  uint64_t max_image_size_pixels, int canvas_w, int canvas_h, const b200_geometry* geom /* NULL = identity */,

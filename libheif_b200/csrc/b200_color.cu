@@ -42,6 +42,7 @@ struct K6Args {
   int pre_shift;                    // Op_to_sdr_planes applied to the YCbCr planes first (then integer op)
   int alpha_fill;                   // alpha value when the target wants alpha and the input has none
   int out_bytes;                    // bytes per output sample (1 or 2)
+  int special;                      // matrix_coefficients branches of the generic op (yuv2rgb.cc:222-262): 1 = 0 (GBR), 2 = 8 (YCgCo), 3 = 16 (YCgCo-Re)
 };
 
 __device__ __forceinline__ int clip_f(float fx, int maxv) {      // common_utils.h:108-114 clip_f_u16
@@ -61,6 +62,27 @@ __device__ __forceinline__ void convert_px(const K6Args& p, int Y, int Cb, int C
     return;
   }
   const int half = 1 << (p.bpp - 1), maxv = (1 << p.bpp) - 1;     // yuv2rgb.cc:270-282
+  if (p.special) {                                                // yuv2rgb.cc:222-262
+    if (p.special == 1) {                                         // GBR: copy, or range-expand
+      if (p.full_range) { r = Cr; g = Y; b = Cb; }
+      else {
+        const float lro = (float)(16 << (p.bpp - 8));
+        r = clip_f(__fmul_rn(__fsub_rn((float)Cr, lro), 1.1429f), maxv);
+        g = clip_f(__fmul_rn(__fsub_rn((float)Y, lro), 1.1689f), maxv);
+        b = clip_f(__fmul_rn(__fsub_rn((float)Cb, lro), 1.1429f), maxv);
+      }
+    } else if (p.special == 2) {                                  // YCgCo; clip_int_u8 also for > 8 bit (reference quirk, :240-242)
+      const int cb = Cb - half, cr = Cr - half;
+      r = clip_u8(Y - cb + cr); g = clip_u8(Y + cb); b = clip_u8(Y - cb - cr);
+    } else {                                                      // YCgCo-Re: int16 arithmetic, x4
+      const short yy = (short)Y, cb = (short)((short)Cb - (short)half), cr = (short)((short)Cr - (short)half);
+      const short t = (short)(yy - (cb >> 1)), gg = (short)(t + cb), bb = (short)(t - (cr >> 1)), rr = (short)(bb + cr);
+      const int rv = rr * 4, gv = gg * 4, bv = bb * 4;
+      r = rv < 0 ? 0 : (rv > maxv ? maxv : rv); g = gv < 0 ? 0 : (gv > maxv ? maxv : gv); b = bv < 0 ? 0 : (bv > maxv ? maxv : bv);
+    }
+    if (p.sdr_shift) { r >>= p.sdr_shift; g >>= p.sdr_shift; b >>= p.sdr_shift; }
+    return;
+  }
   float yv = (float)Y, cb = (float)(Cb - half), cr = (float)(Cr - half);
   if (!p.full_range) {
     yv = __fmul_rn(__fsub_rn(yv, (float)(16 << (p.bpp - 8))), 1.1689f);
@@ -340,7 +362,29 @@ static void primaries_of(int idx, float p[8], bool& defined) {
   }
 }
 
+static void kr_kb(int matrix, int primaries, float* pKr, float* pKb);
 void ycbcr_to_rgb_coefficients(int matrix, int primaries, float out[4]) {
+  float kr, kb; kr_kb(matrix, primaries, &kr, &kb);
+  if (kb != 0 || kr != 0) {
+    out[0] = 2 * (-kr + 1);
+    out[1] = 2 * kb * (-kb + 1) / (kb + kr - 1);
+    out[2] = 2 * kr * (-kr + 1) / (kb + kr - 1);
+    out[3] = 2 * (-kb + 1);
+  } else { out[0] = 1.402f; out[1] = -0.344136f; out[2] = -0.714136f; out[3] = 1.772f; }
+}
+// RGB -> YCbCr coefficients of the same matrix (nclx.cc:177-200)
+static void rgb_to_ycbcr_coefficients(int matrix, int primaries, float c[3][3]) {
+  float Kr, Kb; kr_kb(matrix, primaries, &Kr, &Kb);
+  if (Kb != 0 || Kr != 0) {
+    c[0][0] = Kr; c[0][1] = 1 - Kr - Kb; c[0][2] = Kb;
+    c[1][0] = -Kr / (1 - Kb) / 2; c[1][1] = -(1 - Kr - Kb) / (1 - Kb) / 2; c[1][2] = 0.5f;
+    c[2][0] = 0.5f; c[2][1] = -(1 - Kr - Kb) / (1 - Kr) / 2; c[2][2] = -Kb / (1 - Kr) / 2;
+  } else {
+    c[0][0] = 0.299f; c[0][1] = 0.587f; c[0][2] = 0.114f; c[1][0] = -0.168735f; c[1][1] = -0.331264f; c[1][2] = 0.5f;
+    c[2][0] = 0.5f; c[2][1] = -0.418688f; c[2][2] = -0.081312f;
+  }
+}
+static void kr_kb(int matrix, int primaries, float* pKr, float* pKb) {
   volatile float Kr = 0.0f, Kb = 0.0f;              // volatile: keep every intermediate rounded to float
   if (matrix == 12 || matrix == 13) {
     float p[8]; bool def;
@@ -362,13 +406,7 @@ void ycbcr_to_rgb_coefficients(int matrix, int primaries, float out[4]) {
       default: break;
     }
   }
-  const float kr = Kr, kb = Kb;
-  if (kb != 0 || kr != 0) {
-    out[0] = 2 * (-kr + 1);
-    out[1] = 2 * kb * (-kb + 1) / (kb + kr - 1);
-    out[2] = 2 * kr * (-kr + 1) / (kb + kr - 1);
-    out[3] = 2 * (-kb + 1);
-  } else { out[0] = 1.402f; out[1] = -0.344136f; out[2] = -0.714136f; out[3] = 1.772f; }
+  *pKr = Kr; *pKb = Kb;
 }
 
 // Plane-wise geometry (rotate / mirror / crop on a 4:2:0 picture as the reference's ComponentStorage code does it) for
@@ -377,22 +415,61 @@ void ycbcr_to_rgb_coefficients(int matrix, int primaries, float out[4]) {
 // have been earlier).
 template <typename T>
 __global__ void plane_geometry_kernel(const T* __restrict__ in, long long in_stride, T* __restrict__ out, long long out_stride, int out_w, int out_h,
-                                      int m0, int m1, int m2, int m3, int m4, int m5, int shift) {
+                                      int m0, int m1, int m2, int m3, int m4, int m5, int shx, int shy) {
   const int u = blockIdx.x * blockDim.x + threadIdx.x, v = blockIdx.y;
   if (u >= out_w || v >= out_h) return;
-  const int sx = (m0 * (u << shift) + m1 * (v << shift) + m2) >> shift, sy = (m3 * (u << shift) + m4 * (v << shift) + m5) >> shift;
+  const int sx = (m0 * (u << shx) + m1 * (v << shy) + m2) >> shx, sy = (m3 * (u << shx) + m4 * (v << shy) + m5) >> shy;
   out[(long long)v * out_stride + u] = in[(long long)sy * in_stride + sx];
+}
+
+// Op_YCbCr422_bilinear_to_YCbCr444<T> (chroma_sampling.cc:784-905): chroma (w + 1) / 2 x h -> w x h, both planes
+template <typename T>
+__global__ void bilinear_422_to_444_kernel(const T* __restrict__ cb, const T* __restrict__ cr, long long in_stride, T* __restrict__ ocb, T* __restrict__ ocr,
+                                           long long out_stride, int w, int h) {
+  const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+  if (x >= w || y >= h) return;
+  const T* rb = cb + (long long)y * in_stride; const T* rr = cr + (long long)y * in_stride;
+  unsigned vb, vr;
+  if (x == 0) { vb = rb[0]; vr = rr[0]; }
+  else if ((w & 1) == 0 && x == w - 1) { vb = rb[w / 2 - 1]; vr = rr[w / 2 - 1]; }
+  else if (x & 1) { const int c = x >> 1; vb = ((unsigned)rb[c] * 3 + rb[c + 1] + 2) / 4; vr = ((unsigned)rr[c] * 3 + rr[c + 1] + 2) / 4; }
+  else { const int c = (x - 1) >> 1; vb = ((unsigned)rb[c] + (unsigned)rb[c + 1] * 3 + 2) / 4; vr = ((unsigned)rr[c] + (unsigned)rr[c + 1] * 3 + 2) / 4; }
+  ocb[(long long)y * out_stride + x] = (T)vb; ocr[(long long)y * out_stride + x] = (T)vr;
+}
+
+// The 4:4:4 conversion point of a LIMITED-range picture: the reference's target profile there is full range, and the path
+// its planner finds is Op_YCbCr_to_RGB<T> (yuv2rgb.cc:263-279) followed by Op_RGB_to_YCbCr<T> (rgb2yuv.cc:226-300) with
+// the same matrix.  One pass over the three 4:4:4 planes, float arithmetic in the reference's order.
+struct RangeArgs { float cf[4]; float c[3][3]; int bpp; };
+template <typename T>
+__global__ void range_limited_to_full_444_kernel(const T* __restrict__ y, long long ys, const T* __restrict__ cb, const T* __restrict__ cr, long long cs,
+                                                 T* __restrict__ oy, long long oys, T* __restrict__ ocb, T* __restrict__ ocr, long long ocs, int w, int h, RangeArgs a) {
+  const int x = blockIdx.x * blockDim.x + threadIdx.x, yy = blockIdx.y;
+  if (x >= w || yy >= h) return;
+  const int half = 1 << (a.bpp - 1), maxv = (1 << a.bpp) - 1; const float lro = (float)(16 << (a.bpp - 8));
+  float yv = (float)y[(long long)yy * ys + x], cbv = (float)((int)cb[(long long)yy * cs + x] - half), crv = (float)((int)cr[(long long)yy * cs + x] - half);
+  yv = __fmul_rn(__fsub_rn(yv, lro), 1.1689f); cbv = __fmul_rn(cbv, 1.1429f); crv = __fmul_rn(crv, 1.1429f);
+  const float r = (float)clip_f(__fadd_rn(yv, __fmul_rn(a.cf[0], crv)), maxv);
+  const float g = (float)clip_f(__fadd_rn(__fadd_rn(yv, __fmul_rn(a.cf[1], cbv)), __fmul_rn(a.cf[2], crv)), maxv);
+  const float b = (float)clip_f(__fadd_rn(yv, __fmul_rn(a.cf[3], cbv)), maxv);
+  auto dot = [&](int k) { return __fadd_rn(__fadd_rn(__fmul_rn(r, a.c[k][0]), __fmul_rn(g, a.c[k][1])), __fmul_rn(b, a.c[k][2])); };
+  oy[(long long)yy * oys + x] = (T)clip_f(dot(0), maxv);
+  ocb[(long long)yy * ocs + x] = (T)clip_f(__fadd_rn(dot(1), (float)half), maxv);
+  ocr[(long long)yy * ocs + x] = (T)clip_f(__fadd_rn(dot(2), (float)half), maxv);
 }
 
 int launch_color(const b200_planes* in, const b200_geometry* g, const b200_color_options* opt, void* out, void* out_g,
                  void* out_b, size_t out_stride, cudaStream_t stream, int* pipeline);
 
-// 4:2:0 picture -> (plane-wise geometry `pre`) -> Op_YCbCr420_bilinear_to_YCbCr444 -> the rest of the chain and the colour
-// conversion from 4:4:4.  Serves the reference's 4:4:4 conversion point and bilinear upsampling after geometry.
+// 4:2:0 / 4:2:2 picture -> (plane-wise geometry `pre`) -> Op_YCbCr420_bilinear_to_YCbCr444 / Op_YCbCr422_bilinear_to_YCbCr444
+// -> (limited range: range conversion through RGB) -> the rest of the chain and the colour conversion from 4:4:4.
+// Serves the reference's 4:4:4 conversion point and bilinear upsampling after geometry.
 static int convert_via_444(const b200_planes* in, const b200_geometry* g, const b200_color_options* opt, void* out, void* out_g, void* out_b,
-                           size_t out_stride, cudaStream_t stream, int* pipeline) {
+                           size_t out_stride, cudaStream_t stream, int* pipeline, bool range_convert) {
   const int bps = in->bit_depth > 8 ? 2 : 1;
-  const int pw = g->pre_w, ph = g->pre_h, pcw = (pw + 1) / 2, pch = (ph + 1) / 2;
+  const bool c422 = in->chroma == B200_CHROMA_422;
+  const int shy = c422 ? 0 : 1;
+  const int pw = g->pre_w, ph = g->pre_h, pcw = (pw + 1) / 2, pch = c422 ? ph : (ph + 1) / 2;
   const bool pre_identity = g->pre[0] == 1 && g->pre[1] == 0 && g->pre[2] == 0 && g->pre[3] == 0 && g->pre[4] == 1 && g->pre[5] == 0 && pw == in->width && ph == in->height;
   const size_t pitch = (((size_t)pw * bps) + 255) & ~(size_t)255, cpitch = (((size_t)pcw * bps) + 255) & ~(size_t)255;
   const size_t n_full = pitch * ph, n_c = cpitch * pch;
@@ -402,23 +479,37 @@ static int convert_via_444(const b200_planes* in, const b200_geometry* g, const 
   b200_planes p = *in;
   if (!pre_identity) {
     const int* q = g->pre;
-    auto run = [&](const void* src, size_t sstride, void* dst, size_t dstride, int w, int h, int shift) {
+    auto run = [&](const void* src, size_t sstride, void* dst, size_t dstride, int w, int h, int sx, int sy) {
       dim3 grid((w + 255) / 256, h);
-      if (bps == 1) plane_geometry_kernel<uint8_t><<<grid, 256, 0, stream>>>((const uint8_t*)src, (long long)sstride, (uint8_t*)dst, (long long)dstride, w, h, q[0], q[1], q[2], q[3], q[4], q[5], shift);
-      else plane_geometry_kernel<uint16_t><<<grid, 256, 0, stream>>>((const uint16_t*)src, (long long)sstride / 2, (uint16_t*)dst, (long long)dstride / 2, w, h, q[0], q[1], q[2], q[3], q[4], q[5], shift);
+      if (bps == 1) plane_geometry_kernel<uint8_t><<<grid, 256, 0, stream>>>((const uint8_t*)src, (long long)sstride, (uint8_t*)dst, (long long)dstride, w, h, q[0], q[1], q[2], q[3], q[4], q[5], sx, sy);
+      else plane_geometry_kernel<uint16_t><<<grid, 256, 0, stream>>>((const uint16_t*)src, (long long)sstride / 2, (uint16_t*)dst, (long long)dstride / 2, w, h, q[0], q[1], q[2], q[3], q[4], q[5], sx, sy);
     };
-    run(in->y, in->y_stride, ty, pitch, pw, ph, 0);
-    run(in->cb, in->c_stride, tcb, cpitch, pcw, pch, 1);
-    run(in->cr, in->c_stride, tcr, cpitch, pcw, pch, 1);
-    if (in->alpha) run(in->alpha, in->alpha_stride, ta, pitch, pw, ph, 0);
+    run(in->y, in->y_stride, ty, pitch, pw, ph, 0, 0);
+    run(in->cb, in->c_stride, tcb, cpitch, pcw, pch, 1, shy);
+    run(in->cr, in->c_stride, tcr, cpitch, pcw, pch, 1, shy);
+    if (in->alpha) run(in->alpha, in->alpha_stride, ta, pitch, pw, ph, 0, 0);
     p.y = ty; p.y_stride = pitch; p.cb = tcb; p.cr = tcr; p.c_stride = cpitch;
     if (in->alpha) { p.alpha = ta; p.alpha_stride = pitch; }
     p.width = pw; p.height = ph;
   }
   dim3 grid((pw + 255) / 256, ph);
-  if (bps == 1) bilinear_420_to_444_kernel<uint8_t><<<grid, 256, 0, stream>>>((const uint8_t*)p.cb, (const uint8_t*)p.cr, (long long)p.c_stride, (uint8_t*)u_cb, (uint8_t*)u_cr, (long long)pitch, pw, ph);
-  else bilinear_420_to_444_kernel<uint16_t><<<grid, 256, 0, stream>>>((const uint16_t*)p.cb, (const uint16_t*)p.cr, (long long)p.c_stride / 2, (uint16_t*)u_cb, (uint16_t*)u_cr, (long long)pitch / 2, pw, ph);
+  if (c422) {
+    if (bps == 1) bilinear_422_to_444_kernel<uint8_t><<<grid, 256, 0, stream>>>((const uint8_t*)p.cb, (const uint8_t*)p.cr, (long long)p.c_stride, (uint8_t*)u_cb, (uint8_t*)u_cr, (long long)pitch, pw, ph);
+    else bilinear_422_to_444_kernel<uint16_t><<<grid, 256, 0, stream>>>((const uint16_t*)p.cb, (const uint16_t*)p.cr, (long long)p.c_stride / 2, (uint16_t*)u_cb, (uint16_t*)u_cr, (long long)pitch / 2, pw, ph);
+  } else {
+    if (bps == 1) bilinear_420_to_444_kernel<uint8_t><<<grid, 256, 0, stream>>>((const uint8_t*)p.cb, (const uint8_t*)p.cr, (long long)p.c_stride, (uint8_t*)u_cb, (uint8_t*)u_cr, (long long)pitch, pw, ph);
+    else bilinear_420_to_444_kernel<uint16_t><<<grid, 256, 0, stream>>>((const uint16_t*)p.cb, (const uint16_t*)p.cr, (long long)p.c_stride / 2, (uint16_t*)u_cb, (uint16_t*)u_cr, (long long)pitch / 2, pw, ph);
+  }
   p.cb = u_cb; p.cr = u_cr; p.c_stride = pitch; p.chroma = B200_CHROMA_444;
+  if (range_convert) {
+    // limited -> full range through RGB; Y goes to the scratch plane (the caller's luma plane is never written)
+    RangeArgs ra; ra.bpp = in->bit_depth;
+    ycbcr_to_rgb_coefficients(in->matrix_coefficients, in->colour_primaries, ra.cf);
+    rgb_to_ycbcr_coefficients(in->matrix_coefficients, in->colour_primaries, ra.c);
+    if (bps == 1) range_limited_to_full_444_kernel<uint8_t><<<grid, 256, 0, stream>>>((const uint8_t*)p.y, (long long)p.y_stride, (const uint8_t*)u_cb, (const uint8_t*)u_cr, (long long)pitch, (uint8_t*)ty, (long long)pitch, (uint8_t*)u_cb, (uint8_t*)u_cr, (long long)pitch, pw, ph, ra);
+    else range_limited_to_full_444_kernel<uint16_t><<<grid, 256, 0, stream>>>((const uint16_t*)p.y, (long long)p.y_stride / 2, (const uint16_t*)u_cb, (const uint16_t*)u_cr, (long long)pitch / 2, (uint16_t*)ty, (long long)pitch / 2, (uint16_t*)u_cb, (uint16_t*)u_cr, (long long)pitch / 2, pw, ph, ra);
+    p.y = ty; p.y_stride = pitch; p.width = pw; p.height = ph; p.full_range = 1;
+  }
   b200_geometry rest = *g; rest.detour = 0; rest.chroma = B200_CHROMA_444;
   b200_color_options o2 = *opt; o2.chroma_upsampling = 0;
   int rc = launch_color(&p, &rest, &o2, out, out_g, out_b, out_stride, stream, pipeline);
@@ -438,8 +529,8 @@ int launch_color(const b200_planes* in, const b200_geometry* g, const b200_color
   const bool interleaved16 = fmt >= B200_CHROMA_INTERLEAVED_RRGGBB_BE && fmt <= B200_CHROMA_INTERLEAVED_RRGGBBAA_LE;
   if (!interleaved8 && !interleaved16 && fmt != B200_CHROMA_444) return set_error(B200_E_UNSUPPORTED, "output chroma %d", fmt);
   const int mc = in->matrix_coefficients;
-  if (in->chroma != B200_CHROMA_MONO && (mc == 0 || mc == 8 || mc == 11 || mc == 14 || mc == 16))
-    return set_error(B200_E_UNSUPPORTED, "matrix_coefficients %d has no linear YCbCr->RGB path here", mc);
+  if (in->chroma != B200_CHROMA_MONO && (mc == 11 || mc == 14))
+    return set_error(B200_E_UNSUPPORTED, "matrix_coefficients %d: the reference has no YCbCr->RGB operation for it either (yuv2rgb.cc:107-112)", mc);
   if (interleaved16 && in->bit_depth == 8) return set_error(B200_E_UNSUPPORTED, "8-bit input to RRGGBB output");
   const bool subsampled = in->chroma == B200_CHROMA_420 || in->chroma == B200_CHROMA_422;
   if (g->detour && !subsampled) {
@@ -454,9 +545,10 @@ int launch_color(const b200_planes* in, const b200_geometry* g, const b200_color
     return set_error(B200_E_INVALID, "geometry was composed for chroma format %d, the picture has %d (b200_geometry_init)", g->chroma, in->chroma);
   if (g->detour) {
     // 4:4:4 conversion point of the reference (see b200_geometry)
-    if (in->chroma != B200_CHROMA_420) return set_error(B200_E_UNSUPPORTED, "4:2:2 picture needs the 4:4:4 detour of the reference (Op_YCbCr422_bilinear_to_YCbCr444)");
-    if (!in->full_range) return set_error(B200_E_UNSUPPORTED, "limited-range 4:2:0 picture with an odd-origin crop / odd-size rotate or mirror: the reference range-converts it through RGB");
-    return convert_via_444(in, g, opt, out, out_g, out_b, out_stride, stream, pipeline);
+    // (a limited-range picture is also range-converted there: the conversion's target profile is full range)
+    if (!in->full_range && (mc == 0 || mc == 8 || mc == 16))
+      return set_error(B200_E_UNSUPPORTED, "limited-range picture with matrix_coefficients %d at the 4:4:4 conversion point", mc);
+    return convert_via_444(in, g, opt, out, out_g, out_b, out_stride, stream, pipeline, !in->full_range);
   }
   if (opt->chroma_upsampling == 1 && in->chroma == B200_CHROMA_420) {
     // heif_color_conversion_options.only_use_preferred_chroma_algorithm with bilinear upsampling: the reference runs
@@ -469,7 +561,7 @@ int launch_color(const b200_planes* in, const b200_geometry* g, const b200_color
       for (int i = 0; i < 6; i++) t.pre[i] = g->m[i];
       t.pre_w = g->out_w; t.pre_h = g->out_h;
       t.m[0] = 1; t.m[1] = 0; t.m[2] = 0; t.m[3] = 0; t.m[4] = 1; t.m[5] = 0;
-      return convert_via_444(in, &t, opt, out, out_g, out_b, out_stride, stream, pipeline);
+      return convert_via_444(in, &t, opt, out, out_g, out_b, out_stride, stream, pipeline, false);
     }
     const int bps = in->bit_depth > 8 ? 2 : 1;
     const size_t pitch = (((size_t)in->width * bps) + 255) & ~(size_t)255;
@@ -506,17 +598,24 @@ int launch_color(const b200_planes* in, const b200_geometry* g, const b200_color
   const bool has_alpha = in->alpha != nullptr && want_alpha;
   int pipe = 0;
   // integer fast path: 4:2:0, 8 bit, full range, interleaved 8-bit target (yuv2rgb.cc:300-340, :440-478)
-  a.int_mode = (in->chroma == B200_CHROMA_420 && in->bit_depth == 8 && in->full_range && interleaved8) ? 1 : 0;
+  // matrix_coefficients 0 / 8: the dedicated 4:2:0 ops are not selected (the generic op with its special branch runs);
+  // 16: they are, and convert with the default coefficients (they have no YCgCo-Re branch) -- planner behaviour pinned in
+  // tests/test_color_oracle.py: test_special_matrices_match_reference
+  const bool dedicated_ok = !(mc == 0 || mc == 8);
+  a.int_mode = (in->chroma == B200_CHROMA_420 && in->bit_depth == 8 && in->full_range && interleaved8 && dedicated_ok) ? 1 : 0;
   pipe |= a.int_mode ? B200_PIPE_INT420 : B200_PIPE_FLOAT;
   a.sdr_shift = 0; a.pre_shift = 0;
   a.out_bytes = in->bit_depth > 8 ? 2 : 1;
   if (in->bit_depth > 8 && interleaved8) {
     a.out_bytes = 1; pipe |= B200_PIPE_SDR_SHIFT;
-    if (in->chroma == B200_CHROMA_420 && in->full_range) {
+    if (in->chroma == B200_CHROMA_420 && in->full_range && dedicated_ok) {
       // the reference planner shifts the YCbCr planes to 8 bit first and then takes the integer op
       a.pre_shift = in->bit_depth - 8; a.int_mode = 1; a.bpp = 8; pipe = B200_PIPE_SDR_SHIFT | B200_PIPE_INT420;
     } else a.sdr_shift = in->bit_depth - 8;
   }
+  const bool rrggbb_direct = in->chroma == B200_CHROMA_420 && in->bit_depth > 8 && interleaved16 && dedicated_ok;     // Op_YCbCr420_to_RRGGBBaa
+  a.special = 0;
+  if (in->chroma != B200_CHROMA_MONO && (mc == 0 || mc == 8 || mc == 16) && !a.int_mode && !rrggbb_direct) a.special = mc == 0 ? 1 : (mc == 8 ? 2 : 3);
   a.alpha_fill = a.out_bytes == 1 ? 0xFF : (1 << in->bit_depth) - 1;
   if (fmt == B200_CHROMA_444 && (!out_g || !out_b)) return set_error(B200_E_INVALID, "planar output needs three planes");
   if (pipeline) *pipeline = pipe;
@@ -524,7 +623,7 @@ int launch_color(const b200_planes* in, const b200_geometry* g, const b200_color
   // fast path: identity geometry, 4:2:0, no alpha, everything 16-byte aligned (the grid / single-image decode case)
   const bool identity = g->m[0] == 1 && g->m[1] == 0 && g->m[2] == 0 && g->m[3] == 0 && g->m[4] == 1 && g->m[5] == 0 && g->out_w == in->width && g->out_h == in->height;
   const uintptr_t al = (uintptr_t)in->y | (uintptr_t)in->cb | (uintptr_t)in->cr | (uintptr_t)out | (uintptr_t)in->y_stride | (uintptr_t)in->c_stride | (uintptr_t)out_stride;
-  if (identity && in->chroma == B200_CHROMA_420 && !has_alpha && (al & 15) == 0 && in->width % 16 == 0 && in->height % 2 == 0 && fmt != B200_CHROMA_444 && !(a.sdr_shift && a.out_bytes == 2)) {
+  if (identity && in->chroma == B200_CHROMA_420 && !has_alpha && !a.special && (al & 15) == 0 && in->width % 16 == 0 && in->height % 2 == 0 && fmt != B200_CHROMA_444 && !(a.sdr_shift && a.out_bytes == 2)) {
     bool done;
     if (in->bit_depth == 8) done = a.int_mode ? launch_direct<uint8_t, 1>(a, stream) : launch_direct<uint8_t, 0>(a, stream);
     else done = a.int_mode ? launch_direct<uint16_t, 1>(a, stream) : launch_direct<uint16_t, 0>(a, stream);

@@ -62,6 +62,7 @@ struct EntropyBatch {
   unsigned int* queue; unsigned int* qhead; unsigned int* qtail; unsigned int* deps;
   unsigned int* progress; unsigned int* sub_done; unsigned int* error_flag;
   int blocks_per_sm;             // > 0: cap of resident CTAs per SM (co-residency with K1)
+  int common;                    // 1: every picture matches syn::CfgCommon (specialised kernel)
 };
 int launch_entropy(const EntropyBatch& b, cudaStream_t s);
 int launch_entropy_stats(const EntropyBatch& b, unsigned long long* out2, cudaStream_t s);

@@ -172,6 +172,9 @@ static int run_device_pipeline(b200_decoder* d, int n, cudaStream_t s, int* laun
     e.pics = d->epics.d; e.npics = d->npics; e.subs = d->subs.d; e.nsubs = (int)d->n_subs;
     e.qhead = d->equeue.d; e.qtail = d->equeue.d + 1; e.queue = d->equeue.d + 2; e.deps = d->equeue.d + 2 + d->n_subs;
     e.progress = d->esync.d + 1; e.sub_done = d->esync.d + 1 + d->n_rows; e.error_flag = d->sync.d + 1;
+    e.common = 1;
+    if (getenv("B200_ENTROPY_GENERIC")) e.common = 0;
+    for (int i = 0; i < d->npics && e.common; i++) if (!syn::matches_common(d->epics.h[i].sp)) e.common = 0;
     if (overlap) {
       if (!d->side) { B200_CUDA_CHECK(cudaStreamCreateWithFlags(&d->side, cudaStreamNonBlocking)); B200_CUDA_CHECK(cudaEventCreate(&d->ev_fork)); B200_CUDA_CHECK(cudaEventCreate(&d->ev_join)); }
       e.blocks_per_sm = overlap_blocks("B200_OVERLAP_K0_BLOCKS", 3);
@@ -552,6 +555,20 @@ int b200_decode_grid_to_rgb_host(b200_decoder* d, int cols, int rows, const uint
     B200_CUDA_CHECK(cudaStreamSynchronize(s));
   }
   return check_device_error(d);
+}
+
+// Host-only: size, format and colour description of the picture an access unit holds (headers only, microseconds).
+int b200_probe_access_unit(const uint8_t* au, size_t size, uint64_t max_pixels, b200_image_info* info) {
+  if (!au || !info) return set_error(B200_E_INVALID, "null argument");
+  PictureHeaders H; ParseLimits lim; lim.max_image_size_pixels = max_pixels;
+  int rc = parse_headers(au, size, lim, H);
+  if (rc) return rc;
+  memset(info, 0, sizeof *info);
+  info->width = info->tile_width = H.desc.out_w; info->height = info->tile_height = H.desc.out_h;
+  info->chroma = H.desc.chroma ? B200_CHROMA_420 : B200_CHROMA_MONO; info->bit_depth = H.desc.bit_depth;
+  info->colour_primaries = H.colour_primaries; info->transfer_characteristics = H.transfer_characteristics;
+  info->matrix_coefficients = H.matrix_coefficients; info->full_range = H.full_range;
+  return B200_OK;
 }
 
 // Page-locked host memory for the outputs of b200_decode_grid_to_rgb_host / b200_decoder_read_planes (DMA target).

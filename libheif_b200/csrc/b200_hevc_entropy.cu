@@ -90,9 +90,10 @@ struct DevSync {
 #ifndef B200_ENTROPY_MIN_BLOCKS
 #define B200_ENTROPY_MIN_BLOCKS 1
 #endif
+template <class Cfg>
 __global__ void __launch_bounds__(EWARPS * 32, B200_ENTROPY_MIN_BLOCKS) hevc_entropy_kernel(const EntropyBatch b) {
   __shared__ __align__(8) syn::U2 s_ctx[EWARPS][syn::CTX_COUNT];   // context variables: one state-table entry each
-  __shared__ syn::Decoder s_dec[EWARPS];                    // per-warp decoder state (see run_substream)
+  __shared__ syn::DecoderT<Cfg> s_dec[EWARPS];                    // per-warp decoder state (see run_substream)
   for (int i = threadIdx.x; i < 64; i += blockDim.x) { syn::s_kLps4[i] = syn::d_kLps4[i]; syn::s_kTransLps[i] = syn::d_kTransLps[i]; }
   for (int i = threadIdx.x; i < 134; i += blockDim.x) syn::s_kInitI[i] = syn::d_kInitI[i];
   for (int i = threadIdx.x; i < 256; i += blockDim.x) syn::s_kNextState[i] = syn::d_kNextState[i];
@@ -130,7 +131,7 @@ __global__ void __launch_bounds__(EWARPS * 32, B200_ENTROPY_MIN_BLOCKS) hevc_ent
     sync.progress = b.progress + ep.progress_base; sync.sub_done = b.sub_done + ep.sub_base; sync.error_flag = b.error_flag;
     sync.queue = b.queue; sync.qtail = b.qtail; sync.deps = b.deps;
     sync.dense_tu = sync.dense_coef = sync.dense_tu_cap = sync.dense_coef_cap = 0; sync.end_bit_position = 0;
-    syn::run_substream(s_dec[slot_w], ep.sp, ep.pb, b.subs + ep.sub_base, (int)(item - 1u - ep.sub_base), ctx, sync);
+    syn::run_substream<Cfg>(s_dec[slot_w], ep.sp, ep.pb, b.subs + ep.sub_base, (int)(item - 1u - ep.sub_base), ctx, sync);
   }
 }
 
@@ -151,13 +152,15 @@ __global__ void entropy_stats_kernel(const EntropyBatch b, unsigned long long* o
 int launch_entropy(const EntropyBatch& b, cudaStream_t s) {
   if (b.nsubs <= 0) return B200_OK;
   int dev = 0, sms = 148; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  int occ = 1; cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, hevc_entropy_kernel, EWARPS * 32, 0);
+  // b.common: every picture of the batch has the CfgCommon parameter combination -> the specialised (smaller) kernel
+  auto kern = b.common ? hevc_entropy_kernel<syn::CfgCommon> : hevc_entropy_kernel<syn::CfgRuntime>;
+  int occ = 1; cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, EWARPS * 32, 0);
   if (occ < 1) occ = 1;
   if (b.blocks_per_sm > 0 && b.blocks_per_sm < occ) occ = b.blocks_per_sm;
   if (const char* e = getenv("B200_ENTROPY_BLOCKS_PER_SM")) { const int v = atoi(e); if (v >= 1 && v < occ) occ = v; }   // tuning knob
   const int want = (b.nsubs + EWARPS - 1) / EWARPS;
   const int grid = want < sms * occ ? want : sms * occ;
-  hevc_entropy_kernel<<<grid, EWARPS * 32, 0, s>>>(b);
+  kern<<<grid, EWARPS * 32, 0, s>>>(b);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return set_error(B200_E_CUDA, "entropy launch: %s", cudaGetErrorString(e));
   return B200_OK;

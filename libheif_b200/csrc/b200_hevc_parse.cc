@@ -462,7 +462,7 @@ int parse_access_unit(const uint8_t* data, size_t size, const ParseLimits& limit
   syn::U2 ctx[syn::CTX_COUNT];
   for (size_t i = 0; i < H.subs.size(); i++) {
     syn::Decoder dec;
-    int e = syn::run_substream(dec, sp, pb, H.subs.data(), (int)i, ctx, sync);
+    int e = syn::run_substream<syn::CfgRuntime>(dec, sp, pb, H.subs.data(), (int)i, ctx, sync);
     if (e == syn::SYN_E_OVERFLOW) return set_error(B200_E_BITSTREAM, "slice data produces more transform units / coefficients than the picture can hold");
     if (e) return set_error(B200_E_BITSTREAM, "corrupt slice data (sub-stream %zu, CTB %u..%u)", i, H.subs[i].ctb_begin, H.subs[i].ctb_end);
     // cross-check of the entry points: the next sub-stream of the same segment starts where this one ended

@@ -279,7 +279,22 @@ enum { SYN_OK = 0, SYN_E_BITSTREAM = 1, SYN_E_OVERFLOW = 2 };
 struct SaoRaw { int8_t type[3], band[3], eo[3]; int8_t off[3][4]; };
 
 // ---------------------------------------------------------------------------------------------- sub-stream decoder
-struct Decoder {
+// Compile-time stream profile: a value >= 0 replaces the SeqParams field of the same name by a constant.  The device
+// front-end instantiates the decoder twice: CfgRuntime (anything the parser accepts) and CfgCommon, the parameter
+// combination of x265-produced HEIC files (and of libheif/examples/example.heic: 4:2:0 8 bit, min CB 8, TB 4..32, no
+// transform skip, cu_qp_delta + sign data hiding + SAO on, WPP); the kernel's speed is set by its instruction-cache
+// footprint (profiles/README.md), and the constants remove ~5 KB of it.  The host front-end uses CfgRuntime.
+struct CfgRuntime { enum : int { chroma = -1, bd = -1, log2_min_cb = -1, log2_min_tb = -1, log2_max_tb = -1, transform_skip = -1, cu_qp_delta = -1, sign_hiding = -1, sao_enabled = -1, wpp = -1, dense = -1 }; };
+struct CfgCommon { enum : int { chroma = 1, bd = 8, log2_min_cb = 3, log2_min_tb = 2, log2_max_tb = 5, transform_skip = 0, cu_qp_delta = 1, sign_hiding = 1, sao_enabled = 1, wpp = 1, dense = 0 }; };
+B200_HD inline bool matches_common(const SeqParams& q) {
+  return q.chroma == 1 && q.bd == 8 && q.log2_min_cb == 3 && q.log2_min_tb == 2 && q.log2_max_tb == 5 && !q.transform_skip && q.cu_qp_delta == 1 && q.sign_hiding == 1 &&
+         q.sao_enabled == 1 && q.wpp == 1 && q.dense == 0;
+}
+#define B200_SPC(f) ((int)Cfg::f >= 0 ? (int)Cfg::f : (int)sp->f)
+#define B200_SPR(f) ((int)Cfg::f >= 0 ? (int)Cfg::f : (int)sp.f)
+
+template <class Cfg>
+struct DecoderT {
   const SeqParams* sp; PicBuffers pb; const Substream* ss;
   Cabac cabac; CabacStream stream; CtxPtr ctx;    // ctx: CTX_COUNT context states (caller-provided storage)
   int is_dqp_coded, dqp_val, qpy_prev_qg, last_cu_qpy, first_qg, cur_qpy, err;
@@ -316,11 +331,11 @@ struct Decoder {
       B200_NOUNROLL for (int c = 0; c < 3; c++) dsto[c] = B200_LD_SHARED(o + c);
       return;
     }
-    B200_NOUNROLL for (int c = 0; c < (sp->chroma ? 3 : 1); c++) {
+    B200_NOUNROLL for (int c = 0; c < (B200_SPC(chroma) ? 3 : 1); c++) {
       if ((c == 0 && !ss->sao_luma) || (c > 0 && !ss->sao_chroma)) continue;
       if (c < 2) { int t = 0; if (dbin(CTX_SAO_TYPE)) t = dbypass() ? 2 : 1; ci.sao[c].type = (uint8_t)t; } else ci.sao[2].type = ci.sao[1].type;
       if (!ci.sao[c].type) continue;
-      const int cmax = (1 << (imin(sp->bd, 10) - 5)) - 1;
+      const int cmax = (1 << (imin(B200_SPC(bd), 10) - 5)) - 1;
       int av[4];
       B200_NOUNROLL for (int i = 0; i < 4; i++) { int v = 0; B200_NOUNROLL while (v < cmax && dbypass()) v++; av[i] = v; }
       const int sc = c == 0 ? sp->sao_scale_luma : sp->sao_scale_chroma;
@@ -342,7 +357,7 @@ struct Decoder {
     int qa = qpy_prev_qg, qb = qpy_prev_qg;
     if (avail(xqg - 1, yqg) && ((xqg - 1) & cm) == (xqg & cm)) qa = pb.qp8[(yqg >> 3) * sp->w8 + ((xqg - 1) >> 3)];   // same CTB: own data
     if (avail(xqg, yqg - 1) && ((yqg - 1) & cm) == (yqg & cm)) qb = pb.qp8[((yqg - 1) >> 3) * sp->w8 + (xqg >> 3)];
-    const int pred = (qa + qb + 1) >> 1, qbd = 6 * (sp->bd - 8);
+    const int pred = (qa + qb + 1) >> 1, qbd = 6 * (B200_SPC(bd) - 8);
     cur_qpy = ((pred + dqp_val + 52 + 2 * qbd) % (52 + qbd)) - qbd;
   }
 
@@ -351,10 +366,10 @@ struct Decoder {
     const int n = 1 << log2n;
     // Local copies: their addresses never escape, so they live in registers.
     Cabac cb_ = cabac; const CtxPtr cx = ctx;
-    const int sign_hiding = sp->sign_hiding;
+    const int sign_hiding = B200_SPC(sign_hiding);
     CoefEntry* const coef_out = pb.coefs; uint32_t cn = coef_n; const uint32_t ccap = coef_cap;
     tskip = 0;
-    if (sp->transform_skip && log2n == 2) tskip = cb_.bin(ctx_at(cx, CTX_TSKIP + (c ? 1 : 0)), stream);
+    if (B200_SPC(transform_skip) && log2n == 2) tskip = cb_.bin(ctx_at(cx, CTX_TSKIP + (c ? 1 : 0)), stream);
     const int cmax = (log2n << 1) - 1;
     int off, shift;
     if (c == 0) { off = 3 * (log2n - 2) + ((log2n - 1) >> 2); shift = (log2n + 1) >> 2; } else { off = 15; shift = log2n - 2; }
@@ -485,13 +500,13 @@ struct Decoder {
   }
 
   B200_HDI void transform_unit(const Cu& cu, int x0, int y0, int log2n, int blk, int cbf_l, int cbf_cb, int cbf_cr, int pcb, int pcr) {
-    const int cbf_c = sp->chroma ? (log2n > 2 ? (cbf_cb | cbf_cr) : (pcb | pcr)) : 0;
-    if ((cbf_l || cbf_c) && sp->cu_qp_delta && !is_dqp_coded) {
+    const int cbf_c = B200_SPC(chroma) ? (log2n > 2 ? (cbf_cb | cbf_cr) : (pcb | pcr)) : 0;
+    if ((cbf_l || cbf_c) && B200_SPC(cu_qp_delta) && !is_dqp_coded) {
       int v = 0;
       B200_NOUNROLL while (v < 5 && dbin(CTX_QP_DELTA + (v ? 1 : 0))) v++;
       if (v == 5) { int k = 0; B200_NOUNROLL while (k < 16 && dbypass()) { v += 1 << k; k++; } v += (int)dbits(k); }
       if (v && dbypass()) v = -v;
-      { const int half = 3 * (sp->bd - 8); if (v < -(26 + half) || v > 25 + half) { err = SYN_E_BITSTREAM; return; } }   // CuQpDeltaVal range (7.4.9.10)
+      { const int half = 3 * (B200_SPC(bd) - 8); if (v < -(26 + half) || v > 25 + half) { err = SYN_E_BITSTREAM; return; } }   // CuQpDeltaVal range (7.4.9.10)
       is_dqp_coded = 1; dqp_val = v;
       derive_qpy(cu.x0, cu.y0);
     }
@@ -500,7 +515,7 @@ struct Decoder {
     const uint32_t coef0 = coef_n;
     int ts_l = 0, ts_cb = 0, ts_cr = 0, nl = 0, ncb = 0, ncr = 0;
     int chroma_here = 0, ccb = 0, ccr = 0;
-    if (sp->chroma) {
+    if (B200_SPC(chroma)) {
       if (log2n > 2) { chroma_here = 1; ccb = cbf_cb; ccr = cbf_cr; }
       else if (blk == 3) { chroma_here = 1; ccb = pcb; ccr = pcr; }      // 4x4 chroma blocks of the parent 8x8 node
     }
@@ -543,11 +558,11 @@ struct Decoder {
         const int blk = depth ? (j >> (2 * (levels - depth))) & 3 : 0;
         const int pcb = depth ? (int)((cbm >> (depth - 1)) & 1) : 0, pcr = depth ? (int)((crm >> (depth - 1)) & 1) : 0;
         int split;
-        if (log2n <= sp->log2_max_tb && log2n > sp->log2_min_tb && depth < max_depth && !(cu.nxn && depth == 0)) split = dbin(CTX_SPLIT_TR + 5 - log2n);
-        else split = (log2n > sp->log2_max_tb || (cu.nxn && depth == 0)) ? 1 : 0;
+        if (log2n <= B200_SPC(log2_max_tb) && log2n > B200_SPC(log2_min_tb) && depth < max_depth && !(cu.nxn && depth == 0)) split = dbin(CTX_SPLIT_TR + 5 - log2n);
+        else split = (log2n > B200_SPC(log2_max_tb) || (cu.nxn && depth == 0)) ? 1 : 0;
         if (split && log2n <= 2) { err = SYN_E_BITSTREAM; break; }
         int cb = 0, cr = 0;
-        if (sp->chroma) {
+        if (B200_SPC(chroma)) {
           if (log2n > 2) {
             B200_NOUNROLL for (int k = 0; k < 2; k++) {
               int f = 0;
@@ -591,8 +606,8 @@ struct Decoder {
   B200_HDI void coding_unit(int x0, int y0, int log2cb, int depth) {
     Cu cu; cu.x0 = x0; cu.y0 = y0; cu.log2cb = log2cb; cu.nxn = 0; cu.cmode = 0;
     const int n = 1 << log2cb;
-    if (log2cb == sp->log2_min_cb) cu.nxn = !dbin(CTX_PART_MODE);
-    if (cu.nxn && log2cb == 3 && sp->log2_min_tb > 2) { err = SYN_E_BITSTREAM; return; }
+    if (log2cb == B200_SPC(log2_min_cb)) cu.nxn = !dbin(CTX_PART_MODE);
+    if (cu.nxn && log2cb == 3 && B200_SPC(log2_min_tb) > 2) { err = SYN_E_BITSTREAM; return; }
     const int np = cu.nxn ? 4 : 1, pbs = cu.nxn ? n / 2 : n;
     int prev[4], mi[4] = {0, 0, 0, 0}, rem[4] = {0, 0, 0, 0};
     B200_NOUNROLL for (int i = 0; i < np; i++) prev[i] = dbin(CTX_PREV_INTRA);
@@ -603,12 +618,12 @@ struct Decoder {
       cu.lmode[i] = m;
       B200_NOUNROLL for (int yy = 0; yy < pbs; yy += 4) B200_NOUNROLL for (int xx = 0; xx < pbs; xx += 4) pb.ipm4[((py + yy) >> 2) * sp->w4 + ((px + xx) >> 2)] = (uint8_t)m;
     }
-    if (sp->chroma) {
+    if (B200_SPC(chroma)) {
       int v = 4; if (dbin(CTX_CHROMA_PRED)) v = (int)dbits(2);
       if (v == 4) cu.cmode = cu.lmode[0]; else { cu.cmode = B200_T(kChromaTab)[v]; if (cu.cmode == cu.lmode[0]) cu.cmode = 34; }
     }
     B200_NOUNROLL for (int yy = 0; yy < n; yy += 8) B200_NOUNROLL for (int xx = 0; xx < n; xx += 8) pb.cd8[((y0 + yy) >> 3) * sp->w8 + ((x0 + xx) >> 3)] = (uint8_t)depth;
-    if (!sp->cu_qp_delta) cur_qpy = ss->slice_qp; else derive_qpy(x0, y0);
+    if (!B200_SPC(cu_qp_delta)) cur_qpy = ss->slice_qp; else derive_qpy(x0, y0);
     transform_tree(cu, sp->max_th_depth_intra + cu.nxn);
     B200_NOUNROLL for (int yy = 0; yy < n; yy += 8) B200_NOUNROLL for (int xx = 0; xx < n; xx += 8) pb.qp8[((y0 + yy) >> 3) * sp->w8 + ((x0 + xx) >> 3)] = (int8_t)cur_qpy;
     last_cu_qpy = cur_qpy;
@@ -617,7 +632,7 @@ struct Decoder {
   // -------- 7.3.8.4
   // coding_quadtree (7.3.8.4) of one CTB, iteratively over minimum coding blocks in z-order (same walk as transform_tree)
   B200_HDI void coding_quadtree(int xc, int yc) {
-    const int log2min = sp->log2_min_cb, levels = sp->log2ctb - log2min, total = 1 << (2 * levels);
+    const int log2min = B200_SPC(log2_min_cb), levels = sp->log2ctb - log2min, total = 1 << (2 * levels);
     B200_NOUNROLL for (int i = 0; i < total && !err;) {
       int depth = node_depth((unsigned)i, levels);
       B200_NOUNROLL for (;;) {
@@ -631,7 +646,7 @@ struct Decoder {
           if (avail(x0, y0 - 1) && ld_cell(pb.cd8 + ((y0 - 1) >> 3) * sp->w8 + (x0 >> 3), y0 - 1) > depth) inc++;
           split = dbin(CTX_SPLIT_CU + inc);
         } else split = log2cb > log2min;
-        if (sp->cu_qp_delta && log2cb >= sp->qg_log2) {
+        if (B200_SPC(cu_qp_delta) && log2cb >= sp->qg_log2) {
           is_dqp_coded = 0; dqp_val = 0;
           if (!split || log2cb == sp->qg_log2) { if (first_qg) { qpy_prev_qg = ss->slice_qp; first_qg = 0; } else qpy_prev_qg = last_cu_qpy; }
         }
@@ -652,9 +667,9 @@ struct Decoder {
     up_ok = ry > 0 && pb.ctu_slice[addr - sp->wctb] == (uint16_t)ss->slice_idx;
     CtuInfo& ci = pb.ctus[addr];
     ci.slice_idx = (uint16_t)ss->slice_idx;
-    if (!sp->dense) { tu_n = (uint32_t)addr * (uint32_t)sp->tu_slots; tu_cap = tu_n + (uint32_t)sp->tu_slots; coef_n = (uint32_t)addr * (uint32_t)sp->coef_slots; coef_cap = coef_n + (uint32_t)sp->coef_slots; }
+    if (!B200_SPC(dense)) { tu_n = (uint32_t)addr * (uint32_t)sp->tu_slots; tu_cap = tu_n + (uint32_t)sp->tu_slots; coef_n = (uint32_t)addr * (uint32_t)sp->coef_slots; coef_cap = coef_n + (uint32_t)sp->coef_slots; }
     const uint32_t t0 = tu_n;
-    if (sp->sao_enabled) parse_sao(rx, ry, ci);
+    if (B200_SPC(sao_enabled)) parse_sao(rx, ry, ci);
     else for (int c = 0; c < 3; c++) { ci.sao[c].type = 0; ci.sao[c].band_or_class = 0; B200_NOUNROLL for (int k = 0; k < 4; k++) ci.sao[c].offset[k] = 0; }
     // 4x4 luma transform units only OR their edge bits: clear this CTB's flags first
     { const int b0x = rx << (sp->log2ctb - 3), b0y = ry << (sp->log2ctb - 3), nb = 1 << (sp->log2ctb - 3);
@@ -664,18 +679,20 @@ struct Decoder {
   }
 };
 
+typedef DecoderT<CfgRuntime> Decoder;
+
 // Decodes one sub-stream.  `Sync` supplies wait_row(row, need) -- block until `need` CTBs of CTB row `row` are done --
 // publish_row(row, done) and wait_substream(index); on the host (sequential order) they are no-ops.
-template <class Sync>
+template <class Cfg, class Sync>
 // `d` is caller-provided storage: on the device it lives in SHARED memory -- a lone lane's local memory uses 4 bytes of
 // every 128-byte line, so ~30 resident decoders with their state on the stack overflow L1 (measured: the SM's
 // throughput stopped growing at 8 warps).
-B200_HD int run_substream(Decoder& d, const SeqParams& sp, const PicBuffers& pb, const Substream* all, int index, CtxPtr ctx, Sync& sync) {
+B200_HD int run_substream(DecoderT<Cfg>& d, const SeqParams& sp, const PicBuffers& pb, const Substream* all, int index, CtxPtr ctx, Sync& sync) {
   const Substream& ss = all[index];
   d.sp = &sp; d.pb = pb; d.ss = &ss; d.ctx = ctx; d.err = SYN_OK;
   d.is_dqp_coded = 0; d.dqp_val = 0; d.qpy_prev_qg = ss.slice_qp; d.last_cu_qpy = ss.slice_qp; d.first_qg = 1; d.cur_qpy = ss.slice_qp;
   d.tu_n = 0; d.coef_n = 0; d.tu_cap = 0; d.coef_cap = 0;
-  if (sp.dense) {                                             // host: continue the picture-wide cursors
+  if (B200_SPR(dense)) {                                             // host: continue the picture-wide cursors
     d.tu_n = sync.dense_tu; d.coef_n = sync.dense_coef; d.tu_cap = sync.dense_tu_cap; d.coef_cap = sync.dense_coef_cap;
   }
   const int rx0 = (int)(ss.ctb_begin % (uint32_t)sp.wctb), ry0 = (int)(ss.ctb_begin / (uint32_t)sp.wctb);
@@ -687,7 +704,7 @@ B200_HD int run_substream(Decoder& d, const SeqParams& sp, const PicBuffers& pb,
     d.last_cu_qpy = (int)(int8_t)B200_LD_SHARED(st + CTX_COUNT); d.first_qg = 0;
   }
   if (ss.init_contexts) init_contexts(ctx, ss.slice_qp);
-  if (sp.wpp && rx0 == 0 && (!ss.init_contexts || ss.prev >= 0) && ss.ctb_begin != ss.slice_addr_rs) {
+  if (B200_SPR(wpp) && rx0 == 0 && (!ss.init_contexts || ss.prev >= 0) && ss.ctb_begin != ss.slice_addr_rs) {
     // first CTB of a row inside a slice: take the state stored after the 2nd CTB of the row above when that CTB is
     // available (same slice), otherwise initialise (or, for a dependent segment, keep the inherited state)
     const int xn = 1 << sp.log2ctb, yn = (ry0 - 1) << sp.log2ctb;
@@ -702,25 +719,25 @@ B200_HD int run_substream(Decoder& d, const SeqParams& sp, const PicBuffers& pb,
   B200_NOUNROLL for (uint32_t a = ss.ctb_begin; a < ss.ctb_end; a++) {
     const int rx = (int)(a % (uint32_t)sp.wctb), ry = (int)(a / (uint32_t)sp.wctb);
     if (ry > 0) sync.wait_row(ry - 1, rx + 1);                   // split_cu_flag context / SAO merge-up read the CTB above (same column)
-    if (sp.wpp && rx == 0 && a != ss.ctb_begin) {
+    if (B200_SPR(wpp) && rx == 0 && a != ss.ctb_begin) {
       // only reached without WPP sub-stream splitting (never: WPP rows are separate sub-streams); kept for safety
       d.first_qg = 1;
     }
-    if (!sp.wpp && rx == 0 && a != ss.ctb_begin) { /* QG state simply continues */ }
+    if (!B200_SPR(wpp) && rx == 0 && a != ss.ctb_begin) { /* QG state simply continues */ }
     d.decode_ctb((int)a);
     if (d.err) break;
-    if (sp.wpp && rx == 1) { uint8_t* st = pb.wpp_ctx + (size_t)ry * CTX_STRIDE; B200_NOUNROLL for (int i = 0; i < CTX_COUNT; i++) st[i] = (uint8_t)(ctx_ld(ctx_at(ctx, i)).y >> 24); }
+    if (B200_SPR(wpp) && rx == 1) { uint8_t* st = pb.wpp_ctx + (size_t)ry * CTX_STRIDE; B200_NOUNROLL for (int i = 0; i < CTX_COUNT; i++) st[i] = (uint8_t)(ctx_ld(ctx_at(ctx, i)).y >> 24); }
     const int end = d.cabac.terminate(d.stream);                          // end_of_slice_segment_flag
     const bool last = a + 1 == ss.ctb_end;
     if (end != ((last && ss.last_of_segment) ? 1 : 0)) { d.err = SYN_E_BITSTREAM; break; }
     if (last && !ss.last_of_segment) { if (!d.cabac.terminate(d.stream)) { d.err = SYN_E_BITSTREAM; break; } }   // end_of_subset_one_bit
     sync.publish_row(ry, rx + 1);
-    if (sp.wpp && rx == 1) sync.notify(ss.wake_ctb2);           // the row below may start (its context hand-over is stored)
+    if (B200_SPR(wpp) && rx == 1) sync.notify(ss.wake_ctb2);           // the row below may start (its context hand-over is stored)
     if (d.cabac.pos > pb.rbsp_size + 64u) { d.err = SYN_E_BITSTREAM; break; }
   }
   // end state for a dependent continuation + dense cursors
   { uint8_t* st = pb.end_state + (size_t)index * CTX_STRIDE; B200_NOUNROLL for (int i = 0; i < CTX_COUNT; i++) st[i] = (uint8_t)(ctx_ld(ctx_at(ctx, i)).y >> 24); st[CTX_COUNT] = (uint8_t)(int8_t)d.last_cu_qpy; }
-  if (sp.dense) { sync.dense_tu = d.tu_n; sync.dense_coef = d.coef_n; }
+  if (B200_SPR(dense)) { sync.dense_tu = d.tu_n; sync.dense_coef = d.coef_n; }
   sync.end_bit_position = d.cabac.bit_position();
   sync.finish_substream(index, d.err);
   if (!d.err) sync.notify(ss.wake_end);

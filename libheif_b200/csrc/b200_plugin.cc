@@ -13,8 +13,13 @@
 #include "b200_internal.h"
 #include "../../include/b200_heif_plugin_abi.h"
 #include <dlfcn.h>
+#include <chrono>
+#include <condition_variable>
 #include <deque>
+#include <map>
 #include <mutex>
+#include <thread>
+#include <tuple>
 #include <string>
 #include <vector>
 
@@ -112,7 +117,7 @@ struct DecInstance { std::vector<uint8_t> data; std::deque<uintptr_t> user; int 
 
 const char* dec_name() { return "b200 HEVC intra decoder (sm_100a CUDA kernels)"; }
 void dec_init() {}
-void dec_deinit() { std::lock_guard<std::mutex> l(g_pool_mu); for (auto& e : g_pool) b200_decoder_destroy(e.dec); g_pool.clear(); }
+void dec_deinit();
 int dec_supports(int format) { return format == B200H_COMPRESSION_HEVC ? 200 : 0; }          // libde265 reports 100, ffmpeg 90
 int dec_supports2(const b200h_format_description* f) { return f ? dec_supports(f->format) : 0; }
 b200h_error dec_new2(void** out, const b200h_decoder_options* o) {
@@ -144,34 +149,180 @@ b200h_error dec_push(void* p, const void* data, size_t n) { return dec_push2(p, 
 b200h_error dec_flush(void*) { return ok_err(); }
 void dec_set_strict(void* p, int f) { ((DecInstance*)p)->strict = f; }
 
+// ---- process-wide submission queue.  libheif decodes the tiles of a grid from up to max_decoding_threads threads, one
+// plugin instance and one decode_next_image2 call per tile (image-items/grid.cc:405-453, codecs/decoder.cc:538-562).  A
+// 1024x1024 tile cannot fill the GPU (its CABAC wavefront exposes ~16 runnable rows) and costs a full kernel sequence, so the
+// calls that are in flight at the same time are decoded as ONE batch: every caller parses its headers, allocates its
+// heif_image and enqueues {access unit, destination planes}; a worker thread takes whatever has arrived within a short
+// window, groups pictures of equal format, runs one batched decode per group, copies the canvas into a page-locked staging
+// buffer (one DMA) and wakes the callers, which copy their own tile into their planes in parallel and return.
+// B200_PLUGIN_BATCH=0 restores one decode per call.
+struct Request {
+  const uint8_t* au = nullptr; size_t size = 0; uint64_t max_pixels = 0;
+  b200_image_info info{};
+  uint8_t* pl[3] = {nullptr, nullptr, nullptr}; size_t st[3] = {0, 0, 0};
+  int rc = 0; std::string msg;
+  // filled by the worker: where this picture sits in the staging buffer
+  const uint8_t* src[3] = {nullptr, nullptr, nullptr}; size_t src_st[3] = {0, 0, 0};
+  int state = 0;          // 0 queued, 1 staged (caller copies), 2 failed
+  bool copied = false;
+};
+struct SubmitQueue {
+  std::mutex mu; std::condition_variable cv_worker, cv_done;
+  std::deque<Request*> q; std::thread worker; bool started = false, stop = false;
+  b200_decoder* dec = nullptr; uint8_t* staging = nullptr; size_t staging_cap = 0;
+  uint64_t batches = 0, pictures = 0, max_batch = 0;
+  // process exit without deinit_plugin (libheif only calls it from heif_deinit): stop the idle worker, leave the CUDA
+  // objects alone (the runtime may already be shutting down)
+  ~SubmitQueue() {
+    { std::lock_guard<std::mutex> l(mu); stop = true; }
+    cv_worker.notify_all();
+    if (started && worker.joinable()) worker.join();
+  }
+};
+SubmitQueue g_sq;
+
+bool batching_enabled() { const char* e = getenv("B200_PLUGIN_BATCH"); return !(e && atoi(e) == 0); }
+
+void fail_request(Request* r, int rc) { r->rc = rc; r->msg = b200_last_error(); r->state = 2; }
+
+// decode the requests of one format group; returns false if the batch as a whole failed (the caller retries one by one)
+bool decode_group(SubmitQueue& Q, std::vector<Request*>& g) {
+  const int n = (int)g.size();
+  std::vector<const uint8_t*> au((size_t)n); std::vector<size_t> sz((size_t)n);
+  uint64_t maxpx = 0;
+  for (int i = 0; i < n; i++) { au[(size_t)i] = g[(size_t)i]->au; sz[(size_t)i] = g[(size_t)i]->size; maxpx = std::max(maxpx, g[(size_t)i]->max_pixels); }
+  b200_image_info info;
+  int rc = b200_decoder_decode_grid(Q.dec, n, 1, au.data(), sz.data(), maxpx, 0, 0, &info, nullptr);
+  if (rc) { if (n == 1) fail_request(g[0], rc); return n == 1; }
+  const int bps = info.bit_depth > 8 ? 2 : 1, mono = info.chroma == B200_CHROMA_MONO;
+  const size_t yrow = (size_t)info.width * bps, crow = mono ? 0 : (size_t)((info.width + 1) / 2) * bps;
+  const size_t ch = mono ? 0 : (size_t)(info.height + 1) / 2;
+  const size_t need = yrow * info.height + 2 * crow * ch;
+  if (need > Q.staging_cap) {
+    if (Q.staging) b200_host_free(Q.staging);
+    Q.staging = nullptr; Q.staging_cap = 0;
+    void* p = nullptr;
+    if (b200_host_alloc(need + need / 4, &p)) { for (auto* r : g) fail_request(r, B200_E_CUDA); return true; }
+    Q.staging = (uint8_t*)p; Q.staging_cap = need + need / 4;
+  }
+  uint8_t* sy = Q.staging; uint8_t* scb = sy + yrow * info.height; uint8_t* scr = scb + crow * ch;
+  rc = b200_decoder_read_planes(Q.dec, sy, yrow, mono ? nullptr : scb, mono ? nullptr : scr, crow, nullptr);
+  if (rc) { if (n == 1) fail_request(g[0], rc); return n == 1; }
+  const int tw = info.tile_width;
+  for (int i = 0; i < n; i++) {
+    Request* r = g[(size_t)i];
+    r->src[0] = sy + (size_t)i * tw * bps; r->src_st[0] = yrow;
+    if (!mono) { r->src[1] = scb + (size_t)i * (tw / 2) * bps; r->src[2] = scr + (size_t)i * (tw / 2) * bps; r->src_st[1] = r->src_st[2] = crow; }
+    r->state = 1;
+  }
+  return true;
+}
+
+void worker_main() {
+  SubmitQueue& Q = g_sq;
+  std::unique_lock<std::mutex> lk(Q.mu);
+  for (;;) {
+    Q.cv_worker.wait(lk, [&] { return Q.stop || !Q.q.empty(); });
+    if (Q.stop) return;
+    // batching window: keep collecting while callers keep arriving (150 us of silence ends it, 3 ms at most)
+    const auto t0 = std::chrono::steady_clock::now();
+    size_t last = Q.q.size();
+    for (;;) {
+      Q.cv_worker.wait_for(lk, std::chrono::microseconds(150));
+      if (Q.q.size() == last || std::chrono::steady_clock::now() - t0 > std::chrono::milliseconds(3)) break;
+      last = Q.q.size();
+    }
+    std::vector<Request*> batch(Q.q.begin(), Q.q.end());
+    Q.q.clear();
+    lk.unlock();
+    if (!Q.dec) { int rc = b200_decoder_create(&Q.dec, 0); if (rc) { for (auto* r : batch) fail_request(r, rc); Q.dec = nullptr; } }
+    if (Q.dec) {
+      // groups of equal format (decode_grid needs equal tiles; 4:2:0 tiles of a multi-picture batch must have even sizes)
+      std::map<std::tuple<int, int, int, int>, std::vector<Request*>> groups;
+      for (auto* r : batch) {
+        const bool odd = r->info.chroma != B200_CHROMA_MONO && ((r->info.width | r->info.height) & 1);
+        groups[std::make_tuple(r->info.width, r->info.height, r->info.bit_depth * 4 + r->info.chroma, odd ? (int)(intptr_t)r : 0)].push_back(r);
+      }
+      for (auto& kv : groups) {
+        std::vector<Request*>& g = kv.second;
+        // one group at a time through the staging buffer: stage, wake the callers, wait until they have copied
+        std::vector<std::vector<Request*>> runs;
+        runs.push_back(g);
+        for (size_t ri = 0; ri < runs.size(); ri++) {
+          std::vector<Request*> run = runs[ri];
+          if (!decode_group(Q, run)) { for (auto* r : run) runs.push_back(std::vector<Request*>{r}); continue; }   // a bad tile must not fail its batch mates
+          lk.lock();
+          Q.batches++; Q.pictures += run.size(); Q.max_batch = std::max<uint64_t>(Q.max_batch, run.size());
+          Q.cv_done.notify_all();
+          Q.cv_done.wait(lk, [&] { for (auto* r : run) if (r->state == 1 && !r->copied) return false; return true; });
+          lk.unlock();
+        }
+      }
+    }
+    lk.lock();
+    Q.cv_done.notify_all();
+  }
+}
+
+void ensure_worker() {
+  SubmitQueue& Q = g_sq;
+  if (!Q.started) { Q.started = true; Q.stop = false; Q.worker = std::thread(worker_main); }
+}
+
 b200h_error dec_decode2(void* p, b200h_image** out_img, uintptr_t* out_user, const b200h_security_limits* limits) {
   DecInstance* d = (DecInstance*)p;
   *out_img = nullptr;
   if (d->data.empty()) return ok_err();
   if (out_user) *out_user = d->user.empty() ? 0 : d->user.front();
   if (!limits) limits = d->limits ? d->limits : (g_api.global_limits ? g_api.global_limits() : nullptr);
-  int rc = 0;
-  b200_decoder* dec = acquire_decoder(&rc);
-  if (!dec) { d->data.clear(); return from_b200(rc, false); }
-  const uint8_t* au = d->data.data(); size_t sz = d->data.size();
-  b200_image_info info;
-  rc = b200_decoder_decode_grid(dec, 1, 1, &au, &sz, limits ? limits->max_image_size_pixels : 0, 0, 0, &info, nullptr);
-  d->data.clear(); d->user.clear();
-  if (rc) { release_decoder(dec); return from_b200(rc, false); }
+  const uint64_t maxpx = limits ? limits->max_image_size_pixels : 0;
+  // 1. headers: size and format of the picture (host, microseconds); the heif_image is allocated by this thread
+  Request rq;
+  rq.au = d->data.data(); rq.size = d->data.size(); rq.max_pixels = maxpx;
+  int rc = b200_probe_access_unit(rq.au, rq.size, maxpx, &rq.info);
+  if (rc) { d->data.clear(); d->user.clear(); return from_b200(rc, false); }
+  const b200_image_info info = rq.info;
   const bool mono = info.chroma == B200_CHROMA_MONO;
   b200h_image* img = nullptr;
   b200h_error err = g_api.image_create(info.width, info.height, mono ? B200H_COLORSPACE_MONOCHROME : B200H_COLORSPACE_YCBCR, mono ? 0 : 1, &img);
-  if (err.code) { release_decoder(dec); return err; }
-  uint8_t* pl[3] = {nullptr, nullptr, nullptr}; size_t st[3] = {0, 0, 0};
+  if (err.code) { d->data.clear(); d->user.clear(); return err; }
   for (int c = 0; c < (mono ? 1 : 3) && !err.code; c++) {
     const int w = c ? (info.width + 1) / 2 : info.width, h = c ? (info.height + 1) / 2 : info.height;
     err = g_api.image_add_plane_safe(img, c, w, h, info.bit_depth, limits);
-    if (!err.code) pl[c] = g_api.image_get_plane2(img, c, &st[c]);
+    if (!err.code) rq.pl[c] = g_api.image_get_plane2(img, c, &rq.st[c]);
   }
-  if (err.code) { g_api.image_release(img); release_decoder(dec); return err; }
-  if (!mono && st[1] != st[2]) { g_api.image_release(img); release_decoder(dec); return make_err(B200H_ERR_DECODER_PLUGIN, 0, "chroma strides differ"); }
-  rc = b200_decoder_read_planes(dec, pl[0], st[0], pl[1], pl[2], st[1], nullptr);       // D2H straight into the heif_image planes
-  release_decoder(dec);
+  if (err.code) { g_api.image_release(img); d->data.clear(); d->user.clear(); return err; }
+  if (!mono && rq.st[1] != rq.st[2]) { g_api.image_release(img); d->data.clear(); d->user.clear(); return make_err(B200H_ERR_DECODER_PLUGIN, 0, "chroma strides differ"); }
+  // 2. decode: through the submission queue (batched with the other callers in flight), or directly
+  if (batching_enabled()) {
+    SubmitQueue& Q = g_sq;
+    std::unique_lock<std::mutex> lk(Q.mu);
+    ensure_worker();
+    Q.q.push_back(&rq);
+    Q.cv_worker.notify_one();
+    Q.cv_done.wait(lk, [&] { return rq.state != 0; });       // block inside the call: libheif re-polls without sleeping (decoder.cc:538-562)
+    lk.unlock();
+    if (rq.state == 1) {
+      const int bps = info.bit_depth > 8 ? 2 : 1;
+      for (int c = 0; c < (mono ? 1 : 3); c++) {
+        const int w = c ? (info.width + 1) / 2 : info.width, h = c ? (info.height + 1) / 2 : info.height;
+        for (int y = 0; y < h; y++) memcpy(rq.pl[c] + (size_t)y * rq.st[c], rq.src[c] + (size_t)y * rq.src_st[c], (size_t)w * bps);
+      }
+    }
+    lk.lock(); rq.copied = true; Q.cv_done.notify_all(); lk.unlock();
+    rc = rq.state == 1 ? 0 : rq.rc;
+    if (rc) b200::set_error(rc, "%s", rq.msg.c_str());
+  } else {
+    b200_decoder* dec = acquire_decoder(&rc);
+    if (dec) {
+      const uint8_t* au = rq.au; size_t sz = rq.size; b200_image_info i2;
+      rc = b200_decoder_decode_grid(dec, 1, 1, &au, &sz, maxpx, 0, 0, &i2, nullptr);
+      if (!rc) rc = b200_decoder_read_planes(dec, rq.pl[0], rq.st[0], rq.pl[1], rq.pl[2], rq.st[1], nullptr);       // D2H straight into the heif_image planes
+      release_decoder(dec);
+    }
+  }
+  d->data.clear(); d->user.clear();
   if (rc) { g_api.image_release(img); return from_b200(rc, false); }
   void* nclx = g_api.nclx_alloc();
   if (nclx) {
@@ -184,6 +335,16 @@ b200h_error dec_decode2(void* p, b200h_image** out_img, uintptr_t* out_user, con
   }
   *out_img = img;
   return ok_err();
+}
+void dec_deinit() {
+  { std::lock_guard<std::mutex> l(g_pool_mu); for (auto& e : g_pool) b200_decoder_destroy(e.dec); g_pool.clear(); }
+  SubmitQueue& Q = g_sq;
+  { std::lock_guard<std::mutex> l(Q.mu); Q.stop = true; }
+  Q.cv_worker.notify_all();
+  if (Q.started && Q.worker.joinable()) Q.worker.join();
+  Q.started = false;
+  if (Q.dec) { b200_decoder_destroy(Q.dec); Q.dec = nullptr; }
+  if (Q.staging) { b200_host_free(Q.staging); Q.staging = nullptr; Q.staging_cap = 0; }
 }
 b200h_error dec_decode_next(void* p, b200h_image** out, const b200h_security_limits* l) { return dec_decode2(p, out, nullptr, l); }
 b200h_error dec_decode(void* p, b200h_image** out) { return dec_decode2(p, out, nullptr, nullptr); }
@@ -313,5 +474,7 @@ b200h_plugin_info plugin_info = {1, 1 /* heif_plugin_type_decoder */, &g_decoder
 b200h_plugin_info b200_encoder_plugin_info = {1, 0 /* heif_plugin_type_encoder */, &g_encoder_plugin, nullptr};
 const b200h_decoder_plugin* b200_get_decoder_plugin(void) { return &g_decoder_plugin; }
 const b200h_encoder_plugin* b200_get_encoder_plugin(void) { return &g_encoder_plugin; }
+// batches / pictures / largest batch the submission queue has decoded so far (tests, bench)
+void b200_plugin_queue_stats(uint64_t out3[3]) { std::lock_guard<std::mutex> l(g_sq.mu); out3[0] = g_sq.batches; out3[1] = g_sq.pictures; out3[2] = g_sq.max_batch; }
 int b200_plugin_bind_libheif(void* h) { g_heif_handle = h; resolve_api(); return g_api.ok ? B200_OK : b200::set_error(B200_E_INVALID, "libheif entry points not found in the given handle"); }
 }

@@ -14,6 +14,12 @@ from oracle import bindings as ob  # noqa: E402
 from oracle import refheif as rh  # noqa: E402
 
 mode = sys.argv[1]
+if mode == "plugin-path-gpu":
+    # LIBHEIF_PLUGIN_PATH loading (libheif/plugins_unix.cc:33-119, init.cc:124-133): libheif dlopen()s every *.so of the directory and
+    # registers the table behind its `plugin_info` symbol -- nothing here calls heif_register_decoder_plugin
+    plugdir = tempfile.mkdtemp()
+    os.symlink(os.path.join(ROOT, "libheif_b200", "libb200heif.so"), os.path.join(plugdir, "libb200heif.so"))
+    os.environ["LIBHEIF_PLUGIN_PATH"] = plugdir
 h = rh.load()
 b200 = C.CDLL(os.path.join(ROOT, "libheif_b200", "libb200heif.so"))
 b200.b200_get_decoder_plugin.restype = C.c_void_p
@@ -60,6 +66,44 @@ own = rh.decode_file(os.path.join(tmp, "grid_own.heic"), decoder_id="b200-oracle
 res["grid_md5_own_writer"] = hashlib.md5(own.tobytes()).hexdigest()
 hw.write_heic(os.path.join(tmp, "single_own.heic"), aus[:1])
 res["single_own_shape"] = list(rh.decode_file(os.path.join(tmp, "single_own.heic"), decoder_id="b200-oracle").shape)
+if mode == "plugin-path-gpu":
+    h.heif_init.restype = rh.Err
+    h.heif_init.argtypes = [C.c_void_p]
+    rh.check(h.heif_init(None), "heif_init")
+    for name in ("single", "grid"):
+        a = rh.decode_file(os.path.join(tmp, name + ".heic"), decoder_id="b200", threads=8)
+        res[name + "_md5_gpu"] = hashlib.md5(a.tobytes()).hexdigest()
+    # concurrency: an 8x8 grid decoded from 64 libheif threads, one plugin instance per tile, all in flight at once
+    # (the shape of the reference's tests/test-race.go); the submission queue must batch them and stay bit-exact
+    aus64 = []
+    for k in range(64):
+        ty, tcb, tcr = synthetic_image(300 + k, 128, 128, 8, True)
+        aus64.append(hevc_enc.encode_intra(ty, tcb, tcr, bit_depth=8, log2_ctb_size=4 + k % 3, qp=22 + k % 9, wpp=k % 2, seed=0xB200 + k, vui_present=1,
+                                           colour_description_present=1, colour_primaries=1, transfer_characteristics=13, matrix_coefficients=6, full_range=1))
+    # (tiles of one grid share the parameter sets in a real file; here every tile gets its own hvcC-less item through separate files)
+    same = [hevc_enc.encode_intra(*synthetic_image(400 + k, 128, 128, 8, True), bit_depth=8, log2_ctb_size=5, qp=26, wpp=1, seed=0xB200, vui_present=1,
+                                  colour_description_present=1, colour_primaries=1, transfer_characteristics=13, matrix_coefficients=6, full_range=1) for k in range(64)]
+    hw.write_heic(os.path.join(tmp, "grid64.heic"), same, cols=8, rows=8)
+    cpu64 = rh.decode_file(os.path.join(tmp, "grid64.heic"), decoder_id="b200-oracle", threads=8)
+    res["grid64_md5_cpu"] = hashlib.md5(cpu64.tobytes()).hexdigest()
+    for rep in range(3):
+        g64 = rh.decode_file(os.path.join(tmp, "grid64.heic"), decoder_id="b200", threads=64)
+        res[f"grid64_md5_gpu_{rep}"] = hashlib.md5(g64.tobytes()).hexdigest()
+    st = (C.c_uint64 * 3)()
+    b200.b200_plugin_queue_stats(st)
+    res["queue_batches"], res["queue_pictures"], res["queue_max_batch"] = int(st[0]), int(st[1]), int(st[2])
+    # different pictures in flight at once (mixed CTB sizes / QPs / WPP): single-image files decoded from 16 Python threads
+    import threading
+    files = []
+    for k, a in enumerate(aus64[:16]):
+        f = os.path.join(tmp, f"one{k}.heic"); hw.write_heic(f, [a]); files.append(f)
+    want = [hashlib.md5(rh.decode_file(f, decoder_id="b200-oracle").tobytes()).hexdigest() for f in files]
+    got = [None] * len(files)
+    def work(i):
+        got[i] = hashlib.md5(rh.decode_file(files[i], decoder_id="b200").tobytes()).hexdigest()
+    th = [threading.Thread(target=work, args=(i,)) for i in range(len(files))]
+    [t.start() for t in th]; [t.join() for t in th]
+    res["mixed_ok"] = got == want
 if mode == "roundtrip-gpu":
     rh.check(h.heif_register_decoder_plugin(b200.b200_get_decoder_plugin()), "register decoder plugin")
     for name in ("single", "grid"):

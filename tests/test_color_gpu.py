@@ -138,10 +138,51 @@ def test_444_detour(cuda, case, fmt):
     assert np.array_equal(_as_bytes(out), want)
 
 
-def test_444_detour_limited_range_is_refused(cuda):
-    y, cb, cr, _ = random_ycbcr(5, 34, 18, 1, 8)
-    with pytest.raises(lb.B200Error):
-        lb.convert_colorspace(_img(y, cb, cr, None, 1, 8, (1, 13, 6, 0), cuda), 10, _geom(34, 18, [(3, 3, 30, 1, 16)], 1))
+@pytest.mark.parametrize("case", DETOUR)
+@pytest.mark.parametrize("fmt", [(8, (1, 13, 6, 0), 10, False), (8, (2, 2, 2, 0), 11, True), (10, (9, 16, 9, 0), 14, False), (12, (1, 13, 1, 0), 3, False)])
+def test_444_detour_limited_range(cuda, case, fmt):
+    """Limited-range 4:2:0 pictures at the reference's 4:4:4 conversion point: bilinear upsampling, then the range conversion
+    through RGB (Op_YCbCr_to_RGB -> Op_RGB_to_YCbCr to full range, pixelimage.cc:1187-1215), then the rest of the chain."""
+    w, h, ops = case
+    bpp, nclx, outc, alpha = fmt
+    y, cb, cr, a = random_ycbcr(77, w, h, 1, bpp, alpha=alpha)
+    want, ow, oh = oracle_postprocess(y, cb, cr, a, 1, bpp, nclx, ops, outc)
+    out = lb.convert_colorspace(_img(y, cb, cr, a, 1, bpp, nclx, cuda), outc, _geom(w, h, ops, 1))
+    got = np.concatenate([_as_bytes(t) for t in out]) if isinstance(out, (list, tuple)) else _as_bytes(out)
+    assert np.array_equal(got, want)
+
+
+from test_color_oracle import DETOUR_422  # noqa: E402
+
+
+@pytest.mark.parametrize("case", DETOUR_422)
+@pytest.mark.parametrize("fmt", [(8, (1, 13, 6, 1), 10, False), (8, (1, 13, 6, 0), 11, True), (10, (9, 16, 9, 0), 14, False), (12, (1, 13, 1, 1), 3, False)])
+def test_444_detour_422(cuda, case, fmt):
+    """4:2:2 pictures: rotate 90 / 270, 180 with odd height, horizontal mirror with odd width, crop with odd left convert to
+    4:4:4 first with Op_YCbCr422_bilinear_to_YCbCr444 (chroma_sampling.cc:784-905)."""
+    w, h, ops = case
+    bpp, nclx, outc, alpha = fmt
+    y, cb, cr, a = random_ycbcr(78, w, h, 2, bpp, alpha=alpha)
+    want, ow, oh = oracle_postprocess(y, cb, cr, a, 2, bpp, nclx, ops, outc)
+    out = lb.convert_colorspace(_img(y, cb, cr, a, 2, bpp, nclx, cuda), outc, _geom(w, h, ops, 2))
+    got = np.concatenate([_as_bytes(t) for t in out]) if isinstance(out, (list, tuple)) else _as_bytes(out)
+    assert np.array_equal(got, want)
+
+
+@pytest.mark.parametrize("mc", [0, 8, 16])
+@pytest.mark.parametrize("chroma", [1, 2, 3])
+@pytest.mark.parametrize("bpp,outc", [(8, 10), (8, 11), (8, 3), (10, 10), (10, 14), (10, 3), (12, 15)])
+@pytest.mark.parametrize("full", [0, 1])
+def test_special_matrices(cuda, mc, chroma, bpp, outc, full):
+    """matrix_coefficients 0 (GBR), 8 (YCgCo), 16 (YCgCo-Re): the special branches of Op_YCbCr_to_RGB (yuv2rgb.cc:222-262),
+    including which cases the dedicated 4:2:0 ops take instead -- 126 cases, the same the oracle is pinned on."""
+    for size in ((34, 18), (130, 70)):
+        w, h = size
+        y, cb, cr, a = random_ycbcr(4242 + mc + w, w, h, chroma, bpp, alpha=outc in (11, 15))
+        want, ow, oh = oracle_postprocess(y, cb, cr, a, chroma, bpp, (1, 13, mc, full), [], outc)
+        out = lb.convert_colorspace(_img(y, cb, cr, a, chroma, bpp, (1, 13, mc, full), cuda), outc)
+        got = np.concatenate([_as_bytes(t) for t in out]) if isinstance(out, (list, tuple)) else _as_bytes(out)
+        assert np.array_equal(got, want)
 
 
 @pytest.mark.parametrize("ops", GEOM[:6])

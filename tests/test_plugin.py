@@ -64,3 +64,18 @@ def test_decoder_plugin_drop_in_bit_exact(cuda):
     assert res["single_md5_gpu"] == res["single_md5_cpu"]
     assert res["grid_md5_gpu"] == res["grid_md5_cpu"]
     assert res["single_md5_default"] == res["single_md5_cpu"] and res["grid_md5_default"] == res["grid_md5_cpu"]
+
+
+@pytest.mark.gpu
+@pytest.mark.skipif(not have_ref, reason="oracle/_ref reference build not present")
+def test_plugin_path_loading_and_concurrent_instances(cuda):
+    """The reference loads libb200heif.so through LIBHEIF_PLUGIN_PATH (dlopen + `plugin_info`, plugins_unix.cc:103-119) and
+    decodes with it, bit-exact; 64 plugin instances in flight at once (heif_context_set_max_decoding_threads(64) on an 8x8
+    grid) go through the submission queue in batches and stay bit-exact; so do 16 different pictures decoded from 16 threads."""
+    res = child("plugin-path-gpu")
+    assert res["single_md5_gpu"] == res["single_md5_cpu"]
+    assert res["grid_md5_gpu"] == res["grid_md5_cpu"]
+    for rep in range(3):
+        assert res[f"grid64_md5_gpu_{rep}"] == res["grid64_md5_cpu"]
+    assert res["queue_max_batch"] > 1, res            # concurrent calls were really batched
+    assert res["mixed_ok"]
