@@ -113,7 +113,13 @@ b200_decoder* acquire_decoder(int* rc_out) {
 }
 void release_decoder(b200_decoder* d) { std::lock_guard<std::mutex> l(g_pool_mu); for (auto& e : g_pool) if (e.dec == d) e.busy = false; }
 
-struct DecInstance { std::vector<uint8_t> data; std::deque<uintptr_t> user; int strict = 0; const b200h_security_limits* limits = nullptr; };
+// One entry per push_data2 call: libheif pushes one access unit per call -- the header NALs + the slice NALs of a still image
+// (codecs/decoder.cc:441-446), one sample of a sequence track with its user_data (sequences/track_visual.cc:212-275) -- and
+// expects the pictures back in order, each with the user_data it came with.  (Intra-only streams: every access unit is an
+// independent picture; P/B slices are refused by the header parser.)  Parameter sets seen in earlier pushes stay valid for
+// later ones (a track pushes them once): they are kept and prepended.
+struct Pending { std::vector<uint8_t> au; uintptr_t user; };
+struct DecInstance { std::deque<Pending> q; std::vector<uint8_t> param_sets; std::vector<uint8_t> data; int strict = 0; const b200h_security_limits* limits = nullptr; };
 
 const char* dec_name() { return "b200 HEVC intra decoder (sm_100a CUDA kernels)"; }
 void dec_init() {}
@@ -133,16 +139,26 @@ b200h_error dec_push2(void* p, const void* data, size_t n, uintptr_t user) {
   DecInstance* d = (DecInstance*)p;
   const uint8_t* b = (const uint8_t*)data;
   // same framing check as decoder_libde265.cc:322-368: 4-byte big-endian NAL sizes
-  size_t pos = 0;
+  size_t pos = 0; bool has_slice = false, has_ps = false;
+  std::vector<uint8_t> ps;
   while (pos < n) {
     if (n - pos < 4) return make_err(B200H_ERR_DECODER_PLUGIN, B200H_SUBERR_END_OF_DATA, "truncated NAL size");
     uint32_t len = ((uint32_t)b[pos] << 24) | (b[pos + 1] << 16) | (b[pos + 2] << 8) | b[pos + 3];
     pos += 4;
     if (len > n - pos) return make_err(B200H_ERR_DECODER_PLUGIN, B200H_SUBERR_END_OF_DATA, "NAL size exceeds the pushed data");
+    if (len >= 2) {
+      const int type = (b[pos] >> 1) & 0x3f;
+      if (type < 32) has_slice = true;
+      else if (type <= 34) { has_ps = true; ps.insert(ps.end(), b + pos - 4, b + pos + len); }
+    }
     pos += len;
   }
-  d->data.insert(d->data.end(), b, b + n);
-  d->user.push_back(user);
+  if (has_ps) d->param_sets = ps;                               // the most recent VPS / SPS / PPS
+  if (!has_slice) return ok_err();                               // parameter sets only: nothing to decode yet
+  Pending e; e.user = user;
+  if (!has_ps) e.au = d->param_sets;                             // a later sample of a track: re-use the parameter sets
+  e.au.insert(e.au.end(), b, b + n);
+  d->q.push_back(std::move(e));
   return ok_err();
 }
 b200h_error dec_push(void* p, const void* data, size_t n) { return dec_push2(p, data, n, 0); }
@@ -165,7 +181,7 @@ struct Request {
   // filled by the worker: where this picture sits in the staging buffer
   const uint8_t* src[3] = {nullptr, nullptr, nullptr}; size_t src_st[3] = {0, 0, 0};
   int state = 0;          // 0 queued, 1 staged (caller copies), 2 failed
-  bool copied = false;
+  int* pending_copies = nullptr;   // staged pictures of the current run whose callers have not copied yet (worker's counter, guarded by the queue mutex)
 };
 struct SubmitQueue {
   std::mutex mu; std::condition_variable cv_worker, cv_done;
@@ -184,17 +200,20 @@ SubmitQueue g_sq;
 
 bool batching_enabled() { const char* e = getenv("B200_PLUGIN_BATCH"); return !(e && atoi(e) == 0); }
 
-void fail_request(Request* r, int rc) { r->rc = rc; r->msg = b200_last_error(); r->state = 2; }
+// Outcome of one request as the worker computed it; published to the caller (Request::state etc.) under the queue mutex only.
+struct Outcome { int state = 0; int rc = 0; std::string msg; const uint8_t* src[3] = {nullptr, nullptr, nullptr}; size_t src_st[3] = {0, 0, 0}; };
+void fail(Outcome& o, int rc) { o.state = 2; o.rc = rc; o.msg = b200_last_error(); }
 
 // decode the requests of one format group; returns false if the batch as a whole failed (the caller retries one by one)
-bool decode_group(SubmitQueue& Q, std::vector<Request*>& g) {
+bool decode_group(SubmitQueue& Q, std::vector<Request*>& g, std::vector<Outcome>& out) {
   const int n = (int)g.size();
+  out.assign((size_t)n, Outcome());
   std::vector<const uint8_t*> au((size_t)n); std::vector<size_t> sz((size_t)n);
   uint64_t maxpx = 0;
   for (int i = 0; i < n; i++) { au[(size_t)i] = g[(size_t)i]->au; sz[(size_t)i] = g[(size_t)i]->size; maxpx = std::max(maxpx, g[(size_t)i]->max_pixels); }
   b200_image_info info;
   int rc = b200_decoder_decode_grid(Q.dec, n, 1, au.data(), sz.data(), maxpx, 0, 0, &info, nullptr);
-  if (rc) { if (n == 1) fail_request(g[0], rc); return n == 1; }
+  if (rc) { if (n == 1) fail(out[0], rc); return n == 1; }
   const int bps = info.bit_depth > 8 ? 2 : 1, mono = info.chroma == B200_CHROMA_MONO;
   const size_t yrow = (size_t)info.width * bps, crow = mono ? 0 : (size_t)((info.width + 1) / 2) * bps;
   const size_t ch = mono ? 0 : (size_t)(info.height + 1) / 2;
@@ -203,18 +222,18 @@ bool decode_group(SubmitQueue& Q, std::vector<Request*>& g) {
     if (Q.staging) b200_host_free(Q.staging);
     Q.staging = nullptr; Q.staging_cap = 0;
     void* p = nullptr;
-    if (b200_host_alloc(need + need / 4, &p)) { for (auto* r : g) fail_request(r, B200_E_CUDA); return true; }
+    if (b200_host_alloc(need + need / 4, &p)) { for (auto& o : out) fail(o, B200_E_CUDA); return true; }
     Q.staging = (uint8_t*)p; Q.staging_cap = need + need / 4;
   }
   uint8_t* sy = Q.staging; uint8_t* scb = sy + yrow * info.height; uint8_t* scr = scb + crow * ch;
   rc = b200_decoder_read_planes(Q.dec, sy, yrow, mono ? nullptr : scb, mono ? nullptr : scr, crow, nullptr);
-  if (rc) { if (n == 1) fail_request(g[0], rc); return n == 1; }
+  if (rc) { if (n == 1) fail(out[0], rc); return n == 1; }
   const int tw = info.tile_width;
   for (int i = 0; i < n; i++) {
-    Request* r = g[(size_t)i];
-    r->src[0] = sy + (size_t)i * tw * bps; r->src_st[0] = yrow;
-    if (!mono) { r->src[1] = scb + (size_t)i * (tw / 2) * bps; r->src[2] = scr + (size_t)i * (tw / 2) * bps; r->src_st[1] = r->src_st[2] = crow; }
-    r->state = 1;
+    Outcome& o = out[(size_t)i];
+    o.src[0] = sy + (size_t)i * tw * bps; o.src_st[0] = yrow;
+    if (!mono) { o.src[1] = scb + (size_t)i * (tw / 2) * bps; o.src[2] = scr + (size_t)i * (tw / 2) * bps; o.src_st[1] = o.src_st[2] = crow; }
+    o.state = 1;
   }
   return true;
 }
@@ -236,32 +255,43 @@ void worker_main() {
     std::vector<Request*> batch(Q.q.begin(), Q.q.end());
     Q.q.clear();
     lk.unlock();
-    if (!Q.dec) { int rc = b200_decoder_create(&Q.dec, 0); if (rc) { for (auto* r : batch) fail_request(r, rc); Q.dec = nullptr; } }
-    if (Q.dec) {
-      // groups of equal format (decode_grid needs equal tiles; 4:2:0 tiles of a multi-picture batch must have even sizes)
-      std::map<std::tuple<int, int, int, int>, std::vector<Request*>> groups;
-      for (auto* r : batch) {
-        const bool odd = r->info.chroma != B200_CHROMA_MONO && ((r->info.width | r->info.height) & 1);
-        groups[std::make_tuple(r->info.width, r->info.height, r->info.bit_depth * 4 + r->info.chroma, odd ? (int)(intptr_t)r : 0)].push_back(r);
-      }
-      for (auto& kv : groups) {
-        std::vector<Request*>& g = kv.second;
-        // one group at a time through the staging buffer: stage, wake the callers, wait until they have copied
-        std::vector<std::vector<Request*>> runs;
-        runs.push_back(g);
-        for (size_t ri = 0; ri < runs.size(); ri++) {
-          std::vector<Request*> run = runs[ri];
-          if (!decode_group(Q, run)) { for (auto* r : run) runs.push_back(std::vector<Request*>{r}); continue; }   // a bad tile must not fail its batch mates
-          lk.lock();
-          Q.batches++; Q.pictures += run.size(); Q.max_batch = std::max<uint64_t>(Q.max_batch, run.size());
-          Q.cv_done.notify_all();
-          Q.cv_done.wait(lk, [&] { for (auto* r : run) if (r->state == 1 && !r->copied) return false; return true; });
-          lk.unlock();
+    int create_rc = 0;
+    if (!Q.dec) { create_rc = b200_decoder_create(&Q.dec, 0); if (create_rc) Q.dec = nullptr; }
+    // groups of equal format (decode_grid needs equal tiles; 4:2:0 tiles of a multi-picture batch must have even sizes).
+    // The requests' read-only fields (au, info) may be read here; their result fields are written under the mutex only.
+    std::map<std::tuple<int, int, int, int>, std::vector<Request*>> groups;
+    int odd_id = 0;
+    for (auto* r : batch) {
+      const bool odd = r->info.chroma != B200_CHROMA_MONO && ((r->info.width | r->info.height) & 1);
+      groups[std::make_tuple(r->info.width, r->info.height, r->info.bit_depth * 4 + r->info.chroma, odd ? ++odd_id : 0)].push_back(r);
+    }
+    for (auto& kv : groups) {
+      std::vector<std::vector<Request*>> runs;
+      runs.push_back(kv.second);
+      for (size_t ri = 0; ri < runs.size(); ri++) {
+        std::vector<Request*> run = runs[ri];
+        std::vector<Outcome> out;
+        if (!Q.dec) { out.assign(run.size(), Outcome()); for (auto& o : out) { o.state = 2; o.rc = create_rc; o.msg = b200_last_error(); } }
+        else if (!decode_group(Q, run, out)) { for (auto* r : run) runs.push_back(std::vector<Request*>{r}); continue; }   // a bad tile must not fail its batch mates
+        // publish, wake the callers, and wait until the staged ones have copied their planes out of the staging buffer.  A
+        // caller's Request lives on its stack and is gone once it has returned: after the publication the worker only looks at
+        // its own counter, which the callers decrement under the queue mutex.
+        int pending = 0;
+        lk.lock();
+        for (size_t i = 0; i < run.size(); i++) {
+          Request* r = run[i]; const Outcome& o = out[i];
+          r->rc = o.rc; r->msg = o.msg;
+          for (int c = 0; c < 3; c++) { r->src[c] = o.src[c]; r->src_st[c] = o.src_st[c]; }
+          if (o.state == 1) { r->pending_copies = &pending; pending++; }
+          r->state = o.state;
         }
+        Q.batches++; Q.pictures += run.size(); Q.max_batch = std::max<uint64_t>(Q.max_batch, run.size());
+        Q.cv_done.notify_all();
+        Q.cv_done.wait(lk, [&] { return pending == 0; });
+        lk.unlock();
       }
     }
     lk.lock();
-    Q.cv_done.notify_all();
   }
 }
 
@@ -273,27 +303,29 @@ void ensure_worker() {
 b200h_error dec_decode2(void* p, b200h_image** out_img, uintptr_t* out_user, const b200h_security_limits* limits) {
   DecInstance* d = (DecInstance*)p;
   *out_img = nullptr;
-  if (d->data.empty()) return ok_err();
-  if (out_user) *out_user = d->user.empty() ? 0 : d->user.front();
+  if (d->q.empty()) return ok_err();
+  d->data.swap(d->q.front().au);
+  if (out_user) *out_user = d->q.front().user;
+  d->q.pop_front();
   if (!limits) limits = d->limits ? d->limits : (g_api.global_limits ? g_api.global_limits() : nullptr);
   const uint64_t maxpx = limits ? limits->max_image_size_pixels : 0;
   // 1. headers: size and format of the picture (host, microseconds); the heif_image is allocated by this thread
   Request rq;
   rq.au = d->data.data(); rq.size = d->data.size(); rq.max_pixels = maxpx;
   int rc = b200_probe_access_unit(rq.au, rq.size, maxpx, &rq.info);
-  if (rc) { d->data.clear(); d->user.clear(); return from_b200(rc, false); }
+  if (rc) { d->data.clear(); return from_b200(rc, false); }
   const b200_image_info info = rq.info;
   const bool mono = info.chroma == B200_CHROMA_MONO;
   b200h_image* img = nullptr;
   b200h_error err = g_api.image_create(info.width, info.height, mono ? B200H_COLORSPACE_MONOCHROME : B200H_COLORSPACE_YCBCR, mono ? 0 : 1, &img);
-  if (err.code) { d->data.clear(); d->user.clear(); return err; }
+  if (err.code) { d->data.clear(); return err; }
   for (int c = 0; c < (mono ? 1 : 3) && !err.code; c++) {
     const int w = c ? (info.width + 1) / 2 : info.width, h = c ? (info.height + 1) / 2 : info.height;
     err = g_api.image_add_plane_safe(img, c, w, h, info.bit_depth, limits);
     if (!err.code) rq.pl[c] = g_api.image_get_plane2(img, c, &rq.st[c]);
   }
-  if (err.code) { g_api.image_release(img); d->data.clear(); d->user.clear(); return err; }
-  if (!mono && rq.st[1] != rq.st[2]) { g_api.image_release(img); d->data.clear(); d->user.clear(); return make_err(B200H_ERR_DECODER_PLUGIN, 0, "chroma strides differ"); }
+  if (err.code) { g_api.image_release(img); d->data.clear(); return err; }
+  if (!mono && rq.st[1] != rq.st[2]) { g_api.image_release(img); d->data.clear(); return make_err(B200H_ERR_DECODER_PLUGIN, 0, "chroma strides differ"); }
   // 2. decode: through the submission queue (batched with the other callers in flight), or directly
   if (batching_enabled()) {
     SubmitQueue& Q = g_sq;
@@ -310,7 +342,7 @@ b200h_error dec_decode2(void* p, b200h_image** out_img, uintptr_t* out_user, con
         for (int y = 0; y < h; y++) memcpy(rq.pl[c] + (size_t)y * rq.st[c], rq.src[c] + (size_t)y * rq.src_st[c], (size_t)w * bps);
       }
     }
-    lk.lock(); rq.copied = true; Q.cv_done.notify_all(); lk.unlock();
+    lk.lock(); if (rq.pending_copies) --*rq.pending_copies; Q.cv_done.notify_all(); lk.unlock();
     rc = rq.state == 1 ? 0 : rq.rc;
     if (rc) b200::set_error(rc, "%s", rq.msg.c_str());
   } else {
@@ -322,7 +354,7 @@ b200h_error dec_decode2(void* p, b200h_image** out_img, uintptr_t* out_user, con
       release_decoder(dec);
     }
   }
-  d->data.clear(); d->user.clear();
+  d->data.clear();
   if (rc) { g_api.image_release(img); return from_b200(rc, false); }
   void* nclx = g_api.nclx_alloc();
   if (nclx) {

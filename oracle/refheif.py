@@ -41,9 +41,10 @@ _h = None
 def load():
     global _h
     if _h is None:
-        p = os.path.join(ob.REF, "libheif_ref.so")
+        # B200_REF_LIB=libheif_ref_b200.so selects the second build with the GPU colour operation (oracle/Makefile n2)
+        p = os.path.join(ob.REF, os.environ.get("B200_REF_LIB", "libheif_ref.so"))
         if not os.path.exists(p):
-            raise RuntimeError("oracle/_ref/libheif_ref.so missing")
+            raise RuntimeError(f"{p} missing")
         h = C.CDLL(p, mode=C.RTLD_GLOBAL)
         h.heif_context_alloc.restype = C.c_void_p
         for name in ["heif_context_read_from_file", "heif_context_get_primary_image_handle", "heif_decode_image", "heif_image_create",
@@ -165,7 +166,7 @@ def decode_file(path, chroma=CHROMA_INTERLEAVED_RGB, decoder_id=None, threads=No
     st = C.c_int()
     p = h.heif_image_get_plane_readonly(img, CHANNEL_INTERLEAVED, C.byref(st))
     w, hh = h.heif_image_get_width(img, CHANNEL_INTERLEAVED), h.heif_image_get_height(img, CHANNEL_INTERLEAVED)
-    nch = 3 if chroma == CHROMA_INTERLEAVED_RGB else 4
+    nch = {10: 3, 11: 4, 12: 6, 13: 8, 14: 6, 15: 8}[chroma]        # bytes per pixel of the interleaved formats
     out = np.ctypeslib.as_array(p, shape=(hh, st.value))[:, :w * nch].copy()
     h.heif_image_release(img)
     h.heif_image_handle_release(hd)

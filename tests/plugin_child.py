@@ -111,4 +111,43 @@ if mode == "roundtrip-gpu":
         res[name + "_md5_gpu"] = hashlib.md5(a.tobytes()).hexdigest()
         bdef = rh.decode_file(os.path.join(tmp, name + ".heic"), threads=8)                        # priority selection: 200 > 500? (oracle reports 500)
         res[name + "_md5_default"] = hashlib.md5(bdef.tobytes()).hexdigest()
+if mode == "roundtrip-gpu":
+    # the call sequence of a sequence track (sequences/track_visual.cc:212-275) straight on the plugin table: one instance, one
+    # push_data2 per sample with its user_data (parameter sets only in the first), pictures come back in order with the
+    # user_data they were pushed with
+    FN = C.CFUNCTYPE
+    class DecPlugin(C.Structure):
+        _fields_ = [("api", C.c_int), ("name", C.c_void_p), ("init", C.c_void_p), ("deinit", C.c_void_p), ("supports", C.c_void_p),
+                    ("new_decoder", C.c_void_p), ("free_decoder", FN(None, C.c_void_p)), ("push_data", C.c_void_p), ("decode_image", C.c_void_p),
+                    ("set_strict", C.c_void_p), ("id_name", C.c_char_p), ("decode_next", C.c_void_p), ("min_version", C.c_uint32), ("supports2", C.c_void_p),
+                    ("new_decoder2", FN(rh.Err, C.POINTER(C.c_void_p), C.c_void_p)), ("push_data2", FN(rh.Err, C.c_void_p, C.c_char_p, C.c_size_t, C.c_size_t)),
+                    ("flush_data", FN(rh.Err, C.c_void_p)), ("decode_next2", FN(rh.Err, C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t), C.c_void_p))]
+    tab = C.cast(b200.b200_get_decoder_plugin(), C.POINTER(DecPlugin)).contents
+    frames = []
+    for k in range(3):
+        fy, fcb, fcr = synthetic_image(500 + k, 96, 64, 8, True)
+        frames.append(hevc_enc.encode_intra(fy, fcb, fcr, bit_depth=8, log2_ctb_size=4, qp=25 + k, wpp=1, seed=0xB200))
+    inst = C.c_void_p()
+    rh.check(tab.new_decoder2(C.byref(inst), None), "new_decoder2")
+    for k, au in enumerate(frames):
+        nals = hw.split_nals(au)
+        keep = nals if k == 0 else [x for x in nals if ((x[0] >> 1) & 0x3f) < 32]       # later samples carry no parameter sets
+        data = b"".join(len(x).to_bytes(4, "big") + x for x in keep)
+        rh.check(tab.push_data2(inst, data, len(data), 1000 + k), "push_data2")
+    rh.check(tab.flush_data(inst), "flush_data")
+    seq_ok, users = True, []
+    for k in range(3):
+        img, user = C.c_void_p(), C.c_size_t()
+        rh.check(tab.decode_next2(inst, C.byref(img), C.byref(user), None), "decode_next_image2")
+        users.append(int(user.value))
+        st = C.c_int()
+        ptr = h.heif_image_get_plane_readonly(img, rh.CHANNEL_Y, C.byref(st))
+        got_y = np.ctypeslib.as_array(ptr, shape=(64, st.value))[:, :96]
+        want_y = ob.ffmpeg_decode(frames[k], 1)[0][0]
+        seq_ok = seq_ok and np.array_equal(got_y.astype(np.uint16), np.asarray(want_y).astype(np.uint16))
+        h.heif_image_release(img)
+    img, user = C.c_void_p(), C.c_size_t()
+    rh.check(tab.decode_next2(inst, C.byref(img), C.byref(user), None), "decode_next_image2 (drained)")
+    res["sequence_users"] = users; res["sequence_planes_ok"] = bool(seq_ok); res["sequence_drained"] = img.value is None
+    tab.free_decoder(inst)
 print("RESULT " + json.dumps(res))

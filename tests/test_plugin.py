@@ -64,6 +64,8 @@ def test_decoder_plugin_drop_in_bit_exact(cuda):
     assert res["single_md5_gpu"] == res["single_md5_cpu"]
     assert res["grid_md5_gpu"] == res["grid_md5_cpu"]
     assert res["single_md5_default"] == res["single_md5_cpu"] and res["grid_md5_default"] == res["grid_md5_cpu"]
+    # sequence call order (intra-only): one picture per push_data2, user_data echoed in order, parameter sets reused
+    assert res["sequence_users"] == [1000, 1001, 1002] and res["sequence_planes_ok"] and res["sequence_drained"]
 
 
 @pytest.mark.gpu
