@@ -233,6 +233,15 @@ int b200_decode_grid_to_rgb_host(b200_decoder* dec, int cols, int rows, const ui
                                  uint64_t max_image_size_pixels, int canvas_w, int canvas_h, const b200_geometry* geom /* NULL = identity */,
                                  const b200_color_options* opt, void* out, size_t out_stride, b200_image_info* info);
 
+/* Throughput form: returns when the work is queued; the D2H of this picture overlaps the kernels of the next call (two device
+   RGB buffers, a second stream).  `out` must be page-locked.  b200_decoder_wait() blocks until everything submitted has
+   arrived in host memory and returns the first error.  (The reference has no asynchronous decode; a caller that decodes many
+   pictures -- heif-thumbnailer style batch jobs -- is who this is for.) */
+int b200_decode_grid_to_rgb_host_async(b200_decoder* dec, int cols, int rows, const uint8_t* const* au, const size_t* au_size,
+                                       uint64_t max_image_size_pixels, int canvas_w, int canvas_h, const b200_geometry* geom,
+                                       const b200_color_options* opt, void* out, size_t out_stride, b200_image_info* info);
+int b200_decoder_wait(b200_decoder* dec);
+
 /* Page-locked host memory: outputs of b200_decode_grid_to_rgb_host / b200_decoder_read_planes placed here are written by
    DMA directly (no bounce copy).  b200_host_register page-locks memory the caller owns (e.g. the planes of a heif_image,
    or a shared-memory mapping several ranks write their row bands into).  Counterpart in the reference: none (its planes

@@ -79,8 +79,9 @@ struct b200_decoder {
   std::vector<int> parse_rc; std::vector<std::string> parse_msg;
   DevBuf<PicDesc> pics; DevBuf<CtuInfo> ctus; DevBuf<TuCmd> tus; DevBuf<CoefEntry> coefs; DevBuf<SliceInfo> slices;
   DevBuf<int8_t> qp8; DevBuf<uint8_t> edge8; DevBuf<uint2> rows; DevBuf<unsigned> sync;   // sync: [0] ticket, [1] error flag, [2..] progress
-  DevBuf<uint8_t> rec; DevBuf<uint8_t> canvas; DevBuf<uint8_t> rgb; DevBuf<uint8_t> bounce;   // rgb / bounce: fused host entry point
-  cudaStream_t own = nullptr; cudaEvent_t ev_band[2] = {nullptr, nullptr};
+  DevBuf<uint8_t> rec; DevBuf<uint8_t> canvas; DevBuf<uint8_t> rgb2[2]; DevBuf<uint8_t> bounce;   // fused host entry points: two RGB buffers (D2H of one overlaps the kernels writing the other)
+  cudaStream_t own = nullptr, copy = nullptr; cudaEvent_t ev_band[2] = {nullptr, nullptr}, ev_k6[2] = {nullptr, nullptr}, ev_d2h[2] = {nullptr, nullptr};
+  unsigned* err_host = nullptr; int async_slot = 0; bool async_error = false;
   // device front-end (entropy decoding on the GPU)
   DevBuf<uint8_t> rbsp; DevBuf<syn::Substream> subs; DevBuf<unsigned> equeue; DevBuf<uint16_t> ctu_slice; DevBuf<EntropyPic> epics;
   DevBuf<uint8_t> ipm4, cd8, wpp_ctx, end_state; DevBuf<unsigned> esync; DevBuf<unsigned long long> ecount;
@@ -101,9 +102,13 @@ struct b200_decoder {
   ~b200_decoder() {
     delete pool;
     pics.release(); ctus.release(); tus.release(); coefs.release(); slices.release(); qp8.release(); edge8.release(); rows.release();
-    sync.release(); rec.release(); canvas.release(); rgb.release(); bounce.release();
+    sync.release(); rec.release(); canvas.release(); rgb2[0].release(); rgb2[1].release(); bounce.release();
     if (own) cudaStreamDestroy(own);
+    if (copy) cudaStreamDestroy(copy);
     for (auto& e : ev_band) if (e) cudaEventDestroy(e);
+    for (auto& e : ev_k6) if (e) cudaEventDestroy(e);
+    for (auto& e : ev_d2h) if (e) cudaEventDestroy(e);
+    if (err_host) cudaFreeHost(err_host);
     rbsp.release(); subs.release(); equeue.release(); ctu_slice.release(); epics.release(); ipm4.release(); cd8.release(); wpp_ctx.release();
     end_state.release(); esync.release(); ecount.release();
     for (auto& e : ev) if (e) cudaEventDestroy(e);
@@ -498,16 +503,25 @@ int b200_decoder_debug_read_tile(b200_decoder* d, int index, int stage, void* y,
   return B200_OK;
 }
 
-int b200_decode_grid_to_rgb_host(b200_decoder* d, int cols, int rows, const uint8_t* const* au, const size_t* au_size,
-                                 uint64_t max_pixels, int canvas_w, int canvas_h, const b200_geometry* geom,
-                                 const b200_color_options* opt, void* out, size_t out_stride, b200_image_info* info) {
-  if (!d || !opt || !out) return set_error(B200_E_INVALID, "null argument");
-  if (!d->own) B200_CUDA_CHECK(cudaStreamCreateWithFlags(&d->own, cudaStreamNonBlocking));
+// Common part of the fused entry points: decode -> colour conversion into one of the two device RGB buffers.
+static int decode_to_rgb_device(b200_decoder* d, int cols, int rows, const uint8_t* const* au, const size_t* au_size, uint64_t max_pixels, int canvas_w,
+                                int canvas_h, const b200_geometry* geom, const b200_color_options* opt, b200_image_info* info, int slot, size_t* rowb_out,
+                                size_t* pitch_out, int* out_h) {
+  if (!d->own) {
+    B200_CUDA_CHECK(cudaStreamCreateWithFlags(&d->own, cudaStreamNonBlocking));
+    B200_CUDA_CHECK(cudaStreamCreateWithFlags(&d->copy, cudaStreamNonBlocking));
+    for (int i = 0; i < 2; i++) { B200_CUDA_CHECK(cudaEventCreateWithFlags(&d->ev_k6[i], cudaEventDisableTiming)); B200_CUDA_CHECK(cudaEventCreateWithFlags(&d->ev_d2h[i], cudaEventDisableTiming)); }
+    B200_CUDA_CHECK(cudaHostAlloc((void**)&d->err_host, 2 * sizeof(unsigned), cudaHostAllocDefault));
+    d->err_host[0] = d->err_host[1] = 0;
+  }
   cudaStream_t s = d->own;
+  // the page-locked staging of the previous call must have left for the device before the host overwrites it
+  B200_CUDA_CHECK(cudaEventSynchronize(d->ev[1]));
   b200_image_info inf;
   int rc = b200_decoder_decode_grid(d, cols, rows, au, au_size, max_pixels, canvas_w, canvas_h, &inf, s);
   if (rc) return rc;
   if (info) *info = inf;
+  B200_CUDA_CHECK(cudaMemcpyAsync(&d->err_host[slot], d->sync.d + 1, sizeof(unsigned), cudaMemcpyDeviceToHost, s));   // this step's error flag (the next step clears the device copy)
   b200_planes pl; if ((rc = b200_decoder_get_planes(d, &pl))) return rc;
   b200_geometry g; if (geom) g = *geom; else b200_geometry_identity(inf.width, inf.height, &g);
   size_t bpp;
@@ -515,34 +529,54 @@ int b200_decode_grid_to_rgb_host(b200_decoder* d, int cols, int rows, const uint
     case B200_CHROMA_INTERLEAVED_RGB: bpp = 3; break; case B200_CHROMA_INTERLEAVED_RGBA: bpp = 4; break;
     case B200_CHROMA_INTERLEAVED_RRGGBB_BE: case B200_CHROMA_INTERLEAVED_RRGGBB_LE: bpp = 6; break;
     case B200_CHROMA_INTERLEAVED_RRGGBBAA_BE: case B200_CHROMA_INTERLEAVED_RRGGBBAA_LE: bpp = 8; break;
-    default: return set_error(B200_E_UNSUPPORTED, "b200_decode_grid_to_rgb_host needs an interleaved target");
+    default: return set_error(B200_E_UNSUPPORTED, "the fused entry points need an interleaved target");
   }
   const size_t rowb = (size_t)g.out_w * bpp, pitch = (rowb + 255) & ~(size_t)255;
-  if ((rc = d->rgb.reserve(pitch * g.out_h, false))) return rc;
-  if ((rc = b200_color_convert_device(&pl, &g, opt, d->rgb.d, nullptr, nullptr, pitch, s, nullptr))) return rc;
+  if ((rc = d->rgb2[slot].reserve(pitch * g.out_h, false))) return rc;
+  B200_CUDA_CHECK(cudaStreamWaitEvent(s, d->ev_d2h[slot], 0));           // the copy that last read this buffer has finished
+  if ((rc = b200_color_convert_device(&pl, &g, opt, d->rgb2[slot].d, nullptr, nullptr, pitch, s, nullptr))) return rc;
+  B200_CUDA_CHECK(cudaEventRecord(d->ev_k6[slot], s));
+  *rowb_out = rowb; *pitch_out = pitch; *out_h = g.out_h;
+  return B200_OK;
+}
+
+static bool is_page_locked(const void* p) {
+  cudaPointerAttributes pa{};
+  const bool pinned = cudaPointerGetAttributes(&pa, p) == cudaSuccess && (pa.type == cudaMemoryTypeHost || pa.type == cudaMemoryTypeManaged);
+  cudaGetLastError();
+  return pinned;
+}
+
+int b200_decode_grid_to_rgb_host(b200_decoder* d, int cols, int rows, const uint8_t* const* au, const size_t* au_size,
+                                 uint64_t max_pixels, int canvas_w, int canvas_h, const b200_geometry* geom,
+                                 const b200_color_options* opt, void* out, size_t out_stride, b200_image_info* info) {
+  if (!d || !opt || !out) return set_error(B200_E_INVALID, "null argument");
+  size_t rowb = 0, pitch = 0; int oh = 0;
+  int rc = decode_to_rgb_device(d, cols, rows, au, au_size, max_pixels, canvas_w, canvas_h, geom, opt, info, 0, &rowb, &pitch, &oh);
+  if (rc) return rc;
+  cudaStream_t s = d->own;
+  uint8_t* rgb = d->rgb2[0].d;
   // D2H: straight into the caller's buffer when it is page-locked (b200_host_alloc, cudaHostAlloc, cudaHostRegister);
   // pageable memory goes through a page-locked bounce buffer in row bands, the copy of band i overlapping the memcpy of
   // band i - 1 on the decoder's host threads
-  cudaPointerAttributes pa{};
-  const bool pinned = cudaPointerGetAttributes(&pa, out) == cudaSuccess && (pa.type == cudaMemoryTypeHost || pa.type == cudaMemoryTypeManaged);
-  cudaGetLastError();
-  if (pinned) {
-    B200_CUDA_CHECK(cudaMemcpy2DAsync(out, out_stride, d->rgb.d, pitch, rowb, (size_t)g.out_h, cudaMemcpyDeviceToHost, s));
+  if (is_page_locked(out)) {
+    B200_CUDA_CHECK(cudaMemcpy2DAsync(out, out_stride, rgb, pitch, rowb, (size_t)oh, cudaMemcpyDeviceToHost, s));
+    B200_CUDA_CHECK(cudaEventRecord(d->ev_d2h[0], s));
     B200_CUDA_CHECK(cudaStreamSynchronize(s));
   } else {
     const size_t band_rows = std::max<size_t>(1, (size_t)(32u << 20) / rowb);
-    const int nb = (int)(((size_t)g.out_h + band_rows - 1) / band_rows);
+    const int nb = (int)(((size_t)oh + band_rows - 1) / band_rows);
     if ((rc = d->bounce.reserve(2 * band_rows * rowb, true))) return rc;
     for (auto& e : d->ev_band) if (!e) B200_CUDA_CHECK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     for (int k = 0; k <= nb; k++) {
       if (k < nb) {
-        const size_t y0 = (size_t)k * band_rows, h = std::min(band_rows, (size_t)g.out_h - y0);
-        B200_CUDA_CHECK(cudaMemcpy2DAsync(d->bounce.h + (size_t)(k & 1) * band_rows * rowb, rowb, d->rgb.d + y0 * pitch, pitch, rowb, h, cudaMemcpyDeviceToHost, s));
+        const size_t y0 = (size_t)k * band_rows, h = std::min(band_rows, (size_t)oh - y0);
+        B200_CUDA_CHECK(cudaMemcpy2DAsync(d->bounce.h + (size_t)(k & 1) * band_rows * rowb, rowb, rgb + y0 * pitch, pitch, rowb, h, cudaMemcpyDeviceToHost, s));
         B200_CUDA_CHECK(cudaEventRecord(d->ev_band[k & 1], s));
       }
       if (k > 0) {
         const int j = k - 1;
-        const size_t y0 = (size_t)j * band_rows, h = std::min(band_rows, (size_t)g.out_h - y0);
+        const size_t y0 = (size_t)j * band_rows, h = std::min(band_rows, (size_t)oh - y0);
         B200_CUDA_CHECK(cudaEventSynchronize(d->ev_band[j & 1]));
         const uint8_t* src = d->bounce.h + (size_t)(j & 1) * band_rows * rowb;
         const int parts = 8;
@@ -552,9 +586,42 @@ int b200_decode_grid_to_rgb_host(b200_decoder* d, int cols, int rows, const uint
         });
       }
     }
+    B200_CUDA_CHECK(cudaEventRecord(d->ev_d2h[0], s));
     B200_CUDA_CHECK(cudaStreamSynchronize(s));
   }
-  return check_device_error(d);
+  if (d->err_host[0]) return set_error(B200_E_CUDA, "a decoding kernel gave up waiting for a dependency or met corrupt slice data");
+  return B200_OK;
+}
+
+// Throughput form of the fused entry point: returns once the work is queued (the host part -- header parsing, packing -- is
+// done); the RGB reaches `out` (page-locked memory, see b200_host_alloc) through a second stream, so the D2H of picture i
+// overlaps the kernels of picture i + 1 (two device RGB buffers).  b200_decoder_wait() blocks until everything submitted
+// has arrived and reports the first error.  `out` of consecutive calls may be the same buffer (copies are ordered).
+int b200_decode_grid_to_rgb_host_async(b200_decoder* d, int cols, int rows, const uint8_t* const* au, const size_t* au_size,
+                                       uint64_t max_pixels, int canvas_w, int canvas_h, const b200_geometry* geom,
+                                       const b200_color_options* opt, void* out, size_t out_stride, b200_image_info* info) {
+  if (!d || !opt || !out) return set_error(B200_E_INVALID, "null argument");
+  if (!is_page_locked(out)) return set_error(B200_E_INVALID, "the asynchronous entry point needs a page-locked output buffer (b200_host_alloc / b200_host_register)");
+  const int slot = d->async_slot; d->async_slot ^= 1;
+  if (d->err_host && d->err_host[slot]) d->async_error = true;                 // the step that used this slot two calls ago failed
+  size_t rowb = 0, pitch = 0; int oh = 0;
+  int rc = decode_to_rgb_device(d, cols, rows, au, au_size, max_pixels, canvas_w, canvas_h, geom, opt, info, slot, &rowb, &pitch, &oh);
+  if (rc) return rc;
+  B200_CUDA_CHECK(cudaStreamWaitEvent(d->copy, d->ev_k6[slot], 0));
+  B200_CUDA_CHECK(cudaMemcpy2DAsync(out, out_stride, d->rgb2[slot].d, pitch, rowb, (size_t)oh, cudaMemcpyDeviceToHost, d->copy));
+  B200_CUDA_CHECK(cudaEventRecord(d->ev_d2h[slot], d->copy));
+  return B200_OK;
+}
+
+int b200_decoder_wait(b200_decoder* d) {
+  if (!d) return set_error(B200_E_INVALID, "null argument");
+  if (!d->own) return B200_OK;
+  B200_CUDA_CHECK(cudaStreamSynchronize(d->own));
+  B200_CUDA_CHECK(cudaStreamSynchronize(d->copy));
+  const bool bad = d->async_error || d->err_host[0] || d->err_host[1];
+  d->async_error = false;
+  if (bad) return set_error(B200_E_CUDA, "a decoding kernel gave up waiting for a dependency or met corrupt slice data");
+  return B200_OK;
 }
 
 // Host-only: size, format and colour description of the picture an access unit holds (headers only, microseconds).

@@ -43,6 +43,8 @@ def _bind(l):
     l.b200_decode_grid_to_rgb_host.argtypes = [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_char_p), C.POINTER(C.c_size_t), C.c_uint64,
                                                C.c_int, C.c_int, C.POINTER(_lib.Geometry), C.POINTER(_lib.ColorOptions), C.c_void_p,
                                                C.c_size_t, C.POINTER(ImageInfo)]
+    l.b200_decode_grid_to_rgb_host_async.argtypes = l.b200_decode_grid_to_rgb_host.argtypes
+    l.b200_decoder_wait.argtypes = [C.c_void_p]
     l._dec_bound = True
 
 
@@ -163,3 +165,20 @@ class Decoder:
                                                        C.byref(opt), out.ctypes.data, out.strides[0], C.byref(info)))
         self.info = info
         return out, info
+
+    def decode_grid_to_rgb_host_async(self, aus: Sequence[bytes], cols: int, rows: int, out_chroma: int, out: np.ndarray, canvas=(0, 0),
+                                      geometry: Optional[Geometry] = None, max_image_size_pixels: int = 0):
+        """Throughput form (b200_decode_grid_to_rgb_host_async): returns once the work is queued; `out` must be page-locked
+        (a pinned torch tensor's numpy view, or memory from b200_host_alloc / b200_host_register).  Call wait() before reading."""
+        arr, sizes = self._aus(aus)
+        self._keep = (arr, sizes, aus)                     # the access units are read during this call only, the arrays until it returns
+        info = ImageInfo()
+        opt = _lib.ColorOptions(out_chroma, 0, 0)
+        g = C.byref(geometry.g) if geometry is not None else None
+        _lib.check(self.l.b200_decode_grid_to_rgb_host_async(self.h, cols, rows, arr, sizes, max_image_size_pixels, canvas[0], canvas[1], g,
+                                                             C.byref(opt), out.ctypes.data, out.strides[0], C.byref(info)))
+        self.info = info
+        return info
+
+    def wait(self):
+        _lib.check(self.l.b200_decoder_wait(self.h))

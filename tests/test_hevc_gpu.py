@@ -125,3 +125,22 @@ def test_entropy_and_reconstruction_sequential_and_concurrent(cuda, overlap, mon
                 assert np.array_equal(got[c], want[c]), f"{name} plane {c} overlap={overlap}"
     finally:
         d.close()
+
+
+def test_batch_of_heterogeneous_pictures(dec):
+    """One batch of equally sized pictures coded with DIFFERENT parameters (CTB 16 / 32 / 64, QPs, WPP on and off, slices): the
+    shape the decoder plugin's submission queue produces when libheif decodes unrelated images from several threads."""
+    aus, want = [], []
+    for k in range(12):
+        y, cb, cr = lb.hevc_enc.synthetic_image(300 + k, 128, 128, 8, True)
+        au = lb.hevc_enc.encode_intra(y, cb, cr, bit_depth=8, log2_ctb_size=4 + k % 3, qp=22 + k % 9, wpp=k % 2, seed=0xB200 + k,
+                                      slice_ctb_rows=(2 if k % 4 == 3 else 0), transform_skip=k % 2, cu_qp_delta=(k // 2) % 2)
+        aus.append(au)
+        want.append(ob.restatement_decode(au)[0])
+    dec.decode_grid(aus, cols=len(aus), rows=1)
+    got = dec.planes_host()
+    for k in range(len(aus)):
+        for c in range(3):
+            w = 128 if c == 0 else 64
+            tile = got[c][:, k * w:(k + 1) * w]
+            assert np.array_equal(tile, want[k][c]), f"picture {k} plane {c}: first diffs {np.argwhere(tile != want[k][c])[:4].tolist()}"
