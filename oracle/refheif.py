@@ -92,7 +92,9 @@ def check(e, what=""):
 def register_cpu_decoder():
     """The CPU decoder plugin of the oracle (FFmpeg in the libde265 role), id 'b200-oracle'."""
     load()
-    plug = C.CDLL(os.path.join(ob.REF, "liboracle_plugin.so"))
+    # the plugin variant linked against the reference build in use (one copy of libheif per process)
+    name = "liboracle_plugin_b200.so" if os.environ.get("B200_REF_LIB", "libheif_ref.so") == "libheif_ref_b200.so" else "liboracle_plugin.so"
+    plug = C.CDLL(os.path.join(ob.REF, name))
     rc = plug.b200_oracle_register(ob.avcodec_dir().encode())
     if rc != 0:
         raise RuntimeError("b200_oracle_register failed")

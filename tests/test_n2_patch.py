@@ -12,7 +12,7 @@ import pytest
 from oracle import bindings as ob
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-have = all(os.path.exists(os.path.join(ob.REF, f)) for f in ("libheif_ref.so", "libheif_ref_b200.so", "liboracle_plugin.so")) and ob.avcodec_dir()
+have = all(os.path.exists(os.path.join(ob.REF, f)) for f in ("libheif_ref.so", "libheif_ref_b200.so", "liboracle_plugin.so", "liboracle_plugin_b200.so")) and ob.avcodec_dir()
 
 
 def run(lib):
