@@ -158,6 +158,8 @@ typedef struct b200_hevc_enc_params {
   int still_picture;                 /* Main Still Picture profile signalling for 8-bit 4:2:0 */
   int vui_present, colour_description_present, colour_primaries, transfer_characteristics, matrix_coefficients, full_range;
   uint32_t seed;                     /* LCG seed (0xB200 + tile index) */
+  int scaling_lists;                 /* 0 = off, 1 = scaling_list_enabled_flag with the default lists (Tables 7-5 / 7-6), 2 = lists coded in the SPS,
+                                        3 = lists coded in the PPS (both with predicted / default / explicit matrices chosen by the LCG) */
 } b200_hevc_enc_params;
 
 void b200_hevc_enc_params_default(b200_hevc_enc_params* p);

@@ -3,6 +3,7 @@
 #include "b200_internal.h"
 #include "b200_hevc_types.h"
 #include "b200_hevc_syntax.h"
+#include "b200_hevc_scaling.h"
 #include <vector>
 
 namespace b200 {
@@ -19,6 +20,8 @@ struct PictureHeaders {
   std::vector<uint16_t> ctu_slice;       // slice index per CTB
   // VUI colour description as the libde265 plugin reports it (decoder_libde265.cc:426-448)
   int colour_primaries = 2, transfer_characteristics = 2, matrix_coefficients = 2, full_range = 0;
+  bool scaling_enabled = false;          // scaling_list_enabled_flag: `scaling` holds the factors in effect (PPS > SPS > default lists, 7.4.5)
+  sl::Factors scaling;
 };
 
 struct ParsedPicture {                   // host front-end result: headers + dense command stream
@@ -41,6 +44,7 @@ struct DeviceBatch {
   const PicDesc* pics; int npics;
   const CtuInfo* ctus; const TuCmd* tus; const CoefEntry* coefs; const SliceInfo* slices;
   const int8_t* qp8; const uint8_t* edge8;
+  const uint8_t* scaling;        // sl::Factors of the pictures that use scaling lists (PicDesc::scaling_idx)
   unsigned int* progress;        // two counters (luma, chroma) per CTB row of every picture, zeroed before launch
   const unsigned int* entropy_progress;   // K0's counters of the same rows when K0 runs CONCURRENTLY (nullptr: command stream complete)
   int blocks_per_sm;             // > 0: cap of resident CTAs per SM (co-residency with K0)

@@ -78,7 +78,7 @@ struct b200_decoder {
   std::vector<ParsedPicture> parsed;
   std::vector<int> parse_rc; std::vector<std::string> parse_msg;
   DevBuf<PicDesc> pics; DevBuf<CtuInfo> ctus; DevBuf<TuCmd> tus; DevBuf<CoefEntry> coefs; DevBuf<SliceInfo> slices;
-  DevBuf<int8_t> qp8; DevBuf<uint8_t> edge8; DevBuf<uint2> rows; DevBuf<unsigned> sync;   // sync: [0] ticket, [1] error flag, [2..] progress
+  DevBuf<int8_t> qp8; DevBuf<uint8_t> edge8; DevBuf<uint8_t> scaling; DevBuf<uint2> rows; DevBuf<unsigned> sync;   // sync: [0] ticket, [1] error flag, [2..] progress
   DevBuf<uint8_t> rec; DevBuf<uint8_t> canvas; DevBuf<uint8_t> rgb2[2]; DevBuf<uint8_t> bounce;   // fused host entry points: two RGB buffers (D2H of one overlaps the kernels writing the other)
   cudaStream_t own = nullptr, copy = nullptr; cudaEvent_t ev_band[2] = {nullptr, nullptr}, ev_k6[2] = {nullptr, nullptr}, ev_d2h[2] = {nullptr, nullptr};
   unsigned* err_host = nullptr; int async_slot = 0; bool async_error = false;
@@ -101,7 +101,7 @@ struct b200_decoder {
   size_t n_rows = 0, n_items = 0, cbytes = 0; bool canvas_fully_covered = true; int max_log2_ctb = 6, info_bps = 1;
   ~b200_decoder() {
     delete pool;
-    pics.release(); ctus.release(); tus.release(); coefs.release(); slices.release(); qp8.release(); edge8.release(); rows.release();
+    pics.release(); ctus.release(); tus.release(); coefs.release(); slices.release(); qp8.release(); edge8.release(); scaling.release(); rows.release();
     sync.release(); rec.release(); canvas.release(); rgb2[0].release(); rgb2[1].release(); bounce.release();
     if (own) cudaStreamDestroy(own);
     if (copy) cudaStreamDestroy(copy);
@@ -171,7 +171,7 @@ static int run_device_pipeline(b200_decoder* d, int n, cudaStream_t s, int* laun
   cudaEventRecord(d->ev[1], s);
   DeviceBatch b{};
   b.pics = d->pics.d; b.npics = n; b.ctus = d->ctus.d; b.tus = d->tus.d; b.coefs = d->coefs.d; b.slices = d->slices.d;
-  b.qp8 = d->qp8.d; b.edge8 = d->edge8.d; b.ticket = d->sync.d; b.error_flag = d->sync.d + 1; b.progress = d->sync.d + 2; b.row_list = d->rows.d; b.nrows = (int)d->n_items; b.max_log2_ctb = d->max_log2_ctb; b.wide_samples = d->info_bps == 2;
+  b.qp8 = d->qp8.d; b.edge8 = d->edge8.d; b.scaling = d->scaling.d; b.ticket = d->sync.d; b.error_flag = d->sync.d + 1; b.progress = d->sync.d + 2; b.row_list = d->rows.d; b.nrows = (int)d->n_items; b.max_log2_ctb = d->max_log2_ctb; b.wide_samples = d->info_bps == 2;
   if (devfe) {
     EntropyBatch e{};
     e.pics = d->epics.d; e.npics = d->npics; e.subs = d->subs.d; e.nsubs = (int)d->n_subs;
@@ -286,8 +286,13 @@ int b200_decoder_decode_grid(b200_decoder* d, int cols, int rows, const uint8_t*
       rec_bytes += (size_t)st * h * bps; rec_bytes = (rec_bytes + 255) & ~(size_t)255;
     }
   }
+  // scaling lists: one 780-byte factor table per picture that enables them (784-byte slots)
+  int n_scaling = 0;
+  for (int i = 0; i < n; i++) { ParsedPicture& pp = d->parsed[(size_t)i]; pp.desc.scaling_idx = pp.hdr.scaling_enabled ? n_scaling++ : -1; }
   if (n_tu > 0xffffffffull) return set_error(B200_E_UNSUPPORTED, "batch too large");
   int rc;
+  if ((rc = d->scaling.reserve((size_t)n_scaling * 784 + 16))) return rc;
+  for (int i = 0; i < n; i++) { const ParsedPicture& pp = d->parsed[(size_t)i]; if (pp.desc.scaling_idx >= 0) memcpy(d->scaling.h + (size_t)pp.desc.scaling_idx * 784, &pp.hdr.scaling, sizeof(sl::Factors)); }
   if ((rc = d->pics.reserve((size_t)n)) || (rc = d->ctus.reserve(n_ctu, !devfe)) || (rc = d->tus.reserve(n_tu, !devfe)) || (rc = d->coefs.reserve(n_coef + 1, !devfe)) ||
       (rc = d->slices.reserve(n_slice)) || (rc = d->qp8.reserve(n_map, !devfe)) || (rc = d->edge8.reserve(n_map, !devfe)) || (rc = d->rows.reserve(2 * n_rows)) ||
       (rc = d->sync.reserve(2 * n_rows + 2, false)) || (rc = d->rec.reserve(rec_bytes, false)))
@@ -387,7 +392,8 @@ int b200_decoder_decode_grid(b200_decoder* d, int cols, int rows, const uint8_t*
   B200_CUDA_CHECK(cudaMemcpyAsync(d->pics.d, d->pics.h, (size_t)n * sizeof(PicDesc), cudaMemcpyHostToDevice, s));
   B200_CUDA_CHECK(cudaMemcpyAsync(d->slices.d, d->slices.h, n_slice * sizeof(SliceInfo), cudaMemcpyHostToDevice, s));
   B200_CUDA_CHECK(cudaMemcpyAsync(d->rows.d, d->rows.h, d->n_items * sizeof(uint2), cudaMemcpyHostToDevice, s));
-  size_t h2d = (size_t)n * sizeof(PicDesc) + n_slice * sizeof(SliceInfo) + d->n_items * sizeof(uint2);
+  if (n_scaling) B200_CUDA_CHECK(cudaMemcpyAsync(d->scaling.d, d->scaling.h, (size_t)n_scaling * 784, cudaMemcpyHostToDevice, s));
+  size_t h2d = (size_t)n_scaling * 784 + (size_t)n * sizeof(PicDesc) + n_slice * sizeof(SliceInfo) + d->n_items * sizeof(uint2);
   if (!devfe) {
     B200_CUDA_CHECK(cudaMemcpyAsync(d->ctus.d, d->ctus.h, n_ctu * sizeof(CtuInfo), cudaMemcpyHostToDevice, s));
     B200_CUDA_CHECK(cudaMemcpyAsync(d->tus.d, d->tus.h, n_tu * sizeof(TuCmd), cudaMemcpyHostToDevice, s));

@@ -10,6 +10,7 @@
 // deblocking overrides, WPP entry points, multiple slices and dependent slice segments, 8..12 bit,
 // 4:2:0 and 4:0:0.  Syntax follows ITU-T H.265 7.3 / 9.3; the reconstruction loop follows 8.4 / 8.6.
 #include "b200_internal.h"
+#include "b200_hevc_scaling.h"
 #include <algorithm>
 #include <vector>
 
@@ -198,6 +199,23 @@ class Encoder {
     log2_min_tb = 2; log2_max_tb = std::min(5, log2ctb);
     max_th_depth = clip3(0, 4, p.max_transform_hierarchy_depth_intra);
     qg_log2 = log2ctb - clip3(0, log2ctb - 3, p.diff_cu_qp_delta_depth);
+    // scaling lists (7.3.4): what gets coded (or defaulted) and the factors the closed-loop reconstruction uses
+    sl::set_all_default(sl_lists);
+    if (p.scaling_lists >= 2) {
+      for (int s = 0; s < 4; s++) for (int m = 0; m < 6; m += (s == 3 ? 3 : 1)) {
+        const int kind = (int)rng.range(4);                       // 0 default, 1 copy of the previous matrix, 2/3 explicit
+        sl_kind[s][m] = (uint8_t)((kind == 1 && m == 0) ? 0 : (kind >= 2 ? 2 : kind));
+        if (sl_kind[s][m] == 0) sl::set_default(sl_lists, s, m);
+        else if (sl_kind[s][m] == 1) { const int ref = m - (s == 3 ? 3 : 1); memcpy(sl_lists.list[s][m], sl_lists.list[s][ref], 64); sl_lists.dc[s][m] = sl_lists.dc[s][ref]; }
+        else {
+          const int num = s == 0 ? 16 : 64; int v = 8 + (int)rng.range(16);
+          if (s > 1) sl_lists.dc[s][m] = (uint8_t)(8 + rng.range(40));
+          for (int i = 0; i < num; i++) { v = clip3(1, 255, v + (int)rng.range(7) - 2); sl_lists.list[s][m][i] = (uint8_t)v; }
+        }
+      }
+    }
+    sl_on = p.scaling_lists != 0;
+    if (sl_on) sl::derive(sl_lists, sl_f);
   }
 
   void encode(std::vector<uint8_t>& out) {
@@ -228,6 +246,24 @@ class Encoder {
   int slice_idx = 0, slice_addr_rs = 0, slice_qp = 26;
   int is_qp_delta_coded = 0, cu_qp_delta_val = 0, qpy_prev_qg = 0, last_cu_qpy = 0, first_qg = 1, cur_qpy = 0, qg_target_qp = 0;
   int cu_x0 = 0, cu_y0 = 0;
+  sl::Lists sl_lists; sl::Factors sl_f; uint8_t sl_kind[4][6] = {}; bool sl_on = false;
+
+  void write_scaling_list_data(BitWriter& b) {                    // 7.3.4
+    for (int s = 0; s < 4; s++) for (int m = 0; m < 6; m += (s == 3 ? 3 : 1)) {
+      if (sl_kind[s][m] < 2) { b.put(0, 1); b.ue(sl_kind[s][m]); continue; }       // pred_mode_flag = 0: delta 0 = default, 1 = previous matrix
+      b.put(1, 1);
+      int next = 8; const int num = s == 0 ? 16 : 64;
+      if (s > 1) { b.se((int)sl_lists.dc[s][m] - 8); next = sl_lists.dc[s][m]; }
+      for (int i = 0; i < num; i++) { int d = (int)sl_lists.list[s][m][i] - next; if (d > 127) d -= 256; if (d < -128) d += 256; b.se(d); next = sl_lists.list[s][m][i]; }
+    }
+  }
+  int scaling_factor(int c, int log2n, int pos) const {          // m[x][y] of 8.6.4.2 for raster position pos of an n x n block
+    if (!sl_on) return 16;
+    const int n = 1 << log2n, x = pos & (n - 1), y = pos >> log2n, sid = log2n - 2;
+    if (sid == 0) return sl_f.m[c][0][y * 4 + x];
+    if (pos == 0 && sid >= 2) return sl_f.dc[c][sid];
+    return sl_f.m[c][sid][((y >> (log2n - 3)) << 3) + (x >> (log2n - 3))];
+  }
 
   int stride_of(int c) const { return c ? Wc : W; }
   bool avail(int x, int y) const {
@@ -289,7 +325,8 @@ class Encoder {
     b.ue(log2ctb - 3);
     b.ue(log2_min_tb - 2); b.ue(log2_max_tb - log2_min_tb);
     b.ue(0); b.ue(max_th_depth);
-    b.put(0, 1);                      // scaling_list_enabled
+    b.put(sl_on ? 1 : 0, 1);          // scaling_list_enabled
+    if (sl_on) { b.put(P.scaling_lists == 2 ? 1 : 0, 1); if (P.scaling_lists == 2) write_scaling_list_data(b); }
     b.put(0, 1);                      // amp
     b.put(P.sao ? 1 : 0, 1);
     b.put(0, 1);                      // pcm
@@ -335,7 +372,8 @@ class Encoder {
     b.put(1, 1);                      // deblocking_filter_override_enabled
     b.put(P.deblocking_disabled ? 1 : 0, 1);
     if (!P.deblocking_disabled) { b.se(P.beta_offset_div2); b.se(P.tc_offset_div2); }
-    b.put(0, 1);                      // scaling_list_data_present
+    b.put(P.scaling_lists == 3 ? 1 : 0, 1);   // pps_scaling_list_data_present
+    if (P.scaling_lists == 3) write_scaling_list_data(b);
     b.put(0, 1);                      // lists_modification_present
     b.ue(0);                          // log2_parallel_merge_level_minus2
     b.put(0, 1);                      // slice_segment_header_extension_present
@@ -731,7 +769,7 @@ class Encoder {
     uint16_t* rp = rec[c].data();
     if (r.cbf) {
       int16_t d[1024]; int bs = bd + log2n - 5, scale = kLevelScale[qp % 6] << (qp / 6);
-      for (int i = 0; i < n * n; i++) { long t = ((long)r.lev[i] * 16 * scale + (1L << (bs - 1))) >> bs; d[i] = (int16_t)clip3(-32768, 32767, (int)t); }
+      for (int i = 0; i < n * n; i++) { long t = ((long)r.lev[i] * scaling_factor(c, log2n, i) * scale + (1L << (bs - 1))) >> bs; d[i] = (int16_t)(t < -32768 ? -32768 : (t > 32767 ? 32767 : t)); }
       inverse(d, res, log2n, dst4, r.tskip);
       int maxv = (1 << bd) - 1;
       for (int y = 0; y < n; y++) for (int x = 0; x < n; x++) rp[(size_t)(y0 + y) * st + x0 + x] = (uint16_t)clip3(0, maxv, pred[y * n + x] + res[y * n + x]);

@@ -33,12 +33,14 @@ struct Sps {
   int sao = 0, strong_intra = 0, num_st_rps = 0, long_term = 0, num_lt_sps = 0, temporal_mvp = 0;
   int st_num_delta[65] = {0};
   int vui_signal = 0, vui_full_range = 0, vui_colour = 0, vui_cp = 2, vui_tc = 2, vui_mc = 2;
+  int scaling_enabled = 0, sl_present = 0; sl::Lists lists;
 };
 struct Pps {
   bool valid = false; int sps_id = 0, dependent_slices = 0, output_flag_present = 0, num_extra_bits = 0, sign_hiding = 0;
   int init_qp = 26, transform_skip = 0, cu_qp_delta = 0, diff_cu_qp_delta_depth = 0, cb_qp_offset = 0, cr_qp_offset = 0;
   int slice_chroma_qp_offsets = 0, wpp = 0, lf_across_slices = 0, deblock_override_enabled = 0, deblock_disabled = 0;
   int beta_offset = 0, tc_offset = 0, slice_ext_present = 0, log2_sao_scale_luma = 0, log2_sao_scale_chroma = 0;
+  int sl_present = 0; sl::Lists lists;
 };
 
 inline int clip3(int lo, int hi, int v) { return v < lo ? lo : (v > hi ? hi : v); }
@@ -122,6 +124,23 @@ class HeaderParser {
     }
     return !b.overrun();
   }
+  // 7.3.4 scaling_list_data; false = malformed
+  static bool scaling_list_data(BitRd& b, sl::Lists& L) {
+    sl::set_all_default(L);
+    for (int s = 0; s < 4; s++) for (int m = 0; m < 6; m += (s == 3 ? 3 : 1)) {
+      if (!b.bit()) {                                             // scaling_list_pred_mode_flag = 0: default list or a copy
+        const unsigned delta = b.ue();
+        if (delta > (unsigned)(s == 3 ? m / 3 : m)) return false;
+        if (delta == 0) sl::set_default(L, s, m);
+        else { const int ref = m - (int)delta * (s == 3 ? 3 : 1); memcpy(L.list[s][m], L.list[s][ref], 64); L.dc[s][m] = L.dc[s][ref]; }
+      } else {
+        int next = 8; const int num = s == 0 ? 16 : 64;
+        if (s > 1) { const int dc = b.se(); if (dc < -7 || dc > 247) return false; next = dc + 8; L.dc[s][m] = (uint8_t)next; }
+        for (int i = 0; i < num; i++) { const int d = b.se(); if (d < -128 || d > 127) return false; next = (next + d + 256) % 256; L.list[s][m][i] = (uint8_t)next; }
+      }
+    }
+    return !b.overrun();
+  }
   static bool skip_hrd(BitRd& b, int msl) {
     int nal = b.bit(), vcl = b.bit(), sub = 0;
     if (nal || vcl) { sub = b.bit(); if (sub) { b.bits(8); b.bits(5); b.bit(); b.bits(5); } b.bits(4); b.bits(4); if (sub) b.bits(4); b.bits(5); b.bits(5); b.bits(5); }
@@ -167,7 +186,8 @@ class HeaderParser {
     { const unsigned inter = b.ue(), intra = b.ue(); const unsigned mx = (unsigned)(s.log2_ctb - s.log2_min_tb);
       if (inter > mx || intra > mx) return set_error(B200_E_BITSTREAM, "max_transform_hierarchy_depth");
       s.max_th_depth_intra = (int)intra; }
-    if (b.bit()) return set_error(B200_E_UNSUPPORTED, "scaling lists are not supported");
+    s.scaling_enabled = b.bit();
+    if (s.scaling_enabled) { s.sl_present = b.bit(); if (s.sl_present && !scaling_list_data(b, s.lists)) return set_error(B200_E_BITSTREAM, "sps scaling_list_data"); }
     b.bit(); s.sao = b.bit();
     if (b.bit()) return set_error(B200_E_UNSUPPORTED, "PCM is not supported");
     { const unsigned v = b.ue(); if (v > 64) return set_error(B200_E_BITSTREAM, "num_short_term_ref_pic_sets"); s.num_st_rps = (int)v; }
@@ -217,7 +237,8 @@ class HeaderParser {
     p.wpp = b.bit();
     p.lf_across_slices = b.bit();
     if (b.bit()) { p.deblock_override_enabled = b.bit(); p.deblock_disabled = b.bit(); if (!p.deblock_disabled) { const int be = b.se(), tc = b.se(); if (be < -6 || be > 6 || tc < -6 || tc > 6) return set_error(B200_E_BITSTREAM, "pps deblocking offsets"); p.beta_offset = 2 * be; p.tc_offset = 2 * tc; } }
-    if (b.bit()) return set_error(B200_E_UNSUPPORTED, "scaling lists are not supported");
+    p.sl_present = b.bit();
+    if (p.sl_present && !scaling_list_data(b, p.lists)) return set_error(B200_E_BITSTREAM, "pps scaling_list_data");
     b.bit(); b.ue(); p.slice_ext_present = b.bit();
     if (b.bit()) {
       int range = b.bit(); b.bits(7);
@@ -247,6 +268,13 @@ class HeaderParser {
     d.out_w = W - (S->conf_l + S->conf_r) * sub; d.out_h = H - (S->conf_t + S->conf_b) * sub;
     if (d.out_w <= 0 || d.out_h <= 0) return set_error(B200_E_BITSTREAM, "conformance window");
     d.strong_intra = S->strong_intra; d.sao_enabled = S->sao; d.w8 = W >> 3; d.h8 = H >> 3;
+    d.scaling_idx = -1;
+    P.scaling_enabled = S->scaling_enabled != 0;
+    if (P.scaling_enabled) {                                      // 7.4.5: PPS lists, else SPS lists, else the default lists
+      if (PP->sl_present) sl::derive(PP->lists, P.scaling);
+      else if (S->sl_present) sl::derive(S->lists, P.scaling);
+      else { sl::Lists L; sl::set_all_default(L); sl::derive(L, P.scaling); }
+    }
     total = d.wctb * d.hctb;
     P.ctu_slice.assign((size_t)total, 0xffff);
     P.colour_primaries = S->vui_colour ? S->vui_cp : 2; P.transfer_characteristics = S->vui_colour ? S->vui_tc : 2;

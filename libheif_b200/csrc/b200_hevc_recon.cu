@@ -95,9 +95,9 @@ __device__ __forceinline__ int chroma_qp(int qpy, int off, int bd) {       // 8.
   return qpc + qbd;
 }
 
-// 8.6.3 scaling with the flat scaling list (m = 16): TransCoeffLevel -> d, clipped to 16 bits
-__device__ __forceinline__ int dequant(int level, int qp, int bd_shift) {
-  const long long scale = (long long)(c_level_scale[qp % 6] << (qp / 6)) * 16;
+// 8.6.3 / 8.6.4.2 scaling: TransCoeffLevel -> d, clipped to 16 bits; m = 16 (flat) or the scaling factor of the position
+__device__ __forceinline__ int dequant(int level, int qp, int bd_shift, int m) {
+  const long long scale = (long long)(c_level_scale[qp % 6] << (qp / 6)) * m;
   const long long t = ((long long)level * scale + (1LL << (bd_shift - 1))) >> bd_shift;
   return (int)(t < -32768 ? -32768 : (t > 32767 ? 32767 : t));
 }
@@ -127,7 +127,8 @@ __device__ __forceinline__ unsigned make_desc(int bx, int by, int lg, int mode, 
 
 // ---- phase A, 4x4 blocks: the calling lane owns the block.  scr: the warp's [16][32] int16 scratch (column = lane).
 template <bool LIVE>
-__device__ __forceinline__ void residual4_lane(int16_t* scr, int lane, const CoefEntry* __restrict__ ce, int nnz, int qp, int bd, bool dst, bool tskip, int16_t* out) {
+__device__ __forceinline__ void residual4_lane(int16_t* scr, int lane, const CoefEntry* __restrict__ ce, int nnz, int qp, int bd, bool dst, bool tskip, int16_t* out,
+                                               const uint8_t* __restrict__ sf) {      // sf: the 16 scaling factors of this component (raster), or nullptr
   int16_t* my = scr + lane;
 #pragma unroll
   for (int p = 0; p < 16; p++) my[p * 32] = 0;
@@ -135,7 +136,7 @@ __device__ __forceinline__ void residual4_lane(int16_t* scr, int lane, const Coe
 #pragma unroll 1
   for (int i = 0; i < nnz; i++) {
     const CoefEntry e = ld_coef<LIVE>(&ce[i]);
-    my[(e.pos & 15) * 32] = (int16_t)dequant(e.level, qp, bd_shift);
+    my[(e.pos & 15) * 32] = (int16_t)dequant(e.level, qp, bd_shift, sf ? (int)__ldg(sf + (e.pos & 15)) : 16);
   }
   int c[16];
 #pragma unroll
@@ -186,7 +187,8 @@ __device__ __forceinline__ void residual4_lane(int16_t* scr, int lane, const Coe
 
 // ---- phase A, 8x8 .. 32x32 blocks: the whole warp, in place in the block's residual slot (coefficients -> residuals).
 template <bool LIVE>
-__device__ __noinline__ void residual_big(int16_t* rs, int16_t* tmp, const int8_t* __restrict__ mat, const CoefEntry* __restrict__ ce, int nnz, int lg, int qp, int bd, int lane) {
+__device__ __noinline__ void residual_big(int16_t* rs, int16_t* tmp, const int8_t* __restrict__ mat, const CoefEntry* __restrict__ ce, int nnz, int lg, int qp, int bd, int lane,
+                                          const uint8_t* __restrict__ sf, int sf_dc) {   // sf: 8x8 raster scaling factors of (component, size) or nullptr; sf_dc: factor of position (0, 0) for 16x16 / 32x32
   const int n = 1 << lg;
   unsigned* z = reinterpret_cast<unsigned*>(rs);
 #pragma unroll 1
@@ -198,7 +200,9 @@ __device__ __noinline__ void residual_big(int16_t* rs, int16_t* tmp, const int8_
   for (int i = lane; i < nnz; i += 32) {
     const CoefEntry e = ld_coef<LIVE>(&ce[i]);
     const int pos = e.pos & (n * n - 1);
-    rs[pos] = (int16_t)dequant(e.level, qp, bd_shift);
+    int m = 16;
+    if (sf) { const int x = pos & (n - 1), y = pos >> lg; m = (pos == 0 && lg >= 4) ? sf_dc : (int)__ldg(sf + ((y >> (lg - 3)) << 3) + (x >> (lg - 3))); }
+    rs[pos] = (int16_t)dequant(e.level, qp, bd_shift, m);
     maxrow = max(maxrow, pos >> lg); maxcol = max(maxcol, pos & (n - 1));
   }
   maxrow = __reduce_max_sync(0xffffffffu, maxrow); maxcol = __reduce_max_sync(0xffffffffu, maxcol);
@@ -378,6 +382,7 @@ __global__ void __launch_bounds__(WARPS * 32, B200_RECON_MIN_BLOCKS) hevc_recon_
     const int cs = (1 << log2ctb) >> g, S = cs + PAD;                        // component CTB size, tile row stride
     const int cw = pic->width >> g, ch = pic->height >> g;
     const int y0 = ry << log2ctb, cy0 = y0 >> g;
+    const uint8_t* sfac = pic->scaling_idx >= 0 ? b.scaling + (size_t)pic->scaling_idx * 784 : nullptr;      // sl::Factors: m[3][4][64], dc[3][4]
     const TuCmd* tus = b.tus + pic->tu_base;
     const CoefEntry* coefs = b.coefs + pic->coef_base;
     unsigned* prog = b.progress + 2 * pic->progress_base + g;               // counter of (row r, group g) at prog[2 * r]
@@ -453,7 +458,8 @@ __global__ void __launch_bounds__(WARPS * 32, B200_RECON_MIN_BLOCKS) hevc_recon_
 #pragma unroll 1
           for (int c2 = 0; c2 < 2; c2++)
             if (c2 ? coded1 : coded0)
-              residual4_lane<LIVE>(tmp, lane, c2 ? ce1 : ce, c2 ? n1 : n0, c2 ? qp1 : qp0, bd, g == 0, c2 ? ts1 : ts0, res0 + (c2 ? cs * cs : 0) + roff);
+              residual4_lane<LIVE>(tmp, lane, c2 ? ce1 : ce, c2 ? n1 : n0, c2 ? qp1 : qp0, bd, g == 0, c2 ? ts1 : ts0, res0 + (c2 ? cs * cs : 0) + roff,
+                                   sfac ? sfac + (g + c2) * 256 : nullptr);
         }
         __syncwarp();
         // larger blocks: the whole warp, one block at a time
@@ -466,7 +472,8 @@ __global__ void __launch_bounds__(WARPS * 32, B200_RECON_MIN_BLOCKS) hevc_recon_
             const unsigned long long cp = __shfl_sync(0xffffffffu, (unsigned long long)(c2 ? ce1 : ce), src);
             const int nn = __shfl_sync(0xffffffffu, c2 ? n1 : n0, src), lgg = __shfl_sync(0xffffffffu, lg, src), qq = __shfl_sync(0xffffffffu, c2 ? qp1 : qp0, src);
             const unsigned ro = __shfl_sync(0xffffffffu, roff, src);
-            residual_big<LIVE>(res0 + (c2 ? cs * cs : 0) + ro, tmp, mat, reinterpret_cast<const CoefEntry*>(cp), nn, lgg, qq, bd, lane);
+            residual_big<LIVE>(res0 + (c2 ? cs * cs : 0) + ro, tmp, mat, reinterpret_cast<const CoefEntry*>(cp), nn, lgg, qq, bd, lane,
+                               sfac ? sfac + (g + c2) * 256 + (lgg - 2) * 64 : nullptr, sfac ? (int)sfac[768 + (g + c2) * 4 + (lgg - 2)] : 16);
           }
         }
       }

@@ -66,7 +66,7 @@ struct PicDesc {         // one per picture (tile) of a batch
   void* rec[3]; int32_t rec_stride[3];           // strides in samples
   void* dst[3]; int32_t dst_stride[3];           // dst already offset to the paste position
   uint32_t progress_base;            // first per-CTB-row progress counter of this picture
-  int32_t pad;
+  int32_t scaling_idx;               // index of the picture's scaling factors (sl::Factors, 780 bytes each) in the batch-wide array; -1: flat (m = 16)
 };
 
 }  // namespace b200

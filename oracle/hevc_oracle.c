@@ -81,6 +81,7 @@ typedef struct {
   int num_lt_sps;
   int vui_signal, vui_full_range, vui_colour, vui_cp, vui_tc, vui_mc;
   int range_ext_unsupported;
+  int sl_data_present; uint8_t sl[4][6][64], sl_dc[4][6];   /* ScalingList[sizeId][matrixId][i], scaling_list_dc_coef (7.3.4) */
 } sps_t;
 
 typedef struct {
@@ -93,7 +94,40 @@ typedef struct {
   int scaling_list_present, lists_modification, slice_ext_present;
   int log2_sao_scale_luma, log2_sao_scale_chroma;
   int range_ext_unsupported;
+  uint8_t sl[4][6][64], sl_dc[4][6];
 } pps_t;
+
+/* ---- scaling lists: 7.3.4 scaling_list_data, 7.4.5 (defaults: Table 7-5 = 16 everywhere, Table 7-6 below in diagonal scan order) */
+static const uint8_t default_sl8[2][64] = {
+  {16,16,16,16,16,16,16,16,16,16,17,16,17,16,17,18,17,18,18,17,18,21,19,20,21,20,19,21,24,22,22,24,24,22,22,24,25,25,27,30,27,25,25,29,31,35,35,31,29,36,41,44,41,36,47,54,54,47,65,70,65,88,88,115},
+  {16,16,16,16,16,16,16,16,16,16,17,17,17,17,17,18,18,18,18,18,18,20,20,20,20,20,20,20,24,24,24,24,24,24,24,24,25,25,25,25,25,25,25,28,28,28,28,28,28,33,33,33,33,33,41,41,41,41,54,54,54,71,71,91}};
+static void sl_default(uint8_t sl[4][6][64], uint8_t dc[4][6], int size_id, int matrix_id) {
+  for (int i = 0; i < 64; i++) sl[size_id][matrix_id][i] = size_id == 0 ? 16 : default_sl8[matrix_id < 3 ? 0 : 1][i];
+  dc[size_id][matrix_id] = 16;
+}
+static int parse_scaling_list_data(bitrd* b, uint8_t sl[4][6][64], uint8_t dc[4][6]) {
+  for (int sizeId = 0; sizeId < 4; sizeId++) for (int matrixId = 0; matrixId < 6; matrixId++) sl_default(sl, dc, sizeId, matrixId);
+  for (int sizeId = 0; sizeId < 4; sizeId++)
+    for (int matrixId = 0; matrixId < 6; matrixId += (sizeId == 3) ? 3 : 1) {
+      int pred_mode_flag = rd_bit(b);
+      if (!pred_mode_flag) {
+        unsigned delta = rd_ue(b);                                  /* scaling_list_pred_matrix_id_delta */
+        int step = sizeId == 3 ? 3 : 1;
+        if (delta * step > (unsigned)matrixId) return HO_ERROR;
+        if (delta == 0) sl_default(sl, dc, sizeId, matrixId);
+        else { int ref = matrixId - (int)delta * step; memcpy(sl[sizeId][matrixId], sl[sizeId][ref], 64); dc[sizeId][matrixId] = dc[sizeId][ref]; }
+      } else {
+        int nextCoef = 8, coefNum = sizeId == 0 ? 16 : 64;
+        if (sizeId > 1) { int v = rd_se(b); if (v < -7 || v > 247) return HO_ERROR; nextCoef = v + 8; dc[sizeId][matrixId] = (uint8_t)nextCoef; }
+        for (int i = 0; i < coefNum; i++) {
+          int d = rd_se(b); if (d < -128 || d > 127) return HO_ERROR;
+          nextCoef = (nextCoef + d + 256) % 256;
+          sl[sizeId][matrixId][i] = (uint8_t)nextCoef;
+        }
+      }
+    }
+  return HO_OK;
+}
 
 static void skip_profile_tier_level(bitrd* b, int max_sub_layers_minus1) {
   rd_bits(b, 8); rd_bits(b, 32); rd_bits(b, 4); rd_bits(b, 32); rd_bits(b, 11); rd_bit(b); /* 88 bits */
@@ -176,7 +210,11 @@ static int parse_sps(const uint8_t* rbsp, size_t n, sps_t* s) {
   rd_ue(&b);
   s->max_th_depth_intra = rd_ue(&b);
   s->scaling_list_enabled = rd_bit(&b);
-  if (s->scaling_list_enabled) return HO_UNSUPPORTED;
+  s->sl_data_present = 0;
+  if (s->scaling_list_enabled) {
+    s->sl_data_present = rd_bit(&b);
+    if (s->sl_data_present && parse_scaling_list_data(&b, s->sl, s->sl_dc) != HO_OK) return HO_ERROR;
+  }
   s->amp = rd_bit(&b); s->sao = rd_bit(&b); s->pcm = rd_bit(&b);
   if (s->pcm) return HO_UNSUPPORTED;
   s->num_st_rps = rd_ue(&b);
@@ -258,7 +296,7 @@ static int parse_pps(const uint8_t* rbsp, size_t n, pps_t* p) {
     if (!p->deblock_disabled) { p->beta_offset = 2 * rd_se(&b); p->tc_offset = 2 * rd_se(&b); }
   }
   p->scaling_list_present = rd_bit(&b);
-  if (p->scaling_list_present) return HO_UNSUPPORTED;
+  if (p->scaling_list_present && parse_scaling_list_data(&b, p->sl, p->sl_dc) != HO_OK) return HO_ERROR;
   p->lists_modification = rd_bit(&b);
   rd_ue(&b);
   p->slice_ext_present = rd_bit(&b);
@@ -715,14 +753,35 @@ static void residual_coding(dec_t* d, int x0, int y0, int log2n, int c, int pred
       nsig++;
     }
   }
-  /* 8.6.3 scaling (flat m = 16) */
+  /* 8.6.3 / 8.6.4.2 scaling: m = 16 without scaling lists, else ScalingFactor[sizeId][matrixId][x][y] (7.4.5): the list in
+     effect (PPS, else SPS, else default) mapped through the up-right diagonal scan, 8x8 lists replicated for 16x16 / 32x32
+     with scaling_list_dc_coef at (0, 0); matrixId = cIdx for intra blocks (32x32: matrixId 0) */
   const int bd = d->s->bit_depth;
   int qp = c == 0 ? d->cur_qpy + 6 * (bd - 8)
                   : chroma_qp(d, d->cur_qpy, (c == 1 ? d->p->cb_qp_offset + d->cur_cb_off : d->p->cr_qp_offset + d->cur_cr_off));
   int bd_shift = bd + log2n - 5;
   int scale = level_scale[qp % 6] << (qp / 6);
+  const uint8_t (*sl)[6][64] = NULL; const uint8_t (*sldc)[6] = NULL;
+  uint8_t dsl[4][6][64], ddc[4][6];
+  if (d->s->scaling_list_enabled) {
+    if (d->p->scaling_list_present) { sl = d->p->sl; sldc = d->p->sl_dc; }
+    else if (d->s->sl_data_present) { sl = d->s->sl; sldc = d->s->sl_dc; }
+    else { for (int a = 0; a < 4; a++) for (int bq = 0; bq < 6; bq++) sl_default(dsl, ddc, a, bq); sl = dsl; sldc = ddc; }
+  }
   for (int k = 0; k < n * n; k++) if (coef[k]) {
-    long long t = ((long long)coef[k] * 16 * scale + (1LL << (bd_shift - 1))) >> bd_shift;
+    int m = 16;
+    if (sl) {
+      const int sizeId = log2n - 2, matrixId = sizeId == 3 ? 0 : c, x = k & (n - 1), y = k >> log2n;
+      const int l2 = sizeId == 0 ? 2 : 3, rep = sizeId <= 1 ? 0 : sizeId - 1;     /* replication shift of the 8x8 list */
+      const int xs = x >> rep, ys = y >> rep;
+      /* scan index i of (xs, ys) in the up-right diagonal scan of the (1 << l2) square (6.5.3) */
+      int i = 0;
+      { int xx = 0, yy = 0, found = 0, sz = 1 << l2;
+        while (!found) { while (yy >= 0 && !found) { if (xx < sz && yy < sz) { if (xx == xs && yy == ys) found = 1; else i++; } if (!found) { yy--; xx++; } } if (!found) { yy = xx; xx = 0; } } }
+      m = sl[sizeId][matrixId][i];
+      if (sizeId >= 2 && x == 0 && y == 0) m = sldc[sizeId][matrixId];
+    }
+    long long t = ((long long)coef[k] * m * scale + (1LL << (bd_shift - 1))) >> bd_shift;
     coef[k] = (int16_t)(t < -32768 ? -32768 : (t > 32767 ? 32767 : t));
   }
   int res[32 * 32];

@@ -45,6 +45,10 @@ SYNTH = [
     ("lowqp_deep", 72, 40, 8, True, dict(log2_ctb_size=6, qp=10, dqp_range=10, mode_decision=0, max_transform_hierarchy_depth_intra=4)),
     ("highqp", 72, 40, 8, True, dict(log2_ctb_size=6, qp=48, dqp_range=3, mode_decision=0)),
     ("tile_1024_like", 512, 512, 8, True, dict(log2_ctb_size=5, qp=27, wpp=1)),
+    # scaling lists (7.3.4 / 7.4.5): default lists, lists coded in the SPS, lists coded in the PPS (explicit, copied, defaulted matrices)
+    ("scaling_default", 192, 128, 8, True, dict(log2_ctb_size=5, scaling_lists=1, qp=24)),
+    ("scaling_sps_ctb64", 256, 192, 8, True, dict(log2_ctb_size=6, scaling_lists=2, qp=26, wpp=1, max_transform_hierarchy_depth_intra=2)),
+    ("scaling_pps_main10_tskip", 160, 160, 10, True, dict(log2_ctb_size=5, scaling_lists=3, qp=22, transform_skip=1, mode_decision=0)),
 ]
 
 # More feature combinations, used by the CPU tests only (FFmpeg pin of the restatement, host front-end vs restatement):
@@ -57,6 +61,8 @@ SYNTH_CPU_EXTRA = [
     ("x_main12_highqp_nolf", 160, 96, 12, True, dict(log2_ctb_size=5, qp=45, deblocking_disabled=1, sign_data_hiding=0)),
     ("x_odd_8bit_wpp_random", 74, 58, 8, True, dict(log2_ctb_size=5, wpp=1, mode_decision=0, max_transform_hierarchy_depth_intra=3, cb_qp_offset=-5, cr_qp_offset=7)),
     ("x_main10_ctb64_qg8", 256, 128, 10, True, dict(log2_ctb_size=6, diff_cu_qp_delta_depth=3, dqp_range=12, qp=30)),
+    ("x_scaling_sps_mono_qp12", 136, 72, 8, False, dict(log2_ctb_size=4, scaling_lists=2, qp=12, seed=77)),
+    ("x_scaling_pps_slices_wpp", 256, 192, 8, True, dict(log2_ctb_size=5, scaling_lists=3, slice_ctb_rows=2, wpp=1, qp=30, seed=991)),
     ("x_slices_every_row_nolf_across", 192, 160, 8, True, dict(log2_ctb_size=5, slice_ctb_rows=1, loop_filter_across_slices=0, slice_loop_filter_across_slices=0)),
 ]
 
