@@ -160,6 +160,9 @@ typedef struct b200_hevc_enc_params {
   uint32_t seed;                     /* LCG seed (0xB200 + tile index) */
   int scaling_lists;                 /* 0 = off, 1 = scaling_list_enabled_flag with the default lists (Tables 7-5 / 7-6), 2 = lists coded in the SPS,
                                         3 = lists coded in the PPS (both with predicted / default / explicit matrices chosen by the LCG) */
+  int pcm;                           /* 0 = off; 1 = pcm_enabled_flag, some 2Nx2N coding units coded as PCM at the full bit depth; 2 = PCM bit depths
+                                        reduced by 1 (luma) / 2 (chroma) and pcm_loop_filter_disabled_flag = 1 */
+  int transquant_bypass;             /* 0 = off; 1 = transquant_bypass_enabled_flag, some coding units lossless; 2 = every coding unit lossless */
 } b200_hevc_enc_params;
 
 void b200_hevc_enc_params_default(b200_hevc_enc_params* p);

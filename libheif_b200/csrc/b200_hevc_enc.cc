@@ -21,7 +21,7 @@ namespace enc {
 enum { CTX_SAO_MERGE = 0, CTX_SAO_TYPE = 1, CTX_SPLIT_CU = 2, CTX_PART_MODE = 5, CTX_PREV_INTRA = 6,
        CTX_CHROMA_PRED = 7, CTX_SPLIT_TR = 8, CTX_CBF_LUMA = 11, CTX_CBF_CHROMA = 13, CTX_QP_DELTA = 18,
        CTX_TSKIP = 20, CTX_LAST_X = 22, CTX_LAST_Y = 40, CTX_CSBF = 58, CTX_SIG = 62, CTX_GT1 = 104,
-       CTX_GT2 = 128, CTX_COUNT = 134 };
+       CTX_GT2 = 128, CTX_TQ_BYPASS = 134, CTX_COUNT = 135 };
 
 static const uint8_t kCtxInitI[CTX_COUNT] = {
   153, 200, 139, 141, 157, 184, 184, 63, 153, 138, 138, 111, 141, 94, 138, 182, 154, 154, 154, 154, 139, 139,
@@ -31,7 +31,8 @@ static const uint8_t kCtxInitI[CTX_COUNT] = {
   111, 111, 125, 110, 110, 94, 124, 108, 124, 107, 125, 141, 179, 153, 125, 107, 125, 141, 179, 153, 125,
   107, 125, 141, 179, 153, 125, 140, 139, 182, 182, 152, 136, 152, 136, 153, 136, 139, 111, 136, 139, 111,
   140, 92, 137, 138, 140, 152, 138, 139, 153, 74, 149, 92, 139, 107, 122, 152, 140, 179, 166, 182, 140, 227, 122, 197,
-  138, 153, 136, 167, 152, 152};
+  138, 153, 136, 167, 152, 152,
+  154};                                        // cu_transquant_bypass_flag (Table 9-8)
 
 static const uint8_t kRangeLps[64][4] = {
   {128,176,208,240},{128,167,197,227},{128,158,187,216},{123,150,178,205},{116,142,169,195},{111,135,160,185},
@@ -156,6 +157,7 @@ struct Cabac {
     else { low -= 512; outstanding++; }
   }
   void bypass_bits(unsigned v, int n) { for (int i = n - 1; i >= 0; i--) bypass((v >> i) & 1); }
+  void restart() { low = 0; range = 510; outstanding = 0; first = true; }     // 9.3.2.5 after pcm_sample(): same bit writer, fresh interval
   void terminate(int b) {
     range -= 2;
     if (b) { low += range; range = 2; renorm(); put_bit((low >> 9) & 1); bw.put(((low >> 7) & 3) | 1, 2); bw.align_zero(); }
@@ -214,6 +216,7 @@ class Encoder {
         }
       }
     }
+    pcm_bd_y = p.pcm == 2 ? bd - 1 : bd; pcm_bd_c = p.pcm == 2 ? bd - 2 : bd;
     sl_on = p.scaling_lists != 0;
     if (sl_on) sl::derive(sl_lists, sl_f);
   }
@@ -247,6 +250,7 @@ class Encoder {
   int is_qp_delta_coded = 0, cu_qp_delta_val = 0, qpy_prev_qg = 0, last_cu_qpy = 0, first_qg = 1, cur_qpy = 0, qg_target_qp = 0;
   int cu_x0 = 0, cu_y0 = 0;
   sl::Lists sl_lists; sl::Factors sl_f; uint8_t sl_kind[4][6] = {}; bool sl_on = false;
+  int pcm_bd_y = 8, pcm_bd_c = 8; bool cu_bypass = false;
 
   void write_scaling_list_data(BitWriter& b) {                    // 7.3.4
     for (int s = 0; s < 4; s++) for (int m = 0; m < 6; m += (s == 3 ? 3 : 1)) {
@@ -329,7 +333,12 @@ class Encoder {
     if (sl_on) { b.put(P.scaling_lists == 2 ? 1 : 0, 1); if (P.scaling_lists == 2) write_scaling_list_data(b); }
     b.put(0, 1);                      // amp
     b.put(P.sao ? 1 : 0, 1);
-    b.put(0, 1);                      // pcm
+    b.put(P.pcm ? 1 : 0, 1);          // pcm_enabled
+    if (P.pcm) {
+      b.put(pcm_bd_y - 1, 4); b.put(pcm_bd_c - 1, 4);
+      b.ue(0); b.ue(std::min(5, log2ctb) - 3);                      // Log2MinIpcmCbSizeY = 3, Log2MaxIpcmCbSizeY = min(CtbLog2SizeY, 5)
+      b.put(P.pcm == 2 ? 1 : 0, 1);                                 // pcm_loop_filter_disabled_flag
+    }
     b.ue(0);                          // num_short_term_ref_pic_sets
     b.put(0, 1);                      // long_term_ref_pics_present
     b.put(0, 1);                      // temporal_mvp
@@ -364,7 +373,7 @@ class Encoder {
     b.se(P.cb_qp_offset); b.se(P.cr_qp_offset);
     b.put(P.slice_chroma_qp_offsets ? 1 : 0, 1);
     b.put(0, 1); b.put(0, 1);
-    b.put(0, 1);                      // transquant_bypass
+    b.put(P.transquant_bypass ? 1 : 0, 1);   // transquant_bypass_enabled
     b.put(0, 1);                      // tiles
     b.put(P.wpp ? 1 : 0, 1);
     b.put(P.loop_filter_across_slices ? 1 : 0, 1);
@@ -628,7 +637,7 @@ class Encoder {
       lev[i] = (int16_t)(coef[i] < 0 ? -l : l);
       any |= l != 0;
     }
-    if (any && P.sign_data_hiding) {
+    if (any && P.sign_data_hiding && !cu_bypass) {
       int l2sb = log2n - 2;
       for (int i = 0; i < (1 << (2 * l2sb)); i++) {
         int xs = g_scan_x[l2sb][scan][i], ys = g_scan_y[l2sb][scan][i];
@@ -651,7 +660,7 @@ class Encoder {
 
   void write_residual(const int16_t* lev, int log2n, int c, int scan, bool tskip) {
     const int n = 1 << log2n, l2sb = log2n - 2;
-    if (P.transform_skip && log2n == 2) cabac.bin(ctx[CTX_TSKIP + (c ? 1 : 0)], tskip);
+    if (P.transform_skip && log2n == 2 && !cu_bypass) cabac.bin(ctx[CTX_TSKIP + (c ? 1 : 0)], tskip);
     const uint8_t *sbx = g_scan_x[l2sb][scan], *sby = g_scan_y[l2sb][scan], *px = g_scan_x[2][scan], *py = g_scan_y[2][scan];
     int last_sb = -1, last_pos = -1;
     for (int i = (1 << (2 * l2sb)) - 1; i >= 0 && last_sb < 0; i--) for (int k = 15; k >= 0; k--)
@@ -725,7 +734,7 @@ class Encoder {
         first_sig = k;
       }
       if (any) carry = g1ctx;
-      bool hidden = P.sign_data_hiding && (last_sig - first_sig > 3);
+      bool hidden = P.sign_data_hiding && !cu_bypass && (last_sig - first_sig > 3);
       if (last_g1 >= 0) cabac.bin(ctx[CTX_GT2 + ctx_set + (c ? 4 : 0)], std::abs(v[last_g1]) > 2);
       for (int k = 15; k >= 0; k--) if (v[k] && (!hidden || k != first_sig)) cabac.bypass(v[k] < 0);
       int nsig = 0, rice = 0, cnt1 = 0;
@@ -758,6 +767,15 @@ class Encoder {
     predict(c, x0, y0, log2n, mode, pred);
     for (int y = 0; y < n; y++) for (int x = 0; x < n; x++) res[y * n + x] = (int)org[c][(size_t)(y0 + y) * st + x0 + x] - pred[y * n + x];
     bool dst4 = c == 0 && log2n == 2;
+    if (cu_bypass) {                                  // cu_transquant_bypass_flag: the residual is coded as is (8.6.2), lossless
+      r.tskip = false; r.scan = 0;
+      if (log2n == 2 || (log2n == 3 && c == 0)) { if (mode >= 6 && mode <= 14) r.scan = 2; else if (mode >= 22 && mode <= 30) r.scan = 1; }
+      r.cbf = false;
+      for (int i = 0; i < n * n; i++) { r.lev[i] = (int16_t)res[i]; r.cbf |= res[i] != 0; }
+      uint16_t* rq = rec[c].data();
+      for (int y = 0; y < n; y++) for (int x = 0; x < n; x++) rq[(size_t)(y0 + y) * st + x0 + x] = org[c][(size_t)(y0 + y) * st + x0 + x];
+      return;
+    }
     r.tskip = P.transform_skip && log2n == 2 && rng.range(4) == 0;
     r.scan = 0;
     if (log2n == 2 || (log2n == 3 && c == 0)) { if (mode >= 6 && mode <= 14) r.scan = 2; else if (mode >= 22 && mode <= 30) r.scan = 1; }
@@ -897,7 +915,36 @@ class Encoder {
   void coding_unit(int x0, int y0, int log2cb, int depth) {
     Cu cu{}; cu.x0 = x0; cu.y0 = y0; cu.log2cb = log2cb;
     const int n = 1 << log2cb;
+    cu_bypass = false;
+    if (P.transquant_bypass) { cu_bypass = P.transquant_bypass == 2 || rng.range(4) == 0; cabac.bin(ctx[CTX_TQ_BYPASS], cu_bypass); }
     if (log2cb == 3) { cu.nxn = rng.range(3) == 0; cabac.bin(ctx[CTX_PART_MODE], !cu.nxn); }
+    if (P.pcm && !cu.nxn && log2cb <= std::min(5, log2ctb)) {
+      const bool pcm = rng.range(6) == 0;
+      cabac.terminate(pcm ? 1 : 0);                   // pcm_flag (terminate bin); value 1: flush, stop bit, pcm_alignment_zero_bits
+      if (pcm) {
+        for (int c = 0; c < (chroma ? 3 : 1); c++) {
+          const int sh = c ? 1 : 0, pbd = c ? pcm_bd_c : pcm_bd_y, st = stride_of(c), m = n >> sh;
+          uint16_t* rq = rec[c].data();
+          for (int y = 0; y < m; y++) for (int x = 0; x < m; x++) {
+            const size_t idx = (size_t)((y0 >> sh) + y) * st + (x0 >> sh) + x;
+            const unsigned v = org[c][idx] >> (bd - pbd);
+            cabac.bw.put(v, pbd);                     // pcm_sample_luma / pcm_sample_chroma
+            rq[idx] = (uint16_t)(v << (bd - pbd));
+          }
+        }
+        cabac.restart();
+        for (int yy = 0; yy < n; yy += 4) for (int xx = 0; xx < n; xx += 4) {
+          const size_t idx = (size_t)((y0 + yy) >> 2) * w4 + ((x0 + xx) >> 2);
+          ipm4[idx] = 1; slice_of4[idx] = (uint16_t)(slice_idx + 1); cd4[idx] = (uint8_t)depth;       // a PCM unit counts as INTRA_DC for its neighbours (8.4.2)
+        }
+        // no transform tree, no cu_qp_delta: QpY = predicted QP (+ the delta already coded in this quantization group, 8.6.1)
+        const int pred_qp = P.cu_qp_delta ? predict_qpy(x0, y0) : slice_qp;
+        cur_qpy = P.cu_qp_delta ? pred_qp + (is_qp_delta_coded ? cu_qp_delta_val : 0) : slice_qp;
+        for (int yy = 0; yy < n; yy += 4) for (int xx = 0; xx < n; xx += 4) qp4[(size_t)((y0 + yy) >> 2) * w4 + ((x0 + xx) >> 2)] = (int8_t)cur_qpy;
+        last_cu_qpy = cur_qpy;
+        return;
+      }
+    }
     int np = cu.nxn ? 4 : 1, pb = cu.nxn ? n / 2 : n;
     int prev[4], mpm_idx[4], rem[4];
     for (int i = 0; i < np; i++) {

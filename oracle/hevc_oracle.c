@@ -82,6 +82,7 @@ typedef struct {
   int vui_signal, vui_full_range, vui_colour, vui_cp, vui_tc, vui_mc;
   int range_ext_unsupported;
   int sl_data_present; uint8_t sl[4][6][64], sl_dc[4][6];   /* ScalingList[sizeId][matrixId][i], scaling_list_dc_coef (7.3.4) */
+  int pcm_bd_y, pcm_bd_c, log2_min_pcm, log2_max_pcm, pcm_loop_filter_disabled;
 } sps_t;
 
 typedef struct {
@@ -216,7 +217,12 @@ static int parse_sps(const uint8_t* rbsp, size_t n, sps_t* s) {
     if (s->sl_data_present && parse_scaling_list_data(&b, s->sl, s->sl_dc) != HO_OK) return HO_ERROR;
   }
   s->amp = rd_bit(&b); s->sao = rd_bit(&b); s->pcm = rd_bit(&b);
-  if (s->pcm) return HO_UNSUPPORTED;
+  if (s->pcm) {                                                  /* 7.3.2.2: pcm_enabled_flag */
+    s->pcm_bd_y = 1 + rd_bits(&b, 4); s->pcm_bd_c = 1 + rd_bits(&b, 4);
+    s->log2_min_pcm = 3 + rd_ue(&b); s->log2_max_pcm = s->log2_min_pcm + rd_ue(&b);
+    s->pcm_loop_filter_disabled = rd_bit(&b);
+    if (s->pcm_bd_y > s->bit_depth || s->pcm_bd_c > s->bit_depth_c || s->log2_max_pcm > 5 || s->log2_max_pcm > s->log2_ctb || s->log2_min_pcm < s->log2_min_cb) return HO_ERROR;
+  }
   s->num_st_rps = rd_ue(&b);
   if (s->num_st_rps > 64) return HO_ERROR;
   for (int i = 0; i < s->num_st_rps; i++) parse_st_rps(&b, s, i, s->num_st_rps);
@@ -287,7 +293,6 @@ static int parse_pps(const uint8_t* rbsp, size_t n, pps_t* p) {
   p->tiles = rd_bit(&b);
   p->wpp = rd_bit(&b);
   if (p->tiles) return HO_UNSUPPORTED;
-  if (p->transquant_bypass) return HO_UNSUPPORTED;
   p->lf_across_slices = rd_bit(&b);
   p->deblock_control = rd_bit(&b);
   if (p->deblock_control) {
@@ -319,7 +324,7 @@ static int parse_pps(const uint8_t* rbsp, size_t n, pps_t* p) {
 enum { CTX_SAO_MERGE = 0, CTX_SAO_TYPE = 1, CTX_SPLIT_CU = 2, CTX_PART_MODE = 5, CTX_PREV_INTRA = 6,
        CTX_CHROMA_PRED = 7, CTX_SPLIT_TR = 8, CTX_CBF_LUMA = 11, CTX_CBF_CHROMA = 13, CTX_QP_DELTA = 18,
        CTX_TSKIP = 20, CTX_LAST_X = 22, CTX_LAST_Y = 40, CTX_CSBF = 58, CTX_SIG = 62, CTX_GT1 = 104,
-       CTX_GT2 = 128, CTX_COUNT = 134 };
+       CTX_GT2 = 128, CTX_TQ_BYPASS = 134, CTX_COUNT = 135 };
 
 /* Tables 9-5..9-37, initType 0 (I slices) */
 static const uint8_t ctx_init_I[CTX_COUNT] = {
@@ -340,7 +345,8 @@ static const uint8_t ctx_init_I[CTX_COUNT] = {
   111, 111, 125, 110, 110, 94, 124, 108, 124, 107, 125, 141, 179, 153, 125, 107, 125, 141, 179, 153, 125,
   107, 125, 141, 179, 153, 125, 140, 139, 182, 182, 152, 136, 152, 136, 153, 136, 139, 111, 136, 139, 111, /* sig */
   140, 92, 137, 138, 140, 152, 138, 139, 153, 74, 149, 92, 139, 107, 122, 152, 140, 179, 166, 182, 140, 227, 122, 197, /* gt1 */
-  138, 153, 136, 167, 152, 152          /* gt2 */
+  138, 153, 136, 167, 152, 152,         /* gt2 */
+  154                                   /* cu_transquant_bypass_flag */
 };
 
 /* Table 9-46 */
@@ -383,6 +389,8 @@ typedef struct {
   int8_t* qp4;                  /* QpY */
   uint8_t* tu_edge4;            /* bit0: left edge is a transform edge, bit1: top edge */
   uint8_t* cd4;                 /* coding quadtree depth */
+  uint8_t* nofilt4;             /* 1: samples the in-loop filters must leave unchanged (cu_transquant_bypass; pcm with pcm_loop_filter_disabled) */
+  int cu_bypass;                /* cu_transquant_bypass_flag of the current coding unit */
   /* per slice tables */
   int nslices;
   struct { int addr_rs, lf_across, deblock_disabled, beta_offset, tc_offset, cb_off, cr_off; } sl[1024];
@@ -644,7 +652,7 @@ static void residual_coding(dec_t* d, int x0, int y0, int log2n, int c, int pred
   int16_t coef[32 * 32];
   memset(coef, 0, sizeof(int16_t) * n * n);
   int tskip = 0;
-  if (d->p->transform_skip && log2n == 2) tskip = dec_bin(d, CTX_TSKIP + (c ? 1 : 0));
+  if (d->p->transform_skip && log2n == 2 && !d->cu_bypass) tskip = dec_bin(d, CTX_TSKIP + (c ? 1 : 0));   /* 7.3.8.11 */
   /* last significant coefficient position, 9.3.4.2.3 */
   int cmax = (log2n << 1) - 1, ctx_off, ctx_shift;
   if (c == 0) { ctx_off = 3 * (log2n - 2) + ((log2n - 1) >> 2); ctx_shift = (log2n + 1) >> 2; }
@@ -728,7 +736,7 @@ static void residual_coding(dec_t* d, int x0, int y0, int log2n, int c, int pred
       first_sig = k;
     }
     if (any_sig) greater1_ctx_carry = g1ctx;
-    int sign_hidden = d->p->sign_hiding && (last_sig - first_sig > 3);
+    int sign_hidden = d->p->sign_hiding && !d->cu_bypass && (last_sig - first_sig > 3);
     if (last_g1_pos >= 0) g2[last_g1_pos] = dec_bin(d, CTX_GT2 + ctx_set + (c ? 4 : 0));
     int sign[16] = {0};
     for (int k = 15; k >= 0; k--) if (sig[k] && (!sign_hidden || k != first_sig)) sign[k] = dec_bypass(d);
@@ -753,6 +761,7 @@ static void residual_coding(dec_t* d, int x0, int y0, int log2n, int c, int pred
       nsig++;
     }
   }
+  int16_t raw[32 * 32]; memcpy(raw, coef, sizeof(int16_t) * n * n);
   /* 8.6.3 / 8.6.4.2 scaling: m = 16 without scaling lists, else ScalingFactor[sizeId][matrixId][x][y] (7.4.5): the list in
      effect (PPS, else SPS, else default) mapped through the up-right diagonal scan, 8x8 lists replicated for 16x16 / 32x32
      with scaling_list_dc_coef at (0, 0); matrixId = cIdx for intra blocks (32x32: matrixId 0) */
@@ -786,6 +795,7 @@ static void residual_coding(dec_t* d, int x0, int y0, int log2n, int c, int pred
   }
   int res[32 * 32];
   inverse_transform(coef, res, log2n, bd, c == 0 && log2n == 2, tskip);
+  if (d->cu_bypass) for (int k = 0; k < n * n; k++) res[k] = raw[k];     /* 8.6.2: cu_transquant_bypass_flag -> r = TransCoeffLevel */
   uint16_t* pl = d->pl[c]; int st = d->stride[c], maxv = (1 << bd) - 1;
   for (int y = 0; y < n; y++) for (int x = 0; x < n; x++) {
     uint16_t* q = &pl[(y0 + y) * st + x0 + x];
@@ -915,8 +925,35 @@ static void coding_unit(dec_t* d, int x0, int y0, int log2cb, int cq_depth) {
   cu_t cu; memset(&cu, 0, sizeof cu);
   cu.x0 = x0; cu.y0 = y0; cu.log2cb = log2cb;
   int n = 1 << log2cb;
+  d->cu_bypass = d->p->transquant_bypass ? dec_bin(d, CTX_TQ_BYPASS) : 0;                  /* cu_transquant_bypass_flag */
   if (log2cb == s->log2_min_cb) cu.part_nxn = !dec_bin(d, CTX_PART_MODE);
   if (cu.part_nxn && log2cb == 3 && s->log2_min_tb > 2) { d->err = HO_ERROR; return; }
+  for (int yy = 0; yy < n; yy += 4) for (int xx = 0; xx < n; xx += 4)
+    if (x0 + xx < d->W && y0 + yy < d->H) d->nofilt4[((y0 + yy) >> 2) * d->w4 + ((x0 + xx) >> 2)] = (uint8_t)d->cu_bypass;
+  if (s->pcm && !cu.part_nxn && log2cb >= s->log2_min_pcm && log2cb <= s->log2_max_pcm && dec_terminate(d)) {
+    /* pcm_flag = 1 (7.3.8.5): pcm_alignment_zero_bits, pcm_sample(), then the arithmetic decoder starts over (9.3.2.5) */
+    d->br.pos = (d->br.pos + 7) & ~(size_t)7;
+    for (int c = 0; c < (s->chroma_format_idc ? 3 : 1); c++) {
+      int sh = c ? 1 : 0, pbd = c ? s->pcm_bd_c : s->pcm_bd_y, bdc = c ? s->bit_depth_c : s->bit_depth, m = n >> sh;
+      for (int y = 0; y < m; y++) for (int x = 0; x < m; x++) {
+        unsigned v = rd_bits(&d->br, pbd);
+        d->pl[c][((y0 >> sh) + y) * d->stride[c] + (x0 >> sh) + x] = (uint16_t)(v << (bdc - pbd));       /* 8.4.4.1: recSamples = pcm_sample << (BitDepth - PcmBitDepth) */
+        { unsigned long long hh = ((unsigned long long)x0 * 1000003ULL + (unsigned long long)y0) * 1000003ULL + (unsigned long long)c; hh = hh * 1000003ULL + (unsigned long long)(y * m + x); hh = hh * 1000003ULL + (unsigned long long)(unsigned short)v; hh ^= hh >> 29; hh *= 0x9E3779B97F4A7C15ULL; d->coef_hash += hh; d->coef_count++; }
+      }
+    }
+    cabac_init_engine(d);
+    if (!d->p->cu_qp_delta) d->cur_qpy = d->slice_qp; else derive_qpy(d, x0, y0);
+    d->tu_count++;
+    for (int yy = 0; yy < n; yy += 4) for (int xx = 0; xx < n; xx += 4)
+      if (x0 + xx < d->W && y0 + yy < d->H) {
+        int idx = ((y0 + yy) >> 2) * d->w4 + ((x0 + xx) >> 2);
+        d->ipm4[idx] = 1; d->cd4[idx] = (uint8_t)cq_depth; d->cmode4[idx] = 1;     /* a PCM unit is INTRA_DC for the mode derivation of its neighbours (8.4.2) */
+        if (s->pcm_loop_filter_disabled) d->nofilt4[idx] = 1;
+      }
+    mark_tu(d, x0, y0, log2cb);
+    d->last_cu_qpy = d->cur_qpy;
+    return;
+  }
   int np = cu.part_nxn ? 4 : 1, pb = cu.part_nxn ? n / 2 : n;
   int prev[4], mpm[4] = {0}, rem[4] = {0};
   for (int i = 0; i < np; i++) prev[i] = dec_bin(d, CTX_PREV_INTRA);
@@ -1047,7 +1084,7 @@ static int alloc_picture(dec_t* d) {
   size_t n4 = (size_t)d->w4 * d->h4;
   d->slice_of4 = (uint16_t*)calloc(n4, 2);
   d->ipm4 = (uint8_t*)calloc(n4, 1); d->qp4 = (int8_t*)calloc(n4, 1);
-  d->tu_edge4 = (uint8_t*)calloc(n4, 1); d->cd4 = (uint8_t*)calloc(n4, 1);
+  d->tu_edge4 = (uint8_t*)calloc(n4, 1); d->cd4 = (uint8_t*)calloc(n4, 1); d->nofilt4 = (uint8_t*)calloc(n4, 1);
   d->cmode4 = (uint8_t*)calloc(n4, 1);
   d->sao = (sao_params*)calloc((size_t)d->wctb * d->hctb, sizeof(sao_params));
   d->ctb_slice_sao = (uint8_t*)calloc((size_t)d->wctb * d->hctb, 1);
@@ -1195,6 +1232,9 @@ static void deblock_luma_edge(dec_t* d, int x, int y, int vert) {   /* one 4-sam
   int strong = s0 && s3;
   int dep = dp < ((beta + (beta >> 1)) >> 3), deq = dq < ((beta + (beta >> 1)) >> 3);
   int maxv = (1 << bd) - 1;
+  const int keep_p = d->nofilt4[j], keep_q = d->nofilt4[i];      /* nDp / nDq = 0 (8.7.2.5.7): pcm + pcm_loop_filter_disabled, cu_transquant_bypass */
+  uint16_t save[4][8];
+  for (int l = 0; l < 4; l++) for (int k = 0; k < 8; k++) save[l][k] = q[(k - 4) * xs + l * ls];
   for (int l = 0; l < 4; l++) {
     int p0 = P(0, l), p1 = P(1, l), p2 = P(2, l), p3 = P(3, l), q0 = Q(0, l), q1 = Q(1, l), q2 = Q(2, l), q3 = Q(3, l);
     if (strong) {
@@ -1215,6 +1255,7 @@ static void deblock_luma_edge(dec_t* d, int x, int y, int vert) {   /* one 4-sam
       }
     }
   }
+  for (int l = 0; l < 4; l++) for (int k = 0; k < 8; k++) if (k < 4 ? keep_p : keep_q) q[(k - 4) * xs + l * ls] = save[l][k];
 #undef P
 #undef Q
 }
@@ -1232,8 +1273,8 @@ static void deblock_chroma_edge(dec_t* d, int c, int x, int y, int vert) {  /* l
   for (int l = 0; l < 2; l++) {
     int p0 = q[-xs + l * ls], p1 = q[-2 * xs + l * ls], q0 = q[l * ls], q1 = q[xs + l * ls];
     int delta = clip3(-tc, tc, ((((q0 - p0) << 2) + p1 - q1 + 4) >> 3));
-    q[-xs + l * ls] = (uint16_t)clip3(0, maxv, p0 + delta);
-    q[l * ls] = (uint16_t)clip3(0, maxv, q0 - delta);
+    if (!d->nofilt4[j]) q[-xs + l * ls] = (uint16_t)clip3(0, maxv, p0 + delta);
+    if (!d->nofilt4[i]) q[l * ls] = (uint16_t)clip3(0, maxv, q0 - delta);
   }
 }
 
@@ -1266,6 +1307,7 @@ static void sao_picture(dec_t* d) {
       if (!on || sp->type[c] == 0) continue;
       for (int y = ry * cs; y < (ry + 1) * cs && y < h; y++) for (int x = rx * cs; x < (rx + 1) * cs && x < w; x++) {
         int v = src[y * st + x], idx;
+        if (d->nofilt4[((y << sh) >> 2) * d->w4 + ((x << sh) >> 2)]) continue;     /* 8.7.3: SaoTypeIdx treated as 0 for these samples */
         if (sp->type[c] == 1) {
           int k = ((v >> (bd - 5)) - sp->band_pos[c]) & 31;
           idx = k < 4 ? k + 1 : 0;
@@ -1297,7 +1339,7 @@ static void sao_picture(dec_t* d) {
 /* --------------------------------------------------------------------------------------- top level */
 static void free_dec(dec_t* d) {
   for (int c = 0; c < 3; c++) free(d->pl[c]);
-  free(d->cmode4); free(d->slice_of4); free(d->ipm4); free(d->qp4); free(d->tu_edge4); free(d->cd4); free(d->sao); free(d->ctb_slice_sao);
+  free(d->cmode4); free(d->slice_of4); free(d->ipm4); free(d->qp4); free(d->tu_edge4); free(d->cd4); free(d->nofilt4); free(d->sao); free(d->ctb_slice_sao);
 }
 
 void hevc_oracle_free_picture(hevc_oracle_picture* p) { for (int c = 0; c < 3; c++) { free(p->plane[c]); p->plane[c] = NULL; } }
