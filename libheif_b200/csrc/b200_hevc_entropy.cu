@@ -22,7 +22,7 @@ __shared__ uint32_t s_kLps4[64];
 __shared__ uint8_t s_kTransLps[64];
 __shared__ uint8_t s_kNextState[256];
 __shared__ unsigned long long s_kState[128];
-__shared__ uint8_t s_kInitI[134];
+__shared__ uint8_t s_kInitI[135];                     // CTX_COUNT (declared before the syntax header is included; checked below)
 __shared__ uint8_t s_kSigMap4[16];
 __shared__ uint8_t s_kScanPos[3][16];
 __shared__ uint8_t s_kScanInv[3][16];
@@ -37,6 +37,7 @@ __shared__ uint8_t s_kScanY[4][3][64];
 #define B200_T(name) s_##name
 #endif
 #include "b200_hevc.h"
+static_assert(b200::syn::CTX_COUNT == 135, "s_kInitI above is sized for 135 context variables");
 
 namespace b200 {
 
@@ -95,7 +96,7 @@ __global__ void __launch_bounds__(EWARPS * 32, B200_ENTROPY_MIN_BLOCKS) hevc_ent
   __shared__ __align__(8) syn::U2 s_ctx[EWARPS][syn::CTX_COUNT];   // context variables: one state-table entry each
   __shared__ syn::DecoderT<Cfg> s_dec[EWARPS];                    // per-warp decoder state (see run_substream)
   for (int i = threadIdx.x; i < 64; i += blockDim.x) { syn::s_kLps4[i] = syn::d_kLps4[i]; syn::s_kTransLps[i] = syn::d_kTransLps[i]; }
-  for (int i = threadIdx.x; i < 134; i += blockDim.x) syn::s_kInitI[i] = syn::d_kInitI[i];
+  for (int i = threadIdx.x; i < syn::CTX_COUNT; i += blockDim.x) syn::s_kInitI[i] = syn::d_kInitI[i];
   for (int i = threadIdx.x; i < 256; i += blockDim.x) syn::s_kNextState[i] = syn::d_kNextState[i];
   for (int i = threadIdx.x; i < 128; i += blockDim.x) syn::s_kState[i] = syn::d_kState[i];
   for (int i = threadIdx.x; i < 16; i += blockDim.x) syn::s_kSigMap4[i] = syn::d_kSigMap4[i];

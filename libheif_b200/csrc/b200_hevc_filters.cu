@@ -33,6 +33,7 @@ __global__ void __launch_bounds__(256) deblock_kernel(const DeviceBatch b, int m
   const int bi = (y >> 3) * pic.w8 + (x >> 3);
   if (!(edge8[bi] & (VERT ? 1 : 2))) return;
   const int bj = VERT ? bi - 1 : bi - pic.w8;
+  const bool keep_q = edge8[bi] & 4, keep_p = edge8[bj] & 4;       // cu_transquant_bypass, pcm + pcm_loop_filter_disabled: nDq / nDp = 0 (8.7.2.5.7)
   const CtuInfo& ci = b.ctus[pic.ctu_base + (y >> pic.log2_ctb) * pic.wctb + (x >> pic.log2_ctb)];
   const SliceInfo sl = b.slices[pic.slice_base + ci.slice_idx];
   const int bd = pic.bit_depth, maxv = (1 << bd) - 1;
@@ -64,20 +65,24 @@ __global__ void __launch_bounds__(256) deblock_kernel(const DeviceBatch b, int m
         const int p0 = P_(0, l), p1 = P_(1, l), p2 = P_(2, l), p3 = P_(3, l), q0 = Q_(0, l), q1 = Q_(1, l), q2 = Q_(2, l), q3 = Q_(3, l);
         T* ql = q + (ptrdiff_t)l * ls;
         if (strong) {
-          ql[-1 * (ptrdiff_t)xs] = (T)clip3d(p0 - 2 * tc, p0 + 2 * tc, (p2 + 2 * p1 + 2 * p0 + 2 * q0 + q1 + 4) >> 3);
-          ql[-2 * (ptrdiff_t)xs] = (T)clip3d(p1 - 2 * tc, p1 + 2 * tc, (p2 + p1 + p0 + q0 + 2) >> 2);
-          ql[-3 * (ptrdiff_t)xs] = (T)clip3d(p2 - 2 * tc, p2 + 2 * tc, (2 * p3 + 3 * p2 + p1 + p0 + q0 + 4) >> 3);
-          ql[0] = (T)clip3d(q0 - 2 * tc, q0 + 2 * tc, (p1 + 2 * p0 + 2 * q0 + 2 * q1 + q2 + 4) >> 3);
-          ql[xs] = (T)clip3d(q1 - 2 * tc, q1 + 2 * tc, (p0 + q0 + q1 + q2 + 2) >> 2);
-          ql[2 * (ptrdiff_t)xs] = (T)clip3d(q2 - 2 * tc, q2 + 2 * tc, (p0 + q0 + q1 + 3 * q2 + 2 * q3 + 4) >> 3);
+          if (!keep_p) {
+            ql[-1 * (ptrdiff_t)xs] = (T)clip3d(p0 - 2 * tc, p0 + 2 * tc, (p2 + 2 * p1 + 2 * p0 + 2 * q0 + q1 + 4) >> 3);
+            ql[-2 * (ptrdiff_t)xs] = (T)clip3d(p1 - 2 * tc, p1 + 2 * tc, (p2 + p1 + p0 + q0 + 2) >> 2);
+            ql[-3 * (ptrdiff_t)xs] = (T)clip3d(p2 - 2 * tc, p2 + 2 * tc, (2 * p3 + 3 * p2 + p1 + p0 + q0 + 4) >> 3);
+          }
+          if (!keep_q) {
+            ql[0] = (T)clip3d(q0 - 2 * tc, q0 + 2 * tc, (p1 + 2 * p0 + 2 * q0 + 2 * q1 + q2 + 4) >> 3);
+            ql[xs] = (T)clip3d(q1 - 2 * tc, q1 + 2 * tc, (p0 + q0 + q1 + q2 + 2) >> 2);
+            ql[2 * (ptrdiff_t)xs] = (T)clip3d(q2 - 2 * tc, q2 + 2 * tc, (p0 + q0 + q1 + 3 * q2 + 2 * q3 + 4) >> 3);
+          }
         } else {
           int delta = (9 * (q0 - p0) - 3 * (q1 - p1) + 8) >> 4;
           if (abs(delta) < tc * 10) {
             delta = clip3d(-tc, tc, delta);
-            ql[-1 * (ptrdiff_t)xs] = (T)clip3d(0, maxv, p0 + delta);
-            ql[0] = (T)clip3d(0, maxv, q0 - delta);
-            if (dep) ql[-2 * (ptrdiff_t)xs] = (T)clip3d(0, maxv, p1 + clip3d(-(tc >> 1), tc >> 1, (((p2 + p0 + 1) >> 1) - p1 + delta) >> 1));
-            if (deq) ql[xs] = (T)clip3d(0, maxv, q1 + clip3d(-(tc >> 1), tc >> 1, (((q2 + q0 + 1) >> 1) - q1 - delta) >> 1));
+            if (!keep_p) ql[-1 * (ptrdiff_t)xs] = (T)clip3d(0, maxv, p0 + delta);
+            if (!keep_q) ql[0] = (T)clip3d(0, maxv, q0 - delta);
+            if (dep && !keep_p) ql[-2 * (ptrdiff_t)xs] = (T)clip3d(0, maxv, p1 + clip3d(-(tc >> 1), tc >> 1, (((p2 + p0 + 1) >> 1) - p1 + delta) >> 1));
+            if (deq && !keep_q) ql[xs] = (T)clip3d(0, maxv, q1 + clip3d(-(tc >> 1), tc >> 1, (((q2 + q0 + 1) >> 1) - q1 - delta) >> 1));
           }
         }
       }
@@ -100,8 +105,8 @@ __global__ void __launch_bounds__(256) deblock_kernel(const DeviceBatch b, int m
         T* ql = q + (ptrdiff_t)l * ls;
         const int p0 = ql[-(ptrdiff_t)xs], p1 = ql[-2 * (ptrdiff_t)xs], q0 = ql[0], q1 = ql[xs];
         const int delta = clip3d(-tc, tc, ((((q0 - p0) << 2) + p1 - q1 + 4) >> 3));
-        ql[-(ptrdiff_t)xs] = (T)clip3d(0, maxv, p0 + delta);
-        ql[0] = (T)clip3d(0, maxv, q0 - delta);
+        if (!keep_p) ql[-(ptrdiff_t)xs] = (T)clip3d(0, maxv, p0 + delta);
+        if (!keep_q) ql[0] = (T)clip3d(0, maxv, q0 - delta);
       }
     }
   }
@@ -222,6 +227,16 @@ __global__ void __launch_bounds__(256) sao_kernel(const DeviceBatch b) {
         }
         res[k] = clip3d(0, maxv, v + off);
       }
+    }
+  }
+  {
+    // cu_transquant_bypass / pcm + pcm_loop_filter_disabled (8.7.3: SaoTypeIdx is treated as 0 there): bit 2 of the 8x8 luma cells
+    const uint8_t* cell = b.edge8 + pic.map8_base + ((y << sh) >> 3) * pic.w8 + ((x0 << sh) >> 3);
+    const bool k0 = cell[0] & 4, k1 = sh ? (((x0 + 4) << 1) < pic.width && (cell[1] & 4)) : k0;
+    if (k0 | k1) {
+      const T* row = src + (size_t)y * st + x0;
+#pragma unroll
+      for (int k = 0; k < 8; k++) if (k < n && (k < 4 ? k0 : k1)) res[k] = (int)row[k];
     }
   }
   // store (conformance window applied; destination already offset to the tile's paste position)

@@ -34,6 +34,7 @@ struct Sps {
   int st_num_delta[65] = {0};
   int vui_signal = 0, vui_full_range = 0, vui_colour = 0, vui_cp = 2, vui_tc = 2, vui_mc = 2;
   int scaling_enabled = 0, sl_present = 0; sl::Lists lists;
+  int pcm = 0, pcm_bd_y = 8, pcm_bd_c = 8, log2_min_pcm = 3, log2_max_pcm = 3, pcm_lf_disabled = 0;
 };
 struct Pps {
   bool valid = false; int sps_id = 0, dependent_slices = 0, output_flag_present = 0, num_extra_bits = 0, sign_hiding = 0;
@@ -41,6 +42,7 @@ struct Pps {
   int slice_chroma_qp_offsets = 0, wpp = 0, lf_across_slices = 0, deblock_override_enabled = 0, deblock_disabled = 0;
   int beta_offset = 0, tc_offset = 0, slice_ext_present = 0, log2_sao_scale_luma = 0, log2_sao_scale_chroma = 0;
   int sl_present = 0; sl::Lists lists;
+  int tq_bypass = 0;
 };
 
 inline int clip3(int lo, int hi, int v) { return v < lo ? lo : (v > hi ? hi : v); }
@@ -189,7 +191,17 @@ class HeaderParser {
     s.scaling_enabled = b.bit();
     if (s.scaling_enabled) { s.sl_present = b.bit(); if (s.sl_present && !scaling_list_data(b, s.lists)) return set_error(B200_E_BITSTREAM, "sps scaling_list_data"); }
     b.bit(); s.sao = b.bit();
-    if (b.bit()) return set_error(B200_E_UNSUPPORTED, "PCM is not supported");
+    s.pcm = b.bit();
+    if (s.pcm) {                                                               // 7.4.3.2.1: PCM bit depths and coding block sizes
+      s.pcm_bd_y = 1 + (int)b.bits(4); s.pcm_bd_c = 1 + (int)b.bits(4);
+      const unsigned lo = b.ue(), df = b.ue();
+      if (lo > 2 || df > 2) return set_error(B200_E_BITSTREAM, "pcm coding block size");
+      s.log2_min_pcm = 3 + (int)lo; s.log2_max_pcm = s.log2_min_pcm + (int)df;
+      s.pcm_lf_disabled = b.bit();
+      if (s.pcm_bd_y > s.bit_depth || s.pcm_bd_c > bdc) return set_error(B200_E_BITSTREAM, "pcm sample bit depth");
+      if (s.log2_min_pcm < std::min(s.log2_min_cb, 5) || s.log2_min_pcm > std::min(s.log2_ctb, 5) || s.log2_max_pcm > std::min(s.log2_ctb, 5))
+        return set_error(B200_E_BITSTREAM, "pcm coding block size");
+    }
     { const unsigned v = b.ue(); if (v > 64) return set_error(B200_E_BITSTREAM, "num_short_term_ref_pic_sets"); s.num_st_rps = (int)v; }
     for (int i = 0; i < s.num_st_rps; i++) if (!st_rps(b, s, i, s.num_st_rps)) return set_error(B200_E_BITSTREAM, "short-term reference picture set %d", i);
     s.long_term = b.bit();
@@ -232,7 +244,7 @@ class HeaderParser {
     p.cb_qp_offset = b.se(); p.cr_qp_offset = b.se(); p.slice_chroma_qp_offsets = b.bit();
     if (p.cb_qp_offset < -12 || p.cb_qp_offset > 12 || p.cr_qp_offset < -12 || p.cr_qp_offset > 12) return set_error(B200_E_BITSTREAM, "pps chroma qp offset");
     b.bit(); b.bit();
-    if (b.bit()) return set_error(B200_E_UNSUPPORTED, "transquant bypass is not supported");
+    p.tq_bypass = b.bit();
     if (b.bit()) return set_error(B200_E_UNSUPPORTED, "HEVC tiles are not supported");
     p.wpp = b.bit();
     p.lf_across_slices = b.bit();
@@ -290,6 +302,8 @@ class HeaderParser {
     q.chroma = d.chroma; q.bd = d.bit_depth;
     q.log2_min_cb = S->log2_min_cb; q.log2_min_tb = S->log2_min_tb; q.log2_max_tb = S->log2_max_tb; q.max_th_depth_intra = S->max_th_depth_intra;
     q.sao_enabled = S->sao; q.transform_skip = PP->transform_skip; q.cu_qp_delta = PP->cu_qp_delta; q.qg_log2 = d.log2_ctb - PP->diff_cu_qp_delta_depth;
+    q.pcm = S->pcm; q.pcm_shift_y = d.bit_depth - S->pcm_bd_y; q.pcm_shift_c = d.bit_depth - S->pcm_bd_c; q.pcm_bd_y = S->pcm_bd_y; q.pcm_bd_c = S->pcm_bd_c;
+    q.log2_min_pcm = S->log2_min_pcm; q.log2_max_pcm = S->log2_max_pcm; q.pcm_lf_disabled = S->pcm_lf_disabled; q.tq_bypass = PP->tq_bypass;
     q.sign_hiding = PP->sign_hiding; q.wpp = PP->wpp; q.sao_scale_luma = PP->log2_sao_scale_luma; q.sao_scale_chroma = PP->log2_sao_scale_chroma;
     const int ctb = 1 << d.log2_ctb;
     q.tu_slots = (ctb / 4) * (ctb / 4); q.coef_slots = ctb * ctb * (d.chroma ? 3 : 2) / 2;

@@ -104,7 +104,7 @@ __device__ __forceinline__ int dequant(int level, int qp, int bd_shift, int m) {
 
 // Descriptor of one transform block, built in phase A, consumed in phase B (uint2):
 //  x: bx/4 [0:4) by/4 [4:8) log2n-2 [8:10) mode [10:16) coded [16] (Cr: [17]) availL [18] availCorner [19] availTop [20]
-//     available below-left samples / 4 [21:25)  available above-right samples / 4 [25:29)
+//     available below-left samples / 4 [21:25)  available above-right samples / 4 [25:29)  pcm [29]: the "residuals" are the samples
 //  y: offset of the block's residuals inside the component's residual area (samples)
 __device__ __forceinline__ unsigned make_desc(int bx, int by, int lg, int mode, int coded0, int coded1, int cs, int cx0, int cy0, int cw, int ch,
                                               bool nbL, bool nbAL, bool nbA, bool nbAR) {
@@ -127,8 +127,8 @@ __device__ __forceinline__ unsigned make_desc(int bx, int by, int lg, int mode, 
 
 // ---- phase A, 4x4 blocks: the calling lane owns the block.  scr: the warp's [16][32] int16 scratch (column = lane).
 template <bool LIVE>
-__device__ __forceinline__ void residual4_lane(int16_t* scr, int lane, const CoefEntry* __restrict__ ce, int nnz, int qp, int bd, bool dst, bool tskip, int16_t* out,
-                                               const uint8_t* __restrict__ sf) {      // sf: the 16 scaling factors of this component (raster), or nullptr
+__device__ __forceinline__ void residual4_lane(int16_t* scr, int lane, const CoefEntry* __restrict__ ce, int nnz, int qp, int bd, bool dst, bool tskip, bool raw, int16_t* out,
+                                               const uint8_t* __restrict__ sf) {      // raw: cu_transquant_bypass / pcm, the levels ARE the residuals (8.6.2)      // sf: the 16 scaling factors of this component (raster), or nullptr
   int16_t* my = scr + lane;
 #pragma unroll
   for (int p = 0; p < 16; p++) my[p * 32] = 0;
@@ -136,13 +136,18 @@ __device__ __forceinline__ void residual4_lane(int16_t* scr, int lane, const Coe
 #pragma unroll 1
   for (int i = 0; i < nnz; i++) {
     const CoefEntry e = ld_coef<LIVE>(&ce[i]);
-    my[(e.pos & 15) * 32] = (int16_t)dequant(e.level, qp, bd_shift, sf ? (int)__ldg(sf + (e.pos & 15)) : 16);
+    my[(e.pos & 15) * 32] = raw ? e.level : (int16_t)dequant(e.level, qp, bd_shift, sf ? (int)__ldg(sf + (e.pos & 15)) : 16);
   }
   int c[16];
 #pragma unroll
   for (int p = 0; p < 16; p++) c[p] = my[p * 32];
   const int bs2 = 20 - bd, rnd = 1 << (bs2 - 1);
   unsigned* o32 = reinterpret_cast<unsigned*>(out);
+  if (raw) {
+#pragma unroll
+    for (int p = 0; p < 16; p += 2) o32[p >> 1] = (unsigned)(c[p] & 0xffff) | ((unsigned)c[p + 1] << 16);
+    return;
+  }
   if (tskip) {                                        // 8.6.4.2, transform_skip_flag: r = d << 7
 #pragma unroll
     for (int p = 0; p < 16; p += 2) {
@@ -188,7 +193,7 @@ __device__ __forceinline__ void residual4_lane(int16_t* scr, int lane, const Coe
 // ---- phase A, 8x8 .. 32x32 blocks: the whole warp, in place in the block's residual slot (coefficients -> residuals).
 template <bool LIVE>
 __device__ __noinline__ void residual_big(int16_t* rs, int16_t* tmp, const int8_t* __restrict__ mat, const CoefEntry* __restrict__ ce, int nnz, int lg, int qp, int bd, int lane,
-                                          const uint8_t* __restrict__ sf, int sf_dc) {   // sf: 8x8 raster scaling factors of (component, size) or nullptr; sf_dc: factor of position (0, 0) for 16x16 / 32x32
+                                          const uint8_t* __restrict__ sf, int sf_dc, bool raw) {   // sf: 8x8 raster scaling factors of (component, size) or nullptr; sf_dc: factor of position (0, 0) for 16x16 / 32x32
   const int n = 1 << lg;
   unsigned* z = reinterpret_cast<unsigned*>(rs);
 #pragma unroll 1
@@ -202,11 +207,12 @@ __device__ __noinline__ void residual_big(int16_t* rs, int16_t* tmp, const int8_
     const int pos = e.pos & (n * n - 1);
     int m = 16;
     if (sf) { const int x = pos & (n - 1), y = pos >> lg; m = (pos == 0 && lg >= 4) ? sf_dc : (int)__ldg(sf + ((y >> (lg - 3)) << 3) + (x >> (lg - 3))); }
-    rs[pos] = (int16_t)dequant(e.level, qp, bd_shift, m);
+    rs[pos] = raw ? e.level : (int16_t)dequant(e.level, qp, bd_shift, m);
     maxrow = max(maxrow, pos >> lg); maxcol = max(maxcol, pos & (n - 1));
   }
   maxrow = __reduce_max_sync(0xffffffffu, maxrow); maxcol = __reduce_max_sync(0xffffffffu, maxcol);
   __syncwarp();
+  if (raw) return;                                    // cu_transquant_bypass / pcm (warp-uniform): no scaling, no transform
   const int mstride = 32 << (5 - lg);                 // row k of the n-point DCT = row k << (5 - log2n) of the 32-point one
   // first stage (columns): tmp[x][y] = clip16((sum_k coef[k][x] * M[k][y] + 64) >> 7), only columns that hold coefficients
 #pragma unroll 1
@@ -239,7 +245,7 @@ template <typename P>
 __device__ __forceinline__ void predict_tb(const uint2 d, P* tl, const P* tp, const int16_t* rs, int16_t* rf, int S, int l, int lpc, unsigned gmask, int cidx, bool luma, int bd, int strong_en) {
   const int bx = (int)(d.x & 15) << 2, by = (int)((d.x >> 4) & 15) << 2, lg = 2 + (int)((d.x >> 8) & 3), mode = (int)((d.x >> 10) & 63);
   const int n = 1 << lg, n2 = 2 * n, n4 = 4 * n;
-  const bool coded = (d.x >> (16 + cidx)) & 1;
+  const bool coded = (d.x >> (16 + cidx)) & 1, pcm = (d.x >> 29) & 1;
   const bool fL = (d.x >> 18) & 1, fC = (d.x >> 19) & 1, fT = (d.x >> 20) & 1;
   const int blc = (int)((d.x >> 21) & 15) << 2, trc = (int)((d.x >> 25) & 15) << 2;
   // ---- neighbour array rf[0 .. 4n]: index 0 = bottom of the below-left column ... 2n = corner ... 4n = end of above-right.
@@ -317,6 +323,7 @@ __device__ __forceinline__ void predict_tb(const uint2 d, P* tl, const P* tp, co
   for (int e = l; e < n * n; e += lpc) {
     const int x = e & (n - 1), y = e >> lg;
     int v;
+    if (pcm) { out[y * S + x] = (P)rsb[e]; continue; }                   // 8.4.4.1: no prediction
     if (mode == 0) v = ((n - 1 - x) * LEFT(y) + (x + 1) * TOP(n) + (n - 1 - y) * TOP(x) + (y + 1) * LEFT(n) + n) >> (lg + 1);
     else if (mode == 1) {
       v = dc;
@@ -432,6 +439,7 @@ __global__ void __launch_bounds__(WARPS * 32, B200_RECON_MIN_BLOCKS) hevc_recon_
         const int log2n = 2 + (int)((cmd.w0 >> 24) & 3);
         const int lx = (int)((cmd.w0 & 0xfff) << 2) - x0, ly = (int)(((cmd.w0 >> 12) & 0xfff) << 2) - y0;   // luma position inside the CTB
         const int qpy = (int)((cmd.w1 >> 12) & 0xff) - 64;
+        const bool pcm = (cmd.w1 >> 21) & 1, raw = ((cmd.w1 >> 21) & 3) != 0;
         const int nl = (int)(cmd.w3 & 0x7ff), ncb = (int)((cmd.w3 >> 11) & 0x3ff), ncr = (int)((cmd.w3 >> 21) & 0x3ff);
         const CoefEntry* ce = coefs + cmd.w2;
         bool has; int bx, by, lg, mode, coded0, coded1, qp0, qp1 = 0, ts0, ts1 = 0, n0, n1 = 0; const CoefEntry* ce1 = ce;
@@ -451,14 +459,14 @@ __global__ void __launch_bounds__(WARPS * 32, B200_RECON_MIN_BLOCKS) hevc_recon_
         const unsigned hb = __ballot_sync(0xffffffffu, has);
         const int idx = ntb + __popc(hb & lt_mask);
         const unsigned roff = morton4((unsigned)bx >> 2, (unsigned)by >> 2) * 16;
-        if (has) desc[idx] = make_uint2(make_desc(bx, by, lg, mode, coded0, coded1, cs, cx0, cy0, cw, ch, nbL, nbAL, nbA, nbAR), roff);
+        if (has) desc[idx] = make_uint2(make_desc(bx, by, lg, mode, coded0, coded1, cs, cx0, cy0, cw, ch, nbL, nbAL, nbA, nbAR) | ((unsigned)pcm << 29), roff);
         ntb += __popc(hb);
         // 4x4 blocks: one lane each, in registers
         if (lg == 2) {
 #pragma unroll 1
           for (int c2 = 0; c2 < 2; c2++)
             if (c2 ? coded1 : coded0)
-              residual4_lane<LIVE>(tmp, lane, c2 ? ce1 : ce, c2 ? n1 : n0, c2 ? qp1 : qp0, bd, g == 0, c2 ? ts1 : ts0, res0 + (c2 ? cs * cs : 0) + roff,
+              residual4_lane<LIVE>(tmp, lane, c2 ? ce1 : ce, c2 ? n1 : n0, c2 ? qp1 : qp0, bd, g == 0, c2 ? ts1 : ts0, raw, res0 + (c2 ? cs * cs : 0) + roff,
                                    sfac ? sfac + (g + c2) * 256 : nullptr);
         }
         __syncwarp();
@@ -471,9 +479,9 @@ __global__ void __launch_bounds__(WARPS * 32, B200_RECON_MIN_BLOCKS) hevc_recon_
             const int src = __ffs(m) - 1; m &= m - 1;
             const unsigned long long cp = __shfl_sync(0xffffffffu, (unsigned long long)(c2 ? ce1 : ce), src);
             const int nn = __shfl_sync(0xffffffffu, c2 ? n1 : n0, src), lgg = __shfl_sync(0xffffffffu, lg, src), qq = __shfl_sync(0xffffffffu, c2 ? qp1 : qp0, src);
-            const unsigned ro = __shfl_sync(0xffffffffu, roff, src);
+            const unsigned ro = __shfl_sync(0xffffffffu, roff, src); const bool rw = __shfl_sync(0xffffffffu, (int)raw, src) != 0;
             residual_big<LIVE>(res0 + (c2 ? cs * cs : 0) + ro, tmp, mat, reinterpret_cast<const CoefEntry*>(cp), nn, lgg, qq, bd, lane,
-                               sfac ? sfac + (g + c2) * 256 + (lgg - 2) * 64 : nullptr, sfac ? (int)sfac[768 + (g + c2) * 4 + (lgg - 2)] : 16);
+                               sfac ? sfac + (g + c2) * 256 + (lgg - 2) * 64 : nullptr, sfac ? (int)sfac[768 + (g + c2) * 4 + (lgg - 2)] : 16, rw);
           }
         }
       }

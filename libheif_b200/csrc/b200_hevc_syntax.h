@@ -75,7 +75,7 @@ inline U2 tab_ld64(TabPtr p, int i) { uint64_t v; memcpy(&v, p + 8 * (size_t)i, 
 enum { CTX_SAO_MERGE = 0, CTX_SAO_TYPE = 1, CTX_SPLIT_CU = 2, CTX_PART_MODE = 5, CTX_PREV_INTRA = 6,
        CTX_CHROMA_PRED = 7, CTX_SPLIT_TR = 8, CTX_CBF_LUMA = 11, CTX_CBF_CHROMA = 13, CTX_QP_DELTA = 18,
        CTX_TSKIP = 20, CTX_LAST_X = 22, CTX_LAST_Y = 40, CTX_CSBF = 58, CTX_SIG = 62, CTX_GT1 = 104,
-       CTX_GT2 = 128, CTX_COUNT = 134, CTX_STRIDE = 144 };
+       CTX_GT2 = 128, CTX_TQ_BYPASS = 134, CTX_COUNT = 135, CTX_STRIDE = 144 };
 
 // Tables 9-5 .. 9-37, initType 0 (I slices)
 B200_TABLE(uint8_t, kInitI, [CTX_COUNT], {
@@ -86,7 +86,8 @@ B200_TABLE(uint8_t, kInitI, [CTX_COUNT], {
   111, 111, 125, 110, 110, 94, 124, 108, 124, 107, 125, 141, 179, 153, 125, 107, 125, 141, 179, 153, 125,
   107, 125, 141, 179, 153, 125, 140, 139, 182, 182, 152, 136, 152, 136, 153, 136, 139, 111, 136, 139, 111,
   140, 92, 137, 138, 140, 152, 138, 139, 153, 74, 149, 92, 139, 107, 122, 152, 140, 179, 166, 182, 140, 227, 122, 197,
-  138, 153, 136, 167, 152, 152})
+  138, 153, 136, 167, 152, 152,
+  154})
 // Table 9-46 (rangeTabLps) and 9-47 (transIdxLps)
 B200_TABLE(uint32_t, kLps4, [64], {0xf0d0b080u, 0xe3c5a780u, 0xd8bb9e80u, 0xcdb2967bu, 0xc3a98e74u, 0xb9a0876fu, 0xaf988069u, 0xa6907a64u, 0x9e89745fu, 0x96826e5au, 0x8e7b6855u, 0x87756351u, 0x806f5e4du, 0x7a695949u, 0x74645545u, 0x6e5f5042u, 0x685a4c3eu, 0x6356483bu, 0x5e514538u, 0x594d4135u, 0x55493e33u, 0x50453b30u, 0x4c42382eu, 0x483f352bu, 0x453b3229u, 0x41383027u, 0x3e362d25u, 0x3b332b23u, 0x38302921u, 0x352e2720u, 0x322b251eu, 0x3029231du, 0x2d27211bu, 0x2b251f1au, 0x29231e18u, 0x27211c17u, 0x25201b16u, 0x231e1a15u, 0x211d1814u, 0x1f1b1713u, 0x1e1a1612u, 0x1c191511u, 0x1b171410u, 0x1916130fu, 0x1815120eu, 0x1714110eu, 0x1613100du, 0x15120f0cu, 0x14110e0cu, 0x13100e0bu, 0x120f0d0bu, 0x110f0c0au, 0x100e0c0au, 0x0f0d0b09u, 0x0e0c0b09u, 0x0e0c0a08u, 0x0d0b0908u, 0x0c0b0907u, 0x0c0a0907u, 0x0b0a0807u, 0x0b090806u, 0x0a090706u, 0x09080706u, 0x02020202u})   // rangeTabLps[state][0..3] packed little-endian
 B200_TABLE(uint8_t, kTransLps, [64], {0,0,1,2,2,4,4,5,6,7,8,9,9,11,11,12,13,13,15,15,16,16,18,18,19,19,21,21,22,22,23,24,
@@ -124,6 +125,8 @@ struct SeqParams {
   int32_t sao_enabled, transform_skip, cu_qp_delta, qg_log2, sign_hiding, wpp, sao_scale_luma, sao_scale_chroma;
   int32_t dense;                 // 1: outputs appended densely (host, sequential); 0: fixed per-CTB slots (device, concurrent)
   int32_t tu_slots, coef_slots;  // per-CTB capacity when !dense
+  int32_t pcm, pcm_bd_y, pcm_bd_c, pcm_shift_y, pcm_shift_c, log2_min_pcm, log2_max_pcm, pcm_lf_disabled;   // 7.4.3.2.1 (shift = BitDepth - PcmBitDepth)
+  int32_t tq_bypass;             // transquant_bypass_enabled_flag
 };
 
 // One CABAC sub-stream.
@@ -284,11 +287,11 @@ struct SaoRaw { int8_t type[3], band[3], eo[3]; int8_t off[3][4]; };
 // combination of x265-produced HEIC files (and of libheif/examples/example.heic: 4:2:0 8 bit, min CB 8, TB 4..32, no
 // transform skip, cu_qp_delta + sign data hiding + SAO on, WPP); the kernel's speed is set by its instruction-cache
 // footprint (profiles/README.md), and the constants remove ~5 KB of it.  The host front-end uses CfgRuntime.
-struct CfgRuntime { enum : int { chroma = -1, bd = -1, log2_min_cb = -1, log2_min_tb = -1, log2_max_tb = -1, transform_skip = -1, cu_qp_delta = -1, sign_hiding = -1, sao_enabled = -1, wpp = -1, dense = -1 }; };
-struct CfgCommon { enum : int { chroma = 1, bd = 8, log2_min_cb = 3, log2_min_tb = 2, log2_max_tb = 5, transform_skip = 0, cu_qp_delta = 1, sign_hiding = 1, sao_enabled = 1, wpp = 1, dense = 0 }; };
+struct CfgRuntime { enum : int { chroma = -1, bd = -1, log2_min_cb = -1, log2_min_tb = -1, log2_max_tb = -1, transform_skip = -1, cu_qp_delta = -1, sign_hiding = -1, sao_enabled = -1, wpp = -1, dense = -1, pcm = -1, tq_bypass = -1 }; };
+struct CfgCommon { enum : int { chroma = 1, bd = 8, log2_min_cb = 3, log2_min_tb = 2, log2_max_tb = 5, transform_skip = 0, cu_qp_delta = 1, sign_hiding = 1, sao_enabled = 1, wpp = 1, dense = 0, pcm = 0, tq_bypass = 0 }; };
 B200_HD inline bool matches_common(const SeqParams& q) {
   return q.chroma == 1 && q.bd == 8 && q.log2_min_cb == 3 && q.log2_min_tb == 2 && q.log2_max_tb == 5 && !q.transform_skip && q.cu_qp_delta == 1 && q.sign_hiding == 1 &&
-         q.sao_enabled == 1 && q.wpp == 1 && q.dense == 0;
+         q.sao_enabled == 1 && q.wpp == 1 && q.dense == 0 && !q.pcm && !q.tq_bypass;
 }
 #define B200_SPC(f) ((int)Cfg::f >= 0 ? (int)Cfg::f : (int)sp->f)
 #define B200_SPR(f) ((int)Cfg::f >= 0 ? (int)Cfg::f : (int)sp.f)
@@ -298,6 +301,7 @@ struct DecoderT {
   const SeqParams* sp; PicBuffers pb; const Substream* ss;
   Cabac cabac; CabacStream stream; CtxPtr ctx;    // ctx: CTX_COUNT context states (caller-provided storage)
   int is_dqp_coded, dqp_val, qpy_prev_qg, last_cu_qpy, first_qg, cur_qpy, err;
+  int cu_bypass;                                  // cu_transquant_bypass_flag of the current coding unit
   uint32_t tu_n, coef_n, tu_cap, coef_cap;        // write cursors / limits of the current CTB (or of the picture when dense)
   int cur_ctb_x, cur_ctb_y;
   int ctb_x0, ctb_y0, left_ok, up_ok;            // current CTB: origin, availability of the CTB to the left / above (same slice)
@@ -366,10 +370,11 @@ struct DecoderT {
     const int n = 1 << log2n;
     // Local copies: their addresses never escape, so they live in registers.
     Cabac cb_ = cabac; const CtxPtr cx = ctx;
-    const int sign_hiding = B200_SPC(sign_hiding);
+    const int bypass_cu = B200_SPC(tq_bypass) && cu_bypass;            // 7.3.8.11: no transform_skip_flag, no sign data hiding
+    const int sign_hiding = B200_SPC(sign_hiding) && !bypass_cu;
     CoefEntry* const coef_out = pb.coefs; uint32_t cn = coef_n; const uint32_t ccap = coef_cap;
     tskip = 0;
-    if (B200_SPC(transform_skip) && log2n == 2) tskip = cb_.bin(ctx_at(cx, CTX_TSKIP + (c ? 1 : 0)), stream);
+    if (B200_SPC(transform_skip) && log2n == 2 && !bypass_cu) tskip = cb_.bin(ctx_at(cx, CTX_TSKIP + (c ? 1 : 0)), stream);
     const int cmax = (log2n << 1) - 1;
     int off, shift;
     if (c == 0) { off = 3 * (log2n - 2) + ((log2n - 1) >> 2); shift = (log2n + 1) >> 2; } else { off = 15; shift = log2n - 2; }
@@ -533,7 +538,7 @@ struct DecoderT {
     TuCmd t;
     t.w0 = (uint32_t)(x0 >> 2) | ((uint32_t)(y0 >> 2) << 12) | ((uint32_t)(log2n - 2) << 24) | ((uint32_t)cbf_l << 26) | ((uint32_t)ccb << 27) |
            ((uint32_t)ccr << 28) | ((uint32_t)chroma_here << 29) | ((uint32_t)ts_l << 30) | ((uint32_t)ts_cb << 31);
-    t.w1 = (uint32_t)lmode | ((uint32_t)cu.cmode << 6) | ((uint32_t)(cur_qpy + 64) << 12) | ((uint32_t)ts_cr << 20);
+    t.w1 = (uint32_t)lmode | ((uint32_t)cu.cmode << 6) | ((uint32_t)(cur_qpy + 64) << 12) | ((uint32_t)ts_cr << 20) | ((B200_SPC(tq_bypass) && cu_bypass) ? 1u << 22 : 0u);
     t.w2 = coef0;
     t.w3 = (uint32_t)nl | ((uint32_t)ncb << 11) | ((uint32_t)ncr << 21);
     pb.tus[tu_n++] = t;
@@ -602,12 +607,65 @@ struct DecoderT {
     return m;
   }
 
+  // -------- pcm_sample() (7.3.8.7): the unit becomes ONE TuCmd whose "coefficients" are the samples in raster order,
+  // already scaled to the picture's bit depth (8.4.4.1: recSamples = pcm_sample << (BitDepth - PcmBitDepth))
+  B200_HD inline uint32_t rbsp_byte(uint32_t p) const {
+#ifdef B200_SYN_DEVICE
+    return (uint32_t)__ldg(stream.d + p);
+#else
+    return stream.d[p];
+#endif
+  }
+  B200_HDN void pcm_unit(int x0, int y0, int log2cb, int depth) {
+    const int n = 1 << log2cb, chroma = B200_SPC(chroma) ? 1 : 0;
+    const uint32_t nl = (uint32_t)(n * n), nc = chroma ? nl >> 2 : 0;
+    uint32_t p = (uint32_t)((cabac.bit_position() + 7) >> 3);          // pcm_alignment_zero_bit
+    const uint64_t nbits = (uint64_t)nl * (uint32_t)sp->pcm_bd_y + 2ull * nc * (uint32_t)sp->pcm_bd_c;     // a multiple of 8
+    if ((uint64_t)p * 8 + nbits > (uint64_t)stream.size * 8) { err = SYN_E_BITSTREAM; return; }
+    if (coef_n + nl + 2 * nc > coef_cap || tu_n >= tu_cap) { err = SYN_E_OVERFLOW; return; }
+    const uint32_t coef0 = coef_n;
+    uint32_t acc = 0; int have = 0;
+    B200_NOUNROLL for (int c = 0; c < (chroma ? 3 : 1); c++) {
+      const uint32_t cnt = c ? nc : nl; const int bd = c ? sp->pcm_bd_c : sp->pcm_bd_y, sh = c ? sp->pcm_shift_c : sp->pcm_shift_y;
+      B200_NOUNROLL for (uint32_t k = 0; k < cnt; k++) {
+        B200_NOUNROLL while (have < bd) { acc = (acc << 8) | rbsp_byte(p++); have += 8; }
+        have -= bd;
+        const uint32_t v = (acc >> have) & ((1u << bd) - 1u);
+        acc &= (1u << have) - 1u;
+        CoefEntry e; e.pos = (uint16_t)k; e.level = (int16_t)(v << sh);
+        pb.coefs[coef_n++] = e;
+      }
+    }
+    cabac.start(stream, p);                                             // 9.3.2.5: the arithmetic decoder starts over after the samples
+    if (!B200_SPC(cu_qp_delta)) cur_qpy = ss->slice_qp; else derive_qpy(x0, y0);
+    const int nofilt = sp->pcm_lf_disabled ? 4 : 0;
+    B200_NOUNROLL for (int yy = 0; yy < n; yy += 4) B200_NOUNROLL for (int xx = 0; xx < n; xx += 4) pb.ipm4[((y0 + yy) >> 2) * sp->w4 + ((x0 + xx) >> 2)] = 1;   // INTRA_DC for its neighbours' mode derivation (8.4.2)
+    mark_tu(x0, y0, log2cb);
+    B200_NOUNROLL for (int yy = 0; yy < n; yy += 8) B200_NOUNROLL for (int xx = 0; xx < n; xx += 8) {
+      const int i8 = ((y0 + yy) >> 3) * sp->w8 + ((x0 + xx) >> 3);
+      pb.cd8[i8] = (uint8_t)depth; pb.qp8[i8] = (int8_t)cur_qpy; pb.edge8[i8] |= (uint8_t)nofilt;
+    }
+    last_cu_qpy = cur_qpy;
+    TuCmd t;
+    t.w0 = (uint32_t)(x0 >> 2) | ((uint32_t)(y0 >> 2) << 12) | ((uint32_t)(log2cb - 2) << 24) | (1u << 26) | ((uint32_t)chroma << 27) | ((uint32_t)chroma << 28) | ((uint32_t)chroma << 29);
+    t.w1 = 1u | (1u << 6) | ((uint32_t)(cur_qpy + 64) << 12) | (1u << 21) | ((B200_SPC(tq_bypass) && cu_bypass) ? 1u << 22 : 0u);
+    t.w2 = coef0;
+    t.w3 = nl | (nc << 11) | (nc << 21);
+    pb.tus[tu_n++] = t;
+  }
+
   // -------- 7.3.8.5
   B200_HDI void coding_unit(int x0, int y0, int log2cb, int depth) {
     Cu cu; cu.x0 = x0; cu.y0 = y0; cu.log2cb = log2cb; cu.nxn = 0; cu.cmode = 0;
     const int n = 1 << log2cb;
+    if (B200_SPC(tq_bypass)) {
+      cu_bypass = dbin(CTX_TQ_BYPASS);
+      // in-loop filters leave the samples of this unit unchanged (8.7.2.5.7 nDp / nDq = 0, 8.7.3 SaoTypeIdx = 0): bit 2 of the 8x8 cells
+      if (cu_bypass) B200_NOUNROLL for (int yy = 0; yy < n; yy += 8) B200_NOUNROLL for (int xx = 0; xx < n; xx += 8) pb.edge8[((y0 + yy) >> 3) * sp->w8 + ((x0 + xx) >> 3)] |= 4;
+    }
     if (log2cb == B200_SPC(log2_min_cb)) cu.nxn = !dbin(CTX_PART_MODE);
     if (cu.nxn && log2cb == 3 && B200_SPC(log2_min_tb) > 2) { err = SYN_E_BITSTREAM; return; }
+    if (B200_SPC(pcm) && !cu.nxn && log2cb >= sp->log2_min_pcm && log2cb <= sp->log2_max_pcm && cabac.terminate(stream)) { pcm_unit(x0, y0, log2cb, depth); return; }   // pcm_flag
     const int np = cu.nxn ? 4 : 1, pbs = cu.nxn ? n / 2 : n;
     int prev[4], mi[4] = {0, 0, 0, 0}, rem[4] = {0, 0, 0, 0};
     B200_NOUNROLL for (int i = 0; i < np; i++) prev[i] = dbin(CTX_PREV_INTRA);
@@ -690,7 +748,7 @@ template <class Cfg, class Sync>
 B200_HD int run_substream(DecoderT<Cfg>& d, const SeqParams& sp, const PicBuffers& pb, const Substream* all, int index, CtxPtr ctx, Sync& sync) {
   const Substream& ss = all[index];
   d.sp = &sp; d.pb = pb; d.ss = &ss; d.ctx = ctx; d.err = SYN_OK;
-  d.is_dqp_coded = 0; d.dqp_val = 0; d.qpy_prev_qg = ss.slice_qp; d.last_cu_qpy = ss.slice_qp; d.first_qg = 1; d.cur_qpy = ss.slice_qp;
+  d.is_dqp_coded = 0; d.dqp_val = 0; d.qpy_prev_qg = ss.slice_qp; d.last_cu_qpy = ss.slice_qp; d.first_qg = 1; d.cur_qpy = ss.slice_qp; d.cu_bypass = 0;
   d.tu_n = 0; d.coef_n = 0; d.tu_cap = 0; d.coef_cap = 0;
   if (B200_SPR(dense)) {                                             // host: continue the picture-wide cursors
     d.tu_n = sync.dense_tu; d.coef_n = sync.dense_coef; d.tu_cap = sync.dense_tu_cap; d.coef_cap = sync.dense_coef_cap;

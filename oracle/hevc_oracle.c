@@ -938,7 +938,7 @@ static void coding_unit(dec_t* d, int x0, int y0, int log2cb, int cq_depth) {
       for (int y = 0; y < m; y++) for (int x = 0; x < m; x++) {
         unsigned v = rd_bits(&d->br, pbd);
         d->pl[c][((y0 >> sh) + y) * d->stride[c] + (x0 >> sh) + x] = (uint16_t)(v << (bdc - pbd));       /* 8.4.4.1: recSamples = pcm_sample << (BitDepth - PcmBitDepth) */
-        { unsigned long long hh = ((unsigned long long)x0 * 1000003ULL + (unsigned long long)y0) * 1000003ULL + (unsigned long long)c; hh = hh * 1000003ULL + (unsigned long long)(y * m + x); hh = hh * 1000003ULL + (unsigned long long)(unsigned short)v; hh ^= hh >> 29; hh *= 0x9E3779B97F4A7C15ULL; d->coef_hash += hh; d->coef_count++; }
+        { unsigned long long hh = ((unsigned long long)x0 * 1000003ULL + (unsigned long long)y0) * 1000003ULL + (unsigned long long)c; hh = hh * 1000003ULL + (unsigned long long)(y * m + x); hh = hh * 1000003ULL + (unsigned long long)(unsigned short)(v << (bdc - pbd)); hh ^= hh >> 29; hh *= 0x9E3779B97F4A7C15ULL; d->coef_hash += hh; d->coef_count++; }
       }
     }
     cabac_init_engine(d);
@@ -1460,7 +1460,8 @@ int hevc_oracle_debug_maps(const uint8_t* data, size_t size, int8_t* qp8, uint8_
     int w8 = d->W >> 3, h8 = d->H >> 3;
     for (int by = 0; by < h8; by++) for (int bx = 0; bx < w8; bx++) {
       qp8[by * w8 + bx] = d->qp4[(by * 2) * d->w4 + bx * 2];
-      edge8[by * w8 + bx] = (uint8_t)((edge_filtered(d, bx * 8, by * 8, 1) ? 1 : 0) | (edge_filtered(d, bx * 8, by * 8, 0) ? 2 : 0));
+      edge8[by * w8 + bx] = (uint8_t)((edge_filtered(d, bx * 8, by * 8, 1) ? 1 : 0) | (edge_filtered(d, bx * 8, by * 8, 0) ? 2 : 0) |
+                                      (d->nofilt4[(by * 2) * d->w4 + bx * 2] ? 4 : 0));      /* bit 2: in-loop filters leave the unit unchanged */
     }
     memcpy(lmode4, d->ipm4, (size_t)d->w4 * d->h4);
     memcpy(cmode4, d->cmode4, (size_t)d->w4 * d->h4);

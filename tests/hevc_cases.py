@@ -49,6 +49,15 @@ SYNTH = [
     ("scaling_default", 192, 128, 8, True, dict(log2_ctb_size=5, scaling_lists=1, qp=24)),
     ("scaling_sps_ctb64", 256, 192, 8, True, dict(log2_ctb_size=6, scaling_lists=2, qp=26, wpp=1, max_transform_hierarchy_depth_intra=2)),
     ("scaling_pps_main10_tskip", 160, 160, 10, True, dict(log2_ctb_size=5, scaling_lists=3, qp=22, transform_skip=1, mode_decision=0)),
+    # PCM coding units (7.3.8.7; pcm=2: pcm_loop_filter_disabled_flag) and cu_transquant_bypass_flag (transquant_bypass=2: every unit, i.e. lossless)
+    ("pcm", 128, 96, 8, True, dict(log2_ctb_size=5, pcm=1)),
+    ("pcm_nolf_wpp_ctb64", 192, 128, 8, True, dict(log2_ctb_size=6, pcm=2, wpp=1, mode_decision=0)),
+    ("pcm_nolf_main10", 160, 96, 10, True, dict(log2_ctb_size=5, pcm=2)),
+    ("pcm_mono", 136, 72, 8, False, dict(log2_ctb_size=4, pcm=1)),
+    ("bypass_mixed", 128, 96, 8, True, dict(log2_ctb_size=5, transquant_bypass=1)),
+    ("bypass_lossless", 96, 64, 8, True, dict(log2_ctb_size=4, transquant_bypass=2)),
+    ("bypass_tskip_main12", 160, 96, 12, True, dict(log2_ctb_size=5, transquant_bypass=1, transform_skip=1, mode_decision=0)),
+    ("pcm_bypass_scaling_slices_wpp", 256, 192, 8, True, dict(log2_ctb_size=5, pcm=1, transquant_bypass=1, scaling_lists=2, slice_ctb_rows=2, wpp=1)),
 ]
 
 # More feature combinations, used by the CPU tests only (FFmpeg pin of the restatement, host front-end vs restatement):
@@ -63,10 +72,27 @@ SYNTH_CPU_EXTRA = [
     ("x_main10_ctb64_qg8", 256, 128, 10, True, dict(log2_ctb_size=6, diff_cu_qp_delta_depth=3, dqp_range=12, qp=30)),
     ("x_scaling_sps_mono_qp12", 136, 72, 8, False, dict(log2_ctb_size=4, scaling_lists=2, qp=12, seed=77)),
     ("x_scaling_pps_slices_wpp", 256, 192, 8, True, dict(log2_ctb_size=5, scaling_lists=3, slice_ctb_rows=2, wpp=1, qp=30, seed=991)),
+    ("x_bypass_mixed_nosao", 128, 96, 8, True, dict(log2_ctb_size=5, transquant_bypass=1, sao=0, seed=5)),
+    ("x_pcm_nolf_nosao_ctb16", 136, 72, 8, True, dict(log2_ctb_size=4, pcm=2, sao=0, seed=6)),
+    ("x_lossless_main10_ctb64_wpp", 200, 136, 10, True, dict(log2_ctb_size=6, transquant_bypass=2, wpp=1)),
+    ("x_lossless_mono_nosao", 72, 40, 8, False, dict(log2_ctb_size=5, transquant_bypass=2, sao=0)),
     ("x_slices_every_row_nolf_across", 192, 160, 8, True, dict(log2_ctb_size=5, slice_ctb_rows=1, loop_filter_across_slices=0, slice_loop_filter_across_slices=0)),
 ]
 
 _cache = {}
+
+
+def synth_params(name):
+    for c in SYNTH + SYNTH_CPU_EXTRA:
+        if c[0] == name:
+            return c
+    return None
+
+
+def synth_source(name):
+    """the picture the synthetic stream `name` was encoded from (y, cb, cr)"""
+    (_, w, h, bd, chroma, _) = synth_params(name)
+    return hevc_enc.synthetic_image(0xB200 + w + h, w, h, bd, chroma)
 
 
 def synth_stream(name):
