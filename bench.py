@@ -49,9 +49,24 @@ def make_tile(idx, tile=TILE, log2_ctb=5):
 
 
 def make_tiles(indices, tile=TILE, workers=None, log2_ctb=5):
+    """Encoded tiles (deterministic in idx).  B200_BENCH_TILE_CACHE names a directory this process and its reference-arm
+    children share, so that the 256 tiles are encoded once per bench run (input generation is untimed either way)."""
     workers = workers or min(64, effective_cores())
+    cache = os.environ.get("B200_BENCH_TILE_CACHE")
+
+    def one(i):
+        f = os.path.join(cache, f"t{tile}_c{log2_ctb}_q{QP}_{i}.au") if cache else None
+        if f and os.path.exists(f):
+            return open(f, "rb").read()
+        au = make_tile(i, tile, log2_ctb)
+        if f:
+            tmp = f + f".{os.getpid()}.tmp"
+            with open(tmp, "wb") as fh:
+                fh.write(au)
+            os.replace(tmp, f)
+        return au
     with ThreadPoolExecutor(workers) as ex:
-        return list(ex.map(lambda i: make_tile(i, tile, log2_ctb), indices))
+        return list(ex.map(one, indices))
 
 
 class ClockSampler:
@@ -121,13 +136,14 @@ def measured_peak():
 
 
 # ------------------------------------------------------------------------------------------ reference CPU arm
-def reference_arm(side, sub, steps, warmup, cores, dump=None, log2_ctb=5):
+def reference_arm(side, sub, steps, warmup, cores, dump=None, log2_ctb=5, extra=()):
     """heif_decode_image() of the unmodified reference on the same tiles, in a child process (oracle/ref_arm.py; the
     reference library must not share a process with torch).  Returns (dict, None) or (None, reason)."""
     cmd = [sys.executable, "-m", "oracle.ref_arm", "--side", str(side), "--sub", str(sub), "--steps", str(steps), "--warmup", str(warmup),
            "--threads", str(cores), "--ctb", str(log2_ctb)]
     if dump:
         cmd += ["--dump", dump]
+    cmd += list(extra)
     try:
         r = subprocess.run(cmd, cwd=ROOT, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=3000)
     except Exception as e:  # noqa: BLE001
@@ -154,6 +170,13 @@ def load_traffic():
 
 
 def main():
+    if "B200_BENCH_TILE_CACHE" not in os.environ:
+        import atexit
+        import shutil
+        import tempfile
+        d = tempfile.mkdtemp(prefix="b200_bench_tiles_", dir="/dev/shm" if os.path.isdir("/dev/shm") else None)
+        os.environ["B200_BENCH_TILE_CACHE"] = d
+        atexit.register(shutil.rmtree, d, True)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
@@ -162,6 +185,7 @@ def main():
     ap.add_argument("--tiles-side", type=int, default=16, help="grid is tiles-side x tiles-side tiles of 1024x1024 (16 = BASELINE config)")
     ap.add_argument("--ref-sample-side", type=int, default=8, help="sub-grid the in-run parity check / cpu_baseline decodes with the reference")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-plugin-leg", action="store_true", help="skip the heif_decode_image + plugin legs (e2e_plugin, e2e_plugin_n2)")
     ap.add_argument("--no-ctb64", action="store_true", help="skip the additional CTB 64 measurement (x265's default CTB size)")
     ap.add_argument("--ctb", type=int, default=5, choices=[4, 5, 6], help="log2 CTB size of the synthetic tiles (5 = the benchmark workload)")
     ap.add_argument("--front-end", default="device", choices=["device", "host"], help="where CABAC runs: GPU (one warp per WPP sub-stream) or host cores")
@@ -368,6 +392,20 @@ def main():
             line["parity_checked"] = False
             line["parity"] = {"compared": f"unavailable: {why}"}
             line["cpu_baseline"] = {"value": None, "unit": "MP/s", "cores": cores, "kind": "reference", "sample": f"unavailable: {why}"}
+    # ---- the drop-in path: heif_decode_image() of the unmodified reference library with THIS plugin selected, one libheif
+    # decoding thread per tile so that the plugin's submission queue sees the whole grid; then the same
+    # through the second reference build that carries the GPU colour operation
+    if world == 1 and not args.no_plugin_leg and args.front_end == "device":
+        for key, extra in (("e2e_plugin", []), ("e2e_plugin_n2", ["--lib", "libheif_ref_b200.so"])):
+            dump = f"/dev/shm/b200_bench_plug_{os.getpid()}.rgb"
+            res, why = reference_arm(side, side, 3, 2, side * side, dump=dump, log2_ctb=args.ctb, extra=["--decoder", "b200"] + extra)
+            if res:
+                got = np.fromfile(dump, dtype=np.uint8)
+                os.unlink(dump)
+                line[key] = {"value": res["mp_s"], "unit": "MP/s", "ms_per_step": res["ms_per_step"], "libheif_threads": res["threads"], "plugin_queue": res["plugin_queue"],
+                             "identical_to_e2e_result": bool(got.size == host_out.size and np.array_equal(got, host_out.reshape(-1))), "api": res["api"]}
+            else:
+                line[key] = {"value": None, "unavailable": why}
     # ---- the same grid coded with CTB 64 (x265's default): longer wavefront per tile; device leg only, few steps
     if world == 1 and not args.no_ctb64 and args.ctb == 5 and args.front_end == "device":
         try:

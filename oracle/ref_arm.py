@@ -9,6 +9,13 @@ compiled from /root/reference by oracle/Makefile) with the CPU decoder plugin of
 role, oracle/ref_plugin.cc) to interleaved RGB, heif_context_set_max_decoding_threads(C) -- the call and the thread
 model of SURVEY.md 8(d) "CPU baseline beside it".  Prints one JSON line: per-step milliseconds, MP/s, md5 of the RGB.
 Runs in its own process and never imports torch (libheif_ref.so is loaded RTLD_GLOBAL, see oracle/refheif.py).
+
+    python -m oracle.ref_arm --decoder b200 --threads 256 [--lib libheif_ref_b200.so]
+
+is the drop-in leg of bench.py ("e2e_plugin"): the same file, the same heif_decode_image() call of the same unmodified
+library, but the decoder plugin it selects is the product's (libb200heif.so, registered with heif_register_decoder_plugin);
+here the reference is the HOST APPLICATION of the product, not its checker.  --lib libheif_ref_b200.so uses the second
+build that carries the GPU colour operation (integration/colorconversion_b200.patch).
 """
 import argparse
 import ctypes as C
@@ -33,13 +40,22 @@ def main():
     ap.add_argument("--threads", type=int, default=0)
     ap.add_argument("--ctb", type=int, default=5)
     ap.add_argument("--dump", default="", help="write the RGB of the last step to this file (raw bytes)")
+    ap.add_argument("--decoder", default="b200-oracle", choices=["b200-oracle", "b200"], help="decoder plugin: the oracle's CPU plugin, or the product's GPU plugin")
+    ap.add_argument("--lib", default="", help="reference build to load (default libheif_ref.so; libheif_ref_b200.so = + GPU colour operation)")
     args = ap.parse_args()
+    if args.lib:
+        os.environ["B200_REF_LIB"] = args.lib
     import numpy as np  # noqa: F401
     import bench
     from oracle import bindings as ob
     from oracle import heic_writer as hw
     from oracle import refheif as rh
-    if not (os.path.exists(os.path.join(ob.REF, "libheif_ref.so")) and os.path.exists(os.path.join(ob.REF, "liboracle_plugin.so")) and ob.avcodec_dir()):
+    gpu = args.decoder == "b200"
+    if gpu:
+        if not os.path.exists(os.path.join(ob.REF, args.lib or "libheif_ref.so")):
+            print(json.dumps({"unavailable": f"oracle/_ref/{args.lib or 'libheif_ref.so'} missing"}))
+            return
+    elif not (os.path.exists(os.path.join(ob.REF, "libheif_ref.so")) and os.path.exists(os.path.join(ob.REF, "liboracle_plugin.so")) and ob.avcodec_dir()):
         print(json.dumps({"unavailable": "oracle/_ref reference build or FFmpeg missing"}))
         return
     threads = args.threads or bench.effective_cores()
@@ -52,16 +68,28 @@ def main():
     path = os.path.join(tmpdir, f"b200_ref_arm_{os.getpid()}.heic")
     hw.write_heic(path, tiles, cols=sub, rows=sub)
     try:
-        rh.load()
-        rh.register_cpu_decoder()
+        h = rh.load()
+        stats = None
+        if gpu:
+            b200 = C.CDLL(os.path.join(ROOT, "libheif_b200", "libb200heif.so"))
+            b200.b200_get_decoder_plugin.restype = C.c_void_p
+            if b200.b200_plugin_bind_libheif(None) != 0:
+                raise RuntimeError("the plugin could not resolve the libheif C API")
+            rh.check(h.heif_register_decoder_plugin(C.c_void_p(b200.b200_get_decoder_plugin())), "register decoder plugin")
+        else:
+            rh.register_cpu_decoder()
         out = None
         for _ in range(args.warmup):
-            out = rh.decode_file(path, decoder_id="b200-oracle", threads=threads)
+            out = rh.decode_file(path, decoder_id=args.decoder, threads=threads)
         ts = []
         for _ in range(args.steps):
             t = time.perf_counter()
-            out = rh.decode_file(path, decoder_id="b200-oracle", threads=threads)
+            out = rh.decode_file(path, decoder_id=args.decoder, threads=threads)
             ts.append(time.perf_counter() - t)
+        if gpu:
+            st = (C.c_uint64 * 3)()
+            b200.b200_plugin_queue_stats(st)
+            stats = {"batches": int(st[0]), "pictures": int(st[1]), "largest_batch": int(st[2])}
     finally:
         os.unlink(path)
     ms = 1e3 * sum(ts) / max(1, len(ts))
@@ -71,7 +99,9 @@ def main():
     print(json.dumps({"ms_per_step": ms, "mp_s": px / 1e6 / (ms / 1e3), "pixels": px, "width": out.shape[1] // 3, "height": out.shape[0],
                       "tiles": sub * sub, "threads": threads, "steps": args.steps, "warmup": args.warmup, "rgb_md5": hashlib.md5(out.tobytes()).hexdigest(),
                       "file_bytes": sum(len(t) for t in tiles), "tile_generation_s": t_gen,
-                      "api": "heif_decode_image (libheif_ref.so, unmodified) + oracle CPU decoder plugin (FFmpeg), heif_context_set_max_decoding_threads"}))
+                      "plugin_queue": stats,
+                      "api": (f"heif_decode_image ({args.lib or 'libheif_ref.so'}) + libb200heif.so decoder plugin, heif_context_set_max_decoding_threads" if gpu else
+                              "heif_decode_image (libheif_ref.so, unmodified) + oracle CPU decoder plugin (FFmpeg), heif_context_set_max_decoding_threads")}))
 
 
 if __name__ == "__main__":
