@@ -199,7 +199,11 @@ typedef struct b200_decode_stats {
   uint64_t bitstream_bytes, command_bytes, coefficient_entries, transform_units, ctus, h2d_bytes, pixels;
   int kernel_launches;
   int front_end;                                        /* 0 = CABAC decoded on the host cores, 1 = on the GPU, 2 = on the GPU with the
-                                                           reconstruction kernel running concurrently (entropy_ms then covers both) */
+                                                           reconstruction kernel running concurrently (entropy_ms then covers both),
+                                                           3 = on the GPU, chunked: groups of tile rows leave the entropy kernel in order and
+                                                           are reconstructed / filtered (/ converted / copied out) while it decodes the next
+                                                           ones; recon_ms is then what remains after the entropy kernel, deblock_ms = sao_ms = 0
+                                                           (B200_CHUNKS=0 restores the back-to-back kernels and their separate times) */
 } b200_decode_stats;
 
 /* host_threads: CABAC parser threads (0 = number of online cores).  The CUDA device is the current one. */

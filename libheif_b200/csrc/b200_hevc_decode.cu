@@ -99,6 +99,13 @@ struct b200_decoder {
   bool have_result = false;
   int debug_stage = 0;
   size_t n_rows = 0, n_items = 0, cbytes = 0; bool canvas_fully_covered = true; int max_log2_ctb = 6, info_bps = 1;
+  // Chunked pipeline (grids larger than one wave of sub-streams): K0 decodes the chunks (groups of tile rows) in priority
+  // order; K1, K3, K4 (and, in the fused entry points, K6 + D2H through chunk_hook) of chunk c run on `side` while K0
+  // still works on the later chunks.
+  int nchunks = 1, grid_cols = 1; bool last_chunked = false;
+  int chunk_pic[MAX_CHUNKS + 1] = {0}; size_t chunk_item[MAX_CHUNKS + 1] = {0}; unsigned chunk_sub[MAX_CHUNKS + 1] = {0};
+  std::function<int(int, cudaStream_t)> chunk_hook;   // queued after K4 of chunk c on the side stream
+  cudaEvent_t ev_chunk[MAX_CHUNKS] = {nullptr};
   ~b200_decoder() {
     delete pool;
     pics.release(); ctus.release(); tus.release(); coefs.release(); slices.release(); qp8.release(); edge8.release(); scaling.release(); rows.release();
@@ -115,6 +122,7 @@ struct b200_decoder {
     if (ev_fork) cudaEventDestroy(ev_fork);
     if (ev_join) cudaEventDestroy(ev_join);
     if (side) cudaStreamDestroy(side);
+    for (auto& e : ev_chunk) if (e) cudaEventDestroy(e);
   }
 };
 
@@ -164,19 +172,22 @@ static int run_device_pipeline(b200_decoder* d, int n, cudaStream_t s, int* laun
   int rc;
   int launches = 0;
   const bool devfe = d->used_device_front_end;
-  bool overlap = devfe && use_overlap(d->n_subs);
+  const bool chunked = devfe && d->nchunks > 1;
+  bool overlap = devfe && !chunked && use_overlap(d->n_subs);
   if (overlap) overlap = overlap_acquire(d);
   struct Release { bool armed; ~Release() { if (armed) overlap_release(); } } release{overlap};   // error paths
-  d->last_overlapped = overlap;
+  d->last_overlapped = overlap; d->last_chunked = chunked;
   cudaEventRecord(d->ev[1], s);
   DeviceBatch b{};
   b.pics = d->pics.d; b.npics = n; b.ctus = d->ctus.d; b.tus = d->tus.d; b.coefs = d->coefs.d; b.slices = d->slices.d;
-  b.qp8 = d->qp8.d; b.edge8 = d->edge8.d; b.scaling = d->scaling.d; b.ticket = d->sync.d; b.error_flag = d->sync.d + 1; b.progress = d->sync.d + 2; b.row_list = d->rows.d; b.nrows = (int)d->n_items; b.max_log2_ctb = d->max_log2_ctb; b.wide_samples = d->info_bps == 2;
+  b.qp8 = d->qp8.d; b.edge8 = d->edge8.d; b.scaling = d->scaling.d; b.ticket = d->sync.d + 2 + 2 * d->n_rows; b.error_flag = d->sync.d + 1; b.progress = d->sync.d + 2; b.row_list = d->rows.d; b.nrows = (int)d->n_items; b.max_log2_ctb = d->max_log2_ctb; b.wide_samples = d->info_bps == 2;
   if (devfe) {
     EntropyBatch e{};
     e.pics = d->epics.d; e.npics = d->npics; e.subs = d->subs.d; e.nsubs = (int)d->n_subs;
-    e.qhead = d->equeue.d; e.qtail = d->equeue.d + 1; e.queue = d->equeue.d + 2; e.deps = d->equeue.d + 2 + d->n_subs;
+    e.qctl = d->equeue.d; e.queue = d->equeue.d + 2 * MAX_CHUNKS; e.deps = e.queue + d->n_subs;
     e.progress = d->esync.d + 1; e.sub_done = d->esync.d + 1 + d->n_rows; e.error_flag = d->sync.d + 1;
+    e.chunk_done = d->esync.d + 1 + d->n_rows + d->n_subs;
+    e.nchunks = d->nchunks; for (int c = 0; c <= d->nchunks; c++) e.chunk_first[c] = d->chunk_sub[c];
     e.common = 1;
     if (getenv("B200_ENTROPY_GENERIC")) e.common = 0;
     for (int i = 0; i < d->npics && e.common; i++) if (!syn::matches_common(d->epics.h[i].sp)) e.common = 0;
@@ -191,6 +202,36 @@ static int run_device_pipeline(b200_decoder* d, int n, cudaStream_t s, int* laun
       cudaEventRecord(d->ev[5], d->side);
       if ((rc = launch_entropy_stats(e, d->ecount.d, d->side))) return rc;
       cudaEventRecord(d->ev_join, d->side);
+    } else if (chunked) {
+      // K0 on `s` (a CTA per SM fewer than it could hold, so that the kernels below fit beside it); on `side`, per chunk:
+      // wait for K0's completion flag of the chunk, then K1 -> K3 -> K4 (-> the caller's hook: K6, D2H) of its pictures
+      if (!d->side) { B200_CUDA_CHECK(cudaStreamCreateWithFlags(&d->side, cudaStreamNonBlocking)); B200_CUDA_CHECK(cudaEventCreate(&d->ev_fork)); B200_CUDA_CHECK(cudaEventCreate(&d->ev_join)); }
+      e.blocks_per_sm = overlap_blocks("B200_CHUNK_K0_BLOCKS", 3);
+      cudaEventRecord(d->ev_fork, s);
+      if ((rc = launch_entropy(e, s))) return rc;
+      cudaEventRecord(d->ev[5], s);
+      if ((rc = launch_entropy_stats(e, d->ecount.d, s))) return rc;
+      launches += 1;
+      B200_CUDA_CHECK(cudaStreamWaitEvent(d->side, d->ev_fork, 0));
+      for (int c = 0; c < d->nchunks; c++) {
+        if ((rc = launch_wait_flag(e.chunk_done + MAX_CHUNKS + c, b.error_flag, d->side))) return rc;
+        DeviceBatch bc = b;
+        bc.row_list = d->rows.d + d->chunk_item[c]; bc.nrows = (int)(d->chunk_item[c + 1] - d->chunk_item[c]); bc.ticket = b.ticket + c;
+        bc.entropy_progress = e.progress;            // K0 is still running (on later chunks): read its output past L1
+        if ((rc = launch_recon(bc, d->side))) return rc;
+        DeviceBatch bf = b;
+        const int p0 = d->chunk_pic[c];
+        bf.pics = d->pics.d + p0; bf.npics = d->chunk_pic[c + 1] - p0;
+        if (d->debug_stage != 1 && (rc = launch_deblock(bf, d->pics.h + p0, d->side))) return rc;
+        if (d->debug_stage == 0 && (rc = launch_sao(bf, d->pics.h + p0, d->side))) return rc;
+        launches += 5;
+        if (d->chunk_hook && (rc = d->chunk_hook(c, d->side))) return rc;
+      }
+      cudaEventRecord(d->ev_join, d->side);
+      B200_CUDA_CHECK(cudaStreamWaitEvent(s, d->ev_join, 0));
+      cudaEventRecord(d->ev[2], s); cudaEventRecord(d->ev[3], s); cudaEventRecord(d->ev[4], s);   // recon_ms = what is left of the last chunk after K0
+      if (launches_out) *launches_out = launches;
+      return B200_OK;
     } else {
       if ((rc = launch_entropy(e, s))) return rc;
       cudaEventRecord(d->ev[5], s);
@@ -295,12 +336,12 @@ int b200_decoder_decode_grid(b200_decoder* d, int cols, int rows, const uint8_t*
   for (int i = 0; i < n; i++) { const ParsedPicture& pp = d->parsed[(size_t)i]; if (pp.desc.scaling_idx >= 0) memcpy(d->scaling.h + (size_t)pp.desc.scaling_idx * 784, &pp.hdr.scaling, sizeof(sl::Factors)); }
   if ((rc = d->pics.reserve((size_t)n)) || (rc = d->ctus.reserve(n_ctu, !devfe)) || (rc = d->tus.reserve(n_tu, !devfe)) || (rc = d->coefs.reserve(n_coef + 1, !devfe)) ||
       (rc = d->slices.reserve(n_slice)) || (rc = d->qp8.reserve(n_map, !devfe)) || (rc = d->edge8.reserve(n_map, !devfe)) || (rc = d->rows.reserve(2 * n_rows)) ||
-      (rc = d->sync.reserve(2 * n_rows + 2, false)) || (rc = d->rec.reserve(rec_bytes, false)))
+      (rc = d->sync.reserve(2 * n_rows + 2 + MAX_CHUNKS, false)) || (rc = d->rec.reserve(rec_bytes, false)))
     return rc;
-  if (devfe && ((rc = d->rbsp.reserve(n_rbsp + 16)) || (rc = d->subs.reserve(n_subs)) || (rc = d->equeue.reserve(2 + 2 * n_subs)) || (rc = d->ctu_slice.reserve(n_ctu)) ||
+  if (devfe && ((rc = d->rbsp.reserve(n_rbsp + 16)) || (rc = d->subs.reserve(n_subs)) || (rc = d->equeue.reserve(2 * MAX_CHUNKS + 2 * n_subs)) || (rc = d->ctu_slice.reserve(n_ctu)) ||
                 (rc = d->epics.reserve((size_t)n)) || (rc = d->ipm4.reserve(n_map4, false)) || (rc = d->cd8.reserve(n_map, false)) ||
                 (rc = d->wpp_ctx.reserve(n_rows * syn::CTX_STRIDE, false)) || (rc = d->end_state.reserve(n_subs * syn::CTX_STRIDE + 16, false)) ||
-                (rc = d->esync.reserve(1 + n_rows + n_subs, false)) || (rc = d->ecount.reserve(2, true))))
+                (rc = d->esync.reserve(1 + n_rows + n_subs + 2 * MAX_CHUNKS, false)) || (rc = d->ecount.reserve(2, true))))
     return rc;
   // canvas planes
   size_t cbytes = 0;
@@ -329,12 +370,31 @@ int b200_decoder_decode_grid(b200_decoder* d, int cols, int rows, const uint8_t*
   // Launch order of the CTB rows: row-major ACROSS pictures (all first rows, then all second rows, ...).  A row's
   // predecessor always holds a smaller ticket (deadlock freedom), and the resident warps spread over every tile's
   // wavefront instead of idling behind one tile's 2-CTB stagger.
-  { size_t row_cursor = 0; int max_h = 0; d->max_log2_ctb = 4;
-    for (int i = 0; i < n; i++) { max_h = std::max(max_h, d->parsed[(size_t)i].desc.hctb); d->max_log2_ctb = std::max(d->max_log2_ctb, d->parsed[(size_t)i].desc.log2_ctb); }
-    for (int r = 0; r < max_h; r++) for (int i = 0; i < n; i++) if (r < d->parsed[(size_t)i].desc.hctb) {
-      d->rows.h[row_cursor++] = make_uint2((unsigned)i, (unsigned)r);                                        // luma
-      if (chroma) d->rows.h[row_cursor++] = make_uint2((unsigned)i, (unsigned)r | 0x80000000u);              // Cb + Cr
+  // Chunks: groups of whole tile rows of about one wave of sub-streams each (64 tiles of 1024x1024), when the batch is
+  // larger than what K0 and K1 can overlap CTB by CTB (use_overlap).  One chunk = the classic back-to-back pipeline.
+  { int nch = 1, rpc = rows;
+    const char* ce = getenv("B200_CHUNKS");
+    if (devfe && rows >= 2 && (ce ? atoi(ce) != 0 : !use_overlap(n_subs))) {      // B200_CHUNKS=0 / 1: never / always (tests, diagnostics)
+      int target = 64; if (const char* e = getenv("B200_CHUNK_TILES")) { const int v = atoi(e); if (v > 0) target = v; }
+      rpc = std::max(1, (target + cols / 2) / cols);
+      nch = (rows + rpc - 1) / rpc;
+      if (nch > MAX_CHUNKS) { rpc = (rows + MAX_CHUNKS - 1) / MAX_CHUNKS; nch = (rows + rpc - 1) / rpc; }
     }
+    d->nchunks = nch; d->grid_cols = cols;
+    for (int c = 0; c <= nch; c++) d->chunk_pic[c] = std::min(n, c * rpc * cols);
+    d->chunk_pic[nch] = n; }
+  { size_t row_cursor = 0; d->max_log2_ctb = 4;
+    for (int i = 0; i < n; i++) d->max_log2_ctb = std::max(d->max_log2_ctb, d->parsed[(size_t)i].desc.log2_ctb);
+    for (int c = 0; c < d->nchunks; c++) {
+      d->chunk_item[c] = row_cursor;
+      int max_h = 0;
+      for (int i = d->chunk_pic[c]; i < d->chunk_pic[c + 1]; i++) max_h = std::max(max_h, d->parsed[(size_t)i].desc.hctb);
+      for (int r = 0; r < max_h; r++) for (int i = d->chunk_pic[c]; i < d->chunk_pic[c + 1]; i++) if (r < d->parsed[(size_t)i].desc.hctb) {
+        d->rows.h[row_cursor++] = make_uint2((unsigned)i, (unsigned)r);                                        // luma
+        if (chroma) d->rows.h[row_cursor++] = make_uint2((unsigned)i, (unsigned)r | 0x80000000u);              // Cb + Cr
+      }
+    }
+    d->chunk_item[d->nchunks] = row_cursor;
     d->n_items = row_cursor; d->info_bps = bps; }
   d->pool->parallel_for(n, [&](int i) {
     const ParsedPicture& pp = d->parsed[(size_t)i]; const PicDesc& p = pp.desc;
@@ -354,7 +414,7 @@ int b200_decoder_decode_grid(b200_decoder* d, int cols, int rows, const uint8_t*
       // its first bin -- the conditions of run_substream (b200_hevc_syntax.h): the contexts stored after the 2nd CTB of the
       // row above (WPP, 9.3.2.2) and the end state of the slice segment it continues.
       const size_t so = sub_off[(size_t)i];
-      for (size_t k = 0; k < H.subs.size(); k++) { syn::Substream ss = H.subs[k]; ss.pic = (uint32_t)i; ss.wake_ctb2 = ss.wake_end = -1; ss.deps = 0; d->subs.h[so + k] = ss; }
+      for (size_t k = 0; k < H.subs.size(); k++) { syn::Substream ss = H.subs[k]; ss.pic = (uint32_t)i; ss.wake_ctb2 = ss.wake_end = -1; ss.deps = 0; ss.chunk = 0; d->subs.h[so + k] = ss; }
       for (size_t k = 0; k < H.subs.size(); k++) {
         syn::Substream& ss = d->subs.h[so + k];
         if (ss.prev >= 0) { ss.deps++; d->subs.h[so + (size_t)ss.prev].wake_end = (int32_t)(so + k); }
@@ -377,14 +437,27 @@ int b200_decoder_decode_grid(b200_decoder* d, int cols, int rows, const uint8_t*
     }
   });
   if (devfe) {
-    // ready queue image: cursors, the sub-streams without prerequisites in "k-th sub-stream of every picture" order (so
-    // that whatever a popped sub-stream polls for was popped before it), empty slots, the dependency counters
-    unsigned* q = d->equeue.h; size_t cur = 0, maxs = 0;
-    for (int i = 0; i < n; i++) maxs = std::max(maxs, d->parsed[(size_t)i].hdr.subs.size());
-    for (size_t k = 0; k < maxs; k++) for (int i = 0; i < n; i++) if (k < d->parsed[(size_t)i].hdr.subs.size() && d->subs.h[sub_off[(size_t)i] + k].deps == 0) q[2 + cur++] = (unsigned)(sub_off[(size_t)i] + k) + 1u;
-    q[0] = 0; q[1] = (unsigned)cur;
-    for (size_t k = cur; k < n_subs; k++) q[2 + k] = 0;
-    for (size_t k = 0; k < n_subs; k++) q[2 + n_subs + k] = d->subs.h[k].deps;
+    // ready-queue image, per chunk: cursors, then (in the chunk's slot range) the sub-streams without prerequisites in
+    // "k-th sub-stream of every picture" order (so that whatever a popped sub-stream polls for was popped before it),
+    // empty slots; then the dependency counters
+    unsigned* q = d->equeue.h; unsigned* slots = q + 2 * MAX_CHUNKS;
+    for (int c = 0; c < MAX_CHUNKS; c++) q[2 * c] = q[2 * c + 1] = 0;
+    for (size_t k = 0; k < n_subs; k++) slots[k] = 0;
+    for (int c = 0; c < d->nchunks; c++) {
+      const int p0 = d->chunk_pic[c], p1 = d->chunk_pic[c + 1];
+      const size_t first = sub_off[(size_t)p0];
+      d->chunk_sub[c] = (unsigned)first;
+      size_t cur = 0, maxs = 0;
+      for (int i = p0; i < p1; i++) {
+        const size_t ns = d->parsed[(size_t)i].hdr.subs.size();
+        maxs = std::max(maxs, ns);
+        for (size_t k = 0; k < ns; k++) d->subs.h[sub_off[(size_t)i] + k].chunk = (uint32_t)c;
+      }
+      for (size_t k = 0; k < maxs; k++) for (int i = p0; i < p1; i++) if (k < d->parsed[(size_t)i].hdr.subs.size() && d->subs.h[sub_off[(size_t)i] + k].deps == 0) slots[first + cur++] = (unsigned)(sub_off[(size_t)i] + k) + 1u;
+      q[2 * c + 1] = (unsigned)cur;
+    }
+    d->chunk_sub[d->nchunks] = (unsigned)n_subs;
+    for (size_t k = 0; k < n_subs; k++) slots[n_subs + k] = d->subs.h[k].deps;
   }
   const double t2 = now_ms();
   // ---- 4. H2D + kernels
@@ -404,24 +477,24 @@ int b200_decoder_decode_grid(b200_decoder* d, int cols, int rows, const uint8_t*
   } else {
     B200_CUDA_CHECK(cudaMemcpyAsync(d->rbsp.d, d->rbsp.h, n_rbsp, cudaMemcpyHostToDevice, s));
     B200_CUDA_CHECK(cudaMemcpyAsync(d->subs.d, d->subs.h, n_subs * sizeof(syn::Substream), cudaMemcpyHostToDevice, s));
-    B200_CUDA_CHECK(cudaMemcpyAsync(d->equeue.d, d->equeue.h, (2 + 2 * n_subs) * sizeof(unsigned), cudaMemcpyHostToDevice, s));
+    B200_CUDA_CHECK(cudaMemcpyAsync(d->equeue.d, d->equeue.h, (2 * MAX_CHUNKS + 2 * n_subs) * sizeof(unsigned), cudaMemcpyHostToDevice, s));
     B200_CUDA_CHECK(cudaMemcpyAsync(d->ctu_slice.d, d->ctu_slice.h, n_ctu * sizeof(uint16_t), cudaMemcpyHostToDevice, s));
     B200_CUDA_CHECK(cudaMemcpyAsync(d->epics.d, d->epics.h, (size_t)n * sizeof(EntropyPic), cudaMemcpyHostToDevice, s));
-    B200_CUDA_CHECK(cudaMemsetAsync(d->esync.d, 0, (1 + n_rows + n_subs) * sizeof(unsigned), s));
+    B200_CUDA_CHECK(cudaMemsetAsync(d->esync.d, 0, (1 + n_rows + n_subs + 2 * MAX_CHUNKS) * sizeof(unsigned), s));
     B200_CUDA_CHECK(cudaMemsetAsync(d->ecount.d, 0, 2 * sizeof(unsigned long long), s));
     h2d += n_rbsp + n_subs * (sizeof(syn::Substream) + 2 * sizeof(unsigned)) + n_ctu * sizeof(uint16_t) + (size_t)n * sizeof(EntropyPic);
   }
-  B200_CUDA_CHECK(cudaMemsetAsync(d->sync.d, 0, (2 * n_rows + 2) * sizeof(unsigned), s));
+  B200_CUDA_CHECK(cudaMemsetAsync(d->sync.d, 0, (2 * n_rows + 2 + MAX_CHUNKS) * sizeof(unsigned), s));
   if (!canvas_fully_covered) B200_CUDA_CHECK(cudaMemsetAsync(d->canvas.d, 0, cbytes, s));     // uncovered canvas stays zero (calloc in the reference)
   d->n_rows = n_rows; d->cbytes = cbytes; d->canvas_fully_covered = canvas_fully_covered; d->npics = n; d->n_subs = n_subs; d->used_device_front_end = devfe;
-  int launches = 0;
-  if ((rc = run_device_pipeline(d, n, s, &launches))) return rc;
-  d->last_stream = s; d->have_result = true;
   b200_image_info& inf = d->info;
   inf.width = cw; inf.height = chh; inf.tile_width = tw; inf.tile_height = th; inf.chroma = chroma ? B200_CHROMA_420 : B200_CHROMA_MONO; inf.bit_depth = bd;
   inf.colour_primaries = d->parsed[0].hdr.colour_primaries; inf.transfer_characteristics = d->parsed[0].hdr.transfer_characteristics;
   inf.matrix_coefficients = d->parsed[0].hdr.matrix_coefficients; inf.full_range = d->parsed[0].hdr.full_range;
   if (info) *info = inf;
+  int launches = 0;
+  if ((rc = run_device_pipeline(d, n, s, &launches))) return rc;
+  d->last_stream = s; d->have_result = true;
   b200_decode_stats& st = d->stats;
   memset(&st, 0, sizeof st);
   st.parse_ms = t1 - t0; st.pack_ms = t2 - t1; st.total_ms = now_ms() - t0;
@@ -439,11 +512,11 @@ int b200_decoder_decode_grid(b200_decoder* d, int cols, int rows, const uint8_t*
 int b200_decoder_rerun_device(b200_decoder* d, void* stream_) {
   if (!d || !d->have_result) return set_error(B200_E_INVALID, "no decode result");
   cudaStream_t s = (cudaStream_t)stream_;
-  B200_CUDA_CHECK(cudaMemsetAsync(d->sync.d, 0, (2 * d->n_rows + 2) * sizeof(unsigned), s));
+  B200_CUDA_CHECK(cudaMemsetAsync(d->sync.d, 0, (2 * d->n_rows + 2 + MAX_CHUNKS) * sizeof(unsigned), s));
   if (d->used_device_front_end) {
-    B200_CUDA_CHECK(cudaMemsetAsync(d->esync.d, 0, (1 + d->n_rows + d->n_subs) * sizeof(unsigned), s));
+    B200_CUDA_CHECK(cudaMemsetAsync(d->esync.d, 0, (1 + d->n_rows + d->n_subs + 2 * MAX_CHUNKS) * sizeof(unsigned), s));
     B200_CUDA_CHECK(cudaMemsetAsync(d->ecount.d, 0, 2 * sizeof(unsigned long long), s));
-    B200_CUDA_CHECK(cudaMemcpyAsync(d->equeue.d, d->equeue.h, (2 + 2 * d->n_subs) * sizeof(unsigned), cudaMemcpyHostToDevice, s));
+    B200_CUDA_CHECK(cudaMemcpyAsync(d->equeue.d, d->equeue.h, (2 * MAX_CHUNKS + 2 * d->n_subs) * sizeof(unsigned), cudaMemcpyHostToDevice, s));
   }
   int launches = 0;
   int rc = run_device_pipeline(d, d->npics, s, &launches);
@@ -459,7 +532,7 @@ int b200_decoder_get_stats(b200_decoder* d, b200_decode_stats* out) {
   cudaEventElapsedTime(&c, d->ev[2], d->ev[3]); cudaEventElapsedTime(&e, d->ev[3], d->ev[4]);
   if (b < 0) { en += b; b = 0; }   // K0 and K1 overlap: recon_ms is the part of K1 that runs after K0 has finished
   d->stats.h2d_ms = a; d->stats.entropy_ms = en; d->stats.recon_ms = b; d->stats.deblock_ms = c; d->stats.sao_ms = e; d->stats.gpu_ms = en + b + c + e;
-  d->stats.front_end = d->used_device_front_end ? (d->last_overlapped ? 2 : 1) : 0;
+  d->stats.front_end = d->used_device_front_end ? (d->last_chunked ? 3 : (d->last_overlapped ? 2 : 1)) : 0;
   if (d->used_device_front_end) {
     B200_CUDA_CHECK(cudaMemcpy(d->ecount.h, d->ecount.d, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
     d->stats.transform_units = d->ecount.h[0]; d->stats.coefficient_entries = d->ecount.h[1];
@@ -512,7 +585,7 @@ int b200_decoder_debug_read_tile(b200_decoder* d, int index, int stage, void* y,
 // Common part of the fused entry points: decode -> colour conversion into one of the two device RGB buffers.
 static int decode_to_rgb_device(b200_decoder* d, int cols, int rows, const uint8_t* const* au, const size_t* au_size, uint64_t max_pixels, int canvas_w,
                                 int canvas_h, const b200_geometry* geom, const b200_color_options* opt, b200_image_info* info, int slot, size_t* rowb_out,
-                                size_t* pitch_out, int* out_h) {
+                                size_t* pitch_out, int* out_h, void* direct_out, size_t direct_stride, bool* bands_copied) {
   if (!d->own) {
     B200_CUDA_CHECK(cudaStreamCreateWithFlags(&d->own, cudaStreamNonBlocking));
     B200_CUDA_CHECK(cudaStreamCreateWithFlags(&d->copy, cudaStreamNonBlocking));
@@ -524,12 +597,6 @@ static int decode_to_rgb_device(b200_decoder* d, int cols, int rows, const uint8
   // the page-locked staging of the previous call must have left for the device before the host overwrites it
   B200_CUDA_CHECK(cudaEventSynchronize(d->ev[1]));
   b200_image_info inf;
-  int rc = b200_decoder_decode_grid(d, cols, rows, au, au_size, max_pixels, canvas_w, canvas_h, &inf, s);
-  if (rc) return rc;
-  if (info) *info = inf;
-  B200_CUDA_CHECK(cudaMemcpyAsync(&d->err_host[slot], d->sync.d + 1, sizeof(unsigned), cudaMemcpyDeviceToHost, s));   // this step's error flag (the next step clears the device copy)
-  b200_planes pl; if ((rc = b200_decoder_get_planes(d, &pl))) return rc;
-  b200_geometry g; if (geom) g = *geom; else b200_geometry_identity(inf.width, inf.height, &g);
   size_t bpp;
   switch (opt->out_chroma) {
     case B200_CHROMA_INTERLEAVED_RGB: bpp = 3; break; case B200_CHROMA_INTERLEAVED_RGBA: bpp = 4; break;
@@ -537,11 +604,62 @@ static int decode_to_rgb_device(b200_decoder* d, int cols, int rows, const uint8
     case B200_CHROMA_INTERLEAVED_RRGGBBAA_BE: case B200_CHROMA_INTERLEAVED_RRGGBBAA_LE: bpp = 8; break;
     default: return set_error(B200_E_UNSUPPORTED, "the fused entry points need an interleaved target");
   }
+  // Chunked grids: the colour conversion (and the copy to a page-locked destination) of a band of tile rows is queued right
+  // behind the band's SAO, while the entropy kernel still decodes the bands below.  Band-wise conversion equals the
+  // whole-picture one for the reference's default planner choice (nearest-neighbour chroma, per-sample arithmetic) without
+  // rotate / mirror / crop; every other request converts the finished canvas in one go, below.
+  bool banded = false; int hook_rc = B200_OK;
+  *bands_copied = false;
+  if (!geom && opt->chroma_upsampling == 0) {
+    d->chunk_hook = [&, slot, bpp](int c, cudaStream_t side) -> int {
+      const b200_image_info& I = d->info;
+      const int th = I.tile_height, y0 = std::min(I.height, (d->chunk_pic[c] / d->grid_cols) * th);
+      const int y1 = c + 1 == d->nchunks ? I.height : std::min(I.height, (d->chunk_pic[c + 1] / d->grid_cols) * th);
+      const size_t rowb = (size_t)I.width * bpp, pitch = (rowb + 255) & ~(size_t)255;
+      int rc2;
+      if (c == 0) {
+        if ((rc2 = d->rgb2[slot].reserve(pitch * (size_t)I.height, false))) return hook_rc = rc2;
+        B200_CUDA_CHECK(cudaStreamWaitEvent(side, d->ev_d2h[slot], 0));       // the copy that last read this buffer has finished
+        banded = true;
+      }
+      if (y1 <= y0) return B200_OK;
+      const int bps = I.bit_depth > 8 ? 2 : 1; (void)bps;
+      b200_planes pl; memset(&pl, 0, sizeof pl);
+      pl.y = d->canvas.d + d->canvas_off[0] + (size_t)y0 * d->canvas_pitch[0]; pl.y_stride = d->canvas_pitch[0];
+      if (I.chroma != B200_CHROMA_MONO) {
+        pl.cb = d->canvas.d + d->canvas_off[1] + (size_t)(y0 >> 1) * d->canvas_pitch[1]; pl.cr = d->canvas.d + d->canvas_off[2] + (size_t)(y0 >> 1) * d->canvas_pitch[2];
+        pl.c_stride = d->canvas_pitch[1];
+      }
+      pl.width = I.width; pl.height = y1 - y0; pl.chroma = I.chroma; pl.bit_depth = I.bit_depth;
+      pl.colour_primaries = I.colour_primaries; pl.transfer_characteristics = I.transfer_characteristics; pl.matrix_coefficients = I.matrix_coefficients; pl.full_range = I.full_range;
+      b200_geometry g; b200_geometry_identity(pl.width, pl.height, &g);
+      uint8_t* dst = d->rgb2[slot].d + (size_t)y0 * pitch;
+      if ((rc2 = b200_color_convert_device(&pl, &g, opt, dst, nullptr, nullptr, pitch, side, nullptr))) return hook_rc = rc2;
+      if (direct_out) {
+        if (!d->ev_chunk[c]) B200_CUDA_CHECK(cudaEventCreateWithFlags(&d->ev_chunk[c], cudaEventDisableTiming));
+        B200_CUDA_CHECK(cudaEventRecord(d->ev_chunk[c], side));
+        B200_CUDA_CHECK(cudaStreamWaitEvent(d->copy, d->ev_chunk[c], 0));
+        B200_CUDA_CHECK(cudaMemcpy2DAsync(static_cast<uint8_t*>(direct_out) + (size_t)y0 * direct_stride, direct_stride, dst, pitch, rowb, (size_t)(y1 - y0), cudaMemcpyDeviceToHost, d->copy));
+      }
+      return B200_OK;
+    };
+  }
+  int rc = b200_decoder_decode_grid(d, cols, rows, au, au_size, max_pixels, canvas_w, canvas_h, &inf, s);
+  d->chunk_hook = nullptr;
+  if (rc) return rc;
+  if (hook_rc) return hook_rc;
+  if (info) *info = inf;
+  B200_CUDA_CHECK(cudaMemcpyAsync(&d->err_host[slot], d->sync.d + 1, sizeof(unsigned), cudaMemcpyDeviceToHost, s));   // this step's error flag (the next step clears the device copy)
+  b200_planes pl; if ((rc = b200_decoder_get_planes(d, &pl))) return rc;
+  b200_geometry g; if (geom) g = *geom; else b200_geometry_identity(inf.width, inf.height, &g);
   const size_t rowb = (size_t)g.out_w * bpp, pitch = (rowb + 255) & ~(size_t)255;
-  if ((rc = d->rgb2[slot].reserve(pitch * g.out_h, false))) return rc;
-  B200_CUDA_CHECK(cudaStreamWaitEvent(s, d->ev_d2h[slot], 0));           // the copy that last read this buffer has finished
-  if ((rc = b200_color_convert_device(&pl, &g, opt, d->rgb2[slot].d, nullptr, nullptr, pitch, s, nullptr))) return rc;
+  if (!banded) {
+    if ((rc = d->rgb2[slot].reserve(pitch * g.out_h, false))) return rc;
+    B200_CUDA_CHECK(cudaStreamWaitEvent(s, d->ev_d2h[slot], 0));           // the copy that last read this buffer has finished
+    if ((rc = b200_color_convert_device(&pl, &g, opt, d->rgb2[slot].d, nullptr, nullptr, pitch, s, nullptr))) return rc;
+  }
   B200_CUDA_CHECK(cudaEventRecord(d->ev_k6[slot], s));
+  *bands_copied = banded && direct_out != nullptr;
   *rowb_out = rowb; *pitch_out = pitch; *out_h = g.out_h;
   return B200_OK;
 }
@@ -557,15 +675,20 @@ int b200_decode_grid_to_rgb_host(b200_decoder* d, int cols, int rows, const uint
                                  uint64_t max_pixels, int canvas_w, int canvas_h, const b200_geometry* geom,
                                  const b200_color_options* opt, void* out, size_t out_stride, b200_image_info* info) {
   if (!d || !opt || !out) return set_error(B200_E_INVALID, "null argument");
-  size_t rowb = 0, pitch = 0; int oh = 0;
-  int rc = decode_to_rgb_device(d, cols, rows, au, au_size, max_pixels, canvas_w, canvas_h, geom, opt, info, 0, &rowb, &pitch, &oh);
+  size_t rowb = 0, pitch = 0; int oh = 0; bool copied = false;
+  const bool pinned = is_page_locked(out);
+  int rc = decode_to_rgb_device(d, cols, rows, au, au_size, max_pixels, canvas_w, canvas_h, geom, opt, info, 0, &rowb, &pitch, &oh, pinned ? out : nullptr, out_stride, &copied);
   if (rc) return rc;
   cudaStream_t s = d->own;
   uint8_t* rgb = d->rgb2[0].d;
   // D2H: straight into the caller's buffer when it is page-locked (b200_host_alloc, cudaHostAlloc, cudaHostRegister);
   // pageable memory goes through a page-locked bounce buffer in row bands, the copy of band i overlapping the memcpy of
   // band i - 1 on the decoder's host threads
-  if (is_page_locked(out)) {
+  if (copied) {                                         // the bands left through the copy stream as they were finished
+    B200_CUDA_CHECK(cudaEventRecord(d->ev_d2h[0], d->copy));
+    B200_CUDA_CHECK(cudaStreamSynchronize(s));
+    B200_CUDA_CHECK(cudaStreamSynchronize(d->copy));
+  } else if (pinned) {
     B200_CUDA_CHECK(cudaMemcpy2DAsync(out, out_stride, rgb, pitch, rowb, (size_t)oh, cudaMemcpyDeviceToHost, s));
     B200_CUDA_CHECK(cudaEventRecord(d->ev_d2h[0], s));
     B200_CUDA_CHECK(cudaStreamSynchronize(s));
@@ -610,11 +733,13 @@ int b200_decode_grid_to_rgb_host_async(b200_decoder* d, int cols, int rows, cons
   if (!is_page_locked(out)) return set_error(B200_E_INVALID, "the asynchronous entry point needs a page-locked output buffer (b200_host_alloc / b200_host_register)");
   const int slot = d->async_slot; d->async_slot ^= 1;
   if (d->err_host && d->err_host[slot]) d->async_error = true;                 // the step that used this slot two calls ago failed
-  size_t rowb = 0, pitch = 0; int oh = 0;
-  int rc = decode_to_rgb_device(d, cols, rows, au, au_size, max_pixels, canvas_w, canvas_h, geom, opt, info, slot, &rowb, &pitch, &oh);
+  size_t rowb = 0, pitch = 0; int oh = 0; bool copied = false;
+  int rc = decode_to_rgb_device(d, cols, rows, au, au_size, max_pixels, canvas_w, canvas_h, geom, opt, info, slot, &rowb, &pitch, &oh, out, out_stride, &copied);
   if (rc) return rc;
-  B200_CUDA_CHECK(cudaStreamWaitEvent(d->copy, d->ev_k6[slot], 0));
-  B200_CUDA_CHECK(cudaMemcpy2DAsync(out, out_stride, d->rgb2[slot].d, pitch, rowb, (size_t)oh, cudaMemcpyDeviceToHost, d->copy));
+  if (!copied) {
+    B200_CUDA_CHECK(cudaStreamWaitEvent(d->copy, d->ev_k6[slot], 0));
+    B200_CUDA_CHECK(cudaMemcpy2DAsync(out, out_stride, d->rgb2[slot].d, pitch, rowb, (size_t)oh, cudaMemcpyDeviceToHost, d->copy));
+  }
   B200_CUDA_CHECK(cudaEventRecord(d->ev_d2h[slot], d->copy));
   return B200_OK;
 }

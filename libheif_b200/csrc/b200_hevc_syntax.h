@@ -145,6 +145,7 @@ struct Substream {
   int32_t wake_ctb2;             // sub-stream that becomes startable once this one has stored the contexts after its 2nd CTB of a row (9.3.2.2)
   int32_t wake_end;              // sub-stream that continues this one's end state (dependent slice segment)
   uint32_t deps;                 // number of such events this sub-stream waits for before it may start
+  uint32_t chunk;                // priority class of the ready queue: the chunk (group of tile rows) its picture belongs to
 };
 
 struct PicBuffers {              // per-picture arrays (host memory on the host path, HBM on the device path)
