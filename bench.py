@@ -322,8 +322,8 @@ def main():
     overlapped = False
     chunked = bool(nrows) and stats_e2e.front_end == 3
     if nrows:
-        # the timed legs above ran the chunked pipeline when the band is large enough (K1 / K3 / K4 / K6 / D2H of a group of tile
-        # rows overlap K0 of the next group); the per-kernel times are taken with the kernels back to back (B200_CHUNKS=0)
+        # the e2e legs above ran K1 .. K6 in row bands (D2H of a band overlaps the kernels of the next); the per-kernel times are
+        # taken with one launch per kernel for the whole grid (B200_CHUNKS=0)
         os.environ["B200_CHUNKS"] = "0"
         dec.decode_grid(tiles, cols=side, rows=nrows)
         for _ in range(nk):
@@ -369,9 +369,9 @@ def main():
                 "api": "b200_decode_grid_to_rgb_host (one C-ABI call per rank: host access units -> page-locked host RGB)"},
         "e2e_pipelined": {"value": pixels / 1e6 / (pipe_ms / 1e3), "unit": "MP/s", "ms_per_step": pipe_ms,
                           "api": "b200_decode_grid_to_rgb_host_async x steps + b200_decoder_wait: D2H of step i overlaps the kernels of step i + 1 (throughput of a batch job; e2e above is the latency of one call)"},
-        "pipeline": {"chunked": chunked, "entropy_ms_in_timed_legs": stats_e2e.entropy_ms, "tail_ms_after_entropy": stats_e2e.recon_ms + stats_e2e.deblock_ms + stats_e2e.sao_ms,
-                     "note": "chunked: groups of tile rows leave the entropy kernel in priority order; their reconstruction, deblocking, SAO, colour conversion and D2H run while the entropy kernel decodes the next group (kernels_ms below are measured back to back, B200_CHUNKS=0)"},
-        "gpu_launches": (stats_e2e.kernel_launches + ((stats_e2e.kernel_launches - 1) // 5 if chunked else 1)) * args.steps,   # K0, (wait, K1, K3 x2, K4, K6) per chunk -- of the e2e leg
+        "pipeline": {"bands": stats_e2e.bands, "entropy_ms_in_e2e_leg": stats_e2e.entropy_ms, "band_pipeline_ms_in_e2e_leg": stats_e2e.recon_ms + stats_e2e.deblock_ms + stats_e2e.sao_ms,
+                     "note": "e2e legs of large grids: after the entropy kernel the tile rows go through K1 -> K3 -> K4 -> K6 in row bands and the D2H of band c overlaps the kernels of band c + 1 (kernels_ms below: one launch per kernel for the whole grid, B200_CHUNKS=0)"},
+        "gpu_launches": (stats_e2e.kernel_launches + ((stats_e2e.kernel_launches - 1) // 4 if chunked else 1)) * args.steps,   # K0, (K1, K3 x2, K4, K6) per band -- of the e2e leg
         "clocks": clk.summary(),
         "roofline": {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
                      "traffic": tr["bytes_per_launch"] if tr else None, "traffic_source": tr["source"] if tr else None,

@@ -200,10 +200,11 @@ typedef struct b200_decode_stats {
   int kernel_launches;
   int front_end;                                        /* 0 = CABAC decoded on the host cores, 1 = on the GPU, 2 = on the GPU with the
                                                            reconstruction kernel running concurrently (entropy_ms then covers both),
-                                                           3 = on the GPU, chunked: groups of tile rows leave the entropy kernel in order and
-                                                           are reconstructed / filtered (/ converted / copied out) while it decodes the next
-                                                           ones; recon_ms is then what remains after the entropy kernel, deblock_ms = sao_ms = 0
-                                                           (B200_CHUNKS=0 restores the back-to-back kernels and their separate times) */
+                                                           3 = on the GPU, and after it the tile rows went through reconstruction .. colour
+                                                           conversion in `bands` row bands, the D2H of a band overlapping the kernels of the
+                                                           next (fused host entry points, large grids); recon_ms is then the whole band
+                                                           pipeline, deblock_ms = sao_ms = 0 (B200_CHUNKS=0: separate kernels and times) */
+  int bands;
 } b200_decode_stats;
 
 /* host_threads: CABAC parser threads (0 = number of online cores).  The CUDA device is the current one. */

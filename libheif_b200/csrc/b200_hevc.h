@@ -56,26 +56,20 @@ struct DeviceBatch {
   int max_log2_ctb;              // largest CTB size of the batch (sizes the per-warp shared memory)
 };
 // Device front-end (b200_hevc_entropy.cu)
-enum { MAX_CHUNKS = 8 };
+enum { MAX_CHUNKS = 16 };   // row bands of a large grid that leave the pipeline one after the other (b200_hevc_decode.cu)
 struct EntropyPic { syn::SeqParams sp; syn::PicBuffers pb; uint32_t progress_base, sub_base; };
 struct EntropyBatch {
   const EntropyPic* pics; int npics;
   const syn::Substream* subs;    // batch-wide, grouped per picture (EntropyPic::sub_base)
   int nsubs;
-  // Ready queues, one per CHUNK (a contiguous range of pictures = of sub-stream indices; a lower chunk has priority, so
-  // the chunks finish one after the other and everything downstream of K0 can start on chunk c while K0 still decodes
-  // chunk c + 1): queue[chunk_first[c] + k] holds (batch-wide sub-stream index + 1) of the k-th sub-stream of chunk c that
-  // became ready, 0 = not yet pushed; qctl[2 c] / qctl[2 c + 1] are its pop / push cursors; deps[i] counts the events
-  // sub-stream i still waits for (wake_* links in syn::Substream are batch-wide).  chunk_done[c] counts finished
-  // sub-streams, chunk_done[MAX_CHUNKS + c] becomes 1 when chunk c is complete (polled by launch_wait_flag).
-  unsigned int* queue; unsigned int* qctl; unsigned int* deps; unsigned int* chunk_done;
-  int nchunks; unsigned int chunk_first[MAX_CHUNKS + 1];
+  // ready queue: queue[0 .. nsubs) holds (batch-wide sub-stream index + 1), 0 = not yet pushed; qhead / qtail are the pop and
+  // push cursors; deps[i] counts the events sub-stream i still waits for (wake_* links in syn::Substream are batch-wide)
+  unsigned int* queue; unsigned int* qhead; unsigned int* qtail; unsigned int* deps;
   unsigned int* progress; unsigned int* sub_done; unsigned int* error_flag;
   int blocks_per_sm;             // > 0: cap of resident CTAs per SM (co-residency with K1)
   int common;                    // 1: every picture matches syn::CfgCommon (specialised kernel)
 };
 int launch_entropy(const EntropyBatch& b, cudaStream_t s);
-int launch_wait_flag(const unsigned int* flag, unsigned int* error_flag, cudaStream_t s);   // a one-thread kernel that returns when *flag != 0
 int launch_entropy_stats(const EntropyBatch& b, unsigned long long* out2, cudaStream_t s);
 int launch_recon(const DeviceBatch& b, cudaStream_t s);
 int launch_deblock(const DeviceBatch& b, const PicDesc* host_pics, cudaStream_t s);

@@ -99,12 +99,11 @@ struct b200_decoder {
   bool have_result = false;
   int debug_stage = 0;
   size_t n_rows = 0, n_items = 0, cbytes = 0; bool canvas_fully_covered = true; int max_log2_ctb = 6, info_bps = 1;
-  // Chunked pipeline (grids larger than one wave of sub-streams): K0 decodes the chunks (groups of tile rows) in priority
-  // order; K1, K3, K4 (and, in the fused entry points, K6 + D2H through chunk_hook) of chunk c run on `side` while K0
-  // still works on the later chunks.
+  // Band pipeline of the fused host entry points (large grids): after K0, the tile rows go through K1 -> K3 -> K4 -> K6 in
+  // bands (chunks), and the D2H of band c (copy stream, chunk_hook) overlaps the kernels of band c + 1.
   int nchunks = 1, grid_cols = 1; bool last_chunked = false;
-  int chunk_pic[MAX_CHUNKS + 1] = {0}; size_t chunk_item[MAX_CHUNKS + 1] = {0}; unsigned chunk_sub[MAX_CHUNKS + 1] = {0};
-  std::function<int(int, cudaStream_t)> chunk_hook;   // queued after K4 of chunk c on the side stream
+  int chunk_pic[MAX_CHUNKS + 1] = {0}; size_t chunk_item[MAX_CHUNKS + 1] = {0};
+  std::function<int(int, cudaStream_t)> chunk_hook;   // queued after K4 of band c on the decode stream
   cudaEvent_t ev_chunk[MAX_CHUNKS] = {nullptr};
   ~b200_decoder() {
     delete pool;
@@ -172,7 +171,7 @@ static int run_device_pipeline(b200_decoder* d, int n, cudaStream_t s, int* laun
   int rc;
   int launches = 0;
   const bool devfe = d->used_device_front_end;
-  const bool chunked = devfe && d->nchunks > 1;
+  const bool chunked = d->nchunks > 1;
   bool overlap = devfe && !chunked && use_overlap(d->n_subs);
   if (overlap) overlap = overlap_acquire(d);
   struct Release { bool armed; ~Release() { if (armed) overlap_release(); } } release{overlap};   // error paths
@@ -184,10 +183,8 @@ static int run_device_pipeline(b200_decoder* d, int n, cudaStream_t s, int* laun
   if (devfe) {
     EntropyBatch e{};
     e.pics = d->epics.d; e.npics = d->npics; e.subs = d->subs.d; e.nsubs = (int)d->n_subs;
-    e.qctl = d->equeue.d; e.queue = d->equeue.d + 2 * MAX_CHUNKS; e.deps = e.queue + d->n_subs;
+    e.qhead = d->equeue.d; e.qtail = d->equeue.d + 1; e.queue = d->equeue.d + 2; e.deps = d->equeue.d + 2 + d->n_subs;
     e.progress = d->esync.d + 1; e.sub_done = d->esync.d + 1 + d->n_rows; e.error_flag = d->sync.d + 1;
-    e.chunk_done = d->esync.d + 1 + d->n_rows + d->n_subs;
-    e.nchunks = d->nchunks; for (int c = 0; c <= d->nchunks; c++) e.chunk_first[c] = d->chunk_sub[c];
     e.common = 1;
     if (getenv("B200_ENTROPY_GENERIC")) e.common = 0;
     for (int i = 0; i < d->npics && e.common; i++) if (!syn::matches_common(d->epics.h[i].sp)) e.common = 0;
@@ -202,36 +199,6 @@ static int run_device_pipeline(b200_decoder* d, int n, cudaStream_t s, int* laun
       cudaEventRecord(d->ev[5], d->side);
       if ((rc = launch_entropy_stats(e, d->ecount.d, d->side))) return rc;
       cudaEventRecord(d->ev_join, d->side);
-    } else if (chunked) {
-      // K0 on `s` (a CTA per SM fewer than it could hold, so that the kernels below fit beside it); on `side`, per chunk:
-      // wait for K0's completion flag of the chunk, then K1 -> K3 -> K4 (-> the caller's hook: K6, D2H) of its pictures
-      if (!d->side) { B200_CUDA_CHECK(cudaStreamCreateWithFlags(&d->side, cudaStreamNonBlocking)); B200_CUDA_CHECK(cudaEventCreate(&d->ev_fork)); B200_CUDA_CHECK(cudaEventCreate(&d->ev_join)); }
-      e.blocks_per_sm = overlap_blocks("B200_CHUNK_K0_BLOCKS", 3);
-      cudaEventRecord(d->ev_fork, s);
-      if ((rc = launch_entropy(e, s))) return rc;
-      cudaEventRecord(d->ev[5], s);
-      if ((rc = launch_entropy_stats(e, d->ecount.d, s))) return rc;
-      launches += 1;
-      B200_CUDA_CHECK(cudaStreamWaitEvent(d->side, d->ev_fork, 0));
-      for (int c = 0; c < d->nchunks; c++) {
-        if ((rc = launch_wait_flag(e.chunk_done + MAX_CHUNKS + c, b.error_flag, d->side))) return rc;
-        DeviceBatch bc = b;
-        bc.row_list = d->rows.d + d->chunk_item[c]; bc.nrows = (int)(d->chunk_item[c + 1] - d->chunk_item[c]); bc.ticket = b.ticket + c;
-        bc.entropy_progress = e.progress;            // K0 is still running (on later chunks): read its output past L1
-        if ((rc = launch_recon(bc, d->side))) return rc;
-        DeviceBatch bf = b;
-        const int p0 = d->chunk_pic[c];
-        bf.pics = d->pics.d + p0; bf.npics = d->chunk_pic[c + 1] - p0;
-        if (d->debug_stage != 1 && (rc = launch_deblock(bf, d->pics.h + p0, d->side))) return rc;
-        if (d->debug_stage == 0 && (rc = launch_sao(bf, d->pics.h + p0, d->side))) return rc;
-        launches += 5;
-        if (d->chunk_hook && (rc = d->chunk_hook(c, d->side))) return rc;
-      }
-      cudaEventRecord(d->ev_join, d->side);
-      B200_CUDA_CHECK(cudaStreamWaitEvent(s, d->ev_join, 0));
-      cudaEventRecord(d->ev[2], s); cudaEventRecord(d->ev[3], s); cudaEventRecord(d->ev[4], s);   // recon_ms = what is left of the last chunk after K0
-      if (launches_out) *launches_out = launches;
-      return B200_OK;
     } else {
       if ((rc = launch_entropy(e, s))) return rc;
       cudaEventRecord(d->ev[5], s);
@@ -239,6 +206,27 @@ static int run_device_pipeline(b200_decoder* d, int n, cudaStream_t s, int* laun
     }
     launches += 1;
   } else cudaEventRecord(d->ev[5], s);
+  if (chunked) {
+    // Row bands of a large grid leave the pipeline one after the other: K1 -> K3 -> K4 of band c, then the caller's hook
+    // (K6 of the band + its D2H on the copy stream, which overlaps the kernels of band c + 1).  K0 is NOT part of this:
+    // letting the bands leave K0 in order (priority queues) and running these kernels beside it was measured slower --
+    // K0 loses more from the co-residency (3 instead of 4 CTAs per SM) and the priorities than the overlap gains.
+    for (int c = 0; c < d->nchunks; c++) {
+      DeviceBatch bc = b;
+      bc.row_list = d->rows.d + d->chunk_item[c]; bc.nrows = (int)(d->chunk_item[c + 1] - d->chunk_item[c]); bc.ticket = b.ticket + c;
+      if ((rc = launch_recon(bc, s))) return rc;
+      DeviceBatch bf = b;
+      const int p0 = d->chunk_pic[c];
+      bf.pics = d->pics.d + p0; bf.npics = d->chunk_pic[c + 1] - p0;
+      if (d->debug_stage != 1 && (rc = launch_deblock(bf, d->pics.h + p0, s))) return rc;
+      if (d->debug_stage == 0 && (rc = launch_sao(bf, d->pics.h + p0, s))) return rc;
+      launches += 4;
+      if (d->chunk_hook && (rc = d->chunk_hook(c, s))) return rc;
+    }
+    cudaEventRecord(d->ev[2], s); cudaEventRecord(d->ev[3], s); cudaEventRecord(d->ev[4], s);   // recon_ms = the whole band pipeline (incl. the hooks' K6)
+    if (launches_out) *launches_out = launches;
+    return B200_OK;
+  }
   if ((rc = launch_recon(b, s))) return rc;
   if (devfe && overlap) {
     B200_CUDA_CHECK(cudaStreamWaitEvent(s, d->ev_join, 0));
@@ -338,10 +326,10 @@ int b200_decoder_decode_grid(b200_decoder* d, int cols, int rows, const uint8_t*
       (rc = d->slices.reserve(n_slice)) || (rc = d->qp8.reserve(n_map, !devfe)) || (rc = d->edge8.reserve(n_map, !devfe)) || (rc = d->rows.reserve(2 * n_rows)) ||
       (rc = d->sync.reserve(2 * n_rows + 2 + MAX_CHUNKS, false)) || (rc = d->rec.reserve(rec_bytes, false)))
     return rc;
-  if (devfe && ((rc = d->rbsp.reserve(n_rbsp + 16)) || (rc = d->subs.reserve(n_subs)) || (rc = d->equeue.reserve(2 * MAX_CHUNKS + 2 * n_subs)) || (rc = d->ctu_slice.reserve(n_ctu)) ||
+  if (devfe && ((rc = d->rbsp.reserve(n_rbsp + 16)) || (rc = d->subs.reserve(n_subs)) || (rc = d->equeue.reserve(2 + 2 * n_subs)) || (rc = d->ctu_slice.reserve(n_ctu)) ||
                 (rc = d->epics.reserve((size_t)n)) || (rc = d->ipm4.reserve(n_map4, false)) || (rc = d->cd8.reserve(n_map, false)) ||
                 (rc = d->wpp_ctx.reserve(n_rows * syn::CTX_STRIDE, false)) || (rc = d->end_state.reserve(n_subs * syn::CTX_STRIDE + 16, false)) ||
-                (rc = d->esync.reserve(1 + n_rows + n_subs + 2 * MAX_CHUNKS, false)) || (rc = d->ecount.reserve(2, true))))
+                (rc = d->esync.reserve(1 + n_rows + n_subs, false)) || (rc = d->ecount.reserve(2, true))))
     return rc;
   // canvas planes
   size_t cbytes = 0;
@@ -370,11 +358,12 @@ int b200_decoder_decode_grid(b200_decoder* d, int cols, int rows, const uint8_t*
   // Launch order of the CTB rows: row-major ACROSS pictures (all first rows, then all second rows, ...).  A row's
   // predecessor always holds a smaller ticket (deadlock freedom), and the resident warps spread over every tile's
   // wavefront instead of idling behind one tile's 2-CTB stagger.
-  // Chunks: groups of whole tile rows of about one wave of sub-streams each (64 tiles of 1024x1024), when the batch is
-  // larger than what K0 and K1 can overlap CTB by CTB (use_overlap).  One chunk = the classic back-to-back pipeline.
+  // Chunks: bands of whole tile rows (about 64 tiles each) for callers that take the result band by band (the fused host
+  // entry points: D2H of band c overlaps the kernels of band c + 1), when the batch is larger than what K0 and K1 overlap
+  // CTB by CTB (use_overlap).  One chunk = the classic back-to-back pipeline.
   { int nch = 1, rpc = rows;
     const char* ce = getenv("B200_CHUNKS");
-    if (devfe && rows >= 2 && (ce ? atoi(ce) != 0 : !use_overlap(n_subs))) {      // B200_CHUNKS=0 / 1: never / always (tests, diagnostics)
+    if (rows >= 2 && (ce ? atoi(ce) != 0 : (d->chunk_hook && (!devfe || !use_overlap(n_subs))))) {      // B200_CHUNKS=0 / 1: never / always (tests, diagnostics)
       int target = 64; if (const char* e = getenv("B200_CHUNK_TILES")) { const int v = atoi(e); if (v > 0) target = v; }
       rpc = std::max(1, (target + cols / 2) / cols);
       nch = (rows + rpc - 1) / rpc;
@@ -414,7 +403,7 @@ int b200_decoder_decode_grid(b200_decoder* d, int cols, int rows, const uint8_t*
       // its first bin -- the conditions of run_substream (b200_hevc_syntax.h): the contexts stored after the 2nd CTB of the
       // row above (WPP, 9.3.2.2) and the end state of the slice segment it continues.
       const size_t so = sub_off[(size_t)i];
-      for (size_t k = 0; k < H.subs.size(); k++) { syn::Substream ss = H.subs[k]; ss.pic = (uint32_t)i; ss.wake_ctb2 = ss.wake_end = -1; ss.deps = 0; ss.chunk = 0; d->subs.h[so + k] = ss; }
+      for (size_t k = 0; k < H.subs.size(); k++) { syn::Substream ss = H.subs[k]; ss.pic = (uint32_t)i; ss.wake_ctb2 = ss.wake_end = -1; ss.deps = 0; d->subs.h[so + k] = ss; }
       for (size_t k = 0; k < H.subs.size(); k++) {
         syn::Substream& ss = d->subs.h[so + k];
         if (ss.prev >= 0) { ss.deps++; d->subs.h[so + (size_t)ss.prev].wake_end = (int32_t)(so + k); }
@@ -437,27 +426,14 @@ int b200_decoder_decode_grid(b200_decoder* d, int cols, int rows, const uint8_t*
     }
   });
   if (devfe) {
-    // ready-queue image, per chunk: cursors, then (in the chunk's slot range) the sub-streams without prerequisites in
-    // "k-th sub-stream of every picture" order (so that whatever a popped sub-stream polls for was popped before it),
-    // empty slots; then the dependency counters
-    unsigned* q = d->equeue.h; unsigned* slots = q + 2 * MAX_CHUNKS;
-    for (int c = 0; c < MAX_CHUNKS; c++) q[2 * c] = q[2 * c + 1] = 0;
-    for (size_t k = 0; k < n_subs; k++) slots[k] = 0;
-    for (int c = 0; c < d->nchunks; c++) {
-      const int p0 = d->chunk_pic[c], p1 = d->chunk_pic[c + 1];
-      const size_t first = sub_off[(size_t)p0];
-      d->chunk_sub[c] = (unsigned)first;
-      size_t cur = 0, maxs = 0;
-      for (int i = p0; i < p1; i++) {
-        const size_t ns = d->parsed[(size_t)i].hdr.subs.size();
-        maxs = std::max(maxs, ns);
-        for (size_t k = 0; k < ns; k++) d->subs.h[sub_off[(size_t)i] + k].chunk = (uint32_t)c;
-      }
-      for (size_t k = 0; k < maxs; k++) for (int i = p0; i < p1; i++) if (k < d->parsed[(size_t)i].hdr.subs.size() && d->subs.h[sub_off[(size_t)i] + k].deps == 0) slots[first + cur++] = (unsigned)(sub_off[(size_t)i] + k) + 1u;
-      q[2 * c + 1] = (unsigned)cur;
-    }
-    d->chunk_sub[d->nchunks] = (unsigned)n_subs;
-    for (size_t k = 0; k < n_subs; k++) slots[n_subs + k] = d->subs.h[k].deps;
+    // ready queue image: cursors, the sub-streams without prerequisites in "k-th sub-stream of every picture" order (so
+    // that whatever a popped sub-stream polls for was popped before it), empty slots, the dependency counters
+    unsigned* q = d->equeue.h; size_t cur = 0, maxs = 0;
+    for (int i = 0; i < n; i++) maxs = std::max(maxs, d->parsed[(size_t)i].hdr.subs.size());
+    for (size_t k = 0; k < maxs; k++) for (int i = 0; i < n; i++) if (k < d->parsed[(size_t)i].hdr.subs.size() && d->subs.h[sub_off[(size_t)i] + k].deps == 0) q[2 + cur++] = (unsigned)(sub_off[(size_t)i] + k) + 1u;
+    q[0] = 0; q[1] = (unsigned)cur;
+    for (size_t k = cur; k < n_subs; k++) q[2 + k] = 0;
+    for (size_t k = 0; k < n_subs; k++) q[2 + n_subs + k] = d->subs.h[k].deps;
   }
   const double t2 = now_ms();
   // ---- 4. H2D + kernels
@@ -477,10 +453,10 @@ int b200_decoder_decode_grid(b200_decoder* d, int cols, int rows, const uint8_t*
   } else {
     B200_CUDA_CHECK(cudaMemcpyAsync(d->rbsp.d, d->rbsp.h, n_rbsp, cudaMemcpyHostToDevice, s));
     B200_CUDA_CHECK(cudaMemcpyAsync(d->subs.d, d->subs.h, n_subs * sizeof(syn::Substream), cudaMemcpyHostToDevice, s));
-    B200_CUDA_CHECK(cudaMemcpyAsync(d->equeue.d, d->equeue.h, (2 * MAX_CHUNKS + 2 * n_subs) * sizeof(unsigned), cudaMemcpyHostToDevice, s));
+    B200_CUDA_CHECK(cudaMemcpyAsync(d->equeue.d, d->equeue.h, (2 + 2 * n_subs) * sizeof(unsigned), cudaMemcpyHostToDevice, s));
     B200_CUDA_CHECK(cudaMemcpyAsync(d->ctu_slice.d, d->ctu_slice.h, n_ctu * sizeof(uint16_t), cudaMemcpyHostToDevice, s));
     B200_CUDA_CHECK(cudaMemcpyAsync(d->epics.d, d->epics.h, (size_t)n * sizeof(EntropyPic), cudaMemcpyHostToDevice, s));
-    B200_CUDA_CHECK(cudaMemsetAsync(d->esync.d, 0, (1 + n_rows + n_subs + 2 * MAX_CHUNKS) * sizeof(unsigned), s));
+    B200_CUDA_CHECK(cudaMemsetAsync(d->esync.d, 0, (1 + n_rows + n_subs) * sizeof(unsigned), s));
     B200_CUDA_CHECK(cudaMemsetAsync(d->ecount.d, 0, 2 * sizeof(unsigned long long), s));
     h2d += n_rbsp + n_subs * (sizeof(syn::Substream) + 2 * sizeof(unsigned)) + n_ctu * sizeof(uint16_t) + (size_t)n * sizeof(EntropyPic);
   }
@@ -514,9 +490,9 @@ int b200_decoder_rerun_device(b200_decoder* d, void* stream_) {
   cudaStream_t s = (cudaStream_t)stream_;
   B200_CUDA_CHECK(cudaMemsetAsync(d->sync.d, 0, (2 * d->n_rows + 2 + MAX_CHUNKS) * sizeof(unsigned), s));
   if (d->used_device_front_end) {
-    B200_CUDA_CHECK(cudaMemsetAsync(d->esync.d, 0, (1 + d->n_rows + d->n_subs + 2 * MAX_CHUNKS) * sizeof(unsigned), s));
+    B200_CUDA_CHECK(cudaMemsetAsync(d->esync.d, 0, (1 + d->n_rows + d->n_subs) * sizeof(unsigned), s));
     B200_CUDA_CHECK(cudaMemsetAsync(d->ecount.d, 0, 2 * sizeof(unsigned long long), s));
-    B200_CUDA_CHECK(cudaMemcpyAsync(d->equeue.d, d->equeue.h, (2 * MAX_CHUNKS + 2 * d->n_subs) * sizeof(unsigned), cudaMemcpyHostToDevice, s));
+    B200_CUDA_CHECK(cudaMemcpyAsync(d->equeue.d, d->equeue.h, (2 + 2 * d->n_subs) * sizeof(unsigned), cudaMemcpyHostToDevice, s));
   }
   int launches = 0;
   int rc = run_device_pipeline(d, d->npics, s, &launches);
@@ -533,6 +509,7 @@ int b200_decoder_get_stats(b200_decoder* d, b200_decode_stats* out) {
   if (b < 0) { en += b; b = 0; }   // K0 and K1 overlap: recon_ms is the part of K1 that runs after K0 has finished
   d->stats.h2d_ms = a; d->stats.entropy_ms = en; d->stats.recon_ms = b; d->stats.deblock_ms = c; d->stats.sao_ms = e; d->stats.gpu_ms = en + b + c + e;
   d->stats.front_end = d->used_device_front_end ? (d->last_chunked ? 3 : (d->last_overlapped ? 2 : 1)) : 0;
+  d->stats.bands = d->last_chunked ? d->nchunks : 1;
   if (d->used_device_front_end) {
     B200_CUDA_CHECK(cudaMemcpy(d->ecount.h, d->ecount.d, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
     d->stats.transform_units = d->ecount.h[0]; d->stats.coefficient_entries = d->ecount.h[1];
@@ -604,13 +581,13 @@ static int decode_to_rgb_device(b200_decoder* d, int cols, int rows, const uint8
     case B200_CHROMA_INTERLEAVED_RRGGBBAA_BE: case B200_CHROMA_INTERLEAVED_RRGGBBAA_LE: bpp = 8; break;
     default: return set_error(B200_E_UNSUPPORTED, "the fused entry points need an interleaved target");
   }
-  // Chunked grids: the colour conversion (and the copy to a page-locked destination) of a band of tile rows is queued right
-  // behind the band's SAO, while the entropy kernel still decodes the bands below.  Band-wise conversion equals the
+  // Large grids into page-locked memory: after the entropy kernel the tile rows are reconstructed, filtered and converted in
+  // bands, and the copy of band c to the host overlaps the kernels of band c + 1.  Band-wise conversion equals the
   // whole-picture one for the reference's default planner choice (nearest-neighbour chroma, per-sample arithmetic) without
   // rotate / mirror / crop; every other request converts the finished canvas in one go, below.
   bool banded = false; int hook_rc = B200_OK;
   *bands_copied = false;
-  if (!geom && opt->chroma_upsampling == 0) {
+  if (!geom && opt->chroma_upsampling == 0 && direct_out) {
     d->chunk_hook = [&, slot, bpp](int c, cudaStream_t side) -> int {
       const b200_image_info& I = d->info;
       const int th = I.tile_height, y0 = std::min(I.height, (d->chunk_pic[c] / d->grid_cols) * th);

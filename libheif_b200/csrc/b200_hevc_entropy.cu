@@ -41,7 +41,10 @@ static_assert(b200::syn::CTX_COUNT == 135, "s_kInitI above is sized for 135 cont
 
 namespace b200 {
 
-constexpr int EWARPS = 4;
+#ifndef B200_ENTROPY_WARPS
+#define B200_ENTROPY_WARPS 4
+#endif
+constexpr int EWARPS = B200_ENTROPY_WARPS;
 
 // Polling load: relaxed + gpu scope (served by L2).  ld.acquire would make ptxas emit CCTL.IVALL -- an SM-wide L1 invalidation --
 // on EVERY poll (measured: 43 % of all stall samples of the first version); ordering is obtained instead by reading every
@@ -57,8 +60,7 @@ struct DevSync {
   unsigned* progress;      // per CTB row of this picture
   unsigned* sub_done;      // per sub-stream of this picture
   unsigned* error_flag;
-  unsigned* queue; unsigned* qctl; unsigned* deps;                // ready queues (see the kernel)
-  const syn::Substream* all_subs; const unsigned* chunk_first;    // batch-wide sub-stream table; first sub-stream of every chunk (shared memory)
+  unsigned* queue; unsigned* qtail; unsigned* deps;               // batch-wide ready queue (see the kernel)
   uint32_t dense_tu, dense_coef, dense_tu_cap, dense_coef_cap;   // unused on the device (fixed slots)
   uint64_t end_bit_position;
   // Waits inside a sub-stream are short (the row above runs two CTBs ahead): poll with a sub-microsecond back-off.  Gives
@@ -85,11 +87,7 @@ struct DevSync {
   __device__ void notify(int target) {
     if (target < 0) return;
     __threadfence();                                     // what the target will read (contexts, end state) is published first
-    if (atomicSub(deps + target, 1u) == 1u) {
-      const unsigned c = B200_LD_SHARED(&all_subs[target].chunk);
-      const unsigned s = atomicAdd(qctl + 2 * c + 1, 1u);
-      e_st_release(queue + chunk_first[c] + s, (unsigned)target + 1u);
-    }
+    if (atomicSub(deps + target, 1u) == 1u) { const unsigned s = atomicAdd(qtail, 1u); e_st_release(queue + s, (unsigned)target + 1u); }
   }
 };
 
@@ -110,45 +108,24 @@ __global__ void __launch_bounds__(EWARPS * 32, B200_ENTROPY_MIN_BLOCKS) hevc_ent
   for (int i = threadIdx.x; i < 768; i += blockDim.x) (&syn::s_kSbInv[0][0][0])[i] = (&syn::d_kSbInv[0][0][0])[i];
   for (int i = threadIdx.x; i < 4; i += blockDim.x) syn::s_kChromaTab[i] = syn::d_kChromaTab[i];
   for (int i = threadIdx.x; i < 4 * 3 * 64; i += blockDim.x) { (&syn::s_kScanX[0][0][0])[i] = (&syn::d_kScanX[0][0][0])[i]; (&syn::s_kScanY[0][0][0])[i] = (&syn::d_kScanY[0][0][0])[i]; }
-  __shared__ unsigned s_first[MAX_CHUNKS + 1];
-  if (threadIdx.x <= (unsigned)b.nchunks) s_first[threadIdx.x] = b.chunk_first[threadIdx.x];
   __syncthreads();
   // Lane 0 of every warp decodes: CABAC is serial per sub-stream.  (Several decoders per warp on diverged lanes were
   // measured 25-70 % slower: the diverged paths of one warp serialise.)
   if ((threadIdx.x & 31) != 0) return;
   const int slot_w = threadIdx.x >> 5;
   const syn::CtxPtr ctx = (syn::CtxPtr)__cvta_generic_to_shared(s_ctx[slot_w]);
-  const int nch = b.nchunks;
-  unsigned idle_ns = 500, idle_spins = 0;
   for (;;) {
-    // pop from the first chunk that has a ready sub-stream nobody took yet
-    int c = 0; unsigned slot = 0; bool found = false, all_claimed = true;
-    for (c = 0; c < nch; c++) {
-      const unsigned n_c = s_first[c + 1] - s_first[c];
-      if (e_ld_acquire(b.qctl + 2 * c) >= n_c) continue;               // every sub-stream of this chunk has been taken
-      all_claimed = false;
-      if (e_ld_acquire(b.qctl + 2 * c) < e_ld_acquire(b.qctl + 2 * c + 1)) {
-        slot = atomicAdd(b.qctl + 2 * c, 1u);
-        if (slot < n_c) { found = true; break; }
-      }
-    }
-    if (!found) {
-      if (all_claimed) break;
-      __nanosleep(idle_ns); if (idle_ns < 8000) idle_ns <<= 1;
-      if ((++idle_spins & 63u) == 0 && e_ld_acquire(b.error_flag)) return;   // a producer failed: its dependants never become ready
-      if (idle_spins > (1u << 23)) { atomicExch(b.error_flag, 3u); return; }
-      continue;
-    }
-    idle_ns = 500; idle_spins = 0;
-    // (another warp may have raced us past the push cursor: then the slot is filled a little later)
-    unsigned item = e_ld_acquire(b.queue + s_first[c] + slot);
+    const unsigned slot = atomicAdd(b.qhead, 1u);
+    if (slot >= (unsigned)b.nsubs) break;
+    // the slot is filled when the sub-stream becomes ready (already, for those without prerequisites)
+    unsigned item = e_ld_acquire(b.queue + slot);
     if (!item) {
       unsigned ns = 500, spins = 0;
       for (;;) {
         __nanosleep(ns); if (ns < 16000) ns <<= 1;
-        if ((item = e_ld_acquire(b.queue + s_first[c] + slot)) != 0u) break;
+        if ((item = e_ld_acquire(b.queue + slot)) != 0u) break;
         if ((++spins & 31u) != 0) continue;
-        if (e_ld_acquire(b.error_flag)) return;
+        if (e_ld_acquire(b.error_flag)) return;          // a producer failed: its dependants never become ready
         if (spins > (1u << 22)) { atomicExch(b.error_flag, 3u); return; }
       }
     }
@@ -156,25 +133,10 @@ __global__ void __launch_bounds__(EWARPS * 32, B200_ENTROPY_MIN_BLOCKS) hevc_ent
     const EntropyPic& ep = b.pics[gs.pic];
     DevSync sync;
     sync.progress = b.progress + ep.progress_base; sync.sub_done = b.sub_done + ep.sub_base; sync.error_flag = b.error_flag;
-    sync.queue = b.queue; sync.qctl = b.qctl; sync.deps = b.deps; sync.all_subs = b.subs; sync.chunk_first = s_first;
+    sync.queue = b.queue; sync.qtail = b.qtail; sync.deps = b.deps;
     sync.dense_tu = sync.dense_coef = sync.dense_tu_cap = sync.dense_coef_cap = 0; sync.end_bit_position = 0;
     syn::run_substream<Cfg>(s_dec[slot_w], ep.sp, ep.pb, b.subs + ep.sub_base, (int)(item - 1u - ep.sub_base), ctx, sync);
-    // chunk completion: everything this sub-stream wrote is published before its count; the last one raises the flag
-    __threadfence();
-    if (atomicAdd(b.chunk_done + c, 1u) + 1u == s_first[c + 1] - s_first[c]) { __threadfence(); e_st_release(b.chunk_done + MAX_CHUNKS + c, 1u); }
   }
-}
-
-// One thread that returns when *flag becomes non-zero (or the batch has failed): orders the kernels queued behind it on
-// its stream after an event that happens INSIDE a running kernel (a chunk of K0 is complete).
-__global__ void wait_flag_kernel(const unsigned* flag, unsigned* error_flag) {
-  unsigned ns = 1000, spins = 0;
-  while (!e_ld_acquire(flag)) {
-    __nanosleep(ns); if (ns < 16000) ns <<= 1;
-    if ((++spins & 31u) == 0 && e_ld_acquire(error_flag)) return;
-    if (spins > (1u << 22)) { atomicExch(error_flag, 3u); return; }
-  }
-  __threadfence();
 }
 
 // sums the per-CTB TU / coefficient counts (statistics only: command-stream bytes actually produced)
@@ -205,13 +167,6 @@ int launch_entropy(const EntropyBatch& b, cudaStream_t s) {
   kern<<<grid, EWARPS * 32, 0, s>>>(b);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return set_error(B200_E_CUDA, "entropy launch: %s", cudaGetErrorString(e));
-  return B200_OK;
-}
-
-int launch_wait_flag(const unsigned int* flag, unsigned int* error_flag, cudaStream_t s) {
-  wait_flag_kernel<<<1, 1, 0, s>>>(flag, error_flag);
-  cudaError_t e = cudaGetLastError();
-  if (e != cudaSuccess) return set_error(B200_E_CUDA, "wait launch: %s", cudaGetErrorString(e));
   return B200_OK;
 }
 

@@ -145,7 +145,6 @@ struct Substream {
   int32_t wake_ctb2;             // sub-stream that becomes startable once this one has stored the contexts after its 2nd CTB of a row (9.3.2.2)
   int32_t wake_end;              // sub-stream that continues this one's end state (dependent slice segment)
   uint32_t deps;                 // number of such events this sub-stream waits for before it may start
-  uint32_t chunk;                // priority class of the ready queue: the chunk (group of tile rows) its picture belongs to
 };
 
 struct PicBuffers {              // per-picture arrays (host memory on the host path, HBM on the device path)
@@ -191,6 +190,13 @@ struct Cabac {
     return ((uint32_t)st.d[q] << 8) | st.d[q + 1];
 #endif
   }
+#ifdef B200_SYN_DEVICE
+  // out of line ON PURPOSE: a call inside the refill keeps ptxas from if-converting (predicating) its ~10 instructions into
+  // every bin -- they are needed once per 16 consumed bits (measured: 12 % of K0's issue slots, profiles/README.md)
+  static __device__ __noinline__ uint32_t fetch16_cold(const uint8_t* d, uint32_t q) { return __byte_perm((uint32_t)__ldg(reinterpret_cast<const unsigned short*>(d + q)), 0, 0x4401); }
+#else
+  static inline uint32_t fetch16_cold(const uint8_t* d, uint32_t q) { return ((uint32_t)d[q] << 8) | d[q + 1]; }
+#endif
   B200_HD inline void start(const CabacStream& st, uint32_t start_byte) {
     // initial window: the 9 bits of 9.3.2.5 + look-ahead up to the next even byte offset (2 or 3 bytes), so that every
     // later refill is one aligned 16-bit load
@@ -208,7 +214,7 @@ struct Cabac {
   // (inline: a call here costs a convergence barrier and argument set-up at every one of the ~15 sites it is inlined into)
   B200_HD inline void shift(int n, const CabacStream& st) {
     val <<= n; bits -= n;
-    if (bits < 0) { val |= next16 << (-bits); bits += 16; pos += 2; next16 = fetch16(st, pos); }
+    if (bits < 0) { val |= next16 << (-bits); bits += 16; pos += 2; next16 = fetch16_cold(st.d, pos < st.size - 2 ? pos : st.size - 2); }
   }
   // One context-coded bin with the context's entry `e` already in registers; `ne` returns the entry written back (the
   // caller forwards it when the next bin uses the same context and was fetched before this store).

@@ -22,7 +22,7 @@ class ImageInfo(C.Structure):
 class DecodeStats(C.Structure):
     _fields_ = [(n, C.c_double) for n in ("parse_ms", "pack_ms", "h2d_ms", "gpu_ms", "total_ms", "entropy_ms", "recon_ms", "deblock_ms", "sao_ms")] + \
                [(n, C.c_uint64) for n in ("bitstream_bytes", "command_bytes", "coefficient_entries", "transform_units", "ctus", "h2d_bytes", "pixels")] + \
-               [("kernel_launches", C.c_int), ("front_end", C.c_int)]
+               [("kernel_launches", C.c_int), ("front_end", C.c_int), ("bands", C.c_int)]
 
 
 def _bind(l):

@@ -148,10 +148,9 @@ def test_batch_of_heterogeneous_pictures(dec):
 
 @pytest.mark.parametrize("tiles_per_chunk", [3, 6, 7])
 def test_chunked_pipeline_equals_back_to_back(cuda, tiles_per_chunk, monkeypatch):
-    """Grids larger than one wave of sub-streams are decoded in chunks of tile rows: K0 finishes them in priority order and
-    K1 / K3 / K4 / K6 / D2H of chunk c run while K0 decodes chunk c + 1.  Forced here on a small 3 x 5 grid of different
-    pictures (B200_CHUNKS=1): planes == per-tile oracle, RGB (page-locked and pageable destination, asynchronous form,
-    cropped canvas) == the back-to-back pipeline."""
+    """Large grids headed for page-locked host memory go through K1 / K3 / K4 / K6 in bands of tile rows, the D2H of a band
+    overlapping the kernels of the next.  Forced here on a small 3 x 5 grid of different pictures (B200_CHUNKS=1): planes ==
+    per-tile oracle, RGB (page-locked and pageable destination, asynchronous form, cropped canvas) == the one-launch pipeline."""
     import torch
     from util import oracle_postprocess
     cols, rows, tw, th = 3, 5, 128, 64
