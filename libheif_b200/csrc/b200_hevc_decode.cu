@@ -171,7 +171,11 @@ static int run_device_pipeline(b200_decoder* d, int n, cudaStream_t s, int* laun
   int rc;
   int launches = 0;
   const bool devfe = d->used_device_front_end;
-  const bool chunked = d->nchunks > 1;
+  // bands only pay for the caller that takes them one by one (the synchronous fused entry point); everything else -- the
+  // composition API, b200_decoder_rerun_device, the asynchronous entry point whose D2H already overlaps the next picture --
+  // runs one launch per kernel (the band-major row list is a valid ticket order for that, too)
+  const char* force = getenv("B200_CHUNKS");
+  const bool chunked = d->nchunks > 1 && (d->chunk_hook || (force && atoi(force) != 0));
   bool overlap = devfe && !chunked && use_overlap(d->n_subs);
   if (overlap) overlap = overlap_acquire(d);
   struct Release { bool armed; ~Release() { if (armed) overlap_release(); } } release{overlap};   // error paths
@@ -358,13 +362,15 @@ int b200_decoder_decode_grid(b200_decoder* d, int cols, int rows, const uint8_t*
   // Launch order of the CTB rows: row-major ACROSS pictures (all first rows, then all second rows, ...).  A row's
   // predecessor always holds a smaller ticket (deadlock freedom), and the resident warps spread over every tile's
   // wavefront instead of idling behind one tile's 2-CTB stagger.
-  // Chunks: bands of whole tile rows (about 64 tiles each) for callers that take the result band by band (the fused host
+  // Chunks: bands of whole tile rows for callers that take the result band by band (the fused host
   // entry points: D2H of band c overlaps the kernels of band c + 1), when the batch is larger than what K0 and K1 overlap
   // CTB by CTB (use_overlap).  One chunk = the classic back-to-back pipeline.
   { int nch = 1, rpc = rows;
     const char* ce = getenv("B200_CHUNKS");
     if (rows >= 2 && (ce ? atoi(ce) != 0 : (d->chunk_hook && (!devfe || !use_overlap(n_subs))))) {      // B200_CHUNKS=0 / 1: never / always (tests, diagnostics)
-      int target = 64; if (const char* e = getenv("B200_CHUNK_TILES")) { const int v = atoi(e); if (v > 0) target = v; }
+      // two bands by default: every K1 launch costs one tile's wavefront latency (~5 ms for 1024x1024), so more bands lose
+      // more than their finer D2H overlap gains (measured: 2 / 4 / 8 / 16 bands, profiles/README.md)
+      int target = (n + 1) / 2; if (const char* e = getenv("B200_CHUNK_TILES")) { const int v = atoi(e); if (v > 0) target = v; }
       rpc = std::max(1, (target + cols / 2) / cols);
       nch = (rows + rpc - 1) / rpc;
       if (nch > MAX_CHUNKS) { rpc = (rows + MAX_CHUNKS - 1) / MAX_CHUNKS; nch = (rows + rpc - 1) / rpc; }
@@ -562,7 +568,7 @@ int b200_decoder_debug_read_tile(b200_decoder* d, int index, int stage, void* y,
 // Common part of the fused entry points: decode -> colour conversion into one of the two device RGB buffers.
 static int decode_to_rgb_device(b200_decoder* d, int cols, int rows, const uint8_t* const* au, const size_t* au_size, uint64_t max_pixels, int canvas_w,
                                 int canvas_h, const b200_geometry* geom, const b200_color_options* opt, b200_image_info* info, int slot, size_t* rowb_out,
-                                size_t* pitch_out, int* out_h, void* direct_out, size_t direct_stride, bool* bands_copied) {
+                                size_t* pitch_out, int* out_h, void* direct_out, size_t direct_stride, bool* bands_copied, bool allow_bands) {
   if (!d->own) {
     B200_CUDA_CHECK(cudaStreamCreateWithFlags(&d->own, cudaStreamNonBlocking));
     B200_CUDA_CHECK(cudaStreamCreateWithFlags(&d->copy, cudaStreamNonBlocking));
@@ -587,7 +593,7 @@ static int decode_to_rgb_device(b200_decoder* d, int cols, int rows, const uint8
   // rotate / mirror / crop; every other request converts the finished canvas in one go, below.
   bool banded = false; int hook_rc = B200_OK;
   *bands_copied = false;
-  if (!geom && opt->chroma_upsampling == 0 && direct_out) {
+  if (!geom && opt->chroma_upsampling == 0 && direct_out && allow_bands) {
     d->chunk_hook = [&, slot, bpp](int c, cudaStream_t side) -> int {
       const b200_image_info& I = d->info;
       const int th = I.tile_height, y0 = std::min(I.height, (d->chunk_pic[c] / d->grid_cols) * th);
@@ -654,7 +660,7 @@ int b200_decode_grid_to_rgb_host(b200_decoder* d, int cols, int rows, const uint
   if (!d || !opt || !out) return set_error(B200_E_INVALID, "null argument");
   size_t rowb = 0, pitch = 0; int oh = 0; bool copied = false;
   const bool pinned = is_page_locked(out);
-  int rc = decode_to_rgb_device(d, cols, rows, au, au_size, max_pixels, canvas_w, canvas_h, geom, opt, info, 0, &rowb, &pitch, &oh, pinned ? out : nullptr, out_stride, &copied);
+  int rc = decode_to_rgb_device(d, cols, rows, au, au_size, max_pixels, canvas_w, canvas_h, geom, opt, info, 0, &rowb, &pitch, &oh, pinned ? out : nullptr, out_stride, &copied, true);
   if (rc) return rc;
   cudaStream_t s = d->own;
   uint8_t* rgb = d->rgb2[0].d;
@@ -711,7 +717,7 @@ int b200_decode_grid_to_rgb_host_async(b200_decoder* d, int cols, int rows, cons
   const int slot = d->async_slot; d->async_slot ^= 1;
   if (d->err_host && d->err_host[slot]) d->async_error = true;                 // the step that used this slot two calls ago failed
   size_t rowb = 0, pitch = 0; int oh = 0; bool copied = false;
-  int rc = decode_to_rgb_device(d, cols, rows, au, au_size, max_pixels, canvas_w, canvas_h, geom, opt, info, slot, &rowb, &pitch, &oh, out, out_stride, &copied);
+  int rc = decode_to_rgb_device(d, cols, rows, au, au_size, max_pixels, canvas_w, canvas_h, geom, opt, info, slot, &rowb, &pitch, &oh, out, out_stride, &copied, getenv("B200_CHUNKS") && atoi(getenv("B200_CHUNKS")) != 0);
   if (rc) return rc;
   if (!copied) {
     B200_CUDA_CHECK(cudaStreamWaitEvent(d->copy, d->ev_k6[slot], 0));

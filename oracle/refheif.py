@@ -147,9 +147,15 @@ def encode_file(path, images, columns=1, rows=1, quality=60, params=None):
     h.heif_context_free(ctx)
 
 
+last_timing = {}
+
+
 def decode_file(path, chroma=CHROMA_INTERLEAVED_RGB, decoder_id=None, threads=None):
-    """heif_decode_image(primary image) -> (uint8 array [H, W*channels])."""
+    """heif_decode_image(primary image) -> (uint8 array [H, W*channels]).  last_timing["api_s"]: seconds spent in the libheif
+    calls that produce the picture (heif_context_read_from_file .. heif_decode_image), without this wrapper's copy into numpy."""
+    import time
     h = load()
+    t0 = time.perf_counter()
     ctx = h.heif_context_alloc()
     check(h.heif_context_read_from_file(ctx, path.encode(), None), "read")
     if threads is not None:
@@ -165,6 +171,7 @@ def decode_file(path, chroma=CHROMA_INTERLEAVED_RGB, decoder_id=None, threads=No
         check(h.heif_decode_image(hd, C.byref(img), COLORSPACE_RGB, chroma, opts), "decode_image")
     finally:
         h.heif_decoding_options_free(opts)
+    last_timing["api_s"] = time.perf_counter() - t0
     st = C.c_int()
     p = h.heif_image_get_plane_readonly(img, CHANNEL_INTERLEAVED, C.byref(st))
     w, hh = h.heif_image_get_width(img, CHANNEL_INTERLEAVED), h.heif_image_get_height(img, CHANNEL_INTERLEAVED)
