@@ -304,6 +304,7 @@ def main():
             e2e_step()
         barrier()
         e2e_ms = max_over_ranks((time.perf_counter() - t0) * 1e3) / args.steps
+        stats_e2e = dec.stats() if nrows else None
         # ---- leg C: the same through the throughput form of the call (b200_decode_grid_to_rgb_host_async + b200_decoder_wait):
         # the D2H of step i overlaps the kernels of step i + 1; every step still parses, uploads, decodes and delivers its RGB
         barrier()
@@ -315,7 +316,6 @@ def main():
             dec.wait()
         barrier()
         pipe_ms = max_over_ranks((time.perf_counter() - t0) * 1e3) / args.steps
-    stats_e2e = dec.stats() if nrows else None
     # ---- per-kernel device times (outside the timed regions): average over a few launches, CUDA events
     kern = {"entropy": 0.0, "recon": 0.0, "deblock": 0.0, "sao_paste": 0.0, "k6_colour": 0.0}
     nk = 5

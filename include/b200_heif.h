@@ -163,6 +163,10 @@ typedef struct b200_hevc_enc_params {
   int pcm;                           /* 0 = off; 1 = pcm_enabled_flag, some 2Nx2N coding units coded as PCM at the full bit depth; 2 = PCM bit depths
                                         reduced by 1 (luma) / 2 (chroma) and pcm_loop_filter_disabled_flag = 1 */
   int transquant_bypass;             /* 0 = off; 1 = transquant_bypass_enabled_flag, some coding units lossless; 2 = every coding unit lossless */
+  int tile_cols, tile_rows;          /* > 1 in either: tiles_enabled_flag (6.5.1); not together with wpp */
+  int tiles_uniform;                 /* 1 = uniform_spacing_flag, 0 = column widths / row heights drawn by the LCG and coded explicitly */
+  int loop_filter_across_tiles;      /* loop_filter_across_tiles_enabled_flag */
+  int slice_per_tile;                /* 1 = every tile is a slice of its own, 0 = one slice holds all tiles (one entry point per tile) */
 } b200_hevc_enc_params;
 
 void b200_hevc_enc_params_default(b200_hevc_enc_params* p);

@@ -177,6 +177,8 @@ static int run_device_pipeline(b200_decoder* d, int n, cudaStream_t s, int* laun
   const char* force = getenv("B200_CHUNKS");
   const bool chunked = d->nchunks > 1 && (d->chunk_hook || (force && atoi(force) != 0));
   bool overlap = devfe && !chunked && use_overlap(d->n_subs);
+  // K1 follows K0 through per-row progress counters in raster order; sub-streams of HEVC tiles produce CTBs tile by tile
+  for (int i = 0; i < d->npics && overlap; i++) if (d->epics.h[i].sp.tiles) overlap = false;
   if (overlap) overlap = overlap_acquire(d);
   struct Release { bool armed; ~Release() { if (armed) overlap_release(); } } release{overlap};   // error paths
   d->last_overlapped = overlap; d->last_chunked = chunked;

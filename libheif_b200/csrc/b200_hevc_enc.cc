@@ -216,6 +216,20 @@ class Encoder {
         }
       }
     }
+    {
+      const int tc = std::max(1, std::min(p.tile_cols, wctb)), tr = std::max(1, std::min(p.tile_rows, hctb));
+      tiles = (tc > 1 || tr > 1) && !p.wpp;
+      if (tiles) {
+        auto bounds = [&](int n, int size) {
+          std::vector<int> b(1, 0);
+          if (p.tiles_uniform) for (int i = 1; i <= n; i++) b.push_back((i * size) / n);               // 6.5.1 (6-3)
+          else { std::vector<int> cuts; while ((int)cuts.size() < n - 1) { int c = 1 + (int)rng.range(size - 1); if (std::find(cuts.begin(), cuts.end(), c) == cuts.end()) cuts.push_back(c); }
+                 std::sort(cuts.begin(), cuts.end()); for (int c : cuts) b.push_back(c); b.push_back(size); }
+          return b;
+        };
+        col_bd = bounds(tc, wctb); row_bd = bounds(tr, hctb);
+      }
+    }
     pcm_bd_y = p.pcm == 2 ? bd - 1 : bd; pcm_bd_c = p.pcm == 2 ? bd - 2 : bd;
     sl_on = p.scaling_lists != 0;
     if (sl_on) sl::derive(sl_lists, sl_f);
@@ -224,7 +238,25 @@ class Encoder {
   void encode(std::vector<uint8_t>& out) {
     write_vps(out); write_sps(out); write_pps(out);
     int rows_per_slice = P.slice_ctb_rows > 0 ? P.slice_ctb_rows : hctb;
-    slice_idx = 0;
+    slice_idx = 0; region_idx = 0;
+    ctb_region.assign((size_t)wctb * hctb, -1);
+    if (tiles) {
+      // CTBs in tile scan (6.5.1): tile after tile in raster order of the tiles, raster inside each tile
+      std::vector<int> order, tile_start;
+      for (size_t tr = 0; tr + 1 < row_bd.size(); tr++) for (size_t tc = 0; tc + 1 < col_bd.size(); tc++) {
+        tile_start.push_back((int)order.size());
+        for (int y = row_bd[tr]; y < row_bd[tr + 1]; y++) for (int x = col_bd[tc]; x < col_bd[tc + 1]; x++) order.push_back(y * wctb + x);
+      }
+      tile_start.push_back((int)order.size());
+      if (P.slice_per_tile) {
+        for (size_t t = 0; t + 1 < tile_start.size(); t++) {
+          std::vector<int> o(order.begin() + tile_start[t], order.begin() + tile_start[t + 1]);
+          encode_slice_segment_list(out, o, {0, (int)o.size()}, false, o[0]);
+          slice_idx++;
+        }
+      } else encode_slice_segment_list(out, order, tile_start, false, 0);
+      return;
+    }
     for (int r0 = 0; r0 < hctb; r0 += rows_per_slice) {
       int r1 = std::min(hctb, r0 + rows_per_slice);
       if (P.dependent_slice_segments && P.wpp == 0 && r1 - r0 > 1) {
@@ -247,6 +279,9 @@ class Encoder {
   Cabac cabac; Ctx ctx[CTX_COUNT], ctx_wpp[CTX_COUNT];
   std::vector<SaoParams> sao;
   int slice_idx = 0, slice_addr_rs = 0, slice_qp = 26;
+  int region_idx = 0;                                  // counts (slice, tile) regions: availability = same region
+  bool tiles = false; std::vector<int> col_bd, row_bd;   // tile column / row boundaries in CTBs (6.5.1)
+  std::vector<int> ctb_region;                         // region of every coded CTB (SAO merge candidates)
   int is_qp_delta_coded = 0, cu_qp_delta_val = 0, qpy_prev_qg = 0, last_cu_qpy = 0, first_qg = 1, cur_qpy = 0, qg_target_qp = 0;
   int cu_x0 = 0, cu_y0 = 0;
   sl::Lists sl_lists; sl::Factors sl_f; uint8_t sl_kind[4][6] = {}; bool sl_on = false;
@@ -272,8 +307,8 @@ class Encoder {
   int stride_of(int c) const { return c ? Wc : W; }
   bool avail(int x, int y) const {
     if (x < 0 || y < 0 || x >= W || y >= H) return false;
-    unsigned s = slice_of4[(size_t)(y >> 2) * w4 + (x >> 2)];
-    return s != 0 && s == (unsigned)(slice_idx + 1);
+    unsigned s = slice_of4[(size_t)(y >> 2) * w4 + (x >> 2)];      // 1 + region (slice x tile) of a decoded block: 6.4.1 wants same slice AND same tile
+    return s != 0 && s == (unsigned)(region_idx + 1);
   }
 
   // ---------------------------------------------------------------------------- parameter sets
@@ -374,8 +409,17 @@ class Encoder {
     b.put(P.slice_chroma_qp_offsets ? 1 : 0, 1);
     b.put(0, 1); b.put(0, 1);
     b.put(P.transquant_bypass ? 1 : 0, 1);   // transquant_bypass_enabled
-    b.put(0, 1);                      // tiles
+    b.put(tiles ? 1 : 0, 1);          // tiles_enabled_flag
     b.put(P.wpp ? 1 : 0, 1);
+    if (tiles) {
+      b.ue((unsigned)col_bd.size() - 2); b.ue((unsigned)row_bd.size() - 2);
+      b.put(P.tiles_uniform ? 1 : 0, 1);
+      if (!P.tiles_uniform) {
+        for (size_t i = 0; i + 2 < col_bd.size(); i++) b.ue((unsigned)(col_bd[i + 1] - col_bd[i] - 1));
+        for (size_t i = 0; i + 2 < row_bd.size(); i++) b.ue((unsigned)(row_bd[i + 1] - row_bd[i] - 1));
+      }
+      b.put(P.loop_filter_across_tiles ? 1 : 0, 1);
+    }
     b.put(P.loop_filter_across_slices ? 1 : 0, 1);
     b.put(1, 1);                      // deblocking_filter_control_present
     b.put(1, 1);                      // deblocking_filter_override_enabled
@@ -393,29 +437,44 @@ class Encoder {
 
   // ---------------------------------------------------------------------------- slice segment
   void encode_slice_segment(std::vector<uint8_t>& out, int addr0, int addr1, bool dependent, int slice_addr) {
+    std::vector<int> order; for (int a = addr0; a < addr1; a++) order.push_back(a);
+    encode_slice_segment_list(out, order, {0, (int)order.size()}, dependent, slice_addr);
+  }
+  // order: raster addresses of the segment's CTBs in coding order; starts: indices into `order` where a tile begins (+ the end)
+  void encode_slice_segment_list(std::vector<uint8_t>& out, const std::vector<int>& order, const std::vector<int>& starts, bool dependent, int slice_addr) {
     slice_addr_rs = slice_addr;
+    const int addr0 = order.front();
     int total = wctb * hctb;
     if (!dependent) {
       slice_qp = clip3(0, 51, P.qp + (slice_idx ? (int)(rng.range(5)) - 2 : 0));
       init_contexts(ctx, slice_qp);
       last_cu_qpy = slice_qp; first_qg = 1;
+      region_idx++;
     }
     if (sao.empty()) sao.resize((size_t)total);
-    // slice data: one CABAC sub-stream per CTB row when WPP is on
+    // slice data: one CABAC sub-stream per CTB row when WPP is on, one per tile when tiles are on
     std::vector<std::vector<uint8_t>> substreams;
     cabac.reset();
-    for (int a = addr0; a < addr1; a++) {
+    size_t next_start = 1;
+    for (size_t k = 0; k < order.size(); k++) {
+      const int a = order[k];
       int rx = a % wctb, ry = a / wctb;
+      if (tiles && next_start + 1 < starts.size() && (int)k == starts[next_start]) {      // first CTB of the next tile: 9.3.1 initialisation
+        next_start++;
+        init_contexts(ctx, slice_qp); first_qg = 1; region_idx++;
+      }
       if (P.wpp && rx == 0 && a != addr0) {
         if (avail((rx + 1) << log2ctb, (ry - 1) << log2ctb)) memcpy(ctx, ctx_wpp, sizeof ctx); else init_contexts(ctx, slice_qp);
         first_qg = 1;
       }
+      ctb_region[(size_t)a] = region_idx;
       if (P.sao) { choose_sao(rx, ry); write_sao(rx, ry); }
       coding_quadtree(rx << log2ctb, ry << log2ctb, log2ctb, 0);
       if (P.wpp && rx == 1) memcpy(ctx_wpp, ctx, sizeof ctx);
-      bool end = a + 1 == addr1;
+      bool end = k + 1 == order.size();
       cabac.terminate(end ? 1 : 0);                        // end_of_slice_segment_flag
-      if (!end && P.wpp && (a + 1) % wctb == 0) {
+      const bool tile_end = tiles && next_start < starts.size() && (int)k + 1 == starts[next_start];
+      if (!end && ((P.wpp && (a + 1) % wctb == 0) || tile_end)) {
         cabac.terminate(1);                                // end_of_subset_one_bit (+ byte_alignment)
         substreams.push_back(cabac.bw.buf); cabac.reset();
       }
@@ -447,7 +506,7 @@ class Encoder {
       }
       if (P.loop_filter_across_slices && (P.sao || !dis)) b.put(P.slice_loop_filter_across_slices ? 1 : 0, 1);
     }
-    if (P.wpp) {
+    if (P.wpp || tiles) {
       int ne = (int)substreams.size() - 1;
       b.ue(ne);
       if (ne > 0) { b.ue(31); for (int i = 0; i < ne; i++) b.put((unsigned)(escaped_size(substreams[i]) - 1), 32); }
@@ -463,7 +522,7 @@ class Encoder {
     int addr = ry * wctb + rx;
     SaoParams& s = sao[addr];
     memset(&s, 0, sizeof s);
-    bool left_ok = rx > 0 && addr - 1 >= slice_addr_rs, up_ok = ry > 0 && addr - wctb >= slice_addr_rs;
+    bool left_ok = rx > 0 && ctb_region[(size_t)addr - 1] == region_idx, up_ok = ry > 0 && ctb_region[(size_t)(addr - wctb)] == region_idx;
     int r = rng.range(16);
     if (left_ok && r < 3) { s = sao[addr - 1]; s.merge_left = 1; s.merge_up = 0; return; }
     if (up_ok && r < 6) { s = sao[addr - wctb]; s.merge_up = 1; s.merge_left = 0; return; }
@@ -483,9 +542,9 @@ class Encoder {
   void write_sao(int rx, int ry) {
     int addr = ry * wctb + rx;
     const SaoParams& s = sao[addr];
-    if (rx > 0 && addr - 1 >= slice_addr_rs) cabac.bin(ctx[CTX_SAO_MERGE], s.merge_left);
+    if (rx > 0 && ctb_region[(size_t)addr - 1] == region_idx) cabac.bin(ctx[CTX_SAO_MERGE], s.merge_left);
     if (s.merge_left) return;
-    if (ry > 0 && addr - wctb >= slice_addr_rs) cabac.bin(ctx[CTX_SAO_MERGE], s.merge_up);
+    if (ry > 0 && ctb_region[(size_t)(addr - wctb)] == region_idx) cabac.bin(ctx[CTX_SAO_MERGE], s.merge_up);
     if (s.merge_up) return;
     int cmax = (1 << (std::min(bd, 10) - 5)) - 1;
     for (int c = 0; c < (chroma ? 3 : 1); c++) {
@@ -796,7 +855,7 @@ class Encoder {
 
   void mark_tu(int x0, int y0, int log2n) {
     int n4 = 1 << (log2n - 2);
-    for (int y = 0; y < n4; y++) for (int x = 0; x < n4; x++) { size_t i = (size_t)((y0 >> 2) + y) * w4 + (x0 >> 2) + x; slice_of4[i] = (uint16_t)(slice_idx + 1); qp4[i] = (int8_t)cur_qpy; }
+    for (int y = 0; y < n4; y++) for (int x = 0; x < n4; x++) { size_t i = (size_t)((y0 >> 2) + y) * w4 + (x0 >> 2) + x; slice_of4[i] = (uint16_t)(region_idx + 1); qp4[i] = (int8_t)cur_qpy; }
   }
 
   // ---------------------------------------------------------------------------- transform tree (7.3.8.8)
@@ -935,7 +994,7 @@ class Encoder {
         cabac.restart();
         for (int yy = 0; yy < n; yy += 4) for (int xx = 0; xx < n; xx += 4) {
           const size_t idx = (size_t)((y0 + yy) >> 2) * w4 + ((x0 + xx) >> 2);
-          ipm4[idx] = 1; slice_of4[idx] = (uint16_t)(slice_idx + 1); cd4[idx] = (uint8_t)depth;       // a PCM unit counts as INTRA_DC for its neighbours (8.4.2)
+          ipm4[idx] = 1; slice_of4[idx] = (uint16_t)(region_idx + 1); cd4[idx] = (uint8_t)depth;       // a PCM unit counts as INTRA_DC for its neighbours (8.4.2)
         }
         // no transform tree, no cu_qp_delta: QpY = predicted QP (+ the delta already coded in this quantization group, 8.6.1)
         const int pred_qp = P.cu_qp_delta ? predict_qpy(x0, y0) : slice_qp;
@@ -961,7 +1020,7 @@ class Encoder {
       }
       for (int yy = 0; yy < pb; yy += 4) for (int xx = 0; xx < pb; xx += 4) {
         size_t idx = (size_t)((py + yy) >> 2) * w4 + ((px + xx) >> 2);
-        ipm4[idx] = (uint8_t)mode; slice_of4[idx] = (uint16_t)(slice_idx + 1);
+        ipm4[idx] = (uint8_t)mode; slice_of4[idx] = (uint16_t)(region_idx + 1);
       }
     }
     for (int i = 0; i < np; i++) cabac.bin(ctx[CTX_PREV_INTRA], prev[i]);
@@ -1045,6 +1104,7 @@ extern "C" {
 
 void b200_hevc_enc_params_default(b200_hevc_enc_params* p) {
   memset(p, 0, sizeof *p);
+  p->tile_cols = p->tile_rows = 1; p->tiles_uniform = 1; p->loop_filter_across_tiles = 1; p->slice_per_tile = 0;
   p->bit_depth = 8; p->chroma_format_idc = 1; p->log2_ctb_size = 5; p->qp = 27; p->init_qp = 26;
   p->max_transform_hierarchy_depth_intra = 1; p->sao = 1; p->sign_data_hiding = 1; p->cu_qp_delta = 1;
   p->diff_cu_qp_delta_depth = 1; p->dqp_range = 3; p->strong_intra_smoothing = 1; p->loop_filter_across_slices = 1;

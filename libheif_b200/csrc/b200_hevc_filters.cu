@@ -134,8 +134,11 @@ __device__ __noinline__ int sao_sample_generic(const DeviceBatch& b, const PicDe
       const SliceInfo* sls = b.slices + pic.slice_base;
       const int cur = ci.slice_idx;
       const int sa = ctus[(ya >> lg) * pic.wctb + (xa >> lg)].slice_idx, sb = ctus[(yb >> lg) * pic.wctb + (xb >> lg)].slice_idx;
-      if (sa != cur && !(sa < cur ? sls[cur].lf_across_slices : sls[sa].lf_across_slices)) skip = true;
-      if (sb != cur && !(sb < cur ? sls[cur].lf_across_slices : sls[sb].lf_across_slices)) skip = true;
+      // 8.7.3.2: a neighbour in another slice counts only if the later of the two slices filters across its boundary; one in another
+      // tile only with loop_filter_across_tiles_enabled_flag (regions = slice x tile, compared through their slice / tile ids)
+      const SliceInfo c0 = sls[cur];
+      if (sa != cur) { const SliceInfo o = sls[sa]; if ((o.slice_id != c0.slice_id && !(o.slice_id < c0.slice_id ? c0.lf_across_slices : o.lf_across_slices)) || (o.tile_id != c0.tile_id && !c0.lf_across_tiles)) skip = true; }
+      if (sb != cur) { const SliceInfo o = sls[sb]; if ((o.slice_id != c0.slice_id && !(o.slice_id < c0.slice_id ? c0.lf_across_slices : o.lf_across_slices)) || (o.tile_id != c0.tile_id && !c0.lf_across_tiles)) skip = true; }
       if (!skip) {
         const int a = src[(size_t)ya * st + xa], bb = src[(size_t)yb * st + xb];
         const int ei = 2 + (v > a) - (v < a) + (v > bb) - (v < bb);

@@ -43,6 +43,7 @@ struct Pps {
   int beta_offset = 0, tc_offset = 0, slice_ext_present = 0, log2_sao_scale_luma = 0, log2_sao_scale_chroma = 0;
   int sl_present = 0; sl::Lists lists;
   int tq_bypass = 0;
+  int tiles = 0, num_tile_cols = 1, num_tile_rows = 1, uniform_spacing = 1, lf_across_tiles = 1; int col_width[20] = {0}, row_height[22] = {0};
 };
 
 inline int clip3(int lo, int hi, int v) { return v < lo ? lo : (v > hi ? hi : v); }
@@ -96,6 +97,8 @@ class HeaderParser {
   bool started = false;
   std::vector<uint32_t> epb;
   int slice_idx = -1, slice_addr_rs = 0, slice_qp = 26, sao_luma = 0, sao_chroma = 0, last_seg_sub = -1;
+  SliceInfo cur_slice{}; int n_slices = 0;                 // parameters of the current slice; regions (slice x tile) are made from it
+  std::vector<int> col_bd, row_bd, ts2rs, rs2ts; std::vector<uint16_t> tile_of;   // 6.5.1: tile boundaries (CTBs), CtbAddrTsToRs / RsToTs, TileId by raster address
   int total = 0;
   struct Seg { int addr; int first_sub; int nsubs; };
   std::vector<Seg> segs;
@@ -245,8 +248,20 @@ class HeaderParser {
     if (p.cb_qp_offset < -12 || p.cb_qp_offset > 12 || p.cr_qp_offset < -12 || p.cr_qp_offset > 12) return set_error(B200_E_BITSTREAM, "pps chroma qp offset");
     b.bit(); b.bit();
     p.tq_bypass = b.bit();
-    if (b.bit()) return set_error(B200_E_UNSUPPORTED, "HEVC tiles are not supported");
+    p.tiles = b.bit();
     p.wpp = b.bit();
+    if (p.tiles) {                                                            // 7.3.2.3 / 7.4.3.3
+      if (p.wpp) return set_error(B200_E_UNSUPPORTED, "HEVC tiles together with wavefront parallel processing are not supported");
+      const unsigned nc = b.ue(), nr = b.ue();
+      if (nc > 19 || nr > 21) return set_error(B200_E_BITSTREAM, "number of tile columns / rows");
+      p.num_tile_cols = (int)nc + 1; p.num_tile_rows = (int)nr + 1;
+      p.uniform_spacing = b.bit();
+      if (!p.uniform_spacing) {
+        for (int i = 0; i + 1 < p.num_tile_cols; i++) { const unsigned v = b.ue(); if (v > 4096) return set_error(B200_E_BITSTREAM, "tile column width"); p.col_width[i] = (int)v + 1; }
+        for (int i = 0; i + 1 < p.num_tile_rows; i++) { const unsigned v = b.ue(); if (v > 4096) return set_error(B200_E_BITSTREAM, "tile row height"); p.row_height[i] = (int)v + 1; }
+      }
+      p.lf_across_tiles = b.bit();
+    }
     p.lf_across_slices = b.bit();
     if (b.bit()) { p.deblock_override_enabled = b.bit(); p.deblock_disabled = b.bit(); if (!p.deblock_disabled) { const int be = b.se(), tc = b.se(); if (be < -6 || be > 6 || tc < -6 || tc > 6) return set_error(B200_E_BITSTREAM, "pps deblocking offsets"); p.beta_offset = 2 * be; p.tc_offset = 2 * tc; } }
     p.sl_present = b.bit();
@@ -289,6 +304,21 @@ class HeaderParser {
     }
     total = d.wctb * d.hctb;
     P.ctu_slice.assign((size_t)total, 0xffff);
+    { // 6.5.1: tile boundaries and the conversion between raster and tile scan (identity without tiles)
+      const int ntc = PP->tiles ? PP->num_tile_cols : 1, ntr = PP->tiles ? PP->num_tile_rows : 1;
+      if (ntc > d.wctb || ntr > d.hctb) return set_error(B200_E_BITSTREAM, "more tile columns / rows than CTBs");
+      col_bd.assign(1, 0); row_bd.assign(1, 0);
+      for (int i = 0; i < ntc; i++) { const int w = (!PP->tiles || PP->uniform_spacing) ? ((i + 1) * d.wctb) / ntc - (i * d.wctb) / ntc : (i + 1 < ntc ? PP->col_width[i] : d.wctb - col_bd[(size_t)i]);
+        if (w <= 0 || col_bd[(size_t)i] + w > d.wctb) return set_error(B200_E_BITSTREAM, "tile column widths"); col_bd.push_back(col_bd[(size_t)i] + w); }
+      for (int i = 0; i < ntr; i++) { const int h = (!PP->tiles || PP->uniform_spacing) ? ((i + 1) * d.hctb) / ntr - (i * d.hctb) / ntr : (i + 1 < ntr ? PP->row_height[i] : d.hctb - row_bd[(size_t)i]);
+        if (h <= 0 || row_bd[(size_t)i] + h > d.hctb) return set_error(B200_E_BITSTREAM, "tile row heights"); row_bd.push_back(row_bd[(size_t)i] + h); }
+      if (col_bd.back() != d.wctb || row_bd.back() != d.hctb) return set_error(B200_E_BITSTREAM, "tiles do not cover the picture");
+      ts2rs.assign((size_t)total, 0); rs2ts.assign((size_t)total, 0); tile_of.assign((size_t)total, 0);
+      int ts = 0;
+      for (int tr = 0; tr < ntr; tr++) for (int tc = 0; tc < ntc; tc++)
+        for (int y = row_bd[(size_t)tr]; y < row_bd[(size_t)tr + 1]; y++) for (int x = col_bd[(size_t)tc]; x < col_bd[(size_t)tc + 1]; x++) {
+          const int rs = y * d.wctb + x; ts2rs[(size_t)ts] = rs; rs2ts[(size_t)rs] = ts; tile_of[(size_t)rs] = (uint16_t)(tr * ntc + tc); ts++; }
+    }
     P.colour_primaries = S->vui_colour ? S->vui_cp : 2; P.transfer_characteristics = S->vui_colour ? S->vui_tc : 2;
     P.matrix_coefficients = S->vui_colour ? S->vui_mc : 2; P.full_range = S->vui_signal ? S->vui_full_range : 0;
     started = true;
@@ -304,6 +334,7 @@ class HeaderParser {
     q.sao_enabled = S->sao; q.transform_skip = PP->transform_skip; q.cu_qp_delta = PP->cu_qp_delta; q.qg_log2 = d.log2_ctb - PP->diff_cu_qp_delta_depth;
     q.pcm = S->pcm; q.pcm_shift_y = d.bit_depth - S->pcm_bd_y; q.pcm_shift_c = d.bit_depth - S->pcm_bd_c; q.pcm_bd_y = S->pcm_bd_y; q.pcm_bd_c = S->pcm_bd_c;
     q.log2_min_pcm = S->log2_min_pcm; q.log2_max_pcm = S->log2_max_pcm; q.pcm_lf_disabled = S->pcm_lf_disabled; q.tq_bypass = PP->tq_bypass;
+    q.tiles = PP->tiles;
     q.sign_hiding = PP->sign_hiding; q.wpp = PP->wpp; q.sao_scale_luma = PP->log2_sao_scale_luma; q.sao_scale_chroma = PP->log2_sao_scale_chroma;
     const int ctb = 1 << d.log2_ctb;
     q.tu_slots = (ctb / 4) * (ctb / 4); q.coef_slots = ctb * ctb * (d.chroma ? 3 : 2) / 2;
@@ -331,7 +362,8 @@ class HeaderParser {
     const int wctb = P.desc.wctb;
     int dependent = 0, seg_addr = 0;
     if (!first) { if (p->dependent_slices) dependent = b.bit(); seg_addr = b.bits(ceil_log2((unsigned)total)); if (seg_addr >= total) return set_error(B200_E_BITSTREAM, "slice_segment_address"); }
-    if (!segs.empty() && seg_addr <= segs.back().addr) return set_error(B200_E_BITSTREAM, "slice segments out of order");
+    const int seg_ts = rs2ts[(size_t)seg_addr];                   // segments are consecutive in TILE scan (6.5.1); all bookkeeping below is in that scan
+    if (!segs.empty() && seg_ts <= segs.back().addr) return set_error(B200_E_BITSTREAM, "slice segments out of order");
     if (!dependent) {
       b.bits(p->num_extra_bits);
       if (b.ue() != 2) return set_error(B200_E_UNSUPPORTED, "P/B slices are not supported (intra-only decoder)");
@@ -364,14 +396,14 @@ class HeaderParser {
       int across = p->lf_across_slices;
       if (p->lf_across_slices && (sao_luma || sao_chroma || !dis)) across = b.bit();
       if (P.slices.size() >= 65000) return set_error(B200_E_UNSUPPORTED, "too many slices");
-      SliceInfo si{}; si.cb_qp_offset = (int8_t)clip3(-24, 24, p->cb_qp_offset + cb_off); si.cr_qp_offset = (int8_t)clip3(-24, 24, p->cr_qp_offset + cr_off);
+      SliceInfo& si = cur_slice; si = SliceInfo{}; si.cb_qp_offset = (int8_t)clip3(-24, 24, p->cb_qp_offset + cb_off); si.cr_qp_offset = (int8_t)clip3(-24, 24, p->cr_qp_offset + cr_off);
       si.beta_offset = (int8_t)clip3(-12, 12, beta); si.tc_offset = (int8_t)clip3(-12, 12, tc);
       si.deblocking_disabled = (uint8_t)dis; si.lf_across_slices = (uint8_t)across; si.first_ctb_rs = (uint32_t)seg_addr;
-      P.slices.push_back(si);
-      slice_idx = (int)P.slices.size() - 1; slice_addr_rs = seg_addr;
+      si.slice_id = (uint16_t)n_slices++; si.lf_across_tiles = (uint8_t)p->lf_across_tiles;
+      slice_idx = 0; slice_addr_rs = seg_addr;
     } else if (slice_idx < 0) return set_error(B200_E_BITSTREAM, "dependent slice segment without a slice");
     std::vector<uint32_t> entry;
-    if (p->wpp) { const unsigned ne = b.ue(); if (ne > (unsigned)total) return set_error(B200_E_BITSTREAM, "num_entry_point_offsets"); if (ne > 0) { const unsigned lm1 = b.ue(); if (lm1 > 31) return set_error(B200_E_BITSTREAM, "offset_len_minus1"); const int len = (int)lm1 + 1; for (unsigned i = 0; i < ne; i++) { const uint64_t v = (uint64_t)b.bits(len) + 1; if (v > n) return set_error(B200_E_BITSTREAM, "entry point offset beyond the NAL"); entry.push_back((uint32_t)v); } } }
+    if (p->wpp || p->tiles) { const unsigned ne = b.ue(); if (ne > (unsigned)total) return set_error(B200_E_BITSTREAM, "num_entry_point_offsets"); if (ne > 0) { const unsigned lm1 = b.ue(); if (lm1 > 31) return set_error(B200_E_BITSTREAM, "offset_len_minus1"); const int len = (int)lm1 + 1; for (unsigned i = 0; i < ne; i++) { const uint64_t v = (uint64_t)b.bits(len) + 1; if (v > n) return set_error(B200_E_BITSTREAM, "entry point offset beyond the NAL"); entry.push_back((uint32_t)v); } } }
     if (p->slice_ext_present) { const unsigned len = b.ue(); if (len > 256) return set_error(B200_E_BITSTREAM, "slice_segment_header_extension_length"); for (unsigned i = 0; i < len; i++) b.bits(8); }
     b.bit(); b.pos = (b.pos + 7) & ~(size_t)7;
     if (b.overrun()) return set_error(B200_E_BITSTREAM, "slice segment header is truncated");
@@ -389,9 +421,13 @@ class HeaderParser {
       for (nal_pos = hdr_rbsp; k < epb.size() && epb[k] < nal_pos + 1; k++) nal_pos++;
       hdr_epb = k; }
     const size_t hdr_nal = hdr_rbsp + hdr_epb;
-    Seg sg; sg.addr = seg_addr; sg.first_sub = (int)P.subs.size(); sg.nsubs = 0;
+    Seg sg; sg.addr = seg_ts; sg.first_sub = (int)P.subs.size(); sg.nsubs = 0;
     auto add_sub = [&](uint32_t cb, uint32_t ce, uint32_t byte_begin, bool first_sub) {
       syn::Substream ss{}; ss.pic = 0; ss.byte_begin = base + byte_begin; ss.byte_end = base + data_len; ss.ctb_begin = cb; ss.ctb_end = ce;
+      // region = this slice inside the tile the sub-stream starts in (a sub-stream never leaves its tile)
+      { const uint16_t tid = tile_of[(size_t)ts2rs[(size_t)cb]];
+        if (P.slices.empty() || P.slices.back().slice_id != cur_slice.slice_id || P.slices.back().tile_id != tid) { SliceInfo r = cur_slice; r.tile_id = tid; P.slices.push_back(r); }
+        slice_idx = (int)P.slices.size() - 1; }
       ss.slice_addr_rs = (uint32_t)slice_addr_rs; ss.slice_idx = slice_idx; ss.slice_qp = slice_qp; ss.sao_luma = (uint8_t)sao_luma; ss.sao_chroma = (uint8_t)sao_chroma;
       ss.init_contexts = (uint8_t)(first_sub && !dependent); ss.last_of_segment = 0;
       ss.prev = (first_sub && dependent) ? last_seg_sub : -1;
@@ -414,7 +450,26 @@ class HeaderParser {
         cb = row_end;
         if (cb >= (uint32_t)total) break;
       }
-    } else add_sub((uint32_t)seg_addr, (uint32_t)total, 0, true);
+    } else if (p->tiles) {
+      // one sub-stream per tile the segment touches: sub-stream k + 1 starts at the k-th tile boundary after the segment's start
+      uint32_t nal_off = 0, cb = (uint32_t)seg_ts;
+      for (size_t k = 0; k <= entry.size(); k++) {
+        uint32_t te = cb + 1;
+        while (te < (uint32_t)total && tile_of[(size_t)ts2rs[te]] == tile_of[(size_t)ts2rs[cb]]) te++;       // end of this tile in tile scan
+        size_t abs_nal = hdr_nal + nal_off, cnt = 0;
+        while (cnt < epb.size() && epb[cnt] < abs_nal) cnt++;
+        const uint32_t rb = (uint32_t)(abs_nal - cnt - hdr_rbsp);
+        if (rb > data_len) return set_error(B200_E_BITSTREAM, "entry point beyond the slice segment data");
+        add_sub(cb, te, rb, k == 0);
+        if (k > 0) { syn::Substream& ss = P.subs.back(); ss.init_contexts = 1; ss.prev = -1; }        // 9.3.1: the first CTB of a tile initialises the context variables
+        if (k < entry.size()) nal_off += entry[k];
+        cb = te;
+        if (cb >= (uint32_t)total) break;
+      }
+      // (a segment that begins at a tile's first CTB initialises its contexts there, too -- also a dependent one)
+      { syn::Substream& f = P.subs[(size_t)sg.first_sub]; const int rs0 = ts2rs[(size_t)seg_ts];
+        if (rs0 % wctb == col_bd[(size_t)(tile_of[(size_t)rs0] % (uint16_t)(col_bd.size() - 1))] && (seg_ts == 0 || tile_of[(size_t)ts2rs[(size_t)seg_ts - 1]] != tile_of[(size_t)rs0])) { f.init_contexts = 1; f.prev = -1; } }
+    } else add_sub((uint32_t)seg_ts, (uint32_t)total, 0, true);
     segs.push_back(sg);
     last_seg_sub = (int)P.subs.size() - 1;
     return B200_OK;
@@ -441,13 +496,23 @@ class HeaderParser {
       for (int k = keep; k < sg.nsubs; k++) P.subs[(size_t)sg.first_sub + k].ctb_begin = P.subs[(size_t)sg.first_sub + k].ctb_end = 0;   // unused
       P.subs[(size_t)sg.first_sub + keep - 1].last_of_segment = 1;
       sg.nsubs = keep;
-      for (uint32_t a = (uint32_t)sg.addr; a < seg_end; a++) P.ctu_slice[a] = (uint16_t)P.subs[(size_t)sg.first_sub].slice_idx;
+      for (int k = 0; k < keep; k++) {
+        const syn::Substream& ss = P.subs[(size_t)sg.first_sub + k];
+        for (uint32_t a = ss.ctb_begin; a < ss.ctb_end; a++) P.ctu_slice[(size_t)ts2rs[a]] = (uint16_t)ss.slice_idx;
+      }
     }
     // drop unused sub-streams (entry points past the segment end) while keeping `prev` links valid
     std::vector<int> remap(P.subs.size(), -1); std::vector<syn::Substream> out;
     for (size_t i = 0; i < P.subs.size(); i++) if (P.subs[i].ctb_end > P.subs[i].ctb_begin) { remap[i] = (int)out.size(); out.push_back(P.subs[i]); }
     for (auto& ss : out) if (ss.prev >= 0) { int pr = ss.prev; while (pr >= 0 && remap[(size_t)pr] < 0) pr--; ss.prev = pr >= 0 ? remap[(size_t)pr] : -1; }
     P.subs.swap(out);
+    // tile scan -> what the syntax decoder walks: raster address of the first CTB, CTB count, CTB columns of its tile
+    for (auto& ss : P.subs) {
+      const uint32_t cnt = ss.ctb_end - ss.ctb_begin; const int rs0 = ts2rs[ss.ctb_begin];
+      const int tc = (int)(tile_of[(size_t)rs0] % (uint16_t)(col_bd.size() - 1));
+      ss.tile_x0 = (uint16_t)col_bd[(size_t)tc]; ss.tile_x1 = (uint16_t)col_bd[(size_t)tc + 1];
+      ss.ctb_begin = (uint32_t)rs0; ss.ctb_end = (uint32_t)rs0 + cnt;
+    }
     if (segs.empty() || segs[0].addr != 0) return set_error(B200_E_BITSTREAM, "first slice segment missing");
     for (int a = 0; a < total; a++) if (P.ctu_slice[(size_t)a] == 0xffff) return set_error(B200_E_BITSTREAM, "picture incomplete (missing slice segments)");
     P.desc.nslices = (int)P.slices.size();

@@ -127,15 +127,18 @@ struct SeqParams {
   int32_t tu_slots, coef_slots;  // per-CTB capacity when !dense
   int32_t pcm, pcm_bd_y, pcm_bd_c, pcm_shift_y, pcm_shift_c, log2_min_pcm, log2_max_pcm, pcm_lf_disabled;   // 7.4.3.2.1 (shift = BitDepth - PcmBitDepth)
   int32_t tq_bypass;             // transquant_bypass_enabled_flag
+  int32_t tiles;                 // tiles_enabled_flag: sub-streams walk their tile's CTB rectangle; no per-row progress hand-shake
 };
 
 // One CABAC sub-stream.
 struct Substream {
   uint32_t pic;                  // picture (tile) index in the batch
   uint32_t byte_begin, byte_end; // inside the picture's RBSP buffer (byte_begin need not be aligned)
-  uint32_t ctb_begin, ctb_end;   // raster CTB addresses [begin, end)
+  uint32_t ctb_begin, ctb_end;   // raster address of the first CTB; ctb_end - ctb_begin = number of CTBs.  They are consecutive in TILE scan
+                                 // (6.5.1): raster order inside the CTB columns [tile_x0, tile_x1) -- the whole picture width without tiles
+  uint16_t tile_x0, tile_x1;
   uint32_t slice_addr_rs;        // first CTB of the slice (not segment) this sub-stream belongs to
-  int32_t slice_idx;
+  int32_t slice_idx;             // region (SliceInfo) index: slice x tile
   int32_t slice_qp;
   uint8_t sao_luma, sao_chroma;
   uint8_t init_contexts;         // 1: first sub-stream of an independent slice segment
@@ -294,11 +297,11 @@ struct SaoRaw { int8_t type[3], band[3], eo[3]; int8_t off[3][4]; };
 // combination of x265-produced HEIC files (and of libheif/examples/example.heic: 4:2:0 8 bit, min CB 8, TB 4..32, no
 // transform skip, cu_qp_delta + sign data hiding + SAO on, WPP); the kernel's speed is set by its instruction-cache
 // footprint (profiles/README.md), and the constants remove ~5 KB of it.  The host front-end uses CfgRuntime.
-struct CfgRuntime { enum : int { chroma = -1, bd = -1, log2_min_cb = -1, log2_min_tb = -1, log2_max_tb = -1, transform_skip = -1, cu_qp_delta = -1, sign_hiding = -1, sao_enabled = -1, wpp = -1, dense = -1, pcm = -1, tq_bypass = -1 }; };
-struct CfgCommon { enum : int { chroma = 1, bd = 8, log2_min_cb = 3, log2_min_tb = 2, log2_max_tb = 5, transform_skip = 0, cu_qp_delta = 1, sign_hiding = 1, sao_enabled = 1, wpp = 1, dense = 0, pcm = 0, tq_bypass = 0 }; };
+struct CfgRuntime { enum : int { chroma = -1, bd = -1, log2_min_cb = -1, log2_min_tb = -1, log2_max_tb = -1, transform_skip = -1, cu_qp_delta = -1, sign_hiding = -1, sao_enabled = -1, wpp = -1, dense = -1, pcm = -1, tq_bypass = -1, tiles = -1 }; };
+struct CfgCommon { enum : int { chroma = 1, bd = 8, log2_min_cb = 3, log2_min_tb = 2, log2_max_tb = 5, transform_skip = 0, cu_qp_delta = 1, sign_hiding = 1, sao_enabled = 1, wpp = 1, dense = 0, pcm = 0, tq_bypass = 0, tiles = 0 }; };
 B200_HD inline bool matches_common(const SeqParams& q) {
   return q.chroma == 1 && q.bd == 8 && q.log2_min_cb == 3 && q.log2_min_tb == 2 && q.log2_max_tb == 5 && !q.transform_skip && q.cu_qp_delta == 1 && q.sign_hiding == 1 &&
-         q.sao_enabled == 1 && q.wpp == 1 && q.dense == 0 && !q.pcm && !q.tq_bypass;
+         q.sao_enabled == 1 && q.wpp == 1 && q.dense == 0 && !q.pcm && !q.tq_bypass && !q.tiles;
 }
 #define B200_SPC(f) ((int)Cfg::f >= 0 ? (int)Cfg::f : (int)sp->f)
 #define B200_SPR(f) ((int)Cfg::f >= 0 ? (int)Cfg::f : (int)sp.f)
@@ -311,7 +314,8 @@ struct DecoderT {
   int cu_bypass;                                  // cu_transquant_bypass_flag of the current coding unit
   uint32_t tu_n, coef_n, tu_cap, coef_cap;        // write cursors / limits of the current CTB (or of the picture when dense)
   int cur_ctb_x, cur_ctb_y;
-  int ctb_x0, ctb_y0, left_ok, up_ok;            // current CTB: origin, availability of the CTB to the left / above (same slice)
+  int ctb_x0, ctb_y0, left_ok, up_ok;            // current CTB: origin, availability of the CTB to the left / above (same region: slice and tile)
+  int left_lf, up_lf;                            // deblocking across the CTB's left / upper boundary is allowed (8.7.2.3: slice and tile rules)
   struct Cu { int x0, y0, log2cb, nxn, lmode[4], cmode; };
 
   // 6.4.1 for the LEFT (x - 1, y) or ABOVE (x, y - 1) neighbour of a position inside the current CTB -- the only queries
@@ -334,8 +338,8 @@ struct DecoderT {
     B200_NOUNROLL for (int c = 0; c < 3; c++) { ci.sao[c].type = 0; ci.sao[c].band_or_class = 0; B200_NOUNROLL for (int k = 0; k < 4; k++) ci.sao[c].offset[k] = 0; }
     if (!ss->sao_luma && !ss->sao_chroma) return;
     int ml = 0, mu = 0;
-    if (rx > 0 && (uint32_t)(addr - 1) >= ss->slice_addr_rs) ml = dbin(CTX_SAO_MERGE);
-    if (ry > 0 && !ml && addr - sp->wctb >= (int)ss->slice_addr_rs) mu = dbin(CTX_SAO_MERGE);
+    if (left_ok) ml = dbin(CTX_SAO_MERGE);                        // leftCtbInSliceSeg && leftCtbInTile (7.3.8.3)
+    if (up_ok && !ml) mu = dbin(CTX_SAO_MERGE);
     if (ml || mu) {
       const unsigned long long* o = reinterpret_cast<const unsigned long long*>(pb.ctus[ml ? addr - 1 : addr - sp->wctb].sao);   // 3 x 8 bytes
       unsigned long long* dsto = reinterpret_cast<unsigned long long*>(ci.sao);
@@ -501,8 +505,8 @@ struct DecoderT {
     const int n8 = log2n > 3 ? 1 << (log2n - 3) : 1, bx = x0 >> 3, by = y0 >> 3;
     uint8_t left = 0, top = 0;
     if (!sl.deblocking_disabled) {
-      if ((x0 & 7) == 0 && x0 > 0 && (avail(x0 - 1, y0) || (sl.lf_across_slices && x0 - 1 >= 0))) left = 1;
-      if ((y0 & 7) == 0 && y0 > 0 && (avail(x0, y0 - 1) || sl.lf_across_slices)) top = 2;
+      if ((x0 & 7) == 0 && x0 > 0 && (x0 > ctb_x0 || left_lf)) left = 1;
+      if ((y0 & 7) == 0 && y0 > 0 && (y0 > ctb_y0 || up_lf)) top = 2;
     }
     // the CTB's flags were cleared in decode_ctb: only the first column / row of 8x8 cells carries an edge.  (QpY of the
     // cells is written once per coding unit, at its end.)
@@ -730,6 +734,12 @@ struct DecoderT {
     ctb_x0 = rx << sp->log2ctb; ctb_y0 = ry << sp->log2ctb;
     left_ok = rx > 0 && pb.ctu_slice[addr - 1] == (uint16_t)ss->slice_idx;
     up_ok = ry > 0 && pb.ctu_slice[addr - sp->wctb] == (uint16_t)ss->slice_idx;
+    { // edges on the CTB boundary are filtered unless they are a slice boundary the current slice does not filter across, or a
+      // tile boundary with loop_filter_across_tiles_enabled_flag = 0
+      const SliceInfo& cs = pb.slices[ss->slice_idx];
+      left_lf = left_ok; up_lf = up_ok;
+      if (rx > 0 && !left_ok) { const SliceInfo& o = pb.slices[pb.ctu_slice[addr - 1]]; left_lf = (o.slice_id == cs.slice_id || cs.lf_across_slices) && (o.tile_id == cs.tile_id || cs.lf_across_tiles); }
+      if (ry > 0 && !up_ok) { const SliceInfo& o = pb.slices[pb.ctu_slice[addr - sp->wctb]]; up_lf = (o.slice_id == cs.slice_id || cs.lf_across_slices) && (o.tile_id == cs.tile_id || cs.lf_across_tiles); } }
     CtuInfo& ci = pb.ctus[addr];
     ci.slice_idx = (uint16_t)ss->slice_idx;
     if (!B200_SPC(dense)) { tu_n = (uint32_t)addr * (uint32_t)sp->tu_slots; tu_cap = tu_n + (uint32_t)sp->tu_slots; coef_n = (uint32_t)addr * (uint32_t)sp->coef_slots; coef_cap = coef_n + (uint32_t)sp->coef_slots; }
@@ -781,9 +791,15 @@ B200_HD int run_substream(DecoderT<Cfg>& d, const SeqParams& sp, const PicBuffer
   }
   d.stream.d = pb.rbsp; d.stream.size = pb.rbsp_size;
   d.cabac.start(d.stream, ss.byte_begin);
-  B200_NOUNROLL for (uint32_t a = ss.ctb_begin; a < ss.ctb_end; a++) {
-    const int rx = (int)(a % (uint32_t)sp.wctb), ry = (int)(a / (uint32_t)sp.wctb);
-    if (ry > 0) sync.wait_row(ry - 1, rx + 1);                   // split_cu_flag context / SAO merge-up read the CTB above (same column)
+  const bool tiles = B200_SPR(tiles) != 0;
+  int rx = rx0, ry = ry0;
+  const uint32_t nctb = ss.ctb_end - ss.ctb_begin;
+  B200_NOUNROLL for (uint32_t k = 0; k < nctb; k++, rx++) {
+    if (rx == (int)ss.tile_x1) { rx = (int)ss.tile_x0; ry++; }    // next row of the tile (of the picture without tiles)
+    const uint32_t a = (uint32_t)ry * (uint32_t)sp.wctb + (uint32_t)rx;
+    // split_cu_flag context / SAO merge-up read the CTB above (same column).  With tiles that CTB belongs to this very
+    // sub-stream or is unavailable (another tile / slice), and rows are not produced in raster order: no hand-shake.
+    if (ry > 0 && !tiles) sync.wait_row(ry - 1, rx + 1);
     if (B200_SPR(wpp) && rx == 0 && a != ss.ctb_begin) {
       // only reached without WPP sub-stream splitting (never: WPP rows are separate sub-streams); kept for safety
       d.first_qg = 1;
@@ -793,10 +809,10 @@ B200_HD int run_substream(DecoderT<Cfg>& d, const SeqParams& sp, const PicBuffer
     if (d.err) break;
     if (B200_SPR(wpp) && rx == 1) { uint8_t* st = pb.wpp_ctx + (size_t)ry * CTX_STRIDE; B200_NOUNROLL for (int i = 0; i < CTX_COUNT; i++) st[i] = (uint8_t)(ctx_ld(ctx_at(ctx, i)).y >> 24); }
     const int end = d.cabac.terminate(d.stream);                          // end_of_slice_segment_flag
-    const bool last = a + 1 == ss.ctb_end;
+    const bool last = k + 1 == nctb;
     if (end != ((last && ss.last_of_segment) ? 1 : 0)) { d.err = SYN_E_BITSTREAM; break; }
     if (last && !ss.last_of_segment) { if (!d.cabac.terminate(d.stream)) { d.err = SYN_E_BITSTREAM; break; } }   // end_of_subset_one_bit
-    sync.publish_row(ry, rx + 1);
+    if (!tiles) sync.publish_row(ry, rx + 1);
     if (B200_SPR(wpp) && rx == 1) sync.notify(ss.wake_ctb2);           // the row below may start (its context hand-over is stored)
     if (d.cabac.pos > pb.rbsp_size + 64u) { d.err = SYN_E_BITSTREAM; break; }
   }

@@ -31,18 +31,22 @@ struct SaoComp { uint8_t type; uint8_t band_or_class; int8_t offset[4]; uint8_t 
 struct alignas(8) CtuInfo {
   uint32_t tu_start;     // first TuCmd of this CTU, relative to the picture's TU base
   uint16_t tu_count;
-  uint16_t slice_idx;    // index into the picture's slice table
+  uint16_t slice_idx;    // index into the picture's region table (SliceInfo)
   SaoComp sao[3];
   uint32_t pad[2];
 };
 
-struct SliceInfo {       // 16 bytes
+// One REGION of a picture = the CTBs of one slice inside one tile (without HEVC tiles: one slice).  Availability (6.4.1) is
+// "same region"; a slice that spans several tiles appears once per tile with the same parameters.  16 bytes.
+struct SliceInfo {
   int8_t cb_qp_offset, cr_qp_offset;     // pps + slice offsets used for dequantisation (8.6.1)
   int8_t beta_offset, tc_offset;         // slice_beta_offset_div2 * 2, slice_tc_offset_div2 * 2
   uint8_t deblocking_disabled, lf_across_slices;
-  uint8_t pad[2];
+  uint16_t slice_id;                     // index of the slice in decoding order (in-loop filter rules compare slices, not regions)
   uint32_t first_ctb_rs;
-  uint32_t pad2;
+  uint16_t tile_id;                      // TileId of the region's CTBs (0 without tiles)
+  uint8_t lf_across_tiles;               // loop_filter_across_tiles_enabled_flag
+  uint8_t pad;
 };
 
 // Per 8x8 luma block (one byte each in two maps):

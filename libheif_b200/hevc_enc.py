@@ -16,7 +16,8 @@ class EncParams(C.Structure):
         "tc_offset_div2", "slice_deblocking_override", "slice_deblocking_disabled", "slice_beta_offset_div2",
         "slice_tc_offset_div2", "mode_decision", "split_threshold", "still_picture", "vui_present",
         "colour_description_present", "colour_primaries", "transfer_characteristics", "matrix_coefficients", "full_range")] + \
-        [("seed", C.c_uint32), ("scaling_lists", C.c_int), ("pcm", C.c_int), ("transquant_bypass", C.c_int)]
+        [("seed", C.c_uint32), ("scaling_lists", C.c_int), ("pcm", C.c_int), ("transquant_bypass", C.c_int), ("tile_cols", C.c_int), ("tile_rows", C.c_int), ("tiles_uniform", C.c_int),
+         ("loop_filter_across_tiles", C.c_int), ("slice_per_tile", C.c_int)]
 
 
 def default_params(**kw) -> EncParams:

@@ -91,6 +91,8 @@ typedef struct {
   int init_qp, constrained_intra, transform_skip, cu_qp_delta, diff_cu_qp_delta_depth;
   int cb_qp_offset, cr_qp_offset, slice_chroma_qp_offsets_present;
   int transquant_bypass, tiles, wpp;
+  int num_tile_cols, num_tile_rows, uniform_spacing, lf_across_tiles;   /* 7.3.2.3: tiles */
+  int col_width[20], row_height[22];
   int lf_across_slices, deblock_control, deblock_override_enabled, deblock_disabled, beta_offset, tc_offset;
   int scaling_list_present, lists_modification, slice_ext_present;
   int log2_sao_scale_luma, log2_sao_scale_chroma;
@@ -292,7 +294,18 @@ static int parse_pps(const uint8_t* rbsp, size_t n, pps_t* p) {
   p->transquant_bypass = rd_bit(&b);
   p->tiles = rd_bit(&b);
   p->wpp = rd_bit(&b);
-  if (p->tiles) return HO_UNSUPPORTED;
+  p->num_tile_cols = p->num_tile_rows = 1; p->lf_across_tiles = 1;
+  if (p->tiles) {
+    if (p->wpp) return HO_UNSUPPORTED;                           /* tiles together with wavefronts: not restated */
+    p->num_tile_cols = 1 + rd_ue(&b); p->num_tile_rows = 1 + rd_ue(&b);
+    if (p->num_tile_cols > 20 || p->num_tile_rows > 22) return HO_ERROR;
+    p->uniform_spacing = rd_bit(&b);
+    if (!p->uniform_spacing) {
+      for (int i = 0; i + 1 < p->num_tile_cols; i++) p->col_width[i] = 1 + rd_ue(&b);
+      for (int i = 0; i + 1 < p->num_tile_rows; i++) p->row_height[i] = 1 + rd_ue(&b);
+    }
+    p->lf_across_tiles = rd_bit(&b);
+  }
   p->lf_across_slices = rd_bit(&b);
   p->deblock_control = rd_bit(&b);
   if (p->deblock_control) {
@@ -403,6 +416,9 @@ typedef struct {
   cabac_ctx ctx[CTX_COUNT], ctx_wpp[CTX_COUNT];
   /* QP state */
   int is_cu_qp_delta_coded, cu_qp_delta_val, qpy_prev_qg, last_cu_qpy, first_qg_in_row;
+  int col_bd[21], row_bd[23], ntc, ntr;   /* 6.5.1: tile column / row boundaries in CTBs */
+  int* ts2rs; int* rs2ts; int* tile_of_ctb;   /* CtbAddrTsToRs, CtbAddrRsToTs, TileId (indexed by raster address) */
+  int cur_tile;
   int cur_qpy;
   int picture_started;
   int err;
@@ -467,10 +483,13 @@ static void cabac_byte_align_and_restart(dec_t* d) {
 static inline int clip3(int lo, int hi, int v) { return v < lo ? lo : (v > hi ? hi : v); }
 static inline int iabs(int v) { return v < 0 ? -v : v; }
 
+static int tile_of_xy(const dec_t* d, int x, int y) { return d->tile_of_ctb[(y >> d->s->log2_ctb) * d->wctb + (x >> d->s->log2_ctb)]; }
+
 /* 6.4.1 z-scan availability, restated with the "already decoded in the same slice" map */
 static int avail4(const dec_t* d, int x, int y) {
   if (x < 0 || y < 0 || x >= d->W || y >= d->H) return 0;
   unsigned s = d->slice_of4[(y >> 2) * d->w4 + (x >> 2)];
+  if (d->p->tiles && tile_of_xy(d, x, y) != d->cur_tile) return 0;            /* a different tile is never available */
   return s != 0 && s == (unsigned)(d->slice_idx + 1);
 }
 
@@ -1036,8 +1055,8 @@ static void parse_sao(dec_t* d, int rx, int ry) {
   d->ctb_slice_sao[addr] = (uint8_t)((d->sao_luma ? 1 : 0) | (d->sao_chroma ? 2 : 0));
   if (!d->sao_luma && !d->sao_chroma) return;
   int merge_left = 0, merge_up = 0;
-  if (rx > 0 && addr - 1 >= d->slice_addr_rs) merge_left = dec_bin(d, CTX_SAO_MERGE);
-  if (ry > 0 && !merge_left && addr - d->wctb >= d->slice_addr_rs) merge_up = dec_bin(d, CTX_SAO_MERGE);
+  if (rx > 0 && addr - 1 >= d->slice_addr_rs && d->tile_of_ctb[addr - 1] == d->tile_of_ctb[addr]) merge_left = dec_bin(d, CTX_SAO_MERGE);     /* leftCtbInSliceSeg && leftCtbInTile */
+  if (ry > 0 && !merge_left && addr - d->wctb >= d->slice_addr_rs && d->tile_of_ctb[addr - d->wctb] == d->tile_of_ctb[addr]) merge_up = dec_bin(d, CTX_SAO_MERGE);
   if (merge_left) { *sp = d->sao[addr - 1]; return; }
   if (merge_up) { *sp = d->sao[addr - d->wctb]; return; }
   int ncomp = s->chroma_format_idc ? 3 : 1;
@@ -1090,6 +1109,26 @@ static int alloc_picture(dec_t* d) {
   d->ctb_slice_sao = (uint8_t*)calloc((size_t)d->wctb * d->hctb, 1);
   d->nslices = 0;
   d->picture_started = 1;
+  /* 6.5.1: tile boundaries, CtbAddrRsToTs / TsToRs, TileId */
+  { const pps_t* p = d->p; int nctb = d->wctb * d->hctb;
+    d->ntc = p->num_tile_cols; d->ntr = p->num_tile_rows;
+    if (d->ntc > d->wctb || d->ntr > d->hctb) return HO_ERROR;
+    d->col_bd[0] = d->row_bd[0] = 0;
+    for (int i = 0; i < d->ntc; i++) {
+      int w = (!p->tiles || p->uniform_spacing) ? ((i + 1) * d->wctb) / d->ntc - (i * d->wctb) / d->ntc : (i + 1 < d->ntc ? p->col_width[i] : d->wctb - d->col_bd[i]);
+      if (w <= 0) return HO_ERROR;
+      d->col_bd[i + 1] = d->col_bd[i] + w; }
+    for (int i = 0; i < d->ntr; i++) {
+      int h = (!p->tiles || p->uniform_spacing) ? ((i + 1) * d->hctb) / d->ntr - (i * d->hctb) / d->ntr : (i + 1 < d->ntr ? p->row_height[i] : d->hctb - d->row_bd[i]);
+      if (h <= 0) return HO_ERROR;
+      d->row_bd[i + 1] = d->row_bd[i] + h; }
+    if (d->col_bd[d->ntc] != d->wctb || d->row_bd[d->ntr] != d->hctb) return HO_ERROR;
+    d->ts2rs = (int*)calloc((size_t)nctb, sizeof(int)); d->rs2ts = (int*)calloc((size_t)nctb, sizeof(int)); d->tile_of_ctb = (int*)calloc((size_t)nctb, sizeof(int));
+    int ts = 0;
+    for (int tr = 0; tr < d->ntr; tr++) for (int tc = 0; tc < d->ntc; tc++)
+      for (int y = d->row_bd[tr]; y < d->row_bd[tr + 1]; y++) for (int x = d->col_bd[tc]; x < d->col_bd[tc + 1]; x++) {
+        int rs = y * d->wctb + x; d->ts2rs[ts] = rs; d->rs2ts[rs] = ts; d->tile_of_ctb[rs] = tr * d->ntc + tc; ts++; }
+  }
   return HO_OK;
 }
 
@@ -1103,7 +1142,7 @@ static int decode_slice(dec_t* d, const uint8_t* rbsp, size_t n, int nal_type) {
   const pps_t* p = &d->pps[pps_id];
   if (p->sps_id > 15 || !d->sps[p->sps_id].valid) return HO_ERROR;
   const sps_t* s = &d->sps[p->sps_id];
-  if (first) { if (d->picture_started) return HO_ERROR; d->s = s; d->p = p; alloc_picture(d); }
+  if (first) { if (d->picture_started) return HO_ERROR; d->s = s; d->p = p; int rc = alloc_picture(d); if (rc) return rc; }
   else if (!d->picture_started) return HO_ERROR;
   d->p = p;
   int dependent = 0, seg_addr = 0;
@@ -1150,7 +1189,7 @@ static int decode_slice(dec_t* d, const uint8_t* rbsp, size_t n, int nal_type) {
     d->sl[d->slice_idx].deblock_disabled = dis; d->sl[d->slice_idx].beta_offset = beta; d->sl[d->slice_idx].tc_offset = tc;
     d->sl[d->slice_idx].cb_off = d->cur_cb_off; d->sl[d->slice_idx].cr_off = d->cur_cr_off;
   } else if (d->nslices == 0) return HO_ERROR;
-  if (p->wpp) {
+  if (p->wpp || p->tiles) {
     int ne = rd_ue(&b);
     if (ne > 0) { int len = rd_ue(&b) + 1; for (int i = 0; i < ne; i++) { unsigned v = rd_bits(&b, len); if (getenv("HO_DEBUG") && i < 4) fprintf(stderr, "entry[%d]=%u\n", i, v + 1); } }
   }
@@ -1162,12 +1201,16 @@ static int decode_slice(dec_t* d, const uint8_t* rbsp, size_t n, int nal_type) {
   if (!dependent) cabac_init_contexts(d);
   /* (dependent segments continue with the context state left by the previous segment, 9.3.1) */
   cabac_init_engine(d);
-  int ctb_addr = seg_addr, total = d->wctb * d->hctb;
+  int total = d->wctb * d->hctb;
+  if (seg_addr >= total) return HO_ERROR;
+  int ctb_ts = d->rs2ts[seg_addr], ctb_addr = seg_addr;                 /* the CTBs of a segment are consecutive in TILE scan (6.5.1) */
   d->first_qg_in_row = 1;
   if (dependent) d->first_qg_in_row = 0; /* qPY_PREV continues across a dependent slice segment */
   if (!dependent) d->last_cu_qpy = d->slice_qp;
   for (;;) {
+    ctb_addr = d->ts2rs[ctb_ts];
     int rx = ctb_addr % d->wctb, ry = ctb_addr / d->wctb;
+    d->cur_tile = d->tile_of_ctb[ctb_addr];
     if (p->wpp && rx == 0 && ctb_addr != seg_addr) {
       /* 9.3.1: synchronise with the state stored after the 2nd CTB of the row above */
       if (avail4(d, (rx + 1) << s->log2_ctb, (ry - 1) << s->log2_ctb)) memcpy(d->ctx, d->ctx_wpp, sizeof d->ctx);
@@ -1183,9 +1226,16 @@ static int decode_slice(dec_t* d, const uint8_t* rbsp, size_t n, int nal_type) {
     if (d->err) return d->err;
     if (p->wpp && rx == 1) memcpy(d->ctx_wpp, d->ctx, sizeof d->ctx);   /* 9.3.2.2 storage after the 2nd CTB of a row */
     int end = dec_terminate(d);              /* end_of_slice_segment_flag */
-    ctb_addr++;
+    ctb_ts++; ctb_addr++;
     if (end) break;
-    if (ctb_addr >= total) return HO_ERROR;
+    if (ctb_ts >= total) return HO_ERROR;
+    if (p->tiles && d->tile_of_ctb[d->ts2rs[ctb_ts]] != d->tile_of_ctb[d->ts2rs[ctb_ts - 1]]) {
+      /* the next CTB starts a tile: end_of_subset_one_bit, byte alignment, and 9.3.1 initialisation of the context variables */
+      if (!dec_terminate(d)) return HO_ERROR;
+      cabac_byte_align_and_restart(d);
+      cabac_init_contexts(d);
+      d->first_qg_in_row = 1;              /* first quantization group in a tile: qPY_PREV = SliceQpY (8.6.1) */
+    }
     if (p->wpp && ctb_addr % d->wctb == 0) {
       if (!dec_terminate(d)) return HO_ERROR; /* end_of_subset_one_bit */
       if (getenv("HO_DEBUG")) fprintf(stderr, "row end at ctb %d: bitpos=%zu (byte %zu rem %zu), data start byte %zu, last bytes %02x %02x %02x\n", ctb_addr, d->br.pos, d->br.pos >> 3, d->br.pos & 7, b.pos >> 3, d->br.d[(d->br.pos >> 3) - 1], d->br.d[d->br.pos >> 3], d->br.d[(d->br.pos >> 3) + 1]);
@@ -1209,6 +1259,7 @@ static int edge_filtered(const dec_t* d, int x, int y, int vert) {
   int sq = d->slice_of4[i] - 1, sp = d->slice_of4[j] - 1;
   if (d->sl[sq].deblock_disabled) return 0;
   if (sq != sp && !d->sl[sq].lf_across) return 0;
+  if (d->p->tiles && !d->p->lf_across_tiles && tile_of_xy(d, x, y) != tile_of_xy(d, vert ? x - 1 : x, vert ? y : y - 1)) return 0;   /* tile boundary */
   return 1;
 }
 
@@ -1323,6 +1374,10 @@ static void sao_picture(dec_t* d) {
           int skip = 0;
           if (sa != cur) { if (sa < cur ? !d->sl[cur].lf_across : !d->sl[sa].lf_across) skip = 1; }
           if (sb != cur) { if (sb < cur ? !d->sl[cur].lf_across : !d->sl[sb].lf_across) skip = 1; }
+          if (d->p->tiles && !d->p->lf_across_tiles) {           /* 8.7.3.2: a neighbouring sample in a different tile */
+            int tcur = tile_of_xy(d, x << sh, y << sh);
+            if (tile_of_xy(d, xa << sh, ya << sh) != tcur || tile_of_xy(d, xb << sh, yb << sh) != tcur) skip = 1;
+          }
           if (skip) continue;
           int a = src[ya * st + xa], b2 = src[yb * st + xb];
           int ei = 2 + (v > a) - (v < a) + (v > b2) - (v < b2);
@@ -1339,7 +1394,7 @@ static void sao_picture(dec_t* d) {
 /* --------------------------------------------------------------------------------------- top level */
 static void free_dec(dec_t* d) {
   for (int c = 0; c < 3; c++) free(d->pl[c]);
-  free(d->cmode4); free(d->slice_of4); free(d->ipm4); free(d->qp4); free(d->tu_edge4); free(d->cd4); free(d->nofilt4); free(d->sao); free(d->ctb_slice_sao);
+  free(d->cmode4); free(d->slice_of4); free(d->ipm4); free(d->qp4); free(d->tu_edge4); free(d->cd4); free(d->nofilt4); free(d->sao); free(d->ctb_slice_sao); free(d->ts2rs); free(d->rs2ts); free(d->tile_of_ctb);
 }
 
 void hevc_oracle_free_picture(hevc_oracle_picture* p) { for (int c = 0; c < 3; c++) { free(p->plane[c]); p->plane[c] = NULL; } }

@@ -58,6 +58,13 @@ SYNTH = [
     ("bypass_lossless", 96, 64, 8, True, dict(log2_ctb_size=4, transquant_bypass=2)),
     ("bypass_tskip_main12", 160, 96, 12, True, dict(log2_ctb_size=5, transquant_bypass=1, transform_skip=1, mode_decision=0)),
     ("pcm_bypass_scaling_slices_wpp", 256, 192, 8, True, dict(log2_ctb_size=5, pcm=1, transquant_bypass=1, scaling_lists=2, slice_ctb_rows=2, wpp=1)),
+    # HEVC tiles (6.5.1): uniform and explicit spacing, one slice over all tiles / one slice per tile, loop filters across tile boundaries on and off
+    ("tiles_2x2", 256, 192, 8, True, dict(log2_ctb_size=5, tile_cols=2, tile_rows=2)),
+    ("tiles_3x2_explicit_nolf", 320, 256, 8, True, dict(log2_ctb_size=5, tile_cols=3, tile_rows=2, tiles_uniform=0, loop_filter_across_tiles=0)),
+    ("tiles_2x3_slice_per_tile_main10", 264, 200, 10, True, dict(log2_ctb_size=5, tile_cols=2, tile_rows=3, slice_per_tile=1, loop_filter_across_tiles=0, slice_loop_filter_across_slices=0)),
+    ("tiles_4x1_ctb64", 512, 128, 8, True, dict(log2_ctb_size=6, tile_cols=4, tile_rows=1)),
+    ("tiles_5x4_ctb16_mono_nolf", 208, 176, 8, False, dict(log2_ctb_size=4, tile_cols=5, tile_rows=4, loop_filter_across_tiles=0)),
+    ("tiles_3x3_pcm_bypass_scaling", 200, 168, 8, True, dict(log2_ctb_size=4, tile_cols=3, tile_rows=3, tiles_uniform=0, mode_decision=0, pcm=1, transquant_bypass=1, scaling_lists=2, sao=0)),
 ]
 
 # More feature combinations, used by the CPU tests only (FFmpeg pin of the restatement, host front-end vs restatement):
@@ -76,6 +83,9 @@ SYNTH_CPU_EXTRA = [
     ("x_pcm_nolf_nosao_ctb16", 136, 72, 8, True, dict(log2_ctb_size=4, pcm=2, sao=0, seed=6)),
     ("x_lossless_main10_ctb64_wpp", 200, 136, 10, True, dict(log2_ctb_size=6, transquant_bypass=2, wpp=1)),
     ("x_lossless_mono_nosao", 72, 40, 8, False, dict(log2_ctb_size=5, transquant_bypass=2, sao=0)),
+    ("x_tiles_2x2_main12_dqp_slice_per_tile", 256, 192, 12, True, dict(log2_ctb_size=6, tile_cols=2, tile_rows=2, dqp_range=8, diff_cu_qp_delta_depth=2, slice_per_tile=1)),
+    ("x_tiles_1x3_slices_nolf_across_slices", 136, 200, 8, True, dict(log2_ctb_size=5, tile_cols=1, tile_rows=3, slice_per_tile=1, slice_loop_filter_across_slices=0)),
+    ("x_tiles_7x1_random_deep", 232, 72, 8, True, dict(log2_ctb_size=5, tile_cols=7, tile_rows=1, tiles_uniform=0, mode_decision=0, max_transform_hierarchy_depth_intra=3, transform_skip=1)),
     ("x_slices_every_row_nolf_across", 192, 160, 8, True, dict(log2_ctb_size=5, slice_ctb_rows=1, loop_filter_across_slices=0, slice_loop_filter_across_slices=0)),
 ]
 
