@@ -184,14 +184,15 @@ class Encoder {
   Encoder(const b200_hevc_enc_params& p, const uint16_t* const src[3], const int stride[3]) : P(p) {
     init_tables();
     W = (p.width + 7) & ~7; H = (p.height + 7) & ~7;       // multiples of MinCbSizeY (8); conformance window crops
-    chroma = p.chroma_format_idc ? 1 : 0;
-    Wc = chroma ? W / 2 : 0; Hc = chroma ? H / 2 : 0;
+    cfmt = p.chroma_format_idc; chroma = cfmt ? 1 : 0;
+    sx = (cfmt == 1 || cfmt == 2) ? 1 : 0; sy = cfmt == 1 ? 1 : 0;       // SubWidthC = 1 << sx, SubHeightC = 1 << sy (Table 6-1)
+    Wc = chroma ? W >> sx : 0; Hc = chroma ? H >> sy : 0;
     log2ctb = p.log2_ctb_size; ctb = 1 << log2ctb;
     wctb = (W + ctb - 1) >> log2ctb; hctb = (H + ctb - 1) >> log2ctb;
     w4 = W / 4; h4 = H / 4;
     bd = p.bit_depth;
     for (int c = 0; c < (chroma ? 3 : 1); c++) {
-      int pw = c ? Wc : W, ph = c ? Hc : H, sw = c ? (p.width + 1) / 2 : p.width, sh = c ? (p.height + 1) / 2 : p.height;
+      int pw = c ? Wc : W, ph = c ? Hc : H, sw = c ? (p.width + (1 << sx) - 1) >> sx : p.width, sh = c ? (p.height + (1 << sy) - 1) >> sy : p.height;
       org[c].assign((size_t)pw * ph, 0); rec[c].assign((size_t)pw * ph, 0);
       for (int y = 0; y < ph; y++) for (int x = 0; x < pw; x++)
         org[c][(size_t)y * pw + x] = src[c][(size_t)std::min(y, sh - 1) * stride[c] + std::min(x, sw - 1)];   // edge padding
@@ -272,6 +273,7 @@ class Encoder {
 
  private:
   b200_hevc_enc_params P;
+  int cfmt = 1, sx = 1, sy = 1;
   int W, H, Wc, Hc, chroma, log2ctb, ctb, wctb, hctb, w4, h4, bd, log2_min_tb, log2_max_tb, max_th_depth, qg_log2;
   std::vector<uint16_t> org[3], rec[3];
   std::vector<uint16_t> slice_of4; std::vector<uint8_t> ipm4, cd4; std::vector<int8_t> qp4;
@@ -313,7 +315,7 @@ class Encoder {
 
   // ---------------------------------------------------------------------------- parameter sets
   void profile_tier_level(BitWriter& b) {
-    int profile = bd == 8 ? (P.still_picture ? 3 : 1) : (bd == 10 && chroma ? 2 : 4);
+    int profile = cfmt >= 2 ? 4 : (bd == 8 ? (P.still_picture ? 3 : 1) : (bd == 10 && chroma ? 2 : 4));
     b.put(0, 2); b.put(0, 1); b.put(profile, 5);
     uint32_t compat = 0;
     if (profile == 1) compat = (1u << 30) | (1u << 29);       // Main => also Main 10 compatible
@@ -325,7 +327,7 @@ class Encoder {
     if (profile == 4) {                                         // RExt constraint flags: Main 12 / Monochrome 12 family
       b.put(1, 1);                                              // max_12bit_constraint
       b.put(bd <= 10, 1); b.put(bd <= 8, 1);                    // max_10bit, max_8bit
-      b.put(1, 1); b.put(1, 1); b.put(chroma == 0, 1);          // max_422chroma, max_420chroma, max_monochrome
+      b.put(cfmt <= 2, 1); b.put(cfmt <= 1, 1); b.put(chroma == 0, 1);   // max_422chroma, max_420chroma, max_monochrome
       b.put(1, 1); b.put(1, 1); b.put(1, 1);                    // intra, one_picture_only, lower_bit_rate
       b.put(0, 32); b.put(0, 2);                                // reserved 34 bits
     } else { b.put(0, 32); b.put(0, 11); }
@@ -352,10 +354,10 @@ class Encoder {
     b.put(0, 4); b.put(0, 3); b.put(1, 1);
     profile_tier_level(b);
     b.ue(0);
-    b.ue(chroma ? 1 : 0);
+    b.ue(cfmt);
+    if (cfmt == 3) b.put(0, 1);                                   // separate_colour_plane_flag
     b.ue(W); b.ue(H);
-    int sub = chroma ? 2 : 1;
-    int cr = (W - P.width) / sub, cbm = (H - P.height) / sub;
+    int cr = (W - P.width) >> (chroma ? sx : 0), cbm = (H - P.height) >> (chroma ? sy : 0);     // conformance window in chroma units
     if (cr || cbm) { b.put(1, 1); b.ue(0); b.ue(cr); b.ue(0); b.ue(cbm); } else b.put(0, 1);
     b.ue(bd - 8); b.ue(bd - 8);
     b.ue(4);                          // log2_max_pic_order_cnt_lsb_minus4
@@ -563,14 +565,14 @@ class Encoder {
 
   // ---------------------------------------------------------------------------- intra prediction (8.4.4.2)
   void predict(int c, int x0, int y0, int log2n, int mode, uint16_t* dst /* n*n */) const {
-    const int n = 1 << log2n, sh = c ? 1 : 0, st = stride_of(c);
+    const int n = 1 << log2n, shx = c ? sx : 0, shy = c ? sy : 0, st = stride_of(c);
     const uint16_t* pl = rec[c].data();
     int refbuf[129], fbuf[129]; uint8_t av[129];
     bool any = false;
     for (int i = 0; i <= 4 * n; i++) {
       int px, py;
       if (i < 2 * n) { px = x0 - 1; py = y0 + 2 * n - 1 - i; } else if (i == 2 * n) { px = x0 - 1; py = y0 - 1; } else { px = x0 + (i - 2 * n - 1); py = y0 - 1; }
-      av[i] = avail(px << sh, py << sh);
+      av[i] = avail(px << shx, py << shy);
       if (av[i]) { refbuf[i] = pl[(size_t)py * st + px]; any = true; }
     }
     if (!any) for (int i = 0; i <= 4 * n; i++) refbuf[i] = 1 << (bd - 1);
@@ -580,12 +582,12 @@ class Encoder {
       for (int i = first + 1; i <= 4 * n; i++) if (!av[i]) refbuf[i] = refbuf[i - 1];
     }
     int* ref = refbuf;
-    if (c == 0 && mode != 1 && n != 4) {
+    if ((c == 0 || cfmt == 3) && mode != 1 && n != 4) {            // 8.4.4.2.3: filtering of the neighbours for luma, and for chroma in 4:4:4
       int dist = std::min(std::abs(mode - 26), std::abs(mode - 10));
       int thr = n == 8 ? 7 : (n == 16 ? 1 : 0);
       if (dist > thr) {
         int corner = ref[2 * n], bl = ref[0], tr = ref[4 * n];
-        if (P.strong_intra_smoothing && n == 32 && std::abs(corner + tr - 2 * ref[3 * n]) < (1 << (bd - 5)) && std::abs(corner + bl - 2 * ref[n]) < (1 << (bd - 5))) {
+        if (P.strong_intra_smoothing && c == 0 && n == 32 && std::abs(corner + tr - 2 * ref[3 * n]) < (1 << (bd - 5)) && std::abs(corner + bl - 2 * ref[n]) < (1 << (bd - 5))) {
           fbuf[2 * n] = corner; fbuf[0] = bl; fbuf[4 * n] = tr;
           for (int y = 0; y < 63; y++) fbuf[2 * n - 1 - y] = ((63 - y) * corner + (y + 1) * bl + 32) >> 6;
           for (int x = 0; x < 63; x++) fbuf[2 * n + 1 + x] = ((63 - x) * corner + (x + 1) * tr + 32) >> 6;
@@ -670,7 +672,7 @@ class Encoder {
   }
   int chroma_qp(int qpy, int off) const {
     int qbd = 6 * (bd - 8), qpi = clip3(-qbd, 57, qpy + off);
-    int qpc = qpi < 30 ? qpi : (qpi >= 43 ? qpi - 6 : kQpcTab[qpi - 30]);
+    int qpc = cfmt != 1 ? std::min(qpi, 51) : (qpi < 30 ? qpi : (qpi >= 43 ? qpi - 6 : kQpcTab[qpi - 30]));      // Table 8-10 only for ChromaArrayType == 1
     return qpc + qbd;
   }
 
@@ -828,7 +830,7 @@ class Encoder {
     bool dst4 = c == 0 && log2n == 2;
     if (cu_bypass) {                                  // cu_transquant_bypass_flag: the residual is coded as is (8.6.2), lossless
       r.tskip = false; r.scan = 0;
-      if (log2n == 2 || (log2n == 3 && c == 0)) { if (mode >= 6 && mode <= 14) r.scan = 2; else if (mode >= 22 && mode <= 30) r.scan = 1; }
+      if (log2n == 2 || (log2n == 3 && (c == 0 || cfmt == 3))) { if (mode >= 6 && mode <= 14) r.scan = 2; else if (mode >= 22 && mode <= 30) r.scan = 1; }
       r.cbf = false;
       for (int i = 0; i < n * n; i++) { r.lev[i] = (int16_t)res[i]; r.cbf |= res[i] != 0; }
       uint16_t* rq = rec[c].data();
@@ -837,7 +839,7 @@ class Encoder {
     }
     r.tskip = P.transform_skip && log2n == 2 && rng.range(4) == 0;
     r.scan = 0;
-    if (log2n == 2 || (log2n == 3 && c == 0)) { if (mode >= 6 && mode <= 14) r.scan = 2; else if (mode >= 22 && mode <= 30) r.scan = 1; }
+    if (log2n == 2 || (log2n == 3 && (c == 0 || cfmt == 3))) { if (mode >= 6 && mode <= 14) r.scan = 2; else if (mode >= 22 && mode <= 30) r.scan = 1; }
     forward(res, coef, log2n, dst4, r.tskip);
     int qp = c == 0 ? qg_target_qp + 6 * (bd - 8) : chroma_qp(qg_target_qp, (c == 1 ? P.cb_qp_offset : P.cr_qp_offset) + (P.slice_chroma_qp_offsets ? (c == 1 ? P.slice_cb_qp_offset : P.slice_cr_qp_offset) : 0));
     r.cbf = quantise(coef, r.lev, log2n, qp, r.scan);
@@ -859,11 +861,12 @@ class Encoder {
   }
 
   // ---------------------------------------------------------------------------- transform tree (7.3.8.8)
-  struct Cu { int x0, y0, log2cb, nxn, lmode[4], cmode; };
+  struct Cu { int x0, y0, log2cb, nxn, lmode[4], cmode[4]; };      // cmode: IntraPredModeC per prediction unit (one per PU only in 4:4:4)
 
   // Decide the TU split structure first (so that cbf_cb/cbf_cr of inner nodes are known before they are
   // written) by coding leaves depth-first into a node list, then emit the syntax in a second walk.
-  struct Node { int x0, y0, log2n, depth, blk, split, child[4]; bool cbf_l, cbf_cb, cbf_cr; TbResult *l, *cb, *cr; };
+  // chroma: [t] = the upper / lower square block of a 4:2:2 transform unit (t = 0 only otherwise)
+  struct Node { int x0, y0, log2n, depth, blk, split, child[4]; bool cbf_l, cbf_cb[2], cbf_cr[2]; TbResult *l, *cb[2], *cr[2]; };
   std::vector<Node> nodes; std::vector<TbResult*> pool;
   TbResult* new_tb() { TbResult* t = new TbResult; pool.push_back(t); return t; }
 
@@ -878,12 +881,14 @@ class Encoder {
       bool cb = false, cr = false;
       for (int k = 0; k < 4; k++) {
         int ch = build_tree(cu, x0 + (k & 1) * h, y0 + (k >> 1) * h, log2n - 1, depth + 1, k, max_depth, me);
-        nodes[me].child[k] = ch; cb |= nodes[ch].cbf_cb; cr |= nodes[ch].cbf_cr;
+        nodes[me].child[k] = ch; cb |= nodes[ch].cbf_cb[0] || nodes[ch].cbf_cb[1]; cr |= nodes[ch].cbf_cr[0] || nodes[ch].cbf_cr[1];
       }
-      nodes[me].cbf_cb = cb; nodes[me].cbf_cr = cr;
-      if (log2n == 3 && chroma) {          // 4x4 luma children: the chroma 4x4 blocks are coded with child 3 at this node's origin
-        nodes[me].cbf_cb = nodes[nodes[me].child[3]].cb ? nodes[nodes[me].child[3]].cb->cbf : false;
-        nodes[me].cbf_cr = nodes[nodes[me].child[3]].cr ? nodes[nodes[me].child[3]].cr->cbf : false;
+      nodes[me].cbf_cb[0] = cb; nodes[me].cbf_cr[0] = cr; nodes[me].cbf_cb[1] = nodes[me].cbf_cr[1] = false;
+      if (log2n == 3 && chroma && cfmt != 3) {   // 4x4 luma children: the chroma 4x4 blocks are coded with child 3 at this node's origin
+        for (int t = 0; t < 2; t++) {
+          nodes[me].cbf_cb[t] = nodes[nodes[me].child[3]].cb[t] ? nodes[nodes[me].child[3]].cb[t]->cbf : false;
+          nodes[me].cbf_cr[t] = nodes[nodes[me].child[3]].cr[t] ? nodes[nodes[me].child[3]].cr[t]->cbf : false;
+        }
       }
     } else {
       int pu = cu.nxn ? ((y0 >= cu.y0 + (1 << (cu.log2cb - 1))) ? 2 : 0) + ((x0 >= cu.x0 + (1 << (cu.log2cb - 1))) ? 1 : 0) : 0;
@@ -891,34 +896,37 @@ class Encoder {
       m.l = new_tb(); code_tb(0, x0, y0, log2n, cu.lmode[pu], *m.l); m.cbf_l = m.l->cbf;
       mark_tu(x0, y0, log2n);
       if (chroma) {
-        if (log2n > 2) {
-          m.cb = new_tb(); code_tb(1, x0 >> 1, y0 >> 1, log2n - 1, cu.cmode, *m.cb); m.cbf_cb = m.cb->cbf;
-          m.cr = new_tb(); code_tb(2, x0 >> 1, y0 >> 1, log2n - 1, cu.cmode, *m.cr); m.cbf_cr = m.cr->cbf;
+        const int nb = cfmt == 2 ? 2 : 1;                       // 4:2:2: two square blocks, one above the other (7.3.8.10)
+        if (log2n > 2 || cfmt == 3) {
+          const int lc = cfmt == 3 ? log2n : log2n - 1, cm = cu.cmode[cfmt == 3 ? pu : 0];
+          for (int t = 0; t < nb; t++) { m.cb[t] = new_tb(); code_tb(1, x0 >> sx, (y0 >> sy) + (t << lc), lc, cm, *m.cb[t]); m.cbf_cb[t] = m.cb[t]->cbf; }
+          for (int t = 0; t < nb; t++) { m.cr[t] = new_tb(); code_tb(2, x0 >> sx, (y0 >> sy) + (t << lc), lc, cm, *m.cr[t]); m.cbf_cr[t] = m.cr[t]->cbf; }
         } else if (blk == 3) {
           const Node& par = nodes[parent];
-          m.cb = new_tb(); code_tb(1, par.x0 >> 1, par.y0 >> 1, 2, cu.cmode, *m.cb);
-          m.cr = new_tb(); code_tb(2, par.x0 >> 1, par.y0 >> 1, 2, cu.cmode, *m.cr);
+          for (int t = 0; t < nb; t++) { m.cb[t] = new_tb(); code_tb(1, par.x0 >> sx, (par.y0 >> sy) + (t << 2), 2, cu.cmode[0], *m.cb[t]); }
+          for (int t = 0; t < nb; t++) { m.cr[t] = new_tb(); code_tb(2, par.x0 >> sx, (par.y0 >> sy) + (t << 2), 2, cu.cmode[0], *m.cr[t]); }
         }
       }
     }
     return me;
   }
 
-  void write_tree(const Cu& cu, int me, bool parent_cb, bool parent_cr, int max_depth) {
+  // parent_cb / parent_cr: the cbf_cb / cbf_cr flags of the parent node ([1]: lower 4:2:2 block)
+  void write_tree(const Cu& cu, int me, const bool parent_cb[2], const bool parent_cr[2], int max_depth) {
     const Node& nd = nodes[me];
     bool can_split = nd.log2n <= log2_max_tb && nd.log2n > log2_min_tb && nd.depth < max_depth && !(cu.nxn && nd.depth == 0);
     if (can_split) cabac.bin(ctx[CTX_SPLIT_TR + 5 - nd.log2n], nd.split);
-    bool cb = false, cr = false;
+    bool cb[2] = {false, false}, cr[2] = {false, false};
     if (chroma) {
-      if (nd.log2n > 2) {
-        cb = nd.cbf_cb; cr = nd.cbf_cr;
-        if (nd.depth == 0 || parent_cb) cabac.bin(ctx[CTX_CBF_CHROMA + nd.depth], cb); else cb = false;
-        if (nd.depth == 0 || parent_cr) cabac.bin(ctx[CTX_CBF_CHROMA + nd.depth], cr); else cr = false;
-      } else { cb = parent_cb; cr = parent_cr; }
+      if (nd.log2n > 2 || cfmt == 3) {
+        const bool two = cfmt == 2 && (!nd.split || nd.log2n == 3);
+        if (nd.depth == 0 || parent_cb[0]) { cb[0] = nd.cbf_cb[0]; cabac.bin(ctx[CTX_CBF_CHROMA + nd.depth], cb[0]); if (two) { cb[1] = nd.cbf_cb[1]; cabac.bin(ctx[CTX_CBF_CHROMA + nd.depth], cb[1]); } }
+        if (nd.depth == 0 || parent_cr[0]) { cr[0] = nd.cbf_cr[0]; cabac.bin(ctx[CTX_CBF_CHROMA + nd.depth], cr[0]); if (two) { cr[1] = nd.cbf_cr[1]; cabac.bin(ctx[CTX_CBF_CHROMA + nd.depth], cr[1]); } }
+      } else { cb[0] = parent_cb[0]; cb[1] = parent_cb[1]; cr[0] = parent_cr[0]; cr[1] = parent_cr[1]; }
     }
     if (nd.split) { for (int k = 0; k < 4; k++) write_tree(cu, nd.child[k], cb, cr, max_depth); return; }
     cabac.bin(ctx[CTX_CBF_LUMA + (nd.depth == 0 ? 1 : 0)], nd.cbf_l);
-    bool cbf_chroma = chroma && (cb || cr);
+    bool cbf_chroma = chroma && (cb[0] || cb[1] || cr[0] || cr[1]);
     if ((nd.cbf_l || cbf_chroma) && P.cu_qp_delta && !is_qp_delta_coded) {
       int v = cu_qp_delta_val, a = std::abs(v);
       for (int k = 0; k < std::min(a, 5); k++) cabac.bin(ctx[CTX_QP_DELTA + (k ? 1 : 0)], 1);
@@ -929,12 +937,14 @@ class Encoder {
     }
     if (nd.cbf_l) write_residual(nd.l->lev, nd.log2n, 0, nd.l->scan, nd.l->tskip);
     if (chroma) {
-      if (nd.log2n > 2) {
-        if (cb) write_residual(nd.cb->lev, nd.log2n - 1, 1, nd.cb->scan, nd.cb->tskip);
-        if (cr) write_residual(nd.cr->lev, nd.log2n - 1, 2, nd.cr->scan, nd.cr->tskip);
+      const int nb = cfmt == 2 ? 2 : 1;
+      if (nd.log2n > 2 || cfmt == 3) {
+        const int lc = cfmt == 3 ? nd.log2n : nd.log2n - 1;
+        for (int t = 0; t < nb; t++) if (cb[t]) write_residual(nd.cb[t]->lev, lc, 1, nd.cb[t]->scan, nd.cb[t]->tskip);
+        for (int t = 0; t < nb; t++) if (cr[t]) write_residual(nd.cr[t]->lev, lc, 2, nd.cr[t]->scan, nd.cr[t]->tskip);
       } else if (nd.blk == 3) {
-        if (parent_cb) write_residual(nd.cb->lev, 2, 1, nd.cb->scan, nd.cb->tskip);
-        if (parent_cr) write_residual(nd.cr->lev, 2, 2, nd.cr->scan, nd.cr->tskip);
+        for (int t = 0; t < nb; t++) if (parent_cb[t]) write_residual(nd.cb[t]->lev, 2, 1, nd.cb[t]->scan, nd.cb[t]->tskip);
+        for (int t = 0; t < nb; t++) if (parent_cr[t]) write_residual(nd.cr[t]->lev, 2, 2, nd.cr[t]->scan, nd.cr[t]->tskip);
       }
     }
   }
@@ -982,10 +992,10 @@ class Encoder {
       cabac.terminate(pcm ? 1 : 0);                   // pcm_flag (terminate bin); value 1: flush, stop bit, pcm_alignment_zero_bits
       if (pcm) {
         for (int c = 0; c < (chroma ? 3 : 1); c++) {
-          const int sh = c ? 1 : 0, pbd = c ? pcm_bd_c : pcm_bd_y, st = stride_of(c), m = n >> sh;
+          const int shx = c ? sx : 0, shy = c ? sy : 0, pbd = c ? pcm_bd_c : pcm_bd_y, st = stride_of(c);
           uint16_t* rq = rec[c].data();
-          for (int y = 0; y < m; y++) for (int x = 0; x < m; x++) {
-            const size_t idx = (size_t)((y0 >> sh) + y) * st + (x0 >> sh) + x;
+          for (int y = 0; y < (n >> shy); y++) for (int x = 0; x < (n >> shx); x++) {
+            const size_t idx = (size_t)((y0 >> shy) + y) * st + (x0 >> shx) + x;
             const unsigned v = org[c][idx] >> (bd - pbd);
             cabac.bw.put(v, pbd);                     // pcm_sample_luma / pcm_sample_chroma
             rq[idx] = (uint16_t)(v << (bd - pbd));
@@ -1029,11 +1039,17 @@ class Encoder {
       else cabac.bypass_bits(rem[i], 5);
     }
     if (chroma) {
+      // intra_chroma_pred_mode: one per prediction unit in 4:4:4, else one per coding unit (7.3.8.5); 8.4.3 + Table 8-3 for 4:2:2
       static const uint8_t tab[4] = {0, 26, 10, 1};
-      int v = rng.range(8); if (v > 4) v = 4;
-      if (v < 4 && tab[v] == cu.lmode[0]) cu.cmode = 34; else cu.cmode = v == 4 ? cu.lmode[0] : tab[v];
-      cabac.bin(ctx[CTX_CHROMA_PRED], v != 4);
-      if (v != 4) cabac.bypass_bits(v, 2);
+      static const uint8_t k422[35] = {0, 1, 2, 2, 2, 2, 3, 5, 7, 8, 10, 11, 13, 15, 16, 18, 19, 20, 21, 22, 23, 23, 24, 24, 25, 25, 26, 27, 27, 28, 28, 29, 29, 30, 31};
+      for (int i = 0; i < (cfmt == 3 ? np : 1); i++) {
+        int v = rng.range(8); if (v > 4) v = 4;
+        int m = (v < 4 && tab[v] == cu.lmode[i]) ? 34 : (v == 4 ? cu.lmode[i] : tab[v]);
+        if (cfmt == 2) m = k422[m];
+        cu.cmode[i] = m;
+        cabac.bin(ctx[CTX_CHROMA_PRED], v != 4);
+        if (v != 4) cabac.bypass_bits(v, 2);
+      }
     }
     for (int yy = 0; yy < n; yy += 4) for (int xx = 0; xx < n; xx += 4) {
       size_t idx = (size_t)((y0 + yy) >> 2) * w4 + ((x0 + xx) >> 2);
@@ -1051,13 +1067,13 @@ class Encoder {
     int max_depth = max_th_depth + cu.nxn;
     int root = build_tree(cu, x0, y0, log2cb, 0, 0, max_depth, -1);
     bool any_cbf = false;
-    for (const Node& nd : nodes) if (!nd.split) any_cbf |= nd.cbf_l || (nd.cb && nd.cb->cbf) || (nd.cr && nd.cr->cbf);
+    for (const Node& nd : nodes) if (!nd.split) for (int t = 0; t < 2; t++) any_cbf |= nd.cbf_l || (nd.cb[t] && nd.cb[t]->cbf) || (nd.cr[t] && nd.cr[t]->cbf);
     if (P.cu_qp_delta && !is_qp_delta_coded && !any_cbf) {
       // nothing coded: the decoder will use the predicted QP (CuQpDeltaVal stays 0); pixels are pure prediction so
       // the reconstruction above is already what the decoder produces.
       cur_qpy = pred_qp;
     }
-    write_tree(cu, root, false, false, max_depth);
+    { const bool none[2] = {false, false}; write_tree(cu, root, none, none, max_depth); }
     for (TbResult* t : pool) delete t;
     pool.clear();
     for (int yy = 0; yy < n; yy += 4) for (int xx = 0; xx < n; xx += 4) qp4[(size_t)((y0 + yy) >> 2) * w4 + ((x0 + xx) >> 2)] = (int8_t)cur_qpy;
@@ -1125,7 +1141,8 @@ int b200_hevc_encode_intra(const b200_hevc_enc_params* p, const void* y, const v
   const uint16_t* src[3] = {nullptr, nullptr, nullptr}; int stride[3] = {0, 0, 0};
   const void* in[3] = {y, cb, cr};
   for (int c = 0; c < (p->chroma_format_idc ? 3 : 1); c++) {
-    int w = c ? (p->width + 1) / 2 : p->width, h = c ? (p->height + 1) / 2 : p->height;
+    const int csx = (p->chroma_format_idc == 1 || p->chroma_format_idc == 2) ? 1 : 0, csy = p->chroma_format_idc == 1 ? 1 : 0;
+    int w = c ? (p->width + (1 << csx) - 1) >> csx : p->width, h = c ? (p->height + (1 << csy) - 1) >> csy : p->height;
     size_t st = c ? c_stride : y_stride;
     tmp[c].resize((size_t)w * h);
     for (int yy = 0; yy < h; yy++) for (int xx = 0; xx < w; xx++)

@@ -52,9 +52,11 @@ inline void derive(const Lists& L, Factors& F) {
   for (int c = 0; c < 3; c++) {
     for (int i = 0; i < 16; i++) F.m[c][0][y4[i] * 4 + x4[i]] = L.list[0][c][i];
     for (int s = 1; s < 4; s++) {
-      const int mid = s == 3 ? 0 : c;              // 32x32: only matrixId 0 (intra) / 3 (inter) are coded; chroma 32x32 does not occur in 4:2:0
-      for (int i = 0; i < 64; i++) F.m[c][s][y8[i] * 8 + x8[i]] = L.list[s][mid][i];
-      F.dc[c][s] = s >= 2 ? L.dc[s][mid] : L.list[s][mid][0];
+      // 32x32: only matrixId 0 (intra) / 3 (inter) are coded; a 32x32 CHROMA block exists only in 4:4:4 and takes the 16x16 list of its
+      // matrixId, replicated 4x4, with that list's DC coefficient (7.4.5, ChromaArrayType == 3)
+      const int ls = (s == 3 && c > 0) ? 2 : s, mid = (s == 3 && c == 0) ? 0 : c;
+      for (int i = 0; i < 64; i++) F.m[c][s][y8[i] * 8 + x8[i]] = L.list[ls][mid][i];
+      F.dc[c][s] = s >= 2 ? L.dc[ls][mid] : L.list[ls][mid][0];
     }
   }
 }

@@ -42,7 +42,10 @@ def encode_intra(y, cb=None, cr=None, **kw) -> bytes:
     if chroma:
         cb = np.ascontiguousarray(cb, dtype=dt)
         cr = np.ascontiguousarray(cr, dtype=dt)
-    p = default_params(width=w, height=h, chroma_format_idc=1 if chroma else 0, **kw)
+    cfmt = 0
+    if chroma:                                             # chroma format from the plane shapes (4:2:0 / 4:2:2 / 4:4:4)
+        cfmt = 3 if cb.shape == y.shape else (2 if cb.shape[0] == h else 1)
+    p = default_params(width=w, height=h, chroma_format_idc=cfmt, **kw)
     out = C.POINTER(C.c_uint8)()
     n = C.c_size_t()
     l.b200_hevc_encode_intra.argtypes = [C.POINTER(EncParams), C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t,
@@ -56,7 +59,7 @@ def encode_intra(y, cb=None, cr=None, **kw) -> bytes:
     return data
 
 
-def synthetic_image(seed: int, width: int, height: int, bit_depth: int = 8, chroma: bool = True):
+def synthetic_image(seed: int, width: int, height: int, bit_depth: int = 8, chroma=True):
     """Source picture of SURVEY.md 8(d): smooth gradient + 8 random-oriented sinusoid gratings + 1/16-amplitude noise,
     all driven by the 32-bit LCG s = s*1664525 + 1013904223 seeded with `seed`."""
     s = seed & 0xFFFFFFFF
@@ -69,10 +72,13 @@ def synthetic_image(seed: int, width: int, height: int, bit_depth: int = 8, chro
     maxv = (1 << bit_depth) - 1
     yy, xx = np.mgrid[0:height, 0:width].astype(np.float32)
     planes = []
-    for c in range(3 if chroma else 1):
-        sub = 2 if c else 1
-        h, w = (height + sub - 1) // sub, (width + sub - 1) // sub
-        X, Y = xx[:h, :w] * sub, yy[:h, :w] * sub
+    # chroma: False / 0 = 4:0:0, True / 1 = 4:2:0, 2 = 4:2:2, 3 = 4:4:4 (chroma_format_idc)
+    cfmt = int(chroma)
+    for c in range(3 if cfmt else 1):
+        subx = 2 if (c and cfmt in (1, 2)) else 1
+        suby = 2 if (c and cfmt == 1) else 1
+        h, w = (height + suby - 1) // suby, (width + subx - 1) // subx
+        X, Y = xx[:h, :w] * subx, yy[:h, :w] * suby
         gx, gy = (nxt() % 200 - 100) / 100.0, (nxt() % 200 - 100) / 100.0
         img = 0.5 + 0.25 * (gx * (X / max(width, 1) - 0.5) + gy * (Y / max(height, 1) - 0.5))
         for _ in range(8):

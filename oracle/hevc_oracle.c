@@ -264,7 +264,7 @@ static int parse_sps(const uint8_t* rbsp, size_t n, sps_t* s) {
       if (f[0] || f[1] || f[2] || f[4] || f[5] || f[7] || f[8]) return HO_UNSUPPORTED;
     }
   }
-  if (s->chroma_format_idc > 1) return HO_UNSUPPORTED;
+  if (s->chroma_format_idc > 3) return HO_ERROR;
   if (s->bit_depth != s->bit_depth_c || s->bit_depth > 12) return HO_UNSUPPORTED;
   if (s->log2_ctb > 6 || s->log2_ctb < 4 || s->log2_max_tb > 5) return HO_ERROR;
   s->valid = 1;
@@ -391,6 +391,7 @@ typedef struct {
   sps_t sps[16]; pps_t pps[64];
   const sps_t* s; const pps_t* p;
   int W, H, Wc, Hc;             /* coded plane sizes */
+  int cfmt, sx, sy;             /* ChromaArrayType; log2 of SubWidthC / SubHeightC (Table 6-1) */
   int ctb, wctb, hctb;
   int min_cb_w, min_cb_h;       /* in min-CB units */
   int w4, h4;                   /* in 4x4 units */
@@ -566,7 +567,7 @@ static void intra_predict(dec_t* d, int c, int x0, int y0, int log2n, int mode) 
   const int n = 1 << log2n, bd = d->s->bit_depth;
   uint16_t* pl = d->pl[c];
   const int st = d->stride[c];
-  const int sh = c ? 1 : 0;                 /* 4:2:0 chroma subsampling shift */
+  const int shx = c ? d->sx : 0, shy = c ? d->sy : 0;     /* chroma subsampling shifts */
   int refbuf[4 * 32 + 1], fbuf[4 * 32 + 1];
   uint8_t av[4 * 32 + 1];
   /* linear neighbour array: index 0 = p[-1][2n-1] (bottom of left column) ... 2n = p[-1][-1] ... 4n = p[2n-1][-1] */
@@ -576,7 +577,7 @@ static void intra_predict(dec_t* d, int c, int x0, int y0, int log2n, int mode) 
     if (i < 2 * n) { px = x0 - 1; py = y0 + 2 * n - 1 - i; }
     else if (i == 2 * n) { px = x0 - 1; py = y0 - 1; }
     else { px = x0 + (i - 2 * n - 1); py = y0 - 1; }
-    av[i] = avail4(d, px << sh, py << sh);          /* 8.4.4.2.2 via 6.4.1 on the luma location */
+    av[i] = avail4(d, px << shx, py << shy);        /* 8.4.4.2.2 via 6.4.1 on the luma location */
     if (av[i]) { refbuf[i] = pl[py * st + px]; any = 1; }
   }
   if (!any) { for (int i = 0; i <= 4 * n; i++) refbuf[i] = 1 << (bd - 1); }   /* 8.4.4.2.2 substitution */
@@ -588,12 +589,12 @@ static void intra_predict(dec_t* d, int c, int x0, int y0, int log2n, int mode) 
   }
   int* ref = refbuf;
   /* 8.4.4.2.3 filtering of neighbouring samples (luma only for 4:2:0) */
-  if (c == 0 && mode != 1 && n != 4) {
+  if ((c == 0 || d->cfmt == 3) && mode != 1 && n != 4) {     /* luma, and chroma when ChromaArrayType == 3 */
     int dist = iabs(mode - 26) < iabs(mode - 10) ? iabs(mode - 26) : iabs(mode - 10);
     int thr = n == 8 ? 7 : (n == 16 ? 1 : 0);
     if (dist > thr) {
       int corner = ref[2 * n], bl = ref[0], tr = ref[4 * n];
-      if (d->s->strong_intra_smoothing && n == 32 &&
+      if (d->s->strong_intra_smoothing && c == 0 && n == 32 &&
           iabs(corner + tr - 2 * ref[2 * n + n]) < (1 << (bd - 5)) &&
           iabs(corner + bl - 2 * ref[2 * n - n]) < (1 << (bd - 5))) {
         fbuf[2 * n] = corner; fbuf[0] = bl; fbuf[4 * n] = tr;
@@ -661,7 +662,7 @@ static const uint8_t level_scale[6] = {40, 45, 51, 57, 64, 72};
 static int chroma_qp(const dec_t* d, int qpy, int off) {                     /* 8.6.1, ChromaArrayType 1 */
   int qbd = 6 * (d->s->bit_depth - 8);
   int qpi = clip3(-qbd, 57, qpy + off);
-  int qpc = qpi < 30 ? qpi : (qpi >= 43 ? qpi - 6 : qpc_tab[qpi - 30]);
+  int qpc = d->cfmt != 1 ? (qpi < 51 ? qpi : 51) : (qpi < 30 ? qpi : (qpi >= 43 ? qpi - 6 : qpc_tab[qpi - 30]));   /* Table 8-10 only when ChromaArrayType == 1 */
   return qpc + qbd;
 }
 
@@ -683,7 +684,7 @@ static void residual_coding(dec_t* d, int x0, int y0, int log2n, int c, int pred
   if (ly > 3) { int nb = (ly >> 1) - 1; ly = (1 << nb) * (2 + (ly & 1)) + dec_bypass_bits(d, nb); }
   /* scanIdx, 7.4.9.11 */
   int scan = 0;
-  if (log2n == 2 || (log2n == 3 && c == 0)) {
+  if (log2n == 2 || (log2n == 3 && (c == 0 || d->cfmt == 3))) {
     if (pred_mode >= 6 && pred_mode <= 14) scan = 2;
     else if (pred_mode >= 22 && pred_mode <= 30) scan = 1;
   }
@@ -776,7 +777,7 @@ static void residual_coding(dec_t* d, int x0, int y0, int log2n, int c, int pred
       if (sign_hidden) { sum_abs += absl; if (k == first_sig && (sum_abs & 1)) v = -v; }
       int xc = (xs << 2) + px[k], yc = (ys << 2) + py[k];
       coef[yc * n + xc] = (int16_t)clip3(-32768, 32767, v);
-      { unsigned long long hh = ((unsigned long long)(x0 << (c ? 1 : 0)) * 1000003ULL + (unsigned long long)(y0 << (c ? 1 : 0))) * 1000003ULL + (unsigned long long)c; hh = hh * 1000003ULL + (unsigned long long)(yc * n + xc); hh = hh * 1000003ULL + (unsigned long long)(unsigned short)coef[yc * n + xc]; hh ^= hh >> 29; hh *= 0x9E3779B97F4A7C15ULL; d->coef_hash += hh; d->coef_count++; }
+      { unsigned long long hh = ((unsigned long long)(x0 << (c ? d->sx : 0)) * 1000003ULL + (unsigned long long)(y0 << (c ? d->sy : 0))) * 1000003ULL + (unsigned long long)c; hh = hh * 1000003ULL + (unsigned long long)(yc * n + xc); hh = hh * 1000003ULL + (unsigned long long)(unsigned short)coef[yc * n + xc]; hh ^= hh >> 29; hh *= 0x9E3779B97F4A7C15ULL; d->coef_hash += hh; d->coef_count++; }
       nsig++;
     }
   }
@@ -799,15 +800,16 @@ static void residual_coding(dec_t* d, int x0, int y0, int log2n, int c, int pred
   for (int k = 0; k < n * n; k++) if (coef[k]) {
     int m = 16;
     if (sl) {
-      const int sizeId = log2n - 2, matrixId = sizeId == 3 ? 0 : c, x = k & (n - 1), y = k >> log2n;
-      const int l2 = sizeId == 0 ? 2 : 3, rep = sizeId <= 1 ? 0 : sizeId - 1;     /* replication shift of the 8x8 list */
+      /* 32x32 chroma (ChromaArrayType == 3 only): the 16x16 list of its matrixId, replicated 4x4, with that list's DC (7.4.5) */
+      const int sizeId = (log2n == 5 && c > 0) ? 2 : log2n - 2, matrixId = (log2n == 5 && c == 0) ? 0 : c, x = k & (n - 1), y = k >> log2n;
+      const int l2 = sizeId == 0 ? 2 : 3, rep = log2n <= 3 ? 0 : log2n - 3;        /* replication shift of the 8x8 list */
       const int xs = x >> rep, ys = y >> rep;
       /* scan index i of (xs, ys) in the up-right diagonal scan of the (1 << l2) square (6.5.3) */
       int i = 0;
       { int xx = 0, yy = 0, found = 0, sz = 1 << l2;
         while (!found) { while (yy >= 0 && !found) { if (xx < sz && yy < sz) { if (xx == xs && yy == ys) found = 1; else i++; } if (!found) { yy--; xx++; } } if (!found) { yy = xx; xx = 0; } } }
       m = sl[sizeId][matrixId][i];
-      if (sizeId >= 2 && x == 0 && y == 0) m = sldc[sizeId][matrixId];
+      if (log2n >= 4 && x == 0 && y == 0) m = sldc[sizeId][matrixId];
     }
     long long t = ((long long)coef[k] * m * scale + (1LL << (bd_shift - 1))) >> bd_shift;
     coef[k] = (int16_t)(t < -32768 ? -32768 : (t > 32767 ? 32767 : t));
@@ -838,7 +840,7 @@ static void derive_qpy(dec_t* d, int xcb, int ycb) {
 }
 
 /* ---------------------------------------------------------------------------- transform tree etc. */
-typedef struct { int x0, y0, log2cb, part_nxn, luma_mode[4], chroma_mode; } cu_t;
+typedef struct { int x0, y0, log2cb, part_nxn, luma_mode[4], chroma_mode[4]; } cu_t;   /* chroma_mode: per prediction unit (one per PU only when ChromaArrayType == 3) */
 
 static void mark_tu(dec_t* d, int x0, int y0, int log2n) {
   int n4 = 1 << (log2n - 2), bx = x0 >> 2, by = y0 >> 2;
@@ -851,11 +853,13 @@ static void mark_tu(dec_t* d, int x0, int y0, int log2n) {
   }
 }
 
+/* cbf_cb / cbf_cr: the chroma flags that apply to this unit ([1]: lower block of a 4:2:2 unit) -- its own, or for a 4x4 luma block in
+   4:2:0 / 4:2:2 those of the parent 8x8 node (7.3.8.10) */
 static void transform_unit(dec_t* d, cu_t* cu, int x0, int y0, int xb, int yb, int log2n, int depth, int blk,
-                           int cbf_luma, int cbf_cb, int cbf_cr, int cbf_cb_parent, int cbf_cr_parent) {
-  const int chroma = d->s->chroma_format_idc == 1;
-  int cbf_chroma = (log2n > 2) ? (cbf_cb | cbf_cr) : (cbf_cb_parent | cbf_cr_parent);
-  if (!chroma) cbf_chroma = 0;
+                           int cbf_luma, const int cbf_cb[2], const int cbf_cr[2]) {
+  const int cfmt = d->cfmt;
+  int cbf_chroma = cfmt ? (cbf_cb[0] | cbf_cb[1] | cbf_cr[0] | cbf_cr[1]) : 0;
+  (void)depth;
   if ((cbf_luma || cbf_chroma) && d->p->cu_qp_delta && !d->is_cu_qp_delta_coded) {   /* 7.3.8.10 */
     int v = 0;
     while (v < 5 && dec_bin(d, CTX_QP_DELTA + (v ? 1 : 0))) v++;
@@ -867,30 +871,33 @@ static void transform_unit(dec_t* d, cu_t* cu, int x0, int y0, int xb, int yb, i
   }
   int pu = cu->part_nxn ? ((y0 >= cu->y0 + (1 << (cu->log2cb - 1))) ? 2 : 0) + ((x0 >= cu->x0 + (1 << (cu->log2cb - 1))) ? 1 : 0) : 0;
   int lmode = cu->luma_mode[pu];
+  int cmode = cu->chroma_mode[cfmt == 3 ? pu : 0];
   d->tu_count++;
-  { int n4 = 1 << (log2n - 2); for (int yy = 0; yy < n4; yy++) for (int xx = 0; xx < n4; xx++) d->cmode4[((y0 >> 2) + yy) * d->w4 + (x0 >> 2) + xx] = (uint8_t)cu->chroma_mode; }
+  { int n4 = 1 << (log2n - 2); for (int yy = 0; yy < n4; yy++) for (int xx = 0; xx < n4; xx++) d->cmode4[((y0 >> 2) + yy) * d->w4 + (x0 >> 2) + xx] = (uint8_t)cmode; }
   /* luma: 8.4.4.1 predict, then residual */
   intra_predict(d, 0, x0, y0, log2n, lmode);
   if (cbf_luma) residual_coding(d, x0, y0, log2n, 0, lmode);
   mark_tu(d, x0, y0, log2n);
-  if (chroma) {
-    int cmode = cu->chroma_mode;
-    if (log2n > 2) {
-      for (int c = 1; c <= 2; c++) {
-        intra_predict(d, c, x0 >> 1, y0 >> 1, log2n - 1, cmode);
-        if (c == 1 ? cbf_cb : cbf_cr) residual_coding(d, x0 >> 1, y0 >> 1, log2n - 1, c, cmode);
+  if (cfmt) {
+    const int nb = cfmt == 2 ? 2 : 1;               /* 4:2:2: two square blocks, the lower one predicted from the reconstructed upper one */
+    if (log2n > 2 || cfmt == 3) {
+      const int lc = cfmt == 3 ? log2n : log2n - 1, cx = x0 >> d->sx, cy = y0 >> d->sy;
+      for (int c = 1; c <= 2; c++) for (int t = 0; t < nb; t++) {
+        intra_predict(d, c, cx, cy + (t << lc), lc, cmode);
+        if ((c == 1 ? cbf_cb : cbf_cr)[t]) residual_coding(d, cx, cy + (t << lc), lc, c, cmode);
       }
     } else if (blk == 3) {
-      for (int c = 1; c <= 2; c++) {
-        intra_predict(d, c, xb >> 1, yb >> 1, 2, cmode);
-        if (c == 1 ? cbf_cb_parent : cbf_cr_parent) residual_coding(d, xb >> 1, yb >> 1, 2, c, cmode);
+      const int cx = xb >> d->sx, cy = yb >> d->sy;
+      for (int c = 1; c <= 2; c++) for (int t = 0; t < nb; t++) {
+        intra_predict(d, c, cx, cy + (t << 2), 2, cmode);
+        if ((c == 1 ? cbf_cb : cbf_cr)[t]) residual_coding(d, cx, cy + (t << 2), 2, c, cmode);
       }
     }
   }
 }
 
 static void transform_tree(dec_t* d, cu_t* cu, int x0, int y0, int xb, int yb, int log2n, int depth, int blk,
-                           int parent_cbf_cb, int parent_cbf_cr, int max_depth) {
+                           const int parent_cbf_cb[2], const int parent_cbf_cr[2], int max_depth) {
   const sps_t* s = d->s;
   int split;
   int intra_split = cu->part_nxn;
@@ -898,12 +905,13 @@ static void transform_tree(dec_t* d, cu_t* cu, int x0, int y0, int xb, int yb, i
     split = dec_bin(d, CTX_SPLIT_TR + 5 - log2n);
   else
     split = (log2n > s->log2_max_tb || (intra_split && depth == 0)) ? 1 : 0;
-  int cbf_cb = 0, cbf_cr = 0;
-  if (s->chroma_format_idc == 1) {
-    if (log2n > 2) {
-      if (depth == 0 || parent_cbf_cb) cbf_cb = dec_bin(d, CTX_CBF_CHROMA + depth);
-      if (depth == 0 || parent_cbf_cr) cbf_cr = dec_bin(d, CTX_CBF_CHROMA + depth);
-    } else { cbf_cb = parent_cbf_cb; cbf_cr = parent_cbf_cr; }   /* inferred from parent when log2 == 2 */
+  int cbf_cb[2] = {0, 0}, cbf_cr[2] = {0, 0};
+  if (d->cfmt) {
+    if (log2n > 2 || d->cfmt == 3) {                 /* 7.3.8.8 */
+      const int two = d->cfmt == 2 && (!split || log2n == 3);
+      if (depth == 0 || parent_cbf_cb[0]) { cbf_cb[0] = dec_bin(d, CTX_CBF_CHROMA + depth); if (two) cbf_cb[1] = dec_bin(d, CTX_CBF_CHROMA + depth); }
+      if (depth == 0 || parent_cbf_cr[0]) { cbf_cr[0] = dec_bin(d, CTX_CBF_CHROMA + depth); if (two) cbf_cr[1] = dec_bin(d, CTX_CBF_CHROMA + depth); }
+    } else { cbf_cb[0] = parent_cbf_cb[0]; cbf_cb[1] = parent_cbf_cb[1]; cbf_cr[0] = parent_cbf_cr[0]; cbf_cr[1] = parent_cbf_cr[1]; }   /* 4x4 luma: the parent's */
   }
   if (split) {
     int h = 1 << (log2n - 1);
@@ -911,8 +919,7 @@ static void transform_tree(dec_t* d, cu_t* cu, int x0, int y0, int xb, int yb, i
       transform_tree(d, cu, x0 + (k & 1) * h, y0 + (k >> 1) * h, x0, y0, log2n - 1, depth + 1, k, cbf_cb, cbf_cr, max_depth);
   } else {
     int cbf_luma = dec_bin(d, CTX_CBF_LUMA + (depth == 0 ? 1 : 0));
-    if (log2n > 2) transform_unit(d, cu, x0, y0, xb, yb, log2n, depth, blk, cbf_luma, cbf_cb, cbf_cr, 0, 0);
-    else transform_unit(d, cu, x0, y0, xb, yb, log2n, depth, blk, cbf_luma, 0, 0, parent_cbf_cb, parent_cbf_cr);
+    transform_unit(d, cu, x0, y0, xb, yb, log2n, depth, blk, cbf_luma, cbf_cb, cbf_cr);
   }
 }
 
@@ -953,11 +960,11 @@ static void coding_unit(dec_t* d, int x0, int y0, int log2cb, int cq_depth) {
     /* pcm_flag = 1 (7.3.8.5): pcm_alignment_zero_bits, pcm_sample(), then the arithmetic decoder starts over (9.3.2.5) */
     d->br.pos = (d->br.pos + 7) & ~(size_t)7;
     for (int c = 0; c < (s->chroma_format_idc ? 3 : 1); c++) {
-      int sh = c ? 1 : 0, pbd = c ? s->pcm_bd_c : s->pcm_bd_y, bdc = c ? s->bit_depth_c : s->bit_depth, m = n >> sh;
-      for (int y = 0; y < m; y++) for (int x = 0; x < m; x++) {
+      int shx = c ? d->sx : 0, shy = c ? d->sy : 0, pbd = c ? s->pcm_bd_c : s->pcm_bd_y, bdc = c ? s->bit_depth_c : s->bit_depth, mw = n >> shx, mh = n >> shy;
+      for (int y = 0; y < mh; y++) for (int x = 0; x < mw; x++) {
         unsigned v = rd_bits(&d->br, pbd);
-        d->pl[c][((y0 >> sh) + y) * d->stride[c] + (x0 >> sh) + x] = (uint16_t)(v << (bdc - pbd));       /* 8.4.4.1: recSamples = pcm_sample << (BitDepth - PcmBitDepth) */
-        { unsigned long long hh = ((unsigned long long)x0 * 1000003ULL + (unsigned long long)y0) * 1000003ULL + (unsigned long long)c; hh = hh * 1000003ULL + (unsigned long long)(y * m + x); hh = hh * 1000003ULL + (unsigned long long)(unsigned short)(v << (bdc - pbd)); hh ^= hh >> 29; hh *= 0x9E3779B97F4A7C15ULL; d->coef_hash += hh; d->coef_count++; }
+        d->pl[c][((y0 >> shy) + y) * d->stride[c] + (x0 >> shx) + x] = (uint16_t)(v << (bdc - pbd));       /* 8.4.4.1: recSamples = pcm_sample << (BitDepth - PcmBitDepth) */
+        { unsigned long long hh = ((unsigned long long)x0 * 1000003ULL + (unsigned long long)y0) * 1000003ULL + (unsigned long long)c; hh = hh * 1000003ULL + (unsigned long long)(y * mw + x); hh = hh * 1000003ULL + (unsigned long long)(unsigned short)(v << (bdc - pbd)); hh ^= hh >> 29; hh *= 0x9E3779B97F4A7C15ULL; d->coef_hash += hh; d->coef_count++; }
       }
     }
     cabac_init_engine(d);
@@ -992,12 +999,19 @@ static void coding_unit(dec_t* d, int x0, int y0, int log2cb, int cq_depth) {
     for (int yy = 0; yy < pb; yy += 4) for (int xx = 0; xx < pb; xx += 4)
       if (px + xx < d->W && py + yy < d->H) d->slice_of4[((py + yy) >> 2) * d->w4 + ((px + xx) >> 2)] = (uint16_t)(d->slice_idx + 1);
   }
-  if (s->chroma_format_idc == 1) {
-    int v = 4;
-    if (dec_bin(d, CTX_CHROMA_PRED)) v = dec_bypass_bits(d, 2);
+  if (d->cfmt) {
+    /* intra_chroma_pred_mode: one per prediction unit when ChromaArrayType == 3, else one (7.3.8.5); 8.4.3, and Table 8-3
+       (the 4:2:2 mapping of the mode to the half-width sample grid) */
     static const uint8_t tab[4] = {0, 26, 10, 1};
-    if (v == 4) cu.chroma_mode = cu.luma_mode[0];
-    else { cu.chroma_mode = tab[v]; if (cu.chroma_mode == cu.luma_mode[0]) cu.chroma_mode = 34; }
+    static const uint8_t mode422[35] = {0, 1, 2, 2, 2, 2, 3, 5, 7, 8, 10, 11, 13, 15, 16, 18, 19, 20, 21, 22, 23, 23, 24, 24, 25, 25, 26, 27, 27, 28, 28, 29, 29, 30, 31};
+    for (int i = 0; i < (d->cfmt == 3 ? np : 1); i++) {
+      int v = 4, m;
+      if (dec_bin(d, CTX_CHROMA_PRED)) v = dec_bypass_bits(d, 2);
+      if (v == 4) m = cu.luma_mode[i];
+      else { m = tab[v]; if (m == cu.luma_mode[i]) m = 34; }
+      if (d->cfmt == 2) m = mode422[m];
+      cu.chroma_mode[i] = m;
+    }
   }
   /* undo temporary marks */
   for (int yy = 0; yy < n; yy += 4) for (int xx = 0; xx < n; xx += 4)
@@ -1010,7 +1024,7 @@ static void coding_unit(dec_t* d, int x0, int y0, int log2cb, int cq_depth) {
   if (!d->p->cu_qp_delta) d->cur_qpy = d->slice_qp;
   else derive_qpy(d, x0, y0);
   int max_depth = s->max_th_depth_intra + cu.part_nxn;
-  transform_tree(d, &cu, x0, y0, x0, y0, log2cb, 0, 0, 0, 0, max_depth);
+  { const int none[2] = {0, 0}; transform_tree(d, &cu, x0, y0, x0, y0, log2cb, 0, 0, none, none, max_depth); }
   /* the whole CU carries its final QpY (8.6.1; used by deblocking and by QP prediction) */
   for (int yy = 0; yy < n; yy += 4) for (int xx = 0; xx < n; xx += 4)
     if (x0 + xx < d->W && y0 + yy < d->H) d->qp4[((y0 + yy) >> 2) * d->w4 + ((x0 + xx) >> 2)] = (int8_t)d->cur_qpy;
@@ -1096,7 +1110,8 @@ static int alloc_picture(dec_t* d) {
   d->ctb = 1 << s->log2_ctb;
   d->wctb = (d->W + d->ctb - 1) >> s->log2_ctb; d->hctb = (d->H + d->ctb - 1) >> s->log2_ctb;
   d->w4 = (d->W + 3) >> 2; d->h4 = (d->H + 3) >> 2;
-  d->Wc = s->chroma_format_idc ? d->W >> 1 : 0; d->Hc = s->chroma_format_idc ? d->H >> 1 : 0;
+  d->cfmt = s->chroma_format_idc; d->sx = (d->cfmt == 1 || d->cfmt == 2) ? 1 : 0; d->sy = d->cfmt == 1 ? 1 : 0;
+  d->Wc = d->cfmt ? d->W >> d->sx : 0; d->Hc = d->cfmt ? d->H >> d->sy : 0;
   d->stride[0] = d->W; d->stride[1] = d->stride[2] = d->Wc;
   d->pl[0] = (uint16_t*)calloc((size_t)d->W * d->H, 2);
   for (int c = 1; c < 3; c++) d->pl[c] = d->Wc ? (uint16_t*)calloc((size_t)d->Wc * d->Hc, 2) : NULL;
@@ -1311,17 +1326,19 @@ static void deblock_luma_edge(dec_t* d, int x, int y, int vert) {   /* one 4-sam
 #undef Q
 }
 
-static void deblock_chroma_edge(dec_t* d, int c, int x, int y, int vert) {  /* luma coords; 4 luma = 2 chroma samples */
+/* one 4-luma-sample segment of a chroma edge; (x, y) in luma samples.  Along the edge it covers 4 >> (sub-sampling along the edge) samples */
+static void deblock_chroma_edge(dec_t* d, int c, int x, int y, int vert) {
   uint16_t* pl = d->pl[c]; int st = d->stride[c], bd = d->s->bit_depth;
   int i = (y >> 2) * d->w4 + (x >> 2), j = vert ? i - 1 : i - d->w4;
   int sq = d->slice_of4[i] - 1;
   int off = c == 1 ? d->p->cb_qp_offset : d->p->cr_qp_offset;
   int qpi = ((d->qp4[i] + d->qp4[j] + 1) >> 1) + off;
-  int qpc = qpi < 30 ? qpi : (qpi >= 43 ? qpi - 6 : qpc_tab[qpi - 30]);
+  int qpc = d->cfmt != 1 ? (qpi < 51 ? qpi : 51) : (qpi < 30 ? qpi : (qpi >= 43 ? qpi - 6 : qpc_tab[qpi - 30]));     /* 8.7.2.5.5 */
   int tc = tc_tab[clip3(0, 53, qpc + 2 + d->sl[sq].tc_offset)] * (1 << (bd - 8));
   int xs = vert ? 1 : st, ls = vert ? st : 1, maxv = (1 << bd) - 1;
-  uint16_t* q = pl + (y >> 1) * st + (x >> 1);
-  for (int l = 0; l < 2; l++) {
+  uint16_t* q = pl + (y >> d->sy) * st + (x >> d->sx);
+  int len = 4 >> (vert ? d->sy : d->sx);
+  for (int l = 0; l < len; l++) {
     int p0 = q[-xs + l * ls], p1 = q[-2 * xs + l * ls], q0 = q[l * ls], q1 = q[xs + l * ls];
     int delta = clip3(-tc, tc, ((((q0 - p0) << 2) + p1 - q1 + 4) >> 3));
     if (!d->nofilt4[j]) q[-xs + l * ls] = (uint16_t)clip3(0, maxv, p0 + delta);
@@ -1335,7 +1352,8 @@ static void deblock_picture(dec_t* d) {
       if ((vert ? x : y) & 7) continue;             /* 8x8 luma grid */
       if (!edge_filtered(d, x, y, vert)) continue;
       deblock_luma_edge(d, x, y, vert);
-      if (d->s->chroma_format_idc == 1 && ((vert ? x : y) & 15) == 0) {   /* 8x8 chroma grid */
+      /* chroma edges lie on the 8x8 CHROMA sample grid (8.7.2.5): every 8 << sub-sampling luma samples across the edge */
+      if (d->cfmt && ((vert ? x : y) & ((8 << (vert ? d->sx : d->sy)) - 1)) == 0) {
         deblock_chroma_edge(d, 1, x, y, vert);
         deblock_chroma_edge(d, 2, x, y, vert);
       }
@@ -1348,17 +1366,17 @@ static void sao_picture(dec_t* d) {
   const sps_t* s = d->s;
   int ncomp = s->chroma_format_idc ? 3 : 1, bd = s->bit_depth, maxv = (1 << bd) - 1;
   for (int c = 0; c < ncomp; c++) {
-    int w = c ? d->Wc : d->W, h = c ? d->Hc : d->H, st = d->stride[c], sh = c ? 1 : 0;
+    int w = c ? d->Wc : d->W, h = c ? d->Hc : d->H, st = d->stride[c], shx = c ? d->sx : 0, shy = c ? d->sy : 0;
     uint16_t* src = (uint16_t*)malloc((size_t)w * h * 2);
     memcpy(src, d->pl[c], (size_t)w * h * 2);      /* deblocked picture, read-only */
-    int cs = d->ctb >> sh;
+    int csx = d->ctb >> shx, csy = d->ctb >> shy;
     for (int ry = 0; ry < d->hctb; ry++) for (int rx = 0; rx < d->wctb; rx++) {
       const sao_params* sp = &d->sao[ry * d->wctb + rx];
       int on = d->ctb_slice_sao[ry * d->wctb + rx] & (c ? 2 : 1);
       if (!on || sp->type[c] == 0) continue;
-      for (int y = ry * cs; y < (ry + 1) * cs && y < h; y++) for (int x = rx * cs; x < (rx + 1) * cs && x < w; x++) {
+      for (int y = ry * csy; y < (ry + 1) * csy && y < h; y++) for (int x = rx * csx; x < (rx + 1) * csx && x < w; x++) {
         int v = src[y * st + x], idx;
-        if (d->nofilt4[((y << sh) >> 2) * d->w4 + ((x << sh) >> 2)]) continue;     /* 8.7.3: SaoTypeIdx treated as 0 for these samples */
+        if (d->nofilt4[((y << shy) >> 2) * d->w4 + ((x << shx) >> 2)]) continue;     /* 8.7.3: SaoTypeIdx treated as 0 for these samples */
         if (sp->type[c] == 1) {
           int k = ((v >> (bd - 5)) - sp->band_pos[c]) & 31;
           idx = k < 4 ? k + 1 : 0;
@@ -1368,15 +1386,15 @@ static void sao_picture(dec_t* d) {
           int xa = x + hp[e][0], ya = y + vp[e][0], xb = x + hp[e][1], yb = y + vp[e][1];
           if (xa < 0 || xb < 0 || ya < 0 || yb < 0 || xa >= w || xb >= w || ya >= h || yb >= h) continue;
           /* slice boundary rule of 8.7.3.2 */
-          int cur = d->slice_of4[((y << sh) >> 2) * d->w4 + ((x << sh) >> 2)] - 1;
-          int sa = d->slice_of4[((ya << sh) >> 2) * d->w4 + ((xa << sh) >> 2)] - 1;
-          int sb = d->slice_of4[((yb << sh) >> 2) * d->w4 + ((xb << sh) >> 2)] - 1;
+          int cur = d->slice_of4[((y << shy) >> 2) * d->w4 + ((x << shx) >> 2)] - 1;
+          int sa = d->slice_of4[((ya << shy) >> 2) * d->w4 + ((xa << shx) >> 2)] - 1;
+          int sb = d->slice_of4[((yb << shy) >> 2) * d->w4 + ((xb << shx) >> 2)] - 1;
           int skip = 0;
           if (sa != cur) { if (sa < cur ? !d->sl[cur].lf_across : !d->sl[sa].lf_across) skip = 1; }
           if (sb != cur) { if (sb < cur ? !d->sl[cur].lf_across : !d->sl[sb].lf_across) skip = 1; }
           if (d->p->tiles && !d->p->lf_across_tiles) {           /* 8.7.3.2: a neighbouring sample in a different tile */
-            int tcur = tile_of_xy(d, x << sh, y << sh);
-            if (tile_of_xy(d, xa << sh, ya << sh) != tcur || tile_of_xy(d, xb << sh, yb << sh) != tcur) skip = 1;
+            int tcur = tile_of_xy(d, x << shx, y << shy);
+            if (tile_of_xy(d, xa << shx, ya << shy) != tcur || tile_of_xy(d, xb << shx, yb << shy) != tcur) skip = 1;
           }
           if (skip) continue;
           int a = src[ya * st + xa], b2 = src[yb * st + xb];
@@ -1435,13 +1453,13 @@ int hevc_oracle_decode(const uint8_t* data, size_t size, int stage, hevc_oracle_
     if (stage != 1) deblock_picture(d);
     if (stage == 0 && d->s->sao) sao_picture(d);
     const sps_t* s = d->s;
-    int sub = s->chroma_format_idc ? 2 : 1;
-    int x0 = s->conf_l * sub, y0 = s->conf_t * sub;
-    int w = d->W - (s->conf_l + s->conf_r) * sub, h = d->H - (s->conf_t + s->conf_b) * sub;
+    int subx = s->chroma_format_idc ? 1 << d->sx : 1, suby = s->chroma_format_idc ? 1 << d->sy : 1;      /* conformance window units (7.4.3.2.1) */
+    int x0 = s->conf_l * subx, y0 = s->conf_t * suby;
+    int w = d->W - (s->conf_l + s->conf_r) * subx, h = d->H - (s->conf_t + s->conf_b) * suby;
     if (w <= 0 || h <= 0) rc = HO_ERROR;
     else {
       out->width = w; out->height = h; out->bit_depth = s->bit_depth; out->chroma_format = s->chroma_format_idc;
-      out->cw = s->chroma_format_idc ? (w + 1) / 2 : 0; out->ch = s->chroma_format_idc ? (h + 1) / 2 : 0;
+      out->cw = s->chroma_format_idc ? (w + subx - 1) / subx : 0; out->ch = s->chroma_format_idc ? (h + suby - 1) / suby : 0;
       out->video_signal_present = s->vui_signal; out->full_range = s->vui_full_range;
       out->vui_colour_present = s->vui_colour;
       out->colour_primaries = s->vui_colour ? s->vui_cp : 2;
@@ -1452,7 +1470,7 @@ int hevc_oracle_decode(const uint8_t* data, size_t size, int stage, hevc_oracle_
       if (s->chroma_format_idc) for (int c = 1; c < 3; c++) {
         out->plane[c] = (uint16_t*)malloc((size_t)out->cw * out->ch * 2);
         for (int y = 0; y < out->ch; y++)
-          memcpy(out->plane[c] + (size_t)y * out->cw, d->pl[c] + (size_t)(y + y0 / 2) * d->Wc + x0 / 2, (size_t)out->cw * 2);
+          memcpy(out->plane[c] + (size_t)y * out->cw, d->pl[c] + (size_t)(y + y0 / suby) * d->Wc + x0 / subx, (size_t)out->cw * 2);
       }
     }
   }
