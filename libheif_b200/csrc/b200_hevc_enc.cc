@@ -1041,7 +1041,7 @@ class Encoder {
     if (chroma) {
       // intra_chroma_pred_mode: one per prediction unit in 4:4:4, else one per coding unit (7.3.8.5); 8.4.3 + Table 8-3 for 4:2:2
       static const uint8_t tab[4] = {0, 26, 10, 1};
-      static const uint8_t k422[35] = {0, 1, 2, 2, 2, 2, 3, 5, 7, 8, 10, 11, 13, 15, 16, 18, 19, 20, 21, 22, 23, 23, 24, 24, 25, 25, 26, 27, 27, 28, 28, 29, 29, 30, 31};
+      static const uint8_t k422[35] = {0, 1, 2, 2, 2, 2, 3, 5, 7, 8, 10, 12, 13, 15, 17, 18, 19, 20, 21, 22, 23, 23, 24, 24, 25, 25, 26, 27, 27, 28, 28, 29, 29, 30, 31};
       for (int i = 0; i < (cfmt == 3 ? np : 1); i++) {
         int v = rng.range(8); if (v > 4) v = 4;
         int m = (v < 4 && tab[v] == cu.lmode[i]) ? 34 : (v == 4 ? cu.lmode[i] : tab[v]);

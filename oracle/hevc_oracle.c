@@ -1003,7 +1003,7 @@ static void coding_unit(dec_t* d, int x0, int y0, int log2cb, int cq_depth) {
     /* intra_chroma_pred_mode: one per prediction unit when ChromaArrayType == 3, else one (7.3.8.5); 8.4.3, and Table 8-3
        (the 4:2:2 mapping of the mode to the half-width sample grid) */
     static const uint8_t tab[4] = {0, 26, 10, 1};
-    static const uint8_t mode422[35] = {0, 1, 2, 2, 2, 2, 3, 5, 7, 8, 10, 11, 13, 15, 16, 18, 19, 20, 21, 22, 23, 23, 24, 24, 25, 25, 26, 27, 27, 28, 28, 29, 29, 30, 31};
+    static const uint8_t mode422[35] = {0, 1, 2, 2, 2, 2, 3, 5, 7, 8, 10, 12, 13, 15, 17, 18, 19, 20, 21, 22, 23, 23, 24, 24, 25, 25, 26, 27, 27, 28, 28, 29, 29, 30, 31};   /* Table 8-3 as corrected in the later editions (modeIdc 11 -> 12, 14 -> 17); every entry checked against FFmpeg */
     for (int i = 0; i < (d->cfmt == 3 ? np : 1); i++) {
       int v = 4, m;
       if (dec_bin(d, CTX_CHROMA_PRED)) v = dec_bypass_bits(d, 2);
