@@ -299,6 +299,7 @@ int b200_decoder_decode_grid(b200_decoder* d, int cols, int rows, const uint8_t*
       return set_error(B200_E_UNSUPPORTED, "grid tiles differ in size or format (tile %d)", i);   // grid.cc:261-375 requires equal tiles
   }
   if (chroma && ((tw | th) & 1) && n > 1) return set_error(B200_E_UNSUPPORTED, "odd-sized 4:2:0 grid tiles");
+  if (chroma >= 2) return set_error(B200_E_UNSUPPORTED, "4:2:2 / 4:4:4 coded pictures: the reconstruction kernels handle 4:2:0 and 4:0:0 (the host front-end parses them)");
   const int cw = canvas_w > 0 ? canvas_w : tw * cols, chh = canvas_h > 0 ? canvas_h : th * rows;
   size_t n_ctu = 0, n_tu = 0, n_coef = 0, n_slice = 0, n_map = 0, n_rows = 0, rec_bytes = 0, bits = 0, n_rbsp = 0, n_subs = 0, n_map4 = 0;
   d->rec_off.resize((size_t)n * 3);
@@ -787,20 +788,28 @@ extern "C" int b200_debug_parse(const uint8_t* au, size_t size, int8_t* qp8, uin
     const TuCmd& t = pp.tus[ti];
     const int x4 = t.w0 & 0xfff, y4 = (t.w0 >> 12) & 0xfff, log2n = 2 + ((t.w0 >> 24) & 3), n4 = 1 << (log2n - 2);
     const int lm = t.w1 & 63, cm = (t.w1 >> 6) & 63;
+    const int comp = (int)((t.w1 >> 23) & 3);            // 4:2:2 / 4:4:4: one command per block; 0 = luma block (or a 4:2:0 / 4:0:0 unit)
+    if (p.chroma >= 2) {
+      const int sx = p.chroma == 2 ? 1 : 0;
+      if (comp == 0) { for (int y = 0; y < n4; y++) for (int x = 0; x < n4; x++) lmode4[(size_t)(y4 + y) * w4 + x4 + x] = (uint8_t)lm; }
+      else for (int y = 0; y < n4; y++) for (int x = 0; x < (n4 << sx); x++) cmode4[(size_t)(y4 + y) * w4 + x4 + x] = (uint8_t)lm;
+    } else
     for (int y = 0; y < n4; y++) for (int x = 0; x < n4; x++) { lmode4[(size_t)(y4 + y) * w4 + x4 + x] = (uint8_t)lm; cmode4[(size_t)(y4 + y) * w4 + x4 + x] = (uint8_t)cm; }
     const int nl = ((t.w0 >> 26) & 1) ? (int)(t.w3 & 0x7ff) : 0, ncb = ((t.w0 >> 27) & 1) ? (int)((t.w3 >> 11) & 0x3ff) : 0, ncr = ((t.w0 >> 28) & 1) ? (int)((t.w3 >> 21) & 0x3ff) : 0;
     const CoefEntry* ce = pp.coefs.data() + t.w2;
     int cx = x4 << 2, cy = y4 << 2;
-    if (log2n == 2) { cx -= 4; cy -= 4; }     // chroma of the parent 8x8 node
+    if (log2n == 2 && p.chroma < 2) { cx -= 4; cy -= 4; }     // chroma of the parent 8x8 node
     for (int k = 0; k < nl + ncb + ncr; k++) {
-      const int c = k < nl ? 0 : (k < nl + ncb ? 1 : 2);
+      const int c = comp ? comp : (k < nl ? 0 : (k < nl + ncb ? 1 : 2));
       const unsigned long long bx = c ? (unsigned long long)cx : (unsigned long long)(x4 << 2), by = c ? (unsigned long long)cy : (unsigned long long)(y4 << 2);
       unsigned long long hh = (bx * 1000003ULL + by) * 1000003ULL + (unsigned long long)c;
       hh = hh * 1000003ULL + ce[k].pos; hh = hh * 1000003ULL + (unsigned long long)(unsigned short)ce[k].level;
       hh ^= hh >> 29; hh *= 0x9E3779B97F4A7C15ULL; hash += hh;
     }
   }
-  out5[0] = hash; out5[1] = pp.n_coefs; out5[2] = pp.n_tus; out5[3] = (unsigned long long)p.width; out5[4] = (unsigned long long)p.height;
+  size_t units = 0;                                  // transform units = luma blocks (4:2:2 / 4:4:4 commands are per block)
+  for (size_t ti = 0; ti < pp.n_tus; ti++) if (((pp.tus[ti].w1 >> 23) & 3) == 0) units++;
+  out5[0] = hash; out5[1] = pp.n_coefs; out5[2] = units; out5[3] = (unsigned long long)p.width; out5[4] = (unsigned long long)p.height;
   return B200_OK;
 }
 

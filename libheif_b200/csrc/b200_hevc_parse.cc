@@ -28,7 +28,7 @@ struct BitRd {
 };
 
 struct Sps {
-  bool valid = false; int chroma_format_idc = 1, width = 0, height = 0, conf_l = 0, conf_r = 0, conf_t = 0, conf_b = 0;
+  bool valid = false; int separate_colour_plane = 0; int chroma_format_idc = 1, width = 0, height = 0, conf_l = 0, conf_r = 0, conf_t = 0, conf_b = 0;
   int bit_depth = 8, log2_max_poc_lsb = 4, log2_min_cb = 3, log2_ctb = 4, log2_min_tb = 2, log2_max_tb = 5, max_th_depth_intra = 0;
   int sao = 0, strong_intra = 0, num_st_rps = 0, long_term = 0, num_lt_sps = 0, temporal_mvp = 0;
   int st_num_delta[65] = {0};
@@ -166,7 +166,7 @@ class HeaderParser {
     unsigned id = b.ue(); if (id > 15) return set_error(B200_E_BITSTREAM, "sps id");
     // every ue(v) is range-checked BEFORE it is used in arithmetic (a saturated code is 0xffffffff): 7.4.3.2.1 ranges
     { const unsigned v = b.ue(); if (v > 3) return set_error(B200_E_BITSTREAM, "chroma_format_idc"); s.chroma_format_idc = (int)v; }
-    if (s.chroma_format_idc == 3) b.bit();
+    if (s.chroma_format_idc == 3) s.separate_colour_plane = b.bit();
     { const unsigned w = b.ue(), h = b.ue(); if (w == 0 || h == 0 || w > 16384 || h > 16384) return set_error(B200_E_BITSTREAM, "picture size %ux%u", w, h); s.width = (int)w; s.height = (int)h; }
     if (b.bit()) {
       const unsigned cl = b.ue(), cr = b.ue(), ct = b.ue(), cbm = b.ue();
@@ -225,7 +225,7 @@ class HeaderParser {
       int range = b.bit(); b.bits(7);
       if (range) { int f[9]; for (int i = 0; i < 9; i++) f[i] = b.bit(); if (f[0] || f[1] || f[2] || f[4] || f[5] || f[7] || f[8]) return set_error(B200_E_UNSUPPORTED, "range-extension coding tools are not supported"); }
     }
-    if (s.chroma_format_idc > 1) return set_error(B200_E_UNSUPPORTED, "chroma_format_idc %d (only 4:2:0 and 4:0:0)", s.chroma_format_idc);
+    if (s.chroma_format_idc == 3 && s.separate_colour_plane) return set_error(B200_E_UNSUPPORTED, "separate_colour_plane_flag");
     if (s.bit_depth != bdc || s.bit_depth > 12) return set_error(B200_E_UNSUPPORTED, "bit depth luma %d chroma %d", s.bit_depth, bdc);
     if (b.overrun()) return set_error(B200_E_BITSTREAM, "sequence parameter set is truncated");
     if (s.log2_ctb > 6 || s.log2_ctb < 4 || s.log2_max_tb > 5 || s.log2_min_cb > s.log2_ctb || s.log2_max_tb > s.log2_ctb) return set_error(B200_E_BITSTREAM, "block size configuration");
@@ -290,9 +290,9 @@ class HeaderParser {
     PicDesc& d = P.desc; memset(&d, 0, sizeof d);
     d.width = W; d.height = H; d.log2_ctb = log2ctb; d.wctb = (W + ctb - 1) >> log2ctb; d.hctb = (H + ctb - 1) >> log2ctb;
     d.bit_depth = S->bit_depth; d.chroma = S->chroma_format_idc;
-    const int sub = d.chroma ? 2 : 1;
-    d.crop_x = S->conf_l * sub; d.crop_y = S->conf_t * sub;
-    d.out_w = W - (S->conf_l + S->conf_r) * sub; d.out_h = H - (S->conf_t + S->conf_b) * sub;
+    const int sub = (d.chroma == 1 || d.chroma == 2) ? 2 : 1, subh = d.chroma == 1 ? 2 : 1;      // SubWidthC, SubHeightC: conformance window units
+    d.crop_x = S->conf_l * sub; d.crop_y = S->conf_t * subh;
+    d.out_w = W - (S->conf_l + S->conf_r) * sub; d.out_h = H - (S->conf_t + S->conf_b) * subh;
     if (d.out_w <= 0 || d.out_h <= 0) return set_error(B200_E_BITSTREAM, "conformance window");
     d.strong_intra = S->strong_intra; d.sao_enabled = S->sao; d.w8 = W >> 3; d.h8 = H >> 3;
     d.scaling_idx = -1;
@@ -337,7 +337,8 @@ class HeaderParser {
     q.tiles = PP->tiles;
     q.sign_hiding = PP->sign_hiding; q.wpp = PP->wpp; q.sao_scale_luma = PP->log2_sao_scale_luma; q.sao_scale_chroma = PP->log2_sao_scale_chroma;
     const int ctb = 1 << d.log2_ctb;
-    q.tu_slots = (ctb / 4) * (ctb / 4); q.coef_slots = ctb * ctb * (d.chroma ? 3 : 2) / 2;
+    q.tu_slots = (ctb / 4) * (ctb / 4) * (d.chroma >= 2 ? 3 : 1);          // 4:2:2 / 4:4:4: every chroma block is a command of its own
+    q.coef_slots = d.chroma == 3 ? ctb * ctb * 3 : (d.chroma == 2 ? ctb * ctb * 2 : ctb * ctb * (d.chroma ? 3 : 2) / 2);
   }
 
   // 7.3.6.1 slice_segment_header; then the split of the segment data into sub-streams
@@ -548,7 +549,7 @@ int parse_access_unit(const uint8_t* data, size_t size, const ParseLimits& limit
   out.desc = H.desc;
   syn::SeqParams sp = H.sp; sp.dense = 1;
   const size_t nctb = (size_t)H.desc.wctb * H.desc.hctb, n8 = (size_t)H.desc.w8 * H.desc.h8, n4 = n8 * 4;
-  const size_t tu_cap = (size_t)H.desc.width * H.desc.height / 16, coef_cap = (size_t)H.desc.width * H.desc.height * (H.desc.chroma ? 3 : 2) / 2;
+  const size_t tu_cap = (size_t)H.desc.width * H.desc.height / 16 * (H.desc.chroma >= 2 ? 3 : 1), coef_cap = (size_t)H.desc.width * H.desc.height * (H.desc.chroma == 3 ? 6 : (H.desc.chroma == 2 ? 4 : (H.desc.chroma ? 3 : 2))) / 2;
   if (out.ctus.size() < nctb) out.ctus.resize(nctb);
   if (out.tus.size() < tu_cap) out.tus.resize(tu_cap);
   if (out.coefs.size() < coef_cap) out.coefs.resize(coef_cap);

@@ -316,7 +316,7 @@ struct DecoderT {
   int cur_ctb_x, cur_ctb_y;
   int ctb_x0, ctb_y0, left_ok, up_ok;            // current CTB: origin, availability of the CTB to the left / above (same region: slice and tile)
   int left_lf, up_lf;                            // deblocking across the CTB's left / upper boundary is allowed (8.7.2.3: slice and tile rules)
-  struct Cu { int x0, y0, log2cb, nxn, lmode[4], cmode; };
+  struct Cu { int x0, y0, log2cb, nxn, lmode[4], cmode; int cmodes[4]; };   // cmodes: IntraPredModeC per prediction unit (4:4:4: one per PU; 4:2:2: [0], after Table 8-3)
 
   // 6.4.1 for the LEFT (x - 1, y) or ABOVE (x, y - 1) neighbour of a position inside the current CTB -- the only queries
   // the intra syntax makes.  Such a neighbour precedes the block in decoding order, so it is available iff it lies in the
@@ -413,7 +413,7 @@ struct DecoderT {
       if (xy) ly = l; else lx = l;
     }
     int scan = 0;
-    if (log2n == 2 || (log2n == 3 && c == 0)) { if (mode >= 6 && mode <= 14) scan = 2; else if (mode >= 22 && mode <= 30) scan = 1; }
+    if (log2n == 2 || (log2n == 3 && (c == 0 || B200_SPC(chroma) == 3))) { if (mode >= 6 && mode <= 14) scan = 2; else if (mode >= 22 && mode <= 30) scan = 1; }
     if (scan == 2) { const int t = lx; lx = ly; ly = t; }
     if (lx >= n || ly >= n) { err = SYN_E_BITSTREAM; cabac = cb_; return 0; }
     const int l2sb = log2n - 2;
@@ -598,6 +598,84 @@ struct DecoderT {
     }
   }
 
+  // -------- 4:2:2 / 4:4:4 (chroma_format_idc 2 / 3): the same walk, with the chroma structure of 7.3.8.8 / 7.3.8.10 -- two
+  // cbf_cb / cbf_cr flags per unit and two square chroma blocks one above the other in 4:2:2, chroma blocks down to 4x4 at
+  // every leaf in 4:4:4.  Out of line, so that the 4:2:0 path above keeps its size.  Command stream: the luma block of a
+  // unit is a TuCmd without chroma (chroma_here = 0); every chroma block is a TuCmd of its own that looks like a luma one
+  // (position = its luma location, size, cbf, transform skip, mode, QpY, coefficients) with the component in w1 bits 23-24.
+  B200_HD inline void emit_block(int comp, int lx, int ly, int log2n, int coded, int ts, int mode, uint32_t coef0, int nnz, uint32_t flags = 0) {
+    if (tu_n >= tu_cap) { err = SYN_E_OVERFLOW; return; }
+    TuCmd t;
+    t.w0 = (uint32_t)(lx >> 2) | ((uint32_t)(ly >> 2) << 12) | ((uint32_t)(log2n - 2) << 24) | ((uint32_t)coded << 26) | ((uint32_t)ts << 30);
+    t.w1 = (uint32_t)mode | ((uint32_t)mode << 6) | ((uint32_t)(cur_qpy + 64) << 12) | ((B200_SPC(tq_bypass) && cu_bypass) ? 1u << 22 : 0u) | ((uint32_t)comp << 23) | flags;
+    t.w2 = coef0; t.w3 = (uint32_t)nnz;
+    pb.tus[tu_n++] = t;
+  }
+  B200_HDN void transform_unit_x(const Cu& cu, int x0, int y0, int xb, int yb, int log2n, int blk, int cbf_l, unsigned fcb, unsigned fcr) {
+    const int cfmt = B200_SPC(chroma), sx = cfmt == 3 ? 0 : 1;           // (SubHeightC is 1 in both formats)
+    if ((cbf_l || fcb || fcr) && B200_SPC(cu_qp_delta) && !is_dqp_coded) {
+      int v = 0;
+      B200_NOUNROLL while (v < 5 && dbin(CTX_QP_DELTA + (v ? 1 : 0))) v++;
+      if (v == 5) { int k = 0; B200_NOUNROLL while (k < 16 && dbypass()) { v += 1 << k; k++; } v += (int)dbits(k); }
+      if (v && dbypass()) v = -v;
+      { const int half = 3 * (B200_SPC(bd) - 8); if (v < -(26 + half) || v > 25 + half) { err = SYN_E_BITSTREAM; return; } }
+      is_dqp_coded = 1; dqp_val = v;
+      derive_qpy(cu.x0, cu.y0);
+    }
+    const int pu = cu.nxn ? ((y0 >= cu.y0 + (1 << (cu.log2cb - 1))) ? 2 : 0) + ((x0 >= cu.x0 + (1 << (cu.log2cb - 1))) ? 1 : 0) : 0;
+    const int lmode = cu.lmode[pu], cmode = cu.cmodes[cfmt == 3 ? pu : 0];
+    { int ts = 0; const uint32_t c0 = coef_n; const int cnt = cbf_l ? residual(log2n, 0, lmode, ts) : 0; emit_block(0, x0, y0, log2n, cbf_l, ts, lmode, c0, cnt); }
+    mark_tu(x0, y0, log2n);
+    int lc, cx, cy;                                                       // chroma block size; luma location of the (upper) chroma block
+    if (log2n > 2 || cfmt == 3) { lc = cfmt == 3 ? log2n : log2n - 1; cx = x0; cy = y0; }
+    else if (blk == 3) { lc = 2; cx = xb; cy = yb; }
+    else return;
+    const int nb = cfmt == 2 ? 2 : 1;
+    B200_NOUNROLL for (int c = 1; c <= 2; c++) B200_NOUNROLL for (int t = 0; t < nb; t++) {
+      const int coded = (int)(((c == 1 ? fcb : fcr) >> t) & 1u);
+      int ts = 0; const uint32_t c0 = coef_n;
+      const int cnt = coded ? residual(lc, c, cmode, ts) : 0;
+      if (err) return;
+      emit_block(c, cx, cy + (t << lc), lc, coded, ts, cmode, c0, cnt);   // (4:2:2: chroma rows = luma rows, so the lower block sits lc rows down in luma terms too)
+    }
+    (void)sx;
+  }
+  B200_HDN void transform_tree_x(const Cu& cu, int max_depth) {
+    const int cfmt = B200_SPC(chroma);
+    const int levels = cu.log2cb - 2, total = 1 << (2 * levels);
+    unsigned cbm = 0, crm = 0;                          // cbf_cb / cbf_cr of the node on the current path: 2 bits per depth (bit 1: lower 4:2:2 block)
+    B200_NOUNROLL for (int j = 0; j < total && !err;) {
+      int depth = node_depth((unsigned)j, levels);
+      B200_NOUNROLL for (;;) {
+        const int log2n = cu.log2cb - depth;
+        const int x0 = cu.x0 + (zx((unsigned)j) << 2), y0 = cu.y0 + (zx((unsigned)j >> 1) << 2);
+        const int blk = depth ? (j >> (2 * (levels - depth))) & 3 : 0;
+        const unsigned pcb = depth ? (cbm >> (2 * (depth - 1))) & 3u : 0u, pcr = depth ? (crm >> (2 * (depth - 1))) & 3u : 0u;
+        int split;
+        if (log2n <= B200_SPC(log2_max_tb) && log2n > B200_SPC(log2_min_tb) && depth < max_depth && !(cu.nxn && depth == 0)) split = dbin(CTX_SPLIT_TR + 5 - log2n);
+        else split = (log2n > B200_SPC(log2_max_tb) || (cu.nxn && depth == 0)) ? 1 : 0;
+        if (split && log2n <= 2) { err = SYN_E_BITSTREAM; break; }
+        unsigned cb = 0, cr = 0;
+        if (log2n > 2 || cfmt == 3) {
+          const bool two = cfmt == 2 && (!split || log2n == 3);
+          B200_NOUNROLL for (int k = 0; k < 2; k++) {
+            unsigned f = 0;
+            if (depth == 0 || ((k ? pcr : pcb) & 1u)) { f = (unsigned)dbin(CTX_CBF_CHROMA + depth); if (two) f |= (unsigned)dbin(CTX_CBF_CHROMA + depth) << 1; }
+            if (k) cr = f; else cb = f;
+          }
+        } else { cb = pcb; cr = pcr; }                 // 4x4 luma blocks of an 8x8 node (4:2:2): the node's flags
+        cbm = (cbm & ~(3u << (2 * depth))) | (cb << (2 * depth)); crm = (crm & ~(3u << (2 * depth))) | (cr << (2 * depth));
+        if (split) { depth++; continue; }
+        const int cl = dbin(CTX_CBF_LUMA + (depth == 0 ? 1 : 0));
+        const int half = 1 << log2n;                  // parent origin of a depth > 0 node
+        const int xb = x0 & ~((half << 1) - 1), yb = y0 & ~((half << 1) - 1);
+        transform_unit_x(cu, x0, y0, xb, yb, log2n, blk, cl, cb, cr);
+        j += 1 << (2 * (levels - depth));
+        break;
+      }
+    }
+  }
+
   // -------- 8.4.2
   B200_HDN int luma_mode(int x, int y, int prev, int mpm_idx, int rem) const {
     int ca = 1, cb = 1;
@@ -628,8 +706,9 @@ struct DecoderT {
 #endif
   }
   B200_HDN void pcm_unit(int x0, int y0, int log2cb, int depth) {
-    const int n = 1 << log2cb, chroma = B200_SPC(chroma) ? 1 : 0;
-    const uint32_t nl = (uint32_t)(n * n), nc = chroma ? nl >> 2 : 0;
+    const int n = 1 << log2cb, cfmt = B200_SPC(chroma), chroma = cfmt ? 1 : 0;
+    const int sx = (cfmt == 1 || cfmt == 2) ? 1 : 0, sy = cfmt == 1 ? 1 : 0;
+    const uint32_t nl = (uint32_t)(n * n), nc = chroma ? nl >> (sx + sy) : 0;
     uint32_t p = (uint32_t)((cabac.bit_position() + 7) >> 3);          // pcm_alignment_zero_bit
     const uint64_t nbits = (uint64_t)nl * (uint32_t)sp->pcm_bd_y + 2ull * nc * (uint32_t)sp->pcm_bd_c;     // a multiple of 8
     if ((uint64_t)p * 8 + nbits > (uint64_t)stream.size * 8) { err = SYN_E_BITSTREAM; return; }
@@ -657,12 +736,39 @@ struct DecoderT {
       pb.cd8[i8] = (uint8_t)depth; pb.qp8[i8] = (int8_t)cur_qpy; pb.edge8[i8] |= (uint8_t)nofilt;
     }
     last_cu_qpy = cur_qpy;
+    if (cfmt >= 2) {                                   // 4:2:2 / 4:4:4: one command per block, like transform_unit_x
+      emit_block(0, x0, y0, log2cb, 1, 0, 1, coef0, (int)nl, 1u << 21);
+      B200_NOUNROLL for (int c = 1; c <= 2; c++) {
+        const uint32_t o = coef0 + nl + (uint32_t)(c - 1) * nc;
+        if (cfmt == 3) emit_block(c, x0, y0, log2cb, 1, 0, 1, o, (int)nc, 1u << 21);
+        else { emit_block(c, x0, y0, log2cb - 1, 1, 0, 1, o, (int)(nc >> 1), 1u << 21); emit_block(c, x0, y0 + (n >> 1), log2cb - 1, 1, 0, 1, o + (nc >> 1), (int)(nc >> 1), 1u << 21); }
+      }
+      return;
+    }
     TuCmd t;
     t.w0 = (uint32_t)(x0 >> 2) | ((uint32_t)(y0 >> 2) << 12) | ((uint32_t)(log2cb - 2) << 24) | (1u << 26) | ((uint32_t)chroma << 27) | ((uint32_t)chroma << 28) | ((uint32_t)chroma << 29);
     t.w1 = 1u | (1u << 6) | ((uint32_t)(cur_qpy + 64) << 12) | (1u << 21) | ((B200_SPC(tq_bypass) && cu_bypass) ? 1u << 22 : 0u);
     t.w2 = coef0;
     t.w3 = nl | (nc << 11) | (nc << 21);
     pb.tus[tu_n++] = t;
+  }
+
+  // intra_chroma_pred_mode for chroma_format_idc 2 / 3 (7.3.8.5, 8.4.3): one per prediction unit in 4:4:4; in 4:2:2 the mode goes
+  // through Table 8-3 (as corrected: modeIdc 11 -> 12, 14 -> 17), packed here 6 bits per entry
+  B200_HDN void chroma_modes_x(Cu& cu, int np) {
+    const int cfmt = B200_SPC(chroma);
+    B200_NOUNROLL for (int i = 0; i < (cfmt == 3 ? np : 1); i++) {
+      int v = 4; if (dbin(CTX_CHROMA_PRED)) v = (int)dbits(2);
+      int m;
+      if (v == 4) m = cu.lmode[i]; else { m = B200_T(kChromaTab)[v]; if (m == cu.lmode[i]) m = 34; }
+      if (cfmt == 2) {
+        // {0,1,2,2,2,2,3,5,7,8 | 10,12,13,15,17,18,19,20,21,22 | 23,23,24,24,25,25,26,27,27,28 | 28,29,29,30,31}
+        const unsigned long long w = m < 10 ? 0x207143082082040ull : (m < 20 ? 0x5955134913cd30aull : (m < 30 ? 0x71b6da6596185d7ull : 0x1f79d75cull));
+        m = (int)((w >> (6 * (m % 10))) & 63ull);
+      }
+      cu.cmodes[i] = m;
+    }
+    cu.cmode = cu.cmodes[0];
   }
 
   // -------- 7.3.8.5
@@ -687,13 +793,14 @@ struct DecoderT {
       cu.lmode[i] = m;
       B200_NOUNROLL for (int yy = 0; yy < pbs; yy += 4) B200_NOUNROLL for (int xx = 0; xx < pbs; xx += 4) pb.ipm4[((py + yy) >> 2) * sp->w4 + ((px + xx) >> 2)] = (uint8_t)m;
     }
-    if (B200_SPC(chroma)) {
+    if (B200_SPC(chroma) >= 2) chroma_modes_x(cu, np);
+    else if (B200_SPC(chroma)) {
       int v = 4; if (dbin(CTX_CHROMA_PRED)) v = (int)dbits(2);
       if (v == 4) cu.cmode = cu.lmode[0]; else { cu.cmode = B200_T(kChromaTab)[v]; if (cu.cmode == cu.lmode[0]) cu.cmode = 34; }
     }
     B200_NOUNROLL for (int yy = 0; yy < n; yy += 8) B200_NOUNROLL for (int xx = 0; xx < n; xx += 8) pb.cd8[((y0 + yy) >> 3) * sp->w8 + ((x0 + xx) >> 3)] = (uint8_t)depth;
     if (!B200_SPC(cu_qp_delta)) cur_qpy = ss->slice_qp; else derive_qpy(x0, y0);
-    transform_tree(cu, sp->max_th_depth_intra + cu.nxn);
+    if (B200_SPC(chroma) >= 2) transform_tree_x(cu, sp->max_th_depth_intra + cu.nxn); else transform_tree(cu, sp->max_th_depth_intra + cu.nxn);
     B200_NOUNROLL for (int yy = 0; yy < n; yy += 8) B200_NOUNROLL for (int xx = 0; xx < n; xx += 8) pb.qp8[((y0 + yy) >> 3) * sp->w8 + ((x0 + xx) >> 3)] = (int8_t)cur_qpy;
     last_cu_qpy = cur_qpy;
   }

@@ -964,7 +964,8 @@ static void coding_unit(dec_t* d, int x0, int y0, int log2cb, int cq_depth) {
       for (int y = 0; y < mh; y++) for (int x = 0; x < mw; x++) {
         unsigned v = rd_bits(&d->br, pbd);
         d->pl[c][((y0 >> shy) + y) * d->stride[c] + (x0 >> shx) + x] = (uint16_t)(v << (bdc - pbd));       /* 8.4.4.1: recSamples = pcm_sample << (BitDepth - PcmBitDepth) */
-        { unsigned long long hh = ((unsigned long long)x0 * 1000003ULL + (unsigned long long)y0) * 1000003ULL + (unsigned long long)c; hh = hh * 1000003ULL + (unsigned long long)(y * mw + x); hh = hh * 1000003ULL + (unsigned long long)(unsigned short)(v << (bdc - pbd)); hh ^= hh >> 29; hh *= 0x9E3779B97F4A7C15ULL; d->coef_hash += hh; d->coef_count++; }
+        { unsigned long long hy = (unsigned long long)(y0 + ((d->cfmt == 2 && c && y >= mw) ? mw : 0));   /* 4:2:2: the lower chroma block's own position */
+          unsigned long long hh = ((unsigned long long)x0 * 1000003ULL + hy) * 1000003ULL + (unsigned long long)c; hh = hh * 1000003ULL + (unsigned long long)(y * mw + x); hh = hh * 1000003ULL + (unsigned long long)(unsigned short)(v << (bdc - pbd)); hh ^= hh >> 29; hh *= 0x9E3779B97F4A7C15ULL; d->coef_hash += hh; d->coef_count++; }
       }
     }
     cabac_init_engine(d);

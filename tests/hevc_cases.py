@@ -86,6 +86,23 @@ SYNTH_CPU_EXTRA = [
     ("x_tiles_2x2_main12_dqp_slice_per_tile", 256, 192, 12, True, dict(log2_ctb_size=6, tile_cols=2, tile_rows=2, dqp_range=8, diff_cu_qp_delta_depth=2, slice_per_tile=1)),
     ("x_tiles_1x3_slices_nolf_across_slices", 136, 200, 8, True, dict(log2_ctb_size=5, tile_cols=1, tile_rows=3, slice_per_tile=1, slice_loop_filter_across_slices=0)),
     ("x_tiles_7x1_random_deep", 232, 72, 8, True, dict(log2_ctb_size=5, tile_cols=7, tile_rows=1, tiles_uniform=0, mode_decision=0, max_transform_hierarchy_depth_intra=3, transform_skip=1)),
+    # 4:2:2 and 4:4:4 coded pictures (chroma column: chroma_format_idc)
+    ("x_422_basic", 128, 96, 8, 2, dict(log2_ctb_size=5)),
+    ("x_444_basic", 128, 96, 8, 3, dict(log2_ctb_size=5)),
+    ("x_422_main10_random_tskip", 136, 72, 10, 2, dict(log2_ctb_size=5, mode_decision=0, max_transform_hierarchy_depth_intra=2, transform_skip=1)),
+    ("x_444_main10_ctb16_random_tskip", 136, 72, 10, 3, dict(log2_ctb_size=4, mode_decision=0, max_transform_hierarchy_depth_intra=2, transform_skip=1)),
+    ("x_422_main12_ctb64_deep_dqp", 200, 136, 12, 2, dict(log2_ctb_size=6, mode_decision=0, max_transform_hierarchy_depth_intra=4, qp=18, dqp_range=8)),
+    ("x_444_ctb64_deep_dqp", 200, 136, 8, 3, dict(log2_ctb_size=6, mode_decision=0, max_transform_hierarchy_depth_intra=4, qp=18, dqp_range=8)),
+    ("x_422_wpp_slices", 128, 128, 8, 2, dict(log2_ctb_size=5, wpp=1, slice_ctb_rows=2, qp=35)),
+    ("x_444_wpp_slices", 128, 128, 8, 3, dict(log2_ctb_size=5, wpp=1, slice_ctb_rows=2, qp=35)),
+    ("x_422_pcm_bypass_nosao", 96, 64, 8, 2, dict(log2_ctb_size=5, transquant_bypass=1, pcm=1, sao=0)),
+    ("x_444_pcm_bypass_nosao", 96, 64, 8, 3, dict(log2_ctb_size=4, transquant_bypass=1, pcm=1, sao=0)),
+    ("x_422_scaling_sps", 160, 96, 8, 2, dict(log2_ctb_size=5, scaling_lists=2, qp=20)),
+    ("x_444_scaling_pps_ctb64", 192, 128, 8, 3, dict(log2_ctb_size=6, scaling_lists=3, mode_decision=0, max_transform_hierarchy_depth_intra=1, qp=14)),
+    ("x_422_tiles_nolf", 128, 96, 8, 2, dict(log2_ctb_size=5, tile_cols=2, tile_rows=2, loop_filter_across_tiles=0)),
+    ("x_444_lossless", 72, 40, 8, 3, dict(log2_ctb_size=5, transquant_bypass=2, sao=0)),
+    ("x_422_lossless_main10", 72, 40, 10, 2, dict(log2_ctb_size=5, transquant_bypass=2)),
+    ("x_444_qp_offsets_pcm_nolf", 130, 70, 10, 3, dict(log2_ctb_size=5, mode_decision=0, cb_qp_offset=5, cr_qp_offset=-7, pcm=2)),
     ("x_slices_every_row_nolf_across", 192, 160, 8, True, dict(log2_ctb_size=5, slice_ctb_rows=1, loop_filter_across_slices=0, slice_loop_filter_across_slices=0)),
 ]
 

@@ -34,6 +34,8 @@ def ffmpeg_planes(name, nplanes):
         o = p[5]
         if o.get("pcm") and not p[4]:
             return []
+        if p[4] == 2 and o.get("log2_ctb_size") == 4 and o.get("sao", 1):
+            return [0]                                     # the CTB-16 chroma SAO deviation above, 4:2:2
         if o.get("sao", 1) and (o.get("transquant_bypass") or o.get("pcm") == 2):
             return [0]
     return list(range(nplanes))
