@@ -185,7 +185,7 @@ static int run_device_pipeline(b200_decoder* d, int n, cudaStream_t s, int* laun
   cudaEventRecord(d->ev[1], s);
   DeviceBatch b{};
   b.pics = d->pics.d; b.npics = n; b.ctus = d->ctus.d; b.tus = d->tus.d; b.coefs = d->coefs.d; b.slices = d->slices.d;
-  b.qp8 = d->qp8.d; b.edge8 = d->edge8.d; b.scaling = d->scaling.d; b.ticket = d->sync.d + 2 + 2 * d->n_rows; b.error_flag = d->sync.d + 1; b.progress = d->sync.d + 2; b.row_list = d->rows.d; b.nrows = (int)d->n_items; b.max_log2_ctb = d->max_log2_ctb; b.wide_samples = d->info_bps == 2;
+  b.qp8 = d->qp8.d; b.edge8 = d->edge8.d; b.scaling = d->scaling.d; b.ticket = d->sync.d + 2 + 3 * d->n_rows; b.error_flag = d->sync.d + 1; b.progress = d->sync.d + 2; b.row_list = d->rows.d; b.nrows = (int)d->n_items; b.max_log2_ctb = d->max_log2_ctb; b.wide_samples = d->info_bps == 2;
   if (devfe) {
     EntropyBatch e{};
     e.pics = d->epics.d; e.npics = d->npics; e.subs = d->subs.d; e.nsubs = (int)d->n_subs;
@@ -298,8 +298,8 @@ int b200_decoder_decode_grid(b200_decoder* d, int cols, int rows, const uint8_t*
     if (p.out_w != tw || p.out_h != th || p.bit_depth != bd || p.chroma != chroma)
       return set_error(B200_E_UNSUPPORTED, "grid tiles differ in size or format (tile %d)", i);   // grid.cc:261-375 requires equal tiles
   }
-  if (chroma && ((tw | th) & 1) && n > 1) return set_error(B200_E_UNSUPPORTED, "odd-sized 4:2:0 grid tiles");
-  if (chroma >= 2) return set_error(B200_E_UNSUPPORTED, "4:2:2 / 4:4:4 coded pictures: the reconstruction kernels handle 4:2:0 and 4:0:0 (the host front-end parses them)");
+  const int csx = (chroma == 1 || chroma == 2) ? 1 : 0, csy = chroma == 1 ? 1 : 0;          // chroma sub-sampling shifts (Table 6-1)
+  if (n > 1 && (((tw & 1) && csx) || ((th & 1) && csy))) return set_error(B200_E_UNSUPPORTED, "grid tiles of odd size with sub-sampled chroma");
   const int cw = canvas_w > 0 ? canvas_w : tw * cols, chh = canvas_h > 0 ? canvas_h : th * rows;
   size_t n_ctu = 0, n_tu = 0, n_coef = 0, n_slice = 0, n_map = 0, n_rows = 0, rec_bytes = 0, bits = 0, n_rbsp = 0, n_subs = 0, n_map4 = 0;
   d->rec_off.resize((size_t)n * 3);
@@ -315,7 +315,7 @@ int b200_decoder_decode_grid(b200_decoder* d, int cols, int rows, const uint8_t*
     else { n_tu += pp.n_tus; n_coef += pp.n_coefs; }
     bits += au_size[i];
     for (int c = 0; c < (chroma ? 3 : 1); c++) {
-      const int w = c ? p.width >> 1 : p.width, h = c ? p.height >> 1 : p.height;
+      const int w = c ? p.width >> csx : p.width, h = c ? p.height >> csy : p.height;
       const int st = (w + 63) & ~63;
       p.rec_stride[c] = st;
       d->rec_off[(size_t)i * 3 + c] = rec_bytes;
@@ -330,8 +330,8 @@ int b200_decoder_decode_grid(b200_decoder* d, int cols, int rows, const uint8_t*
   if ((rc = d->scaling.reserve((size_t)n_scaling * 784 + 16))) return rc;
   for (int i = 0; i < n; i++) { const ParsedPicture& pp = d->parsed[(size_t)i]; if (pp.desc.scaling_idx >= 0) memcpy(d->scaling.h + (size_t)pp.desc.scaling_idx * 784, &pp.hdr.scaling, sizeof(sl::Factors)); }
   if ((rc = d->pics.reserve((size_t)n)) || (rc = d->ctus.reserve(n_ctu, !devfe)) || (rc = d->tus.reserve(n_tu, !devfe)) || (rc = d->coefs.reserve(n_coef + 1, !devfe)) ||
-      (rc = d->slices.reserve(n_slice)) || (rc = d->qp8.reserve(n_map, !devfe)) || (rc = d->edge8.reserve(n_map, !devfe)) || (rc = d->rows.reserve(2 * n_rows)) ||
-      (rc = d->sync.reserve(2 * n_rows + 2 + MAX_CHUNKS, false)) || (rc = d->rec.reserve(rec_bytes, false)))
+      (rc = d->slices.reserve(n_slice)) || (rc = d->qp8.reserve(n_map, !devfe)) || (rc = d->edge8.reserve(n_map, !devfe)) || (rc = d->rows.reserve(3 * n_rows)) ||
+      (rc = d->sync.reserve(3 * n_rows + 2 + MAX_CHUNKS, false)) || (rc = d->rec.reserve(rec_bytes, false)))
     return rc;
   if (devfe && ((rc = d->rbsp.reserve(n_rbsp + 16)) || (rc = d->subs.reserve(n_subs)) || (rc = d->equeue.reserve(2 + 2 * n_subs)) || (rc = d->ctu_slice.reserve(n_ctu)) ||
                 (rc = d->epics.reserve((size_t)n)) || (rc = d->ipm4.reserve(n_map4, false)) || (rc = d->cd8.reserve(n_map, false)) ||
@@ -341,7 +341,7 @@ int b200_decoder_decode_grid(b200_decoder* d, int cols, int rows, const uint8_t*
   // canvas planes
   size_t cbytes = 0;
   for (int c = 0; c < (chroma ? 3 : 1); c++) {
-    const int w = c ? (cw + 1) >> 1 : cw, h = c ? (chh + 1) >> 1 : chh;
+    const int w = c ? (cw + csx) >> csx : cw, h = c ? (chh + csy) >> csy : chh;
     d->canvas_pitch[c] = (((size_t)w * bps) + 255) & ~(size_t)255;
     d->canvas_off[c] = cbytes; cbytes += d->canvas_pitch[c] * h;
   }
@@ -356,7 +356,7 @@ int b200_decoder_decode_grid(b200_decoder* d, int cols, int rows, const uint8_t*
     for (int c = 0; c < 3; c++) {
       if (c && !chroma) { p.rec[c] = nullptr; p.dst[c] = nullptr; continue; }
       p.rec[c] = d->rec.d + d->rec_off[(size_t)i * 3 + c];
-      const int sx = c ? px >> 1 : px, sy = c ? py >> 1 : py;
+      const int sx = c ? px >> csx : px, sy = c ? py >> csy : py;
       p.dst[c] = d->canvas.d + d->canvas_off[c] + (size_t)sy * d->canvas_pitch[c] + (size_t)sx * bps;
       p.dst_stride[c] = (int)(d->canvas_pitch[c] / bps);
     }
@@ -389,7 +389,8 @@ int b200_decoder_decode_grid(b200_decoder* d, int cols, int rows, const uint8_t*
       for (int i = d->chunk_pic[c]; i < d->chunk_pic[c + 1]; i++) max_h = std::max(max_h, d->parsed[(size_t)i].desc.hctb);
       for (int r = 0; r < max_h; r++) for (int i = d->chunk_pic[c]; i < d->chunk_pic[c + 1]; i++) if (r < d->parsed[(size_t)i].desc.hctb) {
         d->rows.h[row_cursor++] = make_uint2((unsigned)i, (unsigned)r);                                        // luma
-        if (chroma) d->rows.h[row_cursor++] = make_uint2((unsigned)i, (unsigned)r | 0x80000000u);              // Cb + Cr
+        if (chroma == 1) d->rows.h[row_cursor++] = make_uint2((unsigned)i, (unsigned)r | (1u << 30));           // Cb + Cr of a 4:2:0 picture on the two half-warps
+        else if (chroma >= 2) { d->rows.h[row_cursor++] = make_uint2((unsigned)i, (unsigned)r | (2u << 30)); d->rows.h[row_cursor++] = make_uint2((unsigned)i, (unsigned)r | (3u << 30)); }   // Cb, Cr planes (4:2:2 / 4:4:4)
       }
     }
     d->chunk_item[d->nchunks] = row_cursor;
@@ -469,11 +470,11 @@ int b200_decoder_decode_grid(b200_decoder* d, int cols, int rows, const uint8_t*
     B200_CUDA_CHECK(cudaMemsetAsync(d->ecount.d, 0, 2 * sizeof(unsigned long long), s));
     h2d += n_rbsp + n_subs * (sizeof(syn::Substream) + 2 * sizeof(unsigned)) + n_ctu * sizeof(uint16_t) + (size_t)n * sizeof(EntropyPic);
   }
-  B200_CUDA_CHECK(cudaMemsetAsync(d->sync.d, 0, (2 * n_rows + 2 + MAX_CHUNKS) * sizeof(unsigned), s));
+  B200_CUDA_CHECK(cudaMemsetAsync(d->sync.d, 0, (3 * n_rows + 2 + MAX_CHUNKS) * sizeof(unsigned), s));
   if (!canvas_fully_covered) B200_CUDA_CHECK(cudaMemsetAsync(d->canvas.d, 0, cbytes, s));     // uncovered canvas stays zero (calloc in the reference)
   d->n_rows = n_rows; d->cbytes = cbytes; d->canvas_fully_covered = canvas_fully_covered; d->npics = n; d->n_subs = n_subs; d->used_device_front_end = devfe;
   b200_image_info& inf = d->info;
-  inf.width = cw; inf.height = chh; inf.tile_width = tw; inf.tile_height = th; inf.chroma = chroma ? B200_CHROMA_420 : B200_CHROMA_MONO; inf.bit_depth = bd;
+  inf.width = cw; inf.height = chh; inf.tile_width = tw; inf.tile_height = th; inf.chroma = chroma;        /* B200_CHROMA_MONO / 420 / 422 / 444 = chroma_format_idc */ inf.bit_depth = bd;
   inf.colour_primaries = d->parsed[0].hdr.colour_primaries; inf.transfer_characteristics = d->parsed[0].hdr.transfer_characteristics;
   inf.matrix_coefficients = d->parsed[0].hdr.matrix_coefficients; inf.full_range = d->parsed[0].hdr.full_range;
   if (info) *info = inf;
@@ -497,7 +498,7 @@ int b200_decoder_decode_grid(b200_decoder* d, int cols, int rows, const uint8_t*
 int b200_decoder_rerun_device(b200_decoder* d, void* stream_) {
   if (!d || !d->have_result) return set_error(B200_E_INVALID, "no decode result");
   cudaStream_t s = (cudaStream_t)stream_;
-  B200_CUDA_CHECK(cudaMemsetAsync(d->sync.d, 0, (2 * d->n_rows + 2 + MAX_CHUNKS) * sizeof(unsigned), s));
+  B200_CUDA_CHECK(cudaMemsetAsync(d->sync.d, 0, (3 * d->n_rows + 2 + MAX_CHUNKS) * sizeof(unsigned), s));
   if (d->used_device_front_end) {
     B200_CUDA_CHECK(cudaMemsetAsync(d->esync.d, 0, (1 + d->n_rows + d->n_subs) * sizeof(unsigned), s));
     B200_CUDA_CHECK(cudaMemsetAsync(d->ecount.d, 0, 2 * sizeof(unsigned long long), s));
@@ -545,7 +546,8 @@ int b200_decoder_read_planes(b200_decoder* d, void* y, size_t ys, void* cb, void
   const int bps = d->info.bit_depth > 8 ? 2 : 1, w = d->info.width, h = d->info.height;
   B200_CUDA_CHECK(cudaMemcpy2DAsync(y, ys, d->canvas.d + d->canvas_off[0], d->canvas_pitch[0], (size_t)w * bps, h, cudaMemcpyDeviceToHost, s));
   if (d->info.chroma != B200_CHROMA_MONO && cb && cr) {
-    const int cw = (w + 1) >> 1, ch = (h + 1) >> 1;
+    const int fsx = (d->info.chroma == B200_CHROMA_420 || d->info.chroma == B200_CHROMA_422) ? 1 : 0, fsy = d->info.chroma == B200_CHROMA_420 ? 1 : 0;
+    const int cw = (w + fsx) >> fsx, ch = (h + fsy) >> fsy;
     B200_CUDA_CHECK(cudaMemcpy2DAsync(cb, cs, d->canvas.d + d->canvas_off[1], d->canvas_pitch[1], (size_t)cw * bps, ch, cudaMemcpyDeviceToHost, s));
     B200_CUDA_CHECK(cudaMemcpy2DAsync(cr, cs, d->canvas.d + d->canvas_off[2], d->canvas_pitch[2], (size_t)cw * bps, ch, cudaMemcpyDeviceToHost, s));
   }
@@ -562,7 +564,8 @@ int b200_decoder_debug_read_tile(b200_decoder* d, int index, int stage, void* y,
   B200_CUDA_CHECK(cudaStreamSynchronize(d->last_stream));
   for (int c = 0; c < (p.chroma ? 3 : 1); c++) {
     if (!outs[c]) continue;
-    const int w = c ? p.width >> 1 : p.width, h = c ? p.height >> 1 : p.height;
+    const int fsx = (p.chroma == 1 || p.chroma == 2) ? 1 : 0, fsy = p.chroma == 1 ? 1 : 0;
+    const int w = c ? p.width >> fsx : p.width, h = c ? p.height >> fsy : p.height;
     B200_CUDA_CHECK(cudaMemcpy2D(outs[c], (size_t)w * bps, p.rec[c], (size_t)p.rec_stride[c] * bps, (size_t)w * bps, h, cudaMemcpyDeviceToHost));
   }
   return B200_OK;
@@ -613,7 +616,8 @@ static int decode_to_rgb_device(b200_decoder* d, int cols, int rows, const uint8
       b200_planes pl; memset(&pl, 0, sizeof pl);
       pl.y = d->canvas.d + d->canvas_off[0] + (size_t)y0 * d->canvas_pitch[0]; pl.y_stride = d->canvas_pitch[0];
       if (I.chroma != B200_CHROMA_MONO) {
-        pl.cb = d->canvas.d + d->canvas_off[1] + (size_t)(y0 >> 1) * d->canvas_pitch[1]; pl.cr = d->canvas.d + d->canvas_off[2] + (size_t)(y0 >> 1) * d->canvas_pitch[2];
+        const int bsy = I.chroma == B200_CHROMA_420 ? 1 : 0;
+        pl.cb = d->canvas.d + d->canvas_off[1] + (size_t)(y0 >> bsy) * d->canvas_pitch[1]; pl.cr = d->canvas.d + d->canvas_off[2] + (size_t)(y0 >> bsy) * d->canvas_pitch[2];
         pl.c_stride = d->canvas_pitch[1];
       }
       pl.width = I.width; pl.height = y1 - y0; pl.chroma = I.chroma; pl.bit_depth = I.bit_depth;
@@ -749,7 +753,7 @@ int b200_probe_access_unit(const uint8_t* au, size_t size, uint64_t max_pixels, 
   if (rc) return rc;
   memset(info, 0, sizeof *info);
   info->width = info->tile_width = H.desc.out_w; info->height = info->tile_height = H.desc.out_h;
-  info->chroma = H.desc.chroma ? B200_CHROMA_420 : B200_CHROMA_MONO; info->bit_depth = H.desc.bit_depth;
+  info->chroma = H.desc.chroma; info->bit_depth = H.desc.bit_depth;       /* B200_CHROMA_* = chroma_format_idc */
   info->colour_primaries = H.colour_primaries; info->transfer_characteristics = H.transfer_characteristics;
   info->matrix_coefficients = H.matrix_coefficients; info->full_range = H.full_range;
   return B200_OK;

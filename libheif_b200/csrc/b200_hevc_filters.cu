@@ -90,18 +90,22 @@ __global__ void __launch_bounds__(256) deblock_kernel(const DeviceBatch b, int m
 #undef P_
 #undef Q_
   }
-  // chroma (4:2:0): edges on the 8-sample chroma grid = 16-sample luma grid, bS == 2 only (8.7.2.5.5 / 8.7.2.5.8)
-  if (pic.chroma && ((VERT ? x : y) & 15) == 0) {
+  // chroma: edges on the 8-sample CHROMA grid (every 16 luma samples where the chroma is sub-sampled across the edge), bS == 2 only
+  // (8.7.2.5.5 / 8.7.2.5.8); a 4-luma-sample segment covers 4 >> (sub-sampling along the edge) chroma samples
+  const int fsx = (pic.chroma == 1 || pic.chroma == 2) ? 1 : 0, fsy = pic.chroma == 1 ? 1 : 0;
+  if (pic.chroma && ((VERT ? x : y) & ((8 << (VERT ? fsx : fsy)) - 1)) == 0) {
+    const int len = 4 >> (VERT ? fsy : fsx);
     for (int c = 1; c <= 2; c++) {
       const int qpi = qpl + (c == 1 ? pic.pps_cb_qp_offset : pic.pps_cr_qp_offset);
-      const int qpc = qpi < 30 ? qpi : (qpi >= 43 ? qpi - 6 : c_qpc2[qpi - 30]);
+      const int qpc = pic.chroma != 1 ? min(qpi, 51) : (qpi < 30 ? qpi : (qpi >= 43 ? qpi - 6 : c_qpc2[qpi - 30]));   // Table 8-10 only when ChromaArrayType == 1
       const int tc = c_tc[clip3d(0, 53, qpc + 2 + sl.tc_offset)] * (1 << (bd - 8));
       T* pl = static_cast<T*>(pic.rec[c]);
       const int st = pic.rec_stride[c];
       const int xs = VERT ? 1 : st, ls = VERT ? st : 1;
-      T* q = pl + (size_t)(y >> 1) * st + (x >> 1);
+      T* q = pl + (size_t)(y >> fsy) * st + (x >> fsx);
 #pragma unroll
-      for (int l = 0; l < 2; l++) {
+      for (int l = 0; l < 4; l++) {
+        if (l >= len) break;
         T* ql = q + (ptrdiff_t)l * ls;
         const int p0 = ql[-(ptrdiff_t)xs], p1 = ql[-2 * (ptrdiff_t)xs], q0 = ql[0], q1 = ql[xs];
         const int delta = clip3d(-tc, tc, ((((q0 - p0) << 2) + p1 - q1 + 4) >> 3));
@@ -115,9 +119,9 @@ __global__ void __launch_bounds__(256) deblock_kernel(const DeviceBatch b, int m
 // SAO offset of ONE sample with every rule of 8.7.3 (picture bounds, slice boundaries with
 // slice_loop_filter_across_slices_enabled_flag): the path for pictures with more than one slice.
 template <typename T>
-__device__ __noinline__ int sao_sample_generic(const DeviceBatch& b, const PicDesc& pic, const CtuInfo* ctus, const T* src, int st, int c, int x, int y, int w, int h, int lg) {
+__device__ __noinline__ int sao_sample_generic(const DeviceBatch& b, const PicDesc& pic, const CtuInfo* ctus, const T* src, int st, int c, int x, int y, int w, int h, int lg, int lgy) {   // lg / lgy: log2 of the component's CTB width / height
   int v = src[(size_t)y * st + x];
-  const CtuInfo& ci = ctus[(y >> lg) * pic.wctb + (x >> lg)];
+  const CtuInfo& ci = ctus[(y >> lgy) * pic.wctb + (x >> lg)];
   const SaoComp sp = ci.sao[c];
   if (!pic.sao_enabled || !sp.type) return v;
   const int bd = pic.bit_depth, maxv = (1 << bd) - 1;
@@ -133,7 +137,7 @@ __device__ __noinline__ int sao_sample_generic(const DeviceBatch& b, const PicDe
       bool skip = false;
       const SliceInfo* sls = b.slices + pic.slice_base;
       const int cur = ci.slice_idx;
-      const int sa = ctus[(ya >> lg) * pic.wctb + (xa >> lg)].slice_idx, sb = ctus[(yb >> lg) * pic.wctb + (xb >> lg)].slice_idx;
+      const int sa = ctus[(ya >> lgy) * pic.wctb + (xa >> lg)].slice_idx, sb = ctus[(yb >> lgy) * pic.wctb + (xb >> lg)].slice_idx;
       // 8.7.3.2: a neighbour in another slice counts only if the later of the two slices filters across its boundary; one in another
       // tile only with loop_filter_across_tiles_enabled_flag (regions = slice x tile, compared through their slice / tile ids)
       const SliceInfo c0 = sls[cur];
@@ -157,22 +161,22 @@ __global__ void __launch_bounds__(256) sao_kernel(const DeviceBatch b) {
   const int pi = blockIdx.z / 3, c = blockIdx.z % 3;
   const PicDesc& pic = b.pics[pi];
   if (c > 0 && !pic.chroma) return;
-  const int sh = c ? 1 : 0;
-  const int w = pic.width >> sh, h = pic.height >> sh;
+  const int sh = (c && (pic.chroma == 1 || pic.chroma == 2)) ? 1 : 0, shy = (c && pic.chroma == 1) ? 1 : 0;     // horizontal / vertical sub-sampling of the component
+  const int w = pic.width >> sh, h = pic.height >> shy;
   const int x0 = (blockIdx.x * 64 + threadIdx.x) * 8, y = blockIdx.y * 4 + threadIdx.y;
   if (x0 >= w || y >= h) return;
-  const int cx = pic.crop_x >> sh, cy = pic.crop_y >> sh, ow = (pic.out_w + sh) >> sh, oh = (pic.out_h + sh) >> sh;
+  const int cx = pic.crop_x >> sh, cy = pic.crop_y >> shy, ow = (pic.out_w + sh) >> sh, oh = (pic.out_h + shy) >> shy;
   const int oy = y - cy;
   if (oy < 0 || oy >= oh) return;                                     // outside the conformance window: never output
   const T* src = static_cast<const T*>(pic.rec[c]);
   const int st = pic.rec_stride[c];
-  const int lg = pic.log2_ctb - sh;
+  const int lg = pic.log2_ctb - sh, lgy = pic.log2_ctb - shy;
   const CtuInfo* ctus = b.ctus + pic.ctu_base;
   const int n = min(8, w - x0);
   int res[8];
   if (pic.nslices > 1) {
 #pragma unroll
-    for (int k = 0; k < 8; k++) res[k] = k < n ? sao_sample_generic<T>(b, pic, ctus, src, st, c, x0 + k, y, w, h, lg) : 0;
+    for (int k = 0; k < 8; k++) res[k] = k < n ? sao_sample_generic<T>(b, pic, ctus, src, st, c, x0 + k, y, w, h, lg, lgy) : 0;
   } else {
     // centre row: samples x0-1 .. x0+8 in cur[0..9]
     int cur[10], up[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0}, dn[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
@@ -186,7 +190,7 @@ __global__ void __launch_bounds__(256) sao_kernel(const DeviceBatch b) {
 #pragma unroll
       for (int k = 0; k < 8; k++) cur[1 + k] = k < n ? (int)row[k] : 0;
     }
-    const SaoComp sp = ctus[(y >> lg) * pic.wctb + (x0 >> lg)].sao[c];
+    const SaoComp sp = ctus[(y >> lgy) * pic.wctb + (x0 >> lg)].sao[c];
     const int bd = pic.bit_depth, maxv = (1 << bd) - 1;
     const unsigned offs = (unsigned)(uint8_t)sp.offset[0] | ((unsigned)(uint8_t)sp.offset[1] << 8) | ((unsigned)(uint8_t)sp.offset[2] << 16) | ((unsigned)(uint8_t)sp.offset[3] << 24);
     auto offset = [&](int i) { return (int)(int8_t)(offs >> (8 * i)); };     // register-resident SaoOffsetVal[1..4]
@@ -234,7 +238,7 @@ __global__ void __launch_bounds__(256) sao_kernel(const DeviceBatch b) {
   }
   {
     // cu_transquant_bypass / pcm + pcm_loop_filter_disabled (8.7.3: SaoTypeIdx is treated as 0 there): bit 2 of the 8x8 luma cells
-    const uint8_t* cell = b.edge8 + pic.map8_base + ((y << sh) >> 3) * pic.w8 + ((x0 << sh) >> 3);
+    const uint8_t* cell = b.edge8 + pic.map8_base + ((y << shy) >> 3) * pic.w8 + ((x0 << sh) >> 3);
     const bool k0 = cell[0] & 4, k1 = sh ? (((x0 + 4) << 1) < pic.width && (cell[1] & 4)) : k0;
     if (k0 | k1) {
       const T* row = src + (size_t)y * st + x0;

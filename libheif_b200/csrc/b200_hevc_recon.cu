@@ -88,10 +88,10 @@ template <bool LIVE> __device__ __forceinline__ CtuInfo ld_ctu(const CtuInfo* p)
   return c;
 }
 
-__device__ __forceinline__ int chroma_qp(int qpy, int off, int bd) {       // 8.6.1, ChromaArrayType == 1
+__device__ __forceinline__ int chroma_qp(int qpy, int off, int bd, int cfmt = 1) {       // 8.6.1: Table 8-10 when ChromaArrayType == 1, else Min(qPi, 51)
   const int qbd = 6 * (bd - 8);
   const int qpi = clip3i(-qbd, 57, qpy + off);
-  const int qpc = qpi < 30 ? qpi : (qpi >= 43 ? qpi - 6 : c_qpc[qpi - 30]);
+  const int qpc = cfmt != 1 ? min(qpi, 51) : (qpi < 30 ? qpi : (qpi >= 43 ? qpi - 6 : c_qpc[qpi - 30]));
   return qpc + qbd;
 }
 
@@ -106,19 +106,21 @@ __device__ __forceinline__ int dequant(int level, int qp, int bd_shift, int m) {
 //  x: bx/4 [0:4) by/4 [4:8) log2n-2 [8:10) mode [10:16) coded [16] (Cr: [17]) availL [18] availCorner [19] availTop [20]
 //     available below-left samples / 4 [21:25)  available above-right samples / 4 [25:29)  pcm [29]: the "residuals" are the samples
 //  y: offset of the block's residuals inside the component's residual area (samples)
-__device__ __forceinline__ unsigned make_desc(int bx, int by, int lg, int mode, int coded0, int coded1, int cs, int cx0, int cy0, int cw, int ch,
+// (tw, th: the component's CTB size; shx: its horizontal sub-sampling when the decoding order inside the CTB has to be judged in
+//  LUMA units -- the 4:2:2 chroma planes, whose blocks follow the z-order of the luma quadtree, not of their own coordinates)
+__device__ __forceinline__ unsigned make_desc(int bx, int by, int lg, int mode, int coded0, int coded1, int tw, int th, int shx, int cx0, int cy0, int cw, int ch,
                                               bool nbL, bool nbAL, bool nbA, bool nbAR) {
   const int n = 1 << lg;
   const bool fL = bx > 0 || nbL, fT = by > 0 || nbA;
   const bool fC = (bx > 0 && by > 0) ? true : (bx > 0 ? nbA : (by > 0 ? nbL : nbAL));
-  const unsigned me = morton4((unsigned)bx >> 2, (unsigned)by >> 2);
+  const unsigned me = morton4((unsigned)(bx << shx) >> 2, (unsigned)by >> 2);
   bool tr = false, bl = false;
   if (cx0 + bx + n < cw) {
-    if (by > 0) { if (bx + n < cs) tr = morton4((unsigned)(bx + n) >> 2, (unsigned)(by - 1) >> 2) < me; }
-    else tr = (bx + n < cs) ? nbA : nbAR;
+    if (by > 0) { if (bx + n < tw) tr = morton4((unsigned)((bx + n) << shx) >> 2, (unsigned)(by - 1) >> 2) < me; }
+    else tr = (bx + n < tw) ? nbA : nbAR;
   }
-  if (cy0 + by + n < ch && by + n < cs) {
-    if (bx > 0) bl = morton4((unsigned)(bx - 1) >> 2, (unsigned)(by + n) >> 2) < me; else bl = nbL;
+  if (cy0 + by + n < ch && by + n < th) {
+    if (bx > 0) bl = morton4((unsigned)((bx - 1) << shx) >> 2, (unsigned)(by + n) >> 2) < me; else bl = nbL;
   }
   const int trc = tr ? min(n, cw - (cx0 + bx + n)) : 0, blc = bl ? min(n, ch - (cy0 + by + n)) : 0;
   return (unsigned)(bx >> 2) | ((unsigned)(by >> 2) << 4) | ((unsigned)(lg - 2) << 8) | ((unsigned)mode << 10) | ((unsigned)coded0 << 16) | ((unsigned)coded1 << 17) |
@@ -242,7 +244,7 @@ __device__ __noinline__ void residual_big(int16_t* rs, int16_t* tmp, const int8_
 //  tp[PAD + x]), rs: its residual area, rf: its neighbour array(s), l / lpc: lane index inside / lanes per component,
 //  gmask: the lanes working on this component.
 template <typename P>
-__device__ __forceinline__ void predict_tb(const uint2 d, P* tl, const P* tp, const int16_t* rs, int16_t* rf, int S, int l, int lpc, unsigned gmask, int cidx, bool luma, int bd, int strong_en) {
+__device__ __forceinline__ void predict_tb(const uint2 d, P* tl, const P* tp, const int16_t* rs, int16_t* rf, int S, int l, int lpc, unsigned gmask, int cidx, bool luma, bool smooth, int bd, int strong_en) {   // luma: boundary filters of DC / horizontal / vertical (cIdx == 0); smooth: 8.4.4.2.3 applies (luma; chroma in 4:4:4)
   const int bx = (int)(d.x & 15) << 2, by = (int)((d.x >> 4) & 15) << 2, lg = 2 + (int)((d.x >> 8) & 3), mode = (int)((d.x >> 10) & 63);
   const int n = 1 << lg, n2 = 2 * n, n4 = 4 * n;
   const bool coded = (d.x >> (16 + cidx)) & 1, pcm = (d.x >> 29) & 1;
@@ -287,7 +289,7 @@ __device__ __forceinline__ void predict_tb(const uint2 d, P* tl, const P* tp, co
   __syncwarp();
   // ---- smoothing of the neighbours (8.4.4.2.3): luma only in 4:2:0
   const int16_t* ref = rf;
-  if (luma && mode != 1 && n != 4) {
+  if (smooth && mode != 1 && n != 4) {
     const int dist = min(abs(mode - 26), abs(mode - 10));
     const int thr = n == 8 ? 7 : (n == 16 ? 1 : 0);
     if (dist > thr) {
@@ -382,30 +384,37 @@ __global__ void __launch_bounds__(WARPS * 32, B200_RECON_MIN_BLOCKS) hevc_recon_
     if (t >= (unsigned)b.nrows) break;
     const uint2 pr = b.row_list[t];
     const PicDesc* pic = &b.pics[pr.x];
-    const int g = (int)(pr.y >> 31), ry = (int)(pr.y & 0x7fffffffu);        // g = 0: luma, 1: Cb + Cr
+    // g = 0: luma; 1: Cb + Cr of a 4:2:0 picture on the two half-warps; 2 / 3: the Cb / Cr plane of a 4:2:2 or 4:4:4 picture, handled
+    // like luma (full warp, its own commands: b200_hevc_syntax.h transform_unit_x)
+    const int g = (int)(pr.y >> 30), ry = (int)(pr.y & 0x3fffffffu);
+    const int pl = g >= 2 ? g - 1 : 0;                                      // plane of a luma-like item
+    const int cfmt = pic->chroma;
+    const int shx = g == 0 ? 0 : (g == 1 ? 1 : (cfmt == 2 ? 1 : 0)), shy = g == 1 ? 1 : 0;
+    const bool paired = g == 1;
     const CtuInfo* ctus = b.ctus + pic->ctu_base;
     const SliceInfo* slices = b.slices + pic->slice_base;
     const int log2ctb = pic->log2_ctb, wctb = pic->wctb, bd = pic->bit_depth, strong_en = pic->strong_intra;
-    const int cs = (1 << log2ctb) >> g, S = cs + PAD;                        // component CTB size, tile row stride
-    const int cw = pic->width >> g, ch = pic->height >> g;
-    const int y0 = ry << log2ctb, cy0 = y0 >> g;
+    const int tw = (1 << log2ctb) >> shx, th = (1 << log2ctb) >> shy, S = tw + PAD;   // component CTB size, tile row stride
+    const int cw = pic->width >> shx, ch = pic->height >> shy;
+    const int y0 = ry << log2ctb, cy0 = y0 >> shy;
     const uint8_t* sfac = pic->scaling_idx >= 0 ? b.scaling + (size_t)pic->scaling_idx * 784 : nullptr;      // sl::Factors: m[3][4][64], dc[3][4]
     const TuCmd* tus = b.tus + pic->tu_base;
     const CoefEntry* coefs = b.coefs + pic->coef_base;
-    unsigned* prog = b.progress + 2 * pic->progress_base + g;               // counter of (row r, group g) at prog[2 * r]
+    unsigned* prog = b.progress + 3 * pic->progress_base + (g == 3 ? 2 : (g ? 1 : 0));   // counter of (row r, item kind) at prog[3 * r]
     const unsigned* eprog = b.entropy_progress ? b.entropy_progress + pic->progress_base : nullptr;
     // lane roles in phase B
-    const int lpc = g ? 16 : 32, l = lane & (lpc - 1), cidx = g ? lane >> 4 : 0;
-    const unsigned gmask = g ? (0xffffu << (16 * cidx)) : 0xffffffffu;
-    P* const tl = tile0 + cidx * (cs * S);
-    P* const tp = top0 + cidx * (PAD + 2 * cs + 16);
-    int16_t* const rs = res0 + cidx * (cs * cs);
+    const int lpc = paired ? 16 : 32, l = lane & (lpc - 1), cidx = paired ? lane >> 4 : 0;
+    const unsigned gmask = paired ? (0xffffu << (16 * cidx)) : 0xffffffffu;
+    P* const tl = tile0 + cidx * (th * S);
+    P* const tp = top0 + cidx * (PAD + 2 * tw + 16);
+    int16_t* const rs = res0 + cidx * (tw * th);
     int16_t* const rf = tmp + cidx * REF_STRIDE;
-    P* const recp = static_cast<P*>(pic->rec[g + cidx]);
-    const int rst = pic->rec_stride[g + cidx];
+    const int plane = paired ? 1 + cidx : pl;
+    P* const recp = static_cast<P*>(pic->rec[plane]);
+    const int rst = pic->rec_stride[plane];
 
     for (int rx = 0; rx < wctb; rx++) {
-      const int x0 = rx << log2ctb, cx0 = x0 >> g;
+      const int x0 = rx << log2ctb, cx0 = x0 >> shx;
       // (1) with K0 running concurrently: this CTB's commands must have been published.  Relaxed polling loads (no L1
       // invalidation) with microsecond back-off: waiting rows must not flood L2 with polls.
       if (eprog) {
@@ -443,9 +452,12 @@ __global__ void __launch_bounds__(WARPS * 32, B200_RECON_MIN_BLOCKS) hevc_recon_
         const int nl = (int)(cmd.w3 & 0x7ff), ncb = (int)((cmd.w3 >> 11) & 0x3ff), ncr = (int)((cmd.w3 >> 21) & 0x3ff);
         const CoefEntry* ce = coefs + cmd.w2;
         bool has; int bx, by, lg, mode, coded0, coded1, qp0, qp1 = 0, ts0, ts1 = 0, n0, n1 = 0; const CoefEntry* ce1 = ce;
-        if (g == 0) {
-          has = valid; bx = lx; by = ly; lg = log2n; mode = (int)(cmd.w1 & 63); coded0 = (int)((cmd.w0 >> 26) & 1); coded1 = 0;
-          qp0 = qpy + 6 * (bd - 8); ts0 = (int)((cmd.w0 >> 30) & 1); n0 = nl;
+        if (!paired) {
+          // a luma block, or (4:2:2 / 4:4:4) the block of plane `pl`: the commands of the other planes are skipped
+          has = valid && (int)((cmd.w1 >> 23) & 3) == pl;
+          bx = lx >> shx; by = ly; lg = log2n; mode = (int)(cmd.w1 & 63); coded0 = (int)((cmd.w0 >> 26) & 1); coded1 = 0;
+          qp0 = pl == 0 ? qpy + 6 * (bd - 8) : chroma_qp(qpy, pl == 1 ? sl.cb_qp_offset : sl.cr_qp_offset, bd, cfmt);
+          ts0 = (int)((cmd.w0 >> 30) & 1); n0 = nl;
         } else {
           has = valid && ((cmd.w0 >> 29) & 1);
           if (log2n > 2) { bx = lx >> 1; by = ly >> 1; lg = log2n - 1; } else { bx = (lx - 4) >> 1; by = (ly - 4) >> 1; lg = 2; }
@@ -459,15 +471,15 @@ __global__ void __launch_bounds__(WARPS * 32, B200_RECON_MIN_BLOCKS) hevc_recon_
         const unsigned hb = __ballot_sync(0xffffffffu, has);
         const int idx = ntb + __popc(hb & lt_mask);
         const unsigned roff = morton4((unsigned)bx >> 2, (unsigned)by >> 2) * 16;
-        if (has) desc[idx] = make_uint2(make_desc(bx, by, lg, mode, coded0, coded1, cs, cx0, cy0, cw, ch, nbL, nbAL, nbA, nbAR) | ((unsigned)pcm << 29), roff);
+        if (has) desc[idx] = make_uint2(make_desc(bx, by, lg, mode, coded0, coded1, tw, th, paired ? 0 : shx, cx0, cy0, cw, ch, nbL, nbAL, nbA, nbAR) | ((unsigned)pcm << 29), roff);
         ntb += __popc(hb);
         // 4x4 blocks: one lane each, in registers
         if (lg == 2) {
 #pragma unroll 1
           for (int c2 = 0; c2 < 2; c2++)
             if (c2 ? coded1 : coded0)
-              residual4_lane<LIVE>(tmp, lane, c2 ? ce1 : ce, c2 ? n1 : n0, c2 ? qp1 : qp0, bd, g == 0, c2 ? ts1 : ts0, raw, res0 + (c2 ? cs * cs : 0) + roff,
-                                   sfac ? sfac + (g + c2) * 256 : nullptr);
+              residual4_lane<LIVE>(tmp, lane, c2 ? ce1 : ce, c2 ? n1 : n0, c2 ? qp1 : qp0, bd, g == 0, c2 ? ts1 : ts0, raw, res0 + (c2 ? tw * th : 0) + roff,
+                                   sfac ? sfac + (paired ? 1 + c2 : pl) * 256 : nullptr);
         }
         __syncwarp();
         // larger blocks: the whole warp, one block at a time
@@ -480,8 +492,8 @@ __global__ void __launch_bounds__(WARPS * 32, B200_RECON_MIN_BLOCKS) hevc_recon_
             const unsigned long long cp = __shfl_sync(0xffffffffu, (unsigned long long)(c2 ? ce1 : ce), src);
             const int nn = __shfl_sync(0xffffffffu, c2 ? n1 : n0, src), lgg = __shfl_sync(0xffffffffu, lg, src), qq = __shfl_sync(0xffffffffu, c2 ? qp1 : qp0, src);
             const unsigned ro = __shfl_sync(0xffffffffu, roff, src); const bool rw = __shfl_sync(0xffffffffu, (int)raw, src) != 0;
-            residual_big<LIVE>(res0 + (c2 ? cs * cs : 0) + ro, tmp, mat, reinterpret_cast<const CoefEntry*>(cp), nn, lgg, qq, bd, lane,
-                               sfac ? sfac + (g + c2) * 256 + (lgg - 2) * 64 : nullptr, sfac ? (int)sfac[768 + (g + c2) * 4 + (lgg - 2)] : 16, rw);
+            residual_big<LIVE>(res0 + (c2 ? tw * th : 0) + ro, tmp, mat, reinterpret_cast<const CoefEntry*>(cp), nn, lgg, qq, bd, lane,
+                               sfac ? sfac + (paired ? 1 + c2 : pl) * 256 + (lgg - 2) * 64 : nullptr, sfac ? (int)sfac[768 + (paired ? 1 + c2 : pl) * 4 + (lgg - 2)] : 16, rw);
           }
         }
       }
@@ -492,7 +504,7 @@ __global__ void __launch_bounds__(WARPS * 32, B200_RECON_MIN_BLOCKS) hevc_recon_
         if (lane == 0) {
           const unsigned need = (unsigned)min(rx + 2, wctb);
           unsigned spins = 0, ns = 250;
-          while (ld_acquire(&prog[2 * (ry - 1)]) < need) {
+          while (ld_acquire(&prog[3 * (ry - 1)]) < need) {
             __nanosleep(ns); if (ns < 8000) ns <<= 1;
             if ((++spins & 31u) == 0 && ld_acquire(b.error_flag)) break;
             if (spins > (1u << 23)) { atomicExch(b.error_flag, 1u); break; }
@@ -501,7 +513,7 @@ __global__ void __launch_bounds__(WARPS * 32, B200_RECON_MIN_BLOCKS) hevc_recon_
         }
         if (__shfl_sync(0xffffffffu, abort, 0)) return;                      // the batch is reported as failed; nothing it produced is used
         // halo row above (corner .. above-right) from HBM/L2: written by another SM during this kernel -> L1-bypassing loads
-        const int cnt = 1 + 2 * cs;
+        const int cnt = 1 + 2 * tw;
         const P* grow = recp + (size_t)(cy0 - 1) * rst;
 #pragma unroll 1
         for (int i = l; i < cnt; i += lpc) {
@@ -514,10 +526,10 @@ __global__ void __launch_bounds__(WARPS * 32, B200_RECON_MIN_BLOCKS) hevc_recon_
       __syncwarp();
       // ---- phase B: prediction + reconstruction, block after block
 #pragma unroll 1
-      for (int k = 0; k < ntb; k++) predict_tb<P>(desc[k], tl, tp, rs, rf, S, l, lpc, gmask, cidx, g == 0, bd, strong_en);
+      for (int k = 0; k < ntb; k++) predict_tb<P>(desc[k], tl, tp, rs, rf, S, l, lpc, gmask, cidx, g == 0, g == 0 || (g >= 2 && cfmt == 3), bd, g == 0 ? strong_en : 0);
       // ---- the finished CTB goes to HBM; its last column becomes the next CTB's left halo
       {
-        const int w = min(cs, cw - cx0), h = min(cs, ch - cy0);
+        const int w = min(tw, cw - cx0), h = min(th, ch - cy0);
         const unsigned rowb = (unsigned)(w * (int)sizeof(P));
         P* gdst = recp + (size_t)cy0 * rst + cx0;
         if ((rowb & 15u) == 0) {
@@ -537,15 +549,15 @@ __global__ void __launch_bounds__(WARPS * 32, B200_RECON_MIN_BLOCKS) hevc_recon_
         }
         // last column -> left halo of the next CTB (read before, written after the rows have left the tile)
         P keep0 = 0, keep1 = 0;
-        if (l < cs) keep0 = tl[l * S + PAD + cs - 1];
-        if (l + lpc < cs) keep1 = tl[(l + lpc) * S + PAD + cs - 1];
+        if (l < th) keep0 = tl[l * S + PAD + tw - 1];
+        if (l + lpc < th) keep1 = tl[(l + lpc) * S + PAD + tw - 1];
         if ((rowb & 15u) == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");     // rows are in global memory; the tile may be overwritten
         __syncwarp();
-        if (l < cs) tl[l * S + PAD - 1] = keep0;
-        if (l + lpc < cs) tl[(l + lpc) * S + PAD - 1] = keep1;
+        if (l < th) tl[l * S + PAD - 1] = keep0;
+        if (l + lpc < th) tl[(l + lpc) * S + PAD - 1] = keep1;
         __threadfence();
         __syncwarp();                                         // all lanes' stores precede lane 0's release store (cumulativity)
-        if (lane == 0) st_release(&prog[2 * ry], (unsigned)(rx + 1));
+        if (lane == 0) st_release(&prog[3 * ry], (unsigned)(rx + 1));
       }
     }
   }

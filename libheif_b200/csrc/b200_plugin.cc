@@ -215,8 +215,9 @@ bool decode_group(SubmitQueue& Q, std::vector<Request*>& g, std::vector<Outcome>
   int rc = b200_decoder_decode_grid(Q.dec, n, 1, au.data(), sz.data(), maxpx, 0, 0, &info, nullptr);
   if (rc) { if (n == 1) fail(out[0], rc); return n == 1; }
   const int bps = info.bit_depth > 8 ? 2 : 1, mono = info.chroma == B200_CHROMA_MONO;
-  const size_t yrow = (size_t)info.width * bps, crow = mono ? 0 : (size_t)((info.width + 1) / 2) * bps;
-  const size_t ch = mono ? 0 : (size_t)(info.height + 1) / 2;
+  const int csx = (info.chroma == B200_CHROMA_420 || info.chroma == B200_CHROMA_422) ? 1 : 0, csy = info.chroma == B200_CHROMA_420 ? 1 : 0;
+  const size_t yrow = (size_t)info.width * bps, crow = mono ? 0 : (size_t)((info.width + csx) >> csx) * bps;
+  const size_t ch = mono ? 0 : (size_t)((info.height + csy) >> csy);
   const size_t need = yrow * info.height + 2 * crow * ch;
   if (need > Q.staging_cap) {
     if (Q.staging) b200_host_free(Q.staging);
@@ -232,7 +233,7 @@ bool decode_group(SubmitQueue& Q, std::vector<Request*>& g, std::vector<Outcome>
   for (int i = 0; i < n; i++) {
     Outcome& o = out[(size_t)i];
     o.src[0] = sy + (size_t)i * tw * bps; o.src_st[0] = yrow;
-    if (!mono) { o.src[1] = scb + (size_t)i * (tw / 2) * bps; o.src[2] = scr + (size_t)i * (tw / 2) * bps; o.src_st[1] = o.src_st[2] = crow; }
+    if (!mono) { o.src[1] = scb + (size_t)i * (tw >> csx) * bps; o.src[2] = scr + (size_t)i * (tw >> csx) * bps; o.src_st[1] = o.src_st[2] = crow; }
     o.state = 1;
   }
   return true;
@@ -317,10 +318,11 @@ b200h_error dec_decode2(void* p, b200h_image** out_img, uintptr_t* out_user, con
   const b200_image_info info = rq.info;
   const bool mono = info.chroma == B200_CHROMA_MONO;
   b200h_image* img = nullptr;
-  b200h_error err = g_api.image_create(info.width, info.height, mono ? B200H_COLORSPACE_MONOCHROME : B200H_COLORSPACE_YCBCR, mono ? 0 : 1, &img);
+  b200h_error err = g_api.image_create(info.width, info.height, mono ? B200H_COLORSPACE_MONOCHROME : B200H_COLORSPACE_YCBCR, info.chroma /* heif_chroma_monochrome / 420 / 422 / 444 = 0..3 (heif_image.h:77-82) */, &img);
   if (err.code) { d->data.clear(); return err; }
+  const int psx = (info.chroma == B200_CHROMA_420 || info.chroma == B200_CHROMA_422) ? 1 : 0, psy = info.chroma == B200_CHROMA_420 ? 1 : 0;
   for (int c = 0; c < (mono ? 1 : 3) && !err.code; c++) {
-    const int w = c ? (info.width + 1) / 2 : info.width, h = c ? (info.height + 1) / 2 : info.height;
+    const int w = c ? (info.width + psx) >> psx : info.width, h = c ? (info.height + psy) >> psy : info.height;
     err = g_api.image_add_plane_safe(img, c, w, h, info.bit_depth, limits);
     if (!err.code) rq.pl[c] = g_api.image_get_plane2(img, c, &rq.st[c]);
   }
@@ -338,7 +340,7 @@ b200h_error dec_decode2(void* p, b200h_image** out_img, uintptr_t* out_user, con
     if (rq.state == 1) {
       const int bps = info.bit_depth > 8 ? 2 : 1;
       for (int c = 0; c < (mono ? 1 : 3); c++) {
-        const int w = c ? (info.width + 1) / 2 : info.width, h = c ? (info.height + 1) / 2 : info.height;
+        const int w = c ? (info.width + psx) >> psx : info.width, h = c ? (info.height + psy) >> psy : info.height;
         for (int y = 0; y < h; y++) memcpy(rq.pl[c] + (size_t)y * rq.st[c], rq.src[c] + (size_t)y * rq.src_st[c], (size_t)w * bps);
       }
     }

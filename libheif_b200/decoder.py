@@ -97,7 +97,8 @@ class Decoder:
         if i.chroma == 0:
             _lib.check(self.l.b200_decoder_read_planes(self.h, y.ctypes.data, y.strides[0], None, None, 0, None))
             return [y]
-        cb = np.empty(((i.height + 1) // 2, (i.width + 1) // 2), dt)
+        sx, sy = (1 if i.chroma in (1, 2) else 0), (1 if i.chroma == 1 else 0)      # 4:2:0 / 4:2:2 / 4:4:4
+        cb = np.empty(((i.height + sy) >> sy, (i.width + sx) >> sx), dt)
         cr = np.empty_like(cb)
         _lib.check(self.l.b200_decoder_read_planes(self.h, y.ctypes.data, y.strides[0], cb.ctypes.data, cr.ctypes.data, cb.strides[0], None))
         return [y, cb, cr]
@@ -118,7 +119,8 @@ class Decoder:
         i = self.info
         dt = np.uint8 if i.bit_depth == 8 else np.uint16
         y = np.empty((coded_h, coded_w), dt)
-        cb = np.empty((coded_h // 2, coded_w // 2), dt)
+        sx, sy = (1 if i.chroma in (1, 2) else 0), (1 if i.chroma == 1 else 0)
+        cb = np.empty((coded_h >> sy, coded_w >> sx), dt)
         cr = np.empty_like(cb)
         mono = i.chroma == 0
         _lib.check(self.l.b200_decoder_debug_read_tile(self.h, index, 0, y.ctypes.data, None if mono else cb.ctypes.data, None if mono else cr.ctypes.data))

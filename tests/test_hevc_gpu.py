@@ -7,7 +7,7 @@ import numpy as np
 import pytest
 
 import libheif_b200 as lb
-from hevc_cases import SYNTH, all_streams, synth_stream
+from hevc_cases import SYNTH, SYNTH_CPU_EXTRA, all_streams, synth_stream
 from oracle import bindings as ob
 
 pytestmark = pytest.mark.gpu
@@ -209,3 +209,56 @@ def test_chunked_pipeline_equals_back_to_back(cuda, tiles_per_chunk, monkeypatch
         assert np.array_equal(pinned.numpy(), base)
     finally:
         d.close()
+
+
+CHROMA_FORMAT_STREAMS = [c[0] for c in SYNTH_CPU_EXTRA if c[4] in (2, 3)]
+
+
+@pytest.mark.parametrize("name", CHROMA_FORMAT_STREAMS)
+@pytest.mark.parametrize("stage", [0, 1])
+def test_422_and_444_coded_pictures_match_oracle(dec, name, stage):
+    """chroma_format_idc 2 / 3: the Cb and Cr planes are reconstructed by luma-like work items from their own commands (two
+    square blocks per unit in 4:2:2); deblocking and SAO use the format's chroma grid.  Stage 1 = before the in-loop filters."""
+    au = synth_stream(name)
+    want, info = ob.restatement_decode(au, stage)           # cropped to the conformance window
+    dec.set_debug_stage(stage)
+    try:
+        i = dec.decode_image(au)
+        if stage == 0:
+            got = dec.planes_host()
+        else:
+            h, w = want[0].shape
+            got = dec.debug_tile(0, (w + 7) & ~7, (h + 7) & ~7)
+    finally:
+        dec.set_debug_stage(0)
+    assert i.chroma == info["chroma"] and i.bit_depth == info["bit_depth"]
+    for c in range(3):
+        hh, ww = want[c].shape
+        assert np.array_equal(got[c][:hh, :ww], want[c]), f"{name} stage {stage}: plane {c} first diffs {np.argwhere(got[c][:hh, :ww] != want[c])[:4].tolist()}"
+
+
+@pytest.mark.parametrize("name,out_chroma", [("x_444_basic", lb.CHROMA_INTERLEAVED_RGB), ("x_422_basic", lb.CHROMA_INTERLEAVED_RGB), ("x_444_main10_ctb16_random_tskip", lb.CHROMA_INTERLEAVED_RRGGBB_LE),
+                                             ("x_422_main12_ctb64_deep_dqp", lb.CHROMA_INTERLEAVED_RRGGBBAA_BE)])
+def test_422_and_444_to_rgb_through_the_fused_entry_point(dec, name, out_chroma):
+    from util import oracle_postprocess
+    au = synth_stream(name)
+    planes, info = ob.restatement_decode(au)
+    want, ow, oh = oracle_postprocess(planes[0], planes[1], planes[2], None, info["chroma"], info["bit_depth"], (info["cp"], info["tc"], info["mc"], info["full_range"]), [], out_chroma)
+    bpp = {10: 3, 11: 4, 12: 6, 13: 8, 14: 6, 15: 8}[out_chroma]
+    out = np.empty((oh, ow * bpp), np.uint8)
+    dec.decode_grid_to_rgb_host([au], 1, 1, out_chroma, out=out)
+    assert np.array_equal(out.reshape(-1), want)
+
+
+def test_grid_of_444_tiles(dec):
+    tiles, want = [], []
+    for k in range(4):
+        y, cb, cr = lb.hevc_enc.synthetic_image(0x444 + k, 64, 64, 8, 3)
+        au = lb.hevc_enc.encode_intra(y, cb, cr, log2_ctb_size=4 + k % 2, wpp=k % 2, seed=k + 1)
+        tiles.append(au); want.append(ob.restatement_decode(au)[0])
+    dec.decode_grid(tiles, cols=2, rows=2)
+    got = dec.planes_host()
+    for k in range(4):
+        r, c0 = divmod(k, 2)
+        for c in range(3):
+            assert np.array_equal(got[c][r * 64:(r + 1) * 64, c0 * 64:(c0 + 1) * 64], want[k][c]), f"tile {k} plane {c}"
