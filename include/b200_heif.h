@@ -192,7 +192,7 @@ typedef struct b200_decoder b200_decoder;
 typedef struct b200_image_info {
   int width, height;          /* canvas size (single image: conformance-cropped picture size) */
   int tile_width, tile_height;
-  int chroma;                 /* B200_CHROMA_MONO or B200_CHROMA_420 */
+  int chroma;                 /* B200_CHROMA_MONO / 420 / 422 / 444 (= chroma_format_idc of the coded pictures) */
   int bit_depth;
   int colour_primaries, transfer_characteristics, matrix_coefficients, full_range;   /* from the SPS VUI, defaults 2/2/2/0 */
 } b200_image_info;

@@ -12,9 +12,11 @@
 
 namespace b200 {
 
-// One transform unit in decoding order (z-order inside a CTU).  16 bytes.
+// One transform unit in decoding order (z-order inside a CTU).  16 bytes.  In 4:2:2 / 4:4:4 pictures every BLOCK is a command of its
+// own: the luma block (chroma_here = 0) and then each chroma block, laid out like a luma one (cbf in bit 26, transform skip in bit 30,
+// its intra mode in luma_mode, nnz in w3[0:11)) with the component in w1[23:25) and its LUMA location as position.
 //  w0: x4[0:12) y4[12:24) log2m2[24:26) cbf_luma[26] cbf_cb[27] cbf_cr[28] chroma_here[29] ts_luma[30] ts_cb[31]
-//  w1: luma_mode[0:6) chroma_mode[6:12) qpy+64 [12:20) ts_cr[20]
+//  w1: luma_mode[0:6) chroma_mode[6:12) qpy+64 [12:20) ts_cr[20] pcm[21] cu_transquant_bypass[22] component[23:25)
 //  w2: index of this TU's first coefficient entry (relative to the picture's coefficient base)
 //  w3: nnz_luma[0:11) nnz_cb[11:21) nnz_cr[21:31)
 // x4,y4: luma position of the luma transform block in 4-sample units.  When log2 size is 2 and chroma_here is set,
@@ -57,7 +59,7 @@ struct SliceInfo {
 struct PicDesc {         // one per picture (tile) of a batch
   int32_t width, height;             // coded luma size (multiple of MinCbSizeY)
   int32_t log2_ctb, wctb, hctb;
-  int32_t bit_depth, chroma;         // chroma: 0 = 4:0:0, 1 = 4:2:0
+  int32_t bit_depth, chroma;         // chroma = chroma_format_idc: 0 = 4:0:0, 1 = 4:2:0, 2 = 4:2:2, 3 = 4:4:4
   int32_t crop_x, crop_y, out_w, out_h;   // conformance window in luma samples
   int32_t strong_intra, pps_cb_qp_offset, pps_cr_qp_offset, sao_enabled;
   int32_t log2_sao_scale_luma, log2_sao_scale_chroma;
