@@ -106,6 +106,19 @@ if mode == "plugin-path-gpu":
             got[i] = "ERR " + str(e)[:200]
     th = [threading.Thread(target=work, args=(i,)) for i in range(len(files))]
     [t.start() for t in th]; [t.join() for t in th]
+    # 4:2:2 and 4:4:4 coded pictures through heif_decode_image (the plugin returns heif_chroma_422 / _444 planes; the reference converts them)
+    cf_ok, cf_bad = True, []
+    for cf, bd, outc in ((2, 8, rh.CHROMA_INTERLEAVED_RGB), (3, 8, rh.CHROMA_INTERLEAVED_RGB), (2, 10, 14), (3, 12, 14)):
+        py, pcb, pcr = synthetic_image(500 + cf + bd, 160, 96, bd, cf)
+        a = hevc_enc.encode_intra(py, pcb, pcr, bit_depth=bd, log2_ctb_size=5, qp=24, wpp=1, vui_present=1, colour_description_present=1, colour_primaries=1,
+                                  transfer_characteristics=13, matrix_coefficients=6, full_range=bd == 8)
+        f = os.path.join(tmp, f"cf{cf}_{bd}.heic"); hw.write_heic(f, [a])
+        w_ = hashlib.md5(rh.decode_file(f, chroma=outc, decoder_id="b200-oracle").tobytes()).hexdigest()
+        g_ = hashlib.md5(rh.decode_file(f, chroma=outc, decoder_id="b200").tobytes()).hexdigest()
+        if w_ != g_:
+            cf_ok = False; cf_bad.append((cf, bd))
+    res["chroma_formats_ok"] = cf_ok
+    res["chroma_formats_bad"] = cf_bad
     res["mixed_ok"] = got == want
     res["mixed_bad"] = [(i, got[i][:120]) for i in range(len(files)) if got[i] != want[i]]
 if mode == "roundtrip-gpu":

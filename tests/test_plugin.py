@@ -80,4 +80,5 @@ def test_plugin_path_loading_and_concurrent_instances(cuda):
     for rep in range(3):
         assert res[f"grid64_md5_gpu_{rep}"] == res["grid64_md5_cpu"]
     assert res["queue_max_batch"] > 1, res            # concurrent calls were really batched
-    assert res["mixed_ok"]
+    assert res["mixed_ok"], res.get("mixed_bad")
+    assert res["chroma_formats_ok"], res.get("chroma_formats_bad")      # 4:2:2 / 4:4:4 items through heif_decode_image
