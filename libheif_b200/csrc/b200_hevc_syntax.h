@@ -265,7 +265,7 @@ struct Cabac {
       const uint32_t q = w / range;
       val -= (q * range) << 16;
 #endif
-      out = (out << t) | q; k -= t;
+      out = (out << t) | (q & ((1u << t) - 1u)); k -= t;       // (the mask only matters for corrupt data: an offset >= range, 9.3.2.5)
     }
     return out;
   }
@@ -480,6 +480,7 @@ struct DecoderT {
         int a = base;
         if (base == ((nsig < 8) ? ((kk == last_g1) ? 3 : 2) : 1)) {
           int pre = 0; B200_NOUNROLL while (pre < 32 && cb_.bypass(stream)) pre++;
+          if (pre > 20) { err = SYN_E_BITSTREAM; cabac = cb_; coef_n = cn; return count; }   // far outside the 16-bit range of TransCoeffLevel: corrupt data
           const int rem = (pre <= 3 ? (pre << rice) : (((1 << (pre - 3)) + 3 - 1) << rice)) + (int)cb_.bypass_bits(pre <= 3 ? rice : pre - 3 + rice, stream);
           a = base + rem;
           if (a > 3 * (1 << rice)) rice = imin(rice + 1, 4);

@@ -767,6 +767,7 @@ static void residual_coding(dec_t* d, int x0, int y0, int log2n, int c, int pred
       if (base == ((nsig < 8) ? ((k == last_g1_pos) ? 3 : 2) : 1)) {
         int pre = 0;                                         /* 9.3.3.11 coeff_abs_level_remaining */
         while (pre < 32 && dec_bypass(d)) pre++;
+        if (pre > 20) { d->err = HO_ERROR; return; }          /* a value far outside the 16-bit range of TransCoeffLevel (7.4.9.11): corrupt data */
         int rem;
         if (pre <= 3) rem = (pre << rice) + dec_bypass_bits(d, rice);
         else rem = (((1 << (pre - 3)) + 3 - 1) << rice) + dec_bypass_bits(d, pre - 3 + rice);
