@@ -153,12 +153,9 @@ __device__ __noinline__ int sao_sample_generic(const DeviceBatch& b, const PicDe
   return clip3d(0, maxv, v + off);
 }
 
-// One thread = 8 horizontally adjacent samples (always inside one CTB: a chroma CTB is at least 8 samples wide) of SAO_ROWS
-// consecutive rows of one component; block = 64 segments x 4 row groups; grid.z = picture * 3 + component.  Per row the
-// CTB's SAO parameters are fetched once, the three source rows with 8- / 16-byte loads (the rows a thread walks down stay
-// in L1), the result leaves with one vector store.  (One row per thread meant 393 K blocks of 2 KB each for the 256-tile
-// grid: the kernel was bound by block turnover, not by memory.)
-constexpr int SAO_ROWS = 4;
+// One thread = 8 horizontally adjacent samples of one row of one component (always inside one CTB: a chroma CTB is at
+// least 8 samples wide); block = 64 segments x 4 rows; grid.z = picture * 3 + component.  The CTB's SAO parameters are
+// fetched once per thread, the three source rows with 8- / 16-byte loads, the result leaves with one vector store.
 template <typename T>
 __global__ void __launch_bounds__(256) sao_kernel(const DeviceBatch b) {
   const int pi = blockIdx.z / 3, c = blockIdx.z % 3;
@@ -166,13 +163,11 @@ __global__ void __launch_bounds__(256) sao_kernel(const DeviceBatch b) {
   if (c > 0 && !pic.chroma) return;
   const int sh = (c && (pic.chroma == 1 || pic.chroma == 2)) ? 1 : 0, shy = (c && pic.chroma == 1) ? 1 : 0;     // horizontal / vertical sub-sampling of the component
   const int w = pic.width >> sh, h = pic.height >> shy;
-  const int x0 = (blockIdx.x * 64 + threadIdx.x) * 8, ybase = (blockIdx.y * 4 + threadIdx.y) * SAO_ROWS;
-  if (x0 >= w || ybase >= h) return;
+  const int x0 = (blockIdx.x * 64 + threadIdx.x) * 8, y = blockIdx.y * 4 + threadIdx.y;
+  if (x0 >= w || y >= h) return;
   const int cx = pic.crop_x >> sh, cy = pic.crop_y >> shy, ow = (pic.out_w + sh) >> sh, oh = (pic.out_h + shy) >> shy;
-#pragma unroll 1
-  for (int y = ybase; y < min(h, ybase + SAO_ROWS); y++) {
   const int oy = y - cy;
-  if (oy < 0 || oy >= oh) continue;                                   // outside the conformance window: never output
+  if (oy < 0 || oy >= oh) return;                                     // outside the conformance window: never output
   const T* src = static_cast<const T*>(pic.rec[c]);
   const int st = pic.rec_stride[c];
   const int lg = pic.log2_ctb - sh, lgy = pic.log2_ctb - shy;
@@ -266,7 +261,6 @@ __global__ void __launch_bounds__(256) sao_kernel(const DeviceBatch b) {
 #pragma unroll
     for (int k = 0; k < 8; k++) { const int ox = ox0 + k; if (k < n && ox >= 0 && ox < ow) drow[ox] = (T)res[k]; }
   }
-  }
 }
 
 int launch_deblock(const DeviceBatch& b, const PicDesc* hp, cudaStream_t s) {
@@ -296,7 +290,7 @@ int launch_sao(const DeviceBatch& b, const PicDesc* hp, cudaStream_t s) {
   int max_w = 0, max_h = 0; bool any16 = false;
   for (int i = 0; i < b.npics; i++) { max_w = max(max_w, hp[i].width); max_h = max(max_h, hp[i].height); if (hp[i].bit_depth > 8) any16 = true; }
   if (!b.npics) return B200_OK;
-  const dim3 block(64, 4), grid((max_w / 8 + 63) / 64, (max_h + 4 * SAO_ROWS - 1) / (4 * SAO_ROWS), b.npics * 3);
+  const dim3 block(64, 4), grid((max_w / 8 + 63) / 64, (max_h + 3) / 4, b.npics * 3);
   if (any16) sao_kernel<uint16_t><<<grid, block, 0, s>>>(b); else sao_kernel<uint8_t><<<grid, block, 0, s>>>(b);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return set_error(B200_E_CUDA, "sao launch: %s", cudaGetErrorString(e));
