@@ -31,7 +31,10 @@ namespace b200 {
 #endif
 constexpr int WARPS = 4;                       // warps (= work items in flight) per CTA
 constexpr int PAD = 16;                        // samples left of the tile / halo row: column PAD - 1 is the left halo
-constexpr int MAT_BYTES = 1024 + 32;           // 32x32 DCT matrix (+ padding), shared by the CTA
+// Transposed DCT matrices MT_n[y][k] = transMatrix_n[k][y] for n = 32, 16, 8 (rows padded by 4 bytes: lanes that read different
+// rows hit different banks), shared by the CTA: 32 x 36 + 16 x 20 + 8 x 12 bytes
+constexpr int MT32_OFF = 0, MT16_OFF = 32 * 36, MT8_OFF = MT16_OFF + 16 * 20;
+constexpr int MAT_BYTES = MT8_OFF + 8 * 12;
 constexpr int REF_STRIDE = 136;                // int16 entries per neighbour array (4 * 32 + 1 rounded up)
 
 struct WarpLayout { int tile, top, res, tmp, desc, total; };     // byte offsets inside the warp's shared-memory slice
@@ -42,7 +45,7 @@ __host__ __device__ inline WarpLayout warp_layout(int log2ctb, int bps) {
   L.top = o; o += (2 * PAD + 2 * ctb + 32) * bps;                // halo row(s)
   o = (o + 15) & ~15;
   L.res = o; o += ctb * ctb * 2;                                 // residuals, int16, z-order block-contiguous
-  L.tmp = o; o += (tb * tb * 2 > 1024 ? tb * tb * 2 : 1024);     // first-stage output / 4x4 scratch / neighbour arrays
+  L.tmp = o; o += (tb * (tb + 2) * 2 > 1024 ? tb * (tb + 2) * 2 : 1024);   // first-stage output (rows padded by 2) / 4x4 scratch / neighbour arrays
   L.desc = o; o += (ctb / 4) * (ctb / 4) * 8;                    // one descriptor per transform block of the CTB
   L.total = (o + 15) & ~15;
   return L;
@@ -203,37 +206,46 @@ __device__ __noinline__ void residual_big(int16_t* rs, int16_t* tmp, const int8_
   __syncwarp();
   const int bd_shift = bd + lg - 5;
   int maxrow = 0, maxcol = 0;
+  // coefficients are scattered TRANSPOSED (column x of the block = row x of the buffer): the first transform stage runs down the
+  // columns, and with the vertical frequencies k of a column adjacent in memory two of them ride in one register (dp2a)
 #pragma unroll 1
   for (int i = lane; i < nnz; i += 32) {
     const CoefEntry e = ld_coef<LIVE>(&ce[i]);
     const int pos = e.pos & (n * n - 1);
+    const int x = pos & (n - 1), y = pos >> lg;
     int m = 16;
-    if (sf) { const int x = pos & (n - 1), y = pos >> lg; m = (pos == 0 && lg >= 4) ? sf_dc : (int)__ldg(sf + ((y >> (lg - 3)) << 3) + (x >> (lg - 3))); }
-    rs[pos] = raw ? e.level : (int16_t)dequant(e.level, qp, bd_shift, m);
-    maxrow = max(maxrow, pos >> lg); maxcol = max(maxcol, pos & (n - 1));
+    if (sf) m = (pos == 0 && lg >= 4) ? sf_dc : (int)__ldg(sf + ((y >> (lg - 3)) << 3) + (x >> (lg - 3)));
+    rs[raw ? pos : x * n + y] = raw ? e.level : (int16_t)dequant(e.level, qp, bd_shift, m);
+    maxrow = max(maxrow, y); maxcol = max(maxcol, x);
   }
   maxrow = __reduce_max_sync(0xffffffffu, maxrow); maxcol = __reduce_max_sync(0xffffffffu, maxcol);
   __syncwarp();
   if (raw) return;                                    // cu_transquant_bypass / pcm (warp-uniform): no scaling, no transform
-  const int mstride = 32 << (5 - lg);                 // row k of the n-point DCT = row k << (5 - log2n) of the 32-point one
-  // first stage (columns): tmp[x][y] = clip16((sum_k coef[k][x] * M[k][y] + 64) >> 7), only columns that hold coefficients
+  const int8_t* mt = mat + (lg == 5 ? MT32_OFF : (lg == 4 ? MT16_OFF : MT8_OFF));
+  const int ms = n + 4, P2 = n + 2;                   // row strides: matrix (bytes), intermediate (int16)
+  const int kq1 = (maxrow >> 2) + 1, ncol = ((maxcol >> 2) + 1) << 2;     // groups of 4 vertical frequencies; columns, rounded up to 4 (the extra ones are zero)
+  // first stage (columns): u[y][x] = clip16((sum_k coef[k][x] * M[k][y] + 64) >> 7), only columns that hold coefficients
 #pragma unroll 1
-  for (int i = lane; i < n * (maxcol + 1); i += 32) {
+  for (int i = lane; i < n * ncol; i += 32) {
     const int y = i & (n - 1), x = i >> lg;
+    const int2* c = reinterpret_cast<const int2*>(rs + x * n);
+    const int* mq = reinterpret_cast<const int*>(mt + y * ms);
     int e = 0;
 #pragma unroll 2
-    for (int k = 0; k <= maxrow; k++) e += (int)rs[k * n + x] * (int)mat[k * mstride + y];
-    tmp[x * n + y] = (int16_t)clip3i(-32768, 32767, (e + 64) >> 7);
+    for (int q = 0; q < kq1; q++) { const int2 a = c[q]; const int bq = mq[q]; e = __dp2a_lo(a.x, bq, e); e = __dp2a_hi(a.y, bq, e); }
+    tmp[y * P2 + x] = (int16_t)clip3i(-32768, 32767, (e + 64) >> 7);
   }
   __syncwarp();
-  // second stage (rows): residual r[y][x]
-  const int bs2 = 20 - bd, rnd = 1 << (bs2 - 1);
+  // second stage (rows): residual r[y][x] = (sum_k u[y][k] * M[k][x] + rnd) >> bs2
+  const int bs2 = 20 - bd, rnd = 1 << (bs2 - 1), kq2 = ncol >> 2;
 #pragma unroll 1
   for (int p = lane; p < n * n; p += 32) {
     const int x = p & (n - 1), y = p >> lg;
+    const int* u = reinterpret_cast<const int*>(tmp + y * P2);
+    const int* mq = reinterpret_cast<const int*>(mt + x * ms);
     int e = 0;
 #pragma unroll 2
-    for (int k = 0; k <= maxcol; k++) e += (int)tmp[k * n + y] * (int)mat[k * mstride + x];
+    for (int q = 0; q < kq2; q++) { const int bq = mq[q]; e = __dp2a_lo(u[2 * q], bq, e); e = __dp2a_hi(u[2 * q + 1], bq, e); }
     rs[p] = (int16_t)((e + rnd) >> bs2);
   }
   __syncwarp();
@@ -358,13 +370,14 @@ __device__ __forceinline__ void predict_tb(const uint2 d, P* tl, const P* tp, co
 template <typename P, bool LIVE>
 __global__ void __launch_bounds__(WARPS * 32, B200_RECON_MIN_BLOCKS) hevc_recon_kernel(const DeviceBatch b) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  int8_t* mat = reinterpret_cast<int8_t*>(smem_raw);                       // 32x32 DCT matrix, shared by the CTA
-  for (int i = threadIdx.x; i < 1024; i += blockDim.x) {
-    const int k = i >> 5, x = i & 31;
+  int8_t* mat = reinterpret_cast<int8_t*>(smem_raw);                       // the transposed DCT matrices, shared by the CTA
+  for (int i = threadIdx.x; i < 1024 + 256 + 64; i += blockDim.x) {
+    const int lg = i < 1024 ? 5 : (i < 1280 ? 4 : 3), j0 = i < 1024 ? i : (i < 1280 ? i - 1024 : i - 1280);
+    const int n = 1 << lg, y = j0 >> lg, kn = j0 & (n - 1), k = kn << (5 - lg);     // row kn of the n-point matrix = row kn << (5 - log2 n) of the 32-point one
     int v;
     if (k == 0) v = 64;
-    else { int j = (k * (2 * x + 1)) & 127, sgn = 1; if (j > 64) j = 128 - j; if (j > 32) { j = 64 - j; sgn = -1; } v = sgn * c_dct[j]; }
-    mat[i] = (int8_t)v;
+    else { int j = (k * (2 * y + 1)) & 127, sgn = 1; if (j > 64) j = 128 - j; if (j > 32) { j = 64 - j; sgn = -1; } v = sgn * c_dct[j]; }
+    mat[(lg == 5 ? MT32_OFF : (lg == 4 ? MT16_OFF : MT8_OFF)) + y * (n + 4) + kn] = (int8_t)v;
   }
   __syncthreads();
   const int lane = threadIdx.x & 31;
