@@ -221,3 +221,39 @@ def oracle_scale_plane(plane, out_w, out_h, image_in, image_out, comps=1):
                              C.c_uint32(out_w), C.c_uint32(out_h), C.c_uint32(image_in[0]), C.c_uint32(image_in[1]), C.c_uint32(image_out[0]), C.c_uint32(image_out[1]),
                              comps, bps)
     return out
+
+
+# ---- encoder side (N3): interleaved 8-bit RGB(A) -> YCbCr --------------------------------------------------------------------
+def _ycc_planes(w, h, out_chroma, alpha):
+    sh, sv = (2 if out_chroma in (1, 2) else 1), (2 if out_chroma == 1 else 1)
+    cw, ch = (w + sh - 1) // sh, (h + sv - 1) // sv
+    return np.empty((h, w), np.uint8), np.empty((ch, cw), np.uint8), np.empty((ch, cw), np.uint8), (np.empty((h, w), np.uint8) if alpha else None)
+
+
+def ref_rgb_to_ycbcr(rgb, has_alpha, out_chroma, nclx):
+    """UNMODIFIED reference: convert_colorspace(interleaved RGB(A) 8 bit -> YCbCr out_chroma, target nclx = (cp, tc, mc, full_range))."""
+    pl = ref_plugin()
+    h, wb = rgb.shape
+    w = wb // (4 if has_alpha else 3)
+    y, cb, cr, a = _ycc_planes(w, h, out_chroma, has_alpha)
+    src = np.ascontiguousarray(rgb)
+    rc = pl.ref_rgb_to_ycbcr(src.ctypes.data_as(C.c_void_p), w, h, int(has_alpha), out_chroma, nclx[0], nclx[1], nclx[2], int(nclx[3]),
+                             y.ctypes.data_as(C.c_void_p), cb.ctypes.data_as(C.c_void_p), cr.ctypes.data_as(C.c_void_p), a.ctypes.data_as(C.c_void_p) if a is not None else None)
+    if rc != 0:
+        raise RuntimeError(f"ref_rgb_to_ycbcr rc={rc}")
+    return y, cb, cr, a
+
+
+def oracle_rgb_to_ycbcr(rgb, has_alpha, out_chroma, nclx):
+    """C restatement (oracle/color_oracle.c: co_rgb_to_ycbcr)."""
+    l = lib()
+    h, wb = rgb.shape
+    w = wb // (4 if has_alpha else 3)
+    y, cb, cr, a = _ycc_planes(w, h, out_chroma, has_alpha)
+    src = np.ascontiguousarray(rgb)
+    l.co_rgb_to_ycbcr.argtypes = [C.c_void_p, C.c_size_t, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    rc = l.co_rgb_to_ycbcr(src.ctypes.data, src.strides[0], w, h, int(has_alpha), out_chroma, nclx[2], nclx[0], int(nclx[3]),
+                           y.ctypes.data, cb.ctypes.data, cr.ctypes.data, a.ctypes.data if a is not None else None)
+    if rc != 0:
+        raise RuntimeError("co_rgb_to_ycbcr failed")
+    return y, cb, cr, a

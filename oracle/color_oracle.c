@@ -401,3 +401,76 @@ void co_scale_nearest_plane(const uint8_t* in, size_t in_stride, uint8_t* out, s
     }
   }
 }
+
+
+/* ---- encoder side of the colour stage: Op_RGB24_32_to_YCbCr (color-conversion/rgb2yuv.cc:575-808), the op
+   heif_context_encode_image() runs on interleaved 8-bit RGB / RGBA input before the encoder plugin sees it.  Restated loop for
+   loop: float products in the reference's order, clip_f_u8 / clip_f_u16 rounding (common_utils.h:108-122), 4:2:0 averaging with
+   its odd-width / odd-height border loops, left-aligned 4:2:2.  out_chroma: 1 = 4:2:0, 2 = 4:2:2, 3 = 4:4:4. */
+static int co_clip_f_u8(float fx) { int x = (int)(fx + 0.5f); return x < 0 ? 0 : (x > 255 ? 255 : x); }
+static void co_set_chroma(uint8_t* ocb, uint8_t* ocr, int r, int g, int b, float c[3][3], int full) {   /* rgb2yuv.cc:556-572 */
+  float cb = r * c[1][0] + g * c[1][1] + b * c[1][2];
+  float cr = r * c[2][0] + g * c[2][1] + b * c[2][2];
+  if (full) { *ocb = (uint8_t)co_clip_f_u8(cb + 128); *ocr = (uint8_t)co_clip_f_u8(cr + 128); }
+  else { *ocb = (uint8_t)co_clip_f_u8(cb * 0.875f + 128.0f); *ocr = (uint8_t)co_clip_f_u8(cr * 0.875f + 128.0f); }
+}
+int co_rgb_to_ycbcr(const uint8_t* in, size_t in_stride, int w, int h, int has_alpha, int out_chroma, int mc, int cp, int full,
+                    uint8_t* oy, uint8_t* ocb, uint8_t* ocr, uint8_t* oa) {
+  const int bpp = has_alpha ? 4 : 3, sh = (out_chroma == 1 || out_chroma == 2) ? 2 : 1, sv = out_chroma == 1 ? 2 : 1;
+  const int cw = (w + sh - 1) / sh;
+  if (mc == 2) mc = 6;                                       /* convert_colorspace() works on a copy of the target profile with the */
+  if (cp == 2) cp = 1;                                       /* unspecified values replaced (nclx.cc:360-373, colorconversion.cc:513-515) */
+  float Kr, Kb; co_kr_kb(mc, cp, &Kr, &Kb);
+  float c[3][3];
+  if (Kb != 0 || Kr != 0) {                                  /* nclx.cc:176-200 */
+    c[0][0] = Kr; c[0][1] = 1 - Kr - Kb; c[0][2] = Kb;
+    c[1][0] = -Kr / (1 - Kb) / 2; c[1][1] = -(1 - Kr - Kb) / (1 - Kb) / 2; c[1][2] = 0.5f;
+    c[2][0] = 0.5f; c[2][1] = -(1 - Kr - Kb) / (1 - Kr) / 2; c[2][2] = -Kb / (1 - Kr) / 2;
+  } else {
+    c[0][0] = 0.299f; c[0][1] = 0.587f; c[0][2] = 0.114f; c[1][0] = -0.168735f; c[1][1] = -0.331264f; c[1][2] = 0.5f;
+    c[2][0] = 0.5f; c[2][1] = -0.418688f; c[2][2] = -0.081312f;
+  }
+  for (int y = 0; y < h; y++) for (int x = 0; x < w; x++) {
+    const uint8_t* p = in + (size_t)y * in_stride + (size_t)x * bpp;
+    float yv = p[0] * c[0][0] + p[1] * c[0][1] + p[2] * c[0][2];
+    oy[(size_t)y * w + x] = full ? (uint8_t)co_clip_f_u8(yv) : (uint8_t)(clip_f_u16(yv * 0.85547f, 219) + 16);
+    if (oa) oa[(size_t)y * w + x] = has_alpha ? p[3] : 0xff;
+  }
+  if (sh == 1 && sv == 1) {
+    for (int y = 0; y < h; y++) for (int x = 0; x < w; x++) { const uint8_t* p = in + (size_t)y * in_stride + (size_t)x * bpp; co_set_chroma(ocb + (size_t)y * cw + x, ocr + (size_t)y * cw + x, p[0], p[1], p[2], c, full); }
+  } else if (sh == 2 && sv == 2) {
+    for (int y = 0; y < (h & ~1); y += 2) for (int x = 0; x < (w & ~1); x += 2) {
+      const uint8_t* p = in + (size_t)y * in_stride + (size_t)x * bpp;
+      int r = (uint8_t)((p[0] + p[bpp + 0] + p[in_stride + 0] + p[bpp + in_stride + 0]) / 4);
+      int g = (uint8_t)((p[1] + p[bpp + 1] + p[in_stride + 1] + p[bpp + in_stride + 1]) / 4);
+      int b = (uint8_t)((p[2] + p[bpp + 2] + p[in_stride + 2] + p[bpp + in_stride + 2]) / 4);
+      co_set_chroma(ocb + (size_t)(y / 2) * cw + x / 2, ocr + (size_t)(y / 2) * cw + x / 2, r, g, b, c, full);
+    }
+    if (w & 1) {                                              /* right column */
+      const int x = w - 1;
+      for (int y = 0; y < h; y += 2) {
+        const uint8_t* p = in + (size_t)y * in_stride + (size_t)x * bpp;
+        int r, g, b;
+        if (y + 1 < h) { r = (uint8_t)((p[0] + p[in_stride + 0]) / 2); g = (uint8_t)((p[1] + p[in_stride + 1]) / 2); b = (uint8_t)((p[2] + p[in_stride + 2]) / 2); }
+        else { r = p[0]; g = p[1]; b = p[2]; }
+        co_set_chroma(ocb + (size_t)(y / 2) * cw + x / 2, ocr + (size_t)(y / 2) * cw + x / 2, r, g, b, c, full);
+      }
+    }
+    if (h & 1) {                                              /* bottom row */
+      const int y = h - 1;
+      for (int x = 0; x < w; x += 2) {
+        const uint8_t* p = in + (size_t)y * in_stride + (size_t)x * bpp;
+        int r, g, b;
+        if (x + 1 < w) { r = (uint8_t)((p[0] + p[bpp + 0]) / 2); g = (uint8_t)((p[1] + p[bpp + 1]) / 2); b = (uint8_t)((p[2] + p[bpp + 2]) / 2); }
+        else { r = p[0]; g = p[1]; b = p[2]; }
+        co_set_chroma(ocb + (size_t)(y / 2) * cw + x / 2, ocr + (size_t)(y / 2) * cw + x / 2, r, g, b, c, full);
+      }
+    }
+  } else {                                                    /* 4:2:2, left-aligned chroma (rgb2yuv.cc:760-787) */
+    for (int y = 0; y < h; y++) for (int x = 0; x < w; x += 2) {
+      const uint8_t* p = in + (size_t)y * in_stride + (size_t)x * bpp;
+      co_set_chroma(ocb + (size_t)y * cw + x / 2, ocr + (size_t)y * cw + x / 2, p[0], p[1], p[2], c, full);
+    }
+  }
+  return 0;
+}

@@ -191,6 +191,39 @@ extern "C" int ref_postprocess(const void* y, const void* cb, const void* cr, co
   return 0;
 }
 
+// ---- encoder side: the reference's own conversion of interleaved 8-bit RGB / RGBA to YCbCr, as
+// heif_context_encode_image() performs it before an encoder plugin sees the picture (convert_colorspace picks Op_RGB24_32_to_YCbCr).
+// Packed planes out: Y (w x h), Cb, Cr (cw x ch), optional alpha.
+extern "C" int ref_rgb_to_ycbcr(const uint8_t* rgb, int w, int h, int has_alpha, int out_chroma, int cp, int tc, int mc, int full_range,
+                                uint8_t* oy, uint8_t* ocb, uint8_t* ocr, uint8_t* oa) {
+  const heif_security_limits* limits = heif_get_global_security_limits();
+  auto img = std::make_shared<HeifPixelImage>();
+  img->create(w, h, heif_colorspace_RGB, has_alpha ? heif_chroma_interleaved_RGBA : heif_chroma_interleaved_RGB);
+  if (img->add_channel(heif_channel_interleaved, w, h, 8, limits)) return -1;
+  { size_t stride; uint8_t* dst = img->get_channel_memory(heif_channel_interleaved, &stride); const int bpp = has_alpha ? 4 : 3;
+    for (int r = 0; r < h; r++) memcpy(dst + r * stride, rgb + (size_t)r * w * bpp, (size_t)w * bpp); }
+  nclx_profile target;
+  target.set_colour_primaries((uint16_t)cp); target.set_transfer_characteristics((uint16_t)tc);
+  target.set_matrix_coefficients((uint16_t)mc); target.set_full_range_flag(full_range != 0);
+  heif_color_conversion_options copt{};
+  copt.version = 1;
+  copt.preferred_chroma_downsampling_algorithm = heif_chroma_downsampling_average;
+  copt.preferred_chroma_upsampling_algorithm = heif_chroma_upsampling_bilinear;
+  copt.only_use_preferred_chroma_algorithm = 0;
+  auto res = convert_colorspace(img, heif_colorspace_YCbCr, (heif_chroma)out_chroma, target, 8, copt, nullptr, limits);
+  if (!res) return -4;
+  auto o = *res;
+  struct { heif_channel c; uint8_t* p; } pl[4] = {{heif_channel_Y, oy}, {heif_channel_Cb, ocb}, {heif_channel_Cr, ocr}, {heif_channel_Alpha, oa}};
+  for (auto& q : pl) {
+    if (!q.p) continue;
+    if (!o->has_channel(q.c)) { if (q.c == heif_channel_Alpha) continue; return -5; }
+    size_t stride; const uint8_t* src = o->get_channel_memory(q.c, &stride);
+    const int pw = o->get_width(q.c), ph = o->get_height(q.c);
+    for (int r = 0; r < ph; r++) memcpy(q.p + (size_t)r * pw, src + r * stride, (size_t)pw);
+  }
+  return 0;
+}
+
 // ---- a11 / a12: the reference's own overlay compositing and nearest-neighbour scaler, driven on caller-provided planes.
 // Packed 8-bit planes R,G,B[,A] (row-major, w bytes per row) in, canvas planes R,G,B out.
 extern "C" int ref_overlay(int cw, int ch, const uint16_t bkg[4], int noverlays, const uint8_t* const* ov_data, const int* ov_w, const int* ov_h,
