@@ -103,6 +103,21 @@ int b200_color_convert_device(const b200_planes* in, const b200_geometry* geom, 
 int b200_color_convert_host(const b200_planes* in, const b200_geometry* geom, const b200_color_options* opt,
                             void* out, void* out_g, void* out_b, size_t out_stride, int* pipeline);
 
+/* Encoder-side direction (what heif_context_encode_image runs before the encoder plugin sees the picture,
+   HeifContext::encode_image -> Encoder::convert_colorspace_for_encoding, libheif/context.cc:1642, libheif/codecs/encoder.cc:116-175):
+   interleaved RGB (has_alpha = 0, 3 bytes / pixel) or RGBA (has_alpha = 1, 4 bytes / pixel), 8 bit
+     -> planar YCbCr 8 bit in the chroma format, matrix and range that `out` names.
+   Replaces: Op_RGB24_32_to_YCbCr::convert_colorspace   libheif/color-conversion/rgb2yuv.cc:575-808
+             (float arithmetic in the reference's order; 4:2:0 chroma from the integer mean of the 2x2 RGB quad with the
+              reference's odd-width / odd-height border rules; 4:2:2 chroma from the left pixel; limited range
+              Y*0.85547+16, C*0.875+128; nclx "unspecified" (2) -> matrix 6 / primaries 1 as colorconversion.cc:513-515 does)
+   `out`: caller-owned planes, written through the (const-declared) pointers of b200_planes (y, cb, cr required; alpha optional: receives the source alpha, or 0xff when has_alpha = 0),
+   width / height / chroma (B200_CHROMA_420 / 422 / 444) / bit_depth (8) / colour_primaries / matrix_coefficients /
+   full_range are inputs.  matrix_coefficients 0, 8, 11, 14 -> B200_E_UNSUPPORTED (the reference's op refuses them as
+   well, rgb2yuv.cc:536-539). */
+int b200_rgb_to_ycbcr_device(const void* rgb, size_t rgb_stride, int has_alpha, const b200_planes* out, void* stream);
+int b200_rgb_to_ycbcr_host(const void* rgb, size_t rgb_stride, int has_alpha, const b200_planes* out);
+
 /* nclx helper: the 4 float coefficients exactly as nclx.cc:84-173 derives them */
 void b200_ycbcr_to_rgb_coefficients(int matrix_coefficients, int colour_primaries, float out_coeffs[4] /* r_cr,g_cb,g_cr,b_cb */);
 

@@ -57,6 +57,8 @@ def lib():
                                                  C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.POINTER(C.c_int)]
         _lib.b200_ycbcr_to_rgb_coefficients.argtypes = [C.c_int, C.c_int, C.POINTER(C.c_float)]
         _lib.b200_ycbcr_to_rgb_coefficients.restype = None
+        _lib.b200_rgb_to_ycbcr_device.argtypes = [C.c_void_p, C.c_size_t, C.c_int, C.POINTER(Planes), C.c_void_p]
+        _lib.b200_rgb_to_ycbcr_host.argtypes = [C.c_void_p, C.c_size_t, C.c_int, C.POINTER(Planes)]
     return _lib
 
 

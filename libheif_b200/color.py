@@ -130,3 +130,49 @@ def convert_colorspace_host(img: YCbCrImage, out_chroma: int, geometry: Optional
         o, og, ob, ostride = out.ctypes.data, None, None, out.strides[0]
     _lib.check(l.b200_color_convert_host(C.byref(planes), C.byref(geom.g), C.byref(opt), o, og, ob, ostride, C.byref(pipe)))
     return out, pipe.value
+
+
+def _ycc_out_planes(w, h, out_chroma, want_alpha, alloc):
+    sh = 0 if out_chroma == CHROMA_444 else 1
+    sv = 1 if out_chroma == CHROMA_420 else 0
+    y = alloc((h, w))
+    cb = alloc(((h + sv) >> sv, (w + sh) >> sh))
+    cr = alloc(((h + sv) >> sv, (w + sh) >> sh))
+    a = alloc((h, w)) if want_alpha else None
+    return y, cb, cr, a
+
+
+def rgb_to_ycbcr(rgb, out_chroma: int = CHROMA_420, matrix_coefficients: int = 6, colour_primaries: int = 1, full_range: bool = True,
+                 want_alpha: Optional[bool] = None, stream=None) -> YCbCrImage:
+    """Encoder-side direction, device -> device: interleaved RGB / RGBA (CUDA uint8 tensor [H, W, 3 or 4]) -> YCbCrImage of
+    CUDA uint8 planes, as Op_RGB24_32_to_YCbCr does (libheif/color-conversion/rgb2yuv.cc:575-808).
+    want_alpha: None = an alpha plane iff the source has one (what the reference's planner targets for has_alpha)."""
+    import torch
+    assert rgb.dtype == torch.uint8 and rgb.dim() == 3 and rgb.shape[2] in (3, 4) and rgb.stride(2) == 1 and rgb.stride(1) == rgb.shape[2]
+    h, w, bpp = rgb.shape
+    if want_alpha is None:
+        want_alpha = bpp == 4
+    y, cb, cr, a = _ycc_out_planes(w, h, out_chroma, want_alpha, lambda s: torch.empty(s, dtype=torch.uint8, device=rgb.device))
+    img = YCbCrImage(y, cb, cr, a, chroma=out_chroma, bit_depth=8, colour_primaries=colour_primaries,
+                     matrix_coefficients=matrix_coefficients, full_range=full_range)
+    planes = _fill_planes(img, lambda t: t.data_ptr(), lambda t: t.stride(0) * t.element_size())
+    s = stream if stream is not None else torch.cuda.current_stream(rgb.device)
+    with torch.cuda.device(rgb.device):
+        _lib.check(_lib.lib().b200_rgb_to_ycbcr_device(C.c_void_p(rgb.data_ptr()), C.c_size_t(rgb.stride(0)), int(bpp == 4), C.byref(planes),
+                                                       C.c_void_p(s.cuda_stream)))
+    return img
+
+
+def rgb_to_ycbcr_host(rgb: np.ndarray, out_chroma: int = CHROMA_420, matrix_coefficients: int = 6, colour_primaries: int = 1,
+                      full_range: bool = True, want_alpha: Optional[bool] = None) -> YCbCrImage:
+    """Host -> host through the C ABI (H2D + kernel + D2H inside the call). rgb: uint8 [H, W, 3 or 4], rows may be strided."""
+    assert rgb.dtype == np.uint8 and rgb.ndim == 3 and rgb.shape[2] in (3, 4) and rgb.strides[2] == 1 and rgb.strides[1] == rgb.shape[2]
+    h, w, bpp = rgb.shape
+    if want_alpha is None:
+        want_alpha = bpp == 4
+    y, cb, cr, a = _ycc_out_planes(w, h, out_chroma, want_alpha, lambda s: np.empty(s, np.uint8))
+    img = YCbCrImage(y, cb, cr, a, chroma=out_chroma, bit_depth=8, colour_primaries=colour_primaries,
+                     matrix_coefficients=matrix_coefficients, full_range=full_range)
+    planes = _fill_planes(img, lambda x: x.ctypes.data, lambda x: x.strides[0])
+    _lib.check(_lib.lib().b200_rgb_to_ycbcr_host(C.c_void_p(rgb.ctypes.data), C.c_size_t(rgb.strides[0]), int(bpp == 4), C.byref(planes)))
+    return img

@@ -135,4 +135,44 @@ int b200_color_convert_host(const b200_planes* in, const b200_geometry* geom, co
   return rc;
 }
 
+int b200_rgb_to_ycbcr_device(const void* rgb, size_t rgb_stride, int has_alpha, const b200_planes* out, void* stream) {
+  return launch_rgb_to_ycbcr(rgb, rgb_stride, has_alpha, out, (cudaStream_t)stream);
+}
+
+int b200_rgb_to_ycbcr_host(const void* rgb, size_t rgb_stride, int has_alpha, const b200_planes* out) {
+  if (!rgb || !out || !out->y) return set_error(B200_E_INVALID, "null argument");
+  if (out->width <= 0 || out->height <= 0) return B200_OK;
+  if (out->chroma != B200_CHROMA_420 && out->chroma != B200_CHROMA_422 && out->chroma != B200_CHROMA_444)
+    return set_error(B200_E_UNSUPPORTED, "RGB -> YCbCr: target chroma %d", out->chroma);
+  if (!out->cb || !out->cr) return set_error(B200_E_INVALID, "RGB -> YCbCr: chroma planes missing");
+  const int w = out->width, h = out->height, bpp = has_alpha ? 4 : 3;
+  const int sh = out->chroma == B200_CHROMA_444 ? 0 : 1, sv = out->chroma == B200_CHROMA_420 ? 1 : 0;
+  const int cw = (w + sh) >> sh, ch = (h + sv) >> sv;
+  const size_t ipitch = (((size_t)w * bpp) + 255) & ~(size_t)255, ypitch = ((size_t)w + 255) & ~(size_t)255, cpitch = ((size_t)cw + 255) & ~(size_t)255;
+  char *din = nullptr, *dy = nullptr, *dcb = nullptr, *dcr = nullptr, *da = nullptr;
+  cudaStream_t s; B200_CUDA_CHECK(cudaStreamCreate(&s));
+  int rc = B200_OK;
+  auto fail = [&](cudaError_t e, const char* what) { if (e != cudaSuccess && rc == B200_OK) rc = set_error(B200_E_CUDA, "%s: %s", what, cudaGetErrorString(e)); };
+  fail(cudaMalloc(&din, ipitch * h), "cudaMalloc");
+  fail(cudaMalloc(&dy, ypitch * h), "cudaMalloc");
+  fail(cudaMalloc(&dcb, cpitch * ch), "cudaMalloc");
+  fail(cudaMalloc(&dcr, cpitch * ch), "cudaMalloc");
+  if (out->alpha) fail(cudaMalloc(&da, ypitch * h), "cudaMalloc");
+  if (rc == B200_OK) fail(cudaMemcpy2DAsync(din, ipitch, rgb, rgb_stride, (size_t)w * bpp, h, cudaMemcpyHostToDevice, s), "H2D");
+  if (rc == B200_OK) {
+    b200_planes d = *out;
+    d.y = dy; d.cb = dcb; d.cr = dcr; d.alpha = da; d.y_stride = ypitch; d.c_stride = cpitch; d.alpha_stride = ypitch;
+    rc = launch_rgb_to_ycbcr(din, ipitch, has_alpha, &d, s);
+  }
+  if (rc == B200_OK) {
+    fail(cudaMemcpy2DAsync((void*)out->y, out->y_stride, dy, ypitch, w, h, cudaMemcpyDeviceToHost, s), "D2H");
+    fail(cudaMemcpy2DAsync((void*)out->cb, out->c_stride, dcb, cpitch, cw, ch, cudaMemcpyDeviceToHost, s), "D2H");
+    fail(cudaMemcpy2DAsync((void*)out->cr, out->c_stride, dcr, cpitch, cw, ch, cudaMemcpyDeviceToHost, s), "D2H");
+    if (out->alpha) fail(cudaMemcpy2DAsync((void*)out->alpha, out->alpha_stride, da, ypitch, w, h, cudaMemcpyDeviceToHost, s), "D2H");
+    fail(cudaStreamSynchronize(s), "sync");
+  }
+  cudaFree(din); cudaFree(dy); cudaFree(dcb); cudaFree(dcr); cudaFree(da); cudaStreamDestroy(s);
+  return rc;
+}
+
 }  // extern "C"

@@ -646,4 +646,162 @@ int launch_color(const b200_planes* in, const b200_geometry* g, const b200_color
   return B200_OK;
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Encoder-side colour op: interleaved RGB / RGBA 8 bit -> planar YCbCr 4:2:0 / 4:2:2 / 4:4:4 8 bit
+// (Op_RGB24_32_to_YCbCr, rgb2yuv.cc:575-808: float arithmetic in the reference's order, chroma of 4:2:0 from the integer
+// mean of the 2x2 RGB quad -- 2x1 / 1x2 / 1x1 on an odd right column / bottom row --, chroma of 4:2:2 from the left pixel).
+// One thread converts a 4 x 2 pixel block: 12 / 16 bytes per row in (vector loads when the rows are aligned), 4 luma bytes
+// per row and 2..4 chroma bytes per plane out.  HBM bound: 3 or 4 bytes read, 1.5 .. 4 bytes written per pixel.
+// ---------------------------------------------------------------------------------------------------------------
+struct RgbToYccArgs {
+  const uint8_t* in; long long in_stride;
+  uint8_t *y, *cb, *cr, *a; long long ys, cs, as;
+  int w, h, chroma, full, vec_in, vec_out;
+  float c[3][3];
+};
+__device__ __forceinline__ int clip_round(float v, int maxv) {
+  const int x = __float2int_rz(__fadd_rn(v, 0.5f));
+  return x < 0 ? 0 : (x > maxv ? maxv : x);
+}
+__device__ __forceinline__ float dot3(int r, int g, int b, const float* c) {
+  return __fadd_rn(__fadd_rn(__fmul_rn((float)r, c[0]), __fmul_rn((float)g, c[1])), __fmul_rn((float)b, c[2]));
+}
+__device__ __forceinline__ void put_chroma(const RgbToYccArgs& p, int r, int g, int b, uint8_t* ocb, uint8_t* ocr) {
+  const float cb = dot3(r, g, b, p.c[1]), cr = dot3(r, g, b, p.c[2]);
+  if (p.full) { *ocb = (uint8_t)clip_round(__fadd_rn(cb, 128.0f), 255); *ocr = (uint8_t)clip_round(__fadd_rn(cr, 128.0f), 255); }
+  else {
+    *ocb = (uint8_t)clip_round(__fadd_rn(__fmul_rn(cb, 0.875f), 128.0f), 255);
+    *ocr = (uint8_t)clip_round(__fadd_rn(__fmul_rn(cr, 0.875f), 128.0f), 255);
+  }
+}
+__device__ __forceinline__ void store_bytes(uint8_t* dst, const uint8_t* v, int n, bool vec) {
+  if (vec && n == 4) *(uint32_t*)dst = (uint32_t)v[0] | ((uint32_t)v[1] << 8) | ((uint32_t)v[2] << 16) | ((uint32_t)v[3] << 24);
+  else if (vec && n == 2) *(uint16_t*)dst = (uint16_t)((unsigned)v[0] | ((unsigned)v[1] << 8));
+  else for (int i = 0; i < n; i++) dst[i] = v[i];
+}
+template <int BPP>
+__global__ void __launch_bounds__(256) rgb_to_ycbcr_kernel(const RgbToYccArgs p) {
+  const int x0 = (blockIdx.x * 64 + threadIdx.x) * 4, y0 = (blockIdx.y * 4 + threadIdx.y) * 2;
+  if (x0 >= p.w || y0 >= p.h) return;
+  const int nx = min(4, p.w - x0), ny = min(2, p.h - y0);
+  uint8_t px[2][4][4];
+#pragma unroll
+  for (int j = 0; j < 2; j++) {
+    if (j >= ny) break;
+    const uint8_t* row = p.in + (long long)(y0 + j) * p.in_stride + (long long)x0 * BPP;
+    if (p.vec_in && nx == 4) {
+      if (BPP == 4) {
+        const uint4 v = __ldg((const uint4*)row);
+        const uint32_t q[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int i = 0; i < 4; i++) { px[j][i][0] = q[i] & 255; px[j][i][1] = (q[i] >> 8) & 255; px[j][i][2] = (q[i] >> 16) & 255; px[j][i][3] = q[i] >> 24; }
+      } else {
+        const uint32_t a = __ldg((const uint32_t*)row), b = __ldg((const uint32_t*)row + 1), c = __ldg((const uint32_t*)row + 2);
+        px[j][0][0] = a & 255; px[j][0][1] = (a >> 8) & 255; px[j][0][2] = (a >> 16) & 255;
+        px[j][1][0] = a >> 24; px[j][1][1] = b & 255; px[j][1][2] = (b >> 8) & 255;
+        px[j][2][0] = (b >> 16) & 255; px[j][2][1] = b >> 24; px[j][2][2] = c & 255;
+        px[j][3][0] = (c >> 8) & 255; px[j][3][1] = (c >> 16) & 255; px[j][3][2] = c >> 24;
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < 4; i++) {
+        if (i >= nx) break;
+#pragma unroll
+        for (int k = 0; k < BPP; k++) px[j][i][k] = __ldg(row + i * BPP + k);
+      }
+    }
+  }
+  const bool vo = p.vec_out != 0;
+  // luma (rgb2yuv.cc:640-665) and alpha (:667-691: copied, or 0xff when the source has none)
+#pragma unroll
+  for (int j = 0; j < 2; j++) {
+    if (j >= ny) break;
+    uint8_t yv[4], av[4];
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+      if (i >= nx) break;
+      const float f = dot3(px[j][i][0], px[j][i][1], px[j][i][2], p.c[0]);
+      yv[i] = p.full ? (uint8_t)clip_round(f, 255) : (uint8_t)(clip_round(__fmul_rn(f, 0.85547f), 219) + 16);
+      av[i] = BPP == 4 ? px[j][i][3] : 0xff;
+    }
+    store_bytes(p.y + (long long)(y0 + j) * p.ys + x0, yv, nx, vo);
+    if (p.a) store_bytes(p.a + (long long)(y0 + j) * p.as + x0, av, nx, vo);
+  }
+  if (p.chroma == B200_CHROMA_444) {
+#pragma unroll
+    for (int j = 0; j < 2; j++) {
+      if (j >= ny) break;
+      uint8_t vb[4], vr[4];
+#pragma unroll
+      for (int i = 0; i < 4; i++) { if (i >= nx) break; put_chroma(p, px[j][i][0], px[j][i][1], px[j][i][2], &vb[i], &vr[i]); }
+      store_bytes(p.cb + (long long)(y0 + j) * p.cs + x0, vb, nx, vo);
+      store_bytes(p.cr + (long long)(y0 + j) * p.cs + x0, vr, nx, vo);
+    }
+  } else if (p.chroma == B200_CHROMA_422) {
+    const int nc = (nx + 1) >> 1;
+#pragma unroll
+    for (int j = 0; j < 2; j++) {
+      if (j >= ny) break;
+      uint8_t vb[2], vr[2];
+#pragma unroll
+      for (int i = 0; i < 2; i++) { if (i >= nc) break; put_chroma(p, px[j][2 * i][0], px[j][2 * i][1], px[j][2 * i][2], &vb[i], &vr[i]); }
+      store_bytes(p.cb + (long long)(y0 + j) * p.cs + (x0 >> 1), vb, nc, vo);
+      store_bytes(p.cr + (long long)(y0 + j) * p.cs + (x0 >> 1), vr, nc, vo);
+    }
+  } else {
+    const int nc = (nx + 1) >> 1;
+    uint8_t vb[2], vr[2];
+#pragma unroll
+    for (int i = 0; i < 2; i++) {
+      if (i >= nc) break;
+      const int qx = (2 * i + 1 < nx) ? 2 : 1, n = qx * ny;
+      int s[3];
+#pragma unroll
+      for (int k = 0; k < 3; k++) {
+        int t = px[0][2 * i][k];
+        if (qx == 2) t += px[0][2 * i + 1][k];
+        if (ny == 2) { t += px[1][2 * i][k]; if (qx == 2) t += px[1][2 * i + 1][k]; }
+        s[k] = t / n;
+      }
+      put_chroma(p, s[0], s[1], s[2], &vb[i], &vr[i]);
+    }
+    store_bytes(p.cb + (long long)(y0 >> 1) * p.cs + (x0 >> 1), vb, nc, vo);
+    store_bytes(p.cr + (long long)(y0 >> 1) * p.cs + (x0 >> 1), vr, nc, vo);
+  }
+}
+
+int launch_rgb_to_ycbcr(const void* rgb, size_t rgb_stride, int has_alpha, const b200_planes* out, cudaStream_t stream) {
+  if (!rgb || !out || !out->y) return set_error(B200_E_INVALID, "null argument");
+  if (out->bit_depth != 8) return set_error(B200_E_UNSUPPORTED, "RGB -> YCbCr: %d-bit target (the 8-bit interleaved op only)", out->bit_depth);
+  if (out->chroma != B200_CHROMA_420 && out->chroma != B200_CHROMA_422 && out->chroma != B200_CHROMA_444)
+    return set_error(B200_E_UNSUPPORTED, "RGB -> YCbCr: target chroma %d", out->chroma);
+  if (!out->cb || !out->cr) return set_error(B200_E_INVALID, "RGB -> YCbCr: chroma planes missing");
+  int mc = out->matrix_coefficients, cp = out->colour_primaries;
+  if (mc == 0 || mc == 8 || mc == 11 || mc == 14)
+    return set_error(B200_E_UNSUPPORTED, "matrix_coefficients %d: not converted by this operation in the reference either (rgb2yuv.cc:536-539)", mc);
+  if (mc == 2) mc = 6;              // unspecified -> sRGB defaults, as convert_colorspace() does with the target profile
+  if (cp == 2) cp = 1;              // (nclx.cc:360-373 through colorconversion.cc:513-515)
+  if (out->width <= 0 || out->height <= 0) return B200_OK;
+  const int bpp = has_alpha ? 4 : 3;
+  if (rgb_stride < (size_t)out->width * bpp) return set_error(B200_E_INVALID, "RGB stride %zu < row of %d pixels", rgb_stride, out->width);
+  RgbToYccArgs a;
+  a.in = (const uint8_t*)rgb; a.in_stride = (long long)rgb_stride;
+  a.y = (uint8_t*)out->y; a.cb = (uint8_t*)out->cb; a.cr = (uint8_t*)out->cr; a.a = (uint8_t*)out->alpha;
+  a.ys = (long long)out->y_stride; a.cs = (long long)out->c_stride; a.as = (long long)out->alpha_stride;
+  a.w = out->width; a.h = out->height; a.chroma = out->chroma; a.full = out->full_range ? 1 : 0;
+  rgb_to_ycbcr_coefficients(mc, cp, a.c);
+  const uintptr_t ai = (uintptr_t)rgb | (uintptr_t)rgb_stride;
+  a.vec_in = (ai & (has_alpha ? 15 : 3)) == 0;
+  uintptr_t ao = (uintptr_t)out->y | (uintptr_t)out->cb | (uintptr_t)out->cr | (uintptr_t)out->y_stride | (uintptr_t)out->c_stride;
+  if (out->alpha) ao |= (uintptr_t)out->alpha | (uintptr_t)out->alpha_stride;
+  a.vec_out = (ao & 3) == 0;
+  const dim3 block(64, 4), grid((a.w + 255) / 256, (a.h + 7) / 8);
+  if (has_alpha) rgb_to_ycbcr_kernel<4><<<grid, block, 0, stream>>>(a);
+  else rgb_to_ycbcr_kernel<3><<<grid, block, 0, stream>>>(a);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return set_error(B200_E_CUDA, "RGB -> YCbCr launch: %s", cudaGetErrorString(e));
+  return B200_OK;
+}
+
+
 }  // namespace b200

@@ -21,5 +21,6 @@ int set_error(int code, const char* fmt, ...);     // records a thread-local mes
 void ycbcr_to_rgb_coefficients(int matrix, int primaries, float out[4]);
 int launch_color(const b200_planes* in, const b200_geometry* g, const b200_color_options* opt, void* out, void* out_g,
                  void* out_b, size_t out_stride, cudaStream_t stream, int* pipeline);
+int launch_rgb_to_ycbcr(const void* rgb, size_t rgb_stride, int has_alpha, const b200_planes* out, cudaStream_t stream);
 
 }  // namespace b200

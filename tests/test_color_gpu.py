@@ -191,3 +191,77 @@ def test_bilinear_after_geometry(cuda, ops):
     want, ow, oh = oracle_postprocess(y, cb, cr, None, 1, 8, (1, 13, 6, 0), ops, 10, bilinear=1)
     out = lb.convert_colorspace(_img(y, cb, cr, None, 1, 8, (1, 13, 6, 0), cuda), 10, _geom(32, 24, ops, 1), bilinear=True)
     assert np.array_equal(_as_bytes(out), want)
+
+
+# ---- encoder-side direction: RGB / RGBA 8 bit -> YCbCr (b200_rgb_to_ycbcr_device / _host vs oracle/color_oracle.c) ----
+from test_color_oracle import RGB2YCC_NCLX, RGB2YCC_SIZES, rgb_pattern  # noqa: E402
+
+
+def _check_ycc(img, ref, what):
+    for name, g, r in zip("Y Cb Cr A".split(), (img.y, img.cb, img.cr, img.alpha), ref):
+        if r is None:
+            assert g is None
+            continue
+        g = g.cpu().numpy() if hasattr(g, "cpu") else g
+        assert g.shape == r.shape, (what, name, g.shape, r.shape)
+        assert np.array_equal(g, r), f"{what}: {name} differs, first at {np.argwhere(g != r)[:3].tolist()}"
+
+
+@pytest.mark.parametrize("size", RGB2YCC_SIZES + [(517, 259), (1024, 512), (1030, 77)])
+@pytest.mark.parametrize("alpha", [0, 1])
+@pytest.mark.parametrize("out_chroma", [1, 2, 3])
+def test_rgb_to_ycbcr_device_matches_oracle(cuda, size, alpha, out_chroma):
+    import torch
+    from oracle.bindings import oracle_rgb_to_ycbcr
+    w, h = size
+    bpp = 4 if alpha else 3
+    rgb = rgb_pattern(0xC0DE + w * 13 + h, w, h, bpp)
+    t = torch.from_numpy(rgb.reshape(h, w, bpp)).cuda()
+    for nclx in RGB2YCC_NCLX:
+        cp, _, mc, fr = nclx
+        img = lb.rgb_to_ycbcr(t, out_chroma, matrix_coefficients=mc, colour_primaries=cp, full_range=bool(fr))
+        torch.cuda.synchronize()
+        _check_ycc(img, oracle_rgb_to_ycbcr(rgb, alpha, out_chroma, nclx), f"{size} alpha={alpha} chroma={out_chroma} nclx={nclx}")
+
+
+@pytest.mark.parametrize("out_chroma", [1, 2, 3])
+def test_rgb_to_ycbcr_unaligned_rows_and_host_call(cuda, out_chroma):
+    """Odd row pitch / odd base address take the byte-wise load path; RGB without alpha into an alpha plane gives 0xff."""
+    import torch
+    from oracle.bindings import oracle_rgb_to_ycbcr
+    w, h = 203, 61
+    for bpp in (3, 4):
+        rgb = rgb_pattern(77 + bpp, w, h, bpp)
+        pitch = w * bpp + 5
+        buf = torch.zeros(h * pitch + 1, dtype=torch.uint8, device="cuda")
+        view = buf[1:].as_strided((h, w, bpp), (pitch, bpp, 1))
+        view.copy_(torch.from_numpy(rgb.reshape(h, w, bpp)).cuda())
+        nclx = (1, 13, 6, 0)
+        img = lb.rgb_to_ycbcr(view, out_chroma, matrix_coefficients=6, colour_primaries=1, full_range=False, want_alpha=True)
+        torch.cuda.synchronize()
+        ref = list(oracle_rgb_to_ycbcr(rgb, bpp == 4, out_chroma, nclx))
+        if bpp == 3:
+            ref[3] = np.full((h, w), 255, np.uint8)
+        _check_ycc(img, ref, f"strided bpp={bpp}")
+        himg = lb.rgb_to_ycbcr_host(rgb.reshape(h, w, bpp), out_chroma, matrix_coefficients=6, colour_primaries=1, full_range=False, want_alpha=True)
+        _check_ycc(himg, ref, f"host bpp={bpp}")
+
+
+@pytest.mark.parametrize("mc", [0, 8, 11, 14])
+def test_rgb_to_ycbcr_refuses_what_the_reference_op_refuses(cuda, mc):
+    import torch
+    t = torch.zeros((4, 4, 3), dtype=torch.uint8, device="cuda")
+    with pytest.raises(lb.B200Error) as e:
+        lb.rgb_to_ycbcr(t, 1, matrix_coefficients=mc)
+    assert e.value.code == -2            # B200_E_UNSUPPORTED
+
+
+def test_rgb_to_ycbcr_then_back_is_close(cuda):
+    """Size-independent property at a full-size picture: RGB -> YCbCr 4:4:4 full range -> RGB (K6) is within rounding of identity."""
+    import torch
+    w, h = 4096, 2048
+    g = torch.Generator(device="cuda").manual_seed(5)
+    rgb = torch.randint(0, 256, (h, w, 3), dtype=torch.uint8, device="cuda", generator=g)
+    img = lb.rgb_to_ycbcr(rgb, 3, matrix_coefficients=6, colour_primaries=1, full_range=True)
+    back = lb.convert_colorspace(img, lb.CHROMA_INTERLEAVED_RGB).reshape(h, w, 3)
+    assert (back.int() - rgb.int()).abs().max().item() <= 2

@@ -163,3 +163,38 @@ def test_444_detour_422_matches_reference(case, fmt):
     got, ow, oh = oracle_postprocess(y, cb, cr, a, 2, bpp, nclx, ops, outc)
     assert (ow, oh) == (rw, rh)
     assert np.array_equal(ref, got)
+
+
+# ---- encoder-side direction: Op_RGB24_32_to_YCbCr (rgb2yuv.cc:575-808) ----
+RGB2YCC_SIZES = [(1, 1), (2, 2), (3, 3), (5, 4), (4, 5), (16, 16), (33, 17), (64, 48)]
+RGB2YCC_NCLX = [(1, 13, 6, 1), (1, 13, 6, 0), (1, 13, 1, 1), (1, 13, 1, 0), (9, 16, 9, 0), (9, 16, 9, 1), (1, 13, 5, 1), (2, 2, 2, 0), (2, 2, 2, 1),
+                (1, 13, 12, 1), (9, 13, 13, 0), (1, 13, 4, 0), (1, 13, 7, 1)]
+
+
+def rgb_pattern(seed, w, h, bpp):
+    """LCG bytes with saturated corners and flat runs (clipping and rounding ties are where restatements go wrong)."""
+    rng = np.random.default_rng(seed)
+    img = rng.integers(0, 256, (h, w * bpp), dtype=np.uint8)
+    img[0, :bpp] = 255
+    img[-1, -bpp:] = 0
+    if w >= 4:
+        img[h // 2, : 2 * bpp] = np.tile(np.array([255, 0, 0, 128][:bpp], np.uint8), 2)
+    return img
+
+
+@needs_ref
+@pytest.mark.parametrize("size", RGB2YCC_SIZES)
+@pytest.mark.parametrize("alpha", [0, 1])
+@pytest.mark.parametrize("out_chroma", [1, 2, 3])
+def test_rgb_to_ycbcr_restatement_matches_reference(size, alpha, out_chroma):
+    from oracle.bindings import oracle_rgb_to_ycbcr, ref_rgb_to_ycbcr
+    w, h = size
+    rgb = rgb_pattern(0x5EED + w * 977 + h * 31 + alpha, w, h, 4 if alpha else 3)
+    for nclx in RGB2YCC_NCLX:
+        ref = ref_rgb_to_ycbcr(rgb, alpha, out_chroma, nclx)
+        got = oracle_rgb_to_ycbcr(rgb, alpha, out_chroma, nclx)
+        for name, r, g in zip("Y Cb Cr A".split(), ref, got):
+            if r is None:
+                assert g is None
+                continue
+            assert np.array_equal(r, g), f"{name} differs for nclx {nclx}: first at {np.argwhere(r != g)[:3].tolist()}"
