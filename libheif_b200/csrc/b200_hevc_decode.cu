@@ -164,6 +164,15 @@ static bool use_overlap(size_t n_subs) {
   int dev = 0, sms = 148; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   return n_subs <= (size_t)sms * 16;      // one wave of K0: 4 CTAs x 4 warps per SM
 }
+// TAIL overlap, for batches of more than one wave: K0 keeps the whole GPU (4 CTAs per SM, launched first) and the LIVE K1
+// is queued behind it on the other stream, so K1's CTAs become resident only where K0's persistent CTAs have left -- which
+// they do over the last ~30 % of K0's run time, once every sub-stream has been handed out and the wavefronts of the tiles
+// drain.  K1 (and, with bands, K3 / K4 / K6 / D2H of the first band) then runs in SM slots that would otherwise idle.
+// B200_TAIL_OVERLAP=0/1 forces it.
+static bool use_tail_overlap() {
+  if (const char* e = getenv("B200_TAIL_OVERLAP")) return atoi(e) != 0;
+  return false;
+}
 
 // Device half: K0 entropy decoding (device front-end only) on the side stream, concurrently K1 reconstruction on `s`
 // consuming the command stream CTB by CTB as K0 publishes it, then deblocking and SAO / paste on `s`.
@@ -177,6 +186,8 @@ static int run_device_pipeline(b200_decoder* d, int n, cudaStream_t s, int* laun
   const char* force = getenv("B200_CHUNKS");
   const bool chunked = d->nchunks > 1 && (d->chunk_hook || (force && atoi(force) != 0));
   bool overlap = devfe && !chunked && use_overlap(d->n_subs);
+  const bool tail = devfe && !overlap && !getenv("B200_OVERLAP") && use_tail_overlap();
+  if (tail) overlap = true;
   // K1 follows K0 through per-row progress counters in raster order; sub-streams of HEVC tiles produce CTBs tile by tile
   for (int i = 0; i < d->npics && overlap; i++) if (d->epics.h[i].sp.tiles) overlap = false;
   if (overlap) overlap = overlap_acquire(d);
@@ -196,15 +207,17 @@ static int run_device_pipeline(b200_decoder* d, int n, cudaStream_t s, int* laun
     for (int i = 0; i < d->npics && e.common; i++) if (!syn::matches_common(d->epics.h[i].sp)) e.common = 0;
     if (overlap) {
       if (!d->side) { B200_CUDA_CHECK(cudaStreamCreateWithFlags(&d->side, cudaStreamNonBlocking)); B200_CUDA_CHECK(cudaEventCreate(&d->ev_fork)); B200_CUDA_CHECK(cudaEventCreate(&d->ev_join)); }
-      e.blocks_per_sm = overlap_blocks("B200_OVERLAP_K0_BLOCKS", 3);
-      b.blocks_per_sm = overlap_blocks("B200_OVERLAP_K1_BLOCKS", 2);
+      e.blocks_per_sm = tail ? 0 : overlap_blocks("B200_OVERLAP_K0_BLOCKS", 3);
+      b.blocks_per_sm = tail ? 0 : overlap_blocks("B200_OVERLAP_K1_BLOCKS", 2);
       b.entropy_progress = e.progress;
       cudaEventRecord(d->ev_fork, s);
       B200_CUDA_CHECK(cudaStreamWaitEvent(d->side, d->ev_fork, 0));
-      if ((rc = launch_entropy(e, d->side))) return rc;
+      int k0_warps = 0;
+      if ((rc = launch_entropy(e, d->side, &k0_warps))) return rc;
       cudaEventRecord(d->ev[5], d->side);
       if ((rc = launch_entropy_stats(e, d->ecount.d, d->side))) return rc;
       cudaEventRecord(d->ev_join, d->side);
+      if (tail && (rc = launch_entropy_gate(e, k0_warps, s))) return rc;   // K1 (next on s) must not take the SMs before K0 has them
     } else {
       if ((rc = launch_entropy(e, s))) return rc;
       cudaEventRecord(d->ev[5], s);
@@ -221,6 +234,11 @@ static int run_device_pipeline(b200_decoder* d, int n, cudaStream_t s, int* laun
       DeviceBatch bc = b;
       bc.row_list = d->rows.d + d->chunk_item[c]; bc.nrows = (int)(d->chunk_item[c + 1] - d->chunk_item[c]); bc.ticket = b.ticket + c;
       if ((rc = launch_recon(bc, s))) return rc;
+      if (overlap && c + 1 == d->nchunks) {               // (tail overlap) K0 has finished before anything that follows the last band's K1
+        B200_CUDA_CHECK(cudaStreamWaitEvent(s, d->ev_join, 0));
+        B200_CUDA_CHECK(cudaLaunchHostFunc(s, overlap_done, nullptr));
+        release.armed = false;
+      }
       DeviceBatch bf = b;
       const int p0 = d->chunk_pic[c];
       bf.pics = d->pics.d + p0; bf.npics = d->chunk_pic[c + 1] - p0;

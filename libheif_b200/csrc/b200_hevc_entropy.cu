@@ -153,7 +153,26 @@ __global__ void entropy_stats_kernel(const EntropyBatch b, unsigned long long* o
   atomicAdd(out2, tus); atomicAdd(out2 + 1, coefs);
 }
 
-int launch_entropy(const EntropyBatch& b, cudaStream_t s) {
+// Tail overlap (b200_hevc_decode.cu): the stream that carries K1 passes this one-thread kernel first, so that K1's CTAs are
+// handed to the SMs only after K0's whole grid is resident (every decoder warp has popped its first queue slot).  Purely
+// a scheduling aid: it gives up after ~0.3 s and correctness never depends on it.
+__global__ void entropy_gate_kernel(const unsigned* qhead, unsigned need, const unsigned* error_flag) {
+  for (unsigned spins = 0; spins < 300000u; spins++) {
+    if (e_ld_acquire(qhead) >= need || e_ld_acquire(error_flag)) return;
+    __nanosleep(1000);
+  }
+}
+
+int launch_entropy_gate(const EntropyBatch& b, int resident_warps, cudaStream_t s) {
+  if (b.nsubs <= 0 || resident_warps <= 0) return B200_OK;
+  entropy_gate_kernel<<<1, 1, 0, s>>>(b.qhead, (unsigned)(resident_warps < b.nsubs ? resident_warps : b.nsubs), b.error_flag);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return set_error(B200_E_CUDA, "entropy gate launch: %s", cudaGetErrorString(e));
+  return B200_OK;
+}
+
+int launch_entropy(const EntropyBatch& b, cudaStream_t s, int* resident_warps) {
+  if (resident_warps) *resident_warps = 0;
   if (b.nsubs <= 0) return B200_OK;
   int dev = 0, sms = 148; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   // b.common: every picture of the batch has the CfgCommon parameter combination -> the specialised (smaller) kernel
@@ -164,6 +183,7 @@ int launch_entropy(const EntropyBatch& b, cudaStream_t s) {
   if (const char* e = getenv("B200_ENTROPY_BLOCKS_PER_SM")) { const int v = atoi(e); if (v >= 1 && v < occ) occ = v; }   // tuning knob
   const int want = (b.nsubs + EWARPS - 1) / EWARPS;
   const int grid = want < sms * occ ? want : sms * occ;
+  if (resident_warps) *resident_warps = grid * EWARPS;
   kern<<<grid, EWARPS * 32, 0, s>>>(b);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return set_error(B200_E_CUDA, "entropy launch: %s", cudaGetErrorString(e));
