@@ -325,6 +325,7 @@ def main():
         # the e2e legs above ran K1 .. K6 in row bands (D2H of a band overlaps the kernels of the next); the per-kernel times are
         # taken with one launch per kernel for the whole grid (B200_CHUNKS=0)
         os.environ["B200_CHUNKS"] = "0"
+        os.environ["B200_TAIL_OVERLAP"] = "0"          # per-kernel times: K1 after K0, not inside K0's draining tail
         dec.decode_grid(tiles, cols=side, rows=nrows)
         for _ in range(nk):
             dec.rerun_device(stream)
@@ -335,6 +336,7 @@ def main():
             overlapped = s.front_end == 2
             kern["entropy"] += s.entropy_ms / nk; kern["recon"] += s.recon_ms / nk; kern["deblock"] += s.deblock_ms / nk; kern["sao_paste"] += s.sao_ms / nk; kern["k6_colour"] += k0.elapsed_time(k1) / nk
     os.environ.pop("B200_CHUNKS", None)
+    os.environ.pop("B200_TAIL_OVERLAP", None)
     barrier()
     if rank != 0:
         if world > 1:
@@ -370,7 +372,8 @@ def main():
         "e2e_pipelined": {"value": pixels / 1e6 / (pipe_ms / 1e3), "unit": "MP/s", "ms_per_step": pipe_ms,
                           "api": "b200_decode_grid_to_rgb_host_async x steps + b200_decoder_wait: D2H of step i overlaps the kernels of step i + 1 (throughput of a batch job; e2e above is the latency of one call)"},
         "pipeline": {"bands": stats_e2e.bands, "entropy_ms_in_e2e_leg": stats_e2e.entropy_ms, "band_pipeline_ms_in_e2e_leg": stats_e2e.recon_ms + stats_e2e.deblock_ms + stats_e2e.sao_ms,
-                     "note": "e2e legs of large grids: after the entropy kernel the tile rows go through K1 -> K3 -> K4 -> K6 in row bands and the D2H of band c overlaps the kernels of band c + 1 (kernels_ms below: one launch per kernel for the whole grid, B200_CHUNKS=0)"},
+                     "tail_overlap": os.environ.get("B200_TAIL_OVERLAP", "1") != "0",
+                     "note": "e2e legs of large grids: the tile rows go through K1 -> K3 -> K4 -> K6 in row bands and the D2H of band c overlaps the kernels of band c + 1; K1 is queued behind the full-occupancy entropy kernel and follows it CTB by CTB in the SM slots its draining wavefronts free (tail overlap), so band_pipeline_ms is what remains after the entropy kernel has ended (kernels_ms below: one launch per kernel for the whole grid, one after the other: B200_CHUNKS=0 B200_TAIL_OVERLAP=0)"},
         "gpu_launches": (stats_e2e.kernel_launches + ((stats_e2e.kernel_launches - 1) // 4 if chunked else 1)) * args.steps,   # K0, (K1, K3 x2, K4, K6) per band -- of the e2e leg
         "clocks": clk.summary(),
         "roofline": {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,

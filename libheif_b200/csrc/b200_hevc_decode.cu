@@ -168,10 +168,14 @@ static bool use_overlap(size_t n_subs) {
 // is queued behind it on the other stream, so K1's CTAs become resident only where K0's persistent CTAs have left -- which
 // they do over the last ~30 % of K0's run time, once every sub-stream has been handed out and the wavefronts of the tiles
 // drain.  K1 (and, with bands, K3 / K4 / K6 / D2H of the first band) then runs in SM slots that would otherwise idle.
-// B200_TAIL_OVERLAP=0/1 forces it.
-static bool use_tail_overlap() {
-  if (const char* e = getenv("B200_TAIL_OVERLAP")) return atoi(e) != 0;
-  return false;
+// Measured on the bench grid (256 tiles, profiles/r02_tail_overlap_probe.json): resident step 76.1 -> 71.1 ms (K1 adds 1 - 2 ms
+// to K0 instead of 8.5), end to end 94.0 -> 89.5 ms with two row bands.
+// B200_TAIL_OVERLAP=0 switches it off; 1 (default): with row bands, one live K1 per band (the first band's K1 ends with K0, its
+// filters / K6 / D2H overlap the second band's K1); 2: ONE live K1 over the whole grid, bands only for K3 / K4 / K6 / D2H
+// (measured 3 ms slower end to end: nothing is left to overlap the first band's D2H).
+static int use_tail_overlap() {
+  if (const char* e = getenv("B200_TAIL_OVERLAP")) return atoi(e);
+  return 1;
 }
 
 // Device half: K0 entropy decoding (device front-end only) on the side stream, concurrently K1 reconstruction on `s`
@@ -186,7 +190,8 @@ static int run_device_pipeline(b200_decoder* d, int n, cudaStream_t s, int* laun
   const char* force = getenv("B200_CHUNKS");
   const bool chunked = d->nchunks > 1 && (d->chunk_hook || (force && atoi(force) != 0));
   bool overlap = devfe && !chunked && use_overlap(d->n_subs);
-  const bool tail = devfe && !overlap && !getenv("B200_OVERLAP") && use_tail_overlap();
+  const int tail_mode = use_tail_overlap();
+  const bool tail = devfe && !getenv("B200_OVERLAP") && tail_mode != 0 && (!overlap || getenv("B200_TAIL_FORCE"));   // B200_TAIL_FORCE: small batches too (tests)
   if (tail) overlap = true;
   // K1 follows K0 through per-row progress counters in raster order; sub-streams of HEVC tiles produce CTBs tile by tile
   for (int i = 0; i < d->npics && overlap; i++) if (d->epics.h[i].sp.tiles) overlap = false;
@@ -217,7 +222,7 @@ static int run_device_pipeline(b200_decoder* d, int n, cudaStream_t s, int* laun
       cudaEventRecord(d->ev[5], d->side);
       if ((rc = launch_entropy_stats(e, d->ecount.d, d->side))) return rc;
       cudaEventRecord(d->ev_join, d->side);
-      if (tail && (rc = launch_entropy_gate(e, k0_warps, s))) return rc;   // K1 (next on s) must not take the SMs before K0 has them
+      if (tail) { if ((rc = launch_entropy_gate(e, k0_warps, s))) return rc; launches += 1; }   // K1 (next on s) must not take the SMs before K0 has them
     } else {
       if ((rc = launch_entropy(e, s))) return rc;
       cudaEventRecord(d->ev[5], s);
@@ -230,11 +235,13 @@ static int run_device_pipeline(b200_decoder* d, int n, cudaStream_t s, int* laun
     // (K6 of the band + its D2H on the copy stream, which overlaps the kernels of band c + 1).  K0 is NOT part of this:
     // letting the bands leave K0 in order (priority queues) and running these kernels beside it was measured slower --
     // K0 loses more from the co-residency (3 instead of 4 CTAs per SM) and the priorities than the overlap gains.
+    const bool one_k1 = overlap && tail_mode == 2;
+    if (one_k1) { if ((rc = launch_recon(b, s))) return rc; launches += 1; }   // the band-major row list is a valid ticket order for one launch
     for (int c = 0; c < d->nchunks; c++) {
       DeviceBatch bc = b;
       bc.row_list = d->rows.d + d->chunk_item[c]; bc.nrows = (int)(d->chunk_item[c + 1] - d->chunk_item[c]); bc.ticket = b.ticket + c;
-      if ((rc = launch_recon(bc, s))) return rc;
-      if (overlap && c + 1 == d->nchunks) {               // (tail overlap) K0 has finished before anything that follows the last band's K1
+      if (!one_k1 && (rc = launch_recon(bc, s))) return rc;
+      if (overlap && (one_k1 ? c == 0 : c + 1 == d->nchunks)) {   // (tail overlap) K0 has finished before anything that follows the last K1
         B200_CUDA_CHECK(cudaStreamWaitEvent(s, d->ev_join, 0));
         B200_CUDA_CHECK(cudaLaunchHostFunc(s, overlap_done, nullptr));
         release.armed = false;

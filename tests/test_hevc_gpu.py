@@ -146,8 +146,31 @@ def test_batch_of_heterogeneous_pictures(dec):
             assert np.array_equal(tile, want[k][c]), f"picture {k} plane {c}: first diffs {np.argwhere(tile != want[k][c])[:4].tolist()}"
 
 
+@pytest.mark.parametrize("tail", ["1", "2"])
+def test_tail_overlap_single_pictures(cuda, tail, monkeypatch):
+    """Tail overlap (b200_hevc_decode.cu: K0 at full occupancy, the live K1 queued behind it through the start gate), forced
+    here on single pictures (B200_TAIL_FORCE; by default only batches of more than one K0 wave take it): oracle planes."""
+    monkeypatch.delenv("B200_OVERLAP", raising=False)
+    monkeypatch.setenv("B200_TAIL_OVERLAP", tail)
+    monkeypatch.setenv("B200_TAIL_FORCE", "1")
+    d = lb.Decoder(host_threads=4)
+    try:
+        for name in ["ctb32_wpp_deep", "slices_wpp", "main12_wpp", "dependent_slices", "tile_1024_like", "ctb64"]:
+            au = synth_stream(name)
+            want, _ = ob.restatement_decode(au)
+            for _ in range(2):
+                d.decode_grid([au], 1, 1)
+                assert d.stats().front_end == 2
+                got = d.planes_host()
+                for c in range(len(want)):
+                    assert np.array_equal(got[c], want[c]), f"{name} plane {c} tail={tail}"
+    finally:
+        d.close()
+
+
+@pytest.mark.parametrize("tail", ["0", "1", "2"])
 @pytest.mark.parametrize("tiles_per_chunk", [3, 6, 7])
-def test_chunked_pipeline_equals_back_to_back(cuda, tiles_per_chunk, monkeypatch):
+def test_chunked_pipeline_equals_back_to_back(cuda, tiles_per_chunk, tail, monkeypatch):
     """Large grids headed for page-locked host memory go through K1 / K3 / K4 / K6 in bands of tile rows, the D2H of a band
     overlapping the kernels of the next.  Forced here on a small 3 x 5 grid of different pictures (B200_CHUNKS=1): planes ==
     per-tile oracle, RGB (page-locked and pageable destination, asynchronous form, cropped canvas) == the one-launch pipeline."""
@@ -168,6 +191,7 @@ def test_chunked_pipeline_equals_back_to_back(cuda, tiles_per_chunk, monkeypatch
             s = 1 if c == 0 else 2
             want[c][row * th // s:(row + 1) * th // s, col * tw // s:(col + 1) * tw // s] = ref[k][c]
     monkeypatch.setenv("B200_CHUNKS", "0")
+    monkeypatch.setenv("B200_TAIL_OVERLAP", "0")
     d = lb.Decoder(host_threads=4)
     try:
         base = np.empty((H, W * 3), np.uint8)
@@ -177,6 +201,8 @@ def test_chunked_pipeline_equals_back_to_back(cuda, tiles_per_chunk, monkeypatch
         d.decode_grid_to_rgb_host(tiles, cols, rows, lb.CHROMA_INTERLEAVED_RGB, out=base_crop, canvas=(W - 50, H - 30))
         monkeypatch.setenv("B200_CHUNKS", "1")
         monkeypatch.setenv("B200_CHUNK_TILES", str(tiles_per_chunk))
+        monkeypatch.setenv("B200_TAIL_OVERLAP", tail)      # bands with the live K1 behind a full-occupancy K0 (1: per band, 2: one K1)
+        monkeypatch.setenv("B200_TAIL_FORCE", "1")
         d.decode_grid(tiles, cols=cols, rows=rows)
         assert d.stats().front_end == 3
         got = d.planes_host()
