@@ -374,7 +374,7 @@ def main():
         "pipeline": {"bands": stats_e2e.bands, "entropy_ms_in_e2e_leg": stats_e2e.entropy_ms, "band_pipeline_ms_in_e2e_leg": stats_e2e.recon_ms + stats_e2e.deblock_ms + stats_e2e.sao_ms,
                      "tail_overlap": os.environ.get("B200_TAIL_OVERLAP", "1") != "0",
                      "note": "e2e legs of large grids: the tile rows go through K1 -> K3 -> K4 -> K6 in row bands and the D2H of band c overlaps the kernels of band c + 1; K1 is queued behind the full-occupancy entropy kernel and follows it CTB by CTB in the SM slots its draining wavefronts free (tail overlap), so band_pipeline_ms is what remains after the entropy kernel has ended (kernels_ms below: one launch per kernel for the whole grid, one after the other: B200_CHUNKS=0 B200_TAIL_OVERLAP=0)"},
-        "gpu_launches": (stats_e2e.kernel_launches + ((stats_e2e.kernel_launches - 1) // 4 if chunked else 1)) * args.steps,   # K0, (K1, K3 x2, K4, K6) per band -- of the e2e leg
+        "gpu_launches": (stats_e2e.kernel_launches + (stats_e2e.bands if chunked else 1)) * args.steps,   # K0 (+ gate), (K1, K3 x2, K4 luma + chroma) per band as counted by the library, + K6 per band -- of the e2e leg
         "clocks": clk.summary(),
         "roofline": {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
                      "traffic": tr["bytes_per_launch"] if tr else None, "traffic_source": tr["source"] if tr else None,

@@ -74,6 +74,6 @@ int launch_entropy_gate(const EntropyBatch& b, int resident_warps, cudaStream_t 
 int launch_entropy_stats(const EntropyBatch& b, unsigned long long* out2, cudaStream_t s);
 int launch_recon(const DeviceBatch& b, cudaStream_t s);
 int launch_deblock(const DeviceBatch& b, const PicDesc* host_pics, cudaStream_t s);
-int launch_sao(const DeviceBatch& b, const PicDesc* host_pics, cudaStream_t s);
+int launch_sao(const DeviceBatch& b, const PicDesc* host_pics, cudaStream_t s, int* launches = nullptr);
 
 }  // namespace b200

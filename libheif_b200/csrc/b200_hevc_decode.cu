@@ -250,8 +250,9 @@ static int run_device_pipeline(b200_decoder* d, int n, cudaStream_t s, int* laun
       const int p0 = d->chunk_pic[c];
       bf.pics = d->pics.d + p0; bf.npics = d->chunk_pic[c + 1] - p0;
       if (d->debug_stage != 1 && (rc = launch_deblock(bf, d->pics.h + p0, s))) return rc;
-      if (d->debug_stage == 0 && (rc = launch_sao(bf, d->pics.h + p0, s))) return rc;
-      launches += 4;
+      int nsao = 0;
+      if (d->debug_stage == 0 && (rc = launch_sao(bf, d->pics.h + p0, s, &nsao))) return rc;
+      launches += 3 + nsao;
       if (d->chunk_hook && (rc = d->chunk_hook(c, s))) return rc;
     }
     cudaEventRecord(d->ev[2], s); cudaEventRecord(d->ev[3], s); cudaEventRecord(d->ev[4], s);   // recon_ms = the whole band pipeline (incl. the hooks' K6)
@@ -268,7 +269,7 @@ static int run_device_pipeline(b200_decoder* d, int n, cudaStream_t s, int* laun
   launches += 1;
   if (d->debug_stage != 1) { if ((rc = launch_deblock(b, d->pics.h, s))) return rc; launches += 2; }
   cudaEventRecord(d->ev[3], s);
-  if (d->debug_stage == 0) { if ((rc = launch_sao(b, d->pics.h, s))) return rc; launches += 1; }
+  if (d->debug_stage == 0) { int nsao = 0; if ((rc = launch_sao(b, d->pics.h, s, &nsao))) return rc; launches += nsao; }
   cudaEventRecord(d->ev[4], s);
   if (launches_out) *launches_out = launches;
   return B200_OK;

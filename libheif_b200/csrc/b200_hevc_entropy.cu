@@ -155,9 +155,10 @@ __global__ void entropy_stats_kernel(const EntropyBatch b, unsigned long long* o
 
 // Tail overlap (b200_hevc_decode.cu): the stream that carries K1 passes this one-thread kernel first, so that K1's CTAs are
 // handed to the SMs only after K0's whole grid is resident (every decoder warp has popped its first queue slot).  Purely
-// a scheduling aid: it gives up after ~0.3 s and correctness never depends on it.
+// a scheduling aid: it gives up after ~2 s (K0 kept off the SMs that long by other work of the process) and correctness never
+// depends on it -- should K1 then take every SM slot first, its own dependency time-out turns the stall into an error.
 __global__ void entropy_gate_kernel(const unsigned* qhead, unsigned need, const unsigned* error_flag) {
-  for (unsigned spins = 0; spins < 300000u; spins++) {
+  for (unsigned spins = 0; spins < 2000000u; spins++) {
     if (e_ld_acquire(qhead) >= need || e_ld_acquire(error_flag)) return;
     __nanosleep(1000);
   }
