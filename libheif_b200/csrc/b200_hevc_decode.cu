@@ -847,6 +847,8 @@ extern "C" int b200_debug_parse(const uint8_t* au, size_t size, int8_t* qp8, uin
 // Returns the wall-clock milliseconds of the parallel parse in *ms_out.  Used by tests and for tuning on CPU-only hosts.
 extern "C" int b200_debug_parse_many(const uint8_t* const* au, const size_t* au_size, int n, int threads, int repeat, double* ms_out) {
   if (!au || !au_size || n <= 0) return set_error(B200_E_INVALID, "bad argument");
+  const bool headers_only = threads < 0;
+  if (headers_only) threads = -threads;
   Pool pool(threads > 0 ? threads : 1);
   std::vector<ParsedPicture> parsed((size_t)n);
   std::vector<int> rcs((size_t)n, 0);
@@ -854,7 +856,9 @@ extern "C" int b200_debug_parse_many(const uint8_t* const* au, const size_t* au_
   double best = 1e30;
   for (int r = 0; r < (repeat > 0 ? repeat : 1); r++) {
     const double t0 = now_ms();
-    pool.parallel_for(n, [&](int i) { rcs[(size_t)i] = parse_access_unit(au[i], au_size[i], lim, parsed[(size_t)i]); });
+    // repeat < 0 is not used; threads < 0 selects the headers-only stage of the device front-end (NAL split, emulation prevention, headers)
+    if (headers_only) pool.parallel_for(n, [&](int i) { rcs[(size_t)i] = parse_headers(au[i], au_size[i], lim, parsed[(size_t)i].hdr); });
+    else pool.parallel_for(n, [&](int i) { rcs[(size_t)i] = parse_access_unit(au[i], au_size[i], lim, parsed[(size_t)i]); });
     best = std::min(best, now_ms() - t0);
   }
   for (int i = 0; i < n; i++) if (rcs[(size_t)i]) return rcs[(size_t)i];
