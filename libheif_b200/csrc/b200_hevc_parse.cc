@@ -600,4 +600,19 @@ int parse_access_unit(const uint8_t* data, size_t size, const ParseLimits& limit
   return B200_OK;
 }
 
+// test hook (tests/test_parser.py): the emulation-prevention removal of the header stage on a bare byte string; returns the RBSP
+// length, writes at most epb_cap removed-byte offsets and their total count
+int unescape_for_tests(const uint8_t* in, size_t n, uint8_t* out, uint32_t* epb_out, size_t epb_cap, size_t* epb_count) {
+  std::vector<uint32_t> epb;
+  const size_t o = unescape(in, n, out, &epb);
+  for (size_t i = 0; i < epb.size() && i < epb_cap; i++) epb_out[i] = epb[i];
+  if (epb_count) *epb_count = epb.size();
+  return (int)o;
+}
+
 }  // namespace b200
+
+extern "C" int b200_debug_unescape(const uint8_t* in, size_t n, uint8_t* out, uint32_t* epb_out, size_t epb_cap, size_t* epb_count) {
+  if (!in || !out) return -1;
+  return b200::unescape_for_tests(in, n, out, epb_out, epb_cap, epb_count);
+}

@@ -251,3 +251,41 @@ def test_advice_r1_reproducer_min_cb_wraps():
     buf = np.zeros(1 << 20, np.uint8); out5 = (C.c_ulonglong * 5)()
     l.b200_debug_parse.argtypes = [C.c_char_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_ulonglong)]
     assert l.b200_debug_parse(m, len(m), buf.ctypes.data, buf.ctypes.data, buf.ctypes.data, buf.ctypes.data, out5) != 0
+
+
+def test_emulation_prevention_removal_matches_the_byte_serial_rule():
+    """7.4.2: the header stage strips emulation_prevention_three_byte with memchr + block copies; the result (RBSP bytes and the
+    NAL offsets of the removed bytes, which the entry points are corrected by) must equal the byte-serial rule of the
+    specification -- "0x03 after two zero bytes since the last removal" -- on strings made of little else than 0x00 / 0x03."""
+    import ctypes as C
+    from libheif_b200 import _lib
+    l = _lib.lib()
+    l.b200_debug_unescape.argtypes = [C.c_char_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t)]
+    l.b200_debug_unescape.restype = C.c_int
+    rng = np.random.default_rng(7)
+
+    def serial(b):
+        out, epb, zeros = bytearray(), [], 0
+        for i, v in enumerate(b):
+            if zeros >= 2 and v == 3:
+                zeros = 0
+                epb.append(i)
+                continue
+            out.append(v)
+            zeros = zeros + 1 if v == 0 else 0
+        return bytes(out), epb
+
+    cases = [b"", b"\x00", b"\x00\x00\x03", b"\x00\x00\x03\x00\x00\x03", b"\x00\x00\x00\x03\x03", b"\x03\x00\x00\x03\x01", b"\x00\x00\x03\x00\x03"]
+    for k in range(400):
+        n = int(rng.integers(0, 300))
+        alphabet = [np.array([0, 3], np.uint8), np.array([0, 0, 3, 1], np.uint8), np.arange(256, dtype=np.uint8)][k % 3]
+        cases.append(bytes(alphabet[rng.integers(0, len(alphabet), n)]))
+    cases.append(bytes(rng.integers(0, 4, 200000, dtype=np.uint8)))        # long: many block copies
+    for b in cases:
+        want, want_epb = serial(b)
+        out = np.zeros(len(b) + 16, np.uint8)
+        epb = np.zeros(len(b) + 1, np.uint32)
+        cnt = C.c_size_t(0)
+        n = l.b200_debug_unescape(b, len(b), out.ctypes.data, epb.ctypes.data, len(epb), C.byref(cnt))
+        assert n == len(want) and bytes(out[:n]) == want, b[:40]
+        assert cnt.value == len(want_epb) and epb[:cnt.value].tolist() == want_epb, b[:40]
