@@ -99,7 +99,10 @@ typedef struct b200_color_options {
 int b200_color_convert_device(const b200_planes* in, const b200_geometry* geom, const b200_color_options* opt,
                               void* out, void* out_g, void* out_b, size_t out_stride, void* stream, int* pipeline);
 
-/* Host -> host convenience with H2D/D2H inside (what a libheif ColorConversionOperation would call). */
+/* Host -> host form with H2D / D2H inside (what a libheif ColorConversionOperation calls: integration/b200_color_op.cc).
+   Pageable operands move through a page-locked bounce buffer in bands (host threads fill / drain band k while the DMA
+   engine moves band k - 1); the device buffers, the bounce buffer and the stream are kept for the life of the process and
+   concurrent callers are serialised.  Page-locked operands (b200_host_alloc / b200_host_register) are copied directly. */
 int b200_color_convert_host(const b200_planes* in, const b200_geometry* geom, const b200_color_options* opt,
                             void* out, void* out_g, void* out_b, size_t out_stride, int* pipeline);
 
